@@ -1,0 +1,71 @@
+// C-ABI plumbing: error state, version/device queries and the dense-transform dispatcher.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace fitgnn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int gemm_fp32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, int64_t M, int K, int N,
+              int act, float* Y, int64_t ldy, cudaStream_t st);
+int row_softmax(float* Y, int64_t ldy, int64_t M, int N, int head, cudaStream_t st);
+int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi, const void* W_lo, int64_t ldw,
+                const float* bias, int64_t M, int K, int N, int act, int head, float* Y, int64_t ldy, cudaStream_t st);
+
+}  // namespace fitgnn
+
+using namespace fitgnn;
+
+extern "C" int fitgnn_abi_version(void) { return FITGNN_ABI_VERSION; }
+
+extern "C" int fitgnn_last_error(char* buf, size_t n) {
+  const size_t len = strlen(g_err);
+  if (buf && n > 0) {
+    const size_t c = len < n - 1 ? len : n - 1;
+    memcpy(buf, g_err, c);
+    buf[c] = 0;
+  }
+  return (int)len;
+}
+
+extern "C" int fitgnn_device_info(int* sm_count, int* cc) {
+  int dev = 0;
+  FG_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  FG_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc) *cc = p.major * 10 + p.minor;
+  return FITGNN_OK;
+}
+
+extern "C" int fitgnn_gemm_bias_act(int precision, const void* A, const void* A_lo, int64_t lda, const void* W,
+                                    const void* W_lo, int64_t ldw, const float* bias, int64_t M, int K, int N, int act,
+                                    int head, float* Y, int64_t ldy, void* stream) {
+  FG_REQUIRE(A && W && Y && M >= 0 && K > 0 && N > 0, FITGNN_EINVAL, "gemm: bad arguments (M=%lld K=%d N=%d)",
+             (long long)M, K, N);
+  FG_REQUIRE(lda >= K && ldw >= K && ldy >= N, FITGNN_EINVAL, "gemm: leading dimension smaller than the extent");
+  FG_REQUIRE(act == FITGNN_ACT_NONE || act == FITGNN_ACT_ELU, FITGNN_EINVAL, "gemm: unknown act %d", act);
+  FG_REQUIRE(head >= FITGNN_HEAD_IDENTITY && head <= FITGNN_HEAD_SOFTMAX, FITGNN_EINVAL, "gemm: unknown head %d", head);
+  if (M == 0) return FITGNN_OK;
+  cudaStream_t st = as_stream(stream);
+  if (precision == FITGNN_GEMM_FP32) {
+    FG_TRY(gemm_fp32(static_cast<const float*>(A), lda, static_cast<const float*>(W), ldw, bias, M, K, N, act, Y, ldy,
+                     st));
+    return row_softmax(Y, ldy, M, N, head, st);
+  }
+  if (precision == FITGNN_GEMM_BF16X3) {
+    FG_REQUIRE(A_lo && W_lo, FITGNN_EINVAL, "gemm: BF16X3 needs the lo planes");
+    return gemm_bf16x3(A, A_lo, lda, W, W_lo, ldw, bias, M, K, N, act, head, Y, ldy, st);
+  }
+  set_error("gemm: unknown precision %d", precision);
+  return FITGNN_EINVAL;
+}

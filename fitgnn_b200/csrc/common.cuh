@@ -1,0 +1,79 @@
+// Shared host/device helpers for libfitgnn_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/fitgnn.h"
+
+namespace fitgnn {
+
+void set_error(const char* fmt, ...);
+
+#define FG_CUDA(call)                                                                      \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) {                                                               \
+      ::fitgnn::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      return FITGNN_ECUDA;                                                                 \
+    }                                                                                      \
+  } while (0)
+#define FG_LAUNCH_CHECK() FG_CUDA(cudaGetLastError())
+#define FG_REQUIRE(cond, code, ...)        \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::fitgnn::set_error(__VA_ARGS__);    \
+      return code;                         \
+    }                                      \
+  } while (0)
+#define FG_TRY(expr)            \
+  do {                          \
+    int rc_ = (expr);           \
+    if (rc_ != FITGNN_OK) return rc_; \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+// number of bits needed to represent every value in [0, max_value]
+static inline int bits_for(uint64_t max_value) {
+  int b = 1;
+  while (b < 64 && (max_value >> b) != 0) ++b;
+  return b;
+}
+
+// bump allocator over a caller-provided workspace
+struct Bump {
+  char* base;
+  size_t off;
+  size_t cap;
+  bool ok;
+  Bump(void* p, size_t bytes) : base(static_cast<char*>(p)), off(0), cap(bytes), ok(true) {}
+  template <class T>
+  T* take(size_t n) {
+    size_t bytes = align_up(n * sizeof(T));
+    if (off + bytes > cap) {
+      ok = false;
+      return nullptr;
+    }
+    T* r = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return r;
+  }
+  size_t left() const { return cap - off; }
+  void* here() const { return base + off; }
+};
+
+static inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
+
+// --- internal primitives (primitives.cu) ------------------------------------------------
+size_t scan_ws_bytes(int64_t n);
+// out[i] = sum_{j<i} in[j] for i < n_out, with in[j] = 0 for j >= n_in (so n_out = n_in+1 yields the total)
+int scan_i32(const int32_t* in, int64_t n_in, int32_t* out, int64_t n_out, void* ws, size_t ws_bytes,
+             cudaStream_t st);
+size_t sort_ws_bytes(int64_t n);
+int sort_u64(uint64_t* keys, uint32_t* vals, int64_t n, int key_bits, void* ws, size_t ws_bytes,
+             cudaStream_t st);
+// ptr[r] = first index i with (keys[i] >> shift) >= r, for r in [0, n_rows]; keys sorted, n_keys valid
+int segment_ptr_from_sorted(const uint64_t* keys, int64_t n_keys, int shift, int64_t n_rows, int32_t* ptr,
+                            cudaStream_t st);
+
+}  // namespace fitgnn

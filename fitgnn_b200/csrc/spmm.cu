@@ -1,0 +1,272 @@
+// Segmented symmetric-normalised SpMM over the packed block-diagonal CSR:
+//   Y[i,:] = act( dinv[r] * sum_{e in row r} dinv[col_e] * X[src(col_e), :] + bias ),  r = out_rows[i]
+// Replaces gcn_norm + MessagePassing.propagate + bias (+F.elu) inside PyG GCNConv, as called at
+// /root/reference/network.py:31-32 (and :60,:90,:126,:161,:197).
+//
+// HBM-bound gather kernel.  One warp owns one output row; every lane keeps NV float4
+// accumulators (NV*128 columns per pass), so a 512-wide row is 4 fully coalesced 512-byte
+// LDG.128 requests per source row.  The column indices / dinv / gid of up to 32 edges are
+// fetched by one coalesced load and broadcast with shuffles; the gather loop is unrolled 4
+// edges deep (up to 16 independent 16-byte loads in flight per lane).  Rows of one subgraph are
+// adjacent in the pack, so the 8 warps of a CTA re-hit each other's source rows in L1/L2.
+// High-degree rows (deg >= HUB_DEG) are split across the 8 warps of a CTA and combined through
+// shared memory by a second kernel instantiation (hub path) so one warp never serialises
+// thousands of gathers.
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace fitgnn {
+
+constexpr int SPMM_WARPS = 8;
+constexpr int SPMM_THREADS = SPMM_WARPS * 32;
+
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ void fma4(float4& a, float w, const float4& x) {
+  a.x = fmaf(w, x.x, a.x);
+  a.y = fmaf(w, x.y, a.y);
+  a.z = fmaf(w, x.z, a.z);
+  a.w = fmaf(w, x.w, a.w);
+}
+
+// bf16 hi/lo split of one fp32: hi = rn_bf16(x), lo = rn_bf16(x - hi)
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+template <bool SPLIT>
+__device__ __forceinline__ void store_row4(void* Y, void* Ylo, int64_t off, float4 v) {
+  if (!SPLIT) {
+    *reinterpret_cast<float4*>(static_cast<float*>(Y) + off) = v;
+  } else {
+    __nv_bfloat16 h[4], l[4];
+    split_bf16(v.x, h[0], l[0]);
+    split_bf16(v.y, h[1], l[1]);
+    split_bf16(v.z, h[2], l[2]);
+    split_bf16(v.w, h[3], l[3]);
+    *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(Y) + off) = *reinterpret_cast<uint2*>(h);
+    *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(Ylo) + off) = *reinterpret_cast<uint2*>(l);
+  }
+}
+
+// One warp accumulates edges [beg, end) of row r for the column block starting at float4 index q0.
+template <int NV>
+__device__ __forceinline__ void gather_edges(float4 (&acc)[NV], int beg, int end, const int32_t* __restrict__ col,
+                                             const float* __restrict__ dinv, const int32_t* __restrict__ src_index,
+                                             const float* __restrict__ X, int64_t ldx, int q0, int nq, int lane) {
+  for (int e0 = beg; e0 < end; e0 += 32) {
+    const int cnt = min(32, end - e0);
+    int c = 0;
+    float w = 0.f;
+    int64_t s = 0;
+    if (lane < cnt) {
+      c = __ldg(col + e0 + lane);
+      w = __ldg(dinv + c);
+      s = src_index ? (int64_t)__ldg(src_index + c) : (int64_t)c;
+    }
+    const int64_t soff = s * ldx;
+    int j = 0;
+    for (; j + 4 <= cnt; j += 4) {
+      float wj[4];
+      const float* pj[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        wj[u] = __shfl_sync(0xffffffffu, w, j + u);
+        pj[u] = X + __shfl_sync(0xffffffffu, soff, j + u);
+      }
+      float4 x[4][NV];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int q = q0 + lane + 32 * v;
+          x[u][v] = (q < nq) ? ldg4(pj[u] + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) fma4(acc[v], wj[u], x[u][v]);
+    }
+    for (; j < cnt; ++j) {
+      const float wj = __shfl_sync(0xffffffffu, w, j);
+      const float* pj = X + __shfl_sync(0xffffffffu, soff, j);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int q = q0 + lane + 32 * v;
+        if (q < nq) fma4(acc[v], wj, ldg4(pj + 4 * q));
+      }
+    }
+  }
+}
+
+template <int NV, bool SPLIT>
+__device__ __forceinline__ void epilogue(const float4 (&acc)[NV], float dr, const float* __restrict__ bias, int act,
+                                         void* Y, void* Ylo, int64_t yoff, int q0, int nq, int lane) {
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int q = q0 + lane + 32 * v;
+    if (q < nq) {
+      float4 o = make_float4(acc[v].x * dr, acc[v].y * dr, acc[v].z * dr, acc[v].w * dr);
+      if (bias) {
+        const float4 b = ldg4(bias + 4 * q);
+        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+      }
+      if (act == FITGNN_ACT_ELU) {
+        o.x = elu1(o.x); o.y = elu1(o.y); o.z = elu1(o.z); o.w = elu1(o.w);
+      }
+      store_row4<SPLIT>(Y, Ylo, yoff + 4 * q, o);
+    }
+  }
+}
+
+// warp-per-row kernel; rows with degree >= hub_deg are skipped when hub_list != nullptr (hub pass owns them)
+template <int NV, bool SPLIT>
+__global__ void __launch_bounds__(SPMM_THREADS)
+spmm_warp_row_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                     const float* __restrict__ dinv, const float* __restrict__ X, int64_t ldx, int nq,
+                     const int32_t* __restrict__ src_index, const float* __restrict__ bias, int act,
+                     const int32_t* __restrict__ out_rows, int64_t n_out, void* Y, void* Ylo, int64_t ldy,
+                     int hub_deg) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
+  if (i >= n_out) return;
+  const int r = out_rows ? __ldg(out_rows + i) : (int)i;
+  const int beg = __ldg(rowptr + r), end = __ldg(rowptr + r + 1);
+  if (end - beg >= hub_deg) return;
+  const float dr = __ldg(dinv + r);
+  for (int q0 = 0; q0 < nq; q0 += 32 * NV) {
+    float4 acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gather_edges<NV>(acc, beg, end, col, dinv, src_index, X, ldx, q0, nq, lane);
+    epilogue<NV, SPLIT>(acc, dr, bias, act, Y, Ylo, i * ldy, q0, nq, lane);
+  }
+}
+
+// hub rows: one CTA per row, the 8 warps take interleaved 32-edge chunks, partial sums are
+// reduced through shared memory (NV*128 floats per warp) by warp 0.
+template <int NV, bool SPLIT>
+__global__ void __launch_bounds__(SPMM_THREADS)
+spmm_hub_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ dinv,
+                const float* __restrict__ X, int64_t ldx, int nq, const int32_t* __restrict__ src_index,
+                const float* __restrict__ bias, int act, const int32_t* __restrict__ out_rows,
+                const int32_t* __restrict__ hub_list, void* Y, void* Ylo, int64_t ldy) {
+  __shared__ float4 part[SPMM_WARPS][NV][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t i = __ldg(hub_list + blockIdx.x);
+  const int r = out_rows ? __ldg(out_rows + i) : (int)i;
+  const int beg = __ldg(rowptr + r), end = __ldg(rowptr + r + 1);
+  const float dr = __ldg(dinv + r);
+  for (int q0 = 0; q0 < nq; q0 += 32 * NV) {
+    float4 acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e0 = beg + 32 * w; e0 < end; e0 += 32 * SPMM_WARPS)
+      gather_edges<NV>(acc, e0, min(e0 + 32, end), col, dinv, src_index, X, ldx, q0, nq, lane);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) part[w][v][lane] = acc[v];
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        float4 s = part[0][v][lane];
+#pragma unroll
+        for (int k = 1; k < SPMM_WARPS; ++k) {
+          const float4 t = part[k][v][lane];
+          s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        }
+        acc[v] = s;
+      }
+      epilogue<NV, SPLIT>(acc, dr, bias, act, Y, Ylo, i * ldy, q0, nq, lane);
+    }
+    __syncthreads();
+  }
+}
+
+// hub detection: hub_list[atomic slot] = i for output rows with degree >= hub_deg
+__global__ void spmm_find_hubs_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ out_rows,
+                                      int64_t n_out, int hub_deg, int32_t* hub_list, int32_t* hub_count,
+                                      int hub_cap) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  const int r = out_rows ? out_rows[i] : (int)i;
+  if (rowptr[r + 1] - rowptr[r] >= hub_deg) {
+    const int slot = atomicAdd(hub_count, 1);
+    if (slot < hub_cap) hub_list[slot] = (int32_t)i;
+  }
+}
+
+template <int NV, bool SPLIT>
+static int launch_spmm(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X, int64_t ldx,
+                       int nq, const int32_t* src_index, const float* bias, int act, const int32_t* out_rows,
+                       int64_t n_out, void* Y, void* Ylo, int64_t ldy, const int32_t* hub_list, int n_hub,
+                       int hub_deg, cudaStream_t st) {
+  const int64_t blocks = ceil_div(n_out, SPMM_WARPS);
+  spmm_warp_row_kernel<NV, SPLIT><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(
+      rowptr, col, dinv, X, ldx, nq, src_index, bias, act, out_rows, n_out, Y, Ylo, ldy, hub_deg);
+  FG_LAUNCH_CHECK();
+  if (n_hub > 0) {
+    spmm_hub_kernel<NV, SPLIT><<<(unsigned)n_hub, SPMM_THREADS, 0, st>>>(rowptr, col, dinv, X, ldx, nq, src_index,
+                                                                          bias, act, out_rows, hub_list, Y, Ylo, ldy);
+    FG_LAUNCH_CHECK();
+  }
+  return FITGNN_OK;
+}
+
+}  // namespace fitgnn
+
+using namespace fitgnn;
+
+extern "C" int fitgnn_spmm_hubs(const int32_t* rowptr, const int32_t* out_rows, int64_t n_out, int hub_deg,
+                                int32_t* hub_list, int32_t* hub_count, int hub_cap, void* stream) {
+  FG_REQUIRE(rowptr && hub_list && hub_count && n_out >= 0 && hub_deg > 0, FITGNN_EINVAL, "spmm_hubs: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  FG_CUDA(cudaMemsetAsync(hub_count, 0, sizeof(int32_t), st));
+  if (n_out == 0) return FITGNN_OK;
+  spmm_find_hubs_kernel<<<(unsigned)ceil_div(n_out, 256), 256, 0, st>>>(rowptr, out_rows, n_out, hub_deg, hub_list,
+                                                                        hub_count, hub_cap);
+  FG_LAUNCH_CHECK();
+  return FITGNN_OK;
+}
+
+// The public entry point without a hub list: every row takes the warp-per-row path.
+extern "C" int fitgnn_spmm_symnorm_hub(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X,
+                                       int64_t ldx, int width, const int32_t* src_index, const float* bias, int act,
+                                       const int32_t* out_rows, int64_t n_out, void* Y, void* Y_lo, int64_t ldy,
+                                       const int32_t* hub_list, int n_hub, int hub_deg, void* stream) {
+  FG_REQUIRE(rowptr && col && dinv && X && Y, FITGNN_EINVAL, "spmm: null pointer");
+  FG_REQUIRE(n_out >= 0 && width > 0, FITGNN_EINVAL, "spmm: n_out=%lld width=%d", (long long)n_out, width);
+  FG_REQUIRE(width % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, FITGNN_EUNSUP,
+             "spmm: width (%d), ldx (%lld), ldy (%lld) must be multiples of 4", width, (long long)ldx, (long long)ldy);
+  FG_REQUIRE(((uintptr_t)X % 16) == 0 && ((uintptr_t)Y % 8) == 0 && (!bias || ((uintptr_t)bias % 16) == 0),
+             FITGNN_EUNSUP, "spmm: X/bias must be 16-byte aligned");
+  FG_REQUIRE(act == FITGNN_ACT_NONE || act == FITGNN_ACT_ELU, FITGNN_EINVAL, "spmm: unknown act %d", act);
+  FG_REQUIRE(n_hub == 0 || hub_list, FITGNN_EINVAL, "spmm: n_hub without hub_list");
+  if (n_out == 0) return FITGNN_OK;
+  FG_REQUIRE(ceil_div(n_out, SPMM_WARPS) < (1ll << 31), FITGNN_ERANGE, "spmm: too many rows");
+  cudaStream_t st = as_stream(stream);
+  const int nq = width / 4;
+  const bool split = Y_lo != nullptr;
+  if (n_hub == 0) hub_deg = 0x7fffffff;
+#define FG_SPMM(NV)                                                                                              \
+  return split ? launch_spmm<NV, true>(rowptr, col, dinv, X, ldx, nq, src_index, bias, act, out_rows, n_out, Y,   \
+                                       Y_lo, ldy, hub_list, n_hub, hub_deg, st)                                   \
+               : launch_spmm<NV, false>(rowptr, col, dinv, X, ldx, nq, src_index, bias, act, out_rows, n_out, Y,  \
+                                        Y_lo, ldy, hub_list, n_hub, hub_deg, st)
+  if (nq <= 32) { FG_SPMM(1); }
+  if (nq <= 64) { FG_SPMM(2); }
+  if (nq <= 96) { FG_SPMM(3); }
+  FG_SPMM(4);  // nq > 128 loops over 512-column blocks
+#undef FG_SPMM
+}
+
+extern "C" int fitgnn_spmm_symnorm(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X,
+                                   int64_t ldx, int width, const int32_t* src_index, const float* bias, int act,
+                                   const int32_t* out_rows, int64_t n_out, void* Y, void* Y_lo, int64_t ldy,
+                                   void* stream) {
+  return fitgnn_spmm_symnorm_hub(rowptr, col, dinv, X, ldx, width, src_index, bias, act, out_rows, n_out, Y, Y_lo,
+                                 ldy, nullptr, 0, 0, stream);
+}

@@ -1,0 +1,211 @@
+/*
+ * fitgnn.h — C ABI of libfitgnn_b200.so (sm_100a).
+ *
+ * The reference (Roy-Shubhajit/FIT-GNN) is pure Python and has no FFI; the seam this
+ * library sits behind is the PyG operator/model surface the reference calls
+ * (SURVEY.md §8b).  Every entry point names the reference call site it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative FITGNN_E* code otherwise and never
+ *     throws/aborts across the ABI; fitgnn_last_error() returns the message of the last
+ *     failure on the calling thread;
+ *   - all data pointers are DEVICE pointers unless a parameter is named host_*;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - the library never allocates caller-visible memory: outputs and workspaces are
+ *     caller-owned; data-dependent output sizes come from a *_plan call that leaves its
+ *     intermediates in the workspace for the matching *_fill call;
+ *   - a filled pack is immutable; calls are re-entrant for distinct (pack, ws, stream);
+ *   - dense matrices are row-major fp32 with an explicit leading dimension in elements.
+ */
+#ifndef FITGNN_H_
+#define FITGNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FITGNN_ABI_VERSION 1
+
+enum {
+  FITGNN_OK = 0,
+  FITGNN_EINVAL = -1,   /* bad argument (null pointer, negative size, unknown mode) */
+  FITGNN_ECUDA = -2,    /* a CUDA runtime / driver call failed                        */
+  FITGNN_ERANGE = -3,   /* sizes exceed what the int32 / packed-key layout can hold    */
+  FITGNN_EWS = -4,      /* workspace too small                                         */
+  FITGNN_EUNSUP = -5    /* shape not supported by the requested kernel                 */
+};
+
+/* activation fused into SpMM / GEMM epilogues (network.py:32 uses ELU, alpha = 1) */
+enum { FITGNN_ACT_NONE = 0, FITGNN_ACT_ELU = 1 };
+
+/* head applied after lt1 (network.py:35 log_softmax; :64 identity; :95,:135 softmax) */
+enum { FITGNN_HEAD_IDENTITY = 0, FITGNN_HEAD_LOG_SOFTMAX = 1, FITGNN_HEAD_SOFTMAX = 2 };
+
+/* subgraph augmentation (utils.py:190 cluster_node, :235 extra_node, else none) */
+enum { FITGNN_MODE_NONE = 0, FITGNN_MODE_EXTRA = 1, FITGNN_MODE_CLUSTER = 2 };
+
+/* segment pooling (network.py:93,131 global_max_pool; :164,202 global_mean_pool) */
+enum { FITGNN_POOL_MAX = 0, FITGNN_POOL_MEAN = 1 };
+
+/* GEMM arithmetic.  FP32 = exact fp32 FMA on CUDA cores; BF16X3 = tcgen05 tensor cores on
+ * a hi/lo bf16 split of both operands (3 MMAs, ~2^-17 relative operand error). */
+enum { FITGNN_GEMM_FP32 = 0, FITGNN_GEMM_BF16X3 = 1 };
+
+/*
+ * Packed block-diagonal CSR of all subgraphs Gs (replaces the list[Data] built by
+ * coarsening_classification utils.py:186-267 and re-collated by G_DataLoader run.py:336).
+ * Row r of the pack is one subgraph-local node; rows of one subgraph are contiguous and in
+ * the reference's node order (M.orig_idx ascending, then cluster nodes in first-seen order).
+ * CSR row = message target, col = message source, self loop included, duplicates kept
+ * (PyG gcn_norm semantics).  Edge weight = dinv[row] * dinv[col].
+ */
+typedef struct fitgnn_pack {
+  int64_t n_rows;           /* N' */
+  int64_t nnz;              /* E' + N' */
+  int64_t n_sub;            /* k */
+  int64_t n_core;           /* number of core rows (= N for a node task) */
+  int64_t n_src;            /* rows of the de-duplicated feature table gid points into */
+  const int32_t* rowptr;    /* [n_rows+1] */
+  const int32_t* col;       /* [nnz] pack-local source row, ascending inside a row */
+  const float* dinv;        /* [n_rows] deg^-1/2, deg = row length (self loop counted) */
+  const int32_t* gid;       /* [n_rows] global node id, or N + cluster id for a cluster node */
+  const int32_t* sub_ptr;   /* [n_sub+1] first row of each subgraph */
+  const int32_t* core_rows; /* [n_core] pack rows of core nodes, ascending */
+  const uint8_t* is_core;   /* [n_rows] 1 = node belongs to the subgraph's own cluster */
+  const uint8_t* mask;      /* [n_rows] M.mask exactly as the reference stores it (utils.py:260-265) */
+} fitgnn_pack;
+
+/* result of fitgnn_pack_plan: the data-dependent sizes the caller allocates the pack from, the size
+ * of the second workspace fitgnn_pack_fill needs, and private state carried from plan to fill */
+typedef struct fitgnn_plan {
+  int64_t n_rows, nnz, n_sub, n_core, n_src;
+  int64_t fill_ws_bytes;
+  int64_t priv[27];
+} fitgnn_plan;
+
+int fitgnn_abi_version(void);
+/* copies the calling thread's last error message (NUL terminated) into buf; returns its length */
+int fitgnn_last_error(char* buf, size_t n);
+/* SM count and compute capability (major*10+minor) of the current device */
+int fitgnn_device_info(int* sm_count, int* cc);
+
+/* ------------------------------------------------------------------------------------------
+ * Generic per-call CSR (drop-in GCNConv path).  Replaces gcn_norm inside GCNConv.__call__
+ * (call sites network.py:31,60,90,126,161,197): existing self loops are dropped, one loop per
+ * node is added, deg = in-degree incl. the loop, duplicate edges count twice.
+ * edge_index is the reference's [2,E] int64 COO (row 0 = source, row 1 = target).
+ * nnz = (E - #self loops) + n is returned by the plan call in *host_nnz.
+ * ---------------------------------------------------------------------------------------- */
+size_t fitgnn_csr_workspace_bytes(int64_t E, int64_t n);
+int fitgnn_csr_plan(const int64_t* edge_index, int64_t E, int64_t n, void* ws, size_t ws_bytes,
+                    int64_t* host_nnz, void* stream);
+int fitgnn_csr_fill(int64_t n, void* ws, size_t ws_bytes, int32_t* rowptr /*[n+1]*/,
+                    int32_t* col /*[nnz]*/, float* dinv /*[n]*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Pack builder.  Replaces coarsening_classification / coarsening_regression's per-cluster
+ * loop (utils.py:186-267, :269-350, :417-501, :503-584) plus neighbour()/nodes_2_neighbours()
+ * (utils.py:52-62) and Data.subgraph (utils.py:248).
+ * part[v] = index of v's subgraph in the reference's subgraph_list order.
+ * FITGNN_MODE_CLUSTER additionally needs the coarsened adjacency pattern Ac as CSR over the
+ * same cluster ids (from fitgnn_project_adj_*), i.e. `adj = Gc.A` at utils.py:160,228.
+ * ---------------------------------------------------------------------------------------- */
+size_t fitgnn_pack_workspace_bytes(int64_t E, int64_t N, int64_t k, int mode, int64_t ac_nnz);
+int fitgnn_pack_plan(const int64_t* edge_index, int64_t E, int64_t N, const int32_t* part, int64_t k,
+                     int mode, const int32_t* ac_rowptr, const int32_t* ac_col, int64_t ac_nnz,
+                     void* ws, size_t ws_bytes, fitgnn_plan* host_plan, void* stream);
+/* `out` holds caller-allocated device arrays sized from host_plan (the const is cast away); ws is the
+ * workspace the plan call used, ws2 a second one of host_plan->fill_ws_bytes (may be null when 0).
+ * edge_index / part / ac_* passed to the plan call must still be alive. */
+int fitgnn_pack_fill(const fitgnn_plan* host_plan, const fitgnn_pack* out, void* ws, size_t ws_bytes,
+                     void* ws2, size_t ws2_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Segmented symmetric-normalised SpMM.  Replaces MessagePassing.propagate + bias (+ F.elu)
+ * inside GCNConv (network.py:31-32):
+ *   Y[i,:] = act( sum_{e in row r_i} dinv[r_i]*dinv[col_e] * X[src(col_e), :] + bias )
+ * r_i = out_rows[i] (or i when out_rows is null, n_out = n_rows); src(c) = src_index[c] (gid
+ * de-duplication) or c when src_index is null.  width % 4 == 0, ldx % 4 == 0, ldy % 4 == 0,
+ * 16-byte aligned bases.  If y_lo is non-null Y is written as a bf16 hi/lo split instead of fp32:
+ * y = bf16 hi plane, y_lo = bf16 lo plane (both [n_out, ldy] bf16) feeding FITGNN_GEMM_BF16X3.
+ * ---------------------------------------------------------------------------------------- */
+int fitgnn_spmm_symnorm(const int32_t* rowptr, const int32_t* col, const float* dinv,
+                        const float* X, int64_t ldx, int width, const int32_t* src_index,
+                        const float* bias, int act, const int32_t* out_rows, int64_t n_out,
+                        void* Y, void* Y_lo, int64_t ldy, void* stream);
+/* Same with the high-degree rows split across a CTA: hub_list (from fitgnn_spmm_hubs) holds the output
+ * indices i whose row has >= hub_deg entries; the warp-per-row pass skips them. */
+int fitgnn_spmm_hubs(const int32_t* rowptr, const int32_t* out_rows, int64_t n_out, int hub_deg,
+                     int32_t* hub_list /*[hub_cap]*/, int32_t* hub_count /*[1] device*/, int hub_cap,
+                     void* stream);
+int fitgnn_spmm_symnorm_hub(const int32_t* rowptr, const int32_t* col, const float* dinv,
+                            const float* X, int64_t ldx, int width, const int32_t* src_index,
+                            const float* bias, int act, const int32_t* out_rows, int64_t n_out,
+                            void* Y, void* Y_lo, int64_t ldy, const int32_t* hub_list, int n_hub,
+                            int hub_deg, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense transform.  Replaces GCNConv.lin / lt1 (F.linear, network.py:31,34):
+ *   Y[M,N] = act( A[M,K] · W[N,K]^T + bias[N] ),  W laid out as lin.weight ([out,in] row-major).
+ * FITGNN_GEMM_FP32: A, W fp32.   FITGNN_GEMM_BF16X3: A_hi/A_lo and W_hi/W_lo are bf16 planes
+ * (see fitgnn_split_bf16); K-extent padded to a multiple of 8 with zeros by the caller.
+ * head != IDENTITY applies a row-wise (log-)softmax over the N outputs (N <= 256), after act.
+ * ---------------------------------------------------------------------------------------- */
+int fitgnn_gemm_bias_act(int precision, const void* A, const void* A_lo, int64_t lda,
+                         const void* W, const void* W_lo, int64_t ldw, const float* bias,
+                         int64_t M, int K, int N, int act, int head, float* Y, int64_t ldy,
+                         void* stream);
+/* fp32 [rows, cols] (ld = ldx) -> bf16 hi/lo planes [rows, ldo] (columns >= cols zero filled) */
+int fitgnn_split_bf16(const float* X, int64_t ldx, int64_t rows, int cols, void* hi, void* lo,
+                      int64_t ldo, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Graph-level pooling.  Replaces x[mask] + torch.cat + global_max_pool / global_mean_pool
+ * (network.py:129-131, :200-202).  rows[i] selects the i-th pooled row of X (the masked rows in
+ * pack order); seg_ptr[g]..seg_ptr[g+1] delimits graph g's pooled rows (batch_tensor is sorted).
+ * An empty segment yields 0 (PyG scatter semantics).
+ * ---------------------------------------------------------------------------------------- */
+int fitgnn_segment_pool(const float* X, int64_t ldx, int width, const int32_t* rows,
+                        const int32_t* seg_ptr, int64_t n_seg, int pool, float* Y, int64_t ldy,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Coarsened-graph projection.
+ * fitgnn_project_features replaces C.dot(H_feature) (utils.py:161,738,827):
+ *   Xc[c,:] = fp32( sum_{j: part[j]==c, ascending j} (double)cweight[j] * X[j,:] ), fp64 accumulate.
+ *   members = node ids sorted by (part, id), member_ptr[k+1] (from fitgnn_group_by_part).
+ * fitgnn_project_adj_* replaces zero_diag(coarsen_matrix(W, iC)) (coarsening_utils.py:138,201-205,
+ * graph_utils.py:79-87) and Gc.W.tocoo() (utils.py:745-746): the pattern of P_bin·A·P_bin^T with the
+ * diagonal removed, row-major sorted COO, cnt = number of directed edges between the two clusters.
+ * ---------------------------------------------------------------------------------------- */
+size_t fitgnn_group_workspace_bytes(int64_t N, int64_t k);
+int fitgnn_group_by_part(const int32_t* part, int64_t N, int64_t k, int32_t* members /*[N]*/,
+                         int32_t* member_ptr /*[k+1]*/, void* ws, size_t ws_bytes, void* stream);
+int fitgnn_project_features(const int32_t* members, const int32_t* member_ptr, int64_t k,
+                            const double* cweight /*[N] by node id*/, const float* X, int64_t ldx,
+                            int F, float* Xc, int64_t ldxc, void* stream);
+size_t fitgnn_project_adj_workspace_bytes(int64_t E);
+int fitgnn_project_adj_plan(const int64_t* edge_index, int64_t E, int64_t N, const int32_t* part,
+                            int64_t k, void* ws, size_t ws_bytes, int64_t* host_nnz, void* stream);
+int fitgnn_project_adj_fill(void* ws, size_t ws_bytes, int64_t k, int64_t* out_row, int64_t* out_col,
+                            int32_t* out_cnt, int32_t* out_rowptr /*[k+1] or null*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Device primitives used by the builders, exported for tests.
+ * ---------------------------------------------------------------------------------------- */
+size_t fitgnn_sort_workspace_bytes(int64_t n);
+/* ascending LSD radix sort of the low `key_bits` bits; vals may be null; sorts in place */
+int fitgnn_sort_u64(uint64_t* keys, uint32_t* vals, int64_t n, int key_bits, void* ws,
+                    size_t ws_bytes, void* stream);
+/* exclusive prefix sum, out may alias in; out[n] (one past) receives the total when with_total */
+int fitgnn_scan_i32(const int32_t* in, int32_t* out, int64_t n, int with_total, void* ws,
+                    size_t ws_bytes, void* stream);
+size_t fitgnn_scan_workspace_bytes(int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FITGNN_H_ */
