@@ -1,0 +1,127 @@
+"""Host glue between the reference's coarsening outputs and the device builders.
+
+The coarsening ALGORITHM (graph_coarsening.coarsen: eigsh + greedy contraction, sequential CPU code) is out
+of scope; it produces, once, the coarsening matrices C.  Everything derived from them on
+the hot path runs on the device:
+  * partition vector + C weights  <- C.indices / C.data  (subgraph_mapping utils.py:113-121)
+  * Xc = C·X                      <- utils.py:161, :738, :827
+  * Ac pattern                    <- coarsening_utils.py:138 / utils.py:745-746
+  * Gc assembly                   <- utils.py:705-778 (node tasks), :811-852 (graph tasks)
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+@dataclass
+class Partition:
+    """Global partition in the reference's subgraph_list order."""
+    part: np.ndarray      # int32 [N]: subgraph index of every node
+    cweight: np.ndarray   # float64 [N]: C[part[v], v] (1.0 for un-coarsened single-node components)
+    k: int
+    comp_of_sub: np.ndarray   # int32 [k]: component (candidate index) each subgraph came from
+    sub_offset: np.ndarray    # int64 [n_comp+1]: first subgraph of every component
+
+
+def partition_from_components(comps, C_list, n_nodes) -> Partition:
+    """comps: list of sorted node-id arrays in candidate order (size-descending, utils.py:146);
+    C_list[i]: scipy CSC coarsening matrix of component i (exactly one non-zero per column), or None for a
+    single-node component (utils.py:352-368).  Subgraphs are numbered component by component, supernodes
+    ascending — the order coarsening_classification appends them to subgraph_list (utils.py:186, :267)."""
+    part = np.full(n_nodes, -1, dtype=np.int64)
+    cw = np.ones(n_nodes, dtype=np.float64)
+    comp_of_sub, offs, base = [], [0], 0
+    for i, (comp, C) in enumerate(zip(comps, C_list)):
+        comp = np.asarray(comp, dtype=np.int64)
+        if C is None:
+            assert len(comp) == 1
+            part[comp] = base
+            kc = 1
+        else:
+            C = C.tocsc()
+            if not np.all(np.diff(C.indptr) == 1):
+                raise ValueError("coarsening matrix must have exactly one non-zero per column")
+            part[comp] = base + C.indices
+            cw[comp] = C.data
+            kc = C.shape[0]
+        comp_of_sub.extend([i] * kc)
+        base += kc
+        offs.append(base)
+    if (part < 0).any():
+        raise ValueError("components do not cover every node")
+    return Partition(part.astype(np.int32), cw, base, np.asarray(comp_of_sub, dtype=np.int32),
+                     np.asarray(offs, dtype=np.int64))
+
+
+def project(edge_index: torch.Tensor, X: torch.Tensor, partition: Partition):
+    """Device projection of one graph: returns dict(Xc [k,F] fp32, ac_row, ac_col (int64, row-major sorted),
+    ac_cnt int32, ac_rowptr int32, members, member_ptr)."""
+    dev = edge_index.device
+    part = torch.as_tensor(partition.part, device=dev)
+    cw = torch.as_tensor(partition.cweight, device=dev)
+    members, member_ptr = ops.group_by_part(part, partition.k)
+    Xc = ops.project_features(members, member_ptr, cw, X.contiguous())
+    row, col, cnt, rowptr = ops.project_adj(edge_index, part, partition.k)
+    return dict(Xc=Xc, ac_row=row, ac_col=col, ac_cnt=cnt, ac_rowptr=rowptr, members=members, member_ptr=member_ptr,
+                part=part)
+
+
+def assemble_gc_classification(proj, partition: Partition, comps, edge_index, X, y, train_mask, val_mask, n_classes):
+    """load_data_classification utils.py:705-778 on top of the device projection: components with > 10 nodes
+    holding a train/val node contribute their coarsened block (Xc rows, Ac pattern, projected labels and the
+    "pure class" masks, utils.py:726-742); smaller ones are appended un-coarsened (utils.py:754-769); the
+    rest are skipped.  Returns (coarsen_features, train_labels, train_mask, val_labels, val_mask,
+    coarsen_edge) as device tensors, in the reference's row order."""
+    dev = X.device
+    part = proj["part"].long()
+    k = partition.k
+    y = y.to(dev).long().view(-1)
+    trm, vam = train_mask.to(dev).bool(), val_mask.to(dev).bool()
+    cw = torch.as_tensor(partition.cweight, device=dev)
+
+    def proj_labels(mask):
+        # C.dot(onehot(y) * mask): [k, n_classes] float64 accumulate (utils.py:714-727)
+        idx = torch.nonzero(mask).view(-1)
+        M = torch.zeros(k, n_classes, dtype=torch.float64, device=dev)
+        M.index_put_((part[idx], y[idx]), cw[idx], accumulate=True)
+        any_mass = M.sum(1).bool()                     # torch.BoolTensor(np.sum(C.dot(labels), axis=1))
+        mixed = (M > 0).sum(1) > 1
+        return torch.argmax(M.float(), dim=1), any_mass & ~mixed
+
+    ctl, ctm = proj_labels(trm)
+    cvl, cvm = proj_labels(vam)
+    feats, tl, tm, vl, vm, rows, cols = [], [], [], [], [], [], []
+    node_off = 0
+    started = False
+    ac_row, ac_col, ac_rowptr = proj["ac_row"], proj["ac_col"], proj["ac_rowptr"].long()
+    ei = edge_index
+    for i, comp in enumerate(comps):
+        comp_t = torch.as_tensor(np.asarray(comp), device=dev, dtype=torch.long)
+        has = bool((trm[comp_t].sum() + vam[comp_t].sum()) > 0)
+        if len(comp) > 10 and has:
+            s0, s1 = int(partition.sub_offset[i]), int(partition.sub_offset[i + 1])
+            feats.append(proj["Xc"][s0:s1])
+            tl.append(ctl[s0:s1]); tm.append(ctm[s0:s1]); vl.append(cvl[s0:s1]); vm.append(cvm[s0:s1])
+            e0, e1 = int(ac_rowptr[s0]), int(ac_rowptr[s1])
+            rows.append(ac_row[e0:e1] - s0 + node_off); cols.append(ac_col[e0:e1] - s0 + node_off)
+            node_off += s1 - s0
+            started = True
+        elif has:
+            if not started:
+                raise Exception("The graph does not need coarsening.")  # utils.py:763
+            feats.append(X[comp_t]); tl.append(y[comp_t]); tm.append(trm[comp_t]); vl.append(y[comp_t]); vm.append(vam[comp_t])
+            # H.W.tocoo(): the component's own adjacency, row-major sorted, duplicates merged
+            relabel = torch.full((X.shape[0],), -1, dtype=torch.long, device=dev)
+            relabel[comp_t] = torch.arange(len(comp), device=dev)
+            a, b = relabel[ei[0]], relabel[ei[1]]
+            keep = (a >= 0) & (b >= 0)
+            keys = torch.unique(a[keep] * len(comp) + b[keep])
+            rows.append(keys // len(comp) + node_off); cols.append(keys % len(comp) + node_off)
+            node_off += len(comp)
+    return (torch.cat(feats), torch.cat(tl), torch.cat(tm), torch.cat(vl), torch.cat(vm),
+            torch.stack([torch.cat(rows), torch.cat(cols)]))

@@ -1,0 +1,190 @@
+"""Whole-pack GCN forward: the schedule that runs every subgraph of a pack through the conv stack + head in
+a handful of kernel launches (replaces the per-batch Python loops run.py:59-77 / inference.py:672-688 and
+the per-subgraph loops network.py:118-135, :189-204).
+
+Schedule (SURVEY §7 ideas 2-4; all preserve the reference's arithmetic up to fp32 re-association):
+  * layer 0, F > hidden  : transform-first on the DE-DUPLICATED feature rows (X holds each node once;
+                           the SpMM gathers Z[gid[col]]), because (X W^T)[row] depends on the global row only
+  * layer 0, F <= hidden : aggregate-first (gather F-wide rows), then GEMM with fused bias + ELU
+  * layers >= 1          : aggregate-first; the LAST layer aggregates only the rows the caller reads
+                           (core rows for node tasks, M.mask rows for graph tasks)
+  * head                 : lt1 (+ log_softmax / softmax) on those rows only
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .pack import Pack
+
+_HEADS = {"identity": ops.HEAD_IDENTITY, "log_softmax": ops.HEAD_LOG_SOFTMAX, "softmax": ops.HEAD_SOFTMAX}
+
+
+def conv_layers(sd):
+    return len({k.split(".")[1] for k in sd if k.startswith("conv.")})
+
+
+class PackedForward:
+    """Prepared forward over one pack.  `state_dict` uses the reference's keys (conv.{i}.lin.weight,
+    conv.{i}.bias, lt1.weight, lt1.bias — network.py:11-22).  `rows` selects the output rows:
+    'core' (node tasks), 'mask' (graph tasks: x[mask], network.py:129) or 'all'."""
+
+    def __init__(self, pack: Pack, state_dict, head="log_softmax", rows="core", precision="fp32",
+                 with_head=True):
+        self.pack = pack
+        dev = pack.device
+        self.precision = ops.GEMM_BF16X3 if precision == "bf16x3" else ops.GEMM_FP32
+        self.kalign = 8 if self.precision == ops.GEMM_BF16X3 else 4
+        self.L = conv_layers(state_dict)
+        assert self.L >= 1
+        self.head = _HEADS[head]
+        self.with_head = with_head
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.W, self.b = [], []
+        for i in range(self.L):
+            w = state_dict[f"conv.{i}.lin.weight"].detach().to(**f32)
+            self.W.append(self._prep_weight(w))
+            self.b.append(state_dict[f"conv.{i}.bias"].detach().to(**f32).contiguous())
+        self.F = state_dict["conv.0.lin.weight"].shape[1]
+        self.H = state_dict["conv.0.lin.weight"].shape[0]
+        assert self.H % 4 == 0, "hidden width must be a multiple of 4"
+        if with_head:
+            self.Wl = self._prep_weight(state_dict["lt1.weight"].detach().to(**f32))
+            self.bl = state_dict["lt1.bias"].detach().to(**f32).contiguous()
+            self.C = state_dict["lt1.weight"].shape[0]
+        if rows == "core":
+            self.out_rows = pack.core_rows
+        elif rows == "mask":
+            self.out_rows = pack.mask_rows()
+        elif rows == "all":
+            self.out_rows = None
+        else:
+            self.out_rows = rows.to(device=dev, dtype=torch.int32).contiguous()
+        self.n_out = pack.n_rows if self.out_rows is None else self.out_rows.numel()
+        self.Fp = self._kpad(self.F)
+        self.transform_first = self.F > self.H
+        # high-degree rows are split across a CTA (found once; the pack is immutable)
+        self.hubs_all = ops.find_hubs(pack.rowptr, None, pack.n_rows)
+        self.hubs_out = self.hubs_all if self.out_rows is None else ops.find_hubs(pack.rowptr, self.out_rows, self.n_out)
+        self.launches = 0
+        self.prof = None  # set to {} by enable_profile(): op name -> dict(events, bytes, flops)
+        self._nnz_cache = {}
+
+    # -- per-kernel timing for the roofline report (CUDA events on the launching stream) ---------
+    def enable_profile(self, on=True):
+        self.prof = {} if on else None
+
+    def _timed(self, name, fn, nbytes=0, flops=0):
+        if self.prof is None:
+            return fn()
+        st = torch.cuda.current_stream()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        out = fn()
+        b.record(st)
+        rec = self.prof.setdefault(name, dict(events=[], bytes=nbytes, flops=flops))
+        rec["events"].append((a, b))
+        return out
+
+    def profile_summary(self):
+        """{op: dict(ms=mean launch duration, launches, bytes, flops)} — call after a synchronize."""
+        out = {}
+        for name, rec in (self.prof or {}).items():
+            ms = [a.elapsed_time(b) for a, b in rec["events"]]
+            out[name] = dict(ms=sum(ms) / len(ms), launches=len(ms), bytes=rec["bytes"], flops=rec["flops"])
+        return out
+
+    def _spmm_bytes(self, width, src_index, last, n_src_rows, out_elem=4):
+        """Algorithmic bytes of one SpMM launch: CSR rowptr + col, dinv of the sources, the
+        optional gid read, every distinct source row once, every output row once, bias."""
+        p = self.pack
+        key = ("nnz", last)
+        if key not in self._nnz_cache:
+            if last and self.out_rows is not None:
+                r = self.out_rows.long()
+                rp = p.rowptr.long()
+                nnz = int((rp[r + 1] - rp[r]).sum())
+            else:
+                nnz = p.nnz
+            self._nnz_cache[key] = nnz
+        nnz = self._nnz_cache[key]
+        r_out = self.n_out if last else p.n_rows
+        b = 4 * (r_out + 1) + 4 * nnz + 4 * n_src_rows * width + out_elem * r_out * width + 4 * width + 4 * n_src_rows
+        if src_index is not None:
+            b += 4 * p.n_rows
+        if last and self.out_rows is not None:
+            b += 4 * r_out
+        return b
+
+    # -- helpers -------------------------------------------------------------------------------
+    def _kpad(self, k):
+        return (k + self.kalign - 1) // self.kalign * self.kalign
+
+    def _prep_weight(self, w):
+        """[out, in] fp32 -> K padded with zero columns; bf16 hi/lo planes for the tensor-core path."""
+        kp = self._kpad(w.shape[1])
+        if self.precision == ops.GEMM_BF16X3:
+            return ops.split_bf16(w.contiguous(), ldo=kp)
+        if kp != w.shape[1]:
+            w = torch.nn.functional.pad(w, (0, kp - w.shape[1]))
+        return w.contiguous()
+
+    def _gemm(self, A, W, bias, act, head=ops.HEAD_IDENTITY, N=None, K=None, name="gemm"):
+        self.launches += 1 + (1 if (head != ops.HEAD_IDENTITY and self.precision == ops.GEMM_FP32) else 0)
+        M = (A[0] if isinstance(A, tuple) else A).shape[0]
+        return self._timed(name, lambda: ops.gemm_bias_act(A, W, bias, act, head, precision=self.precision, N=N, K=K),
+                           nbytes=4 * (M * K + K * N + M * N), flops=2 * M * K * N)
+
+    def _spmm(self, X, width, src_index, bias, act, last, split, name="spmm"):
+        p = self.pack
+        rows = self.out_rows if last else None
+        hubs = self.hubs_out if last else self.hubs_all
+        self.launches += 1 + (1 if hubs[1] > 0 else 0)
+        n_src_rows = X.shape[0] if src_index is not None else p.n_rows
+        return self._timed(name, lambda: ops.spmm_symnorm(p.rowptr, p.col, p.dinv, X, width, src_index, bias, act, rows,
+                                                          split=split, hubs=hubs),
+                           nbytes=self._spmm_bytes(width, src_index, last, n_src_rows))
+
+    def pad_features(self, X):
+        """Rows of the de-duplicated feature table, K-padded (a view when no padding is needed)."""
+        if X.shape[1] == self.Fp and X.is_contiguous():
+            return X
+        Xp = torch.zeros(X.shape[0], self.Fp, dtype=torch.float32, device=X.device)
+        Xp[:, : X.shape[1]].copy_(X)
+        return Xp
+
+    # -- forward -------------------------------------------------------------------------------
+    @torch.no_grad()
+    def __call__(self, X):
+        """X: [n_src, F] fp32 CUDA — every node once (+ one row per cluster for cluster mode, i.e. C·X).
+        Returns [n_out, C] (or the last hidden [n_out, H] when with_head=False), rows in pack order."""
+        p = self.pack
+        assert X.is_cuda and X.dtype == torch.float32 and X.shape[0] == p.n_src and X.shape[1] in (self.F, self.Fp)
+        bf = self.precision == ops.GEMM_BF16X3
+        X = self.pad_features(X)
+        h = None
+        for i in range(self.L):
+            last = i == self.L - 1
+            if i == 0 and self.transform_first:
+                A = ops.split_bf16(X) if bf else X
+                if bf:
+                    self.launches += 1
+                Z = self._gemm(A, self.W[0], None, ops.ACT_NONE, N=self.H, K=self.Fp, name="gemm0_unique_rows")
+                h = self._spmm(Z, self.H, p.gid, self.b[0], ops.ACT_ELU, last, split=False, name="spmm0")
+            else:
+                src, width, idx = (X, self.Fp, p.gid) if i == 0 else (h, self.H, None)
+                A = self._spmm(src, width, idx, None, ops.ACT_NONE, last, split=bf, name=f"spmm{i}")
+                h = self._gemm(A, self.W[i], self.b[i], ops.ACT_ELU, N=self.H, K=width, name=f"gemm{i}")
+        if not self.with_head:
+            return h
+        if bf:
+            h = ops.split_bf16(h)
+            self.launches += 1
+        return self._gemm(h, self.Wl, self.bl, ops.ACT_NONE, self.head, N=self.C, K=self.H, name="head")
+
+    def scatter_to_nodes(self, out, n_nodes=None):
+        """Core-row outputs (pack order) -> [N, C] in global node order."""
+        n_nodes = self.pack.n_nodes if n_nodes is None else n_nodes
+        full = torch.empty(n_nodes, out.shape[1], dtype=out.dtype, device=out.device)
+        full[self.pack.core_gid.long()] = out
+        return full

@@ -1,0 +1,73 @@
+"""Inference drivers over a pack — the callers of the hot path.
+
+  node_infer_Gs     <- node_infer_Gs_GD /root/reference/run.py:49-115 (and the MB variant :117-175): the
+                       reference loops over 128-subgraph batches, skips batches without a selected node, and
+                       concatenates out[mask] in batch order — i.e. the selected rows in pack order.
+  per_query         <- the per-sample loop /root/reference/inference.py:672-688 (node_reg :805-819): one
+                       subgraph forward per queried node; here all queried subgraphs run as one small pack.
+"""
+from __future__ import annotations
+
+import torch
+
+from .engine import PackedForward
+from .pack import Pack
+
+
+def node_infer_Gs(state_dict, pack: Pack, X, select_mask=None, task="node_cls", precision="fp32",
+                  reference_quirks=True):
+    """Whole-pack inference.  Returns (out [n_selected, C], node_ids [n_selected]) with rows in the order the
+    reference concatenates them.  select_mask: global bool mask (test_mask / val_mask) or None for every node."""
+    head = "log_softmax" if task == "node_cls" else "identity"
+    fwd = PackedForward(pack, state_dict, head=head, rows="core", precision=precision)
+    out = fwd(X)
+    ids = pack.core_gid
+    if select_mask is not None:
+        sel = pack.split_masks(select_mask, reference_quirks)[pack.core_rows.long()]
+        out, ids = out[sel], ids[sel]
+    return out, ids
+
+
+def select_subgraphs(pack: Pack, sub_ids: torch.Tensor) -> Pack:
+    """The pack restricted to the given subgraphs (kept in the given order); block-diagonal, so columns only
+    need re-basing.  Index plumbing on the device, no host loop."""
+    dev = pack.device
+    sub_ids = sub_ids.to(dev).long()
+    sp = pack.sub_ptr.long()
+    lens = sp[sub_ids + 1] - sp[sub_ids]
+    new_sub_ptr = torch.zeros(sub_ids.numel() + 1, dtype=torch.long, device=dev)
+    new_sub_ptr[1:] = torch.cumsum(lens, 0)
+    n_rows = int(new_sub_ptr[-1])
+    which = torch.repeat_interleave(torch.arange(sub_ids.numel(), device=dev), lens)
+    rows = sp[sub_ids][which] + (torch.arange(n_rows, device=dev) - new_sub_ptr[:-1][which])
+    shift = (new_sub_ptr[:-1] - sp[sub_ids])[which]  # new row = old row + shift
+    rp = pack.rowptr.long()
+    deg = rp[rows + 1] - rp[rows]
+    new_rowptr = torch.zeros(n_rows + 1, dtype=torch.long, device=dev)
+    new_rowptr[1:] = torch.cumsum(deg, 0)
+    nnz = int(new_rowptr[-1])
+    erow = torch.repeat_interleave(torch.arange(n_rows, device=dev), deg)
+    eidx = rp[rows][erow] + (torch.arange(nnz, device=dev) - new_rowptr[:-1][erow])
+    col = pack.col.long()[eidx] + shift[erow]
+    is_core = pack.is_core[rows]
+    core_rows = torch.nonzero(is_core).view(-1)
+    return Pack(n_rows=n_rows, nnz=nnz, n_sub=sub_ids.numel(), n_core=core_rows.numel(), n_src=pack.n_src,
+                n_nodes=pack.n_nodes, mode=pack.mode, rowptr=new_rowptr.to(torch.int32), col=col.to(torch.int32),
+                dinv=pack.dinv[rows].contiguous(), gid=pack.gid[rows].contiguous(),
+                sub_ptr=new_sub_ptr.to(torch.int32), core_rows=core_rows.to(torch.int32),
+                is_core=is_core.contiguous(), mask=pack.mask[rows].contiguous(), part=pack.part)
+
+
+def per_query(state_dict, pack: Pack, X, query_nodes: torch.Tensor, task="node_cls", precision="fp32"):
+    """Outputs for the queried nodes, each computed on its own subgraph only (inference.py:672-688), all
+    queried subgraphs batched into one small pack.  Returns [n_queries, C] in query order."""
+    dev = pack.device
+    q = query_nodes.to(dev).long()
+    subs, inv = torch.unique(pack.part.long()[q], return_inverse=True)
+    small = select_subgraphs(pack, subs)
+    head = "log_softmax" if task == "node_cls" else "identity"
+    out = PackedForward(small, state_dict, head=head, rows="core", precision=precision)(X)
+    ids = small.core_gid.long()
+    lookup = torch.full((pack.n_nodes,), -1, dtype=torch.long, device=dev)
+    lookup[ids] = torch.arange(ids.numel(), device=dev)
+    return out[lookup[q]]

@@ -1,0 +1,275 @@
+"""Drop-in operator and model classes: same names, constructor arguments, forward signatures and
+state_dict keys as the reference (/root/reference/network.py:8-204 and the Net1/Net2 duplicates in
+inference.py:72-116), computing on the sm_100a kernels of libfitgnn_b200.so.
+
+`GCNConv` stands where `getattr(pyg_nn, args.layer_name)` resolves (network.py:13): ctor
+`GCNConv(in_channels, out_channels)`, parameters `lin.weight [out,in]` (glorot) and `bias [out]` (zeros),
+`__call__(x[n,in] fp32, edge_index[2,E] int64) -> [n,out]`.
+
+Inference only for now (eval mode; the training backward is the first "next" row): outputs
+carry no grad_fn, and calling a model in .train() mode raises.  CUDA tensors only — there is no CPU path.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .engine import PackedForward
+from .pack import Pack
+
+_CSR_CACHE: dict = {}
+_CSR_CACHE_MAX = 64
+
+
+def _csr_for(edge_index, n):
+    """gcn_norm structure, cached per edge_index tensor (PyG recomputes it on every call; cached=False)."""
+    key = (edge_index.data_ptr(), edge_index.shape[1], n, edge_index._version, edge_index.device.index)
+    hit = _CSR_CACHE.get(key)
+    if hit is None:
+        if len(_CSR_CACHE) >= _CSR_CACHE_MAX:
+            _CSR_CACHE.clear()
+        hit = ops.csr_from_coo(edge_index, n)
+        _CSR_CACHE[key] = hit
+    return hit
+
+
+def _as_f32_padded(x):
+    """fp32, contiguous, row pitch a multiple of 4 floats (16-byte vector loads)."""
+    if x.dtype != torch.float32:
+        x = x.float()
+    f = x.shape[1]
+    if f % 4 != 0:
+        xp = torch.zeros(x.shape[0], ops.pad4(f), dtype=torch.float32, device=x.device)
+        xp[:, :f] = x
+        return xp
+    return x.contiguous()
+
+
+def _pad_weight(w):
+    w = w.detach()
+    if w.shape[1] % 4 != 0:
+        w = torch.nn.functional.pad(w, (0, ops.pad4(w.shape[1]) - w.shape[1]))
+    return w.contiguous()
+
+
+def _require_cuda(x):
+    if not x.is_cuda:
+        raise RuntimeError("fitgnn_b200 computes on CUDA tensors only (no CPU fallback); got a CPU tensor")
+
+
+class GCNConv(torch.nn.Module):
+    """Replacement for torch_geometric.nn.GCNConv as the reference uses it (add_self_loops=True,
+    normalize=True, cached=False, bias=True)."""
+
+    def __init__(self, in_channels: int, out_channels: int, **kwargs):
+        super().__init__()
+        if kwargs:
+            raise TypeError(f"unsupported GCNConv options: {sorted(kwargs)}")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin = torch.nn.Linear(in_channels, out_channels, bias=False)
+        self.bias = torch.nn.Parameter(torch.zeros(out_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        torch.nn.init.xavier_uniform_(self.lin.weight)  # PyG: glorot
+        torch.nn.init.zeros_(self.bias)
+
+    def forward(self, x, edge_index, act: int = ops.ACT_NONE):
+        _require_cuda(x)
+        if self.out_channels % 4 != 0:
+            raise RuntimeError("fitgnn_b200.GCNConv needs out_channels % 4 == 0")
+        n = x.shape[0]
+        rowptr, col, dinv = _csr_for(edge_index, n)
+        xp = _as_f32_padded(x.detach())
+        w = _pad_weight(self.lin.weight)
+        b = self.bias.detach().contiguous()
+        if self.in_channels > self.out_channels:  # transform, then aggregate the narrower rows
+            z = ops.gemm_bias_act(xp, w, None, ops.ACT_NONE, K=xp.shape[1])
+            return ops.spmm_symnorm(rowptr, col, dinv, z, bias=b, act=act)
+        a = ops.spmm_symnorm(rowptr, col, dinv, xp)  # aggregate-first: Â(XW^T) = (ÂX)W^T
+        return ops.gemm_bias_act(a, w, b, act, K=xp.shape[1])
+
+    def extra_repr(self):
+        return f"{self.in_channels}, {self.out_channels}"
+
+
+_LAYERS = {"GCNConv": GCNConv}
+
+
+def _layer_class(args):
+    name = getattr(args, "layer_name", "GCNConv")
+    if name not in _LAYERS:
+        raise NotImplementedError(f"layer_name={name!r}: only GCNConv is on the B200 hot path (SURVEY §2 row 15)")
+    return _LAYERS[name]
+
+
+class _ConvStack(torch.nn.Module):
+    """Shared body of the six reference model classes (network.py:9-27 etc.)."""
+    _out_dim_from_args = True
+
+    def __init__(self, args):
+        super().__init__()
+        self.num_layers = args.num_layers1
+        Layer = _layer_class(args)
+        self.conv = torch.nn.ModuleList()
+        self.conv.append(Layer(args.num_features, args.hidden))
+        for _ in range(self.num_layers - 1):
+            self.conv.append(Layer(args.hidden, args.hidden))
+        self.lt1 = torch.nn.Linear(args.hidden, args.num_classes if self._out_dim_from_args else 1)
+
+    def reset_parameters(self):
+        for module in self.conv:
+            module.reset_parameters()
+        self.lt1.reset_parameters()
+
+    def _check_eval(self):
+        if self.training:
+            raise NotImplementedError("fitgnn_b200 models are inference-only for now: call model.eval() "
+                                      "(the training backward is the next row of the scope table)")
+
+    def _convs(self, x, edge_index):
+        # network.py:30-33: conv -> F.elu -> F.dropout(training=False) (identity); ELU is fused into the epilogue
+        for i in range(self.num_layers):
+            x = self.conv[i](x, edge_index, act=ops.ACT_ELU)
+        return x
+
+    def _lt1(self, x, head):
+        w = self.lt1.weight.detach().contiguous()
+        return ops.gemm_bias_act(x, w, self.lt1.bias.detach().contiguous(), ops.ACT_NONE, head)
+
+    def packed(self, pack: Pack, head=None, rows=None, precision="fp32") -> PackedForward:
+        """Fast path: the prepared whole-pack forward with this module's current parameters."""
+        return PackedForward(pack, self.state_dict(), head=head or self._head, rows=rows or self._rows,
+                             precision=precision)
+
+
+class Classify_node(_ConvStack):
+    """network.py:8-35."""
+    _head, _rows = "log_softmax", "core"
+
+    def forward(self, x, edge_index):
+        self._check_eval()
+        return self._lt1(self._convs(x, edge_index), ops.HEAD_LOG_SOFTMAX)
+
+
+class Regress_node(_ConvStack):
+    """network.py:37-64."""
+    _out_dim_from_args = False
+    _head, _rows = "identity", "core"
+
+    def forward(self, x, edge_index):
+        self._check_eval()
+        return self._lt1(self._convs(x, edge_index), ops.HEAD_IDENTITY)
+
+
+class GraphBatch:
+    """A collated batch of graphs, each given as its list of subgraphs (the `set_gs` argument of the
+    reference's *_gs models, built by colater utils.py:893-908): one block-diagonal CSR for all subgraphs of
+    all graphs, the masked rows in order, and the pooling segments of batch_tensor."""
+
+    def __init__(self, set_gs, batch_tensor, device):
+        xs, eis, masks, off = [], [], [], 0
+        for gs in set_gs:
+            for g in gs:
+                xs.append(g.x.float())
+                eis.append(g.edge_index + off)
+                masks.append(g.mask)
+                off += g.x.shape[0]
+        self.x = torch.cat(xs, 0).to(device)
+        self.edge_index = torch.cat(eis, 1).to(device).contiguous()
+        mask = torch.cat(masks, 0).to(device)
+        self.rows = torch.nonzero(mask).view(-1).to(torch.int32)
+        bt = batch_tensor.to(device).to(torch.int64)  # network.py:131: batch_tensor.type(torch.int64)
+        n_graphs = int(bt.max().item()) + 1 if bt.numel() else 0
+        assert bt.numel() == self.rows.numel(), "batch_tensor must have one entry per masked row"
+        assert bool((bt[1:] >= bt[:-1]).all()), "batch_tensor must be sorted (colater builds it that way)"
+        counts = torch.bincount(bt, minlength=n_graphs)
+        self.seg_ptr = torch.zeros(n_graphs + 1, dtype=torch.int32, device=device)
+        self.seg_ptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+
+
+class _GraphGs(_ConvStack):
+    def _forward_gs(self, set_gs, batch_tensor, pool, head):
+        self._check_eval()
+        dev = self.lt1.weight.device
+        gb = set_gs if isinstance(set_gs, GraphBatch) else GraphBatch(set_gs, batch_tensor, dev)
+        x = self._convs(gb.x, gb.edge_index)
+        pooled = ops.segment_pool(x, gb.rows, gb.seg_ptr, pool)
+        return self._lt1(pooled, head)
+
+
+class _GraphGc(_ConvStack):
+    def _forward_gc(self, gc, pool, head):
+        self._check_eval()
+        x, edge_index, batch = gc.x, gc.edge_index, gc.batch
+        _require_cuda(x)
+        n_graphs = int(batch.max().item()) + 1
+        assert bool((batch[1:] >= batch[:-1]).all()), "gc.batch must be sorted (PyG Batch builds it that way)"
+        seg_ptr = torch.zeros(n_graphs + 1, dtype=torch.int32, device=x.device)
+        seg_ptr[1:] = torch.cumsum(torch.bincount(batch, minlength=n_graphs), 0).to(torch.int32)
+        h = self._convs(x.float(), edge_index.contiguous())
+        return self._lt1(ops.segment_pool(h, None, seg_ptr, pool), head)
+
+
+class Classify_graph_gc(_GraphGc):
+    """network.py:66-95: conv stack -> global_max_pool -> lt1 -> softmax."""
+    _head, _rows = "softmax", "all"
+
+    def forward(self, gc):
+        return self._forward_gc(gc, ops.POOL_MAX, ops.HEAD_SOFTMAX)
+
+
+class Classify_graph_gs(_GraphGs):
+    """network.py:97-135: per-subgraph conv stack -> x[mask] -> global_max_pool -> lt1 -> softmax."""
+    _head, _rows = "softmax", "mask"
+
+    def forward(self, set_gs, batch_tensor=None):
+        return self._forward_gs(set_gs, batch_tensor, ops.POOL_MAX, ops.HEAD_SOFTMAX)
+
+
+class Regress_graph_gc(_GraphGc):
+    """network.py:137-166: conv stack -> global_mean_pool -> lt1."""
+    _out_dim_from_args = False
+    _head, _rows = "identity", "all"
+
+    def forward(self, gc):
+        return self._forward_gc(gc, ops.POOL_MEAN, ops.HEAD_IDENTITY)
+
+
+class Regress_graph_gs(_GraphGs):
+    """network.py:168-204: per-subgraph conv stack -> x[mask] -> global_mean_pool -> lt1."""
+    _out_dim_from_args = False
+    _head, _rows = "identity", "mask"
+
+    def forward(self, set_gs, batch_tensor=None):
+        return self._forward_gs(set_gs, batch_tensor, ops.POOL_MEAN, ops.HEAD_IDENTITY)
+
+
+def _ns(num_features, hidden, num_layers, num_classes):
+    import argparse
+    return argparse.Namespace(num_features=num_features, hidden=hidden, num_layers1=num_layers,
+                              num_classes=num_classes, layer_name="GCNConv")
+
+
+class Net1(Classify_node):
+    """inference.py:72-93 `Net1(num_features, hidden, num_layers, num_classes)` — same state_dict keys."""
+
+    def __init__(self, num_features, hidden, num_layers, num_classes):
+        super().__init__(_ns(num_features, hidden, num_layers, num_classes))
+
+
+class Net2(Regress_node):
+    """inference.py:95-116 `Net2(num_features, hidden, num_layers)`."""
+
+    def __init__(self, num_features, hidden, num_layers, num_classes=1):
+        super().__init__(_ns(num_features, hidden, num_layers, 1))
+
+
+def install():
+    """Route the reference's layer lookup to this module: after `fitgnn_b200.nn.install()`,
+    `getattr(torch_geometric.nn, 'GCNConv')` (network.py:13) and `from torch_geometric.nn import GCNConv`
+    (network.py:5, inference.py) resolve to the B200 operator.  Call before importing network.py."""
+    import importlib
+    pyg_nn = importlib.import_module("torch_geometric.nn")
+    pyg_nn.GCNConv = GCNConv
+    return pyg_nn

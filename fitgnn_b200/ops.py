@@ -1,0 +1,181 @@
+"""Thin torch-tensor wrappers over the C ABI (include/fitgnn.h).  torch is used for device memory and
+streams only; every computation happens inside libfitgnn_b200.so on the current CUDA stream."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, stream_ptr
+
+ACT_NONE, ACT_ELU = 0, 1
+HEAD_IDENTITY, HEAD_LOG_SOFTMAX, HEAD_SOFTMAX = 0, 1, 2
+MODE_NONE, MODE_EXTRA, MODE_CLUSTER = 0, 1, 2
+POOL_MAX, POOL_MEAN = 0, 1
+GEMM_FP32, GEMM_BF16X3 = 0, 1
+MODES = {"none": MODE_NONE, "extra": MODE_EXTRA, "cluster": MODE_CLUSTER}
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def pad4(n):
+    return (int(n) + 3) // 4 * 4
+
+
+# ----------------------------------------------------------------------------------------- primitives
+def sort_u64(keys, vals=None, key_bits=64):
+    """In-place ascending radix sort of int64 keys interpreted as unsigned (low key_bits bits)."""
+    assert keys.dtype == torch.int64 and (vals is None or vals.dtype == torch.int32)
+    ws = _ws(lib().fitgnn_sort_workspace_bytes(keys.numel()), keys.device)
+    check(lib().fitgnn_sort_u64(ptr(keys), ptr(vals), keys.numel(), key_bits, ptr(ws), ws.numel(), stream_ptr()))
+    return keys, vals
+
+
+def scan_i32(x, with_total=True):
+    assert x.dtype == torch.int32
+    out = torch.empty(x.numel() + (1 if with_total else 0), dtype=torch.int32, device=x.device)
+    ws = _ws(lib().fitgnn_scan_workspace_bytes(x.numel()), x.device)
+    check(lib().fitgnn_scan_i32(ptr(x), ptr(out), x.numel(), int(with_total), ptr(ws), ws.numel(), stream_ptr()))
+    return out
+
+
+# ----------------------------------------------------------------------------------------- CSR / SpMM
+def csr_from_coo(edge_index, n):
+    """gcn_norm structure for the drop-in GCNConv: (rowptr, col, dinv) with self loops re-added."""
+    assert edge_index.dtype == torch.int64 and edge_index.dim() == 2 and edge_index.shape[0] == 2
+    ei = edge_index.contiguous()
+    E = ei.shape[1]
+    ws = _ws(lib().fitgnn_csr_workspace_bytes(E, n), ei.device)
+    nnz = C.c_int64(0)
+    check(lib().fitgnn_csr_plan(ptr(ei), E, n, ptr(ws), ws.numel(), C.byref(nnz), stream_ptr()))
+    rowptr = torch.empty(n + 1, dtype=torch.int32, device=ei.device)
+    col = torch.empty(max(nnz.value, 1), dtype=torch.int32, device=ei.device)[: nnz.value]
+    dinv = torch.empty(n, dtype=torch.float32, device=ei.device)
+    check(lib().fitgnn_csr_fill(n, ptr(ws), ws.numel(), ptr(rowptr), ptr(col), ptr(dinv), stream_ptr()))
+    return rowptr, col, dinv
+
+
+def spmm_symnorm(rowptr, col, dinv, X, width=None, src_index=None, bias=None, act=ACT_NONE, out_rows=None,
+                 out=None, split=False, hubs=None):
+    """Y = act(Â·X[src_index] + bias) on the rows `out_rows` (all rows when None).
+    split=True returns bf16 (hi, lo) planes for the tensor-core GEMM instead of fp32."""
+    assert X.dtype == torch.float32 and X.dim() == 2
+    ldx = X.stride(0)
+    width = X.shape[1] if width is None else width
+    n_out = out_rows.numel() if out_rows is not None else rowptr.numel() - 1
+    if split:
+        if out is None:
+            out = (torch.empty(n_out, width, dtype=torch.bfloat16, device=X.device),
+                   torch.empty(n_out, width, dtype=torch.bfloat16, device=X.device))
+        y, ylo, ldy = out[0], out[1], out[0].stride(0)
+    else:
+        if out is None:
+            out = torch.empty(n_out, width, dtype=torch.float32, device=X.device)
+        y, ylo, ldy = out, None, out.stride(0)
+    if hubs is not None and hubs[1] > 0:
+        hub_list, n_hub, hub_deg = hubs
+        check(lib().fitgnn_spmm_symnorm_hub(ptr(rowptr), ptr(col), ptr(dinv), ptr(X), ldx, width, ptr(src_index),
+                                            ptr(bias), act, ptr(out_rows), n_out, ptr(y), ptr(ylo), ldy,
+                                            ptr(hub_list), n_hub, hub_deg, stream_ptr()))
+    else:
+        check(lib().fitgnn_spmm_symnorm(ptr(rowptr), ptr(col), ptr(dinv), ptr(X), ldx, width, ptr(src_index),
+                                        ptr(bias), act, ptr(out_rows), n_out, ptr(y), ptr(ylo), ldy, stream_ptr()))
+    return out
+
+
+def find_hubs(rowptr, out_rows, n_out, hub_deg=256, cap=None):
+    """Output rows with >= hub_deg entries -> (hub_list, n_hub, hub_deg).  Synchronises once (build time)."""
+    cap = int(cap if cap is not None else max(1024, n_out // 64))
+    hub_list = torch.empty(cap, dtype=torch.int32, device=rowptr.device)
+    cnt = torch.zeros(1, dtype=torch.int32, device=rowptr.device)
+    check(lib().fitgnn_spmm_hubs(ptr(rowptr), ptr(out_rows), n_out, hub_deg, ptr(hub_list), ptr(cnt), cap,
+                                 stream_ptr()))
+    n = int(cnt.item())
+    if n > cap:
+        return find_hubs(rowptr, out_rows, n_out, hub_deg, n)
+    hub_list = torch.sort(hub_list[:n]).values.contiguous() if n > 0 else hub_list[:0]
+    return hub_list, n, hub_deg
+
+
+# ----------------------------------------------------------------------------------------- dense
+def gemm_bias_act(A, W, bias=None, act=ACT_NONE, head=HEAD_IDENTITY, out=None, K=None, N=None, precision=GEMM_FP32):
+    """Y = head(act(A·W^T + bias)).  FP32: A [M,K] fp32, W [N,K] fp32.  BF16X3: A=(hi,lo), W=(hi,lo) bf16 planes."""
+    if precision == GEMM_FP32:
+        a_hi, a_lo, w_hi, w_lo = A, None, W, None
+        assert A.dtype == torch.float32 and W.dtype == torch.float32
+    else:
+        (a_hi, a_lo), (w_hi, w_lo) = A, W
+        assert a_hi.dtype == torch.bfloat16 and w_hi.dtype == torch.bfloat16
+    M = a_hi.shape[0]
+    K = a_hi.shape[1] if K is None else K
+    N = w_hi.shape[0] if N is None else N
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=a_hi.device)
+    check(lib().fitgnn_gemm_bias_act(precision, ptr(a_hi), ptr(a_lo), a_hi.stride(0), ptr(w_hi), ptr(w_lo),
+                                     w_hi.stride(0), ptr(bias), M, K, N, act, head, ptr(out), out.stride(0),
+                                     stream_ptr()))
+    return out
+
+
+def split_bf16(X, cols=None, ldo=None):
+    """fp32 [rows, cols] -> bf16 (hi, lo) planes [rows, ldo] with zero-filled padding columns."""
+    rows = X.shape[0]
+    cols = X.shape[1] if cols is None else cols
+    ldo = cols if ldo is None else ldo
+    hi = torch.empty(rows, ldo, dtype=torch.bfloat16, device=X.device)
+    lo = torch.empty(rows, ldo, dtype=torch.bfloat16, device=X.device)
+    check(lib().fitgnn_split_bf16(ptr(X), X.stride(0), rows, cols, ptr(hi), ptr(lo), ldo, stream_ptr()))
+    return hi, lo
+
+
+def segment_pool(X, rows, seg_ptr, pool, width=None):
+    width = X.shape[1] if width is None else width
+    n_seg = seg_ptr.numel() - 1
+    out = torch.empty(n_seg, width, dtype=torch.float32, device=X.device)
+    check(lib().fitgnn_segment_pool(ptr(X), X.stride(0), width, ptr(rows), ptr(seg_ptr), n_seg, pool, ptr(out),
+                                    out.stride(0), stream_ptr()))
+    return out
+
+
+# ----------------------------------------------------------------------------------------- projection
+def group_by_part(part, k):
+    assert part.dtype == torch.int32
+    N = part.numel()
+    members = torch.empty(N, dtype=torch.int32, device=part.device)
+    member_ptr = torch.empty(k + 1, dtype=torch.int32, device=part.device)
+    ws = _ws(lib().fitgnn_group_workspace_bytes(N, k), part.device)
+    check(lib().fitgnn_group_by_part(ptr(part), N, k, ptr(members), ptr(member_ptr), ptr(ws), ws.numel(),
+                                     stream_ptr()))
+    return members, member_ptr
+
+
+def project_features(members, member_ptr, cweight, X):
+    """Xc = C·X with C given as (part -> members/member_ptr, cweight[N] float64)."""
+    assert cweight.dtype == torch.float64 and X.dtype == torch.float32
+    k = member_ptr.numel() - 1
+    F = X.shape[1]
+    Xc = torch.empty(k, F, dtype=torch.float32, device=X.device)
+    check(lib().fitgnn_project_features(ptr(members), ptr(member_ptr), k, ptr(cweight), ptr(X), X.stride(0), F,
+                                        ptr(Xc), Xc.stride(0), stream_ptr()))
+    return Xc
+
+
+def project_adj(edge_index, part, k, want_rowptr=True):
+    """Pattern of P_bin·A·P_bin^T minus its diagonal: (row int64, col int64, cnt int32, rowptr int32)."""
+    ei = edge_index.contiguous()
+    E = ei.shape[1]
+    N = part.numel()
+    ws = _ws(lib().fitgnn_project_adj_workspace_bytes(E), ei.device)
+    nnz = C.c_int64(0)
+    check(lib().fitgnn_project_adj_plan(ptr(ei), E, N, ptr(part), k, ptr(ws), ws.numel(), C.byref(nnz), stream_ptr()))
+    n = nnz.value
+    row = torch.empty(max(n, 1), dtype=torch.int64, device=ei.device)[:n]
+    col = torch.empty(max(n, 1), dtype=torch.int64, device=ei.device)[:n]
+    cnt = torch.empty(max(n, 1), dtype=torch.int32, device=ei.device)[:n]
+    rowptr = torch.empty(k + 1, dtype=torch.int32, device=ei.device) if want_rowptr else None
+    check(lib().fitgnn_project_adj_fill(ptr(ws), ws.numel(), k, ptr(row), ptr(col), ptr(cnt), ptr(rowptr),
+                                        stream_ptr()))
+    return row, col, cnt, rowptr

@@ -1,0 +1,116 @@
+"""The packed block-diagonal CSR of all subgraphs Gs, built once on the device from the partition vector.
+
+Replaces the list[Data] the reference builds in coarsening_classification / coarsening_regression
+(/root/reference/utils.py:143-374, :376-605) and re-collates every epoch with G_DataLoader (run.py:336).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import ops
+from ._lib import PackStruct, PlanStruct, check, lib, ptr, stream_ptr
+
+
+@dataclass
+class Pack:
+    """Device arrays of one pack (see include/fitgnn.h `fitgnn_pack`).  Immutable after build."""
+    n_rows: int
+    nnz: int
+    n_sub: int
+    n_core: int
+    n_src: int
+    n_nodes: int          # N of the graph the pack was built from
+    mode: str
+    rowptr: torch.Tensor  # int32 [n_rows+1]
+    col: torch.Tensor     # int32 [nnz]
+    dinv: torch.Tensor    # fp32  [n_rows]
+    gid: torch.Tensor     # int32 [n_rows]
+    sub_ptr: torch.Tensor  # int32 [n_sub+1]
+    core_rows: torch.Tensor  # int32 [n_core]
+    is_core: torch.Tensor  # uint8 [n_rows]
+    mask: torch.Tensor    # uint8 [n_rows]
+    part: torch.Tensor | None = None  # int32 [N]
+
+    def struct(self) -> PackStruct:
+        return PackStruct(self.n_rows, self.nnz, self.n_sub, self.n_core, self.n_src,
+                          self.rowptr.data_ptr(), self.col.data_ptr(), self.dinv.data_ptr(), self.gid.data_ptr(),
+                          self.sub_ptr.data_ptr(), self.core_rows.data_ptr(), self.is_core.data_ptr(),
+                          self.mask.data_ptr())
+
+    @property
+    def device(self):
+        return self.rowptr.device
+
+    @property
+    def core_gid(self):
+        """Global node id of every core row, in pack order (= the order outputs are returned in)."""
+        return self.gid[self.core_rows.long()]
+
+    def mask_rows(self):
+        """Pack rows with M.mask == True, ascending (the rows graph-level models pool, network.py:129,200)."""
+        return torch.nonzero(self.mask).view(-1).to(torch.int32)
+
+    def split_masks(self, global_mask, reference_quirks=True):
+        """Per-row mask = global mask mapped through map_dict with extra / cluster nodes forced to False
+        (load_data_classification /root/reference/utils.py:683-703).  With reference_quirks the key
+        collision of utils.py:258-259 is reproduced: in cluster mode a real node whose global id equals the
+        local id of one of its subgraph's cluster nodes never receives its mask."""
+        gm = global_mask.to(self.device).bool()
+        rows = torch.zeros(self.n_rows, dtype=torch.bool, device=self.device)
+        core = self.is_core.bool()
+        gid = self.gid.long()
+        rows[core] = gm[gid[core]]
+        if reference_quirks and self.mode == "cluster":
+            sub_of_row = torch.repeat_interleave(torch.arange(self.n_sub, device=self.device),
+                                                 (self.sub_ptr[1:] - self.sub_ptr[:-1]).long())
+            n_rows_s = (self.sub_ptr[1:] - self.sub_ptr[:-1]).long()
+            n_core_s = torch.zeros(self.n_sub, dtype=torch.long, device=self.device).index_add_(
+                0, sub_of_row, core.long())
+            lo, hi = n_core_s[sub_of_row], n_rows_s[sub_of_row]
+            rows &= ~(core & (gid >= lo) & (gid < hi))
+        return rows
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in
+                   (self.rowptr, self.col, self.dinv, self.gid, self.sub_ptr, self.core_rows, self.is_core, self.mask))
+
+
+def build_pack(edge_index: torch.Tensor, part: torch.Tensor, k: int, mode: str = "none",
+               ac_rowptr: torch.Tensor | None = None, ac_col: torch.Tensor | None = None) -> Pack:
+    """Build the pack on the device.  edge_index [2,E] int64 (the reference's COO), part[v] = index of v's
+    subgraph in the reference's subgraph_list order.  mode 'cluster' needs the coarsened adjacency pattern
+    as CSR (ops.project_adj gives it; computed here when not supplied)."""
+    assert edge_index.is_cuda and edge_index.dtype == torch.int64
+    ei = edge_index.contiguous()
+    part = part.to(device=ei.device, dtype=torch.int32).contiguous()
+    N, E = part.numel(), ei.shape[1]
+    m = ops.MODES[mode]
+    ac_nnz = 0
+    if m == ops.MODE_CLUSTER:
+        if ac_rowptr is None:
+            _, c, _, ac_rowptr = ops.project_adj(ei, part, k)
+            ac_col = c.to(torch.int32)
+        ac_col = ac_col.to(torch.int32).contiguous()
+        ac_nnz = ac_col.numel()
+    ws = ops._ws(lib().fitgnn_pack_workspace_bytes(E, N, k, m, ac_nnz), ei.device)
+    plan = PlanStruct()
+    check(lib().fitgnn_pack_plan(ptr(ei), E, N, ptr(part), k, m, ptr(ac_rowptr), ptr(ac_col), ac_nnz, ptr(ws),
+                                 ws.numel(), C.byref(plan), stream_ptr()))
+    dev = ei.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    p = Pack(n_rows=plan.n_rows, nnz=plan.nnz, n_sub=plan.n_sub, n_core=plan.n_core, n_src=plan.n_src, n_nodes=N,
+             mode=mode,
+             rowptr=torch.empty(plan.n_rows + 1, **i32), col=torch.empty(plan.nnz, **i32),
+             dinv=torch.empty(plan.n_rows, dtype=torch.float32, device=dev), gid=torch.empty(plan.n_rows, **i32),
+             sub_ptr=torch.empty(plan.n_sub + 1, **i32), core_rows=torch.empty(plan.n_core, **i32),
+             is_core=torch.empty(plan.n_rows, dtype=torch.uint8, device=dev),
+             mask=torch.empty(plan.n_rows, dtype=torch.uint8, device=dev), part=part)
+    ws2 = ops._ws(plan.fill_ws_bytes, dev) if plan.fill_ws_bytes > 0 else None
+    st = p.struct()
+    check(lib().fitgnn_pack_fill(C.byref(plan), C.byref(st), ptr(ws), ws.numel(), ptr(ws2),
+                                 ws2.numel() if ws2 is not None else 0, stream_ptr()))
+    torch.cuda.current_stream().synchronize()  # ws / ws2 are released on return
+    return p

@@ -1,0 +1,99 @@
+"""CPU: host-side logic and the C-ABI surface (no compute calls — there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fitgnn_oracle as fo
+from tests import golden_io as gio
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    import fitgnn_b200
+    hdr = open(os.path.join(ROOT, "include", "fitgnn.h")).read()
+    declared = set(re.findall(r"\b(fitgnn_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(fitgnn_b200._lib.SIGNATURES), declared ^ set(fitgnn_b200._lib.SIGNATURES)
+    handle = ctypes.CDLL(fitgnn_b200._lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert handle.fitgnn_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    import fitgnn_b200
+    assert ctypes.sizeof(fitgnn_b200._lib.PackStruct) == 5 * 8 + 8 * 8
+    assert ctypes.sizeof(fitgnn_b200._lib.PlanStruct) == (6 + 27) * 8
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "fitgnn_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "fitgnn_oracle" not in src, f
+
+
+def test_cpu_tensors_are_rejected():
+    import fitgnn_b200
+    with pytest.raises(fitgnn_b200._lib.FitgnnError):
+        fitgnn_b200.ops.gemm_bias_act(torch.zeros(2, 4), torch.zeros(4, 4))
+    conv = fitgnn_b200.GCNConv(4, 8)
+    with pytest.raises(RuntimeError):
+        conv(torch.zeros(3, 4), torch.zeros(2, 0, dtype=torch.long))
+
+
+def test_state_dict_keys_match_reference():
+    import argparse
+    import fitgnn_b200
+    args = argparse.Namespace(num_layers1=2, num_features=12, hidden=32, num_classes=4, layer_name="GCNConv")
+    sd = gio.state_dict(gio.load("node_small"))
+    for cls in (fitgnn_b200.Classify_node, fitgnn_b200.Classify_graph_gc, fitgnn_b200.Classify_graph_gs):
+        m = cls(args)
+        assert set(m.state_dict().keys()) == set(sd.keys())
+        m.load_state_dict(sd)
+    assert fitgnn_b200.Regress_node(args).lt1.out_features == 1
+    with pytest.raises(NotImplementedError):
+        fitgnn_b200.Classify_node(argparse.Namespace(num_layers1=2, num_features=4, hidden=8, num_classes=2,
+                                                     layer_name="GATConv"))
+
+
+@pytest.mark.parametrize("mode", ["none", "extra", "cluster"])
+def test_partition_from_components_matches_reference_order(mode):
+    import fitgnn_b200
+    d = gio.load("node_small")
+    comps = gio.components(d, mode)
+    cos = gio.coarsenings_for_oracle(d, mode, comps)
+    p = fitgnn_b200.coarsen.partition_from_components(comps, [c["C"] if c else None for c in cos], int(d["n"]))
+    ref = gio.subgraphs(d, mode + "_sub")
+    assert p.k == len(ref)
+    # every node's subgraph is the one whose map_dict / core set holds it
+    subs = fo.build_subgraphs(d["edge_index"], d["x"], d["y"], comps, cos, mode)
+    assert np.array_equal(p.part, fo.partition_vector(subs, int(d["n"])))
+
+
+def test_synth_generators_are_seeded():
+    import fitgnn_b200
+    a = fitgnn_b200.synth.powerlaw_graph(500, 1200, seed=1)
+    b = fitgnn_b200.synth.powerlaw_graph(500, 1200, seed=1)
+    assert np.array_equal(a, b)
+    pa, comps, C_list = fitgnn_b200.synth.neighborhood_partition(a, 500, 0.3, seed=1)
+    pb, _, _ = fitgnn_b200.synth.neighborhood_partition(a, 500, 0.3, seed=1)
+    assert np.array_equal(pa.part, pb.part)
+    # ratio is honoured per component: k_c == ceil(ratio * n_c) unless neighbourhoods run out
+    for comp, C in zip(comps, C_list):
+        if C is not None:
+            assert C.shape[0] >= int(np.ceil(0.3 * len(comp)))
+            assert np.all(np.diff(C.tocsc().indptr) == 1)
+    ei, part, cw, k = fitgnn_b200.synth.planted_partition(3000, 20000, 0.5, seed=2, device="cpu")
+    ei2, part2, _, _ = fitgnn_b200.synth.planted_partition(3000, 20000, 0.5, seed=2, device="cpu")
+    assert torch.equal(ei, ei2) and torch.equal(part, part2)
+    assert int(part.max()) + 1 == k and ei.shape[0] == 2
+    sizes = torch.bincount(part.long())
+    assert torch.allclose(cw, 1.0 / torch.sqrt(sizes[part.long()].double()))
