@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path on BASELINE.json's headline workload.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]              (torchrun launches N>1, one rank per GPU)
+  python bench.py --impl reference [...]                            (the restated reference CPU path)
+
+Workload (config.workload = "products"): ogbn-products-shaped synthetic graph — 2,449,029 nodes, 61,859,140
+undirected edges, 100 features, 47 classes, planted partition at coarsening ratio 0.5 — all subgraphs Gs
+through a 2-layer GCN (hidden 512) + lt1 + log_softmax.  One step = one forward of EVERY subgraph, i.e. logits
+for every node.  metric = subgraph-inference nodes/sec.  Prints one JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "subgraph-inference nodes/sec"
+UNIT = "nodes/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--workload", default="products", choices=["products", "products-small"])
+    p.add_argument("--mode", default="none", choices=["none", "extra", "cluster"])
+    p.add_argument("--ratio", type=float, default=0.5)
+    p.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16x3"])
+    p.add_argument("--hidden", type=int, default=512)
+    p.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline sample")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--seed", type=int, default=0)
+    return p.parse_args()
+
+
+def workload_shape(name):
+    if name == "products":
+        return 2449029, 61859140, 100, 47
+    return 200000, 5000000, 100, 47  # products-small: same generator, for quick checks
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self):
+        sm, smax, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); smax = max(smax, float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+def generate(args, device):
+    import fitgnn_b200 as fg
+    n, e_und, F, C = workload_shape(args.workload)
+    ei, part, cw, k = fg.synth.planted_partition(n, e_und, args.ratio, seed=args.seed, device=device)
+    part = fg.synth.relabel_partition_reference_order(part)
+    X = fg.synth.features(n, F, seed=args.seed, device=device)
+    sd = fg.synth.init_state_dict(F, args.hidden, C, seed=args.seed)
+    return n, F, C, ei, part, cw, k, X, sd
+
+
+# ------------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference(args, ei, part, X, sd, k, seconds, steps=1, warmup=0):
+    """The reference's batched CPU inference (node_infer_Gs_GD run.py:49-115: 128-subgraph block-diagonal batches,
+    gcn_norm + F.linear + index_select/index_add per layer, lt1, log_softmax; timer around model() only) restated
+    in oracle/fitgnn_oracle.py, on all host cores, over a bounded sample of consecutive subgraphs."""
+    from oracle import fitgnn_oracle as fo
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ei_c, part_c, X_c = ei.cpu().numpy(), part.cpu().numpy(), X.cpu().numpy()
+    sd_c = {k_: v.cpu() for k_, v in sd.items()}
+    # calibrate on 8 batches, then size the sample for ~`seconds` of CPU work per step
+    def prep(sub_ids):
+        subs = fo.subgraphs_from_partition(ei_c, X_c, part_c, sub_ids)
+        batches = [fo.collate(subs[b:b + 128]) for b in range(0, len(subs), 128)]
+        return batches, sum(s["x"].shape[0] for s in subs)
+
+    def run(batches):
+        t = 0.0
+        with torch.no_grad():
+            for x, e in batches:
+                t0 = time.perf_counter()
+                fo.classify_node(sd_c, x, e)
+                t += time.perf_counter() - t0
+        return t
+
+    cal, cal_nodes = prep(np.arange(0, min(k, 8 * 128)))
+    run(cal[:2])
+    t_cal = run(cal)
+    n_batches = int(max(8, min(k // 128, seconds / max(t_cal / len(cal), 1e-6))))
+    batches, nodes = prep(np.arange(0, min(k, n_batches * 128)))
+    for _ in range(warmup):
+        run(batches)
+    times = [run(batches) for _ in range(max(1, steps))]
+    t = float(np.median(times))
+    return dict(value=nodes / t, unit=UNIT, cores=cores, kind="port",
+                sample=f"first {len(batches)} batches x 128 subgraphs ({nodes} nodes) of the same graph, "
+                       f"torch {torch.__version__} CPU fp32 no_grad, median of {len(times)}"), t, nodes
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    device = "cuda" if torch.cuda.is_available() else "cpu"  # generation only; nothing timed runs on the GPU
+    n, F, C, ei, part, cw, k, X, sd = generate(args, device)
+    base, t, nodes = cpu_reference(args, ei, part, X, sd, k, args.cpu_seconds, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_of(args, n, F, C, k), "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def config_of(args, n, F, C, k):
+    return {"workload": f"{args.workload}: ogbn-products-shaped synthetic, {n} nodes, "
+                        f"{workload_shape(args.workload)[1]} undirected edges, F={F}, C={C}, planted partition "
+                        f"ratio {args.ratio} (k={k}), mode={args.mode}, 2-layer GCN hidden={args.hidden} + lt1 + log_softmax",
+            "subgraphs": k, "mode": args.mode, "l2": "inputs larger than L2 (activations are GBs per layer)"}
+
+
+# ------------------------------------------------------------------------------------------------- GPU arm
+def main_ours(args):
+    import torch.distributed as dist
+
+    import fitgnn_b200 as fg
+    from fitgnn_b200.dist import ShardedPack
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    n, F, C, ei, part, cw, k, X, sd = generate(args, device)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    pack = fg.build_pack(ei, part, k, args.mode)
+    torch.cuda.synchronize()
+    pack_build_ms = (time.perf_counter() - t0) * 1e3
+    ei_keep = ei if (rank == 0 and not args.no_cpu_baseline) else None
+    del ei
+    if args.mode == "cluster":
+        raise SystemExit("bench: cluster mode needs the C·X rows appended to X; use tests for that mode")
+    shard = ShardedPack(pack, world, rank, args.hidden, F)
+    precision = args.precision
+    if precision == "auto":
+        precision = os.environ.get("FITGNN_PRECISION", "fp32")
+    fwd = fg.PackedForward(shard.local, sd, head="log_softmax", rows="core", precision=precision)
+    Xd = fwd.pad_features(X)
+
+    def step():
+        out = fwd(Xd)
+        return shard.gather_outputs(out) if world > 1 else out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    fwd.enable_profile(True)
+    launches0 = fwd.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    gpu_launches = fwd.launches - launches0
+    prof = fwd.profile_summary()
+    fwd.enable_profile(False)
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+
+    # ---- end to end: host pinned X -> device, forward, logits -> host pinned, every step
+    e2e = None
+    if not args.no_e2e:
+        X_host = X.cpu().pin_memory()
+        n_out = n if world > 1 else fwd.n_out
+        out_host = torch.empty(n_out, C, dtype=torch.float32).pin_memory()
+        X_in = torch.empty_like(Xd)
+
+        def e2e_step():
+            X_in[:, :F].copy_(X_host, non_blocking=True)
+            o = fwd(X_in)
+            if world > 1:
+                o = shard.gather_outputs(o)
+            out_host.copy_(o, non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        ev1.record()
+        barrier()
+        t2 = torch.tensor([ev0.elapsed_time(ev1) / args.steps], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e = {"value": n / (float(t2.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(t2.item()),
+               "h2d_bytes_per_step": int(X_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4)}
+    if rank == 0:
+        sampler.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, tc_peak, peak_src = measured_peaks()
+    kernels = {}
+    for name, r in prof.items():
+        gbs = r["bytes"] / (r["ms"] * 1e-3) / 1e9
+        tfs = r["flops"] / (r["ms"] * 1e-3) / 1e12 if r["flops"] else 0.0
+        kernels[name] = {"ms": r["ms"], "algo_GB": r["bytes"] / 1e9, "GBps": gbs, "TFLOPs": tfs,
+                         "share": r["ms"] / max(1e-9, sum(x["ms"] for x in prof.values()))}
+    dom = max(kernels, key=lambda k_: kernels[k_]["ms"])
+
+    def roofline_of(name):
+        r = kernels[name]
+        tensor_bound = name.startswith("gemm") and precision == "bf16x3" and r["TFLOPs"] / tc_peak > r["GBps"] / hbm_peak
+        if tensor_bound:
+            # 3 bf16 MMAs per logical product (hi*hi + hi*lo + lo*hi)
+            ach = 3 * r["TFLOPs"]
+            return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s",
+                    "frac": ach / tc_peak, "traffic": None, "peak_source": peak_src}
+        return {"kernel": name, "bound": "hbm", "achieved": r["GBps"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": r["GBps"] / hbm_peak, "frac_of_nominal_8000": r["GBps"] / 8000.0, "traffic": None,
+                "peak_source": peak_src}
+
+    spmm_names = [k_ for k_ in kernels if k_.startswith("spmm")]
+    spmm_main = max(spmm_names, key=lambda k_: kernels[k_]["algo_GB"]) if spmm_names else dom
+    line = {"metric": METRIC, "value": n / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32" if precision == "fp32" else "bf16x3(f32 accumulate)", "data": "synthetic",
+            "config": config_of(args, n, F, C, k), "roofline": roofline_of(dom), "roofline_spmm": roofline_of(spmm_main),
+            "kernels": kernels, "gpu_launches": gpu_launches, "clocks": sampler.summary(),
+            "pack": {"rows": pack.n_rows, "nnz": pack.nnz, "subgraphs": pack.n_sub, "build_ms": pack_build_ms,
+                     "bytes": pack.nbytes(), "rank_loads": shard.loads}}
+    if e2e:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu_baseline:
+        base, _, _ = cpu_reference(args, ei_keep, part, X, sd, k, args.cpu_seconds)
+        line["cpu_baseline"] = base
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)

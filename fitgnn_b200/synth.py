@@ -196,3 +196,19 @@ def molecule_graphs(n_graphs, seed=0, mean_nodes=23):
         out.append((rng.integers(0, 21, (n, 1)).astype(np.int64), np.ascontiguousarray(ei),
                     rng.normal(size=(1,)).astype(np.float32)))
     return out
+
+
+def init_state_dict(num_features, hidden, num_classes, num_layers=2, seed=0, bias_scale=0.1):
+    """Random-init parameters under the reference's state_dict keys (network.py:11-22): lin.weight glorot-uniform
+    like PyG; biases non-zero so the bias paths are exercised (there are no checkpoints to download)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    dims = [num_features] + [hidden] * num_layers
+    for i in range(num_layers):
+        a = (6.0 / (dims[i] + dims[i + 1])) ** 0.5
+        sd[f"conv.{i}.lin.weight"] = (torch.rand(dims[i + 1], dims[i], generator=g) * 2 - 1) * a
+        sd[f"conv.{i}.bias"] = (torch.rand(dims[i + 1], generator=g) * 2 - 1) * bias_scale
+    a = (1.0 / hidden) ** 0.5
+    sd["lt1.weight"] = (torch.rand(num_classes, hidden, generator=g) * 2 - 1) * a
+    sd["lt1.bias"] = (torch.rand(num_classes, generator=g) * 2 - 1) * a
+    return sd

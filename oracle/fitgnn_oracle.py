@@ -535,3 +535,37 @@ def node_infer_per_query(sd, subgraphs, queries, task="node_cls"):
     with torch.no_grad():
         return torch.stack([fwd(sd, torch.as_tensor(subgraphs[i]["x"]), torch.as_tensor(subgraphs[i]["edge_index"]))[j]
                             for i, j in queries])
+
+
+def subgraphs_from_partition(edge_index, x, part, sub_ids):
+    """Vectorised form of build_subgraphs(mode='none') for a SAMPLE of clusters of one big graph (bench.py's CPU
+    baseline): subgraph i = nodes of cluster sub_ids[i] ascending + induced edges in original edge order,
+    relabelled (utils.py:243-248).  Checked against build_subgraphs in tests/test_oracle_golden.py."""
+    edge_index = np.asarray(edge_index)
+    part = np.asarray(part)
+    sub_ids = np.asarray(sub_ids)
+    k = int(part.max()) + 1
+    rank_of = np.full(k, -1, dtype=np.int64)
+    rank_of[sub_ids] = np.arange(len(sub_ids))
+    node_rank = rank_of[part]
+    nodes = np.nonzero(node_rank >= 0)[0]
+    order = np.lexsort((nodes, node_rank[nodes]))
+    nodes = nodes[order]
+    bounds = np.searchsorted(node_rank[nodes], np.arange(len(sub_ids) + 1))
+    local = np.zeros(part.shape[0], dtype=np.int64)
+    local[nodes] = np.arange(len(nodes)) - bounds[node_rank[nodes]]
+    src, dst = edge_index
+    em = (node_rank[src] >= 0) & (node_rank[src] == node_rank[dst])
+    es, ed, er = src[em], dst[em], node_rank[src[em]]
+    eorder = np.argsort(er, kind="stable")
+    es, ed, er = es[eorder], ed[eorder], er[eorder]
+    ebounds = np.searchsorted(er, np.arange(len(sub_ids) + 1))
+    out = []
+    x = np.asarray(x)
+    for i in range(len(sub_ids)):
+        nd = nodes[bounds[i]:bounds[i + 1]]
+        a, b = ebounds[i], ebounds[i + 1]
+        out.append(dict(x=x[nd].astype(np.float32), edge_index=np.stack([local[es[a:b]], local[ed[a:b]]]),
+                        mask=np.ones(len(nd), dtype=bool), orig_idx=nd, core=nd, n_real=len(nd),
+                        actual_ext=np.zeros(0, dtype=np.int64), cluster_ids=np.zeros(0, dtype=np.int64)))
+    return out
