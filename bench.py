@@ -201,7 +201,7 @@ def main_ours(args):
     shard = ShardedPack(pack, world, rank, args.hidden, F)
     precision = args.precision
     if precision == "auto":
-        precision = os.environ.get("FITGNN_PRECISION", "fp32")
+        precision = os.environ.get("FITGNN_PRECISION", "bf16x3")
     fwd = fg.PackedForward(shard.local, sd, head="log_softmax", rows="core", precision=precision)
     Xd = fwd.pad_features(X)
 

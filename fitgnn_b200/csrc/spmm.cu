@@ -20,7 +20,8 @@ namespace fitgnn {
 constexpr int SPMM_WARPS = 8;
 constexpr int SPMM_THREADS = SPMM_WARPS * 32;
 
-__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+// branchless ELU (MUFU.EX2 path), absolute error <= ~2e-7
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : __expf(x) - 1.0f; }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 

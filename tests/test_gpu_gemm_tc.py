@@ -1,0 +1,64 @@
+"""GPU: the tcgen05/TMA dense transform (FITGNN_GEMM_BF16X3) against an fp64 product of the ORIGINAL fp32 operands.
+Tolerance: the path's 1e-3 relative bound with a 10x margin (bf16 hi/lo split keeps ~2^-17 per operand)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def fg():
+    import fitgnn_b200
+    return fitgnn_b200
+
+
+def run_tc(fg, A, W, b, act=0, head=0):
+    K = A.shape[1]
+    kp = (K + 7) // 8 * 8
+    a = fg.ops.split_bf16(A.to(DEV), ldo=kp)
+    w = fg.ops.split_bf16(W.to(DEV), ldo=kp)
+    out = fg.ops.gemm_bias_act(a, w, None if b is None else b.to(DEV), act, head, precision=fg.ops.GEMM_BF16X3, K=kp)
+    torch.cuda.synchronize()
+    return out.cpu().numpy().astype(np.float64)
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 64, 16), (1, 8, 16), (5, 3, 7), (129, 72, 130), (300, 100, 512), (1000, 512, 512),
+                                   (4097, 1433, 512), (20000, 512, 512), (333, 512, 256), (640, 200, 48), (2000, 64, 96)])
+def test_bf16x3_gemm_matches_fp64(fg, M, K, N):
+    g = torch.Generator().manual_seed(M * 7 + K * 3 + N)
+    A, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    want = (A.double() @ W.double().T + b.double()).numpy()
+    got = run_tc(fg, A, W, b)
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() <= 1e-4 * scale, np.abs(got - want).max() / scale
+    got = run_tc(fg, A, W, b, act=fg.ops.ACT_ELU)
+    want_elu = np.where(want > 0, want, np.expm1(np.minimum(want, 0)))
+    assert np.abs(got - want_elu).max() <= 1e-4 * scale
+
+
+@pytest.mark.parametrize("M,K,N,head", [(777, 512, 47, 1), (1000, 512, 7, 1), (300, 64, 3, 2), (2500, 512, 256, 1), (64, 32, 1, 0)])
+def test_bf16x3_head(fg, M, K, N, head):
+    g = torch.Generator().manual_seed(M + N)
+    A, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    logits = A.double() @ W.double().T + b.double()
+    want = {0: logits, 1: torch.log_softmax(logits, 1), 2: torch.softmax(logits, 1)}[head].numpy()
+    got = run_tc(fg, A, W, b, head=head)
+    assert np.abs(got - want).max() <= 1e-4 * max(1.0, np.abs(want).max())
+
+
+def test_bf16x3_engine_matches_fp32_engine(fg):
+    """Whole forward with tensor-core GEMMs vs exact-fp32 GEMMs on the same pack (both orders of layer 0)."""
+    from oracle import fitgnn_oracle as fo
+    for F in (100, 600):
+        n = 6000
+        ei = fg.synth.powerlaw_graph(n, 15000, seed=1)
+        partition, comps, C_list = fg.synth.neighborhood_partition(ei, n, 0.3, seed=1)
+        X = fg.synth.features(n, F, seed=1).to(DEV)
+        sd = fo.init_state_dict(F, 512, 47, seed=1)
+        pack = fg.build_pack(torch.tensor(ei, device=DEV), torch.tensor(partition.part), partition.k, "extra")
+        a = fg.PackedForward(pack, sd, precision="fp32")(X).cpu().numpy()
+        b = fg.PackedForward(pack, sd, precision="bf16x3")(X).cpu().numpy()
+        assert np.abs(a - b).max() <= 1e-4 * np.abs(a).max(), np.abs(a - b).max()
