@@ -286,7 +286,9 @@ def main_ours(args):
 
     def roofline_of(name):
         r = kernels[name]
-        tensor_bound = name.startswith("gemm") and precision == "bf16x3" and r["TFLOPs"] / tc_peak > r["GBps"] / hbm_peak
+        # bf16x3: three bf16 MMAs per logical product (hi*hi + lo*hi + hi*lo)
+        tensor_bound = (name.startswith("gemm") or name == "head") and precision == "bf16x3" and \
+            3 * r["TFLOPs"] / tc_peak > r["GBps"] / hbm_peak
         if tensor_bound:
             # 3 bf16 MMAs per logical product (hi*hi + hi*lo + lo*hi)
             ach = 3 * r["TFLOPs"]

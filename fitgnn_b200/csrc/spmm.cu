@@ -3,15 +3,16 @@
 // Replaces gcn_norm + MessagePassing.propagate + bias (+F.elu) inside PyG GCNConv, as called at
 // /root/reference/network.py:31-32 (and :60,:90,:126,:161,:197).
 //
-// HBM-bound gather kernel.  One warp owns one output row; every lane keeps NV float4
-// accumulators (NV*128 columns per pass), so a 512-wide row is 4 fully coalesced 512-byte
-// LDG.128 requests per source row.  The column indices / dinv / gid of up to 32 edges are
-// fetched by one coalesced load and broadcast with shuffles; the gather loop is unrolled 4
-// edges deep (up to 16 independent 16-byte loads in flight per lane).  Rows of one subgraph are
-// adjacent in the pack, so the 8 warps of a CTA re-hit each other's source rows in L1/L2.
-// High-degree rows (deg >= HUB_DEG) are split across the 8 warps of a CTA and combined through
-// shared memory by a second kernel instantiation (hub path) so one warp never serialises
-// thousands of gathers.
+// HBM-bound gather kernel.  A group of LPR lanes (8, 16 or 32, chosen from the row width) owns one output row
+// and every lane keeps NV float4 accumulators, so a 512-wide row is 4 fully coalesced 512-byte LDG.128 requests
+// per source row while a 100-wide row uses 8 lanes and a warp works on 4 rows at once.  The packed subgraphs
+// have 2-6 entries per row, so the kernel is latency- not bandwidth-limited unless the dependent chain
+// rowptr -> col -> dinv/gid -> X rows is hidden: each warp walks a run of consecutive rows and software-pipelines
+// it (row info 3 rows ahead, column indices 2 ahead, dinv/gid 1 ahead of the row being gathered), which keeps
+// the 16-byte feature gathers of the current row in flight back to back.  Rows of one subgraph are adjacent in
+// the pack, so neighbouring warps re-hit each other's source rows in L1/L2 and every source row comes from HBM
+// once.  High-degree rows (deg >= hub_deg) are split across the 8 warps of a CTA and reduced through shared
+// memory by the hub kernel so one warp never serialises thousands of gathers.
 #include <cuda_bf16.h>
 #include "common.cuh"
 
@@ -147,6 +148,122 @@ spmm_warp_row_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// software-pipelined kernel: LPR lanes per row, G = 32 / LPR rows per warp per step, rows_per_warp steps
+// ---------------------------------------------------------------------------------------------------------
+struct RowInfo {
+  int beg, end;  // CSR range (end = beg for rows this warp must not produce)
+  float dr;
+};
+
+template <int NV, int LPR, bool SPLIT>
+__global__ void __launch_bounds__(SPMM_THREADS, 3)
+spmm_pipe_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ dinv,
+                 const float* __restrict__ X, int64_t ldx, int nq, const int32_t* __restrict__ src_index,
+                 const float* __restrict__ bias, int act, const int32_t* __restrict__ out_rows, int64_t n_out, void* Y,
+                 void* Ylo, int64_t ldy, int hub_deg, int rows_per_warp) {
+  constexpr int G = 32 / LPR;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (LPR - 1);
+  const int grp = lane / LPR;
+  const int64_t warp_global = (int64_t)blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
+  const int64_t i_base = warp_global * rows_per_warp * G + grp;
+  if (warp_global * rows_per_warp * G >= n_out) return;
+
+  auto load_info = [&](int step) {
+    RowInfo ri{0, 0, 0.f};
+    const int64_t i = i_base + (int64_t)step * G;
+    if (step < rows_per_warp && i < n_out) {
+      const int r = out_rows ? __ldg(out_rows + i) : (int)i;
+      ri.beg = __ldg(rowptr + r);
+      ri.end = __ldg(rowptr + r + 1);
+      ri.dr = __ldg(dinv + r);
+      if (ri.end - ri.beg >= hub_deg) ri.end = ri.beg;  // the hub kernel owns this row
+    }
+    return ri;
+  };
+  auto load_col = [&](const RowInfo& ri, int e0) { return (e0 + sub < ri.end) ? __ldg(col + e0 + sub) : -1; };
+  auto load_w = [&](int c) { return c >= 0 ? __ldg(dinv + c) : 0.f; };
+  auto load_s = [&](int c) { return c >= 0 ? (src_index ? __ldg(src_index + c) : c) : 0; };
+
+  // gather up to LPR edges (one per sub-lane: weight w, source row s) into acc for the column block at q0
+  auto gather_chunk = [&](float4 (&acc)[NV], int cnt, float w, int s, int q0) {
+    const int maxcnt = __reduce_max_sync(FULL, cnt);
+    for (int j = 0; j < maxcnt; j += 2) {
+      float wj[2];
+      const float* pj[2];
+      bool on[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        wj[u] = __shfl_sync(FULL, w, j + u, LPR);
+        const int sj = __shfl_sync(FULL, s, j + u, LPR);
+        pj[u] = X + (int64_t)sj * ldx;
+        on[u] = j + u < cnt;
+      }
+      float4 x[2][NV];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int q = q0 + sub + LPR * v;
+          x[u][v] = (on[u] && q < nq) ? ldg4(pj[u] + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) fma4(acc[v], wj[u], x[u][v]);
+    }
+  };
+
+  RowInfo ia = load_info(0), ib = load_info(1), ic = load_info(2);
+  int ca = load_col(ia, ia.beg), cb = load_col(ib, ib.beg);
+  float wa = load_w(ca);
+  int sa = load_s(ca);
+  for (int step = 0; step < rows_per_warp; ++step) {
+    // prefetch: row info 3 steps ahead, column indices 2 ahead, weights / source rows 1 ahead
+    const RowInfo id = load_info(step + 3);
+    const int cc = load_col(ic, ic.beg);
+    const float wb = load_w(cb);
+    const int sb = load_s(cb);
+
+    const int64_t i = i_base + (int64_t)step * G;
+    const int deg = ia.end - ia.beg;
+    const bool long_row = deg > LPR;
+    for (int q0 = 0; q0 < nq; q0 += LPR * NV) {
+      float4 acc[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      gather_chunk(acc, min(deg, LPR), wa, sa, q0);
+      for (int e0 = ia.beg + LPR; __any_sync(FULL, long_row && e0 < ia.end); e0 += LPR) {
+        const int c = (long_row) ? load_col(ia, e0) : -1;
+        gather_chunk(acc, long_row ? max(0, min(ia.end - e0, LPR)) : 0, load_w(c), load_s(c), q0);
+      }
+      if (deg > 0) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int q = q0 + sub + LPR * v;
+          if (q < nq) {
+            float4 o = make_float4(acc[v].x * ia.dr, acc[v].y * ia.dr, acc[v].z * ia.dr, acc[v].w * ia.dr);
+            if (bias) {
+              const float4 b = ldg4(bias + 4 * q);
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            if (act == FITGNN_ACT_ELU) {
+              o.x = elu1(o.x); o.y = elu1(o.y); o.z = elu1(o.z); o.w = elu1(o.w);
+            }
+            store_row4<SPLIT>(Y, Ylo, i * ldy + 4 * q, o);
+          }
+        }
+      }
+    }
+    ia = ib; ib = ic; ic = id;
+    ca = cb; cb = cc;
+    wa = wb; sa = sb;
+  }
+}
+
 // hub rows: one CTA per row, the 8 warps take interleaved 32-edge chunks, partial sums are
 // reduced through shared memory (NV*128 floats per warp) by warp 0.
 template <int NV, bool SPLIT>
@@ -200,18 +317,22 @@ __global__ void spmm_find_hubs_kernel(const int32_t* __restrict__ rowptr, const 
   }
 }
 
-template <int NV, bool SPLIT>
+template <int NV, int LPR, bool SPLIT>
 static int launch_spmm(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X, int64_t ldx,
                        int nq, const int32_t* src_index, const float* bias, int act, const int32_t* out_rows,
                        int64_t n_out, void* Y, void* Ylo, int64_t ldy, const int32_t* hub_list, int n_hub,
                        int hub_deg, cudaStream_t st) {
-  const int64_t blocks = ceil_div(n_out, SPMM_WARPS);
-  spmm_warp_row_kernel<NV, SPLIT><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(
-      rowptr, col, dinv, X, ldx, nq, src_index, bias, act, out_rows, n_out, Y, Ylo, ldy, hub_deg);
+  constexpr int G = 32 / LPR;
+  // long enough runs per warp for the prefetch pipeline to pay, but keep >= ~4 CTAs per SM on small inputs
+  int rpw = 8;
+  while (rpw > 1 && ceil_div(n_out, (int64_t)G * rpw * SPMM_WARPS) < 148 * 4) rpw >>= 1;
+  const int64_t blocks = ceil_div(n_out, (int64_t)G * rpw * SPMM_WARPS);
+  spmm_pipe_kernel<NV, LPR, SPLIT><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(
+      rowptr, col, dinv, X, ldx, nq, src_index, bias, act, out_rows, n_out, Y, Ylo, ldy, hub_deg, rpw);
   FG_LAUNCH_CHECK();
   if (n_hub > 0) {
-    spmm_hub_kernel<NV, SPLIT><<<(unsigned)n_hub, SPMM_THREADS, 0, st>>>(rowptr, col, dinv, X, ldx, nq, src_index,
-                                                                          bias, act, out_rows, hub_list, Y, Ylo, ldy);
+    spmm_hub_kernel<4, SPLIT><<<(unsigned)n_hub, SPMM_THREADS, 0, st>>>(rowptr, col, dinv, X, ldx, nq, src_index,
+                                                                         bias, act, out_rows, hub_list, Y, Ylo, ldy);
     FG_LAUNCH_CHECK();
   }
   return FITGNN_OK;
@@ -252,15 +373,16 @@ extern "C" int fitgnn_spmm_symnorm_hub(const int32_t* rowptr, const int32_t* col
   const int nq = width / 4;
   const bool split = Y_lo != nullptr;
   if (n_hub == 0) hub_deg = 0x7fffffff;
-#define FG_SPMM(NV)                                                                                              \
-  return split ? launch_spmm<NV, true>(rowptr, col, dinv, X, ldx, nq, src_index, bias, act, out_rows, n_out, Y,   \
-                                       Y_lo, ldy, hub_list, n_hub, hub_deg, st)                                   \
-               : launch_spmm<NV, false>(rowptr, col, dinv, X, ldx, nq, src_index, bias, act, out_rows, n_out, Y,  \
-                                        Y_lo, ldy, hub_list, n_hub, hub_deg, st)
-  if (nq <= 32) { FG_SPMM(1); }
-  if (nq <= 64) { FG_SPMM(2); }
-  if (nq <= 96) { FG_SPMM(3); }
-  FG_SPMM(4);  // nq > 128 loops over 512-column blocks
+#define FG_SPMM(NV, LPR)                                                                                          \
+  return split ? launch_spmm<NV, LPR, true>(rowptr, col, dinv, X, ldx, nq, src_index, bias, act, out_rows, n_out, \
+                                            Y, Y_lo, ldy, hub_list, n_hub, hub_deg, st)                          \
+               : launch_spmm<NV, LPR, false>(rowptr, col, dinv, X, ldx, nq, src_index, bias, act, out_rows,      \
+                                             n_out, Y, Y_lo, ldy, hub_list, n_hub, hub_deg, st)
+  if (nq <= 8) { FG_SPMM(1, 8); }
+  if (nq <= 16) { FG_SPMM(2, 8); }
+  if (nq <= 32) { FG_SPMM(4, 8); }
+  if (nq <= 64) { FG_SPMM(4, 16); }
+  FG_SPMM(4, 32);  // nq > 128 loops over 512-column blocks
 #undef FG_SPMM
 }
 
