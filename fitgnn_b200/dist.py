@@ -63,18 +63,32 @@ class ShardedPack:
             assert torch.equal(self.local.core_gid.long(), self.core_ids[rank])
         self.loads = [float(subgraph_costs(rows[s], nnz[s], hidden, in_features).sum()) for s in self.sub_ids]
 
-    def gather_outputs(self, local_out: torch.Tensor, group=None) -> torch.Tensor:
-        """all-gather(v) of the per-rank core outputs into [N, C] in global node order on every rank."""
-        import torch.distributed as dist
-        C = local_out.shape[1]
-        full = torch.empty(self.n_nodes, C, dtype=local_out.dtype, device=local_out.device)
-        if self.world == 1:
-            full[self.core_ids[0]] = local_out
-            return full
-        send = torch.zeros(self.max_count, C, dtype=local_out.dtype, device=local_out.device)
-        send[: local_out.shape[0]] = local_out
-        recv = torch.empty(self.world, self.max_count, C, dtype=local_out.dtype, device=local_out.device)
-        dist.all_gather_into_tensor(recv.view(-1, C), send, group=group)
+    # ---- all-gather of the core-node outputs -------------------------------------------------------------
+    def gather_buffer(self, C: int, device, dtype=torch.float32) -> torch.Tensor:
+        """[world, max_count, C] buffer; rank r's logits live in slot r (rows beyond counts[r] are padding).  Pass
+        `slot(buf)` as `out=` to the forward so the head kernel writes straight into the buffer (no staging copy)."""
+        return torch.zeros(self.world, self.max_count, C, dtype=dtype, device=device)
+
+    def slot(self, buf: torch.Tensor) -> torch.Tensor:
+        return buf[self.rank, : self.counts[self.rank]]
+
+    def all_gather_(self, buf: torch.Tensor, group=None) -> torch.Tensor:
+        """In-place all-gather: after the call every rank holds every rank's slot."""
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(buf.view(self.world * self.max_count, -1), buf[self.rank], group=group)
+        return buf
+
+    def node_index(self, device) -> torch.Tensor:
+        """row_of_node[v] = flat row of node v in the gather buffer (buf.view(-1, C)[row_of_node] is node order)."""
+        idx = torch.empty(self.n_nodes, dtype=torch.long, device=device)
         for r in range(self.world):
-            full[self.core_ids[r]] = recv[r, : self.counts[r]]
-        return full
+            idx[self.core_ids[r].to(device)] = r * self.max_count + torch.arange(self.counts[r], device=device)
+        return idx
+
+    def gather_outputs(self, local_out: torch.Tensor, group=None) -> torch.Tensor:
+        """Convenience form: all-gather the per-rank core outputs and return [N, C] in global node order."""
+        buf = self.gather_buffer(local_out.shape[1], local_out.device, local_out.dtype)
+        self.slot(buf).copy_(local_out)
+        self.all_gather_(buf, group)
+        return buf.view(self.world * self.max_count, -1)[self.node_index(local_out.device)]

@@ -129,10 +129,11 @@ class PackedForward:
             w = torch.nn.functional.pad(w, (0, kp - w.shape[1]))
         return w.contiguous()
 
-    def _gemm(self, A, W, bias, act, head=ops.HEAD_IDENTITY, N=None, K=None, name="gemm"):
+    def _gemm(self, A, W, bias, act, head=ops.HEAD_IDENTITY, N=None, K=None, name="gemm", out=None):
         self.launches += 1 + (1 if (head != ops.HEAD_IDENTITY and self.precision == ops.GEMM_FP32) else 0)
         M = (A[0] if isinstance(A, tuple) else A).shape[0]
-        return self._timed(name, lambda: ops.gemm_bias_act(A, W, bias, act, head, precision=self.precision, N=N, K=K),
+        return self._timed(name, lambda: ops.gemm_bias_act(A, W, bias, act, head, precision=self.precision, N=N, K=K,
+                                                           out=out),
                            nbytes=4 * (M * K + K * N + M * N), flops=2 * M * K * N)
 
     def _spmm(self, X, width, src_index, bias, act, last, split, name="spmm"):
@@ -155,9 +156,10 @@ class PackedForward:
 
     # -- forward -------------------------------------------------------------------------------
     @torch.no_grad()
-    def __call__(self, X):
+    def __call__(self, X, out=None):
         """X: [n_src, F] fp32 CUDA — every node once (+ one row per cluster for cluster mode, i.e. C·X).
-        Returns [n_out, C] (or the last hidden [n_out, H] when with_head=False), rows in pack order."""
+        Returns [n_out, C] (or the last hidden [n_out, H] when with_head=False), rows in pack order.
+        `out` ([n_out, C] fp32, e.g. this rank's slot of an all-gather buffer) receives the head output in place."""
         p = self.pack
         assert X.is_cuda and X.dtype == torch.float32 and X.shape[0] == p.n_src and X.shape[1] in (self.F, self.Fp)
         bf = self.precision == ops.GEMM_BF16X3
@@ -180,7 +182,7 @@ class PackedForward:
         if bf:
             h = ops.split_bf16(h)
             self.launches += 1
-        return self._gemm(h, self.Wl, self.bl, ops.ACT_NONE, self.head, N=self.C, K=self.H, name="head")
+        return self._gemm(h, self.Wl, self.bl, ops.ACT_NONE, self.head, N=self.C, K=self.H, name="head", out=out)
 
     def scatter_to_nodes(self, out, n_nodes=None):
         """Core-row outputs (pack order) -> [N, C] in global node order."""

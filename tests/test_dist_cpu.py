@@ -1,0 +1,71 @@
+"""CPU (gloo, world_size 2): the sharding + all-gather plumbing of fitgnn_b200.dist, on a pack assembled from the
+oracle's expected arrays (no GPU needed: ShardedPack is index plumbing over torch tensors)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import fitgnn_oracle as fo
+from tests import golden_io as gio
+
+
+def cpu_pack(mode="extra"):
+    from fitgnn_b200.pack import Pack
+    d = gio.load("node_mid")
+    comps = gio.components(d, mode)
+    cos = gio.coarsenings_for_oracle(d, mode, comps)
+    n = int(d["n"])
+    subs = fo.build_subgraphs(d["edge_index"], d["x"], d["y"], comps, cos, mode)
+    w = fo.expected_pack(subs, n, mode)
+    t32 = lambda a: torch.tensor(np.asarray(a), dtype=torch.int32)
+    return Pack(n_rows=len(w["gid"]), nnz=len(w["col"]), n_sub=len(subs), n_core=len(w["core_rows"]), n_src=n, n_nodes=n,
+                mode=mode, rowptr=t32(w["rowptr"]), col=t32(w["col"]), dinv=torch.tensor(w["dinv"]), gid=t32(w["gid"]),
+                sub_ptr=t32(w["sub_ptr"]), core_rows=t32(w["core_rows"]),
+                is_core=torch.tensor(w["is_core"].astype(np.uint8)), mask=torch.tensor(w["mask"].astype(np.uint8)),
+                part=t32(fo.partition_vector(subs, n))), d
+
+
+def test_balanced_bins_and_local_packs():
+    from fitgnn_b200.dist import ShardedPack, balanced_bins
+    costs = torch.tensor([100., 1, 1, 1, 50, 50, 2, 2, 2, 90])
+    bins = balanced_bins(costs, 2)
+    loads = [float(costs[bins == r].sum()) for r in range(2)]
+    assert abs(loads[0] - loads[1]) <= 0.2 * sum(loads)
+    pack, d = cpu_pack()
+    for world in (1, 2, 4):
+        shards = [ShardedPack(pack, world, r, 512, 20) for r in range(world)]
+        ids = torch.cat([s.core_ids[s.rank] for s in shards])
+        assert sorted(ids.tolist()) == list(range(pack.n_nodes))  # every node is core on exactly one rank
+        assert max(shards[0].loads) <= 1.25 * (sum(shards[0].loads) / world) + 1e5
+        for s in shards:
+            lp = s.local
+            # the local pack is a valid block-diagonal CSR: columns stay inside their subgraph
+            rows_sub = torch.repeat_interleave(torch.arange(lp.n_sub), (lp.sub_ptr[1:] - lp.sub_ptr[:-1]).long())
+            erow = torch.repeat_interleave(torch.arange(lp.n_rows), (lp.rowptr[1:] - lp.rowptr[:-1]).long())
+            assert torch.equal(rows_sub[erow], rows_sub[lp.col.long()])
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fitgnn_b200.dist import ShardedPack
+    pack, d = cpu_pack()
+    sp = ShardedPack(pack, world, rank, 512, 20)
+    # stand-in for the forward: "logits" of a node = f(node id), in local pack order
+    ids = sp.local.core_gid.long()
+    local_out = torch.stack([ids.float(), ids.float() * 2 + 1], 1)
+    full = sp.gather_outputs(local_out)
+    want = torch.stack([torch.arange(pack.n_nodes).float(), torch.arange(pack.n_nodes).float() * 2 + 1], 1)
+    ret[rank] = bool(torch.equal(full, want))
+    dist.destroy_process_group()
+
+
+def test_all_gather_world2_gloo():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
