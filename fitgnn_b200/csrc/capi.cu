@@ -19,7 +19,8 @@ int gemm_fp32(const float* A, int64_t lda, const float* W, int64_t ldw, const fl
               int act, float* Y, int64_t ldy, cudaStream_t st);
 int row_softmax(float* Y, int64_t ldy, int64_t M, int N, int head, cudaStream_t st);
 int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi, const void* W_lo, int64_t ldw,
-                const float* bias, int64_t M, int K, int N, int act, int head, float* Y, int64_t ldy, cudaStream_t st);
+                const float* bias, int64_t M, int K, int N, int act, int head, float* Y, void* Y_lo, int64_t ldy,
+                cudaStream_t st);
 
 }  // namespace fitgnn
 
@@ -47,9 +48,10 @@ extern "C" int fitgnn_device_info(int* sm_count, int* cc) {
   return FITGNN_OK;
 }
 
-extern "C" int fitgnn_gemm_bias_act(int precision, const void* A, const void* A_lo, int64_t lda, const void* W,
-                                    const void* W_lo, int64_t ldw, const float* bias, int64_t M, int K, int N, int act,
-                                    int head, float* Y, int64_t ldy, void* stream) {
+extern "C" int fitgnn_gemm_bias_act_split(int precision, const void* A, const void* A_lo, int64_t lda, const void* W,
+                                          const void* W_lo, int64_t ldw, const float* bias, int64_t M, int K, int N,
+                                          int act, int head, void* Yv, void* Y_lo, int64_t ldy, void* stream) {
+  float* Y = static_cast<float*>(Yv);
   FG_REQUIRE(A && W && Y && M >= 0 && K > 0 && N > 0, FITGNN_EINVAL, "gemm: bad arguments (M=%lld K=%d N=%d)",
              (long long)M, K, N);
   FG_REQUIRE(lda >= K && ldw >= K && ldy >= N, FITGNN_EINVAL, "gemm: leading dimension smaller than the extent");
@@ -58,14 +60,22 @@ extern "C" int fitgnn_gemm_bias_act(int precision, const void* A, const void* A_
   if (M == 0) return FITGNN_OK;
   cudaStream_t st = as_stream(stream);
   if (precision == FITGNN_GEMM_FP32) {
+    FG_REQUIRE(!Y_lo, FITGNN_EUNSUP, "gemm: bf16 hi/lo output planes need FITGNN_GEMM_BF16X3");
     FG_TRY(gemm_fp32(static_cast<const float*>(A), lda, static_cast<const float*>(W), ldw, bias, M, K, N, act, Y, ldy,
                      st));
     return row_softmax(Y, ldy, M, N, head, st);
   }
   if (precision == FITGNN_GEMM_BF16X3) {
     FG_REQUIRE(A_lo && W_lo, FITGNN_EINVAL, "gemm: BF16X3 needs the lo planes");
-    return gemm_bf16x3(A, A_lo, lda, W, W_lo, ldw, bias, M, K, N, act, head, Y, ldy, st);
+    return gemm_bf16x3(A, A_lo, lda, W, W_lo, ldw, bias, M, K, N, act, head, Y, Y_lo, ldy, st);
   }
   set_error("gemm: unknown precision %d", precision);
   return FITGNN_EINVAL;
+}
+
+extern "C" int fitgnn_gemm_bias_act(int precision, const void* A, const void* A_lo, int64_t lda, const void* W,
+                                    const void* W_lo, int64_t ldw, const float* bias, int64_t M, int K, int N, int act,
+                                    int head, float* Y, int64_t ldy, void* stream) {
+  return fitgnn_gemm_bias_act_split(precision, A, A_lo, lda, W, W_lo, ldw, bias, M, K, N, act, head, Y, nullptr, ldy,
+                                    stream);
 }

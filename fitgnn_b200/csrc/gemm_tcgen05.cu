@@ -143,8 +143,9 @@ template <int BLOCK_N>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
-                   const __grid_constant__ CUtensorMap map_y, int tma_store, const float* __restrict__ bias, int64_t M,
-                   int K, int N, int act, int head, float* __restrict__ Y, int64_t ldy) {
+                   const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_y_lo,
+                   int tma_store, const float* __restrict__ bias, int64_t M, int K, int N, int act, int head,
+                   float* __restrict__ Y, int64_t ldy) {
   constexpr int STAGES = num_stages(BLOCK_N);
   constexpr uint32_t B_PLANE_BYTES = (uint32_t)BLOCK_N * BLOCK_K * 2;
   constexpr uint32_t STAGE_BYTES = stage_bytes(BLOCK_N);
@@ -311,13 +312,50 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __expf(v[j] - row_max) * inv_sum;
         }
-        if (tma_store) {
+        if (tma_store == 2) {
+          // bf16 hi/lo planes for the next tensor-core GEMM: the 4 KB buffer holds a 32x32 hi box (64-byte rows,
+          // 64B-swizzled: chunk c of row r at c ^ ((r >> 1) & 3)) followed by the matching lo box
+          const int half = (c0 >> 4) & 1;
+          const uint32_t buf = stage_base + (uint32_t)((c0 >> 5) & 1) * EPI_BOX_BYTES;
+          if (half == 0) {
+            if (lane == 0) bulk_wait_read<1>();  // the store group (hi + lo) that last read this buffer has finished reading
+            __syncwarp();
+          }
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
+            hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+          }
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint32_t chunk = (uint32_t)(half * 2 + j) ^ (uint32_t)((lane >> 1) & 3);
+            const uint32_t a = buf + lane * 64 + chunk * 16;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(hi[4 * j]), "r"(hi[4 * j + 1]),
+                         "r"(hi[4 * j + 2]), "r"(hi[4 * j + 3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + EPI_BOX_BYTES / 2), "r"(lo[4 * j]),
+                         "r"(lo[4 * j + 1]), "r"(lo[4 * j + 2]), "r"(lo[4 * j + 3]) : "memory");
+          }
+          if (half == 1 || n0 + c0 + 16 >= N || c0 + 16 >= BLOCK_N) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              const int col = n0 + (c0 & ~31), row = (int)((t / n_tiles) * BLOCK_M) + quad * 32;
+              tma_store_2d(&map_y, buf, col, row);
+              tma_store_2d(&map_y_lo, buf + EPI_BOX_BYTES / 2, col, row);
+              bulk_commit();
+            }
+          }
+        } else if (tma_store) {
           // stage a 32x32 box (row = lane, 128 bytes, 128B-swizzled: 16-byte chunk c of row r sits at chunk c ^ (r & 7)),
           // then one bulk tensor store per box; double-buffered so the next box is staged while this one drains
           const int half = (c0 >> 4) & 1;
           const uint32_t buf = stage_base + (uint32_t)((c0 >> 5) & 1) * EPI_BOX_BYTES;
           if (half == 0) {
-            if (lane == 0) bulk_wait_read<1>();  // the store that last read this buffer has finished reading
+            if (lane == 0) bulk_wait_read<1>();  // the store group that last read this buffer has finished reading
             __syncwarp();
           }
 #pragma unroll
@@ -412,17 +450,40 @@ static int make_store_map(CUtensorMap* map, float* base, int64_t rows, int64_t c
   return FITGNN_OK;
 }
 
+// bf16 output plane [rows, cols] with pitch ld: 32 x 32 store boxes (64-byte rows), 64B swizzle
+static int make_store_map_bf16(CUtensorMap* map, void* base, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn fn = encode_fn();
+  FG_REQUIRE(fn, FITGNN_ECUDA, "gemm_bf16x3: cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {32, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FG_REQUIRE(r == CUDA_SUCCESS, FITGNN_ECUDA, "gemm_bf16x3: cuTensorMapEncodeTiled (bf16 store) failed (%d)", (int)r);
+  return FITGNN_OK;
+}
+
 template <int BLOCK_N>
 static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const void* W_hi, const void* W_lo, int64_t ldw,
-                  const float* bias, int64_t M, int K, int N, int act, int head, float* Y, int64_t ldy, int sms,
-                  cudaStream_t st) {
+                  const float* bias, int64_t M, int K, int N, int act, int head, float* Y, void* Y_lo, int64_t ldy,
+                  int sms, cudaStream_t st) {
   CUtensorMap w_hi, w_lo;
   FG_TRY(make_map(&w_hi, W_hi, N, K, ldw, BLOCK_N));
   FG_TRY(make_map(&w_lo, W_lo, N, K, ldw, BLOCK_N));
-  CUtensorMap y_map;
-  const int tma_store = ((ldy * 4) % 16 == 0 && ((uintptr_t)Y & 15) == 0) ? 1 : 0;
-  if (tma_store) FG_TRY(make_store_map(&y_map, Y, M, N, ldy));
-  else y_map = w_hi;  // unused placeholder
+  CUtensorMap y_map, y_lo_map;
+  int tma_store = ((ldy * 4) % 16 == 0 && ((uintptr_t)Y & 15) == 0) ? 1 : 0;
+  y_map = w_hi;  // placeholders when unused
+  y_lo_map = w_hi;
+  if (Y_lo) {
+    FG_REQUIRE((ldy * 2) % 16 == 0 && ((uintptr_t)Y & 15) == 0 && ((uintptr_t)Y_lo & 15) == 0, FITGNN_EUNSUP,
+               "gemm_bf16x3: split output needs 16-byte aligned planes and a pitch that is a multiple of 8");
+    tma_store = 2;
+    FG_TRY(make_store_map_bf16(&y_map, Y, M, N, ldy));
+    FG_TRY(make_store_map_bf16(&y_lo_map, Y_lo, M, N, ldy));
+  } else if (tma_store) {
+    FG_TRY(make_store_map(&y_map, Y, M, N, ldy));
+  }
   constexpr int STAGES = num_stages(BLOCK_N);
   const size_t smem =
       (size_t)STAGES * stage_bytes(BLOCK_N) + EPI_STAGING_BYTES + 1024 + 8 * (2 * STAGES + 2 * ACC_STAGES) + 16;
@@ -430,7 +491,8 @@ static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const void* 
   FG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t tiles = ceil_div(M, BLOCK_M) * ceil_div(N, BLOCK_N);
   const int grid = (int)(tiles < sms ? tiles : sms);
-  kern<<<grid, THREADS, smem, st>>>(a_hi, a_lo, w_hi, w_lo, y_map, tma_store, bias, M, K, N, act, head, Y, ldy);
+  kern<<<grid, THREADS, smem, st>>>(a_hi, a_lo, w_hi, w_lo, y_map, y_lo_map, tma_store, bias, M, K, N, act, head, Y,
+                                    ldy);
   FG_LAUNCH_CHECK();
   return FITGNN_OK;
 }
@@ -438,8 +500,9 @@ static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const void* 
 }  // namespace tc
 
 int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi, const void* W_lo, int64_t ldw,
-                const float* bias, int64_t M, int K, int N, int act, int head, float* Y, int64_t ldy,
+                const float* bias, int64_t M, int K, int N, int act, int head, float* Y, void* Y_lo, int64_t ldy,
                 cudaStream_t st) {
+  FG_REQUIRE(!Y_lo || head == FITGNN_HEAD_IDENTITY, FITGNN_EUNSUP, "gemm_bf16x3: split output cannot carry a head");
   FG_REQUIRE(head == FITGNN_HEAD_IDENTITY || N <= 256, FITGNN_EUNSUP,
              "gemm_bf16x3: a fused (log-)softmax head needs N <= 256 (got %d)", N);
   FG_REQUIRE(M < (1ll << 31) - 128, FITGNN_ERANGE, "gemm_bf16x3: M exceeds the TMA coordinate range");
@@ -452,7 +515,7 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
   CUtensorMap a_hi, a_lo;
   FG_TRY(tc::make_map(&a_hi, A_hi, M, K, lda, tc::BLOCK_M));
   FG_TRY(tc::make_map(&a_lo, A_lo, M, K, lda, tc::BLOCK_M));
-#define FG_TC(BN) return tc::launch<BN>(a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y, ldy, sms, st)
+#define FG_TC(BN) return tc::launch<BN>(a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y, Y_lo, ldy, sms, st)
   if (N <= 16) FG_TC(16);
   if (N <= 32) FG_TC(32);
   if (N <= 48) FG_TC(48);

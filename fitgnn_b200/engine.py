@@ -129,11 +129,11 @@ class PackedForward:
             w = torch.nn.functional.pad(w, (0, kp - w.shape[1]))
         return w.contiguous()
 
-    def _gemm(self, A, W, bias, act, head=ops.HEAD_IDENTITY, N=None, K=None, name="gemm", out=None):
+    def _gemm(self, A, W, bias, act, head=ops.HEAD_IDENTITY, N=None, K=None, name="gemm", out=None, split_out=False):
         self.launches += 1 + (1 if (head != ops.HEAD_IDENTITY and self.precision == ops.GEMM_FP32) else 0)
         M = (A[0] if isinstance(A, tuple) else A).shape[0]
         return self._timed(name, lambda: ops.gemm_bias_act(A, W, bias, act, head, precision=self.precision, N=N, K=K,
-                                                           out=out),
+                                                           out=out, split_out=split_out),
                            nbytes=4 * (M * K + K * N + M * N), flops=2 * M * K * N)
 
     def _spmm(self, X, width, src_index, bias, act, last, split, name="spmm"):
@@ -176,11 +176,14 @@ class PackedForward:
             else:
                 src, width, idx = (X, self.Fp, p.gid) if i == 0 else (h, self.H, None)
                 A = self._spmm(src, width, idx, None, ops.ACT_NONE, last, split=bf, name=f"spmm{i}")
-                h = self._gemm(A, self.W[i], self.b[i], ops.ACT_ELU, N=self.H, K=width, name=f"gemm{i}")
+                # the last conv layer feeds only the head GEMM: emit its bf16 hi/lo planes straight from the epilogue
+                to_head = bf and last and self.with_head and self.H % 8 == 0
+                h = self._gemm(A, self.W[i], self.b[i], ops.ACT_ELU, N=self.H, K=width, name=f"gemm{i}",
+                               split_out=to_head)
         if not self.with_head:
             return h
-        if bf:
-            h = ops.split_bf16(h)
+        if bf and not isinstance(h, tuple):
+            h = self._timed("split_head", lambda: ops.split_bf16(h), nbytes=8 * h.numel())
             self.launches += 1
         return self._gemm(h, self.Wl, self.bl, ops.ACT_NONE, self.head, N=self.C, K=self.H, name="head", out=out)
 

@@ -101,8 +101,10 @@ def find_hubs(rowptr, out_rows, n_out, hub_deg=256, cap=None):
 
 
 # ----------------------------------------------------------------------------------------- dense
-def gemm_bias_act(A, W, bias=None, act=ACT_NONE, head=HEAD_IDENTITY, out=None, K=None, N=None, precision=GEMM_FP32):
-    """Y = head(act(A·W^T + bias)).  FP32: A [M,K] fp32, W [N,K] fp32.  BF16X3: A=(hi,lo), W=(hi,lo) bf16 planes."""
+def gemm_bias_act(A, W, bias=None, act=ACT_NONE, head=HEAD_IDENTITY, out=None, K=None, N=None, precision=GEMM_FP32,
+                  split_out=False):
+    """Y = head(act(A·W^T + bias)).  FP32: A [M,K] fp32, W [N,K] fp32.  BF16X3: A=(hi,lo), W=(hi,lo) bf16 planes.
+    split_out=True (BF16X3 only) returns the result as bf16 (hi, lo) planes for the next tensor-core GEMM."""
     if precision == GEMM_FP32:
         a_hi, a_lo, w_hi, w_lo = A, None, W, None
         assert A.dtype == torch.float32 and W.dtype == torch.float32
@@ -112,6 +114,14 @@ def gemm_bias_act(A, W, bias=None, act=ACT_NONE, head=HEAD_IDENTITY, out=None, K
     M = a_hi.shape[0]
     K = a_hi.shape[1] if K is None else K
     N = w_hi.shape[0] if N is None else N
+    if split_out:
+        if out is None:
+            out = (torch.empty(M, N, dtype=torch.bfloat16, device=a_hi.device),
+                   torch.empty(M, N, dtype=torch.bfloat16, device=a_hi.device))
+        check(lib().fitgnn_gemm_bias_act_split(precision, ptr(a_hi), ptr(a_lo), a_hi.stride(0), ptr(w_hi), ptr(w_lo),
+                                               w_hi.stride(0), ptr(bias), M, K, N, act, head, ptr(out[0]), ptr(out[1]),
+                                               out[0].stride(0), stream_ptr()))
+        return out
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=a_hi.device)
     check(lib().fitgnn_gemm_bias_act(precision, ptr(a_hi), ptr(a_lo), a_hi.stride(0), ptr(w_hi), ptr(w_lo),

@@ -158,6 +158,12 @@ int fitgnn_gemm_bias_act(int precision, const void* A, const void* A_lo, int64_t
                          const void* W, const void* W_lo, int64_t ldw, const float* bias,
                          int64_t M, int K, int N, int act, int head, float* Y, int64_t ldy,
                          void* stream);
+/* Same, with the result written as bf16 hi/lo planes (Y = hi, Y_lo = lo, both [M, ldy] bf16) ready to be the A
+ * operand of the next FITGNN_GEMM_BF16X3 call; Y_lo == NULL means fp32 output as above.  BF16X3 only, no head. */
+int fitgnn_gemm_bias_act_split(int precision, const void* A, const void* A_lo, int64_t lda,
+                               const void* W, const void* W_lo, int64_t ldw, const float* bias,
+                               int64_t M, int K, int N, int act, int head, void* Y, void* Y_lo,
+                               int64_t ldy, void* stream);
 /* fp32 [rows, cols] (ld = ldx) -> bf16 hi/lo planes [rows, ldo] (columns >= cols zero filled) */
 int fitgnn_split_bf16(const float* X, int64_t ldx, int64_t rows, int cols, void* hi, void* lo,
                       int64_t ldo, void* stream);

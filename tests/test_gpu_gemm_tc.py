@@ -62,3 +62,19 @@ def test_bf16x3_engine_matches_fp32_engine(fg):
         a = fg.PackedForward(pack, sd, precision="fp32")(X).cpu().numpy()
         b = fg.PackedForward(pack, sd, precision="bf16x3")(X).cpu().numpy()
         assert np.abs(a - b).max() <= 1e-4 * np.abs(a).max(), np.abs(a - b).max()
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 64, 64), (1000, 512, 512), (4097, 104, 512), (333, 256, 40), (50, 64, 256)])
+def test_bf16x3_split_output(fg, M, K, N):
+    """Epilogue emitting bf16 hi/lo planes (the A operand of the next tensor-core GEMM): hi + lo == the fp32 result."""
+    g = torch.Generator().manual_seed(M + K + N)
+    A, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    kp = (K + 7) // 8 * 8
+    a = fg.ops.split_bf16(A.to(DEV), ldo=kp)
+    w = fg.ops.split_bf16(W.to(DEV), ldo=kp)
+    ref = fg.ops.gemm_bias_act(a, w, b.to(DEV), fg.ops.ACT_ELU, precision=fg.ops.GEMM_BF16X3, K=kp)
+    hi, lo = fg.ops.gemm_bias_act(a, w, b.to(DEV), fg.ops.ACT_ELU, precision=fg.ops.GEMM_BF16X3, K=kp, split_out=True)
+    torch.cuda.synchronize()
+    want_hi = ref.to(torch.bfloat16)
+    assert torch.equal(hi, want_hi)
+    assert torch.equal(lo, (ref - want_hi.float()).to(torch.bfloat16))
