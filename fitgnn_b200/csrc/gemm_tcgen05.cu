@@ -24,7 +24,8 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                      // bf16 elements = 128 bytes = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int THREADS = 192;
+constexpr int EPI_WARPS = 8;                      // two per TMEM lane quadrant, each taking half of the columns
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr int EPI_WARP0 = 2;
 constexpr int ACC_STAGES = 2;
 constexpr uint32_t A_PLANE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
@@ -124,6 +125,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"
+      "%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -133,7 +148,7 @@ __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : __expf(x) 
 __host__ __device__ constexpr int tmem_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 __host__ __device__ constexpr uint32_t stage_bytes(int block_n) { return 2 * A_PLANE_BYTES + 2 * (uint32_t)block_n * BLOCK_K * 2; }
 constexpr uint32_t EPI_BOX_BYTES = 32 * 32 * 4;             // one 32-row x 32-column fp32 store box (128B rows)
-constexpr uint32_t EPI_STAGING_BYTES = 4 * 2 * EPI_BOX_BYTES;  // 4 epilogue warps x double buffer = 32 KB
+constexpr uint32_t EPI_STAGING_BYTES = EPI_WARPS * EPI_BOX_BYTES;  // one box per epilogue warp = 32 KB
 __host__ __device__ constexpr int num_stages(int block_n) {
   int s = (int)((192 * 1024) / stage_bytes(block_n));
   return s > 8 ? 8 : s;
@@ -179,7 +194,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);  // one arrival per epilogue warp
+      mbar_init(tempty_bar(s), EPI_WARPS);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -252,6 +267,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     const int row_in_tile = quad * 32 + lane;
     const bool vec_ok = (ldy % 4 == 0) && (((uintptr_t)Y & 15) == 0);
     const bool bias_vec = (((uintptr_t)bias & 15) == 0);
+    // column split: 32-column boxes; the second warp of a quadrant takes the upper half of the boxes.  A fused
+    // (log-)softmax needs the whole row in one thread, so the first warp of the quadrant then takes every box.
+    constexpr int N_BOXES = (BLOCK_N + 31) / 32;
+    const int col_group = (warp - EPI_WARP0) >> 2;
+    const int split_at = (head != FITGNN_HEAD_IDENTITY) ? N_BOXES : (N_BOXES + 1) / 2;
+    const int box_beg = col_group == 0 ? 0 : split_at;
+    const int box_end = col_group == 0 ? split_at : N_BOXES;
     int64_t it = 0;
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
       const uint32_t acc = (uint32_t)(it % ACC_STAGES);
@@ -263,7 +285,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
       float* yrow = Y + m * ldy + n0;
       float row_max = -INFINITY, row_sum = 0.f;
-      if (head != FITGNN_HEAD_IDENTITY) {
+      if (head != FITGNN_HEAD_IDENTITY && col_group == 0) {
         // pass 1: online max / sum of exp over the row (the whole row lives in this tile: N <= BLOCK_N)
         for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
           float v[16];
@@ -282,106 +304,94 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         }
       }
       const float log_sum = logf(row_sum), inv_sum = 1.f / row_sum;
-      const uint32_t stage_base = smem_u32(staging) + (uint32_t)(warp - EPI_WARP0) * 2 * EPI_BOX_BYTES;
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+      const uint32_t buf = smem_u32(staging) + (uint32_t)(warp - EPI_WARP0) * EPI_BOX_BYTES;
+      const int m_base = (int)((t / n_tiles) * BLOCK_M) + quad * 32;
+      for (int box = box_beg; box < box_end; ++box) {
+        const int c0 = box * 32;
         if (n0 + c0 >= N) break;
-        float v[16];
-        tmem_ld16(taddr + c0, v);
-        const bool full = n0 + c0 + 16 <= N;  // warp-uniform
-        if (bias) {
-          if (full && bias_vec) {
+        const int box_cols = (BLOCK_N - c0 >= 32) ? 32 : 16;  // BLOCK_N is a multiple of 16
+        float v[32];
+        if (box_cols == 32) {
+          tmem_ld32(taddr + c0, v);
+        } else {
+          float lo16[16];
+          tmem_ld16(taddr + c0, lo16);
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
+          for (int j = 0; j < 16; ++j) { v[j] = lo16[j]; v[16 + j] = 0.f; }
+        }
+        if (bias) {
+          if (n0 + c0 + 32 <= N && bias_vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
               const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
               v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
+            for (int j = 0; j < 32; ++j)
               if (n0 + c0 + j < N) v[j] += __ldg(bias + n0 + c0 + j);
           }
         }
         if (act == FITGNN_ACT_ELU) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = elu1(v[j]);
+          for (int j = 0; j < 32; ++j) v[j] = elu1(v[j]);
         }
         if (head == FITGNN_HEAD_LOG_SOFTMAX) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = v[j] - row_max - log_sum;
+          for (int j = 0; j < 32; ++j) v[j] = v[j] - row_max - log_sum;
         } else if (head == FITGNN_HEAD_SOFTMAX) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __expf(v[j] - row_max) * inv_sum;
+          for (int j = 0; j < 32; ++j) v[j] = __expf(v[j] - row_max) * inv_sum;
         }
-        if (tma_store == 2) {
-          // bf16 hi/lo planes for the next tensor-core GEMM: the 4 KB buffer holds a 32x32 hi box (64-byte rows,
-          // 64B-swizzled: chunk c of row r at c ^ ((r >> 1) & 3)) followed by the matching lo box
-          const int half = (c0 >> 4) & 1;
-          const uint32_t buf = stage_base + (uint32_t)((c0 >> 5) & 1) * EPI_BOX_BYTES;
-          if (half == 0) {
-            if (lane == 0) bulk_wait_read<1>();  // the store group (hi + lo) that last read this buffer has finished reading
-            __syncwarp();
-          }
-          uint32_t hi[8], lo[8];
+        if (tma_store) {
+          // stage the box in this warp's 4 KB buffer (row = lane) and hand it to the TMA unit, which clips at the
+          // tensor bounds.  fp32: 128-byte rows, 16-byte chunk c of row r at c ^ (r & 7).  bf16 hi/lo planes: two
+          // 2 KB boxes of 64-byte rows, chunk c of row r at c ^ ((r >> 1) & 3).
+          if (lane == 0) bulk_wait_read<0>();  // the store(s) that last read this buffer have finished reading
+          __syncwarp();
+          if (tma_store == 2) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
-            const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
-            const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
-            hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-          }
+            for (int j = 0; j < 4; ++j) {
+              uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const uint32_t chunk = (uint32_t)(half * 2 + j) ^ (uint32_t)((lane >> 1) & 3);
-            const uint32_t a = buf + lane * 64 + chunk * 16;
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(hi[4 * j]), "r"(hi[4 * j + 1]),
-                         "r"(hi[4 * j + 2]), "r"(hi[4 * j + 3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + EPI_BOX_BYTES / 2), "r"(lo[4 * j]),
-                         "r"(lo[4 * j + 1]), "r"(lo[4 * j + 2]), "r"(lo[4 * j + 3]) : "memory");
-          }
-          if (half == 1 || n0 + c0 + 16 >= N || c0 + 16 >= BLOCK_N) {
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              const int col = n0 + (c0 & ~31), row = (int)((t / n_tiles) * BLOCK_M) + quad * 32;
-              tma_store_2d(&map_y, buf, col, row);
-              tma_store_2d(&map_y_lo, buf + EPI_BOX_BYTES / 2, col, row);
-              bulk_commit();
+              for (int u = 0; u < 4; ++u) {
+                const float x0 = v[8 * j + 2 * u], x1 = v[8 * j + 2 * u + 1];
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+                const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                hi[u] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                lo[u] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              }
+              const uint32_t a = buf + lane * 64 + ((uint32_t)j ^ (uint32_t)((lane >> 1) & 3)) * 16;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]),
+                           "r"(hi[3]) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + EPI_BOX_BYTES / 2), "r"(lo[0]),
+                           "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t a = buf + lane * 128 + ((uint32_t)j ^ (uint32_t)(lane & 7)) * 16;
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                           "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
             }
           }
-        } else if (tma_store) {
-          // stage a 32x32 box (row = lane, 128 bytes, 128B-swizzled: 16-byte chunk c of row r sits at chunk c ^ (r & 7)),
-          // then one bulk tensor store per box; double-buffered so the next box is staged while this one drains
-          const int half = (c0 >> 4) & 1;
-          const uint32_t buf = stage_base + (uint32_t)((c0 >> 5) & 1) * EPI_BOX_BYTES;
-          if (half == 0) {
-            if (lane == 0) bulk_wait_read<1>();  // the store group that last read this buffer has finished reading
-            __syncwarp();
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t chunk = (uint32_t)(half * 4 + j) ^ (uint32_t)(lane & 7);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(buf + lane * 128 + chunk * 16), "f"(v[4 * j]),
-                         "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
-                         : "memory");
-          }
-          if (half == 1 || n0 + c0 + 16 >= N || c0 + 16 >= BLOCK_N) {
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&map_y, buf, n0 + (c0 & ~31), (int)((t / n_tiles) * BLOCK_M) + quad * 32);
-              bulk_commit();
-            }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&map_y, buf, n0 + c0, m_base);
+            if (tma_store == 2) tma_store_2d(&map_y_lo, buf + EPI_BOX_BYTES / 2, n0 + c0, m_base);
+            bulk_commit();
           }
         } else if (m < M) {
-          if (vec_ok && n0 + c0 + 16 <= N) {
+          if (vec_ok && n0 + c0 + 32 <= N) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4)
+            for (int j = 0; j < 32; j += 4)
               *reinterpret_cast<float4*>(yrow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (n0 + c0 + j < N) yrow[c0 + j] = v[j];
+            for (int j = 0; j < 32; ++j)
+              if (j < box_cols && n0 + c0 + j < N) yrow[c0 + j] = v[j];
           }
         }
       }
