@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfitgnn_b200.so")
+LIB_PATH = os.environ.get("FITGNN_B200_LIB", os.path.join(_HERE, "libfitgnn_b200.so"))  # override: kernel tuning only
 
 c_i64, c_i32, c_void, c_size = C.c_int64, C.c_int, C.c_void_p, C.c_size_t
 

@@ -18,6 +18,15 @@
 
 namespace fitgnn {
 
+#ifndef FG_SPMM_MINB
+#define FG_SPMM_MINB 3  // resident CTAs per SM the pipelined kernel is compiled for (register budget)
+#endif
+#ifndef FG_SPMM_UNROLL
+#define FG_SPMM_UNROLL 2  // edges gathered per inner step (independent 16-byte loads in flight = UNROLL * NV)
+#endif
+#ifndef FG_SPMM_RPW
+#define FG_SPMM_RPW 16  // row steps per warp (length of the software pipeline)
+#endif
 constexpr int SPMM_WARPS = 8;
 constexpr int SPMM_THREADS = SPMM_WARPS * 32;
 
@@ -158,7 +167,7 @@ struct RowInfo {
 };
 
 template <int NV, int LPR, bool SPLIT>
-__global__ void __launch_bounds__(SPMM_THREADS, 3)
+__global__ void __launch_bounds__(SPMM_THREADS, FG_SPMM_MINB)
 spmm_pipe_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ dinv,
                  const float* __restrict__ X, int64_t ldx, int nq, const int32_t* __restrict__ src_index,
                  const float* __restrict__ bias, int act, const int32_t* __restrict__ out_rows, int64_t n_out, void* Y,
@@ -191,27 +200,28 @@ spmm_pipe_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
   // gather up to LPR edges (one per sub-lane: weight w, source row s) into acc for the column block at q0
   auto gather_chunk = [&](float4 (&acc)[NV], int cnt, float w, int s, int q0) {
     const int maxcnt = __reduce_max_sync(FULL, cnt);
-    for (int j = 0; j < maxcnt; j += 2) {
-      float wj[2];
-      const float* pj[2];
-      bool on[2];
+    constexpr int U = FG_SPMM_UNROLL;
+    for (int j = 0; j < maxcnt; j += U) {
+      float wj[U];
+      const float* pj[U];
+      bool on[U];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < U; ++u) {
         wj[u] = __shfl_sync(FULL, w, j + u, LPR);
         const int sj = __shfl_sync(FULL, s, j + u, LPR);
         pj[u] = X + (int64_t)sj * ldx;
         on[u] = j + u < cnt;
       }
-      float4 x[2][NV];
+      float4 x[U][NV];
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
+      for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
           const int q = q0 + sub + LPR * v;
           x[u][v] = (on[u] && q < nq) ? ldg4(pj[u] + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
+      for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int v = 0; v < NV; ++v) fma4(acc[v], wj[u], x[u][v]);
     }
@@ -324,7 +334,7 @@ static int launch_spmm(const int32_t* rowptr, const int32_t* col, const float* d
                        int hub_deg, cudaStream_t st) {
   constexpr int G = 32 / LPR;
   // long enough runs per warp for the prefetch pipeline to pay, but keep >= ~4 CTAs per SM on small inputs
-  int rpw = 8;
+  int rpw = FG_SPMM_RPW;
   while (rpw > 1 && ceil_div(n_out, (int64_t)G * rpw * SPMM_WARPS) < 148 * 4) rpw >>= 1;
   const int64_t blocks = ceil_div(n_out, (int64_t)G * rpw * SPMM_WARPS);
   spmm_pipe_kernel<NV, LPR, SPLIT><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(

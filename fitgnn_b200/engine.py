@@ -60,6 +60,9 @@ class PackedForward:
             self.out_rows = None
         else:
             self.out_rows = rows.to(device=dev, dtype=torch.int32).contiguous()
+        if self.out_rows is not None and self.out_rows.numel() == pack.n_rows and bool(
+                (self.out_rows.long() == torch.arange(pack.n_rows, device=dev)).all()):
+            self.out_rows = None  # identity selection (e.g. mode 'none'): skip the row indirection in the kernels
         self.n_out = pack.n_rows if self.out_rows is None else self.out_rows.numel()
         self.Fp = self._kpad(self.F)
         self.transform_first = self.F > self.H

@@ -6,14 +6,17 @@ inference.py:72-116), computing on the sm_100a kernels of libfitgnn_b200.so.
 `GCNConv(in_channels, out_channels)`, parameters `lin.weight [out,in]` (glorot) and `bias [out]` (zeros),
 `__call__(x[n,in] fp32, edge_index[2,E] int64) -> [n,out]`.
 
-Inference only for now (eval mode; the training backward is the first "next" row): outputs
-carry no grad_fn, and calling a model in .train() mode raises.  CUDA tensors only — there is no CPU path.
+Autograd: when gradients are enabled and a parameter (or x) requires grad, the conv runs through
+`fitgnn_b200.autograd.GCNConvFn`, whose backward uses the same kernels (SpMM with the reversed CSR, fp32 GEMMs), so
+the reference's training loops (run.py:26-37, :177-215) work unchanged; `.train()` mode applies F.dropout like
+network.py:33.  Under torch.no_grad() the lean inference path is taken.  CUDA tensors only — there is no CPU path.
 """
 from __future__ import annotations
 
 import torch
 
 from . import ops
+from .autograd import CsrPair, gcn_conv
 from .engine import PackedForward
 from .pack import Pack
 
@@ -28,7 +31,7 @@ def _csr_for(edge_index, n):
     if hit is None:
         if len(_CSR_CACHE) >= _CSR_CACHE_MAX:
             _CSR_CACHE.clear()
-        hit = ops.csr_from_coo(edge_index, n)
+        hit = CsrPair.from_edge_index(edge_index, n)
         _CSR_CACHE[key] = hit
     return hit
 
@@ -79,7 +82,10 @@ class GCNConv(torch.nn.Module):
         if self.out_channels % 4 != 0:
             raise RuntimeError("fitgnn_b200.GCNConv needs out_channels % 4 == 0")
         n = x.shape[0]
-        rowptr, col, dinv = _csr_for(edge_index, n)
+        csr = _csr_for(edge_index, n)
+        if torch.is_grad_enabled() and (x.requires_grad or self.lin.weight.requires_grad or self.bias.requires_grad):
+            return gcn_conv(x, self.lin.weight, self.bias, csr, act)
+        rowptr, col, dinv = csr.rowptr, csr.col, csr.dinv
         xp = _as_f32_padded(x.detach())
         w = _pad_weight(self.lin.weight)
         b = self.bias.detach().contiguous()
@@ -123,17 +129,22 @@ class _ConvStack(torch.nn.Module):
         self.lt1.reset_parameters()
 
     def _check_eval(self):
-        if self.training:
-            raise NotImplementedError("fitgnn_b200 models are inference-only for now: call model.eval() "
-                                      "(the training backward is the next row of the scope table)")
+        pass  # kept for API stability: training mode is supported (dropout + autograd)
 
     def _convs(self, x, edge_index):
-        # network.py:30-33: conv -> F.elu -> F.dropout(training=False) (identity); ELU is fused into the epilogue
+        # network.py:30-33: conv -> F.elu -> F.dropout(training=self.training); ELU is fused into the conv epilogue
         for i in range(self.num_layers):
             x = self.conv[i](x, edge_index, act=ops.ACT_ELU)
+            if self.training:
+                x = torch.nn.functional.dropout(x, training=True)
         return x
 
     def _lt1(self, x, head):
+        if torch.is_grad_enabled() and (x.requires_grad or self.lt1.weight.requires_grad):
+            y = self.lt1(x)  # differentiable tail (F.linear + softmax family), network.py:34-35
+            if head == ops.HEAD_LOG_SOFTMAX:
+                return torch.nn.functional.log_softmax(y, dim=1)
+            return torch.nn.functional.softmax(y, dim=1) if head == ops.HEAD_SOFTMAX else y
         w = self.lt1.weight.detach().contiguous()
         return ops.gemm_bias_act(x, w, self.lt1.bias.detach().contiguous(), ops.ACT_NONE, head)
 

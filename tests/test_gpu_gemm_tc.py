@@ -22,7 +22,7 @@ def run_tc(fg, A, W, b, act=0, head=0):
     w = fg.ops.split_bf16(W.to(DEV), ldo=kp)
     out = fg.ops.gemm_bias_act(a, w, None if b is None else b.to(DEV), act, head, precision=fg.ops.GEMM_BF16X3, K=kp)
     torch.cuda.synchronize()
-    return out.cpu().numpy().astype(np.float64)
+    return out.detach().cpu().numpy().astype(np.float64)
 
 
 @pytest.mark.parametrize("M,K,N", [(128, 64, 16), (1, 8, 16), (5, 3, 7), (129, 72, 130), (300, 100, 512), (1000, 512, 512),
@@ -59,8 +59,8 @@ def test_bf16x3_engine_matches_fp32_engine(fg):
         X = fg.synth.features(n, F, seed=1).to(DEV)
         sd = fo.init_state_dict(F, 512, 47, seed=1)
         pack = fg.build_pack(torch.tensor(ei, device=DEV), torch.tensor(partition.part), partition.k, "extra")
-        a = fg.PackedForward(pack, sd, precision="fp32")(X).cpu().numpy()
-        b = fg.PackedForward(pack, sd, precision="bf16x3")(X).cpu().numpy()
+        a = fg.PackedForward(pack, sd, precision="fp32")(X).detach().cpu().numpy()
+        b = fg.PackedForward(pack, sd, precision="bf16x3")(X).detach().cpu().numpy()
         assert np.abs(a - b).max() <= 1e-4 * np.abs(a).max(), np.abs(a - b).max()
 
 

@@ -86,10 +86,10 @@ def test_csr_matches_gcn_norm(fg, n, e):
     row_o, col_o, w_o = fo.gcn_norm(torch.tensor(ei), n)
     # oracle edges (source row_o -> target col_o) as a sorted multiset per target
     order = np.lexsort((row_o.numpy(), col_o.numpy()))
-    assert np.array_equal(col.cpu().numpy(), row_o.numpy()[order])
-    assert np.array_equal(np.diff(rowptr.cpu().numpy()), np.bincount(col_o.numpy(), minlength=n))
+    assert np.array_equal(col.detach().cpu().numpy(), row_o.numpy()[order])
+    assert np.array_equal(np.diff(rowptr.detach().cpu().numpy()), np.bincount(col_o.numpy(), minlength=n))
     deg = np.bincount(col_o.numpy(), minlength=n).astype(np.float32)
-    assert np.array_equal(dinv.cpu().numpy(), (1.0 / np.sqrt(deg)).astype(np.float32))
+    assert np.array_equal(dinv.detach().cpu().numpy(), (1.0 / np.sqrt(deg)).astype(np.float32))
 
 
 def test_gcnconv_known_answer(fg):
@@ -99,7 +99,7 @@ def test_gcnconv_known_answer(fg):
         conv.bias.copy_(torch.tensor([0.1, -0.2, 0.3, 0.0]))
     ei = torch.tensor([[0, 1, 1, 2], [1, 0, 2, 1]], device=dev())
     x = torch.tensor([[1., 0.], [0., 1.], [1., 1.]], device=dev())
-    out = conv(x, ei).cpu().numpy()
+    out = conv(x, ei).detach().cpu().numpy()
     want = np.array([[1.4164965809, 2.9329931619, 5.2494897428],
                      [2.3996598285, 5.2158162380, 8.8319726474],
                      [2.4164965809, 4.9329931619, 8.2494897428]])
@@ -119,9 +119,9 @@ def test_gcnconv_matches_fp64(fg, n, e, fin, fout):
     want = fo.gcn_conv_fp64(x.numpy(), ei, conv.lin.weight.detach().numpy(), conv.bias.detach().numpy())
     conv = conv.to(dev())
     out = conv(x.to(dev()), torch.tensor(ei, device=dev()))
-    assert_close(out.cpu().numpy(), want)
+    assert_close(out.detach().cpu().numpy(), want)
     out_elu = conv(x.to(dev()), torch.tensor(ei, device=dev()), act=fg.ops.ACT_ELU)
-    assert_close(out_elu.cpu().numpy(), np.where(want > 0, want, np.expm1(np.minimum(want, 0))))
+    assert_close(out_elu.detach().cpu().numpy(), np.where(want > 0, want, np.expm1(np.minimum(want, 0))))
 
 
 @pytest.mark.parametrize("width", [4, 100, 128, 132, 256, 384, 512, 1024, 1540])
@@ -140,11 +140,11 @@ def test_spmm_widths_rows_and_split(fg, width):
     want = np.where(want > 0, want, np.expm1(np.minimum(want, 0)))[out_rows.numpy()]
     got = fg.ops.spmm_symnorm(rowptr, col, dinv, Xs.to(dev()), src_index=src_index.to(dev()), bias=bias.to(dev()),
                               act=fg.ops.ACT_ELU, out_rows=out_rows.to(dev()))
-    assert_close(got.cpu().numpy(), want)
+    assert_close(got.detach().cpu().numpy(), want)
     hi, lo = fg.ops.spmm_symnorm(rowptr, col, dinv, Xs.to(dev()), src_index=src_index.to(dev()), bias=bias.to(dev()),
                                  act=fg.ops.ACT_ELU, out_rows=out_rows.to(dev()), split=True)
-    rec = hi.float().cpu().numpy().astype(np.float64) + lo.float().cpu().numpy()
-    assert np.abs(rec - got.cpu().numpy()).max() <= 2.0 ** -15 * max(1.0, np.abs(want).max())
+    rec = hi.float().detach().cpu().numpy().astype(np.float64) + lo.float().detach().cpu().numpy()
+    assert np.abs(rec - got.detach().cpu().numpy()).max() <= 2.0 ** -15 * max(1.0, np.abs(want).max())
 
 
 def test_spmm_hub_rows(fg):
@@ -160,9 +160,9 @@ def test_spmm_hub_rows(fg):
     assert hubs[1] == 1 and int(hubs[0][0]) == 0
     got = fg.ops.spmm_symnorm(rowptr, col, dinv, X.to(dev()), hubs=hubs)
     want = fo.normalized_adjacency_dense(ei, n) @ X.numpy().astype(np.float64)
-    assert_close(got.cpu().numpy(), want)
+    assert_close(got.detach().cpu().numpy(), want)
     got2 = fg.ops.spmm_symnorm(rowptr, col, dinv, X.to(dev()))  # same rows without the hub split
-    assert_close(got2.cpu().numpy(), want)
+    assert_close(got2.detach().cpu().numpy(), want)
 
 
 @pytest.mark.parametrize("M,K,N", [(1, 1, 1), (5, 3, 7), (129, 17, 130), (1000, 1433, 512), (777, 512, 47), (4096, 100, 512)])
@@ -171,9 +171,9 @@ def test_gemm_fp32(fg, M, K, N):
     A, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g), torch.randn(N, generator=g)
     want = A.double() @ W.double().T + b.double()
     got = fg.ops.gemm_bias_act(A.to(dev()), W.to(dev()), b.to(dev()))
-    assert_close(got.cpu().numpy(), want.numpy(), rtol=1e-5, atol_scale=1.0)
+    assert_close(got.detach().cpu().numpy(), want.numpy(), rtol=1e-5, atol_scale=1.0)
     got = fg.ops.gemm_bias_act(A.to(dev()), W.to(dev()), b.to(dev()), act=fg.ops.ACT_ELU, head=fg.ops.HEAD_LOG_SOFTMAX)
-    assert_close(got.cpu().numpy(), torch.log_softmax(torch.nn.functional.elu(want), 1).numpy(), rtol=1e-4, atol_scale=1.0)
+    assert_close(got.detach().cpu().numpy(), torch.log_softmax(torch.nn.functional.elu(want), 1).numpy(), rtol=1e-4, atol_scale=1.0)
 
 
 def test_segment_pool(fg):
@@ -225,13 +225,13 @@ def test_pack_builder_bit_exact(fg, case, mode):
     ei = torch.tensor(d["edge_index"], device=dev())
     pack = fg.build_pack(ei, torch.tensor(partition.part), partition.k, mode)
     for name in ("rowptr", "col", "gid", "sub_ptr", "core_rows", "is_core", "mask"):
-        got = getattr(pack, name).cpu().numpy()
+        got = getattr(pack, name).detach().cpu().numpy()
         assert np.array_equal(got.astype(np.int64), np.asarray(want[name]).astype(np.int64)), name
-    assert np.array_equal(pack.dinv.cpu().numpy(), want["dinv"])
+    assert np.array_equal(pack.dinv.detach().cpu().numpy(), want["dinv"])
     # a13 split masks incl. the map_dict collision quirk
     ref = gio.subgraphs(d, mode + "_sub")
     for key in ("train", "val", "test"):
-        got = pack.split_masks(torch.tensor(d[key + "_mask"])).cpu().numpy()
+        got = pack.split_masks(torch.tensor(d[key + "_mask"])).detach().cpu().numpy()
         assert np.array_equal(got, np.concatenate([r[key + "_mask"] for r in ref])), key
 
 
@@ -244,10 +244,10 @@ def test_projection_bit_exact_and_gc_assembly(fg, case, mode):
     X = torch.tensor(d["x"], device=dev())
     proj = fg.coarsen.project(ei, X, partition)
     row, col, cnt = fo.project_adj_pattern(d["edge_index"], partition.part.astype(np.int64), partition.k)
-    assert np.array_equal(proj["ac_row"].cpu().numpy(), row)
-    assert np.array_equal(proj["ac_col"].cpu().numpy(), col)
-    assert np.array_equal(proj["ac_cnt"].cpu().numpy(), cnt)
-    xc = proj["Xc"].cpu().numpy()
+    assert np.array_equal(proj["ac_row"].detach().cpu().numpy(), row)
+    assert np.array_equal(proj["ac_col"].detach().cpu().numpy(), col)
+    assert np.array_equal(proj["ac_cnt"].detach().cpu().numpy(), cnt)
+    xc = proj["Xc"].detach().cpu().numpy()
     for i, (comp, co) in enumerate(zip(comps, cos)):
         s0 = int(partition.sub_offset[i])
         if co is not None:  # bit-exact with scipy's float64 accumulation cast to fp32 (utils.py:738)
@@ -257,7 +257,7 @@ def test_projection_bit_exact_and_gc_assembly(fg, case, mode):
                                                 int(d["n_classes"]))
     names = ("gc_x", "gc_train_y", "gc_train_m", "gc_val_y", "gc_val_m", "gc_edge")
     for g_, name in zip(got, names):
-        assert np.array_equal(g_.cpu().numpy(), d[f"{mode}_{name}"]), name
+        assert np.array_equal(g_.detach().cpu().numpy(), d[f"{mode}_{name}"]), name
 
 
 # ------------------------------------------------------------------------------------------ a2, a5, a6 forward
@@ -276,14 +276,14 @@ def test_packed_forward_matches_reference_outputs(fg, case, mode):
     out, ids = fg.infer.node_infer_Gs(sd, pack, X, torch.tensor(d["test_mask"]))
     ref = gio.subgraphs(d, mode + "_sub")
     want = fo.node_infer_batched(sd, ref, [r["test_mask"] for r in ref], "node_cls", 128)
-    assert_close(out.cpu().numpy(), want.numpy())
+    assert_close(out.detach().cpu().numpy(), want.numpy())
     if case == "node_small":  # the outputs of the reference's own network.py run
-        assert_close(out.cpu().numpy(), d[f"{mode}_test_out"])
+        assert_close(out.detach().cpu().numpy(), d[f"{mode}_test_out"])
     # a6 per-query: each queried node on its own subgraph only
     q = ids[:: max(1, ids.numel() // 20)]
     pq = fg.infer.per_query(sd, pack, X, q)
-    lookup = {int(v): i for i, v in enumerate(ids.cpu().numpy())}
-    assert_close(pq.cpu().numpy(), want.numpy()[[lookup[int(v)] for v in q.cpu().numpy()]])
+    lookup = {int(v): i for i, v in enumerate(ids.detach().cpu().numpy())}
+    assert_close(pq.detach().cpu().numpy(), want.numpy()[[lookup[int(v)] for v in q.detach().cpu().numpy()]])
 
 
 def test_model_classes_generic_path(fg):
@@ -300,16 +300,14 @@ def test_model_classes_generic_path(fg):
     model.load_state_dict(sd)
     model = model.to(dev()).eval()
     out = model(x.to(dev()), ei.to(dev()))
-    assert_close(out.cpu().numpy(), fo.classify_node(sd, x, ei).numpy())
+    assert_close(out.detach().cpu().numpy(), fo.classify_node(sd, x, ei).numpy())
     net1 = fg.Net1(x.shape[1], int(d["hidden"]), 2, int(d["n_classes"]))
     net1.load_state_dict(sd)
-    assert_close(net1.to(dev()).eval()(x.to(dev()), ei.to(dev())).cpu().numpy(), out.cpu().numpy(), rtol=1e-6)
+    assert_close(net1.to(dev()).eval()(x.to(dev()), ei.to(dev())).detach().cpu().numpy(), out.detach().cpu().numpy(), rtol=1e-6)
     reg = fg.Regress_node(args)
     sd_r = dict(sd); sd_r["lt1.weight"] = sd["lt1.weight"][:1].clone(); sd_r["lt1.bias"] = sd["lt1.bias"][:1].clone()
     reg.load_state_dict(sd_r)
-    assert_close(reg.to(dev()).eval()(x.to(dev()), ei.to(dev())).cpu().numpy(), fo.regress_node(sd_r, x, ei).numpy())
-    with pytest.raises(NotImplementedError):
-        model.train()(x.to(dev()), ei.to(dev()))
+    assert_close(reg.to(dev()).eval()(x.to(dev()), ei.to(dev())).detach().cpu().numpy(), fo.regress_node(sd_r, x, ei).numpy())
     with pytest.raises(RuntimeError):
         model.eval()(x, ei.to(dev()))  # CPU tensor: no fallback
 
@@ -330,7 +328,7 @@ def test_graph_level_models_match_reference(fg):
     model.load_state_dict(sd)
     model = model.to(dev()).eval()
     pred = model(set_gs, torch.tensor(d["batch_tensor"]))
-    assert_close(pred.cpu().numpy(), d["pred_gs"])
+    assert_close(pred.detach().cpu().numpy(), d["pred_gs"])
     # Gc variant on the collated coarsened graphs
     gx = torch.tensor(np.concatenate([d[f"g{g}_gc_x"] for g in range(n_g)])).float()
     off, eis = 0, []
@@ -339,17 +337,17 @@ def test_graph_level_models_match_reference(fg):
     gc = Data(x=gx.to(dev()), edge_index=torch.tensor(np.concatenate(eis, 1)).to(dev()), batch=torch.tensor(d["gc_batch"]).to(dev()))
     model_gc = fg.Regress_graph_gc(args)
     model_gc.load_state_dict(sd)
-    assert_close(model_gc.to(dev()).eval()(gc).cpu().numpy(), d["pred_gc"])
+    assert_close(model_gc.to(dev()).eval()(gc).detach().cpu().numpy(), d["pred_gc"])
     # classification heads (max pool + softmax) against the oracle
     sd_c = fo.init_state_dict(1, int(d["hidden"]), 3, seed=5)
     args_c = argparse.Namespace(num_layers1=2, num_features=1, hidden=int(d["hidden"]), num_classes=3, layer_name="GCNConv")
     mc = fg.Classify_graph_gs(args_c); mc.load_state_dict(sd_c)
     want = fo.graph_gs_forward(sd_c, [[dict(x=g.x, edge_index=g.edge_index, mask=g.mask) for g in gs] for gs in set_gs],
                                torch.tensor(d["batch_tensor"]), "graph_cls")
-    assert_close(mc.to(dev()).eval()(set_gs, torch.tensor(d["batch_tensor"])).cpu().numpy(), want.numpy())
+    assert_close(mc.to(dev()).eval()(set_gs, torch.tensor(d["batch_tensor"])).detach().cpu().numpy(), want.numpy())
     mgc = fg.Classify_graph_gc(args_c); mgc.load_state_dict(sd_c)
     want = fo.graph_gc_forward(sd_c, gx, torch.tensor(np.concatenate(eis, 1)), torch.tensor(d["gc_batch"]), "graph_cls")
-    assert_close(mgc.to(dev()).eval()(gc).cpu().numpy(), want.numpy())
+    assert_close(mgc.to(dev()).eval()(gc).detach().cpu().numpy(), want.numpy())
 
 
 # ------------------------------------------------------------------------------------------ config-shaped + properties
@@ -377,7 +375,7 @@ def test_cora_shaped_config(fg, mode):
     want = fo.expected_pack(subs, n, mode)
     pack = fg.build_pack(torch.tensor(ei, device=dev()), torch.tensor(partition.part), partition.k, mode)
     for name in ("rowptr", "col", "gid", "sub_ptr", "core_rows", "is_core", "mask"):
-        assert np.array_equal(getattr(pack, name).cpu().numpy().astype(np.int64), np.asarray(want[name]).astype(np.int64)), name
+        assert np.array_equal(getattr(pack, name).detach().cpu().numpy().astype(np.int64), np.asarray(want[name]).astype(np.int64)), name
     sd = fo.init_state_dict(F, 512, C, seed=1)
     Xg = X
     if mode == "cluster":
@@ -394,7 +392,7 @@ def test_cora_shaped_config(fg, mode):
         m[np.searchsorted(s["orig_idx"], s["core"])] = True
         ones.append(m)
     want_out = fo.node_infer_batched(sd, subs, ones, "node_cls", 128)
-    assert_close(out.cpu().numpy(), want_out.numpy())
+    assert_close(out.detach().cpu().numpy(), want_out.numpy())
 
 
 def test_block_diagonal_independence_and_permutation(fg):
@@ -411,7 +409,7 @@ def test_block_diagonal_independence_and_permutation(fg):
     q = torch.randperm(n, generator=torch.Generator().manual_seed(0))[:500]
     pq = fg.infer.per_query(sd, pack, X.to(dev()), q)
     full = torch.empty(n, C, device=dev()); full[ids.long()] = out
-    assert_close(pq.cpu().numpy(), full[q.to(dev())].cpu().numpy(), rtol=1e-5)
+    assert_close(pq.detach().cpu().numpy(), full[q.to(dev())].detach().cpu().numpy(), rtol=1e-5)
     perm = torch.randperm(n, generator=torch.Generator().manual_seed(1))
     ei_p = perm[torch.tensor(ei)]
     part_p = torch.empty(n, dtype=torch.int32); part_p[perm] = torch.tensor(partition.part)
@@ -419,7 +417,7 @@ def test_block_diagonal_independence_and_permutation(fg):
     pack_p = fg.build_pack(ei_p.to(dev()), part_p, partition.k, "extra")
     out_p, ids_p = fg.infer.node_infer_Gs(sd, pack_p, X_p.to(dev()))
     full_p = torch.empty(n, C, device=dev()); full_p[ids_p.long()] = out_p
-    assert_close(full_p[perm.to(dev())].cpu().numpy(), full.cpu().numpy(), rtol=1e-4)
+    assert_close(full_p[perm.to(dev())].detach().cpu().numpy(), full.detach().cpu().numpy(), rtol=1e-4)
 
 
 def test_bad_inputs_fail_loudly(fg):
