@@ -278,7 +278,7 @@ def extract_components(edge_index, n):
     return sorted(comps, key=lambda c: len(c), reverse=True)
 
 
-def build_subgraphs(edge_index, x, y, comps, coarsenings, mode):
+def build_subgraphs(edge_index, x, y, comps, coarsenings, mode, only=None):
     """coarsening_classification utils.py:143-374 (node_cls branch :186-267; the other task branch :269-350
     and coarsening_regression :417-584 are the same body).
 
@@ -289,7 +289,8 @@ def build_subgraphs(edge_index, x, y, comps, coarsenings, mode):
     mode:        'none' | 'extra' | 'cluster'   (args.extra_node / args.cluster_node after arg_correction
                  main.py:117-121)
     Returns list of dicts: x, edge_index, y, mask, orig_idx, actual_ext, map_dict, n_real, cluster_ids
-    (cluster_ids = global subgraph index of every cluster node, which the reference leaves implicit)."""
+    (cluster_ids = global subgraph index of every cluster node, which the reference leaves implicit).
+    only: optional set of subgraph_list indices to build (the others become None) — for sampling big graphs."""
     edge_index = np.asarray(edge_index)
     n = x.shape[0]
     adjl = _Adj(edge_index, n)
@@ -308,6 +309,9 @@ def build_subgraphs(edge_index, x, y, comps, coarsenings, mode):
                 meta_node_2_node.setdefault(int(part[comp_node]), []).append(int(comp[comp_node]))
             meta_order = {m: i for i, m in enumerate(meta_node_2_node.keys())}
             for key, value in meta_node_2_node.items():
+                if only is not None and len(out) not in only:
+                    out.append(None)
+                    continue
                 value = np.sort(np.asarray(value, dtype=np.int64))
                 num_nodes = len(value)
                 actual_ext = np.zeros(0, dtype=np.int64)
@@ -368,6 +372,9 @@ def build_subgraphs(edge_index, x, y, comps, coarsenings, mode):
                                 cluster_ids=np.asarray(cluster_ids, dtype=np.int64)))
         else:  # utils.py:352-368
             nodes = comp
+            if only is not None and len(out) not in only:
+                out.append(None)
+                continue
             out.append(dict(x=x[nodes].astype(np.float32), edge_index=induced_subgraph(edge_index, nodes, n),
                             y=y[nodes], mask=np.array([True]), orig_idx=nodes, actual_ext=np.zeros(0, dtype=np.int64),
                             map_dict={int(nodes[0]): 0}, n_real=1, core=nodes,

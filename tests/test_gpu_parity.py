@@ -428,3 +428,63 @@ def test_bad_inputs_fail_loudly(fg):
         fg.build_pack(torch.tensor([[0, 1], [1, 0]], device=dev()), torch.tensor([0, 7], dtype=torch.int32), 2, "none")
     with pytest.raises(fg._lib.FitgnnError):
         fg.ops.gemm_bias_act(torch.zeros(2, 3), torch.zeros(4, 3))  # CPU tensors
+
+
+@pytest.mark.parametrize("mode", ["extra", "cluster"])
+def test_physics_shaped_config_sampled(fg, mode):
+    """configs[2]: Coauthor-Physics-shaped synthetic (34,493 nodes, 247,962 undirected edges, 8,415 features, ratio 0.1,
+    many small subgraphs + a few huge ones).  Whole-pack invariants, then a sample of subgraphs bit-exact against the
+    oracle builder and their logits against the oracle forward."""
+    n, e_und, F, C, ratio = fg.synth.SHAPES["physics"]
+    ei = fg.synth.powerlaw_graph(n, e_und, seed=2)
+    partition, comps, C_list = fg.synth.neighborhood_partition(ei, n, ratio, seed=2)
+    eid = torch.tensor(ei, device=dev())
+    X = fg.synth.features(n, F, seed=2, kind="bow", device=dev())
+    proj = fg.coarsen.project(eid, X, partition)
+    pack = fg.build_pack(eid, torch.tensor(partition.part), partition.k, mode, proj["ac_rowptr"], proj["ac_col"])
+    # invariants: every node is core exactly once; rows of a subgraph stay inside it; the CSR is symmetric
+    assert sorted(pack.core_gid.cpu().tolist()) == list(range(n))
+    sp = pack.sub_ptr.long()
+    rows_sub = torch.repeat_interleave(torch.arange(pack.n_sub, device=dev()), sp[1:] - sp[:-1])
+    deg = (pack.rowptr[1:] - pack.rowptr[:-1]).long()
+    erow = torch.repeat_interleave(torch.arange(pack.n_rows, device=dev()), deg)
+    assert torch.equal(rows_sub[erow], rows_sub[pack.col.long()])
+    fwd_keys = erow * pack.n_rows + pack.col.long()
+    bwd_keys = torch.sort(pack.col.long() * pack.n_rows + erow).values
+    assert torch.equal(fwd_keys, bwd_keys)  # fwd_keys are already sorted (CSR order)
+    assert torch.equal(pack.dinv, 1.0 / torch.sqrt(deg.float()))
+    # sample: the 3 biggest subgraphs + 40 random ones
+    sizes = (sp[1:] - sp[:-1]).cpu().numpy()
+    rng = np.random.default_rng(0)
+    ids = np.unique(np.concatenate([np.argsort(-sizes)[:3], rng.choice(pack.n_sub, 40, replace=False)]))
+    import scipy.sparse as sp_
+    xc = proj["Xc"].cpu().numpy()
+    cos = []
+    for i, (comp, Cm) in enumerate(zip(comps, C_list)):
+        if Cm is None:
+            cos.append(None); continue
+        part_c, _ = fo.partition_of(Cm)
+        s0, s1 = int(partition.sub_offset[i]), int(partition.sub_offset[i + 1])
+        r0, r1 = int(proj["ac_rowptr"][s0]), int(proj["ac_rowptr"][s1])
+        adj = sp_.csr_matrix((np.ones(r1 - r0, dtype=bool), (proj["ac_row"][r0:r1].cpu().numpy() - s0,
+                                                               proj["ac_col"][r0:r1].cpu().numpy() - s0)), shape=(s1 - s0, s1 - s0))
+        cos.append(dict(part=part_c, CX=xc[s0:s1], adj=adj))
+    Xn = X.cpu().numpy()
+    subs = fo.build_subgraphs(ei, Xn, np.zeros(n, dtype=np.int64), comps, cos, mode, only=set(ids.tolist()))
+    small = fg.infer.select_subgraphs(pack, torch.tensor(ids))
+    want = fo.expected_pack([subs[i] for i in ids], n, mode)
+    for name in ("rowptr", "col", "sub_ptr", "core_rows", "is_core", "mask"):
+        assert np.array_equal(getattr(small, name).cpu().numpy().astype(np.int64), np.asarray(want[name]).astype(np.int64)), name
+    gid_want = want["gid"].copy()
+    assert np.array_equal(small.gid.cpu().numpy().astype(np.int64), gid_want)
+    # logits of the sampled subgraphs (bf16x3 tensor-core GEMMs, transform-first on the de-duplicated rows)
+    sd = fo.init_state_dict(F, 512, C, seed=4)
+    Xg = torch.cat([X, proj["Xc"]], 0) if mode == "cluster" else X
+    out = fg.PackedForward(small, sd, precision="bf16x3")(Xg).detach().cpu().numpy()
+    sel = []
+    for i in ids:
+        m = np.zeros(subs[i]["x"].shape[0], dtype=bool)
+        m[np.searchsorted(subs[i]["orig_idx"], subs[i]["core"])] = True
+        sel.append(m)
+    want_out = fo.node_infer_batched(sd, [subs[i] for i in ids], sel, "node_cls", 128).numpy()
+    assert_close(out, want_out)
