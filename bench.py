@@ -44,6 +44,7 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--seed", type=int, default=0)
+    p.add_argument("--chunks", type=int, default=1, help="N>1: chunks per rank; chunk c's all-gather overlaps chunk c+1")
     return p.parse_args()
 
 
@@ -198,20 +199,30 @@ def main_ours(args):
     del ei
     if args.mode == "cluster":
         raise SystemExit("bench: cluster mode needs the C·X rows appended to X; use tests for that mode")
-    shard = ShardedPack(pack, world, rank, args.hidden, F)
+    n_chunks = 1 if world == 1 else args.chunks
+    shard = ShardedPack(pack, world, rank, args.hidden, F, n_chunks=n_chunks)
     precision = args.precision
     if precision == "auto":
         precision = os.environ.get("FITGNN_PRECISION", "bf16x3")
-    fwd = fg.PackedForward(shard.local, sd, head="log_softmax", rows="core", precision=precision)
+    fwds = [fg.PackedForward(lp, sd, head="log_softmax", rows="core", precision=precision) for lp in shard.locals]
+    fwd = fwds[0]
     Xd = fwd.pad_features(X)
 
     gbuf = shard.gather_buffer(C, device) if world > 1 else None
 
+    def run_chunks(Xin, buf):
+        """forward of every local chunk; chunk c's all-gather is enqueued asynchronously (NCCL stream) right after its
+        head kernel, so it overlaps the compute of chunk c+1; the current stream then waits for all of them."""
+        works = []
+        for c, f in enumerate(fwds):
+            f(Xin, out=shard.slot(buf, c))  # the head kernel writes straight into this rank's slot
+            works.append(shard.all_gather_(buf, c, async_op=True))
+        for w in works:
+            w.wait()
+        return buf
+
     def step():
-        if world > 1:  # the head kernel writes this rank's logits straight into its slot of the gather buffer
-            fwd(Xd, out=shard.slot(gbuf))
-            return shard.all_gather_(gbuf)
-        return fwd(Xd)
+        return run_chunks(Xd, gbuf) if world > 1 else fwd(Xd)
 
     def barrier():
         if world > 1:
@@ -225,8 +236,9 @@ def main_ours(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    fwd.enable_profile(True)
-    launches0 = fwd.launches
+    for f in fwds:
+        f.enable_profile(True)
+    launches0 = sum(f.launches for f in fwds)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -235,9 +247,19 @@ def main_ours(args):
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1) / args.steps
-    gpu_launches = fwd.launches - launches0
-    prof = fwd.profile_summary()
-    fwd.enable_profile(False)
+    gpu_launches = sum(f.launches for f in fwds) - launches0
+    prof = {}
+    for f in fwds:  # per-kernel time summed over this rank's chunks (ms per step)
+        for name, r in f.profile_summary().items():
+            agg = prof.setdefault(name, dict(ms=0.0, launches=0, bytes=0, flops=0))
+            agg["ms"] += r["ms"]; agg["launches"] += r["launches"]; agg["bytes"] += r["bytes"]; agg["flops"] += r["flops"]
+        f.enable_profile(False)
+    rank_kernel_ms = None
+    if world > 1:
+        fwd_ms = torch.tensor([sum(v["ms"] for v in prof.values())], device=device, dtype=torch.float64)
+        all_fwd = [torch.zeros_like(fwd_ms) for _ in range(world)]
+        dist.all_gather(all_fwd, fwd_ms)
+        rank_kernel_ms = [float(x.item()) for x in all_fwd]
     t = torch.tensor([ms], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -250,7 +272,7 @@ def main_ours(args):
     e2e = None
     if not args.no_e2e:
         X_host = Xd.cpu().pin_memory()  # K-padded rows (104 floats) so the H2D copy is one contiguous DMA
-        n_loc = fwd.n_out
+        n_loc = sum(f.n_out for f in fwds)
         NB = 2
         X_in = [torch.zeros_like(Xd) for _ in range(NB)]
         o_dev = [shard.gather_buffer(C, device) if world > 1 else torch.empty(n_loc, C, device=device) for _ in range(NB)]
@@ -271,15 +293,20 @@ def main_ours(args):
                     s_cmp.wait_event(ev_in[b])
                     s_cmp.wait_event(ev_out[b])  # the D2H that last read o_dev[b] is done
                     if world > 1:
-                        fwd(X_in[b], out=shard.slot(o_dev[b]))
-                        shard.all_gather_(o_dev[b])
+                        run_chunks(X_in[b], o_dev[b])
                     else:
                         fwd(X_in[b], out=o_dev[b])
                     ev_cmp[b].record(s_cmp)
                 with torch.cuda.stream(s_out):
                     s_out.wait_event(ev_cmp[b])
-                    src = shard.slot(o_dev[b]) if world > 1 else o_dev[b]
-                    o_host[b].copy_(src, non_blocking=True)
+                    if world > 1:  # this rank's own slice of the logits, chunk by chunk
+                        off = 0
+                        for c in range(n_chunks):
+                            sl = shard.slot(o_dev[b], c)
+                            o_host[b][off: off + sl.shape[0]].copy_(sl, non_blocking=True)
+                            off += sl.shape[0]
+                    else:
+                        o_host[b].copy_(o_dev[b], non_blocking=True)
                     ev_out[b].record(s_out)
 
         e2e_run(2)
@@ -313,6 +340,7 @@ def main_ours(args):
         tfs = r["flops"] / (r["ms"] * 1e-3) / 1e12 if r["flops"] else 0.0
         kernels[name] = {"ms": r["ms"], "algo_GB": r["bytes"] / 1e9, "GBps": gbs, "TFLOPs": tfs,
                          "share": r["ms"] / max(1e-9, sum(x["ms"] for x in prof.values()))}
+
     dom = max(kernels, key=lambda k_: kernels[k_]["ms"])
 
     def roofline_of(name):
@@ -337,7 +365,10 @@ def main_ours(args):
             "config": config_of(args, n, F, C, k), "roofline": roofline_of(dom), "roofline_spmm": roofline_of(spmm_main),
             "kernels": kernels, "gpu_launches": gpu_launches, "clocks": sampler.summary(),
             "pack": {"rows": pack.n_rows, "nnz": pack.nnz, "subgraphs": pack.n_sub, "build_ms": pack_build_ms,
-                     "bytes": pack.nbytes(), "rank_loads": shard.loads}}
+                     "bytes": pack.nbytes(), "rank_loads": shard.loads},
+            "multi_gpu": {"chunks_per_rank": n_chunks, "rank_kernel_ms": rank_kernel_ms,
+                          "all_gather_bytes": int(n * C * 4) if world > 1 else 0,
+                          "exposed_ms": (ms - max(rank_kernel_ms)) if rank_kernel_ms else 0.0}}
     if e2e:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:

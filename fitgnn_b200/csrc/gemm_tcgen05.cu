@@ -160,8 +160,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                    const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_y_lo,
                    int tma_store, const float* __restrict__ bias, int64_t M, int K, int N, int act, int head,
-                   float* __restrict__ Y, int64_t ldy) {
+                   float* __restrict__ Y, int64_t ldy, int w_stationary, int n_stages) {
   constexpr int STAGES = num_stages(BLOCK_N);
+  constexpr int MAX_STAGES = 8;
   constexpr uint32_t B_PLANE_BYTES = (uint32_t)BLOCK_N * BLOCK_K * 2;
   constexpr uint32_t STAGE_BYTES = stage_bytes(BLOCK_N);
   constexpr int TMEM_COLS = tmem_cols(ACC_STAGES * BLOCK_N);
@@ -171,27 +172,40 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B atoms
-  uint8_t* staging = smem + (size_t)STAGES * STAGE_BYTES;  // 1024-aligned: STAGE_BYTES is a multiple of 1024
+  const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  // Two smem plans.  Streaming: n_stages x {A_hi, A_lo, W_hi, W_lo}.  W-stationary (small K): the CTA keeps its
+  // N-block of the weights resident for the whole kernel (k_blocks x {W_hi, W_lo}) and only A streams, which removes
+  // the per-tile weight re-load from L2 that otherwise dominates the SM<->L2 traffic of a small-K transform.
+  const uint32_t w_region_bytes = w_stationary ? (uint32_t)k_blocks * 2u * B_PLANE_BYTES : 0u;
+  const uint32_t stage_bytes_rt = w_stationary ? 2u * A_PLANE_BYTES : STAGE_BYTES;
+  uint8_t* staging = smem + w_region_bytes + (size_t)n_stages * stage_bytes_rt;  // multiples of 1024 throughout
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + EPI_STAGING_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES);
-  const uint32_t smem_base = smem_u32(smem);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 2 * ACC_STAGES + 1);
+  const uint32_t smem_base = smem_u32(smem) + w_region_bytes;  // first streaming stage
+  const uint32_t w_base = smem_u32(smem);                       // resident weights (W-stationary)
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + ACC_STAGES + s); };
+  const uint32_t wfull_bar = bar_base + 8u * (2 * MAX_STAGES + 2 * ACC_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
   const int64_t m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
   const int64_t tiles = m_tiles * n_tiles;
-  const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  // tile walk: streaming = round robin over (m, n) with n fastest; W-stationary = this CTA's n-block is fixed
+  // (blockIdx % n_tiles) and it strides over the m-blocks
+  const int ctas_per_n = (int)gridDim.x / n_tiles;
+  const int64_t t_first = w_stationary ? (int64_t)(blockIdx.x / n_tiles) * n_tiles + (blockIdx.x % n_tiles) : blockIdx.x;
+  const int64_t t_step = w_stationary ? (int64_t)ctas_per_n * n_tiles : gridDim.x;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < n_stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
+    mbar_init(wfull_bar, 1);
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), EPI_WARPS);  // one arrival per epilogue warp
@@ -213,18 +227,28 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      if (w_stationary && t_first < tiles) {
+        const int n0 = (int)(t_first % n_tiles) * BLOCK_N;
+        mbar_arrive_expect_tx(wfull_bar, w_region_bytes);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          tma_load_2d(w_base + kb * 2 * B_PLANE_BYTES, &map_w_hi, wfull_bar, kb * BLOCK_K, n0);
+          tma_load_2d(w_base + kb * 2 * B_PLANE_BYTES + B_PLANE_BYTES, &map_w_lo, wfull_bar, kb * BLOCK_K, n0);
+        }
+      }
+      for (int64_t t = t_first; t < tiles; t += t_step) {
         const int m0 = (int)(t / n_tiles) * BLOCK_M;
         const int n0 = (int)(t % n_tiles) * BLOCK_N;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t dst = smem_base + stage * STAGE_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+          const uint32_t dst = smem_base + stage * stage_bytes_rt;
+          mbar_arrive_expect_tx(full_bar(stage), stage_bytes_rt);
           tma_load_2d(dst, &map_a_hi, full_bar(stage), kb * BLOCK_K, m0);
           tma_load_2d(dst + A_PLANE_BYTES, &map_a_lo, full_bar(stage), kb * BLOCK_K, m0);
-          tma_load_2d(dst + 2 * A_PLANE_BYTES, &map_w_hi, full_bar(stage), kb * BLOCK_K, n0);
-          tma_load_2d(dst + 2 * A_PLANE_BYTES + B_PLANE_BYTES, &map_w_lo, full_bar(stage), kb * BLOCK_K, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (!w_stationary) {
+            tma_load_2d(dst + 2 * A_PLANE_BYTES, &map_w_hi, full_bar(stage), kb * BLOCK_K, n0);
+            tma_load_2d(dst + 2 * A_PLANE_BYTES + B_PLANE_BYTES, &map_w_lo, full_bar(stage), kb * BLOCK_K, n0);
+          }
+          if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -233,7 +257,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       int64_t it = 0;
-      for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+      if (w_stationary && t_first < tiles) mbar_wait(wfull_bar, 0);  // resident weights have landed
+      for (int64_t t = t_first; t < tiles; t += t_step, ++it) {
         const uint32_t acc = (uint32_t)(it % ACC_STAGES);
         const uint32_t acc_phase = (uint32_t)((it / ACC_STAGES) & 1);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
@@ -242,11 +267,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(full_bar(stage), phase);  // TMA bytes have landed
           fence_after();
-          const uint32_t a_hi = smem_base + stage * STAGE_BYTES;
+          const uint32_t a_hi = smem_base + stage * stage_bytes_rt;
+          const uint32_t w_hi = w_stationary ? w_base + kb * 2 * B_PLANE_BYTES : a_hi + 2 * A_PLANE_BYTES;
           const uint64_t d_a_hi = umma_desc_sw128(a_hi);
           const uint64_t d_a_lo = umma_desc_sw128(a_hi + A_PLANE_BYTES);
-          const uint64_t d_w_hi = umma_desc_sw128(a_hi + 2 * A_PLANE_BYTES);
-          const uint64_t d_w_lo = umma_desc_sw128(a_hi + 2 * A_PLANE_BYTES + B_PLANE_BYTES);
+          const uint64_t d_w_hi = umma_desc_sw128(w_hi);
+          const uint64_t d_w_lo = umma_desc_sw128(w_hi + B_PLANE_BYTES);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);  // +32 bytes per K=16 step inside the swizzle row
@@ -256,7 +282,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           }
           umma_commit(empty_bar(stage));  // smem stage is free once these MMAs retire
           if (kb == k_blocks - 1) umma_commit(tfull_bar(acc));
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -275,7 +301,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     const int box_beg = col_group == 0 ? 0 : split_at;
     const int box_end = col_group == 0 ? split_at : N_BOXES;
     int64_t it = 0;
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+    for (int64_t t = t_first; t < tiles; t += t_step, ++it) {
       const uint32_t acc = (uint32_t)(it % ACC_STAGES);
       const uint32_t acc_phase = (uint32_t)((it / ACC_STAGES) & 1);
       const int64_t m = (t / n_tiles) * BLOCK_M + row_in_tile;
@@ -494,15 +520,29 @@ static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const void* 
   } else if (tma_store) {
     FG_TRY(make_store_map(&y_map, Y, M, N, ldy));
   }
-  constexpr int STAGES = num_stages(BLOCK_N);
-  const size_t smem =
-      (size_t)STAGES * stage_bytes(BLOCK_N) + EPI_STAGING_BYTES + 1024 + 8 * (2 * STAGES + 2 * ACC_STAGES) + 16;
+  constexpr size_t SMEM_LIMIT = 227 * 1024;
+  constexpr size_t FIXED = EPI_STAGING_BYTES + 1024 + 8 * (2 * 8 + 2 * ACC_STAGES + 1) + 16;
+  const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  const int n_tiles = (int)ceil_div(N, BLOCK_N);
+  const int64_t m_tiles = ceil_div(M, BLOCK_M);
+  const int64_t tiles = m_tiles * n_tiles;
+  int n_stages = num_stages(BLOCK_N);
+  int grid = (int)(tiles < sms ? tiles : sms);
+  size_t smem = (size_t)n_stages * stage_bytes(BLOCK_N) + FIXED;
+  // W-stationary plan: worth it when the resident weights fit beside >= 2 A stages and every CTA gets several m-blocks
+  int w_stationary = 0;
+  const size_t w_bytes = (size_t)k_blocks * 2 * BLOCK_N * BLOCK_K * 2;
+  if (w_bytes + 2 * 2 * A_PLANE_BYTES + FIXED <= SMEM_LIMIT && sms >= n_tiles && m_tiles >= 4 * (sms / n_tiles)) {
+    w_stationary = 1;
+    n_stages = (int)((SMEM_LIMIT - FIXED - w_bytes) / (2 * A_PLANE_BYTES));
+    if (n_stages > 8) n_stages = 8;
+    grid = (sms / n_tiles) * n_tiles;
+    smem = w_bytes + (size_t)n_stages * 2 * A_PLANE_BYTES + FIXED;
+  }
   auto kern = gemm_bf16x3_kernel<BLOCK_N>;
   FG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t tiles = ceil_div(M, BLOCK_M) * ceil_div(N, BLOCK_N);
-  const int grid = (int)(tiles < sms ? tiles : sms);
   kern<<<grid, THREADS, smem, st>>>(a_hi, a_lo, w_hi, w_lo, y_map, y_lo_map, tma_store, bias, M, K, N, act, head, Y,
-                                    ldy);
+                                    ldy, w_stationary, n_stages);
   FG_LAUNCH_CHECK();
   return FITGNN_OK;
 }

@@ -39,56 +39,73 @@ def pack_subgraph_sizes(pack: Pack):
 
 
 class ShardedPack:
-    """Rank-local slice of a pack plus what the all-gather needs: for every rank the global node ids of its
-    core rows (every rank derives all of them from the replicated full pack, so no metadata is exchanged)."""
+    """Rank-local slices of a pack plus what the all-gather needs.  Subgraphs are dealt into world * n_chunks
+    size-balanced units; rank r owns units r*n_chunks .. (r+1)*n_chunks-1, each a small pack of its own, so the
+    all-gather of chunk c can run (asynchronously, on NCCL's stream) behind the compute of chunk c+1.  Every rank
+    derives every unit's node ids from the replicated full pack, so no metadata is exchanged."""
 
-    def __init__(self, pack: Pack, world: int, rank: int, hidden: int, in_features: int):
+    def __init__(self, pack: Pack, world: int, rank: int, hidden: int, in_features: int, n_chunks: int = 1):
         rows, nnz = pack_subgraph_sizes(pack)
-        self.bins = balanced_bins(subgraph_costs(rows, nnz, hidden, in_features), world)
-        self.world, self.rank = world, rank
-        self.sub_ids = [torch.nonzero(self.bins == r).view(-1) for r in range(world)]
-        self.local = select_subgraphs(pack, self.sub_ids[rank]) if world > 1 else pack
-        # core node ids per rank, in that rank's local pack order
+        self.world, self.rank, self.n_chunks = world, rank, n_chunks
+        units = world * n_chunks
+        self.bins = balanced_bins(subgraph_costs(rows, nnz, hidden, in_features), units)
+        self.sub_ids = [torch.nonzero(self.bins == u).view(-1) for u in range(units)]
+        if units == 1:
+            self.locals = [pack]
+        else:
+            self.locals = [select_subgraphs(pack, self.sub_ids[rank * n_chunks + c]) for c in range(n_chunks)]
+        self.local = self.locals[0]
+        # core node ids per unit, in that unit's pack order (select_subgraphs keeps ascending subgraph order)
         core_sub = torch.repeat_interleave(torch.arange(pack.n_sub, device=pack.device), rows)[pack.core_rows.long()]
         core_gid = pack.core_gid.long()
-        rank_of_core = self.bins[core_sub]
-        self.core_ids = []
-        for r in range(world):
-            # select_subgraphs keeps subgraphs in ascending id order -> core rows keep their relative order
-            self.core_ids.append(core_gid[rank_of_core == r])
+        unit_of_core = self.bins[core_sub]
+        self.core_ids = [core_gid[unit_of_core == u] for u in range(units)]
         self.counts = [int(c.numel()) for c in self.core_ids]
         self.max_count = max(self.counts) if self.counts else 0
         self.n_nodes = pack.n_nodes
-        if world > 1:
-            assert torch.equal(self.local.core_gid.long(), self.core_ids[rank])
-        self.loads = [float(subgraph_costs(rows[s], nnz[s], hidden, in_features).sum()) for s in self.sub_ids]
+        if units > 1:
+            for c in range(n_chunks):
+                assert torch.equal(self.locals[c].core_gid.long(), self.core_ids[rank * n_chunks + c])
+        costs = subgraph_costs(rows, nnz, hidden, in_features)
+        self.loads = [float(sum(costs[self.sub_ids[r * n_chunks + c]].sum() for c in range(n_chunks)))
+                      for r in range(world)]
 
     # ---- all-gather of the core-node outputs -------------------------------------------------------------
     def gather_buffer(self, C: int, device, dtype=torch.float32) -> torch.Tensor:
-        """[world, max_count, C] buffer; rank r's logits live in slot r (rows beyond counts[r] are padding).  Pass
-        `slot(buf)` as `out=` to the forward so the head kernel writes straight into the buffer (no staging copy)."""
-        return torch.zeros(self.world, self.max_count, C, dtype=dtype, device=device)
+        """[n_chunks, world, max_count, C]; unit (r, c) writes rows [0, counts) of buf[c, r] (the rest is padding).
+        Pass `slot(buf, c)` as `out=` to the forward of chunk c so the head kernel writes straight into the buffer."""
+        return torch.zeros(self.n_chunks, self.world, self.max_count, C, dtype=dtype, device=device)
 
-    def slot(self, buf: torch.Tensor) -> torch.Tensor:
-        return buf[self.rank, : self.counts[self.rank]]
+    def slot(self, buf: torch.Tensor, chunk: int = 0) -> torch.Tensor:
+        return buf[chunk, self.rank, : self.counts[self.rank * self.n_chunks + chunk]]
 
-    def all_gather_(self, buf: torch.Tensor, group=None) -> torch.Tensor:
-        """In-place all-gather: after the call every rank holds every rank's slot."""
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_gather_into_tensor(buf.view(self.world * self.max_count, -1), buf[self.rank], group=group)
-        return buf
+    def all_gather_(self, buf: torch.Tensor, chunk: int = 0, group=None, async_op: bool = False):
+        """In-place all-gather of one chunk: afterwards every rank holds every rank's slot of that chunk.  With
+        async_op the NCCL work handle is returned: the collective runs on NCCL's stream behind whatever the caller
+        enqueues next, and `handle.wait()` makes the current stream wait for it."""
+        if self.world == 1:
+            return None
+        import torch.distributed as dist
+        b = buf[chunk]
+        return dist.all_gather_into_tensor(b.view(self.world * self.max_count, -1), b[self.rank], group=group,
+                                           async_op=async_op)
 
     def node_index(self, device) -> torch.Tensor:
         """row_of_node[v] = flat row of node v in the gather buffer (buf.view(-1, C)[row_of_node] is node order)."""
         idx = torch.empty(self.n_nodes, dtype=torch.long, device=device)
         for r in range(self.world):
-            idx[self.core_ids[r].to(device)] = r * self.max_count + torch.arange(self.counts[r], device=device)
+            for c in range(self.n_chunks):
+                u = r * self.n_chunks + c
+                base = (c * self.world + r) * self.max_count
+                idx[self.core_ids[u].to(device)] = base + torch.arange(self.counts[u], device=device)
         return idx
 
-    def gather_outputs(self, local_out: torch.Tensor, group=None) -> torch.Tensor:
-        """Convenience form: all-gather the per-rank core outputs and return [N, C] in global node order."""
-        buf = self.gather_buffer(local_out.shape[1], local_out.device, local_out.dtype)
-        self.slot(buf).copy_(local_out)
-        self.all_gather_(buf, group)
-        return buf.view(self.world * self.max_count, -1)[self.node_index(local_out.device)]
+    def gather_outputs(self, local_outs, group=None) -> torch.Tensor:
+        """Convenience form: all-gather per-chunk core outputs (a tensor when n_chunks == 1, else a list) and
+        return [N, C] in global node order."""
+        outs = [local_outs] if torch.is_tensor(local_outs) else list(local_outs)
+        buf = self.gather_buffer(outs[0].shape[1], outs[0].device, outs[0].dtype)
+        for c, o in enumerate(outs):
+            self.slot(buf, c).copy_(o)
+            self.all_gather_(buf, c, group)
+        return buf.view(-1, outs[0].shape[1])[self.node_index(outs[0].device)]

@@ -36,13 +36,13 @@ def test_balanced_bins_and_local_packs():
     loads = [float(costs[bins == r].sum()) for r in range(2)]
     assert abs(loads[0] - loads[1]) <= 0.2 * sum(loads)
     pack, d = cpu_pack()
-    for world in (1, 2, 4):
-        shards = [ShardedPack(pack, world, r, 512, 20) for r in range(world)]
-        ids = torch.cat([s.core_ids[s.rank] for s in shards])
+    for world, chunks in ((1, 1), (2, 1), (4, 1), (2, 3)):
+        shards = [ShardedPack(pack, world, r, 512, 20, n_chunks=chunks) for r in range(world)]
+        ids = torch.cat([lp.core_gid.long() for s in shards for lp in s.locals])
         assert sorted(ids.tolist()) == list(range(pack.n_nodes))  # every node is core on exactly one rank
         assert max(shards[0].loads) <= 1.25 * (sum(shards[0].loads) / world) + 1e5
         for s in shards:
-            lp = s.local
+          for lp in s.locals:
             # the local pack is a valid block-diagonal CSR: columns stay inside their subgraph
             rows_sub = torch.repeat_interleave(torch.arange(lp.n_sub), (lp.sub_ptr[1:] - lp.sub_ptr[:-1]).long())
             erow = torch.repeat_interleave(torch.arange(lp.n_rows), (lp.rowptr[1:] - lp.rowptr[:-1]).long())
@@ -54,11 +54,13 @@ def _worker(rank, world, port, ret):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from fitgnn_b200.dist import ShardedPack
     pack, d = cpu_pack()
-    sp = ShardedPack(pack, world, rank, 512, 20)
-    # stand-in for the forward: "logits" of a node = f(node id), in local pack order
-    ids = sp.local.core_gid.long()
-    local_out = torch.stack([ids.float(), ids.float() * 2 + 1], 1)
-    full = sp.gather_outputs(local_out)
+    sp = ShardedPack(pack, world, rank, 512, 20, n_chunks=2)
+    # stand-in for the forward: "logits" of a node = f(node id), in each chunk's local pack order
+    outs = []
+    for lp in sp.locals:
+        ids = lp.core_gid.long()
+        outs.append(torch.stack([ids.float(), ids.float() * 2 + 1], 1))
+    full = sp.gather_outputs(outs)
     want = torch.stack([torch.arange(pack.n_nodes).float(), torch.arange(pack.n_nodes).float() * 2 + 1], 1)
     ret[rank] = bool(torch.equal(full, want))
     dist.destroy_process_group()

@@ -39,6 +39,17 @@ def test_bf16x3_gemm_matches_fp64(fg, M, K, N):
     assert np.abs(got - want_elu).max() <= 1e-4 * scale
 
 
+@pytest.mark.parametrize("M,K,N", [(40000, 100, 512), (80000, 64, 256), (50001, 128, 512), (160000, 40, 48)])
+def test_bf16x3_w_stationary_plan(fg, M, K, N):
+    """Small K and many row blocks: the kernel keeps its weight block resident in shared memory (W-stationary)."""
+    g = torch.Generator().manual_seed(M + K + N)
+    A, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    want = (A.double() @ W.double().T + b.double()).numpy()
+    got = run_tc(fg, A, W, b)
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() <= 1e-4 * scale, np.abs(got - want).max() / scale
+
+
 @pytest.mark.parametrize("M,K,N,head", [(777, 512, 47, 1), (1000, 512, 7, 1), (300, 64, 3, 2), (2500, 512, 256, 1), (64, 32, 1, 0)])
 def test_bf16x3_head(fg, M, K, N, head):
     g = torch.Generator().manual_seed(M + N)
