@@ -14,6 +14,7 @@
 // Every mbarrier wait is bounded (clock64 budget) and traps instead of hanging the GPU.
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 #include "common.cuh"
 
@@ -296,8 +297,14 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     // column split: 32-column boxes; the second warp of a quadrant takes the upper half of the boxes.  A fused
     // (log-)softmax needs the whole row in one thread, so the first warp of the quadrant then takes every box.
     constexpr int N_BOXES = (BLOCK_N + 31) / 32;
-    const int col_group = (warp - EPI_WARP0) >> 2;
-    const int split_at = (head != FITGNN_HEAD_IDENTITY) ? N_BOXES : (N_BOXES + 1) / 2;
+    // Narrow heads (<= 64 columns, i.e. one box per warp): single pass — both warps of a quadrant keep their box in
+    // registers, exchange (max, sum exp) through shared memory and normalise.  Wider heads: two passes by warp 0.
+    constexpr bool FAST_HEAD = N_BOXES <= 2;
+    const bool use_fast_head = FAST_HEAD && head != FITGNN_HEAD_IDENTITY;
+    float2* exch = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2][EPI_WARPS][32]
+    const int ew = warp - EPI_WARP0;
+    const int col_group = ew >> 2;
+    const int split_at = (head != FITGNN_HEAD_IDENTITY && !FAST_HEAD) ? N_BOXES : (N_BOXES + 1) / 2;
     const int box_beg = col_group == 0 ? 0 : split_at;
     const int box_end = col_group == 0 ? split_at : N_BOXES;
     int64_t it = 0;
@@ -311,7 +318,19 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
       float* yrow = Y + m * ldy + n0;
       float row_max = -INFINITY, row_sum = 0.f;
-      if (head != FITGNN_HEAD_IDENTITY && col_group == 0) {
+      bool exchanged = false;
+      auto exchange_stats = [&](float lmax, float lsum) {
+        // partner warp = same TMEM quadrant, other column group; buffers alternate by tile parity
+        float2* mine = exch + ((it & 1) * EPI_WARPS + ew) * 32 + lane;
+        const float2* theirs = exch + ((it & 1) * EPI_WARPS + (ew ^ 4)) * 32 + lane;
+        *mine = make_float2(lmax, lsum);
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+        const float2 o = *theirs;
+        row_max = fmaxf(lmax, o.x);
+        row_sum = (lsum > 0.f ? lsum * __expf(lmax - row_max) : 0.f) + (o.y > 0.f ? o.y * __expf(o.x - row_max) : 0.f);
+        exchanged = true;
+      };
+      if (head != FITGNN_HEAD_IDENTITY && !FAST_HEAD && col_group == 0) {
         // pass 1: online max / sum of exp over the row (the whole row lives in this tile: N <= BLOCK_N)
         for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
           float v[16];
@@ -329,7 +348,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           }
         }
       }
-      const float log_sum = logf(row_sum), inv_sum = 1.f / row_sum;
+      float log_sum = logf(row_sum), inv_sum = 1.f / row_sum;
       const uint32_t buf = smem_u32(staging) + (uint32_t)(warp - EPI_WARP0) * EPI_BOX_BYTES;
       const int m_base = (int)((t / n_tiles) * BLOCK_M) + quad * 32;
       for (int box = box_beg; box < box_end; ++box) {
@@ -361,6 +380,18 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         if (act == FITGNN_ACT_ELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = elu1(v[j]);
+        }
+        if (use_fast_head) {
+          float lmax = -INFINITY, lsum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < box_cols && n0 + c0 + j < N) lmax = fmaxf(lmax, v[j]);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < box_cols && n0 + c0 + j < N) lsum += __expf(v[j] - lmax);
+          exchange_stats(lmax, lsum);
+          log_sum = logf(row_sum);
+          inv_sum = 1.f / row_sum;
         }
         if (head == FITGNN_HEAD_LOG_SOFTMAX) {
 #pragma unroll
@@ -421,6 +452,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           }
         }
       }
+      if (use_fast_head && !exchanged) exchange_stats(-INFINITY, 0.f);  // no box this tile: still meet the partner
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));  // this warp's quadrant of the accumulator is drained
@@ -521,12 +553,14 @@ static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const void* 
     FG_TRY(make_store_map(&y_map, Y, M, N, ldy));
   }
   constexpr size_t SMEM_LIMIT = 227 * 1024;
-  constexpr size_t FIXED = EPI_STAGING_BYTES + 1024 + 8 * (2 * 8 + 2 * ACC_STAGES + 1) + 16;
+  // staging + alignment slack + barriers/TMEM slot (256 B) + softmax exchange buffers (2 x 8 warps x 32 x float2)
+  constexpr size_t FIXED = EPI_STAGING_BYTES + 1024 + 256 + (BLOCK_N <= 64 ? 2 * EPI_WARPS * 32 * 8 : 0);
   const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
   const int n_tiles = (int)ceil_div(N, BLOCK_N);
   const int64_t m_tiles = ceil_div(M, BLOCK_M);
   const int64_t tiles = m_tiles * n_tiles;
-  int n_stages = num_stages(BLOCK_N);
+  int n_stages = (int)((SMEM_LIMIT - FIXED) / stage_bytes(BLOCK_N));
+  if (n_stages > 8) n_stages = 8;
   int grid = (int)(tiles < sms ? tiles : sms);
   size_t smem = (size_t)n_stages * stage_bytes(BLOCK_N) + FIXED;
   // W-stationary plan: worth it when the resident weights fit beside >= 2 A stages and every CTA gets several m-blocks
@@ -538,6 +572,15 @@ static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const void* 
     if (n_stages > 8) n_stages = 8;
     grid = (sms / n_tiles) * n_tiles;
     smem = w_bytes + (size_t)n_stages * 2 * A_PLANE_BYTES + FIXED;
+  }
+  if (const char* e = getenv("FITGNN_GEMM_WS")) {  // tuning override: 0 = force streaming plan
+    if (e[0] == '0' && w_stationary) {
+      w_stationary = 0;
+      n_stages = (int)((SMEM_LIMIT - FIXED) / stage_bytes(BLOCK_N));
+      if (n_stages > 8) n_stages = 8;
+      grid = (int)(tiles < sms ? tiles : sms);
+      smem = (size_t)n_stages * stage_bytes(BLOCK_N) + FIXED;
+    }
   }
   auto kern = gemm_bf16x3_kernel<BLOCK_N>;
   FG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

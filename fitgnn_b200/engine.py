@@ -188,7 +188,13 @@ class PackedForward:
         if bf and not isinstance(h, tuple):
             h = self._timed("split_head", lambda: ops.split_bf16(h), nbytes=8 * h.numel())
             self.launches += 1
-        return self._gemm(h, self.Wl, self.bl, ops.ACT_NONE, self.head, N=self.C, K=self.H, name="head", out=out)
+        view = None
+        if out is None and self.C % 4 != 0:
+            # 16-byte aligned row pitch -> coalesced / TMA stores in the head epilogue; callers get the [:, :C] view
+            out = torch.empty(self.n_out, ops.pad4(self.C), dtype=torch.float32, device=X.device)
+            view = out[:, : self.C]
+        res = self._gemm(h, self.Wl, self.bl, ops.ACT_NONE, self.head, N=self.C, K=self.H, name="head", out=out)
+        return res if view is None else view
 
     def scatter_to_nodes(self, out, n_nodes=None):
         """Core-row outputs (pack order) -> [N, C] in global node order."""
