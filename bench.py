@@ -344,6 +344,11 @@ def main_ours(args):
 
     dom = max(kernels, key=lambda k_: kernels[k_]["ms"])
 
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath) and world == 1 and args.workload == "products" and args.mode == "none":
+        traffic = json.load(open(tpath))  # per-launch DRAM bytes from the committed ncu capture of this same command
+
     def roofline_of(name):
         r = kernels[name]
         # bf16x3: three bf16 MMAs per logical product (hi*hi + lo*hi + hi*lo)
@@ -353,10 +358,11 @@ def main_ours(args):
             # 3 bf16 MMAs per logical product (hi*hi + hi*lo + lo*hi)
             ach = 3 * r["TFLOPs"]
             return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s",
-                    "frac": ach / tc_peak, "traffic": None, "peak_source": peak_src}
+                    "frac": ach / tc_peak, "traffic": traffic.get(name), "algorithmic_bytes": int(r["algo_GB"] * 1e9),
+                    "peak_source": peak_src + " (bf16_tflops_sustained; 3 bf16 MMAs per logical product)"}
         return {"kernel": name, "bound": "hbm", "achieved": r["GBps"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": r["GBps"] / hbm_peak, "frac_of_nominal_8000": r["GBps"] / 8000.0, "traffic": None,
-                "peak_source": peak_src}
+                "frac": r["GBps"] / hbm_peak, "frac_of_nominal_8000": r["GBps"] / 8000.0, "traffic": traffic.get(name),
+                "algorithmic_bytes": int(r["algo_GB"] * 1e9), "peak_source": peak_src + " (hbm_gbs)"}
 
     spmm_names = [k_ for k_ in kernels if k_.startswith("spmm")]
     spmm_main = max(spmm_names, key=lambda k_: kernels[k_]["algo_GB"]) if spmm_names else dom
