@@ -50,6 +50,8 @@ SIGNATURES = {
                                      c_i32, c_i32, c_void, c_i64, c_void]),
     "fitgnn_gemm_bias_act_split": (c_i32, [c_i32, c_void, c_void, c_i64, c_void, c_void, c_i64, c_void, c_i64, c_i32,
                                            c_i32, c_i32, c_i32, c_void, c_void, c_i64, c_void]),
+    "fitgnn_gcn_layer_fused": (c_i32, [c_void, c_void, c_void, c_void, c_i64, c_i32, c_void, c_void, c_i64, c_void, c_void,
+                                       c_i64, c_void, c_i32, c_i32, c_void, c_void, c_i64, c_void]),
     "fitgnn_split_bf16": (c_i32, [c_void, c_i64, c_i64, c_i32, c_void, c_void, c_i64, c_void]),
     "fitgnn_segment_pool": (c_i32, [c_void, c_i64, c_i32, c_void, c_void, c_i64, c_i32, c_void, c_i64, c_void]),
     "fitgnn_group_workspace_bytes": (c_size, [c_i64, c_i64]),

@@ -22,6 +22,10 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
                 const float* bias, int64_t M, int K, int N, int act, int head, float* Y, void* Y_lo, int64_t ldy,
                 cudaStream_t st);
 
+int gcn_layer_fused(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X, int64_t ldx, int width,
+                    const int32_t* src_index, const int32_t* out_rows, int64_t M, const void* W_hi, const void* W_lo,
+                    int64_t ldw, const float* bias, int N, int act, float* Y, void* Y_lo, int64_t ldy, cudaStream_t st);
+
 }  // namespace fitgnn
 
 using namespace fitgnn;
@@ -78,4 +82,16 @@ extern "C" int fitgnn_gemm_bias_act(int precision, const void* A, const void* A_
                                     int head, float* Y, int64_t ldy, void* stream) {
   return fitgnn_gemm_bias_act_split(precision, A, A_lo, lda, W, W_lo, ldw, bias, M, K, N, act, head, Y, nullptr, ldy,
                                     stream);
+}
+
+extern "C" int fitgnn_gcn_layer_fused(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X,
+                                      int64_t ldx, int width, const int32_t* src_index, const int32_t* out_rows,
+                                      int64_t n_out, const void* W_hi, const void* W_lo, int64_t ldw, const float* bias,
+                                      int N, int act, void* Y, void* Y_lo, int64_t ldy, void* stream) {
+  FG_REQUIRE(rowptr && col && dinv && X && W_hi && W_lo && Y && n_out >= 0 && N > 0 && width > 0, FITGNN_EINVAL,
+             "gcn_layer_fused: bad arguments");
+  FG_REQUIRE(act == FITGNN_ACT_NONE || act == FITGNN_ACT_ELU, FITGNN_EINVAL, "gcn_layer_fused: unknown act %d", act);
+  if (n_out == 0) return FITGNN_OK;
+  return gcn_layer_fused(rowptr, col, dinv, X, ldx, width, src_index, out_rows, n_out, W_hi, W_lo, ldw, bias, N, act,
+                         static_cast<float*>(Y), Y_lo, ldy, as_stream(stream));
 }

@@ -27,6 +27,22 @@ constexpr int BLOCK_K = 64;                      // bf16 elements = 128 bytes = 
 constexpr int UMMA_K = 16;
 constexpr int EPI_WARPS = 8;                      // two per TMEM lane quadrant, each taking half of the columns
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
+constexpr int GATHER_WARPS = 4;                   // fused layer: produce the A tile (Â·X) in-kernel, 32 rows per warp
+constexpr int GATHER_WARP0 = 2 + EPI_WARPS;
+constexpr int THREADS_GATHER = THREADS + 32 * GATHER_WARPS;
+
+// Fused GCN layer (aggregate-first, K <= 128): the A operand of the transform is Â·X[src], gathered through the
+// pack CSR by dedicated warps instead of being loaded by TMA (replaces a separate SpMM launch and its HBM round trip).
+struct GatherArgs {
+  const int32_t* rowptr;
+  const int32_t* col;
+  const float* dinv;
+  const float* X;          // [n_src, ldx] fp32
+  const int32_t* src_index;  // gid (may be null)
+  const int32_t* out_rows;   // output row -> pack row (may be null)
+  int64_t ldx;
+  int nq;                  // float4 per feature row (width / 4)
+};
 constexpr int EPI_WARP0 = 2;
 constexpr int ACC_STAGES = 2;
 constexpr uint32_t A_PLANE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
@@ -155,9 +171,9 @@ __host__ __device__ constexpr int num_stages(int block_n) {
   return s > 8 ? 8 : s;
 }
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(THREADS, 1)
-gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+template <int BLOCK_N, bool GATHER>
+__global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS, 1)
+gemm_bf16x3_kernel(const GatherArgs ga, const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                    const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_y_lo,
                    int tma_store, const float* __restrict__ bias, int64_t M, int K, int N, int act, int head,
@@ -203,7 +219,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < n_stages; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), GATHER ? GATHER_WARPS : 1);
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(wfull_bar, 1);
@@ -236,7 +252,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           tma_load_2d(w_base + kb * 2 * B_PLANE_BYTES + B_PLANE_BYTES, &map_w_lo, wfull_bar, kb * BLOCK_K, n0);
         }
       }
-      for (int64_t t = t_first; t < tiles; t += t_step) {
+      for (int64_t t = t_first; t < tiles && !GATHER; t += t_step) {  // gather mode: A is produced by the gather warps
         const int m0 = (int)(t / n_tiles) * BLOCK_M;
         const int n0 = (int)(t % n_tiles) * BLOCK_N;
         for (int kb = 0; kb < k_blocks; ++kb) {
@@ -288,6 +304,126 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       }
     }
     __syncwarp();
+  } else if (GATHER && warp >= GATHER_WARP0) {
+    // ------------------------------------------------------------------ gather warps: A tile = Â·X[src] (bf16 hi/lo)
+    // 8 lanes per row, 4 rows per warp step, 8 steps per tile; software-pipelined across steps AND tiles exactly like
+    // spmm_pipe_kernel (row info 3 steps ahead, column indices 2, dinv/gid 1).  A row's 128 columns (4 float4 per
+    // lane) cover both 64-column k-blocks; element (row r, col c) of k-block c/64 goes to the canonical K-major
+    // SWIZZLE_128B position r*128 + (((c%64)/8) ^ (r&7))*16 + ((c%8)/4)*8 of the hi / lo plane.
+    constexpr int LPR = 8, STEPS = BLOCK_M / (GATHER_WARPS * 4);
+    constexpr unsigned FULL = 0xffffffffu;
+    const int gw = warp - GATHER_WARP0, sub = lane & (LPR - 1), grp = lane / LPR;
+    const int64_t my_tiles = (t_first < tiles) ? (tiles - 1 - t_first) / t_step + 1 : 0;
+    const int64_t total_steps = my_tiles * STEPS;
+    struct RI { int beg, end; float dr; };
+    auto load_info = [&](int64_t step) {
+      RI ri{0, 0, 0.f};
+      if (step < total_steps) {
+        const int64_t t = t_first + (step / STEPS) * t_step;
+        const int64_t i = (t / n_tiles) * BLOCK_M + gw * 32 + (int)(step % STEPS) * 4 + grp;
+        if (i < M) {
+          const int r = ga.out_rows ? __ldg(ga.out_rows + i) : (int)i;
+          ri.beg = __ldg(ga.rowptr + r);
+          ri.end = __ldg(ga.rowptr + r + 1);
+          ri.dr = __ldg(ga.dinv + r);
+        }
+      }
+      return ri;
+    };
+    auto load_col = [&](const RI& ri, int e0) { return (e0 + sub < ri.end) ? __ldg(ga.col + e0 + sub) : -1; };
+    auto load_w = [&](int c) { return c >= 0 ? __ldg(ga.dinv + c) : 0.f; };
+    auto load_s = [&](int c) { return c >= 0 ? (ga.src_index ? __ldg(ga.src_index + c) : c) : 0; };
+    auto gather_chunk = [&](float4 (&acc)[4], int cnt, float w, int sidx) {
+      const int maxcnt = __reduce_max_sync(FULL, cnt);
+      for (int j = 0; j < maxcnt; j += 2) {
+        float wj[2];
+        const float* pj[2];
+        bool on[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          wj[u] = __shfl_sync(FULL, w, j + u, LPR);
+          const int sj = __shfl_sync(FULL, sidx, j + u, LPR);
+          pj[u] = ga.X + (int64_t)sj * ga.ldx;
+          on[u] = j + u < cnt;
+        }
+        float4 x[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const int q = sub + LPR * v;
+            x[u][v] = (on[u] && q < ga.nq) ? __ldg(reinterpret_cast<const float4*>(pj[u]) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            acc[v].x = fmaf(wj[u], x[u][v].x, acc[v].x); acc[v].y = fmaf(wj[u], x[u][v].y, acc[v].y);
+            acc[v].z = fmaf(wj[u], x[u][v].z, acc[v].z); acc[v].w = fmaf(wj[u], x[u][v].w, acc[v].w);
+          }
+      }
+    };
+    RI ia = load_info(0), ib = load_info(1), ic = load_info(2);
+    int ca = load_col(ia, ia.beg), cb = load_col(ib, ib.beg);
+    float wa = load_w(ca);
+    int sa = load_s(ca);
+    uint32_t stage = 0, phase = 0;
+    for (int64_t step = 0; step < total_steps; ++step) {
+      const RI id = load_info(step + 3);
+      const int cc = load_col(ic, ic.beg);
+      const float wb = load_w(cb);
+      const int sb = load_s(cb);
+      const int s_in_tile = (int)(step % STEPS);
+      if (s_in_tile == 0) {  // the k_blocks stages of this tile must have been released by the MMAs that read them
+        if (lane == 0)
+          for (int kb = 0; kb < k_blocks; ++kb) mbar_wait(empty_bar(stage + kb), phase ^ 1);
+        __syncwarp();
+      }
+      const int deg = ia.end - ia.beg;
+      float4 acc[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      gather_chunk(acc, min(deg, LPR), wa, sa);
+      const bool long_row = deg > LPR;
+      for (int e0 = ia.beg + LPR; __any_sync(FULL, long_row && e0 < ia.end); e0 += LPR) {
+        const int c = long_row ? load_col(ia, e0) : -1;
+        gather_chunk(acc, long_row ? max(0, min(ia.end - e0, LPR)) : 0, load_w(c), load_s(c));
+      }
+      const int lr = gw * 32 + s_in_tile * 4 + grp;  // row inside the tile
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int c = 4 * (sub + LPR * v);  // first of this lane's 4 columns
+        const int kb = c >> 6;
+        if (kb < k_blocks) {
+          const float x[4] = {acc[v].x * ia.dr, acc[v].y * ia.dr, acc[v].z * ia.dr, acc[v].w * ia.dr};
+          uint32_t hi[2], lo[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * u]), h1 = __float2bfloat16_rn(x[2 * u + 1]);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * u] - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * u + 1] - __bfloat162float(h1));
+            hi[u] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lo[u] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+          }
+          const int cc64 = c & 63;
+          const uint32_t a = smem_base + (stage + kb) * stage_bytes_rt + lr * 128 +
+                             ((uint32_t)(cc64 >> 3) ^ (uint32_t)(lr & 7)) * 16 + ((cc64 & 7) >> 2) * 8;
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(hi[0]), "r"(hi[1]) : "memory");
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a + A_PLANE_BYTES), "r"(lo[0]), "r"(lo[1]) : "memory");
+        }
+      }
+      if (s_in_tile == STEPS - 1) {
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0)
+          for (int kb = 0; kb < k_blocks; ++kb) mbar_arrive(full_bar(stage + kb));
+        stage += k_blocks;
+        if (stage >= (uint32_t)n_stages) { stage = 0; phase ^= 1; }
+      }
+      ia = ib; ib = ic; ic = id;
+      ca = cb; cb = cc;
+      wa = wb; sa = sb;
+    }
   } else {
     // ------------------------------------------------------------------ epilogue (thread = output row)
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
@@ -532,8 +668,8 @@ static int make_store_map_bf16(CUtensorMap* map, void* base, int64_t rows, int64
   return FITGNN_OK;
 }
 
-template <int BLOCK_N>
-static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const void* W_hi, const void* W_lo, int64_t ldw,
+template <int BLOCK_N, bool GATHER>
+static int launch(const GatherArgs& ga, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const void* W_hi, const void* W_lo, int64_t ldw,
                   const float* bias, int64_t M, int K, int N, int act, int head, float* Y, void* Y_lo, int64_t ldy,
                   int sms, cudaStream_t st) {
   CUtensorMap w_hi, w_lo;
@@ -582,10 +718,17 @@ static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const void* 
       smem = (size_t)n_stages * stage_bytes(BLOCK_N) + FIXED;
     }
   }
-  auto kern = gemm_bf16x3_kernel<BLOCK_N>;
+  if (GATHER) {
+    // the gather warps fill all k-blocks of a tile at once: needs the W-stationary plan with n_stages % k_blocks == 0
+    FG_REQUIRE(w_stationary && k_blocks <= 2 && n_stages >= k_blocks, FITGNN_EUNSUP,
+               "gcn_layer_fused: shape not eligible (needs K <= 128 and enough row blocks for the W-stationary plan)");
+    n_stages = (n_stages / k_blocks) * k_blocks;
+    smem = w_bytes + (size_t)n_stages * 2 * A_PLANE_BYTES + FIXED;
+  }
+  auto kern = gemm_bf16x3_kernel<BLOCK_N, GATHER>;
   FG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, THREADS, smem, st>>>(a_hi, a_lo, w_hi, w_lo, y_map, y_lo_map, tma_store, bias, M, K, N, act, head, Y,
-                                    ldy, w_stationary, n_stages);
+  kern<<<grid, GATHER ? THREADS_GATHER : THREADS, smem, st>>>(ga, a_hi, a_lo, w_hi, w_lo, y_map, y_lo_map, tma_store, bias,
+                                                              M, K, N, act, head, Y, ldy, w_stationary, n_stages);
   FG_LAUNCH_CHECK();
   return FITGNN_OK;
 }
@@ -608,7 +751,9 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
   CUtensorMap a_hi, a_lo;
   FG_TRY(tc::make_map(&a_hi, A_hi, M, K, lda, tc::BLOCK_M));
   FG_TRY(tc::make_map(&a_lo, A_lo, M, K, lda, tc::BLOCK_M));
-#define FG_TC(BN) return tc::launch<BN>(a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y, Y_lo, ldy, sms, st)
+  const tc::GatherArgs ga{};
+#define FG_TC(BN) \
+  return tc::launch<BN, false>(ga, a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y, Y_lo, ldy, sms, st)
   if (N <= 16) FG_TC(16);
   if (N <= 32) FG_TC(32);
   if (N <= 48) FG_TC(48);
@@ -616,6 +761,30 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
   if (N <= 128) FG_TC(128);
   FG_TC(256);
 #undef FG_TC
+}
+
+
+// Y = act( (Â · X[src_index])[out_rows] · W^T + bias ) in one kernel (layer width K = 4 * nq <= 128, N = 512-style wide
+// outputs).  Returns FITGNN_EUNSUP when the shape is not eligible so the caller can fall back to SpMM + GEMM.
+int gcn_layer_fused(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X, int64_t ldx, int width,
+                    const int32_t* src_index, const int32_t* out_rows, int64_t M, const void* W_hi, const void* W_lo,
+                    int64_t ldw, const float* bias, int N, int act, float* Y, void* Y_lo, int64_t ldy, cudaStream_t st) {
+  FG_REQUIRE(width % 4 == 0 && width <= 128 && ldx % 4 == 0 && ((uintptr_t)X & 15) == 0, FITGNN_EUNSUP,
+             "gcn_layer_fused: feature width must be a multiple of 4 and <= 128 (got %d)", width);
+  FG_REQUIRE(N > 128, FITGNN_EUNSUP, "gcn_layer_fused: only the wide-output tile (N > 128) is instantiated");
+  FG_REQUIRE(M < (1ll << 31) - 128, FITGNN_ERANGE, "gcn_layer_fused: M exceeds the coordinate range");
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    FG_CUDA(cudaGetDevice(&dev));
+    FG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int K = (width + 7) / 8 * 8;
+  tc::GatherArgs ga{rowptr, col, dinv, X, src_index, out_rows, ldx, width / 4};
+  CUtensorMap dummy;
+  FG_TRY(tc::make_map(&dummy, W_hi, N, K, ldw, 16));  // placeholder for the unused A maps
+  return tc::launch<256, true>(ga, dummy, dummy, W_hi, W_lo, ldw, bias, M, K, N, act, FITGNN_HEAD_IDENTITY, Y, Y_lo, ldy,
+                               sms, st);
 }
 
 }  // namespace fitgnn

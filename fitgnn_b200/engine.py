@@ -30,7 +30,7 @@ class PackedForward:
     'core' (node tasks), 'mask' (graph tasks: x[mask], network.py:129) or 'all'."""
 
     def __init__(self, pack: Pack, state_dict, head="log_softmax", rows="core", precision="fp32",
-                 with_head=True):
+                 with_head=True, fuse_layer0=False):
         self.pack = pack
         dev = pack.device
         self.precision = ops.GEMM_BF16X3 if precision == "bf16x3" else ops.GEMM_FP32
@@ -70,6 +70,10 @@ class PackedForward:
         self.hubs_all = ops.find_hubs(pack.rowptr, None, pack.n_rows)
         self.hubs_out = self.hubs_all if self.out_rows is None else ops.find_hubs(pack.rowptr, self.out_rows, self.n_out)
         self.launches = 0
+        # fitgnn_gcn_layer_fused for layer 0 (gather warps inside the GEMM).  Correct but measured SLOWER than
+        # SpMM + GEMM on B200 (5.1 ms vs 2.1 ms on the products workload: 4 gather warps per SM cannot hide the gather
+        # latency that the stand-alone SpMM hides with 24 warps per SM), hence opt-in.
+        self.fused_layer0 = None if fuse_layer0 else False
         self.prof = None  # set to {} by enable_profile(): op name -> dict(events, bytes, flops)
         self._nnz_cache = {}
 
@@ -149,6 +153,30 @@ class PackedForward:
                                                           split=split, hubs=hubs),
                            nbytes=self._spmm_bytes(width, src_index, last, n_src_rows))
 
+    def _fused_layer0(self, X, last):
+        """Layer 0 as ONE kernel: gather warps build Â·X[gid] tiles in shared memory for the tensor-core transform."""
+        from ._lib import FitgnnError
+        p = self.pack
+        rows = self.out_rows if last else None
+        n_rows = self.n_out if last else p.n_rows
+        to_head = last and self.with_head and self.H % 8 == 0
+        nbytes = self._spmm_bytes(self.Fp, p.gid, last, X.shape[0], out_elem=0) + 4 * n_rows * self.H
+        flops = 2 * n_rows * self.Fp * self.H
+        try:
+            out = self._timed("layer0_fused", lambda: ops.gcn_layer_fused(
+                p.rowptr, p.col, p.dinv, X, self.Fp, self.W[0], self.b[0], ops.ACT_ELU, src_index=p.gid, out_rows=rows,
+                N=self.H, split_out=to_head), nbytes=nbytes, flops=flops)
+        except FitgnnError as e:
+            if "EUNSUP" not in str(e):
+                raise
+            self.fused_layer0 = False
+            if self.prof is not None:
+                self.prof.pop("layer0_fused", None)
+            return None
+        self.fused_layer0 = True
+        self.launches += 1
+        return out
+
     def pad_features(self, X):
         """Rows of the de-duplicated feature table, K-padded (a view when no padding is needed)."""
         if X.shape[1] == self.Fp and X.is_contiguous():
@@ -176,6 +204,12 @@ class PackedForward:
                     self.launches += 1
                 Z = self._gemm(A, self.W[0], None, ops.ACT_NONE, N=self.H, K=self.Fp, name="gemm0_unique_rows")
                 h = self._spmm(Z, self.H, p.gid, self.b[0], ops.ACT_ELU, last, split=False, name="spmm0")
+            elif i == 0 and bf and self.fused_layer0 is not False and self.Fp <= 128 and self.H > 128:
+                h = self._fused_layer0(X, last)
+                if h is None:  # not eligible for this shape: SpMM + GEMM below
+                    A = self._spmm(X, self.Fp, p.gid, None, ops.ACT_NONE, last, split=bf, name="spmm0")
+                    h = self._gemm(A, self.W[0], self.b[0], ops.ACT_ELU, N=self.H, K=self.Fp, name="gemm0",
+                                   split_out=bf and last and self.with_head and self.H % 8 == 0)
             else:
                 src, width, idx = (X, self.Fp, p.gid) if i == 0 else (h, self.H, None)
                 A = self._spmm(src, width, idx, None, ops.ACT_NONE, last, split=bf, name=f"spmm{i}")

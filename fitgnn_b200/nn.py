@@ -20,20 +20,30 @@ from .autograd import CsrPair, gcn_conv
 from .engine import PackedForward
 from .pack import Pack
 
-_CSR_CACHE: dict = {}
+_CSR_CACHE: dict = {}  # id(edge_index) -> (weakref to the tensor, version, n, CsrPair)
 _CSR_CACHE_MAX = 64
 
 
 def _csr_for(edge_index, n):
-    """gcn_norm structure, cached per edge_index tensor (PyG recomputes it on every call; cached=False)."""
-    key = (edge_index.data_ptr(), edge_index.shape[1], n, edge_index._version, edge_index.device.index)
+    """gcn_norm structure, cached per edge_index TENSOR OBJECT (PyG recomputes it on every call; cached=False).
+    The entry is valid only while that very tensor is alive and unmodified: the weak reference must still resolve to
+    the same object (an address or id reused by a new tensor can never alias a stale entry) and `_version` must match
+    (in-place edits invalidate)."""
+    import weakref
+    key = id(edge_index)
     hit = _CSR_CACHE.get(key)
-    if hit is None:
+    if hit is not None:
+        ref, version, n_hit, csr = hit
+        if ref() is edge_index and version == edge_index._version and n_hit == n:
+            return csr
+    if len(_CSR_CACHE) >= _CSR_CACHE_MAX:
+        for k in [k for k, v in _CSR_CACHE.items() if v[0]() is None]:
+            del _CSR_CACHE[k]
         if len(_CSR_CACHE) >= _CSR_CACHE_MAX:
             _CSR_CACHE.clear()
-        hit = CsrPair.from_edge_index(edge_index, n)
-        _CSR_CACHE[key] = hit
-    return hit
+    csr = CsrPair.from_edge_index(edge_index, n)
+    _CSR_CACHE[key] = (weakref.ref(edge_index), edge_index._version, n, csr)
+    return csr
 
 
 def _as_f32_padded(x):

@@ -130,6 +130,26 @@ def gemm_bias_act(A, W, bias=None, act=ACT_NONE, head=HEAD_IDENTITY, out=None, K
     return out
 
 
+def gcn_layer_fused(rowptr, col, dinv, X, width, W, bias=None, act=ACT_NONE, src_index=None, out_rows=None, N=None,
+                    split_out=False):
+    """One fused GCN layer (aggregate-first, feature width <= 128): act((Â·X[src_index])[out_rows]·W^T + bias) with
+    the A operand gathered in-kernel.  W = bf16 (hi, lo) planes.  Raises FitgnnError (EUNSUP) for ineligible shapes."""
+    w_hi, w_lo = W
+    N = w_hi.shape[0] if N is None else N
+    n_out = out_rows.numel() if out_rows is not None else rowptr.numel() - 1
+    if split_out:
+        out = (torch.empty(n_out, N, dtype=torch.bfloat16, device=X.device),
+               torch.empty(n_out, N, dtype=torch.bfloat16, device=X.device))
+        y, ylo, ldy = out[0], out[1], N
+    else:
+        out = torch.empty(n_out, N, dtype=torch.float32, device=X.device)
+        y, ylo, ldy = out, None, N
+    check(lib().fitgnn_gcn_layer_fused(ptr(rowptr), ptr(col), ptr(dinv), ptr(X), X.stride(0), width, ptr(src_index),
+                                       ptr(out_rows), n_out, ptr(w_hi), ptr(w_lo), w_hi.stride(0), ptr(bias), N, act,
+                                       ptr(y), ptr(ylo), ldy, stream_ptr()))
+    return out
+
+
 def split_bf16(X, cols=None, ldo=None):
     """fp32 [rows, cols] -> bf16 (hi, lo) planes [rows, ldo] with zero-filled padding columns."""
     rows = X.shape[0]

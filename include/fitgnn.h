@@ -164,6 +164,17 @@ int fitgnn_gemm_bias_act_split(int precision, const void* A, const void* A_lo, i
                                const void* W, const void* W_lo, int64_t ldw, const float* bias,
                                int64_t M, int K, int N, int act, int head, void* Y, void* Y_lo,
                                int64_t ldy, void* stream);
+/* One fused GCN layer, aggregate-first (replaces GCNConv.__call__ + F.elu, network.py:31-32, for feature widths <= 128):
+ *   Y[i,:] = act( (Â · X[src_index])[r_i,:] · W^T + bias ),  r_i = out_rows[i] or i
+ * The A operand of the tensor-core transform is produced in-kernel by gather warps walking the pack CSR, so there is
+ * no separate SpMM launch and no HBM round trip for Â·X.  W_hi/W_lo: bf16 planes [N, ldw] with K padded to 8.
+ * Y fp32 [n_out, ldy], or bf16 hi/lo planes when Y_lo != NULL.  Returns FITGNN_EUNSUP for ineligible shapes
+ * (width > 128, N <= 128, too few row blocks): callers then use fitgnn_spmm_symnorm + fitgnn_gemm_bias_act. */
+int fitgnn_gcn_layer_fused(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X,
+                           int64_t ldx, int width, const int32_t* src_index, const int32_t* out_rows,
+                           int64_t n_out, const void* W_hi, const void* W_lo, int64_t ldw,
+                           const float* bias, int N, int act, void* Y, void* Y_lo, int64_t ldy,
+                           void* stream);
 /* fp32 [rows, cols] (ld = ldx) -> bf16 hi/lo planes [rows, ldo] (columns >= cols zero filled) */
 int fitgnn_split_bf16(const float* X, int64_t ldx, int64_t rows, int cols, void* hi, void* lo,
                       int64_t ldo, void* stream);

@@ -89,3 +89,45 @@ def test_bf16x3_split_output(fg, M, K, N):
     want_hi = ref.to(torch.bfloat16)
     assert torch.equal(hi, want_hi)
     assert torch.equal(lo, (ref - want_hi.float()).to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("n,F,H,mode", [(60000, 100, 512, "none"), (40000, 64, 512, "extra"), (45000, 128, 512, "extra")])
+def test_fused_gcn_layer_matches_spmm_plus_gemm(fg, n, F, H, mode):
+    """fitgnn_gcn_layer_fused (gather warps feeding the tensor-core GEMM) vs the two-kernel path and vs fp64."""
+    from oracle import fitgnn_oracle as fo
+    ei, part, cw, k = fg.synth.planted_partition(n, 4 * n, 0.4, seed=n, device=DEV, locality=16)
+    part = fg.synth.relabel_partition_reference_order(part)
+    pack = fg.build_pack(ei, part, k, mode)
+    g = torch.Generator().manual_seed(F)
+    X = torch.rand(n, F, generator=g).to(DEV)
+    W = (torch.randn(H, F, generator=g) / F ** 0.5).to(DEV)
+    b = torch.randn(H, generator=g).to(DEV)
+    kp = (F + 7) // 8 * 8
+    Xp = torch.zeros(n, kp, device=DEV); Xp[:, :F] = X
+    Wp = fg.ops.split_bf16(W, ldo=kp)
+    rows = pack.core_rows
+    fused = fg.ops.gcn_layer_fused(pack.rowptr, pack.col, pack.dinv, Xp, kp, Wp, b, fg.ops.ACT_ELU, src_index=pack.gid,
+                                   out_rows=rows)
+    A = fg.ops.spmm_symnorm(pack.rowptr, pack.col, pack.dinv, Xp, kp, pack.gid, out_rows=rows, split=True)
+    two = fg.ops.gemm_bias_act(A, Wp, b, fg.ops.ACT_ELU, precision=fg.ops.GEMM_BF16X3, K=kp)
+    torch.cuda.synchronize()
+    assert torch.equal(fused, two)  # same arithmetic, same order -> bit-identical
+    # fp64 check on a sample of rows
+    sel = torch.randperm(rows.numel(), generator=torch.Generator().manual_seed(1))[:2000]
+    Ad = fg.ops.spmm_symnorm(pack.rowptr, pack.col, pack.dinv, Xp, kp, pack.gid, out_rows=rows[sel.to(DEV)].contiguous())
+    want = Ad.double().cpu() @ torch.nn.functional.pad(W, (0, kp - F)).double().cpu().T + b.double().cpu()
+    want = torch.where(want > 0, want, torch.expm1(want))
+    got = fused[sel.to(DEV)].double().cpu()
+    assert (got - want).abs().max() <= 1e-4 * want.abs().max()
+    hi, lo = fg.ops.gcn_layer_fused(pack.rowptr, pack.col, pack.dinv, Xp, kp, Wp, b, fg.ops.ACT_ELU, src_index=pack.gid,
+                                    out_rows=rows, split_out=True)
+    assert torch.equal(hi, fused.to(torch.bfloat16))
+    # the engine's opt-in use of the fused layer gives the same logits as the default schedule
+    sd = fo.init_state_dict(F, H, 7, seed=3)
+    a = fg.PackedForward(pack, sd, precision="bf16x3")(X)
+    f = fg.PackedForward(pack, sd, precision="bf16x3", fuse_layer0=True)
+    bq = f(X)
+    assert f.fused_layer0 is True and torch.equal(a, bq)
+    # ineligible shapes are refused loudly at the ABI (callers fall back)
+    with pytest.raises(fg._lib.FitgnnError):
+        fg.ops.gcn_layer_fused(pack.rowptr, pack.col, pack.dinv, Xp[:1000], kp, Wp, b, out_rows=rows[:1000].contiguous())

@@ -488,3 +488,26 @@ def test_physics_shaped_config_sampled(fg, mode):
         sel.append(m)
     want_out = fo.node_infer_batched(sd, [subs[i] for i in ids], sel, "node_cls", 128).numpy()
     assert_close(out, want_out)
+
+
+def test_csr_cache_never_serves_a_stale_graph(fg):
+    """The drop-in GCNConv caches gcn_norm per edge_index tensor object; a new tensor that reuses the address (and
+    shape) of a freed one must not hit the old entry, and in-place edits must invalidate."""
+    conv = fg.GCNConv(4, 8).to(dev()).eval()
+    x = torch.rand(6, 4, device=dev())
+    with torch.no_grad():
+        for trial in range(20):
+            g = torch.Generator().manual_seed(trial)
+            src = torch.randint(0, 6, (9,), generator=g)
+            dst = torch.randint(0, 6, (9,), generator=g)
+            ei = torch.stack([src, dst]).to(dev())  # same shape every time; freed at the end of each iteration
+            want = fo.gcn_conv_fp64(x.cpu().numpy(), ei.cpu().numpy(), conv.lin.weight.cpu().numpy(), conv.bias.cpu().numpy())
+            assert_close(conv(x, ei).cpu().numpy(), want)
+            del ei
+        ei = torch.tensor([[0, 1], [1, 0]], device=dev())
+        a = conv(x, ei).clone()
+        ei[0, 0] = 2  # in-place edit bumps _version
+        b = conv(x, ei)
+        want = fo.gcn_conv_fp64(x.cpu().numpy(), ei.cpu().numpy(), conv.lin.weight.cpu().numpy(), conv.bias.cpu().numpy())
+        assert_close(b.cpu().numpy(), want)
+        assert not torch.equal(a, b)
