@@ -726,7 +726,11 @@ static int launch(const GatherArgs& ga, const CUtensorMap& a_hi, const CUtensorM
     smem = w_bytes + (size_t)n_stages * 2 * A_PLANE_BYTES + FIXED;
   }
   auto kern = gemm_bf16x3_kernel<BLOCK_N, GATHER>;
-  FG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t smem_configured = 0;  // per instantiation; raised outside of stream capture by the first (warm-up) call
+  if (smem > smem_configured) {
+    FG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    smem_configured = SMEM_LIMIT;
+  }
   kern<<<grid, GATHER ? THREADS_GATHER : THREADS, smem, st>>>(ga, a_hi, a_lo, w_hi, w_lo, y_map, y_lo_map, tma_store, bias,
                                                               M, K, N, act, head, Y, ldy, w_stationary, n_stages);
   FG_LAUNCH_CHECK();

@@ -230,6 +230,28 @@ class PackedForward:
         res = self._gemm(h, self.Wl, self.bl, ops.ACT_NONE, self.head, N=self.C, K=self.H, name="head", out=out)
         return res if view is None else view
 
+    def capture(self, X_example):
+        """CUDA-graph the whole forward (the small configs are launch-bound): returns run(X) that copies X
+        into a static buffer, replays the captured launches and returns the static output tensor."""
+        static_x = self.pad_features(X_example).clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self(static_x)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_out = self(static_x)
+
+        def run(X):
+            static_x[:, : X.shape[1]].copy_(X)
+            graph.replay()
+            return static_out
+
+        run.graph, run.static_out = graph, static_out
+        return run
+
     def scatter_to_nodes(self, out, n_nodes=None):
         """Core-row outputs (pack order) -> [N, C] in global node order."""
         n_nodes = self.pack.n_nodes if n_nodes is None else n_nodes

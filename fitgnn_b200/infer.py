@@ -71,3 +71,29 @@ def per_query(state_dict, pack: Pack, X, query_nodes: torch.Tensor, task="node_c
     lookup = torch.full((pack.n_nodes,), -1, dtype=torch.long, device=dev)
     lookup[ids] = torch.arange(ids.numel(), device=dev)
     return out[lookup[q]]
+
+
+def graph_level_Gs(state_dict, pack: Pack, X, graph_of_sub: torch.Tensor, task="graph_reg", precision="fp32"):
+    """Graph-level models on subgraphs (Classify_graph_gs / Regress_graph_gs, /root/reference/network.py:118-135,
+    :189-204) for a whole dataset at once: `pack` holds the subgraphs of ALL graphs (subgraphs numbered graph by graph,
+    as main.py:370-381 builds them), `graph_of_sub[s]` is the graph each subgraph belongs to (non-decreasing).
+    conv stack on every subgraph -> rows with M.mask -> global max / mean pool per graph -> lt1 -> softmax / identity.
+    Returns [n_graphs, C]."""
+    from . import ops
+    dev = pack.device
+    fwd = PackedForward(pack, state_dict, rows="mask", precision=precision, with_head=False)
+    h = fwd(X)
+    if isinstance(h, tuple):
+        raise RuntimeError("graph_level_Gs needs the fp32 hidden state")
+    rows = pack.mask_rows().long()
+    sp = pack.sub_ptr.long()
+    sub_of_row = torch.repeat_interleave(torch.arange(pack.n_sub, device=dev), sp[1:] - sp[:-1])
+    g = graph_of_sub.to(dev).long()[sub_of_row[rows]]
+    assert bool((g[1:] >= g[:-1]).all()), "subgraphs must be numbered graph by graph"
+    n_graphs = int(graph_of_sub.max().item()) + 1
+    seg_ptr = torch.zeros(n_graphs + 1, dtype=torch.int32, device=dev)
+    seg_ptr[1:] = torch.cumsum(torch.bincount(g, minlength=n_graphs), 0).to(torch.int32)
+    pooled = ops.segment_pool(h, None, seg_ptr, ops.POOL_MAX if task == "graph_cls" else ops.POOL_MEAN)
+    w = state_dict["lt1.weight"].detach().to(dev).float().contiguous()
+    b = state_dict["lt1.bias"].detach().to(dev).float().contiguous()
+    return ops.gemm_bias_act(pooled, w, b, ops.ACT_NONE, ops.HEAD_SOFTMAX if task == "graph_cls" else ops.HEAD_IDENTITY)

@@ -138,9 +138,6 @@ class _ConvStack(torch.nn.Module):
             module.reset_parameters()
         self.lt1.reset_parameters()
 
-    def _check_eval(self):
-        pass  # kept for API stability: training mode is supported (dropout + autograd)
-
     def _convs(self, x, edge_index):
         # network.py:30-33: conv -> F.elu -> F.dropout(training=self.training); ELU is fused into the conv epilogue
         for i in range(self.num_layers):
@@ -169,7 +166,6 @@ class Classify_node(_ConvStack):
     _head, _rows = "log_softmax", "core"
 
     def forward(self, x, edge_index):
-        self._check_eval()
         return self._lt1(self._convs(x, edge_index), ops.HEAD_LOG_SOFTMAX)
 
 
@@ -179,7 +175,6 @@ class Regress_node(_ConvStack):
     _head, _rows = "identity", "core"
 
     def forward(self, x, edge_index):
-        self._check_eval()
         return self._lt1(self._convs(x, edge_index), ops.HEAD_IDENTITY)
 
 
@@ -211,7 +206,6 @@ class GraphBatch:
 
 class _GraphGs(_ConvStack):
     def _forward_gs(self, set_gs, batch_tensor, pool, head):
-        self._check_eval()
         dev = self.lt1.weight.device
         gb = set_gs if isinstance(set_gs, GraphBatch) else GraphBatch(set_gs, batch_tensor, dev)
         x = self._convs(gb.x, gb.edge_index)
@@ -221,7 +215,6 @@ class _GraphGs(_ConvStack):
 
 class _GraphGc(_ConvStack):
     def _forward_gc(self, gc, pool, head):
-        self._check_eval()
         x, edge_index, batch = gc.x, gc.edge_index, gc.batch
         _require_cuda(x)
         n_graphs = int(batch.max().item()) + 1

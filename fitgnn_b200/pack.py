@@ -73,6 +73,25 @@ class Pack:
             rows &= ~(core & (gid >= lo) & (gid < hi))
         return rows
 
+    # ---- on-disk form (the reference pickles its subgraph lists: main.py:131-172; a pack is ten flat arrays) -------
+    _ARRAYS = ("rowptr", "col", "dinv", "gid", "sub_ptr", "core_rows", "is_core", "mask", "part")
+    _SCALARS = ("n_rows", "nnz", "n_sub", "n_core", "n_src", "n_nodes", "mode")
+
+    def save(self, path):
+        blob = {k: getattr(self, k) for k in self._SCALARS}
+        blob.update({k: (getattr(self, k).cpu() if getattr(self, k) is not None else None) for k in self._ARRAYS})
+        blob["format"] = "fitgnn_b200.pack.v1"
+        torch.save(blob, path)
+
+    @staticmethod
+    def load(path, device="cuda"):
+        blob = torch.load(path, map_location="cpu", weights_only=True)
+        if blob.get("format") != "fitgnn_b200.pack.v1":
+            raise ValueError(f"{path} is not a fitgnn_b200 pack")
+        kw = {k: blob[k] for k in Pack._SCALARS}
+        kw.update({k: (blob[k].to(device) if blob[k] is not None else None) for k in Pack._ARRAYS})
+        return Pack(**kw)
+
     def nbytes(self):
         return sum(t.numel() * t.element_size() for t in
                    (self.rowptr, self.col, self.dinv, self.gid, self.sub_ptr, self.core_rows, self.is_core, self.mask))

@@ -84,3 +84,38 @@ def test_training_steps_follow_the_oracle(fg):
     model.train()
     a = model(x.to(DEV), ei.to(DEV)); b = model(x.to(DEV), ei.to(DEV))
     assert not torch.equal(a, b)
+
+
+def test_packed_train_step_and_pack_roundtrip(fg, tmp_path):
+    """train_step_Gs on a pack (all subgraphs in one forward/backward) lowers the loss and equals the collated-batch loss;
+    Pack.save / Pack.load round-trips bit-exactly."""
+    d = gio.load("node_small")
+    comps = gio.components(d, "extra")
+    cos = gio.coarsenings_for_oracle(d, "extra", comps)
+    partition = fg.coarsen.partition_from_components(comps, [c["C"] if c else None for c in cos], int(d["n"]))
+    pack = fg.build_pack(torch.tensor(d["edge_index"], device=DEV), torch.tensor(partition.part), partition.k, "extra")
+    path = tmp_path / "pack.pt"
+    pack.save(path)
+    again = fg.Pack.load(path, DEV)
+    for name in fg.Pack._ARRAYS:
+        assert torch.equal(getattr(pack, name), getattr(again, name)), name
+    assert (again.n_rows, again.nnz, again.mode) == (pack.n_rows, pack.nnz, pack.mode)
+    args = argparse.Namespace(num_layers1=2, num_features=d["x"].shape[1], hidden=32, num_classes=int(d["n_classes"]),
+                              layer_name="GCNConv")
+    model = fg.Classify_node(args); model.load_state_dict(gio.state_dict(d)); model = model.to(DEV)
+    X, y, tm = torch.tensor(d["x"], device=DEV), torch.tensor(d["y"]), torch.tensor(d["train_mask"])
+    # loss of the packed forward == loss of the reference-style collated forward (eval mode: no dropout)
+    model.eval()
+    ref = gio.subgraphs(d, "extra_sub")
+    xc, eic = fo.collate(ref)
+    yc = torch.tensor(np.concatenate([r["y"] for r in ref])).long().to(DEV)
+    tmc = torch.tensor(np.concatenate([r["train_mask"] for r in ref])).to(DEV)
+    l_ref = torch.nn.functional.nll_loss(model(xc.to(DEV), eic.to(DEV))[tmc], yc[tmc])
+    out = fg.train.forward_on_pack(model, pack, X)
+    rows = pack.split_masks(tm)
+    l_pack = torch.nn.functional.nll_loss(out[rows], y.to(DEV)[pack.gid.long()][rows])
+    close(l_pack, l_ref, rtol=1e-5)
+    opt = torch.optim.Adam(model.parameters(), lr=0.01, weight_decay=0.0005)
+    torch.manual_seed(0)
+    losses = [fg.train.train_step_Gs(model, again, X, y, tm, opt) for _ in range(15)]
+    assert losses[-1] < losses[0]
