@@ -511,3 +511,70 @@ def test_csr_cache_never_serves_a_stale_graph(fg):
         want = fo.gcn_conv_fp64(x.cpu().numpy(), ei.cpu().numpy(), conv.lin.weight.cpu().numpy(), conv.bias.cpu().numpy())
         assert_close(b.cpu().numpy(), want)
         assert not torch.equal(a, b)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_pack_builder_duplicates_self_loops_and_isolated(fg, mode):
+    """Edge cases of the input COO: duplicate edges (kept, they count twice in gcn_norm), self loops (dropped and
+    re-added once), isolated nodes and 1-2 node components — all three modes against the oracle builder."""
+    import scipy.sparse as sp_
+    n = 400
+    ei = fg.synth.powerlaw_graph(n - 30, 700, seed=9)  # the last 30 nodes stay isolated / tiny
+    extra_pairs = np.array([[n - 30, n - 29], [n - 29, n - 30], [n - 28, n - 27], [n - 27, n - 28], [n - 27, n - 26], [n - 26, n - 27]]).T
+    ei = np.concatenate([ei, extra_pairs], 1)
+    partition, comps, C_list = fg.synth.neighborhood_partition(ei, n, 0.4, seed=9)
+    rng = np.random.default_rng(9)
+    dup = ei[:, rng.choice(ei.shape[1], 60, replace=False)]
+    loops = np.stack([rng.integers(0, n, 25)] * 2)
+    ei2 = np.concatenate([ei, dup, dup[:, :10], loops], 1)
+    ei2 = np.ascontiguousarray(ei2[:, rng.permutation(ei2.shape[1])])
+    X = fg.synth.features(n, 8, seed=9)
+    cos = []
+    for comp, Cm in zip(comps, C_list):
+        if Cm is None:
+            cos.append(None); continue
+        part_c, _ = fo.partition_of(Cm)
+        relabel = np.full(n, -1); relabel[comp] = np.arange(len(comp))
+        em = relabel[ei2[0]] >= 0
+        r, c, v = fo.project_adj_pattern(relabel[ei2[:, em]], part_c, Cm.shape[0])
+        cos.append(dict(part=part_c, CX=fo.project_features(Cm, X.numpy()[comp]),
+                        adj=sp_.csr_matrix((v > 0, (r, c)), shape=(Cm.shape[0], Cm.shape[0]))))
+    subs = fo.build_subgraphs(ei2, X.numpy(), np.zeros(n, dtype=np.int64), comps, cos, mode)
+    want = fo.expected_pack(subs, n, mode)
+    pack = fg.build_pack(torch.tensor(ei2, device=dev()), torch.tensor(partition.part), partition.k, mode)
+    for name in ("rowptr", "col", "gid", "sub_ptr", "core_rows", "is_core", "mask"):
+        assert np.array_equal(getattr(pack, name).cpu().numpy().astype(np.int64), np.asarray(want[name]).astype(np.int64)), name
+    assert np.array_equal(pack.dinv.cpu().numpy(), want["dinv"])
+    # logits of the whole pack against the oracle forward on the reference-style subgraph list
+    sd = fo.init_state_dict(8, 64, 3, seed=9)
+    Xg = X
+    if mode == "cluster":
+        proj = fg.coarsen.project(torch.tensor(ei2, device=dev()), X.to(dev()), partition)
+        xc = proj["Xc"].cpu()
+        for i, co in enumerate(cos):
+            if co is None:
+                xc[int(partition.sub_offset[i])] = X[comps[i][0]]
+        Xg = torch.cat([X, xc], 0)
+    out, ids = fg.infer.node_infer_Gs(sd, pack, Xg.to(dev()))
+    sel = []
+    for s in subs:
+        m = np.zeros(s["x"].shape[0], dtype=bool)
+        m[np.searchsorted(s["orig_idx"], s["core"])] = True
+        sel.append(m)
+    assert_close(out.detach().cpu().numpy(), fo.node_infer_batched(sd, subs, sel, "node_cls", 128).numpy())
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_pack_builder_edgeless_graph(fg, mode):
+    """No edges at all: every node is its own single-node subgraph with only its self loop (utils.py:352-368)."""
+    n = 37
+    ei = torch.zeros(2, 0, dtype=torch.long, device=dev())
+    pack = fg.build_pack(ei, torch.arange(n, dtype=torch.int32), n, mode)
+    assert (pack.n_rows, pack.nnz, pack.n_sub) == (n, n, n)
+    assert torch.equal(pack.col.cpu(), torch.arange(n, dtype=torch.int32))
+    assert torch.equal(pack.dinv.cpu(), torch.ones(n))
+    sd = fo.init_state_dict(5, 16, 3, seed=1)
+    X = torch.rand(n + (n if mode == "cluster" else 0), 5)
+    out, ids = fg.infer.node_infer_Gs(sd, pack, X.to(dev()))
+    want = fo.classify_node(sd, X[:n], torch.zeros(2, 0, dtype=torch.long))  # isolated nodes: out = lin(x) + b
+    assert_close(out.detach().cpu().numpy(), want.numpy()[ids.cpu().numpy()])
