@@ -43,6 +43,11 @@ def parse():
     p.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--profiler-range", action="store_true",
+                   help="cudaProfilerStart/Stop around the timed steps (for `ncu --profile-from-start off`)")
+    p.add_argument("--no-projection", action="store_true", help="skip the Gc projection kernels (Xc = C·X, Ac = P·A·P^T)")
+    p.add_argument("--no-fuse-aggregate", action="store_true",
+                   help="classic schedule: stand-alone SpMM per layer instead of the aggregation fused into the transform")
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--chunks", type=int, default=1, help="N>1: chunks per rank; chunk c's all-gather overlaps chunk c+1")
     return p.parse_args()
@@ -174,6 +179,61 @@ def config_of(args, n, F, C, k):
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
+def _time_cuda(fn, reps=3, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts)), r
+
+
+def projection_bench(fg, ei, part, cw, k, X, n, F):
+    """The coarsened-graph projection on the same graph: group nodes by cluster, Xc = C·X
+    (fp64 accumulate), Ac = P·A·P^T pattern + counts.  Algorithmic bytes per SURVEY §8d."""
+    hbm_peak, _, _ = measured_peaks()
+    E = ei.shape[1]
+    t_grp, (members, member_ptr) = _time_cuda(lambda: fg.ops.group_by_part(part, k))
+    t_xc, Xc = _time_cuda(lambda: fg.ops.project_features(members, member_ptr, cw, X))
+    b_xc = 4 * n * F + 4 * k * F + 12 * n + 4 * (k + 1)
+    del Xc
+    t_ac, (row, col, cnt, rowptr) = _time_cuda(lambda: fg.ops.project_adj(ei, part, k), reps=2)
+    nnz_ac = int(row.numel())
+    b_ac = 16 * E + 4 * n + 20 * nnz_ac
+    del row, col, cnt, rowptr
+    torch.cuda.empty_cache()
+    return {"group_by_part_ms": t_grp,
+            "xc": {"kernel": "project_features_kernel", "ms": t_xc, "algo_GB": b_xc / 1e9, "GBps": b_xc / t_xc / 1e6,
+                   "frac": b_xc / t_xc / 1e6 / hbm_peak, "bound": "hbm"},
+            "ac": {"kernel": "adj_keys + radix sort + run-length (plan + fill, incl. 3 host syncs)", "ms": t_ac,
+                   "algo_GB": b_ac / 1e9, "GBps": b_ac / t_ac / 1e6, "frac": b_ac / t_ac / 1e6 / hbm_peak,
+                   "nnz_ac": nnz_ac, "directed_edges": E, "bound": "hbm (sort passes are not algorithmic bytes)"}}
+
+
+def spmm_standalone_bench(fg, pack, H):
+    """The H-wide segmented SpMM as its own launch on the same pack (the default schedule fuses this aggregation into
+    the previous transform's epilogue, so it is timed here on its own): fp32 in, bf16 hi/lo planes out."""
+    hbm_peak, _, _ = measured_peaks()
+    Hm = torch.rand(pack.n_rows, H, device=pack.device)
+    hubs = fg.ops.find_hubs(pack.rowptr, None, pack.n_rows)
+    out = (torch.empty(pack.n_rows, H, dtype=torch.bfloat16, device=pack.device),
+           torch.empty(pack.n_rows, H, dtype=torch.bfloat16, device=pack.device))
+    t, _ = _time_cuda(lambda: fg.ops.spmm_symnorm(pack.rowptr, pack.col, pack.dinv, Hm, H, None, None, 0, None, out=out,
+                                                  split=True, hubs=hubs), reps=5, warm=2)
+    R = pack.n_rows
+    b = 4 * (R + 1) + 4 * pack.nnz + 4 * R + 4 * R * H + 4 * R * H
+    return {"kernel": "spmm_512_standalone", "bound": "hbm", "achieved": b / t / 1e6, "peak": hbm_peak, "unit": "GB/s",
+            "frac": b / t / 1e6 / hbm_peak, "frac_of_nominal_8000": b / t / 1e6 / 8000.0, "traffic": None,
+            "algorithmic_bytes": int(b), "ms": t, "peak_source": "measured (hbm_gbs)",
+            "note": "stand-alone launch on the same pack; the default schedule fuses this aggregation into gemm0's epilogue"}
+
+
 def main_ours(args):
     import torch.distributed as dist
 
@@ -195,6 +255,7 @@ def main_ours(args):
     pack = fg.build_pack(ei, part, k, args.mode)
     torch.cuda.synchronize()
     pack_build_ms = (time.perf_counter() - t0) * 1e3
+    projection = projection_bench(fg, ei, part, cw, k, X, n, F) if (rank == 0 and world == 1 and not args.no_projection) else None
     ei_keep = ei if (rank == 0 and not args.no_cpu_baseline) else None
     del ei
     if args.mode == "cluster":
@@ -204,7 +265,8 @@ def main_ours(args):
     precision = args.precision
     if precision == "auto":
         precision = os.environ.get("FITGNN_PRECISION", "bf16x3")
-    fwds = [fg.PackedForward(lp, sd, head="log_softmax", rows="core", precision=precision) for lp in shard.locals]
+    fwds = [fg.PackedForward(lp, sd, head="log_softmax", rows="core", precision=precision,
+                             fuse_aggregate=False if args.no_fuse_aggregate else "auto") for lp in shard.locals]
     fwd = fwds[0]
     Xd = fwd.pad_features(X)
 
@@ -230,23 +292,33 @@ def main_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
+    # nvidia-smi takes a few hundred ms to initialise NVML and can stall kernel launches while it does: start it before
+    # the warm-up and wait for its first sample, so that only its steady 200 ms polling overlaps the timed region
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    if rank == 0:
+        t_wait = time.time()
+        while not sampler.rows and time.time() - t_wait < 10.0:
+            time.sleep(0.05)
+        sampler.rows.clear()  # keep only samples taken from here on
     for f in fwds:
         f.enable_profile(True)
     launches0 = sum(f.launches for f in fwds)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if args.profiler_range:
+        torch.cuda.cudart().cudaProfilerStart()
     ev0.record()
     for _ in range(args.steps):
         out = step()
     ev1.record()
     barrier()
+    if args.profiler_range:
+        torch.cuda.cudart().cudaProfilerStop()
     ms = ev0.elapsed_time(ev1) / args.steps
     gpu_launches = sum(f.launches for f in fwds) - launches0
     prof = {}
@@ -376,16 +448,22 @@ def main_ours(args):
 
     spmm_names = [k_ for k_ in kernels if k_.startswith("spmm")]
     spmm_main = max(spmm_names, key=lambda k_: kernels[k_]["algo_GB"]) if spmm_names else dom
+    fused = fwd.apack is not None
+    spmm_roof = spmm_standalone_bench(fg, shard.locals[0], args.hidden) if (fused and world == 1) else roofline_of(spmm_main)
     line = {"metric": METRIC, "value": n / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32" if precision == "fp32" else "bf16x3(f32 accumulate)", "data": "synthetic",
-            "config": config_of(args, n, F, C, k), "roofline": roofline_of(dom), "roofline_spmm": roofline_of(spmm_main),
+            "config": config_of(args, n, F, C, k), "roofline": roofline_of(dom), "roofline_spmm": spmm_roof,
+            "schedule": ("spmm0 -> [transform + next layer's aggregation in the epilogue] -> transform -> head (group-aligned "
+                         f"pack, {fwd.apack.n_rows} rows incl. padding)") if fused else "spmm + transform per layer -> head",
             "kernels": kernels, "gpu_launches": gpu_launches, "clocks": sampler.summary(),
             "pack": {"rows": pack.n_rows, "nnz": pack.nnz, "subgraphs": pack.n_sub, "build_ms": pack_build_ms,
                      "bytes": pack.nbytes(), "rank_loads": shard.loads},
             "multi_gpu": {"chunks_per_rank": n_chunks, "rank_kernel_ms": rank_kernel_ms,
                           "all_gather_bytes": int(n * Cp * 4) if world > 1 else 0,
                           "exposed_ms": (ms - max(rank_kernel_ms)) if rank_kernel_ms else 0.0}}
+    if projection:
+        line["projection"] = projection
     if e2e:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:

@@ -64,6 +64,28 @@ struct Bump {
 
 static inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 
+#ifdef __CUDACC__
+// ---- device helpers shared by the SpMM and GEMM epilogues -------------------------------------------------------
+// two fp32 -> packed bf16x2 (round to nearest even), `a` in the low half: one F2FP on the ALU pipe instead of two
+// single conversions on the quarter-rate XU pipe plus a PRMT
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// hi/lo bf16 split of two fp32 values: hi = rn_bf16(x), lo = rn_bf16(x - hi), each packed as bf16x2 (x0 low half)
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16x2_rn(x0, x1);
+  lo = pack_bf16x2_rn(x0 - __uint_as_float(hi << 16), x1 - __uint_as_float(hi & 0xffff0000u));
+}
+// ELU (alpha = 1, network.py:32): exp through one MUFU.EX2 (flush-to-zero), absolute error <= ~2e-7
+__device__ __forceinline__ float elu_fast(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+  return x > 0.f ? x : e - 1.0f;
+}
+#endif
+
 // --- internal primitives (primitives.cu) ------------------------------------------------
 size_t scan_ws_bytes(int64_t n);
 // out[i] = sum_{j<i} in[j] for i < n_out, with in[j] = 0 for j >= n_in (so n_out = n_in+1 yields the total)

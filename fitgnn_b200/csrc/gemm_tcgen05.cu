@@ -43,6 +43,19 @@ struct GatherArgs {
   int64_t ldx;
   int nq;                  // float4 per feature row (width / 4)
 };
+// Epilogue extensions.
+//  * agg_desc / agg_dinv (AGG instantiation): the rows form a group-aligned pack (align.cu) and the epilogue applies
+//    the NEXT layer's normalised aggregation to the activated tile before storing it:
+//        G[r,:] = dinv[r] * ( dinv[r]*h[r,:] + sum_{c in desc(r)} dinv[c]*h[c,:] ),   h = act(A·W^T + bias)
+//    Thread = row and a warp's 32 rows are exactly one aligned group, so every neighbour c is another lane of the same
+//    warp: the exchange is register-to-register (__shfl_sync), no shared memory, no HBM round trip for h.
+//  * row_map: output row m is written to Y row row_map[m] (skipped when negative) with per-thread stores instead of
+//    TMA boxes — used by the head to drop the padding rows / scatter straight into the caller's row order.
+struct EpiArgs {
+  const unsigned long long* agg_desc;  // [M] bits [0,4) = entry count (<= 12), then 5-bit lanes
+  const float* agg_dinv;               // [M] deg^-1/2 (0 for padding rows)
+  const int32_t* row_map;              // [M] or null
+};
 constexpr int EPI_WARP0 = 2;
 constexpr int ACC_STAGES = 2;
 constexpr uint32_t A_PLANE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
@@ -160,7 +173,7 @@ __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::be
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // branchless ELU: exp via MUFU.EX2, absolute error <= ~2e-7 (far below the fp32 re-association noise of the GEMM)
-__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : __expf(x) - 1.0f; }
+__device__ __forceinline__ float elu1(float x) { return elu_fast(x); }
 
 __host__ __device__ constexpr int tmem_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 __host__ __device__ constexpr uint32_t stage_bytes(int block_n) { return 2 * A_PLANE_BYTES + 2 * (uint32_t)block_n * BLOCK_K * 2; }
@@ -171,9 +184,9 @@ __host__ __device__ constexpr int num_stages(int block_n) {
   return s > 8 ? 8 : s;
 }
 
-template <int BLOCK_N, bool GATHER>
+template <int BLOCK_N, bool GATHER, bool AGG>
 __global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS, 1)
-gemm_bf16x3_kernel(const GatherArgs ga, const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                    const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_y_lo,
                    int tma_store, const float* __restrict__ bias, int64_t M, int K, int N, int act, int head,
@@ -398,13 +411,7 @@ gemm_bf16x3_kernel(const GatherArgs ga, const __grid_constant__ CUtensorMap map_
           const float x[4] = {acc[v].x * ia.dr, acc[v].y * ia.dr, acc[v].z * ia.dr, acc[v].w * ia.dr};
           uint32_t hi[2], lo[2];
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * u]), h1 = __float2bfloat16_rn(x[2 * u + 1]);
-            const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * u] - __bfloat162float(h0));
-            const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * u + 1] - __bfloat162float(h1));
-            hi[u] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            lo[u] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-          }
+          for (int u = 0; u < 2; ++u) split_bf16x2(x[2 * u], x[2 * u + 1], hi[u], lo[u]);
           const int cc64 = c & 63;
           const uint32_t a = smem_base + (stage + kb) * stage_bytes_rt + lr * 128 +
                              ((uint32_t)(cc64 >> 3) ^ (uint32_t)(lr & 7)) * 16 + ((cc64 & 7) >> 2) * 8;
@@ -444,15 +451,36 @@ gemm_bf16x3_kernel(const GatherArgs ga, const __grid_constant__ CUtensorMap map_
     const int box_beg = col_group == 0 ? 0 : split_at;
     const int box_end = col_group == 0 ? split_at : N_BOXES;
     int64_t it = 0;
+    // aggregation descriptor + dinv of this thread's row, fetched one tile ahead of its use
+    unsigned long long desc_next = 0ull;
+    float dr_next = 0.f;
+    auto load_agg = [&](int64_t t) {
+      desc_next = 0ull;
+      dr_next = 0.f;
+      if (AGG && t < tiles) {
+        const int64_t mm = (t / n_tiles) * BLOCK_M + row_in_tile;
+        if (mm < M) {
+          desc_next = __ldg(ea.agg_desc + mm);
+          dr_next = __ldg(ea.agg_dinv + mm);
+        }
+      }
+    };
+    load_agg(t_first);
     for (int64_t t = t_first; t < tiles; t += t_step, ++it) {
       const uint32_t acc = (uint32_t)(it % ACC_STAGES);
       const uint32_t acc_phase = (uint32_t)((it / ACC_STAGES) & 1);
       const int64_t m = (t / n_tiles) * BLOCK_M + row_in_tile;
       const int n0 = (int)(t % n_tiles) * BLOCK_N;
+      const unsigned long long desc = desc_next;
+      const float dr = dr_next;
+      load_agg(t + t_step);
+      const int agg_cnt = (int)(desc & 15ull);
+      const int agg_max = AGG ? __reduce_max_sync(0xffffffffu, agg_cnt) : 0;
       mbar_wait(tfull_bar(acc), acc_phase);
       fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
-      float* yrow = Y + m * ldy + n0;
+      const int64_t dest_row = (ea.row_map && m < M) ? (int64_t)__ldg(ea.row_map + m) : m;
+      float* yrow = Y + dest_row * ldy + n0;
       float row_max = -INFINITY, row_sum = 0.f;
       bool exchanged = false;
       auto exchange_stats = [&](float lmax, float lsum) {
@@ -517,6 +545,27 @@ gemm_bf16x3_kernel(const GatherArgs ga, const __grid_constant__ CUtensorMap map_
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = elu1(v[j]);
         }
+        if (AGG) {
+          // next layer's aggregation over the warp's aligned group (see EpiArgs); padding rows (dr = 0) give 0 * h = 0
+          // (the A operand's padding rows must hold finite values: the engine's SpMM writes zeros there)
+          float u[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            u[j] = v[j] * dr;
+            v[j] = u[j];
+          }
+          for (int sl = 0; sl < agg_max; ++sl) {
+            const bool on = sl < agg_cnt;
+            const int src = on ? (int)((desc >> (4 + 5 * sl)) & 31ull) : lane;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float tv = __shfl_sync(0xffffffffu, u[j], src);
+              if (on) v[j] += tv;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= dr;
+        }
         if (use_fast_head) {
           float lmax = -INFINITY, lsum = 0.f;
 #pragma unroll
@@ -547,14 +596,7 @@ gemm_bf16x3_kernel(const GatherArgs ga, const __grid_constant__ CUtensorMap map_
             for (int j = 0; j < 4; ++j) {
               uint32_t hi[4], lo[4];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const float x0 = v[8 * j + 2 * u], x1 = v[8 * j + 2 * u + 1];
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-                const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
-                const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-                hi[u] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                lo[u] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-              }
+              for (int u = 0; u < 4; ++u) split_bf16x2(v[8 * j + 2 * u], v[8 * j + 2 * u + 1], hi[u], lo[u]);
               const uint32_t a = buf + lane * 64 + ((uint32_t)j ^ (uint32_t)((lane >> 1) & 3)) * 16;
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]),
                            "r"(hi[3]) : "memory");
@@ -576,15 +618,16 @@ gemm_bf16x3_kernel(const GatherArgs ga, const __grid_constant__ CUtensorMap map_
             if (tma_store == 2) tma_store_2d(&map_y_lo, buf + EPI_BOX_BYTES / 2, n0 + c0, m_base);
             bulk_commit();
           }
-        } else if (m < M) {
-          if (vec_ok && n0 + c0 + 32 <= N) {
+        } else if (m < M && dest_row >= 0) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
+          for (int j = 0; j < 32; j += 4) {
+            if (vec_ok && j + 4 <= box_cols && n0 + c0 + j + 4 <= N) {
               *reinterpret_cast<float4*>(yrow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < box_cols && n0 + c0 + j < N) yrow[c0 + j] = v[j];
+              for (int u = 0; u < 4; ++u)
+                if (j + u < box_cols && n0 + c0 + j + u < N) yrow[c0 + j + u] = v[j + u];
+            }
           }
         }
       }
@@ -668,8 +711,8 @@ static int make_store_map_bf16(CUtensorMap* map, void* base, int64_t rows, int64
   return FITGNN_OK;
 }
 
-template <int BLOCK_N, bool GATHER>
-static int launch(const GatherArgs& ga, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const void* W_hi, const void* W_lo, int64_t ldw,
+template <int BLOCK_N, bool GATHER, bool AGG>
+static int launch(const GatherArgs& ga, const EpiArgs& ea, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const void* W_hi, const void* W_lo, int64_t ldw,
                   const float* bias, int64_t M, int K, int N, int act, int head, float* Y, void* Y_lo, int64_t ldy,
                   int sms, cudaStream_t st) {
   CUtensorMap w_hi, w_lo;
@@ -685,6 +728,8 @@ static int launch(const GatherArgs& ga, const CUtensorMap& a_hi, const CUtensorM
     tma_store = 2;
     FG_TRY(make_store_map_bf16(&y_map, Y, M, N, ldy));
     FG_TRY(make_store_map_bf16(&y_lo_map, Y_lo, M, N, ldy));
+  } else if (ea.row_map) {
+    tma_store = 0;  // remapped rows: per-thread stores
   } else if (tma_store) {
     FG_TRY(make_store_map(&y_map, Y, M, N, ldy));
   }
@@ -725,13 +770,13 @@ static int launch(const GatherArgs& ga, const CUtensorMap& a_hi, const CUtensorM
     n_stages = (n_stages / k_blocks) * k_blocks;
     smem = w_bytes + (size_t)n_stages * 2 * A_PLANE_BYTES + FIXED;
   }
-  auto kern = gemm_bf16x3_kernel<BLOCK_N, GATHER>;
+  auto kern = gemm_bf16x3_kernel<BLOCK_N, GATHER, AGG>;
   static size_t smem_configured = 0;  // per instantiation; raised outside of stream capture by the first (warm-up) call
   if (smem > smem_configured) {
     FG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
     smem_configured = SMEM_LIMIT;
   }
-  kern<<<grid, GATHER ? THREADS_GATHER : THREADS, smem, st>>>(ga, a_hi, a_lo, w_hi, w_lo, y_map, y_lo_map, tma_store, bias,
+  kern<<<grid, GATHER ? THREADS_GATHER : THREADS, smem, st>>>(ga, ea, a_hi, a_lo, w_hi, w_lo, y_map, y_lo_map, tma_store, bias,
                                                               M, K, N, act, head, Y, ldy, w_stationary, n_stages);
   FG_LAUNCH_CHECK();
   return FITGNN_OK;
@@ -741,8 +786,11 @@ static int launch(const GatherArgs& ga, const CUtensorMap& a_hi, const CUtensorM
 
 int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi, const void* W_lo, int64_t ldw,
                 const float* bias, int64_t M, int K, int N, int act, int head, float* Y, void* Y_lo, int64_t ldy,
-                cudaStream_t st) {
+                const uint64_t* agg_desc, const float* agg_dinv, const int32_t* row_map, cudaStream_t st) {
   FG_REQUIRE(!Y_lo || head == FITGNN_HEAD_IDENTITY, FITGNN_EUNSUP, "gemm_bf16x3: split output cannot carry a head");
+  FG_REQUIRE(!agg_desc || (agg_dinv && head == FITGNN_HEAD_IDENTITY && !row_map && N > 128), FITGNN_EUNSUP,
+             "gemm_bf16x3: the fused aggregation needs dinv, no head, no row map and a wide output (N > 128)");
+  FG_REQUIRE(!row_map || !Y_lo, FITGNN_EUNSUP, "gemm_bf16x3: a row map needs fp32 output");
   FG_REQUIRE(head == FITGNN_HEAD_IDENTITY || N <= 256, FITGNN_EUNSUP,
              "gemm_bf16x3: a fused (log-)softmax head needs N <= 256 (got %d)", N);
   FG_REQUIRE(M < (1ll << 31) - 128, FITGNN_ERANGE, "gemm_bf16x3: M exceeds the TMA coordinate range");
@@ -756,8 +804,11 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
   FG_TRY(tc::make_map(&a_hi, A_hi, M, K, lda, tc::BLOCK_M));
   FG_TRY(tc::make_map(&a_lo, A_lo, M, K, lda, tc::BLOCK_M));
   const tc::GatherArgs ga{};
+  const tc::EpiArgs ea{reinterpret_cast<const unsigned long long*>(agg_desc), agg_dinv, row_map};
+  if (agg_desc)
+    return tc::launch<256, false, true>(ga, ea, a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y, Y_lo, ldy, sms, st);
 #define FG_TC(BN) \
-  return tc::launch<BN, false>(ga, a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y, Y_lo, ldy, sms, st)
+  return tc::launch<BN, false, false>(ga, ea, a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y, Y_lo, ldy, sms, st)
   if (N <= 16) FG_TC(16);
   if (N <= 32) FG_TC(32);
   if (N <= 48) FG_TC(48);
@@ -787,8 +838,9 @@ int gcn_layer_fused(const int32_t* rowptr, const int32_t* col, const float* dinv
   tc::GatherArgs ga{rowptr, col, dinv, X, src_index, out_rows, ldx, width / 4};
   CUtensorMap dummy;
   FG_TRY(tc::make_map(&dummy, W_hi, N, K, ldw, 16));  // placeholder for the unused A maps
-  return tc::launch<256, true>(ga, dummy, dummy, W_hi, W_lo, ldw, bias, M, K, N, act, FITGNN_HEAD_IDENTITY, Y, Y_lo, ldy,
-                               sms, st);
+  const tc::EpiArgs ea{nullptr, nullptr, nullptr};
+  return tc::launch<256, true, false>(ga, ea, dummy, dummy, W_hi, W_lo, ldw, bias, M, K, N, act, FITGNN_HEAD_IDENTITY, Y,
+                                      Y_lo, ldy, sms, st);
 }
 
 }  // namespace fitgnn

@@ -31,7 +31,7 @@ constexpr int SPMM_WARPS = 8;
 constexpr int SPMM_THREADS = SPMM_WARPS * 32;
 
 // branchless ELU (MUFU.EX2 path), absolute error <= ~2e-7
-__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : __expf(x) - 1.0f; }
+__device__ __forceinline__ float elu1(float x) { return elu_fast(x); }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
@@ -53,13 +53,11 @@ __device__ __forceinline__ void store_row4(void* Y, void* Ylo, int64_t off, floa
   if (!SPLIT) {
     *reinterpret_cast<float4*>(static_cast<float*>(Y) + off) = v;
   } else {
-    __nv_bfloat16 h[4], l[4];
-    split_bf16(v.x, h[0], l[0]);
-    split_bf16(v.y, h[1], l[1]);
-    split_bf16(v.z, h[2], l[2]);
-    split_bf16(v.w, h[3], l[3]);
-    *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(Y) + off) = *reinterpret_cast<uint2*>(h);
-    *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(Ylo) + off) = *reinterpret_cast<uint2*>(l);
+    uint2 h, l;
+    split_bf16x2(v.x, v.y, h.x, l.x);
+    split_bf16x2(v.z, v.w, h.y, l.y);
+    *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(Y) + off) = h;
+    *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(Ylo) + off) = l;
   }
 }
 
@@ -162,8 +160,9 @@ spmm_warp_row_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
 // software-pipelined kernel: LPR lanes per row, G = 32 / LPR rows per warp per step, rows_per_warp steps
 // ---------------------------------------------------------------------------------------------------------
 struct RowInfo {
-  int beg, end;  // CSR range (end = beg for rows this warp must not produce)
+  int beg, end;  // CSR range (end = beg for rows this warp must not gather)
   float dr;
+  bool live;     // this warp writes the row (false: out of range, or a hub row the hub kernel owns)
 };
 
 template <int NV, int LPR, bool SPLIT>
@@ -182,14 +181,18 @@ spmm_pipe_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
   if (warp_global * rows_per_warp * G >= n_out) return;
 
   auto load_info = [&](int step) {
-    RowInfo ri{0, 0, 0.f};
+    RowInfo ri{0, 0, 0.f, false};
     const int64_t i = i_base + (int64_t)step * G;
     if (step < rows_per_warp && i < n_out) {
       const int r = out_rows ? __ldg(out_rows + i) : (int)i;
       ri.beg = __ldg(rowptr + r);
       ri.end = __ldg(rowptr + r + 1);
       ri.dr = __ldg(dinv + r);
-      if (ri.end - ri.beg >= hub_deg) ri.end = ri.beg;  // the hub kernel owns this row
+      ri.live = true;
+      if (ri.end - ri.beg >= hub_deg) {  // the hub kernel owns this row
+        ri.end = ri.beg;
+        ri.live = false;
+      }
     }
     return ri;
   };
@@ -250,7 +253,7 @@ spmm_pipe_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
         const int c = (long_row) ? load_col(ia, e0) : -1;
         gather_chunk(acc, long_row ? max(0, min(ia.end - e0, LPR)) : 0, load_w(c), load_s(c), q0);
       }
-      if (deg > 0) {
+      if (ia.live) {  // empty rows (the padding rows of a group-aligned pack) are written too: act(bias), i.e. zeros
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
           const int q = q0 + sub + LPR * v;

@@ -9,6 +9,10 @@ Schedule (SURVEY §7 ideas 2-4; all preserve the reference's arithmetic up to fp
   * layers >= 1          : aggregate-first; the LAST layer aggregates only the rows the caller reads
                            (core rows for node tasks, M.mask rows for graph tasks)
   * head                 : lt1 (+ log_softmax / softmax) on those rows only
+  * fused aggregation    : when every row is an output row and every subgraph has <= 32 rows (the many-tiny-subgraphs
+                           regime of high coarsening ratios, e.g. the products workload) the pack is group-aligned once
+                           and layers >= 1 get their propagate from the PREVIOUS transform's epilogue
+                           (fitgnn_gcn_transform_aggregate): no SpMM launch and no fp32 round trip of the hidden state
 """
 from __future__ import annotations
 
@@ -30,7 +34,7 @@ class PackedForward:
     'core' (node tasks), 'mask' (graph tasks: x[mask], network.py:129) or 'all'."""
 
     def __init__(self, pack: Pack, state_dict, head="log_softmax", rows="core", precision="fp32",
-                 with_head=True, fuse_layer0=False):
+                 with_head=True, fuse_layer0=False, fuse_aggregate="auto"):
         self.pack = pack
         dev = pack.device
         self.precision = ops.GEMM_BF16X3 if precision == "bf16x3" else ops.GEMM_FP32
@@ -76,6 +80,17 @@ class PackedForward:
         self.fused_layer0 = None if fuse_layer0 else False
         self.prof = None  # set to {} by enable_profile(): op name -> dict(events, bytes, flops)
         self._nnz_cache = {}
+        # group-aligned pack + aggregation fused into the transform epilogues (see module docstring)
+        self.apack = None
+        eligible = (self.precision == ops.GEMM_BF16X3 and self.L >= 2 and not self.transform_first and with_head
+                    and self.out_rows is None and self.H > 128 and self.H % 8 == 0 and pack.n_rows > 0)
+        if fuse_aggregate and eligible:
+            ap = pack.aligned(32)
+            if ap is not None and ap.agg_ok:
+                self.apack = ap
+                self.hubs_aligned = ops.find_hubs(ap.rowptr, None, ap.n_rows)
+        if fuse_aggregate is True and self.apack is None:
+            raise ValueError("fuse_aggregate=True but the pack / model is not eligible for the fused aggregation")
 
     # -- per-kernel timing for the roofline report (CUDA events on the launching stream) ---------
     def enable_profile(self, on=True):
@@ -143,10 +158,12 @@ class PackedForward:
                                                            out=out, split_out=split_out),
                            nbytes=4 * (M * K + K * N + M * N), flops=2 * M * K * N)
 
-    def _spmm(self, X, width, src_index, bias, act, last, split, name="spmm"):
-        p = self.pack
+    def _spmm(self, X, width, src_index, bias, act, last, split, name="spmm", pack=None):
+        p = self.pack if pack is None else pack
         rows = self.out_rows if last else None
         hubs = self.hubs_out if last else self.hubs_all
+        if pack is not None:
+            hubs = self.hubs_aligned
         self.launches += 1 + (1 if hubs[1] > 0 else 0)
         n_src_rows = X.shape[0] if src_index is not None else p.n_rows
         return self._timed(name, lambda: ops.spmm_symnorm(p.rowptr, p.col, p.dinv, X, width, src_index, bias, act, rows,
@@ -185,6 +202,31 @@ class PackedForward:
         Xp[:, : X.shape[1]].copy_(X)
         return Xp
 
+    def _forward_aligned(self, X, out):
+        """spmm0 -> [transform + next layer's aggregation]* -> last transform -> head with the padding rows dropped."""
+        ap = self.apack
+        M = ap.n_rows
+        A = self._spmm(X, self.Fp, ap.gid, None, ops.ACT_NONE, False, split=True, name="spmm0", pack=ap)
+        K = self.Fp
+        for i in range(self.L - 1):
+            Ai, Ki = A, K
+            self.launches += 1
+            A = self._timed(f"gemm{i}_agg", lambda: ops.gcn_transform_aggregate(
+                Ai, self.W[i], self.b[i], ops.ACT_ELU, ap.agg_desc, ap.dinv, K=Ki, N=self.H),
+                nbytes=4 * (M * Ki + Ki * self.H + M * self.H) + 12 * M, flops=2 * M * Ki * self.H)
+            K = self.H
+        i = self.L - 1
+        h = self._gemm(A, self.W[i], self.b[i], ops.ACT_ELU, N=self.H, K=K, name=f"gemm{i}", split_out=True)
+        view = None
+        if out is None:
+            out = torch.empty(self.n_out, ops.pad4(self.C), dtype=torch.float32, device=X.device)
+            view = out[:, : self.C]
+        self.launches += 1
+        self._timed("head", lambda: ops.gemm_head_rows(h, self.Wl, self.bl, ops.ACT_NONE, self.head, ap.orig_row, out,
+                                                       K=self.H, N=self.C),
+                    nbytes=4 * (M * self.H + self.H * self.C + self.n_out * self.C) + 4 * M, flops=2 * M * self.H * self.C)
+        return out if view is None else view
+
     # -- forward -------------------------------------------------------------------------------
     @torch.no_grad()
     def __call__(self, X, out=None):
@@ -195,6 +237,8 @@ class PackedForward:
         assert X.is_cuda and X.dtype == torch.float32 and X.shape[0] == p.n_src and X.shape[1] in (self.F, self.Fp)
         bf = self.precision == ops.GEMM_BF16X3
         X = self.pad_features(X)
+        if self.apack is not None:
+            return self._forward_aligned(X, out)
         h = None
         for i in range(self.L):
             last = i == self.L - 1

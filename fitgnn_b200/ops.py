@@ -150,6 +150,40 @@ def gcn_layer_fused(rowptr, col, dinv, X, width, W, bias=None, act=ACT_NONE, src
     return out
 
 
+def gcn_transform_aggregate(A, W, bias, act, agg_desc, dinv, K=None, N=None, split_out=True):
+    """G = Â_local·act(A·W^T + bias) on a group-aligned pack: the next layer's propagate fused into the tensor-core
+    transform's epilogue.  A, W = bf16 (hi, lo) planes; agg_desc / dinv come from Pack.aligned()."""
+    (a_hi, a_lo), (w_hi, w_lo) = A, W
+    assert a_hi.dtype == torch.bfloat16 and w_hi.dtype == torch.bfloat16 and agg_desc.dtype == torch.int64
+    M = a_hi.shape[0]
+    K = a_hi.shape[1] if K is None else K
+    N = w_hi.shape[0] if N is None else N
+    assert agg_desc.numel() == M and dinv.numel() == M
+    if split_out:
+        out = (torch.empty(M, N, dtype=torch.bfloat16, device=a_hi.device),
+               torch.empty(M, N, dtype=torch.bfloat16, device=a_hi.device))
+        y, ylo, ldy = out[0], out[1], N
+    else:
+        out = torch.empty(M, N, dtype=torch.float32, device=a_hi.device)
+        y, ylo, ldy = out, None, N
+    check(lib().fitgnn_gcn_transform_aggregate(ptr(a_hi), ptr(a_lo), a_hi.stride(0), ptr(w_hi), ptr(w_lo), w_hi.stride(0),
+                                               ptr(bias), M, K, N, act, ptr(agg_desc), ptr(dinv), ptr(y), ptr(ylo), ldy,
+                                               stream_ptr()))
+    return out
+
+
+def gemm_head_rows(A, W, bias, act, head, row_map, out, K=None, N=None):
+    """head(act(A·W^T + bias)) with output row m written to out[row_map[m]] (skipped when row_map[m] < 0)."""
+    (a_hi, a_lo), (w_hi, w_lo) = A, W
+    M = a_hi.shape[0]
+    K = a_hi.shape[1] if K is None else K
+    N = w_hi.shape[0] if N is None else N
+    assert row_map.dtype == torch.int32 and row_map.numel() == M and out.dtype == torch.float32
+    check(lib().fitgnn_gemm_head_rows(ptr(a_hi), ptr(a_lo), a_hi.stride(0), ptr(w_hi), ptr(w_lo), w_hi.stride(0), ptr(bias),
+                                      M, K, N, act, head, ptr(row_map), ptr(out), out.stride(0), stream_ptr()))
+    return out
+
+
 def split_bf16(X, cols=None, ldo=None):
     """fp32 [rows, cols] -> bf16 (hi, lo) planes [rows, ldo] with zero-filled padding columns."""
     rows = X.shape[0]

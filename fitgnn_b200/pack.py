@@ -33,6 +33,11 @@ class Pack:
     is_core: torch.Tensor  # uint8 [n_rows]
     mask: torch.Tensor    # uint8 [n_rows]
     part: torch.Tensor | None = None  # int32 [N]
+    # group-aligned packs only (Pack.aligned): see include/fitgnn.h fitgnn_pack_align_*
+    orig_row: torch.Tensor | None = None    # int32 [n_rows] row of the source pack, -1 for padding rows
+    new_of_old: torch.Tensor | None = None  # int32 [source n_rows] aligned row of every source row
+    agg_desc: torch.Tensor | None = None    # int64 [n_rows] per-row neighbour lanes for the fused aggregation
+    agg_ok: bool = False                    # every row has <= 12 non-self entries: agg_desc is complete
 
     def struct(self) -> PackStruct:
         return PackStruct(self.n_rows, self.nnz, self.n_sub, self.n_core, self.n_src,
@@ -91,6 +96,37 @@ class Pack:
         kw = {k: blob[k] for k in Pack._SCALARS}
         kw.update({k: (blob[k].to(device) if blob[k] is not None else None) for k in Pack._ARRAYS})
         return Pack(**kw)
+
+    def aligned(self, group=32):
+        """The same pack re-laid-out so that no subgraph straddles a multiple of `group` rows (padding rows are empty
+        CSR rows with dinv = 0 at the tail of a group).  Returns None when a subgraph has more than `group` rows.
+        The result carries orig_row / new_of_old / agg_desc for fitgnn_gcn_transform_aggregate."""
+        dev = self.device
+        i32 = dict(dtype=torch.int32, device=dev)
+        new_sub = torch.empty(self.n_sub + 1, **i32)
+        ws = torch.zeros(64, dtype=torch.uint8, device=dev)
+        n_al, ok = C.c_int64(0), C.c_int(0)
+        check(lib().fitgnn_pack_align_plan(ptr(self.sub_ptr), self.n_sub, group, ptr(new_sub), C.byref(n_al),
+                                           C.byref(ok), ptr(ws), ws.numel(), stream_ptr()))
+        if not ok.value:
+            return None
+        n = n_al.value
+        a = Pack(n_rows=n, nnz=self.nnz, n_sub=self.n_sub, n_core=self.n_core, n_src=self.n_src, n_nodes=self.n_nodes,
+                 mode=self.mode, rowptr=torch.empty(n + 1, **i32), col=torch.empty(self.nnz, **i32),
+                 dinv=torch.empty(n, dtype=torch.float32, device=dev), gid=torch.empty(n, **i32),
+                 sub_ptr=torch.empty(self.n_sub + 1, **i32), core_rows=torch.empty(self.n_core, **i32),
+                 is_core=torch.empty(n, dtype=torch.uint8, device=dev), mask=torch.empty(n, dtype=torch.uint8, device=dev),
+                 part=self.part, orig_row=torch.empty(n, **i32), new_of_old=torch.empty(self.n_rows, **i32),
+                 agg_desc=torch.empty(n, dtype=torch.int64, device=dev))
+        flags = C.c_int(0)
+        src, dst = self.struct(), a.struct()
+        check(lib().fitgnn_pack_align_fill(C.byref(src), ptr(new_sub), group, n, C.byref(dst), ptr(a.orig_row),
+                                           ptr(a.new_of_old), ptr(a.agg_desc), C.byref(flags), ptr(ws), ws.numel(),
+                                           stream_ptr()))
+        if flags.value & 6:
+            raise ValueError("Pack.aligned: the pack is not block-diagonal with one self loop per row")
+        a.agg_ok = (flags.value & 1) == 0
+        return a
 
     def nbytes(self):
         return sum(t.numel() * t.element_size() for t in

@@ -175,6 +175,46 @@ int fitgnn_gcn_layer_fused(const int32_t* rowptr, const int32_t* col, const floa
                            int64_t n_out, const void* W_hi, const void* W_lo, int64_t ldw,
                            const float* bias, int N, int act, void* Y, void* Y_lo, int64_t ldy,
                            void* stream);
+/* ------------------------------------------------------------------------------------------
+ * Group-aligned packs and the aggregation fused into the transform's epilogue.
+ * Between two conv layers the reference runs  x = F.elu(conv_i(x)); ...; conv_{i+1}(x)  (network.py:31-33), i.e. the
+ * activated output of one transform is immediately propagated over the same block-diagonal adjacency.  When every
+ * subgraph has at most 32 rows the pack can be re-laid-out so that no subgraph straddles a multiple of 32 rows
+ * (fitgnn_pack_align_*); a row's neighbours are then rows of its own group of 32, which is exactly one TMEM lane
+ * quadrant / one epilogue warp of the tensor-core transform, and the propagate step becomes register shuffles inside
+ * that epilogue (fitgnn_gcn_transform_aggregate) instead of an SpMM launch with an HBM round trip.
+ *
+ * fitgnn_pack_align_plan: new_sub_ptr[s] = first aligned row of subgraph s (device, [n_sub+1], last = aligned row
+ *   count, also returned in *host_n_rows_aligned); *host_alignable = 0 when some subgraph has more than `group` rows.
+ * fitgnn_pack_align_fill: fills the caller-allocated aligned pack `out` (n_rows = aligned row count; nnz, n_sub,
+ *   n_core, n_src as `in`): padding rows are empty CSR rows with dinv = 0, they belong to the subgraph they follow.
+ *   orig_row[aligned row] = row of `in` (-1 for padding), new_of_old[row of in] = aligned row,
+ *   agg_desc[aligned row] = bits [0,4): number c <= 12 of non-self CSR entries, bits [4+5j, 9+5j): row-in-group of the
+ *   j-th one (duplicates kept).  *host_flags: bit 0 = a row has more than 12 non-self entries (descriptor truncated:
+ *   do not use the fused aggregation), bit 1 = a row without self loop, bit 2 = an entry leaves its subgraph.
+ * Both need a 64-byte device workspace.  group must be 32.
+ * ---------------------------------------------------------------------------------------- */
+int fitgnn_pack_align_plan(const int32_t* sub_ptr, int64_t n_sub, int group, int32_t* new_sub_ptr,
+                           int64_t* host_n_rows_aligned, int* host_alignable, void* ws, size_t ws_bytes,
+                           void* stream);
+int fitgnn_pack_align_fill(const fitgnn_pack* in, const int32_t* new_sub_ptr, int group,
+                           int64_t n_rows_aligned, const fitgnn_pack* out, int32_t* orig_row,
+                           int32_t* new_of_old, uint64_t* agg_desc, int* host_flags, void* ws,
+                           size_t ws_bytes, void* stream);
+/* G = Â_local · act(A·W^T + bias) on a group-aligned pack (FITGNN_GEMM_BF16X3 operands, N > 128):
+ *   G[r,:] = dinv[r] * ( dinv[r]*h[r,:] + sum_{c in agg_desc(r)} dinv[c]*h[c,:] ),  h = act(A·W^T + bias)
+ * = the next GCNConv's propagate (gcn_norm weights, self loop included) applied to this layer's activated output.
+ * Y fp32 [M, ldy], or bf16 hi/lo planes when Y_lo != NULL.  Padding rows (dinv = 0) are written as zeros. */
+int fitgnn_gcn_transform_aggregate(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi,
+                                   const void* W_lo, int64_t ldw, const float* bias, int64_t M, int K,
+                                   int N, int act, const uint64_t* agg_desc, const float* dinv, void* Y,
+                                   void* Y_lo, int64_t ldy, void* stream);
+/* fitgnn_gemm_bias_act (BF16X3) whose output row m is written to Y row row_map[m] and skipped when row_map[m] < 0:
+ * drops the padding rows of an aligned pack / scatters lt1's output (network.py:34-35) straight into the caller's
+ * row order. */
+int fitgnn_gemm_head_rows(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi,
+                          const void* W_lo, int64_t ldw, const float* bias, int64_t M, int K, int N,
+                          int act, int head, const int32_t* row_map, float* Y, int64_t ldy, void* stream);
 /* fp32 [rows, cols] (ld = ldx) -> bf16 hi/lo planes [rows, ldo] (columns >= cols zero filled) */
 int fitgnn_split_bf16(const float* X, int64_t ldx, int64_t rows, int cols, void* hi, void* lo,
                       int64_t ldo, void* stream);

@@ -576,3 +576,88 @@ def subgraphs_from_partition(edge_index, x, part, sub_ids):
                         mask=np.ones(len(nd), dtype=bool), orig_idx=nd, core=nd, n_real=len(nd),
                         actual_ext=np.zeros(0, dtype=np.int64), cluster_ids=np.zeros(0, dtype=np.int64)))
     return out
+
+
+# ============================================================================================
+# Group-aligned layout of a pack (no reference counterpart: a pure re-layout; the checker for
+# fitgnn_pack_align_* and for the aggregation fused into the transform epilogue)
+# ============================================================================================
+
+
+def aligned_layout(sub_ptr, group=32):
+    """Greedy in-order placement: subgraph s starts at the current position unless it would straddle a multiple of
+    `group`, in which case the group is closed with padding first.  Returns (new_start[n_sub+1], n_rows_aligned) or
+    None when a subgraph has more than `group` rows."""
+    sub_ptr = np.asarray(sub_ptr, dtype=np.int64)
+    sizes = np.diff(sub_ptr)
+    if sizes.size and sizes.max() > group:
+        return None
+    new_start = np.zeros(sizes.size + 1, dtype=np.int64)
+    pos = 0
+    for s, size in enumerate(sizes):
+        off = pos % group
+        if off + size > group:
+            pos += group - off
+        new_start[s] = pos
+        pos += size
+    new_start[-1] = pos
+    return new_start, int(pos)
+
+
+def aligned_pack(pack, group=32):
+    """Expected arrays of Pack.aligned(): `pack` is a dict of numpy arrays (rowptr, col, dinv, gid, sub_ptr, core_rows,
+    is_core, mask).  Padding rows: empty CSR row, dinv 0, gid 0, flags 0, orig_row -1."""
+    lay = aligned_layout(pack["sub_ptr"], group)
+    if lay is None:
+        return None
+    new_start, n_al = lay
+    sub_ptr = np.asarray(pack["sub_ptr"], dtype=np.int64)
+    n_rows = int(sub_ptr[-1]) if sub_ptr.size else 0
+    sizes = np.diff(sub_ptr)
+    shift_of_row = np.repeat(new_start[:-1] - sub_ptr[:-1], sizes)
+    new_of_old = np.arange(n_rows) + shift_of_row
+    orig_row = np.full(n_al, -1, dtype=np.int64)
+    orig_row[new_of_old] = np.arange(n_rows)
+    rowptr = np.asarray(pack["rowptr"], dtype=np.int64)
+    deg = np.zeros(n_al, dtype=np.int64)
+    deg[new_of_old] = np.diff(rowptr)
+    rowptr_a = np.concatenate([[0], np.cumsum(deg)])
+    row_of_entry = np.repeat(np.arange(n_rows), np.diff(rowptr))
+    col_a = np.asarray(pack["col"], dtype=np.int64) + shift_of_row[row_of_entry]
+    out = dict(rowptr=rowptr_a, col=col_a, new_of_old=new_of_old, orig_row=orig_row, sub_ptr=new_start,
+               core_rows=new_of_old[np.asarray(pack["core_rows"], dtype=np.int64)], n_rows=n_al)
+    for name, dt in (("dinv", np.float32), ("gid", np.int64), ("is_core", np.uint8), ("mask", np.uint8)):
+        a = np.zeros(n_al, dtype=dt)
+        a[new_of_old] = pack[name]
+        out[name] = a
+    # aggregation descriptors: count of non-self entries + their row-in-group, in CSR order
+    desc = np.zeros(n_al, dtype=np.uint64)
+    truncated = False
+    for r in range(n_rows):
+        nr = int(new_of_old[r])
+        lanes, self_seen = [], False
+        for c in pack["col"][rowptr[r]:rowptr[r + 1]]:
+            if c == r and not self_seen:
+                self_seen = True
+                continue
+            lanes.append((int(c) + int(shift_of_row[r])) % group)
+        if len(lanes) > 12:
+            truncated, lanes = True, lanes[:12]
+        d = len(lanes)
+        for j, ln in enumerate(lanes):
+            d |= ln << (4 + 5 * j)
+        desc[nr] = d
+    out["agg_desc"], out["agg_ok"] = desc, not truncated
+    return out
+
+
+def aggregate_dense(rowptr, col, dinv, H):
+    """Â·H for a CSR with materialised self loops: out[r] = dinv[r] * sum_e dinv[col_e] * H[col_e]  (fp64)."""
+    H = np.asarray(H, dtype=np.float64)
+    out = np.zeros_like(H)
+    dinv = np.asarray(dinv, dtype=np.float64)
+    for r in range(len(rowptr) - 1):
+        cs = col[rowptr[r]:rowptr[r + 1]]
+        if len(cs):
+            out[r] = dinv[r] * (dinv[cs, None] * H[cs]).sum(0)
+    return out

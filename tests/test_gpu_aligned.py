@@ -1,0 +1,185 @@
+"""GPU tests of the group-aligned pack layout and the aggregation fused into the tensor-core transform's epilogue
+(fitgnn_pack_align_*, fitgnn_gcn_transform_aggregate, fitgnn_gemm_head_rows).  Integer structure bit-exact against
+the oracle's restatement of the layout; fp32 results within 1e-3 relative (RTOL) of the fp64 oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fitgnn_oracle as fo
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-3
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def fg():
+    import fitgnn_b200
+    return fitgnn_b200
+
+
+def small_subgraph_graph(n, k, seed, extra_intra=1.0, inter=3.0, max_size=None):
+    """Random graph whose partition has k clusters of small random sizes; intra-cluster tree + extras (with duplicate
+    edges), plus inter-cluster edges that the 'none' pack drops."""
+    rng = np.random.default_rng(seed)
+    part = np.sort(rng.integers(0, k, n))
+    if max_size:
+        # cap cluster sizes by re-assigning the overflow to fresh clusters
+        out, nxt, cnt = part.copy(), k, {}
+        for i, p in enumerate(part):
+            c = cnt.get(p, 0)
+            if c >= max_size:
+                out[i] = nxt + (c - max_size) // max_size + 1000 * p
+            cnt[p] = c + 1
+        part = out
+    _, part = np.unique(part, return_inverse=True)
+    k = int(part.max()) + 1
+    perm = rng.permutation(n)
+    start = np.searchsorted(part, np.arange(k))
+    size = np.bincount(part, minlength=k)
+    pos = np.arange(n) - start[part]
+    child = np.nonzero(pos > 0)[0]
+    parent = start[part[child]] + (rng.random(child.size) * pos[child]).astype(np.int64)
+    s, d = [child], [parent]
+    ne = int(extra_intra * child.size)
+    if ne:
+        c2 = child[rng.integers(0, child.size, ne)]
+        p2 = start[part[c2]] + (rng.random(ne) * size[part[c2]]).astype(np.int64)
+        ok = p2 != c2
+        s.append(c2[ok]); d.append(p2[ok])
+    ni = int(inter * n)
+    u, v = rng.integers(0, n, ni), rng.integers(0, n, ni)
+    ok = part[u] != part[v]
+    s.append(u[ok]); d.append(v[ok])
+    s, d = np.concatenate(s), np.concatenate(d)
+    a, b = perm[s], perm[d]
+    ei = np.stack([np.concatenate([a, b]), np.concatenate([b, a])]).astype(np.int64)
+    part_by_node = np.empty(n, dtype=np.int64)
+    part_by_node[perm] = part
+    # renumber clusters by smallest member (reference convention)
+    first = np.full(k, n)
+    np.minimum.at(first, part_by_node, np.arange(n))
+    new_id = np.empty(k, dtype=np.int64)
+    new_id[np.argsort(first)] = np.arange(k)
+    return ei, new_id[part_by_node].astype(np.int32), k
+
+
+def pack_arrays(p):
+    return {k: getattr(p, k).cpu().numpy() for k in ("rowptr", "col", "dinv", "gid", "sub_ptr", "core_rows", "is_core", "mask")}
+
+
+@pytest.mark.parametrize("n,k,seed,max_size", [(40, 20, 0, None), (5000, 2300, 1, None), (3000, 400, 2, 13), (64, 2, 3, 32),
+                                               (33, 33, 4, None)])
+def test_aligned_pack_matches_oracle_layout(fg, n, k, seed, max_size):
+    ei, part, k = small_subgraph_graph(n, k, seed, max_size=max_size)
+    pack = fg.build_pack(torch.tensor(ei, device=dev()), torch.tensor(part), k, "none")
+    want = fo.aligned_pack(pack_arrays(pack), 32)
+    ap = pack.aligned(32)
+    if want is None:
+        assert ap is None
+        return
+    assert ap is not None and ap.n_rows == want["n_rows"]
+    for name in ("rowptr", "col", "gid", "sub_ptr", "core_rows", "is_core", "mask", "orig_row", "new_of_old"):
+        assert np.array_equal(getattr(ap, name).cpu().numpy().astype(np.int64), want[name].astype(np.int64)), name
+    assert np.array_equal(ap.dinv.cpu().numpy(), want["dinv"])  # bit-exact copy
+    assert np.array_equal(ap.agg_desc.cpu().numpy().view(np.uint64), want["agg_desc"])
+    assert ap.agg_ok == want["agg_ok"]
+    # the property the fused kernel relies on: every entry of a row lies in the row's own group of 32
+    rp, col = want["rowptr"], want["col"]
+    rows = np.repeat(np.arange(ap.n_rows), np.diff(rp))
+    assert np.array_equal(rows // 32, col // 32)
+
+
+def test_unalignable_pack_returns_none(fg):
+    ei, part, k = small_subgraph_graph(400, 4, 5)  # ~100 rows per subgraph
+    pack = fg.build_pack(torch.tensor(ei, device=dev()), torch.tensor(part), k, "none")
+    assert pack.aligned(32) is None
+    sd = fo.init_state_dict(16, 256, 5, seed=0)
+    f = fg.PackedForward(pack, sd, precision="bf16x3")  # auto: falls back to SpMM + GEMM
+    assert f.apack is None
+    with pytest.raises(ValueError):
+        fg.PackedForward(pack, sd, precision="bf16x3", fuse_aggregate=True)
+
+
+@pytest.mark.parametrize("n,k,K,N,seed", [(300, 130, 104, 512, 0), (6000, 2700, 64, 256, 1), (9000, 4000, 512, 512, 2),
+                                          (1000, 90, 104, 512, 3)])
+def test_transform_aggregate_matches_fp64(fg, n, k, K, N, seed):
+    ei, part, k = small_subgraph_graph(n, k, seed, max_size=30)
+    pack = fg.build_pack(torch.tensor(ei, device=dev()), torch.tensor(part), k, "none")
+    ap = pack.aligned(32)
+    assert ap is not None
+    g = torch.Generator().manual_seed(seed)
+    M = ap.n_rows
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g) * 0.1
+    A_pl = fg.ops.split_bf16(A.to(dev()))
+    W_pl = fg.ops.split_bf16(W.to(dev()))
+    if not ap.agg_ok:
+        pytest.skip("a row has more than 12 neighbours")
+    for split in (True, False):
+        out = fg.ops.gcn_transform_aggregate(A_pl, W_pl, b.to(dev()), fg.ops.ACT_ELU, ap.agg_desc, ap.dinv, split_out=split)
+        got = (out[0].float() + out[1].float()) if split else out
+        h = torch.nn.functional.elu(A.double() @ W.double().T + b.double()).numpy()
+        a = fo.aligned_pack(pack_arrays(pack), 32)
+        want = fo.aggregate_dense(a["rowptr"], a["col"], a["dinv"], h)
+        got = got.cpu().numpy()
+        real = a["orig_row"] >= 0
+        scale = np.abs(want).max()
+        err = np.abs(got[real] - want[real]).max() / scale
+        assert err < 1e-4, err
+        assert (got[~real] == 0).all()  # padding rows are written as zeros
+
+
+@pytest.mark.parametrize("N,head", [(47, "log_softmax"), (7, "softmax"), (1, "identity"), (48, "identity")])
+def test_head_rows_drops_padding(fg, N, head):
+    g = torch.Generator().manual_seed(N)
+    M, K = 1000, 512
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    keep = torch.rand(M, generator=g) > 0.1
+    row_map = torch.full((M,), -1, dtype=torch.int32)
+    n_keep = int(keep.sum())
+    row_map[keep] = torch.randperm(n_keep, generator=g).to(torch.int32)
+    ld = (N + 3) // 4 * 4
+    out = torch.full((n_keep, ld), 7.0, device=dev())
+    hd = {"identity": 0, "log_softmax": 1, "softmax": 2}[head]
+    fg.ops.gemm_head_rows(fg.ops.split_bf16(A.to(dev())), fg.ops.split_bf16(W.to(dev())), b.to(dev()), fg.ops.ACT_NONE, hd,
+                          row_map.to(dev()), out, K=K, N=N)
+    z = A.double() @ W.double().T + b.double()
+    if head == "log_softmax":
+        z = torch.log_softmax(z, 1)
+    elif head == "softmax":
+        z = torch.softmax(z, 1)
+    want = torch.empty(n_keep, N, dtype=torch.float64)
+    want[row_map[keep].long()] = z[keep]
+    got = out.cpu()[:, :N].double()
+    assert (got - want).abs().max() / max(1.0, want.abs().max()) < 1e-4
+    assert (out.cpu()[:, N:] == 7.0).all()  # columns past N untouched
+
+
+@pytest.mark.parametrize("n,k,F,H,C,layers", [(3000, 1300, 100, 512, 47, 2), (2000, 900, 30, 256, 5, 3), (500, 400, 100, 512, 7, 2)])
+def test_forward_fused_aggregation_matches_classic_and_oracle(fg, n, k, F, H, C, layers):
+    ei, part, k = small_subgraph_graph(n, k, 11, max_size=12)
+    pack = fg.build_pack(torch.tensor(ei, device=dev()), torch.tensor(part), k, "none")
+    X = fg.synth.features(n, F, seed=1).to(dev())
+    sd = fo.init_state_dict(F, H, C, num_layers=layers, seed=2)
+    fused = fg.PackedForward(pack, sd, precision="bf16x3", fuse_aggregate=True)
+    classic = fg.PackedForward(pack, sd, precision="bf16x3", fuse_aggregate=False)
+    assert fused.apack is not None and classic.apack is None
+    a, b = fused(X), classic(X)
+    assert a.shape == b.shape == (pack.n_rows, C)
+    assert (a - b).abs().max().item() < 1e-4 * max(1.0, b.abs().max().item())
+    # oracle: per-subgraph fp32 torch-CPU restatement of network.py:29-35
+    subs = fo.subgraphs_from_partition(ei, X.cpu().numpy(), part, np.arange(k))
+    want = fo.node_infer_batched(sd, subs, [np.ones(s["x"].shape[0], dtype=bool) for s in subs], "node_cls", 128).numpy()
+    got = a.cpu().numpy()
+    assert np.abs(got - want).max() / max(1.0, np.abs(want).max()) < RTOL
+    # writing into a caller-provided (padded-pitch) buffer
+    buf = torch.zeros(pack.n_rows, (C + 3) // 4 * 4, device=dev())
+    fused(X, out=buf)
+    assert torch.equal(buf[:, :C], a)

@@ -124,8 +124,8 @@ def test_fused_gcn_layer_matches_spmm_plus_gemm(fg, n, F, H, mode):
     assert torch.equal(hi, fused.to(torch.bfloat16))
     # the engine's opt-in use of the fused layer gives the same logits as the default schedule
     sd = fo.init_state_dict(F, H, 7, seed=3)
-    a = fg.PackedForward(pack, sd, precision="bf16x3")(X)
-    f = fg.PackedForward(pack, sd, precision="bf16x3", fuse_layer0=True)
+    a = fg.PackedForward(pack, sd, precision="bf16x3", fuse_aggregate=False)(X)
+    f = fg.PackedForward(pack, sd, precision="bf16x3", fuse_layer0=True, fuse_aggregate=False)
     bq = f(X)
     assert f.fused_layer0 is True and torch.equal(a, bq)
     # ineligible shapes are refused loudly at the ABI (callers fall back)

@@ -97,3 +97,27 @@ def test_synth_generators_are_seeded():
     assert int(part.max()) + 1 == k and ei.shape[0] == 2
     sizes = torch.bincount(part.long())
     assert torch.allclose(cw, 1.0 / torch.sqrt(sizes[part.long()].double()))
+
+
+def test_oracle_aligned_layout_invariants():
+    """The layout checker itself: in-order greedy placement, no subgraph straddles a multiple of 32, padding only at
+    group tails, nothing moves when everything already fits."""
+    import numpy as np
+    from oracle import fitgnn_oracle as fo
+    rng = np.random.default_rng(0)
+    sizes = rng.integers(1, 14, 5000)
+    sub_ptr = np.concatenate([[0], np.cumsum(sizes)])
+    new_start, n_al = fo.aligned_layout(sub_ptr, 32)
+    assert (np.diff(new_start[:-1]) >= sizes[:-1]).all() and n_al == new_start[-2] + sizes[-1]
+    first, last = new_start[:-1], new_start[:-1] + sizes - 1
+    assert (first // 32 == last // 32).all()
+    pad = np.diff(new_start) - sizes  # padding rows after each subgraph
+    nxt = new_start[1:-1]
+    assert ((pad[:-1] == 0) | (nxt % 32 == 0)).all() and pad[-1] == 0
+    assert 1.0 <= n_al / sub_ptr[-1] < 1.25
+    assert fo.aligned_layout([0, 33], 32) is None
+    s2, n2 = fo.aligned_layout([0, 32, 64, 96], 32)
+    assert list(s2) == [0, 32, 64, 96] and n2 == 96
+    # known answer (sizes 3,7,20,3,7,24,6)
+    s3, n3 = fo.aligned_layout([0, 3, 10, 30, 33, 40, 64, 70], 32)
+    assert list(s3) == [0, 3, 10, 32, 35, 64, 88, 94] and n3 == 94
