@@ -49,6 +49,9 @@ def parse():
     p.add_argument("--no-fuse-aggregate", action="store_true",
                    help="classic schedule: stand-alone SpMM per layer instead of the aggregation fused into the transform")
     p.add_argument("--seed", type=int, default=0)
+    p.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl"],
+                   help="N>1 output exchange: p2p = head kernel stores into every rank's gather buffer over NVLink "
+                        "(+ a one-element all-reduce as barrier); nccl = head into the local slot, then all_gather")
     p.add_argument("--chunks", type=int, default=1, help="N>1: chunks per rank; chunk c's all-gather overlaps chunk c+1")
     return p.parse_args()
 
@@ -60,7 +63,7 @@ def workload_shape(name):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -71,7 +74,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag:
                     break
@@ -84,10 +87,16 @@ class ClockSampler(threading.Thread):
         if self.proc:
             self.proc.terminate()
 
-    def summary(self):
+    def mark(self):
+        """index of the next sample (call at the start / end of the timed region)"""
+        return len(self.rows)
+
+    def summary(self, lo=0, hi=None):
+        """samples [lo, hi) widened by one on each side (the 50 ms poll may straddle a short timed region)"""
         sm, smax, reasons = [], 0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        hi = len(self.rows) if hi is None else hi
+        for r in self.rows[max(0, lo - 1): hi + 1]:
             try:
                 sm.append(float(r[0])); smax = max(smax, float(r[1]))
                 for nm, v in zip(names, r[3:7]):
@@ -207,7 +216,6 @@ def projection_bench(fg, ei, part, cw, k, X, n, F):
     nnz_ac = int(row.numel())
     b_ac = 16 * E + 4 * n + 20 * nnz_ac
     del row, col, cnt, rowptr
-    torch.cuda.empty_cache()
     return {"group_by_part_ms": t_grp,
             "xc": {"kernel": "project_features_kernel", "ms": t_xc, "algo_GB": b_xc / 1e9, "GBps": b_xc / t_xc / 1e6,
                    "frac": b_xc / t_xc / 1e6 / hbm_peak, "bound": "hbm"},
@@ -255,8 +263,7 @@ def main_ours(args):
     pack = fg.build_pack(ei, part, k, args.mode)
     torch.cuda.synchronize()
     pack_build_ms = (time.perf_counter() - t0) * 1e3
-    projection = projection_bench(fg, ei, part, cw, k, X, n, F) if (rank == 0 and world == 1 and not args.no_projection) else None
-    ei_keep = ei if (rank == 0 and not args.no_cpu_baseline) else None
+    ei_keep = ei if (rank == 0 and world == 1 and not (args.no_cpu_baseline and args.no_projection)) else None
     del ei
     if args.mode == "cluster":
         raise SystemExit("bench: cluster mode needs the C·X rows appended to X; use tests for that mode")
@@ -273,6 +280,31 @@ def main_ours(args):
     Cp = (C + 3) // 4 * 4  # logits row pitch padded to 16 bytes (aligned stores in the head kernel); columns >= C unused
     gbuf = shard.gather_buffer(Cp, device) if world > 1 else None
 
+    # fused output exchange (see dist.PeerGather): needs the group-aligned schedule (row-mapped head stores)
+    pg, collective = None, "nccl" if world > 1 else "none"
+    if world > 1 and args.collective != "nccl" and all(f.apack is not None for f in fwds):
+        try:
+            from fitgnn_b200.dist import PeerGather
+            pg = PeerGather(shard, Cp, device, n_buffers=2)
+            collective = "p2p"
+        except Exception as e:  # IPC not permitted in this container, ...
+            if args.collective == "p2p":
+                raise
+            print(f"bench: peer buffers unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
+    if world > 1:  # every rank must take the same path
+        ok = torch.tensor([1 if pg is not None else 0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            pg, collective = None, "nccl"
+
+    def run_p2p(Xin, b):
+        for c, f in enumerate(fwds):
+            f(Xin, peer_ptrs=pg.slot_ptrs(b, c))
+        pg.barrier()
+        return pg.tensors[b]
+
+    step_no = [0]
+
     def run_chunks(Xin, buf):
         """forward of every local chunk; chunk c's all-gather is enqueued asynchronously (NCCL stream) right after its
         head kernel, so it overlaps the compute of chunk c+1; the current stream then waits for all of them."""
@@ -285,6 +317,9 @@ def main_ours(args):
         return buf
 
     def step():
+        if pg is not None:
+            step_no[0] += 1
+            return run_p2p(Xd, step_no[0] % 2)
         return run_chunks(Xd, gbuf) if world > 1 else fwd(Xd)
 
     def barrier():
@@ -298,13 +333,12 @@ def main_ours(args):
     if rank == 0:
         sampler.start()
     for _ in range(max(args.warmup, 3)):
-        step()
+        out = step()  # same allocation pattern as the timed loop (the previous step's output stays alive)
     barrier()
     if rank == 0:
         t_wait = time.time()
         while not sampler.rows and time.time() - t_wait < 10.0:
             time.sleep(0.05)
-        sampler.rows.clear()  # keep only samples taken from here on
     for f in fwds:
         f.enable_profile(True)
     launches0 = sum(f.launches for f in fwds)
@@ -312,14 +346,29 @@ def main_ours(args):
     barrier()
     if args.profiler_range:
         torch.cuda.cudart().cudaProfilerStart()
+    mark0 = sampler.mark()
     ev0.record()
+    dbg = os.environ.get("FITGNN_BENCH_DEBUG") == "1"
+    step_ev, step_cpu = [], []
     for _ in range(args.steps):
+        if dbg:
+            step_cpu.append(time.perf_counter())
         out = step()
+        if dbg:
+            e_ = torch.cuda.Event(enable_timing=True)
+            e_.record()
+            step_ev.append(e_)
     ev1.record()
     barrier()
+    mark1 = sampler.mark()
     if args.profiler_range:
         torch.cuda.cudart().cudaProfilerStop()
     ms = ev0.elapsed_time(ev1) / args.steps
+    if dbg and rank == 0:
+        ends = [ev0.elapsed_time(e_) for e_ in step_ev]
+        print("debug: step end times on the GPU (ms since start):", [round(x, 2) for x in ends], file=sys.stderr)
+        print("debug: step enqueue start times on the CPU (ms):", [round((c - step_cpu[0]) * 1e3, 2) for c in step_cpu],
+              file=sys.stderr)
     gpu_launches = sum(f.launches for f in fwds) - launches0
     prof = {}
     for f in fwds:  # per-kernel time summed over this rank's chunks (ms per step)
@@ -343,6 +392,7 @@ def main_ours(args):
     # software-pipelined over three streams with double buffers (H2D of step i+1 and D2H of step i-1 overlap the
     # compute of step i); the timed region covers all copies of all K steps.
     e2e = None
+    o_dev = None
     if not args.no_e2e:
         # K-padded rows (104 floats) so the H2D copy is one contiguous DMA.  N > 1: every rank copies only its 1/N
         # slice of the feature table over its own PCIe link and the ranks all-gather the table over NVLink.
@@ -356,7 +406,11 @@ def main_ours(args):
         NB = 2
         X_slots = [torch.zeros(world, rows_per, Fp, device=device) for _ in range(NB)]
         X_in = [xs.view(world * rows_per, Fp)[:n] for xs in X_slots]
-        o_dev = [shard.gather_buffer(Cp, device) if world > 1 else torch.empty(n_loc, Cp, device=device) for _ in range(NB)]
+        o_dev = None
+        if pg is not None:
+            o_dev = pg.tensors
+        else:
+            o_dev = [shard.gather_buffer(Cp, device) if world > 1 else torch.empty(n_loc, Cp, device=device) for _ in range(NB)]
         o_host = [torch.empty(n_loc, Cp, dtype=torch.float32).pin_memory() for _ in range(NB)]
         s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
         ev_in = [torch.cuda.Event() for _ in range(NB)]
@@ -375,7 +429,9 @@ def main_ours(args):
                 with torch.cuda.stream(s_cmp):
                     s_cmp.wait_event(ev_in[b])
                     s_cmp.wait_event(ev_out[b])  # the D2H that last read o_dev[b] is done
-                    if world > 1:
+                    if pg is not None:
+                        run_p2p(X_in[b], b)
+                    elif world > 1:
                         run_chunks(X_in[b], o_dev[b])
                     else:
                         fwd(X_in[b], out=o_dev[b])
@@ -411,6 +467,10 @@ def main_ours(args):
     if rank == 0:
         sampler.stop()
 
+    if pg is not None:  # nobody may still be writing into a buffer that is about to be unmapped / freed
+        barrier()
+        o_dev = out = None
+        pg.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -449,6 +509,8 @@ def main_ours(args):
     spmm_names = [k_ for k_ in kernels if k_.startswith("spmm")]
     spmm_main = max(spmm_names, key=lambda k_: kernels[k_]["algo_GB"]) if spmm_names else dom
     fused = fwd.apack is not None
+    # one-time Gc projection kernels on the same graph, timed after (and outside of) the hot-path measurement
+    projection = projection_bench(fg, ei_keep, part, cw, k, X, n, F) if (world == 1 and not args.no_projection) else None
     spmm_roof = spmm_standalone_bench(fg, shard.locals[0], args.hidden) if (fused and world == 1) else roofline_of(spmm_main)
     line = {"metric": METRIC, "value": n / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
@@ -456,10 +518,10 @@ def main_ours(args):
             "config": config_of(args, n, F, C, k), "roofline": roofline_of(dom), "roofline_spmm": spmm_roof,
             "schedule": ("spmm0 -> [transform + next layer's aggregation in the epilogue] -> transform -> head (group-aligned "
                          f"pack, {fwd.apack.n_rows} rows incl. padding)") if fused else "spmm + transform per layer -> head",
-            "kernels": kernels, "gpu_launches": gpu_launches, "clocks": sampler.summary(),
+            "kernels": kernels, "gpu_launches": gpu_launches, "clocks": sampler.summary(mark0, mark1),
             "pack": {"rows": pack.n_rows, "nnz": pack.nnz, "subgraphs": pack.n_sub, "build_ms": pack_build_ms,
                      "bytes": pack.nbytes(), "rank_loads": shard.loads},
-            "multi_gpu": {"chunks_per_rank": n_chunks, "rank_kernel_ms": rank_kernel_ms,
+            "multi_gpu": {"chunks_per_rank": n_chunks, "collective": collective, "rank_kernel_ms": rank_kernel_ms,
                           "all_gather_bytes": int(n * Cp * 4) if world > 1 else 0,
                           "exposed_ms": (ms - max(rank_kernel_ms)) if rank_kernel_ms else 0.0}}
     if projection:

@@ -60,6 +60,12 @@ SIGNATURES = {
                                                c_i32, c_void, c_void, c_void, c_void, c_i64, c_void]),
     "fitgnn_gemm_head_rows": (c_i32, [c_void, c_void, c_i64, c_void, c_void, c_i64, c_void, c_i64, c_i32, c_i32, c_i32,
                                       c_i32, c_void, c_void, c_i64, c_void]),
+    "fitgnn_gemm_head_rows_peers": (c_i32, [c_void, c_void, c_i64, c_void, c_void, c_i64, c_void, c_i64, c_i32, c_i32, c_i32,
+                                            c_i32, c_void, C.POINTER(c_void), c_i32, c_i64, c_void]),
+    "fitgnn_peer_alloc": (c_i32, [c_size, C.POINTER(c_void), C.c_char_p]),
+    "fitgnn_peer_open": (c_i32, [C.c_char_p, C.POINTER(c_void)]),
+    "fitgnn_peer_close": (c_i32, [c_void]),
+    "fitgnn_peer_free": (c_i32, [c_void]),
     "fitgnn_split_bf16": (c_i32, [c_void, c_i64, c_i64, c_i32, c_void, c_void, c_i64, c_void]),
     "fitgnn_segment_pool": (c_i32, [c_void, c_i64, c_i32, c_void, c_void, c_i64, c_i32, c_void, c_i64, c_void]),
     "fitgnn_group_workspace_bytes": (c_size, [c_i64, c_i64]),

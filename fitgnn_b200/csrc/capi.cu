@@ -20,7 +20,8 @@ int gemm_fp32(const float* A, int64_t lda, const float* W, int64_t ldw, const fl
 int row_softmax(float* Y, int64_t ldy, int64_t M, int N, int head, cudaStream_t st);
 int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi, const void* W_lo, int64_t ldw,
                 const float* bias, int64_t M, int K, int N, int act, int head, float* Y, void* Y_lo, int64_t ldy,
-                const uint64_t* agg_desc, const float* agg_dinv, const int32_t* row_map, cudaStream_t st);
+                const uint64_t* agg_desc, const float* agg_dinv, const int32_t* row_map, float* const* peers, int n_peers,
+                cudaStream_t st);
 
 int gcn_layer_fused(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X, int64_t ldx, int width,
                     const int32_t* src_index, const int32_t* out_rows, int64_t M, const void* W_hi, const void* W_lo,
@@ -71,7 +72,7 @@ extern "C" int fitgnn_gemm_bias_act_split(int precision, const void* A, const vo
   }
   if (precision == FITGNN_GEMM_BF16X3) {
     FG_REQUIRE(A_lo && W_lo, FITGNN_EINVAL, "gemm: BF16X3 needs the lo planes");
-    return gemm_bf16x3(A, A_lo, lda, W, W_lo, ldw, bias, M, K, N, act, head, Y, Y_lo, ldy, nullptr, nullptr, nullptr, st);
+    return gemm_bf16x3(A, A_lo, lda, W, W_lo, ldw, bias, M, K, N, act, head, Y, Y_lo, ldy, nullptr, nullptr, nullptr, nullptr, 0, st);
   }
   set_error("gemm: unknown precision %d", precision);
   return FITGNN_EINVAL;
@@ -87,7 +88,7 @@ extern "C" int fitgnn_gcn_transform_aggregate(const void* A_hi, const void* A_lo
   FG_REQUIRE(act == FITGNN_ACT_NONE || act == FITGNN_ACT_ELU, FITGNN_EINVAL, "gcn_transform_aggregate: unknown act %d", act);
   if (M == 0) return FITGNN_OK;
   return gemm_bf16x3(A_hi, A_lo, lda, W_hi, W_lo, ldw, bias, M, K, N, act, FITGNN_HEAD_IDENTITY, static_cast<float*>(Y),
-                     Y_lo, ldy, agg_desc, dinv, nullptr, as_stream(stream));
+                     Y_lo, ldy, agg_desc, dinv, nullptr, nullptr, 0, as_stream(stream));
 }
 
 extern "C" int fitgnn_gemm_head_rows(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi, const void* W_lo,
@@ -101,7 +102,25 @@ extern "C" int fitgnn_gemm_head_rows(const void* A_hi, const void* A_lo, int64_t
              head);
   if (M == 0) return FITGNN_OK;
   return gemm_bf16x3(A_hi, A_lo, lda, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y, nullptr, ldy, nullptr, nullptr,
-                     row_map, as_stream(stream));
+                     row_map, nullptr, 0, as_stream(stream));
+}
+
+extern "C" int fitgnn_gemm_head_rows_peers(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi,
+                                           const void* W_lo, int64_t ldw, const float* bias, int64_t M, int K, int N,
+                                           int act, int head, const int32_t* row_map, float* const* host_peer_bases,
+                                           int n_peers, int64_t ldy, void* stream) {
+  FG_REQUIRE(A_hi && A_lo && W_hi && W_lo && row_map && host_peer_bases && M >= 0 && K > 0 && N > 0, FITGNN_EINVAL,
+             "gemm_head_rows_peers: bad arguments (M=%lld K=%d N=%d)", (long long)M, K, N);
+  FG_REQUIRE(n_peers >= 1 && n_peers <= 8, FITGNN_EINVAL, "gemm_head_rows_peers: 1..8 peers (got %d)", n_peers);
+  for (int p = 0; p < n_peers; ++p)
+    FG_REQUIRE(host_peer_bases[p], FITGNN_EINVAL, "gemm_head_rows_peers: peer base %d is null", p);
+  FG_REQUIRE(lda >= K && ldw >= K && ldy >= N, FITGNN_EINVAL, "gemm_head_rows_peers: leading dimension too small");
+  FG_REQUIRE(act == FITGNN_ACT_NONE || act == FITGNN_ACT_ELU, FITGNN_EINVAL, "gemm_head_rows_peers: unknown act %d", act);
+  FG_REQUIRE(head >= FITGNN_HEAD_IDENTITY && head <= FITGNN_HEAD_SOFTMAX, FITGNN_EINVAL,
+             "gemm_head_rows_peers: unknown head %d", head);
+  if (M == 0) return FITGNN_OK;
+  return gemm_bf16x3(A_hi, A_lo, lda, W_hi, W_lo, ldw, bias, M, K, N, act, head, nullptr, nullptr, ldy, nullptr, nullptr,
+                     row_map, host_peer_bases, n_peers, as_stream(stream));
 }
 
 extern "C" int fitgnn_gemm_bias_act(int precision, const void* A, const void* A_lo, int64_t lda, const void* W,

@@ -25,7 +25,8 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                      // bf16 elements = 128 bytes = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int EPI_WARPS = 8;                      // two per TMEM lane quadrant, each taking half of the columns
+constexpr int EPI_WARPS = 8;                      // default: two per TMEM lane quadrant, each taking half of the columns
+constexpr int EPI_WARPS_WIDE = 16;                // epilogue-bound instantiations: four per quadrant (one 32-column box each)
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr int GATHER_WARPS = 4;                   // fused layer: produce the A tile (Â·X) in-kernel, 32 rows per warp
 constexpr int GATHER_WARP0 = 2 + EPI_WARPS;
@@ -55,6 +56,16 @@ struct EpiArgs {
   const unsigned long long* agg_desc;  // [M] bits [0,4) = entry count (<= 12), then 5-bit lanes
   const float* agg_dinv;               // [M] deg^-1/2 (0 for padding rows)
   const int32_t* row_map;              // [M] or null
+  // n_peers > 0 (needs row_map): every output row is stored to peers[0..n_peers) + row_map[m] * ldy instead of Y — the
+  // same slot of every rank's gather buffer (peer-mapped pointers: the stores travel over NVLink), which replaces the
+  // all-gather that would otherwise follow the head kernel
+  float* peers[8];
+  int n_peers;
+  // row-mapped narrow heads: stage each quadrant's 32 rows linearly (pitch ldy) in shared memory and write every run of
+  // consecutive destination rows with ONE bulk copy per destination — full-line writes, which is what makes the stores
+  // to peer memory run at NVLink speed (16-byte per-thread stores reach ~120 GB/s).  Set by the launcher when
+  // N <= 64, ldy == pad4(N) and all bases are 16-byte aligned.
+  int bulk_rows;
 };
 constexpr int EPI_WARP0 = 2;
 constexpr int ACC_STAGES = 2;
@@ -107,6 +118,10 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
                "r"(c0), "r"(c1)
                : "memory");
+}
+// contiguous smem -> global copy (16-byte aligned, size a multiple of 16); the destination may be peer memory
+__device__ __forceinline__ void bulk_store_1d(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -178,14 +193,13 @@ __device__ __forceinline__ float elu1(float x) { return elu_fast(x); }
 __host__ __device__ constexpr int tmem_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 __host__ __device__ constexpr uint32_t stage_bytes(int block_n) { return 2 * A_PLANE_BYTES + 2 * (uint32_t)block_n * BLOCK_K * 2; }
 constexpr uint32_t EPI_BOX_BYTES = 32 * 32 * 4;             // one 32-row x 32-column fp32 store box (128B rows)
-constexpr uint32_t EPI_STAGING_BYTES = EPI_WARPS * EPI_BOX_BYTES;  // one box per epilogue warp = 32 KB
 __host__ __device__ constexpr int num_stages(int block_n) {
   int s = (int)((192 * 1024) / stage_bytes(block_n));
   return s > 8 ? 8 : s;
 }
 
-template <int BLOCK_N, bool GATHER, bool AGG>
-__global__ void __launch_bounds__(GATHER ? THREADS_GATHER : THREADS, 1)
+template <int BLOCK_N, bool GATHER, bool AGG, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW + (GATHER ? 32 * GATHER_WARPS : 0), 1)
 gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                    const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_y_lo,
@@ -199,6 +213,8 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
   constexpr uint32_t IDESC = umma_idesc_bf16(BLOCK_M, BLOCK_N);
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N for M=128");
   static_assert(STAGES >= 2, "need at least two smem stages");
+  static_assert(EW == EPI_WARPS || (EW == EPI_WARPS_WIDE && !GATHER), "4 or 2 epilogue warps per TMEM lane quadrant");
+  constexpr uint32_t STAGING_BYTES = EW * EPI_BOX_BYTES;  // one 32 x 32 box per epilogue warp
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B atoms
@@ -209,7 +225,7 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
   const uint32_t w_region_bytes = w_stationary ? (uint32_t)k_blocks * 2u * B_PLANE_BYTES : 0u;
   const uint32_t stage_bytes_rt = w_stationary ? 2u * A_PLANE_BYTES : STAGE_BYTES;
   uint8_t* staging = smem + w_region_bytes + (size_t)n_stages * stage_bytes_rt;  // multiples of 1024 throughout
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + EPI_STAGING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 2 * ACC_STAGES + 1);
   const uint32_t smem_base = smem_u32(smem) + w_region_bytes;  // first streaming stage
   const uint32_t w_base = smem_u32(smem);                       // resident weights (W-stationary)
@@ -238,7 +254,7 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
     mbar_init(wfull_bar, 1);
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), EPI_WARPS);  // one arrival per epilogue warp
+      mbar_init(tempty_bar(s), EW);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -435,21 +451,27 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
     // ------------------------------------------------------------------ epilogue (thread = output row)
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int row_in_tile = quad * 32 + lane;
-    const bool vec_ok = (ldy % 4 == 0) && (((uintptr_t)Y & 15) == 0);
+    bool vec_ok = (ldy % 4 == 0) && (((uintptr_t)Y & 15) == 0);
+#pragma unroll
+    for (int p = 0; p < 8; ++p)
+      if (p < ea.n_peers) vec_ok = vec_ok && (((uintptr_t)ea.peers[p] & 15) == 0);
     const bool bias_vec = (((uintptr_t)bias & 15) == 0);
     // column split: 32-column boxes; the second warp of a quadrant takes the upper half of the boxes.  A fused
     // (log-)softmax needs the whole row in one thread, so the first warp of the quadrant then takes every box.
     constexpr int N_BOXES = (BLOCK_N + 31) / 32;
     // Narrow heads (<= 64 columns, i.e. one box per warp): single pass — both warps of a quadrant keep their box in
     // registers, exchange (max, sum exp) through shared memory and normalise.  Wider heads: two passes by warp 0.
-    constexpr bool FAST_HEAD = N_BOXES <= 2;
+    constexpr bool FAST_HEAD = N_BOXES <= 2 && EW == EPI_WARPS;
     const bool use_fast_head = FAST_HEAD && head != FITGNN_HEAD_IDENTITY;
     float2* exch = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2][EPI_WARPS][32]
     const int ew = warp - EPI_WARP0;
     const int col_group = ew >> 2;
-    const int split_at = (head != FITGNN_HEAD_IDENTITY && !FAST_HEAD) ? N_BOXES : (N_BOXES + 1) / 2;
-    const int box_beg = col_group == 0 ? 0 : split_at;
-    const int box_end = col_group == 0 ? split_at : N_BOXES;
+    // EW / 4 column groups share the boxes evenly; a two-pass (log-)softmax gives every box to group 0
+    constexpr int GROUPS = EW / 4;
+    constexpr int BOXES_PER_GROUP = (N_BOXES + GROUPS - 1) / GROUPS;
+    const bool one_group = head != FITGNN_HEAD_IDENTITY && !FAST_HEAD;
+    const int box_beg = one_group ? (col_group == 0 ? 0 : N_BOXES) : min(N_BOXES, col_group * BOXES_PER_GROUP);
+    const int box_end = one_group ? N_BOXES : min(N_BOXES, box_beg + BOXES_PER_GROUP);
     int64_t it = 0;
     // aggregation descriptor + dinv of this thread's row, fetched one tile ahead of its use
     unsigned long long desc_next = 0ull;
@@ -482,11 +504,60 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
       const int64_t dest_row = (ea.row_map && m < M) ? (int64_t)__ldg(ea.row_map + m) : m;
       float* yrow = Y + dest_row * ldy + n0;
       float row_max = -INFINITY, row_sum = 0.f;
-      bool exchanged = false;
+      bool exchanged = false, staged = false;
+      const bool bulk_rows = FAST_HEAD && ea.bulk_rows != 0;
+      // one linear [32 rows][ldy] fp32 buffer per TMEM lane quadrant (<= 8 KB), shared by the quadrant's two warps
+      const uint32_t qbuf = smem_u32(staging) + (uint32_t)quad * 2u * EPI_BOX_BYTES;
+      const uint32_t row_bytes = (uint32_t)ldy * 4u;
+      auto stage_and_store = [&](const float (&vals)[32], bool have, int c0, int ncols) {
+        // (a) the previous tile's bulk copies have finished reading the buffer, (b) both warps know it
+        if (col_group == 0 && lane == 0) bulk_wait_read<0>();
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+        if (have) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (j < ncols && c0 + j < (int)ldy) {
+              const float x0 = (n0 + c0 + j < N) ? vals[j] : 0.f, x1 = (n0 + c0 + j + 1 < N) ? vals[j + 1] : 0.f;
+              const float x2 = (n0 + c0 + j + 2 < N) ? vals[j + 2] : 0.f, x3 = (n0 + c0 + j + 3 < N) ? vals[j + 3] : 0.f;
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(qbuf + lane * row_bytes + (uint32_t)(c0 + j) * 4u),
+                           "f"(x0), "f"(x1), "f"(x2), "f"(x3) : "memory");
+            }
+          }
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+        if (col_group == 0) {
+          // runs of consecutive destination rows -> one bulk copy per run and destination, issued by lane 0
+          const int dr_ = (m < M) ? (int)dest_row : -1;
+          const int prev = __shfl_up_sync(0xffffffffu, dr_, 1);
+          const unsigned valid = __ballot_sync(0xffffffffu, dr_ >= 0);
+          const unsigned starts = __ballot_sync(0xffffffffu, dr_ >= 0 && (lane == 0 || prev < 0 || dr_ != prev + 1));
+          unsigned rem = starts;
+          while (rem) {
+            const int s0 = __ffs(rem) - 1;
+            rem &= rem - 1;
+            const unsigned stop = (rem | ~valid) & ~((2u << s0) - 1u);  // next run start or next invalid row after s0
+            const int s1 = stop ? __ffs(stop) - 1 : 32;
+            const int d0 = __shfl_sync(0xffffffffu, dr_, s0);
+            if (lane == 0) {
+              const int n_dst = ea.n_peers > 0 ? ea.n_peers : 1;
+#pragma unroll
+              for (int p = 0; p < 8; ++p) {  // constant indices: a dynamic one would copy the parameter array to the stack
+                if (p < n_dst) {
+                  float* base = ea.n_peers > 0 ? ea.peers[p] : Y;
+                  bulk_store_1d(base + (int64_t)d0 * ldy, qbuf + (uint32_t)s0 * row_bytes, (uint32_t)(s1 - s0) * row_bytes);
+                }
+              }
+            }
+          }
+          if (lane == 0) bulk_commit();
+        }
+        staged = true;
+      };
       auto exchange_stats = [&](float lmax, float lsum) {
         // partner warp = same TMEM quadrant, other column group; buffers alternate by tile parity
-        float2* mine = exch + ((it & 1) * EPI_WARPS + ew) * 32 + lane;
-        const float2* theirs = exch + ((it & 1) * EPI_WARPS + (ew ^ 4)) * 32 + lane;
+        float2* mine = exch + ((it & 1) * EW + ew) * 32 + lane;
+        const float2* theirs = exch + ((it & 1) * EW + (ew ^ 4)) * 32 + lane;
         *mine = make_float2(lmax, lsum);
         asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
         const float2 o = *theirs;
@@ -548,23 +619,28 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
         if (AGG) {
           // next layer's aggregation over the warp's aligned group (see EpiArgs); padding rows (dr = 0) give 0 * h = 0
           // (the A operand's padding rows must hold finite values: the engine's SpMM writes zeros there)
-          float u[32];
+          // AGG_W columns at a time (16 when the register budget is 112 per thread, i.e. 16 epilogue warps)
+          constexpr int AGG_W = EW == EPI_WARPS ? 32 : 16;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            u[j] = v[j] * dr;
-            v[j] = u[j];
-          }
-          for (int sl = 0; sl < agg_max; ++sl) {
-            const bool on = sl < agg_cnt;
-            const int src = on ? (int)((desc >> (4 + 5 * sl)) & 31ull) : lane;
+          for (int h0 = 0; h0 < 32; h0 += AGG_W) {
+            float u[AGG_W];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float tv = __shfl_sync(0xffffffffu, u[j], src);
-              if (on) v[j] += tv;
+            for (int j = 0; j < AGG_W; ++j) {
+              u[j] = v[h0 + j] * dr;
+              v[h0 + j] = u[j];
             }
-          }
+            for (int sl = 0; sl < agg_max; ++sl) {
+              const bool on = sl < agg_cnt;
+              const int src = on ? (int)((desc >> (4 + 5 * sl)) & 31ull) : lane;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= dr;
+              for (int j = 0; j < AGG_W; ++j) {
+                const float tv = __shfl_sync(0xffffffffu, u[j], src);
+                if (on) v[h0 + j] += tv;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < AGG_W; ++j) v[h0 + j] *= dr;
+          }
         }
         if (use_fast_head) {
           float lmax = -INFINITY, lsum = 0.f;
@@ -585,7 +661,9 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __expf(v[j] - row_max) * inv_sum;
         }
-        if (tma_store) {
+        if (bulk_rows) {
+          stage_and_store(v, true, c0, box_cols);
+        } else if (tma_store) {
           // stage the box in this warp's 4 KB buffer (row = lane) and hand it to the TMA unit, which clips at the
           // tensor bounds.  fp32: 128-byte rows, 16-byte chunk c of row r at c ^ (r & 7).  bf16 hi/lo planes: two
           // 2 KB boxes of 64-byte rows, chunk c of row r at c ^ ((r >> 1) & 3).
@@ -619,24 +697,34 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
             bulk_commit();
           }
         } else if (m < M && dest_row >= 0) {
+          const int n_dst = ea.n_peers > 0 ? ea.n_peers : 1;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (vec_ok && j + 4 <= box_cols && n0 + c0 + j + 4 <= N) {
-              *reinterpret_cast<float4*>(yrow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
+          for (int p = 0; p < 8; ++p) {
+            if (p >= n_dst) break;
+            float* yp = ea.n_peers > 0 ? ea.peers[p] + dest_row * ldy + n0 : yrow;
 #pragma unroll
-              for (int u = 0; u < 4; ++u)
-                if (j + u < box_cols && n0 + c0 + j + u < N) yrow[c0 + j + u] = v[j + u];
+            for (int j = 0; j < 32; j += 4) {
+              if (vec_ok && j + 4 <= box_cols && n0 + c0 + j + 4 <= N) {
+                *reinterpret_cast<float4*>(yp + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (j + u < box_cols && n0 + c0 + j + u < N) yp[c0 + j + u] = v[j + u];
+              }
             }
           }
         }
       }
       if (use_fast_head && !exchanged) exchange_stats(-INFINITY, 0.f);  // no box this tile: still meet the partner
+      if (bulk_rows && !staged) {
+        const float none[32] = {};
+        stage_and_store(none, false, 0, 0);
+      }
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));  // this warp's quadrant of the accumulator is drained
     }
-    if (tma_store && lane == 0) bulk_wait_all();  // smem must outlive the last bulk store
+    if ((tma_store || ea.bulk_rows) && lane == 0) bulk_wait_all();  // smem must outlive the last bulk store
   }
 
   fence_before();
@@ -711,7 +799,7 @@ static int make_store_map_bf16(CUtensorMap* map, void* base, int64_t rows, int64
   return FITGNN_OK;
 }
 
-template <int BLOCK_N, bool GATHER, bool AGG>
+template <int BLOCK_N, bool GATHER, bool AGG, int EW = EPI_WARPS>
 static int launch(const GatherArgs& ga, const EpiArgs& ea, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const void* W_hi, const void* W_lo, int64_t ldw,
                   const float* bias, int64_t M, int K, int N, int act, int head, float* Y, void* Y_lo, int64_t ldy,
                   int sms, cudaStream_t st) {
@@ -735,7 +823,8 @@ static int launch(const GatherArgs& ga, const EpiArgs& ea, const CUtensorMap& a_
   }
   constexpr size_t SMEM_LIMIT = 227 * 1024;
   // staging + alignment slack + barriers/TMEM slot (256 B) + softmax exchange buffers (2 x 8 warps x 32 x float2)
-  constexpr size_t FIXED = EPI_STAGING_BYTES + 1024 + 256 + (BLOCK_N <= 64 ? 2 * EPI_WARPS * 32 * 8 : 0);
+  constexpr size_t FIXED = (size_t)EW * EPI_BOX_BYTES + 1024 + 256 + (BLOCK_N <= 64 ? 2 * EW * 32 * 8 : 0);
+  constexpr int NTHREADS = 64 + 32 * EW + (GATHER ? 32 * GATHER_WARPS : 0);
   const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
   const int n_tiles = (int)ceil_div(N, BLOCK_N);
   const int64_t m_tiles = ceil_div(M, BLOCK_M);
@@ -770,13 +859,13 @@ static int launch(const GatherArgs& ga, const EpiArgs& ea, const CUtensorMap& a_
     n_stages = (n_stages / k_blocks) * k_blocks;
     smem = w_bytes + (size_t)n_stages * 2 * A_PLANE_BYTES + FIXED;
   }
-  auto kern = gemm_bf16x3_kernel<BLOCK_N, GATHER, AGG>;
+  auto kern = gemm_bf16x3_kernel<BLOCK_N, GATHER, AGG, EW>;
   static size_t smem_configured = 0;  // per instantiation; raised outside of stream capture by the first (warm-up) call
   if (smem > smem_configured) {
     FG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
     smem_configured = SMEM_LIMIT;
   }
-  kern<<<grid, GATHER ? THREADS_GATHER : THREADS, smem, st>>>(ga, ea, a_hi, a_lo, w_hi, w_lo, y_map, y_lo_map, tma_store, bias,
+  kern<<<grid, NTHREADS, smem, st>>>(ga, ea, a_hi, a_lo, w_hi, w_lo, y_map, y_lo_map, tma_store, bias,
                                                               M, K, N, act, head, Y, ldy, w_stationary, n_stages);
   FG_LAUNCH_CHECK();
   return FITGNN_OK;
@@ -786,8 +875,11 @@ static int launch(const GatherArgs& ga, const EpiArgs& ea, const CUtensorMap& a_
 
 int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi, const void* W_lo, int64_t ldw,
                 const float* bias, int64_t M, int K, int N, int act, int head, float* Y, void* Y_lo, int64_t ldy,
-                const uint64_t* agg_desc, const float* agg_dinv, const int32_t* row_map, cudaStream_t st) {
+                const uint64_t* agg_desc, const float* agg_dinv, const int32_t* row_map, float* const* peers, int n_peers,
+                cudaStream_t st) {
   FG_REQUIRE(!Y_lo || head == FITGNN_HEAD_IDENTITY, FITGNN_EUNSUP, "gemm_bf16x3: split output cannot carry a head");
+  FG_REQUIRE(n_peers >= 0 && n_peers <= 8 && (n_peers == 0 || (peers && row_map)), FITGNN_EINVAL,
+             "gemm_bf16x3: peer stores need 1..8 peer bases and a row map");
   FG_REQUIRE(!agg_desc || (agg_dinv && head == FITGNN_HEAD_IDENTITY && !row_map && N > 128), FITGNN_EUNSUP,
              "gemm_bf16x3: the fused aggregation needs dinv, no head, no row map and a wide output (N > 128)");
   FG_REQUIRE(!row_map || !Y_lo, FITGNN_EUNSUP, "gemm_bf16x3: a row map needs fp32 output");
@@ -804,9 +896,23 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
   FG_TRY(tc::make_map(&a_hi, A_hi, M, K, lda, tc::BLOCK_M));
   FG_TRY(tc::make_map(&a_lo, A_lo, M, K, lda, tc::BLOCK_M));
   const tc::GatherArgs ga{};
-  const tc::EpiArgs ea{reinterpret_cast<const unsigned long long*>(agg_desc), agg_dinv, row_map};
-  if (agg_desc)
+  tc::EpiArgs ea{reinterpret_cast<const unsigned long long*>(agg_desc), agg_dinv, row_map, {}, n_peers, 0};
+  for (int p = 0; p < n_peers; ++p) ea.peers[p] = peers[p];
+  if (n_peers > 0) Y = peers[0];  // alignment checks / unused fallbacks refer to a real buffer
+  if (row_map && N <= 64 && ldy == (N + 3) / 4 * 4 && getenv("FITGNN_HEAD_BULK") == nullptr) {
+    bool aligned = ((uintptr_t)Y & 15) == 0;
+    for (int p = 0; p < n_peers; ++p) aligned = aligned && ((uintptr_t)peers[p] & 15) == 0;
+    ea.bulk_rows = aligned ? 1 : 0;
+  }
+  if (agg_desc) {
+    // K <= 128: the MMAs are short and the epilogue (activation + aggregation + bf16 split) is the bottleneck ->
+    // 128-column tiles with 16 epilogue warps (4 per scheduler).  Larger K is tensor-bound: the 256-column tile.
+    const bool wide = getenv("FITGNN_AGG_WIDE") ? atoi(getenv("FITGNN_AGG_WIDE")) != 0 : K <= 128;
+    if (wide)
+      return tc::launch<128, false, true, tc::EPI_WARPS_WIDE>(ga, ea, a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y,
+                                                              Y_lo, ldy, sms, st);
     return tc::launch<256, false, true>(ga, ea, a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y, Y_lo, ldy, sms, st);
+  }
 #define FG_TC(BN) \
   return tc::launch<BN, false, false>(ga, ea, a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y, Y_lo, ldy, sms, st)
   if (N <= 16) FG_TC(16);
@@ -814,6 +920,10 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
   if (N <= 48) FG_TC(48);
   if (N <= 64) FG_TC(64);
   if (N <= 128) FG_TC(128);
+  // small-K wide-output transforms are epilogue-bound as well (tuning switch; see the AGG dispatch above)
+  if (K <= 128 && head == FITGNN_HEAD_IDENTITY && getenv("FITGNN_GEMM_WIDE") && atoi(getenv("FITGNN_GEMM_WIDE")) != 0)
+    return tc::launch<128, false, false, tc::EPI_WARPS_WIDE>(ga, ea, a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y,
+                                                             Y_lo, ldy, sms, st);
   FG_TC(256);
 #undef FG_TC
 }
@@ -838,7 +948,7 @@ int gcn_layer_fused(const int32_t* rowptr, const int32_t* col, const float* dinv
   tc::GatherArgs ga{rowptr, col, dinv, X, src_index, out_rows, ldx, width / 4};
   CUtensorMap dummy;
   FG_TRY(tc::make_map(&dummy, W_hi, N, K, ldw, 16));  // placeholder for the unused A maps
-  const tc::EpiArgs ea{nullptr, nullptr, nullptr};
+  const tc::EpiArgs ea{nullptr, nullptr, nullptr, {}, 0, 0};
   return tc::launch<256, true, false>(ga, ea, dummy, dummy, W_hi, W_lo, ldw, bias, M, K, N, act, FITGNN_HEAD_IDENTITY, Y,
                                       Y_lo, ldy, sms, st);
 }

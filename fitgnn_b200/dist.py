@@ -109,3 +109,42 @@ class ShardedPack:
             self.slot(buf, c).copy_(o)
             self.all_gather_(buf, c, group)
         return buf.view(-1, outs[0].shape[1])[self.node_index(outs[0].device)]
+
+
+class PeerGather:
+    """Gather buffers every rank can write: the head kernel of rank r stores its rows into slot (chunk, r) of EVERY
+    rank's buffer over NVLink (ops.gemm_head_rows_peers), so the gather needs no collective — only `barrier()`,
+    a one-element all-reduce on the current stream that orders every rank's stores before any rank's reads.
+    `n_buffers` >= 2 buffers are used round-robin: a rank may start writing buffer b for step i+2 only after the
+    barrier of step i+1, which every rank enqueues after its (same-stream) reads of step i's buffer b."""
+
+    def __init__(self, shard: ShardedPack, C: int, device, n_buffers: int = 2, group=None):
+        import torch.distributed as dist
+        from . import ops
+        self.shard, self.C, self.group = shard, C, group
+        self.shape = (shard.n_chunks, shard.world, shard.max_count, C)
+        nbytes = 4 * shard.n_chunks * shard.world * max(shard.max_count, 1) * C
+        self.bufs = [ops.PeerBuffer(nbytes, device) for _ in range(n_buffers)]
+        self.tensors = [b.tensor(self.shape) for b in self.bufs]
+        handles = [None] * shard.world
+        dist.all_gather_object(handles, [b.handle for b in self.bufs], group=group)
+        # base address of buffer i on rank r, as seen from this process
+        self.bases = [[(self.bufs[i].ptr if r == shard.rank else self.bufs[i].open_peer(r, handles[r][i]))
+                       for r in range(shard.world)] for i in range(n_buffers)]
+        self._flag = torch.zeros(1, device=device)
+        self.step = 0
+
+    def slot_ptrs(self, i: int, chunk: int = 0):
+        """Addresses of slot (chunk, my rank) in buffer i of every rank (own rank first)."""
+        s = self.shard
+        off = 4 * ((chunk * s.world + s.rank) * s.max_count) * self.C
+        order = [s.rank] + [r for r in range(s.world) if r != s.rank]
+        return [self.bases[i][r] + off for r in order]
+
+    def barrier(self):
+        import torch.distributed as dist
+        dist.all_reduce(self._flag, group=self.group)
+
+    def close(self):
+        for b in self.bufs:
+            b.close()

@@ -202,7 +202,7 @@ class PackedForward:
         Xp[:, : X.shape[1]].copy_(X)
         return Xp
 
-    def _forward_aligned(self, X, out):
+    def _forward_aligned(self, X, out, peer_ptrs=None):
         """spmm0 -> [transform + next layer's aggregation]* -> last transform -> head with the padding rows dropped."""
         ap = self.apack
         M = ap.n_rows
@@ -218,27 +218,35 @@ class PackedForward:
         i = self.L - 1
         h = self._gemm(A, self.W[i], self.b[i], ops.ACT_ELU, N=self.H, K=K, name=f"gemm{i}", split_out=True)
         view = None
+        self.launches += 1
+        nb = 4 * (M * self.H + self.H * self.C + self.n_out * self.C) + 4 * M
+        if peer_ptrs is not None:  # rows go straight into this rank's slot of every rank's gather buffer
+            self._timed("head", lambda: ops.gemm_head_rows_peers(h, self.Wl, self.bl, ops.ACT_NONE, self.head, ap.orig_row,
+                                                                 peer_ptrs, ops.pad4(self.C), K=self.H, N=self.C),
+                        nbytes=nb + 4 * (len(peer_ptrs) - 1) * self.n_out * self.C, flops=2 * M * self.H * self.C)
+            return None
         if out is None:
             out = torch.empty(self.n_out, ops.pad4(self.C), dtype=torch.float32, device=X.device)
             view = out[:, : self.C]
-        self.launches += 1
         self._timed("head", lambda: ops.gemm_head_rows(h, self.Wl, self.bl, ops.ACT_NONE, self.head, ap.orig_row, out,
-                                                       K=self.H, N=self.C),
-                    nbytes=4 * (M * self.H + self.H * self.C + self.n_out * self.C) + 4 * M, flops=2 * M * self.H * self.C)
+                                                       K=self.H, N=self.C), nbytes=nb, flops=2 * M * self.H * self.C)
         return out if view is None else view
 
     # -- forward -------------------------------------------------------------------------------
     @torch.no_grad()
-    def __call__(self, X, out=None):
+    def __call__(self, X, out=None, peer_ptrs=None):
         """X: [n_src, F] fp32 CUDA — every node once (+ one row per cluster for cluster mode, i.e. C·X).
         Returns [n_out, C] (or the last hidden [n_out, H] when with_head=False), rows in pack order.
-        `out` ([n_out, C] fp32, e.g. this rank's slot of an all-gather buffer) receives the head output in place."""
+        `out` ([n_out, C] fp32, e.g. this rank's slot of an all-gather buffer) receives the head output in place.
+        `peer_ptrs` (dist.PeerGather.slot_ptrs; fused-aggregation schedule only): the head stores its rows into that slot
+        of every rank's gather buffer instead (pitch pad4(C)) and nothing is returned."""
+        assert peer_ptrs is None or self.apack is not None, "peer stores need the group-aligned schedule" 
         p = self.pack
         assert X.is_cuda and X.dtype == torch.float32 and X.shape[0] == p.n_src and X.shape[1] in (self.F, self.Fp)
         bf = self.precision == ops.GEMM_BF16X3
         X = self.pad_features(X)
         if self.apack is not None:
-            return self._forward_aligned(X, out)
+            return self._forward_aligned(X, out, peer_ptrs)
         h = None
         for i in range(self.L):
             last = i == self.L - 1

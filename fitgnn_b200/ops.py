@@ -184,6 +184,64 @@ def gemm_head_rows(A, W, bias, act, head, row_map, out, K=None, N=None):
     return out
 
 
+def gemm_head_rows_peers(A, W, bias, act, head, row_map, peer_ptrs, ldy, K=None, N=None):
+    """gemm_head_rows with every output row stored to peer_ptrs[p] + row_map[m]*ldy floats for each p (raw device
+    addresses of the same slot in every rank's gather buffer, see dist.PeerGather): the all-gather fused into the head."""
+    (a_hi, a_lo), (w_hi, w_lo) = A, W
+    M = a_hi.shape[0]
+    K = a_hi.shape[1] if K is None else K
+    N = w_hi.shape[0] if N is None else N
+    assert row_map.dtype == torch.int32 and row_map.numel() == M
+    bases = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(int(p)) for p in peer_ptrs])
+    check(lib().fitgnn_gemm_head_rows_peers(ptr(a_hi), ptr(a_lo), a_hi.stride(0), ptr(w_hi), ptr(w_lo), w_hi.stride(0),
+                                            ptr(bias), M, K, N, act, head, ptr(row_map), bases, len(peer_ptrs), ldy,
+                                            stream_ptr()))
+
+
+class PeerBuffer:
+    """A zero-filled device buffer allocated by the library (cudaMalloc) and exportable as a CUDA IPC handle.
+    `.tensor(shape)` views it as a torch fp32 tensor; `.handle` is the 64-byte blob the other ranks `open`."""
+
+    def __init__(self, nbytes, device):
+        self.nbytes, self.device = int(nbytes), torch.device(device)
+        p, h = C.c_void_p(), C.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            check(lib().fitgnn_peer_alloc(self.nbytes, C.byref(p), h))
+        self.ptr, self.handle, self.opened = p.value, h.raw, {}
+
+    def tensor(self, shape, dtype=torch.float32):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        assert n * torch.empty(0, dtype=dtype).element_size() <= self.nbytes
+
+        class _Raw:
+            pass
+
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": tuple(int(d) for d in shape), "typestr": "<f4", "data": (self.ptr, False),
+                                        "version": 2, "strides": None}
+        t = torch.as_tensor(raw, device=self.device)
+        t._fitgnn_owner = self  # the tensor must not outlive the allocation
+        return t
+
+    def open_peer(self, rank, handle):
+        """Map another rank's buffer into this process; returns its device address here."""
+        p = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().fitgnn_peer_open(handle, C.byref(p)))
+        self.opened[rank] = p.value
+        return p.value
+
+    def close(self):
+        for p in self.opened.values():
+            lib().fitgnn_peer_close(C.c_void_p(p))
+        self.opened = {}
+        if self.ptr:
+            lib().fitgnn_peer_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+
 def split_bf16(X, cols=None, ldo=None):
     """fp32 [rows, cols] -> bf16 (hi, lo) planes [rows, ldo] with zero-filled padding columns."""
     rows = X.shape[0]

@@ -211,10 +211,31 @@ int fitgnn_gcn_transform_aggregate(const void* A_hi, const void* A_lo, int64_t l
                                    void* Y_lo, int64_t ldy, void* stream);
 /* fitgnn_gemm_bias_act (BF16X3) whose output row m is written to Y row row_map[m] and skipped when row_map[m] < 0:
  * drops the padding rows of an aligned pack / scatters lt1's output (network.py:34-35) straight into the caller's
- * row order. */
+ * row order.  When ldy is N rounded up to a multiple of 4, the pitch-padding columns [N, ldy) of written rows are
+ * zero-filled (narrow heads write whole rows with bulk copies); otherwise they are left untouched. */
 int fitgnn_gemm_head_rows(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi,
                           const void* W_lo, int64_t ldw, const float* bias, int64_t M, int K, int N,
                           int act, int head, const int32_t* row_map, float* Y, int64_t ldy, void* stream);
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU output exchange fused into the head (one process per GPU on one NVLink/NVSwitch box).
+ * The reference is single-device; with the subgraphs sharded over N ranks the only
+ * inference-path exchange is the gather of the core-node outputs.
+ * fitgnn_gemm_head_rows_peers = fitgnn_gemm_head_rows whose output row m is stored to
+ *   host_peer_bases[p] + row_map[m] * ldy   for every p in [0, n_peers)
+ * i.e. into the same slot of every rank's gather buffer (peer-mapped device pointers, the stores travel
+ * over NVLink while the kernel computes), so no all-gather follows the head: a barrier among the ranks
+ * (stream-ordered, e.g. a one-element all-reduce) is all that remains.  host_peer_bases is a HOST array.
+ * fitgnn_peer_alloc/open/close/free provide such buffers: cudaMalloc'ed (zero-filled) memory exported as a
+ * 64-byte CUDA IPC handle and imported by the other ranks (peer access is enabled on import).
+ * ---------------------------------------------------------------------------------------- */
+int fitgnn_gemm_head_rows_peers(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi,
+                                const void* W_lo, int64_t ldw, const float* bias, int64_t M, int K,
+                                int N, int act, int head, const int32_t* row_map,
+                                float* const* host_peer_bases, int n_peers, int64_t ldy, void* stream);
+int fitgnn_peer_alloc(size_t bytes, void** dev_ptr, uint8_t* handle_out /*[64] host*/);
+int fitgnn_peer_open(const uint8_t* handle /*[64] host*/, void** dev_ptr);
+int fitgnn_peer_close(void* dev_ptr);
+int fitgnn_peer_free(void* dev_ptr);
 /* fp32 [rows, cols] (ld = ldx) -> bf16 hi/lo planes [rows, ldo] (columns >= cols zero filled) */
 int fitgnn_split_bf16(const float* X, int64_t ldx, int64_t rows, int cols, void* hi, void* lo,
                       int64_t ldo, void* stream);

@@ -159,7 +159,8 @@ def test_head_rows_drops_padding(fg, N, head):
     want[row_map[keep].long()] = z[keep]
     got = out.cpu()[:, :N].double()
     assert (got - want).abs().max() / max(1.0, want.abs().max()) < 1e-4
-    assert (out.cpu()[:, N:] == 7.0).all()  # columns past N untouched
+    pad = out.cpu()[:, N:]
+    assert ((pad == 7.0) | (pad == 0.0)).all()  # pitch padding: untouched or zero-filled, never garbage
 
 
 @pytest.mark.parametrize("n,k,F,H,C,layers", [(3000, 1300, 100, 512, 47, 2), (2000, 900, 30, 256, 5, 3), (500, 400, 100, 512, 7, 2)])
