@@ -49,9 +49,12 @@ def parse():
     p.add_argument("--no-fuse-aggregate", action="store_true",
                    help="classic schedule: stand-alone SpMM per layer instead of the aggregation fused into the transform")
     p.add_argument("--seed", type=int, default=0)
-    p.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl"],
+    p.add_argument("--collective", default="auto", choices=["auto", "p2p", "mc", "ce", "nccl"],
                    help="N>1 output exchange: p2p = head kernel stores into every rank's gather buffer over NVLink "
-                        "(+ a one-element all-reduce as barrier); nccl = head into the local slot, then all_gather")
+                        "(+ a one-element all-reduce as barrier); ce = head into the local slot, copy-engine pushes to the "
+                        "peers on a side stream overlapping the next step's compute; nccl = local slot, then all_gather; "
+                        "mc = like p2p but ONE store to the NVLS multicast address (replicated by the NVSwitch); "
+                        "auto = p2p up to 4 GPUs, ce above (measured)")
     p.add_argument("--chunks", type=int, default=1, help="N>1: chunks per rank; chunk c's all-gather overlaps chunk c+1")
     return p.parse_args()
 
@@ -285,8 +288,11 @@ def main_ours(args):
     if world > 1 and args.collective != "nccl" and all(f.apack is not None for f in fwds):
         try:
             from fitgnn_b200.dist import PeerGather
-            pg = PeerGather(shard, Cp, device, n_buffers=2)
-            collective = "p2p"
+            pg = PeerGather(shard, Cp, device, n_buffers=2, backend="symm" if args.collective == "mc" else "ipc")
+            # measured on 8xB200 (profiles/r1_multi_gpu.md): the fused peer stores win up to 4 GPUs; at 8 the head becomes
+            # NVLink-bound (7 x its slot per rank) and the overlapped copy-engine exchange is ahead; the multicast store
+            # does not help an all-gather (every rank still has to RECEIVE all the other slots)
+            collective = args.collective if args.collective != "auto" else ("p2p" if world <= 4 else "ce")
         except Exception as e:  # IPC not permitted in this container, ...
             if args.collective == "p2p":
                 raise
@@ -298,10 +304,21 @@ def main_ours(args):
             pg, collective = None, "nccl"
 
     def run_p2p(Xin, b):
+        if collective == "ce":
+            pg.acquire(b)
+            for c, f in enumerate(fwds):
+                f(Xin, out=shard.slot(pg.tensors[b], c))
+            pg.exchange_async(b)  # completes behind the next step; the timed region ends with pg.wait on both buffers
+            return pg.tensors[b]
         for c, f in enumerate(fwds):
-            f(Xin, peer_ptrs=pg.slot_ptrs(b, c))
+            f(Xin, peer_ptrs=pg.slot_ptrs(b, c, multicast=(collective == "mc")))
         pg.barrier()
         return pg.tensors[b]
+
+    def drain():
+        if pg is not None and collective == "ce":
+            for b in range(2):
+                pg.wait(b)
 
     step_no = [0]
 
@@ -358,6 +375,7 @@ def main_ours(args):
             e_ = torch.cuda.Event(enable_timing=True)
             e_.record()
             step_ev.append(e_)
+    drain()  # pipelined exchange: every step's outputs are complete on every rank before the clock stops
     ev1.record()
     barrier()
     mark1 = sampler.mark()
@@ -386,6 +404,23 @@ def main_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+
+    # ---- N > 1: the gathered result on EVERY rank equals a single-GPU forward of the whole pack (outside the timing)
+    verify = None
+    if world > 1:
+        res = step()
+        drain()
+        barrier()
+        gathered = res.view(-1, Cp)[shard.node_index(device)][:, :C]
+        ref_rows = fg.PackedForward(pack, sd, head="log_softmax", rows="core", precision=precision,
+                                    fuse_aggregate=False if args.no_fuse_aggregate else "auto")(Xd)
+        full = torch.empty(n, C, device=device)
+        full[pack.core_gid.long()] = ref_rows[:, :C]
+        err = (gathered - full).abs().max().reshape(1)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        verify = float(err.item())
+        del gathered, ref_rows, full, res
+        barrier()
 
     # ---- end to end through the public API with HOST buffers: every step copies X from pinned host memory to the
     # device, runs the forward (+ all-gather) and copies this rank's logits back to pinned host memory.  Steps are
@@ -455,6 +490,8 @@ def main_ours(args):
         e2e_run(args.steps)
         s_out.wait_stream(s_cmp)
         s_out.wait_stream(s_in)
+        with torch.cuda.stream(s_out):
+            drain()
         e1.record(s_out)
         barrier()
         t2 = torch.tensor([e0.elapsed_time(e1) / args.steps], device=device, dtype=torch.float64)
@@ -521,7 +558,8 @@ def main_ours(args):
             "kernels": kernels, "gpu_launches": gpu_launches, "clocks": sampler.summary(mark0, mark1),
             "pack": {"rows": pack.n_rows, "nnz": pack.nnz, "subgraphs": pack.n_sub, "build_ms": pack_build_ms,
                      "bytes": pack.nbytes(), "rank_loads": shard.loads},
-            "multi_gpu": {"chunks_per_rank": n_chunks, "collective": collective, "rank_kernel_ms": rank_kernel_ms,
+            "multi_gpu": {"chunks_per_rank": n_chunks, "collective": collective,
+                          "gathered_vs_single_gpu_max_abs_err_all_ranks": verify, "rank_kernel_ms": rank_kernel_ms,
                           "all_gather_bytes": int(n * Cp * 4) if world > 1 else 0,
                           "exposed_ms": (ms - max(rank_kernel_ms)) if rank_kernel_ms else 0.0}}
     if projection:

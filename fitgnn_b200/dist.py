@@ -118,26 +118,60 @@ class PeerGather:
     `n_buffers` >= 2 buffers are used round-robin: a rank may start writing buffer b for step i+2 only after the
     barrier of step i+1, which every rank enqueues after its (same-stream) reads of step i's buffer b."""
 
-    def __init__(self, shard: ShardedPack, C: int, device, n_buffers: int = 2, group=None):
+    def __init__(self, shard: ShardedPack, C: int, device, n_buffers: int = 2, group=None, backend: str = "ipc"):
+        """backend 'ipc': cudaMalloc + CUDA IPC handles (fitgnn_peer_*).  backend 'symm': torch symmetric memory (CUDA
+        VMM allocations mapped on every rank) which additionally yields an NVLS multicast address: ONE store to it is
+        replicated by the NVSwitch into every rank's buffer, so a rank's egress is its own slot once instead of
+        once per peer (`slot_ptrs(..., multicast=True)`)."""
         import torch.distributed as dist
         from . import ops
-        self.shard, self.C, self.group = shard, C, group
+        self.shard, self.C, self.group, self.backend = shard, C, group, backend
         self.shape = (shard.n_chunks, shard.world, shard.max_count, C)
-        nbytes = 4 * shard.n_chunks * shard.world * max(shard.max_count, 1) * C
-        self.bufs = [ops.PeerBuffer(nbytes, device) for _ in range(n_buffers)]
-        self.tensors = [b.tensor(self.shape) for b in self.bufs]
-        handles = [None] * shard.world
-        dist.all_gather_object(handles, [b.handle for b in self.bufs], group=group)
-        # base address of buffer i on rank r, as seen from this process
-        self.bases = [[(self.bufs[i].ptr if r == shard.rank else self.bufs[i].open_peer(r, handles[r][i]))
-                       for r in range(shard.world)] for i in range(n_buffers)]
+        numel = shard.n_chunks * shard.world * max(shard.max_count, 1) * C
+        nbytes = 4 * numel
+        self.bufs, self.mc_bases = [], [0] * n_buffers
+        if backend == "symm":
+            import torch.distributed._symmetric_memory as symm_mem
+            stride = (nbytes + 4095) // 4096 * 4096  # every buffer starts on a 4 KB boundary
+            self._symm = symm_mem.empty(n_buffers * stride // 4, dtype=torch.float32, device=torch.device(device))
+            self._symm.zero_()
+            self._hdl = symm_mem.rendezvous(self._symm, dist.group.WORLD if group is None else group)
+            self.tensors = [self._symm[i * stride // 4: i * stride // 4 + numel].view(self.shape) for i in range(n_buffers)]
+            ptrs = list(self._hdl.buffer_ptrs)
+            self.bases = [[int(ptrs[r]) + i * stride for r in range(shard.world)] for i in range(n_buffers)]
+            mc = int(getattr(self._hdl, "multicast_ptr", 0) or 0)
+            if mc:
+                self.mc_bases = [mc + i * stride for i in range(n_buffers)]
+        else:
+            self.bufs = [ops.PeerBuffer(nbytes, device) for _ in range(n_buffers)]
+            self.tensors = [b.tensor(self.shape) for b in self.bufs]
+            handles = [None] * shard.world
+            dist.all_gather_object(handles, [b.handle for b in self.bufs], group=group)
+            # base address of buffer i on rank r, as seen from this process
+            self.bases = [[(self.bufs[i].ptr if r == shard.rank else self.bufs[i].open_peer(r, handles[r][i]))
+                           for r in range(shard.world)] for i in range(n_buffers)]
         self._flag = torch.zeros(1, device=device)
         self.step = 0
+        self._peer_slots = {}
+        self.xstream = torch.cuda.Stream(device=device)
+        self.pstreams = [torch.cuda.Stream(device=device) for _ in range(max(shard.world - 1, 0))]
+        self._ready = [torch.cuda.Event() for _ in range(n_buffers)]
+        self._done = [torch.cuda.Event() for _ in range(n_buffers)]
+        for e in self._done:
+            e.record(torch.cuda.current_stream())
 
-    def slot_ptrs(self, i: int, chunk: int = 0):
-        """Addresses of slot (chunk, my rank) in buffer i of every rank (own rank first)."""
+    @property
+    def has_multicast(self):
+        return all(b != 0 for b in self.mc_bases)
+
+    def slot_ptrs(self, i: int, chunk: int = 0, multicast: bool = False):
+        """Addresses of slot (chunk, my rank) in buffer i of every rank (own rank first), or — multicast — the single
+        NVLS address whose stores land in that slot on every rank (this one included)."""
         s = self.shard
         off = 4 * ((chunk * s.world + s.rank) * s.max_count) * self.C
+        if multicast:
+            assert self.has_multicast, "no multicast mapping (backend 'symm' on an NVSwitch box needed)"
+            return [self.mc_bases[i] + off]
         order = [s.rank] + [r for r in range(s.world) if r != s.rank]
         return [self.bases[i][r] + off for r in order]
 
@@ -145,6 +179,52 @@ class PeerGather:
         import torch.distributed as dist
         dist.all_reduce(self._flag, group=self.group)
 
+    # ---- copy-engine exchange, overlapped with the next step's compute ------------------------------------------
+    def _peer_slot(self, i: int, r: int, chunk: int):
+        """slot (chunk, my rank) of buffer i on rank r as a tensor in this process (peer-mapped address)"""
+        from . import ops
+        key = (i, r, chunk)
+        if key not in self._peer_slots:
+            s = self.shard
+            cnt = s.counts[s.rank * s.n_chunks + chunk]
+            off = 4 * ((chunk * s.world + s.rank) * s.max_count) * self.C
+            self._peer_slots[key] = ops.raw_tensor(self.bases[i][r] + off, (cnt, self.C), self._flag.device, owner=self)
+        return self._peer_slots[key]
+
+    def exchange_async(self, i: int):
+        """After this rank's head kernels wrote slot (c, rank) of its OWN buffer i on the current stream: push the slots to
+        every peer with device-to-device copies (copy engines over NVLink, no SM time) on a side stream, then the
+        barrier, all behind whatever the current stream does next (the following step's compute).  `wait(i)` makes the
+        current stream wait for buffer i to be complete on every rank; `acquire(i)` must precede the next write of it."""
+        s = self.shard
+        cur = torch.cuda.current_stream()
+        self._ready[i].record(cur)
+        # one side stream per peer: a single copy stream reaches ~200 GB/s, the copy engines together saturate NVLink
+        k = 0
+        for r in range(s.world):
+            if r == s.rank:
+                continue
+            ps = self.pstreams[k]
+            k += 1
+            with torch.cuda.stream(ps):
+                ps.wait_event(self._ready[i])
+                for c in range(s.n_chunks):
+                    self._peer_slot(i, r, c).copy_(s.slot(self.tensors[i], c), non_blocking=True)
+        with torch.cuda.stream(self.xstream):
+            for ps in self.pstreams:
+                self.xstream.wait_stream(ps)
+            self.barrier()
+            self._done[i].record(self.xstream)
+
+    def acquire(self, i: int):
+        """Before the head kernels overwrite this rank's slots of buffer i: the pushes that read them are finished."""
+        torch.cuda.current_stream().wait_event(self._done[i])
+
+    def wait(self, i: int):
+        torch.cuda.current_stream().wait_event(self._done[i])
+
     def close(self):
+        self._peer_slots = {}
+        self.tensors = None
         for b in self.bufs:
             b.close()

@@ -198,6 +198,19 @@ def gemm_head_rows_peers(A, W, bias, act, head, row_map, peer_ptrs, ldy, K=None,
                                             stream_ptr()))
 
 
+def raw_tensor(ptr_value, shape, device, owner=None):
+    """fp32 torch view of a raw device address (library-allocated or peer-mapped memory); `owner` is kept alive by it."""
+    class _Raw:
+        pass
+
+    raw = _Raw()
+    raw.__cuda_array_interface__ = {"shape": tuple(int(d) for d in shape), "typestr": "<f4", "data": (int(ptr_value), False),
+                                    "version": 2, "strides": None}
+    t = torch.as_tensor(raw, device=torch.device(device))
+    t._fitgnn_owner = owner
+    return t
+
+
 class PeerBuffer:
     """A zero-filled device buffer allocated by the library (cudaMalloc) and exportable as a CUDA IPC handle.
     `.tensor(shape)` views it as a torch fp32 tensor; `.handle` is the 64-byte blob the other ranks `open`."""
@@ -215,15 +228,7 @@ class PeerBuffer:
             n *= int(d)
         assert n * torch.empty(0, dtype=dtype).element_size() <= self.nbytes
 
-        class _Raw:
-            pass
-
-        raw = _Raw()
-        raw.__cuda_array_interface__ = {"shape": tuple(int(d) for d in shape), "typestr": "<f4", "data": (self.ptr, False),
-                                        "version": 2, "strides": None}
-        t = torch.as_tensor(raw, device=self.device)
-        t._fitgnn_owner = self  # the tensor must not outlive the allocation
-        return t
+        return raw_tensor(self.ptr, shape, self.device, owner=self)  # the tensor must not outlive the allocation
 
     def open_peer(self, rank, handle):
         """Map another rank's buffer into this process; returns its device address here."""

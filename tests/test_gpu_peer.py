@@ -83,6 +83,18 @@ def _rank_main(rank, world, port, ret):
         err = float((got - full).abs().max())
         ret[(rank, step)] = err
         dist.barrier()
+    # copy-engine exchange: head into the local slot, pushes + barrier on the side stream
+    for step in range(3):
+        b = step % 2
+        pgather.acquire(b)
+        f(X, out=shard.slot(pgather.tensors[b], 0))
+        pgather.exchange_async(b)
+        pgather.wait(b)
+        torch.cuda.synchronize()
+        dist.barrier()
+        got = pgather.tensors[b].view(-1, Cp)[shard.node_index(d)][:, :Cc]
+        ret[(rank, 10 + step)] = float((got - full).abs().max())
+        dist.barrier()
     del got
     pgather.tensors = None
     dist.barrier()
@@ -101,4 +113,4 @@ def test_two_ranks_exchange_through_peer_buffers(fg):
     for p in procs:
         p.join(300)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    assert len(ret) == 6 and max(ret.values()) < 1e-5, dict(ret)
+    assert len(ret) == 12 and max(ret.values()) < 1e-5, dict(ret)
