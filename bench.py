@@ -46,6 +46,8 @@ def parse():
     p.add_argument("--profiler-range", action="store_true",
                    help="cudaProfilerStart/Stop around the timed steps (for `ncu --profile-from-start off`)")
     p.add_argument("--no-projection", action="store_true", help="skip the Gc projection kernels (Xc = C·X, Ac = P·A·P^T)")
+    p.add_argument("--align-policy", default="degree", choices=["degree", "order"],
+                   help="placement of the subgraphs in the group-aligned pack (see include/fitgnn.h)")
     p.add_argument("--no-fuse-aggregate", action="store_true",
                    help="classic schedule: stand-alone SpMM per layer instead of the aggregation fused into the transform")
     p.add_argument("--seed", type=int, default=0)
@@ -276,9 +278,11 @@ def main_ours(args):
     if precision == "auto":
         precision = os.environ.get("FITGNN_PRECISION", "bf16x3")
     fwds = [fg.PackedForward(lp, sd, head="log_softmax", rows="core", precision=precision,
-                             fuse_aggregate=False if args.no_fuse_aggregate else "auto") for lp in shard.locals]
+                             fuse_aggregate=False if args.no_fuse_aggregate else "auto", align_policy=args.align_policy)
+            for lp in shard.locals]
     fwd = fwds[0]
-    Xd = fwd.pad_features(X)
+    # the group-aligned schedule takes the feature table un-padded ([n, 100]); the classic one wants the K-padded pitch
+    Xd = X if (fwd.apack is not None and F % 4 == 0) else fwd.pad_features(X)
 
     Cp = (C + 3) // 4 * 4  # logits row pitch padded to 16 bytes (aligned stores in the head kernel); columns >= C unused
     gbuf = shard.gather_buffer(Cp, device) if world > 1 else None
@@ -413,7 +417,8 @@ def main_ours(args):
         barrier()
         gathered = res.view(-1, Cp)[shard.node_index(device)][:, :C]
         ref_rows = fg.PackedForward(pack, sd, head="log_softmax", rows="core", precision=precision,
-                                    fuse_aggregate=False if args.no_fuse_aggregate else "auto")(Xd)
+                                    fuse_aggregate=False if args.no_fuse_aggregate else "auto",
+                                    align_policy=args.align_policy)(Xd)
         full = torch.empty(n, C, device=device)
         full[pack.core_gid.long()] = ref_rows[:, :C]
         err = (gathered - full).abs().max().reshape(1)

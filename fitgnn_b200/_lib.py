@@ -52,8 +52,9 @@ SIGNATURES = {
                                            c_i32, c_i32, c_i32, c_void, c_void, c_i64, c_void]),
     "fitgnn_gcn_layer_fused": (c_i32, [c_void, c_void, c_void, c_void, c_i64, c_i32, c_void, c_void, c_i64, c_void, c_void,
                                        c_i64, c_void, c_i32, c_i32, c_void, c_void, c_i64, c_void]),
-    "fitgnn_pack_align_plan": (c_i32, [c_void, c_i64, c_i32, c_void, C.POINTER(c_i64), C.POINTER(c_i32), c_void, c_size,
-                                       c_void]),
+    "fitgnn_pack_align_workspace_bytes": (c_size, [c_i64, c_i64]),
+    "fitgnn_pack_align_plan": (c_i32, [C.POINTER(PackStruct), c_i32, c_i32, c_void, C.POINTER(c_i64), C.POINTER(c_i32),
+                                       c_void, c_size, c_void]),
     "fitgnn_pack_align_fill": (c_i32, [C.POINTER(PackStruct), c_void, c_i32, c_i64, C.POINTER(PackStruct), c_void, c_void,
                                        c_void, C.POINTER(c_i32), c_void, c_size, c_void]),
     "fitgnn_gcn_transform_aggregate": (c_i32, [c_void, c_void, c_i64, c_void, c_void, c_i64, c_void, c_i64, c_i32, c_i32,

@@ -34,7 +34,7 @@ class PackedForward:
     'core' (node tasks), 'mask' (graph tasks: x[mask], network.py:129) or 'all'."""
 
     def __init__(self, pack: Pack, state_dict, head="log_softmax", rows="core", precision="fp32",
-                 with_head=True, fuse_layer0=False, fuse_aggregate="auto"):
+                 with_head=True, fuse_layer0=False, fuse_aggregate="auto", align_policy="degree"):
         self.pack = pack
         dev = pack.device
         self.precision = ops.GEMM_BF16X3 if precision == "bf16x3" else ops.GEMM_FP32
@@ -85,7 +85,7 @@ class PackedForward:
         eligible = (self.precision == ops.GEMM_BF16X3 and self.L >= 2 and not self.transform_first and with_head
                     and self.out_rows is None and self.H > 128 and self.H % 8 == 0 and pack.n_rows > 0)
         if fuse_aggregate and eligible:
-            ap = pack.aligned(32)
+            ap = pack.aligned(32, align_policy)
             if ap is not None and ap.agg_ok:
                 self.apack = ap
                 self.hubs_aligned = ops.find_hubs(ap.rowptr, None, ap.n_rows)
@@ -158,7 +158,7 @@ class PackedForward:
                                                            out=out, split_out=split_out),
                            nbytes=4 * (M * K + K * N + M * N), flops=2 * M * K * N)
 
-    def _spmm(self, X, width, src_index, bias, act, last, split, name="spmm", pack=None):
+    def _spmm(self, X, width, src_index, bias, act, last, split, name="spmm", pack=None, out=None):
         p = self.pack if pack is None else pack
         rows = self.out_rows if last else None
         hubs = self.hubs_out if last else self.hubs_all
@@ -167,7 +167,7 @@ class PackedForward:
         self.launches += 1 + (1 if hubs[1] > 0 else 0)
         n_src_rows = X.shape[0] if src_index is not None else p.n_rows
         return self._timed(name, lambda: ops.spmm_symnorm(p.rowptr, p.col, p.dinv, X, width, src_index, bias, act, rows,
-                                                          split=split, hubs=hubs),
+                                                          split=split, hubs=hubs, out=out),
                            nbytes=self._spmm_bytes(width, src_index, last, n_src_rows))
 
     def _fused_layer0(self, X, last):
@@ -206,8 +206,12 @@ class PackedForward:
         """spmm0 -> [transform + next layer's aggregation]* -> last transform -> head with the padding rows dropped."""
         ap = self.apack
         M = ap.n_rows
-        A = self._spmm(X, self.Fp, ap.gid, None, ops.ACT_NONE, False, split=True, name="spmm0", pack=ap)
-        K = self.Fp
+        # X may come un-padded ([n, F] with F % 4 == 0): the planes keep the 8-element pitch the TMA maps need, the
+        # transform runs with K = F and the TMA unit zero-fills the columns beyond it
+        K = X.shape[1]
+        planes = (torch.empty(M, self.Fp, dtype=torch.bfloat16, device=X.device),
+                  torch.empty(M, self.Fp, dtype=torch.bfloat16, device=X.device))
+        A = self._spmm(X, K, ap.gid, None, ops.ACT_NONE, False, split=True, name="spmm0", pack=ap, out=planes)
         for i in range(self.L - 1):
             Ai, Ki = A, K
             self.launches += 1
@@ -244,9 +248,11 @@ class PackedForward:
         p = self.pack
         assert X.is_cuda and X.dtype == torch.float32 and X.shape[0] == p.n_src and X.shape[1] in (self.F, self.Fp)
         bf = self.precision == ops.GEMM_BF16X3
-        X = self.pad_features(X)
         if self.apack is not None:
+            if not (X.is_contiguous() and X.shape[1] % 4 == 0):
+                X = self.pad_features(X)
             return self._forward_aligned(X, out, peer_ptrs)
+        X = self.pad_features(X)
         h = None
         for i in range(self.L):
             last = i == self.L - 1

@@ -97,20 +97,25 @@ class Pack:
         kw.update({k: (blob[k].to(device) if blob[k] is not None else None) for k in Pack._ARRAYS})
         return Pack(**kw)
 
-    def aligned(self, group=32):
+    def aligned(self, group=32, policy="degree"):
         """The same pack re-laid-out so that no subgraph straddles a multiple of `group` rows (padding rows are empty
-        CSR rows with dinv = 0 at the tail of a group).  Returns None when a subgraph has more than `group` rows.
-        The result carries orig_row / new_of_old / agg_desc for fitgnn_gcn_transform_aggregate."""
+        CSR rows with dinv = 0).  policy 'order' keeps the subgraph order; 'degree' groups subgraphs of similar row degree
+        and fills group tails with low-degree subgraphs instead of padding (see include/fitgnn.h).  Returns None when a
+        subgraph has more than `group` rows.  The result carries orig_row / new_of_old / agg_desc for
+        fitgnn_gcn_transform_aggregate; its sub_ptr[s] is the first row of subgraph s (not monotone under 'degree')."""
         dev = self.device
         i32 = dict(dtype=torch.int32, device=dev)
         new_sub = torch.empty(self.n_sub + 1, **i32)
-        ws = torch.zeros(64, dtype=torch.uint8, device=dev)
+        pol = {"order": 0, "degree": 1}[policy]
+        ws = ops._ws(lib().fitgnn_pack_align_workspace_bytes(self.n_sub, 0), dev)
         n_al, ok = C.c_int64(0), C.c_int(0)
-        check(lib().fitgnn_pack_align_plan(ptr(self.sub_ptr), self.n_sub, group, ptr(new_sub), C.byref(n_al),
-                                           C.byref(ok), ptr(ws), ws.numel(), stream_ptr()))
+        src = self.struct()
+        check(lib().fitgnn_pack_align_plan(C.byref(src), group, pol, ptr(new_sub), C.byref(n_al), C.byref(ok), ptr(ws),
+                                           ws.numel(), stream_ptr()))
         if not ok.value:
             return None
         n = n_al.value
+        ws = ops._ws(lib().fitgnn_pack_align_workspace_bytes(self.n_sub, n), dev)
         a = Pack(n_rows=n, nnz=self.nnz, n_sub=self.n_sub, n_core=self.n_core, n_src=self.n_src, n_nodes=self.n_nodes,
                  mode=self.mode, rowptr=torch.empty(n + 1, **i32), col=torch.empty(self.nnz, **i32),
                  dinv=torch.empty(n, dtype=torch.float32, device=dev), gid=torch.empty(n, **i32),
@@ -119,7 +124,7 @@ class Pack:
                  part=self.part, orig_row=torch.empty(n, **i32), new_of_old=torch.empty(self.n_rows, **i32),
                  agg_desc=torch.empty(n, dtype=torch.int64, device=dev))
         flags = C.c_int(0)
-        src, dst = self.struct(), a.struct()
+        dst = a.struct()
         check(lib().fitgnn_pack_align_fill(C.byref(src), ptr(new_sub), group, n, C.byref(dst), ptr(a.orig_row),
                                            ptr(a.new_of_old), ptr(a.agg_desc), C.byref(flags), ptr(ws), ws.numel(),
                                            stream_ptr()))

@@ -184,17 +184,25 @@ int fitgnn_gcn_layer_fused(const int32_t* rowptr, const int32_t* col, const floa
  * quadrant / one epilogue warp of the tensor-core transform, and the propagate step becomes register shuffles inside
  * that epilogue (fitgnn_gcn_transform_aggregate) instead of an SpMM launch with an HBM round trip.
  *
+ * Placement policy: FITGNN_ALIGN_IN_ORDER keeps the subgraph order (greedy; a group is closed with padding when the next
+ *   subgraph does not fit); FITGNN_ALIGN_BY_DEGREE places subgraphs by (largest non-self row degree desc, size desc, index
+ *   asc) and fills the gap at a group's tail from the other end of that order — the fused aggregation loops to the largest
+ *   row degree among a warp's 32 rows, so similar degrees belong together, and low-degree fillers replace the padding.
  * fitgnn_pack_align_plan: new_sub_ptr[s] = first aligned row of subgraph s (device, [n_sub+1], last = aligned row
  *   count, also returned in *host_n_rows_aligned); *host_alignable = 0 when some subgraph has more than `group` rows.
+ *   Workspace: fitgnn_pack_align_workspace_bytes(n_sub, 0) for the plan, (n_sub, n_rows_aligned) for the fill.
  * fitgnn_pack_align_fill: fills the caller-allocated aligned pack `out` (n_rows = aligned row count; nnz, n_sub,
  *   n_core, n_src as `in`): padding rows are empty CSR rows with dinv = 0, they belong to the subgraph they follow.
  *   orig_row[aligned row] = row of `in` (-1 for padding), new_of_old[row of in] = aligned row,
  *   agg_desc[aligned row] = bits [0,4): number c <= 12 of non-self CSR entries, bits [4+5j, 9+5j): row-in-group of the
  *   j-th one (duplicates kept).  *host_flags: bit 0 = a row has more than 12 non-self entries (descriptor truncated:
  *   do not use the fused aggregation), bit 1 = a row without self loop, bit 2 = an entry leaves its subgraph.
- * Both need a 64-byte device workspace.  group must be 32.
+ *   In the aligned pack sub_ptr[s] is the first row of subgraph s (not monotone under BY_DEGREE), sub_ptr[n_sub] the
+ *   aligned row count.  group must be 32.
  * ---------------------------------------------------------------------------------------- */
-int fitgnn_pack_align_plan(const int32_t* sub_ptr, int64_t n_sub, int group, int32_t* new_sub_ptr,
+enum { FITGNN_ALIGN_IN_ORDER = 0, FITGNN_ALIGN_BY_DEGREE = 1 };
+size_t fitgnn_pack_align_workspace_bytes(int64_t n_sub, int64_t n_rows_aligned);
+int fitgnn_pack_align_plan(const fitgnn_pack* in, int group, int policy, int32_t* new_sub_ptr,
                            int64_t* host_n_rows_aligned, int* host_alignable, void* ws, size_t ws_bytes,
                            void* stream);
 int fitgnn_pack_align_fill(const fitgnn_pack* in, const int32_t* new_sub_ptr, int group,

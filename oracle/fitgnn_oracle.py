@@ -584,30 +584,47 @@ def subgraphs_from_partition(edge_index, x, part, sub_ids):
 # ============================================================================================
 
 
-def aligned_layout(sub_ptr, group=32):
-    """Greedy in-order placement: subgraph s starts at the current position unless it would straddle a multiple of
-    `group`, in which case the group is closed with padding first.  Returns (new_start[n_sub+1], n_rows_aligned) or
-    None when a subgraph has more than `group` rows."""
+def aligned_layout(sub_ptr, group=32, policy="order", rowptr=None):
+    """Placement of the subgraphs in the group-aligned layout (restates fitgnn_pack_align_plan).
+    policy 'order': greedy in subgraph order; a group is closed with padding when the next subgraph does not fit.
+    policy 'degree': order = (largest non-self row degree desc, size desc, index asc); when the next subgraph does not
+    fit, subgraphs are taken from the END of that order while they fit, else the group is closed with padding.
+    Returns (new_start[n_sub+1] indexed by subgraph, n_rows_aligned) or None when a subgraph has more than `group` rows."""
     sub_ptr = np.asarray(sub_ptr, dtype=np.int64)
     sizes = np.diff(sub_ptr)
-    if sizes.size and sizes.max() > group:
+    n_sub = sizes.size
+    if n_sub and sizes.max() > group:
         return None
-    new_start = np.zeros(sizes.size + 1, dtype=np.int64)
-    pos = 0
-    for s, size in enumerate(sizes):
-        off = pos % group
-        if off + size > group:
-            pos += group - off
-        new_start[s] = pos
-        pos += size
+    if policy == "degree":
+        deg = np.diff(np.asarray(rowptr, dtype=np.int64)) - 1
+        maxdeg = np.array([min(max(int(deg[sub_ptr[s]:sub_ptr[s + 1]].max()) if sizes[s] else 0, 0), 63) for s in range(n_sub)],
+                          dtype=np.int64)
+        order = np.lexsort((np.arange(n_sub), -sizes, -maxdeg))
+    else:
+        order = np.arange(n_sub)
+    new_start = np.zeros(n_sub + 1, dtype=np.int64)
+    pos, head, tail = 0, 0, n_sub - 1
+    while head <= tail:
+        size = int(sizes[order[head]])
+        rem = group - pos % group
+        if size <= rem:
+            new_start[order[head]] = pos
+            pos += size
+            head += 1
+        elif policy == "degree" and head < tail and sizes[order[tail]] <= rem:
+            new_start[order[tail]] = pos
+            pos += int(sizes[order[tail]])
+            tail -= 1
+        else:
+            pos += rem
     new_start[-1] = pos
     return new_start, int(pos)
 
 
-def aligned_pack(pack, group=32):
+def aligned_pack(pack, group=32, policy="order"):
     """Expected arrays of Pack.aligned(): `pack` is a dict of numpy arrays (rowptr, col, dinv, gid, sub_ptr, core_rows,
     is_core, mask).  Padding rows: empty CSR row, dinv 0, gid 0, flags 0, orig_row -1."""
-    lay = aligned_layout(pack["sub_ptr"], group)
+    lay = aligned_layout(pack["sub_ptr"], group, policy, pack["rowptr"])
     if lay is None:
         return None
     new_start, n_al = lay
@@ -622,8 +639,12 @@ def aligned_pack(pack, group=32):
     deg = np.zeros(n_al, dtype=np.int64)
     deg[new_of_old] = np.diff(rowptr)
     rowptr_a = np.concatenate([[0], np.cumsum(deg)])
-    row_of_entry = np.repeat(np.arange(n_rows), np.diff(rowptr))
-    col_a = np.asarray(pack["col"], dtype=np.int64) + shift_of_row[row_of_entry]
+    col = np.asarray(pack["col"], dtype=np.int64)
+    col_a = np.zeros(col.size, dtype=np.int64)
+    for r in range(n_rows):  # entries keep their order inside a row; rows land where the aligned row pointers say
+        e0, e1 = rowptr[r], rowptr[r + 1]
+        d0 = rowptr_a[new_of_old[r]]
+        col_a[d0:d0 + (e1 - e0)] = col[e0:e1] + shift_of_row[r]
     out = dict(rowptr=rowptr_a, col=col_a, new_of_old=new_of_old, orig_row=orig_row, sub_ptr=new_start,
                core_rows=new_of_old[np.asarray(pack["core_rows"], dtype=np.int64)], n_rows=n_al)
     for name, dt in (("dinv", np.float32), ("gid", np.int64), ("is_core", np.uint8), ("mask", np.uint8)):
@@ -636,7 +657,7 @@ def aligned_pack(pack, group=32):
     for r in range(n_rows):
         nr = int(new_of_old[r])
         lanes, self_seen = [], False
-        for c in pack["col"][rowptr[r]:rowptr[r + 1]]:
+        for c in col[rowptr[r]:rowptr[r + 1]]:
             if c == r and not self_seen:
                 self_seen = True
                 continue
@@ -644,8 +665,8 @@ def aligned_pack(pack, group=32):
         if len(lanes) > 12:
             truncated, lanes = True, lanes[:12]
         d = len(lanes)
-        for j, ln in enumerate(lanes):
-            d |= ln << (4 + 5 * j)
+        for k_, ln in enumerate(lanes):
+            d |= ln << (4 + 5 * k_)
         desc[nr] = d
     out["agg_desc"], out["agg_ok"] = desc, not truncated
     return out

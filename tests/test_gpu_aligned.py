@@ -71,13 +71,14 @@ def pack_arrays(p):
     return {k: getattr(p, k).cpu().numpy() for k in ("rowptr", "col", "dinv", "gid", "sub_ptr", "core_rows", "is_core", "mask")}
 
 
+@pytest.mark.parametrize("policy", ["order", "degree"])
 @pytest.mark.parametrize("n,k,seed,max_size", [(40, 20, 0, None), (5000, 2300, 1, None), (3000, 400, 2, 13), (64, 2, 3, 32),
                                                (33, 33, 4, None)])
-def test_aligned_pack_matches_oracle_layout(fg, n, k, seed, max_size):
+def test_aligned_pack_matches_oracle_layout(fg, n, k, seed, max_size, policy):
     ei, part, k = small_subgraph_graph(n, k, seed, max_size=max_size)
     pack = fg.build_pack(torch.tensor(ei, device=dev()), torch.tensor(part), k, "none")
-    want = fo.aligned_pack(pack_arrays(pack), 32)
-    ap = pack.aligned(32)
+    want = fo.aligned_pack(pack_arrays(pack), 32, policy)
+    ap = pack.aligned(32, policy)
     if want is None:
         assert ap is None
         return
@@ -91,6 +92,12 @@ def test_aligned_pack_matches_oracle_layout(fg, n, k, seed, max_size):
     rp, col = want["rowptr"], want["col"]
     rows = np.repeat(np.arange(ap.n_rows), np.diff(rp))
     assert np.array_equal(rows // 32, col // 32)
+    # every source row appears exactly once; the aligned CSR is the source CSR relabelled
+    orig = want["orig_row"]
+    assert np.array_equal(np.sort(orig[orig >= 0]), np.arange(pack.n_rows))
+    if policy == "degree" and want["n_rows"] > 64:
+        n_order = fo.aligned_layout(pack_arrays(pack)["sub_ptr"], 32, "order")[1]
+        assert want["n_rows"] <= n_order  # gap filling never pads more than the in-order placement
 
 
 def test_unalignable_pack_returns_none(fg):
@@ -124,7 +131,7 @@ def test_transform_aggregate_matches_fp64(fg, n, k, K, N, seed):
         out = fg.ops.gcn_transform_aggregate(A_pl, W_pl, b.to(dev()), fg.ops.ACT_ELU, ap.agg_desc, ap.dinv, split_out=split)
         got = (out[0].float() + out[1].float()) if split else out
         h = torch.nn.functional.elu(A.double() @ W.double().T + b.double()).numpy()
-        a = fo.aligned_pack(pack_arrays(pack), 32)
+        a = fo.aligned_pack(pack_arrays(pack), 32, "degree")
         want = fo.aggregate_dense(a["rowptr"], a["col"], a["dinv"], h)
         got = got.cpu().numpy()
         real = a["orig_row"] >= 0

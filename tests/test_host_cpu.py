@@ -121,3 +121,14 @@ def test_oracle_aligned_layout_invariants():
     # known answer (sizes 3,7,20,3,7,24,6)
     s3, n3 = fo.aligned_layout([0, 3, 10, 30, 33, 40, 64, 70], 32)
     assert list(s3) == [0, 3, 10, 32, 35, 64, 88, 94] and n3 == 94
+    # degree policy: (max row degree desc, size desc, index asc) with gap filling from the end of that order.
+    # sizes 3,1,1,30 with chain graphs inside (row degree incl. self loop: 2,3,2 | 1 | 1 | 2,3,...,3,2)
+    sub_ptr = np.array([0, 3, 4, 5, 35])
+    deg = np.concatenate([[2, 3, 2], [1], [1], [2] + [3] * 28 + [2]])
+    rowptr = np.concatenate([[0], np.cumsum(deg)])
+    s4, n4 = fo.aligned_layout(sub_ptr, 32, "degree", rowptr)
+    # order: sub 3 (deg 2, size 30), sub 0 (deg 2, size 3), sub 1, sub 2 (deg 0).  sub 3 -> 0..29; sub 0 does not fit the
+    # 2 remaining rows -> the tail fills them: sub 2 at 30, sub 1 at 31; then sub 0 at 32
+    assert list(s4) == [32, 31, 30, 0, 35] and n4 == 35
+    s5, n5 = fo.aligned_layout(sub_ptr, 32, "order", rowptr)
+    assert list(s5) == [0, 3, 4, 32, 62] and n5 == 62
