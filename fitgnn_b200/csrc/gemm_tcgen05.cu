@@ -905,9 +905,10 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
     ea.bulk_rows = aligned ? 1 : 0;
   }
   if (agg_desc) {
-    // K <= 128: the MMAs are short and the epilogue (activation + aggregation + bf16 split) is the bottleneck ->
-    // 128-column tiles with 16 epilogue warps (4 per scheduler).  Larger K is tensor-bound: the 256-column tile.
-    const bool wide = getenv("FITGNN_AGG_WIDE") ? atoi(getenv("FITGNN_AGG_WIDE")) != 0 : K <= 128;
+    // Tuning switch: 128-column tiles with 16 epilogue warps (4 per scheduler).  The small-K aggregation epilogue is
+    // instruction-bound, yet the wide variant measured SLOWER (2.05 vs 1.91 ms on the products workload: twice as many
+    // tiles, each warp handling a single box per tile), so the 256-column / 8-warp tile stays the default.
+    const bool wide = getenv("FITGNN_AGG_WIDE") ? atoi(getenv("FITGNN_AGG_WIDE")) != 0 : false;
     if (wide)
       return tc::launch<128, false, true, tc::EPI_WARPS_WIDE>(ga, ea, a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y,
                                                               Y_lo, ldy, sms, st);
