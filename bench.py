@@ -273,7 +273,7 @@ def main_ours(args):
     if args.mode == "cluster":
         raise SystemExit("bench: cluster mode needs the C·X rows appended to X; use tests for that mode")
     n_chunks = 1 if world == 1 else args.chunks
-    shard = ShardedPack(pack, world, rank, args.hidden, F, n_chunks=n_chunks)
+    shard = ShardedPack(pack, world, rank, args.hidden, F, n_chunks=n_chunks, local_table=world > 1)
     precision = args.precision
     if precision == "auto":
         precision = os.environ.get("FITGNN_PRECISION", "bf16x3")
@@ -283,6 +283,9 @@ def main_ours(args):
     fwd = fwds[0]
     # the group-aligned schedule takes the feature table un-padded ([n, 100]); the classic one wants the K-padded pitch
     Xd = X if (fwd.apack is not None and F % 4 == 0) else fwd.pad_features(X)
+    X_full = Xd
+    if shard.table_ids is not None:  # N > 1: this rank's rows of the feature table only (its own nodes in mode none)
+        Xd = Xd[shard.table_ids].contiguous()
 
     Cp = (C + 3) // 4 * 4  # logits row pitch padded to 16 bytes (aligned stores in the head kernel); columns >= C unused
     gbuf = shard.gather_buffer(Cp, device) if world > 1 else None
@@ -418,7 +421,7 @@ def main_ours(args):
         gathered = res.view(-1, Cp)[shard.node_index(device)][:, :C]
         ref_rows = fg.PackedForward(pack, sd, head="log_softmax", rows="core", precision=precision,
                                     fuse_aggregate=False if args.no_fuse_aggregate else "auto",
-                                    align_policy=args.align_policy)(Xd)
+                                    align_policy=args.align_policy)(X_full)
         full = torch.empty(n, C, device=device)
         full[pack.core_gid.long()] = ref_rows[:, :C]
         err = (gathered - full).abs().max().reshape(1)
@@ -434,18 +437,13 @@ def main_ours(args):
     e2e = None
     o_dev = None
     if not args.no_e2e:
-        # K-padded rows (104 floats) so the H2D copy is one contiguous DMA.  N > 1: every rank copies only its 1/N
-        # slice of the feature table over its own PCIe link and the ranks all-gather the table over NVLink.
-        rows_per = (n + world - 1) // world
+        # one contiguous DMA per step.  N > 1: every rank copies only the feature rows its own subgraphs reference
+        # (ShardedPack(local_table=True)): nothing about X is exchanged between the ranks.
         Fp = Xd.shape[1]
-        X_host = torch.zeros(rows_per, Fp)
-        lo_row = rank * rows_per
-        X_host[: max(0, min(n, lo_row + rows_per) - lo_row)] = Xd[lo_row: lo_row + rows_per].cpu()
-        X_host = X_host.pin_memory()
+        X_host = Xd.cpu().pin_memory()  # N > 1: the rank's own rows of the feature table (shard.table_ids)
         n_loc = sum(f.n_out for f in fwds)
         NB = 2
-        X_slots = [torch.zeros(world, rows_per, Fp, device=device) for _ in range(NB)]
-        X_in = [xs.view(world * rows_per, Fp)[:n] for xs in X_slots]
+        X_in = [torch.zeros_like(Xd) for _ in range(NB)]
         o_dev = None
         if pg is not None:
             o_dev = pg.tensors
@@ -462,9 +460,7 @@ def main_ours(args):
                 b = i % NB
                 with torch.cuda.stream(s_in):
                     s_in.wait_event(ev_cmp[b])  # the compute that last read X_in[b] is done
-                    X_slots[b][rank].copy_(X_host, non_blocking=True)
-                    if world > 1:
-                        dist.all_gather_into_tensor(X_slots[b].view(world * rows_per, Fp), X_slots[b][rank])
+                    X_in[b].copy_(X_host, non_blocking=True)
                     ev_in[b].record(s_in)
                 with torch.cuda.stream(s_cmp):
                     s_cmp.wait_event(ev_in[b])
@@ -502,10 +498,13 @@ def main_ours(args):
         t2 = torch.tensor([e0.elapsed_time(e1) / args.steps], device=device, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        h2d = torch.tensor([X_host.numel() * 4], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(h2d)
         e2e = {"value": n / (float(t2.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(t2.item()),
-               "h2d_bytes_per_step": int(X_host.numel() * 4) * world, "d2h_bytes_per_step": int(n * Cp * 4),
-               "pipelining": "3 streams, double-buffered; every rank copies its 1/N slice of the feature table in "
-                             "(all-gathered over NVLink when N > 1) and its own slice of the logits out"}
+               "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": int(n * Cp * 4),
+               "pipelining": "3 streams, double-buffered; every rank copies in the feature rows its own subgraphs reference "
+                             "(the whole table at N = 1) over its own PCIe link and copies its own slice of the logits out"}
     if rank == 0:
         sampler.stop()
 

@@ -44,7 +44,12 @@ class ShardedPack:
     all-gather of chunk c can run (asynchronously, on NCCL's stream) behind the compute of chunk c+1.  Every rank
     derives every unit's node ids from the replicated full pack, so no metadata is exchanged."""
 
-    def __init__(self, pack: Pack, world: int, rank: int, hidden: int, in_features: int, n_chunks: int = 1):
+    def __init__(self, pack: Pack, world: int, rank: int, hidden: int, in_features: int, n_chunks: int = 1,
+                 local_table: bool = False):
+        """local_table: instead of replicating the whole de-duplicated feature table, every rank keeps only the rows
+        its own subgraphs reference — `table_ids` (ascending global feature-row ids; exactly the rank's own nodes in mode
+        'none') — and its packs' `gid` index into that table: X_rank = X[table_ids].  A rank's host->device traffic
+        and feature memory then shrink by ~1/world and nothing about X has to be exchanged between ranks."""
         rows, nnz = pack_subgraph_sizes(pack)
         self.world, self.rank, self.n_chunks = world, rank, n_chunks
         units = world * n_chunks
@@ -54,6 +59,13 @@ class ShardedPack:
             self.locals = [pack]
         else:
             self.locals = [select_subgraphs(pack, self.sub_ids[rank * n_chunks + c]) for c in range(n_chunks)]
+        self.table_ids = None
+        if local_table:
+            import dataclasses
+            ids = torch.unique(torch.cat([lp.gid.long() for lp in self.locals]))  # sorted ascending
+            self.table_ids = ids
+            self.locals = [dataclasses.replace(lp, gid=torch.searchsorted(ids, lp.gid.long()).to(torch.int32).contiguous(),
+                                               n_src=int(ids.numel())) for lp in self.locals]
         self.local = self.locals[0]
         # core node ids per unit, in that unit's pack order (select_subgraphs keeps ascending subgraph order)
         core_sub = torch.repeat_interleave(torch.arange(pack.n_sub, device=pack.device), rows)[pack.core_rows.long()]
@@ -65,7 +77,9 @@ class ShardedPack:
         self.n_nodes = pack.n_nodes
         if units > 1:
             for c in range(n_chunks):
-                assert torch.equal(self.locals[c].core_gid.long(), self.core_ids[rank * n_chunks + c])
+                lg = self.locals[c].core_gid.long()
+                lg = self.table_ids[lg] if self.table_ids is not None else lg
+                assert torch.equal(lg, self.core_ids[rank * n_chunks + c])
         costs = subgraph_costs(rows, nnz, hidden, in_features)
         self.loads = [float(sum(costs[self.sub_ids[r * n_chunks + c]].sum() for c in range(n_chunks)))
                       for r in range(world)]

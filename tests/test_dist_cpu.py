@@ -71,3 +71,24 @@ def test_all_gather_world2_gloo():
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+@pytest.mark.parametrize("mode", ["none", "extra"])
+def test_rank_local_feature_tables(mode):
+    """ShardedPack(local_table=True): every rank keeps only the feature rows its own subgraphs reference and its packs
+    index into that table; gathering X[table_ids] rank by rank reproduces exactly the rows the full pack would read."""
+    from fitgnn_b200.dist import ShardedPack
+    pack, d = cpu_pack(mode)
+    X = torch.arange(pack.n_src, dtype=torch.float32)[:, None] * torch.tensor([1.0, -2.0])
+    for world, chunks in ((2, 1), (3, 2)):
+        plain = [ShardedPack(pack, world, r, 512, 20, n_chunks=chunks) for r in range(world)]
+        local = [ShardedPack(pack, world, r, 512, 20, n_chunks=chunks, local_table=True) for r in range(world)]
+        for a, b in zip(plain, local):
+            assert torch.equal(b.table_ids, torch.unique(torch.cat([lp.gid.long() for lp in a.locals])))
+            Xr = X[b.table_ids]
+            for la, lb in zip(a.locals, b.locals):
+                assert lb.n_src == b.table_ids.numel() and int(lb.gid.max()) < lb.n_src
+                assert torch.equal(Xr[lb.gid.long()], X[la.gid.long()])  # same feature rows through the local table
+                assert torch.equal(la.col, lb.col) and torch.equal(la.rowptr, lb.rowptr)
+        if mode == "none":  # every node's features live on exactly one rank
+            assert sorted(torch.cat([s.table_ids for s in local]).tolist()) == list(range(pack.n_nodes))
