@@ -131,3 +131,27 @@ def test_fused_gcn_layer_matches_spmm_plus_gemm(fg, n, F, H, mode):
     # ineligible shapes are refused loudly at the ABI (callers fall back)
     with pytest.raises(fg._lib.FitgnnError):
         fg.ops.gcn_layer_fused(pack.rowptr, pack.col, pack.dinv, Xp[:1000], kp, Wp, b, out_rows=rows[:1000].contiguous())
+
+
+@pytest.mark.parametrize("M,K,N", [(4096, 512, 512), (5000, 512, 512), (4224, 192, 384), (100003, 512, 512), (8192, 1024, 256)])
+def test_cta_pair_gemm_bit_identical_to_single_cta(fg, M, K, N, monkeypatch):
+    """cta_group::2 kernel (two SMs share a 256-row MMA, each staging half of the B tile) against the single-CTA kernel
+    (same MMA order per output element -> bit-identical) and fp64."""
+    g = torch.Generator().manual_seed(M)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g) * 0.1
+    A_pl, W_pl, bd = fg.ops.split_bf16(A.to(DEV)), fg.ops.split_bf16(W.to(DEV)), b.to(DEV)
+    for split in (False, True):
+        monkeypatch.setenv("FITGNN_GEMM_PAIR", "0")
+        y1 = fg.ops.gemm_bias_act(A_pl, W_pl, bd, fg.ops.ACT_ELU, precision=fg.ops.GEMM_BF16X3, split_out=split)
+        monkeypatch.setenv("FITGNN_GEMM_PAIR", "1")
+        y2 = fg.ops.gemm_bias_act(A_pl, W_pl, bd, fg.ops.ACT_ELU, precision=fg.ops.GEMM_BF16X3, split_out=split)
+        if split:
+            assert torch.equal(y1[0], y2[0]) and torch.equal(y1[1], y2[1])
+            got = y2[0].float() + y2[1].float()
+        else:
+            assert torch.equal(y1, y2)
+            got = y2
+        want = torch.nn.functional.elu(A[:1500].double() @ W.double().T + b.double())
+        assert (got[:1500].cpu().double() - want).abs().max() <= 1e-4 * want.abs().max()
