@@ -58,7 +58,9 @@ SIGNATURES = {
     "fitgnn_pack_align_fill": (c_i32, [C.POINTER(PackStruct), c_void, c_i32, c_i64, C.POINTER(PackStruct), c_void, c_void,
                                        c_void, C.POINTER(c_i32), c_void, c_size, c_void]),
     "fitgnn_gcn_transform_aggregate": (c_i32, [c_void, c_void, c_i64, c_void, c_void, c_i64, c_void, c_i64, c_i32, c_i32,
-                                               c_i32, c_void, c_void, c_void, c_void, c_i64, c_void]),
+                                               c_i32, c_void, c_void, c_i32, c_void, c_void, c_i64, c_void]),
+    "fitgnn_gemm_rowscale_bias_act_split": (c_i32, [c_i32, c_void, c_void, c_i64, c_void, c_void, c_i64, c_void, c_void, c_i64,
+                                                    c_i32, c_i32, c_i32, c_i32, c_void, c_void, c_i64, c_void]),
     "fitgnn_gemm_head_rows": (c_i32, [c_void, c_void, c_i64, c_void, c_void, c_i64, c_void, c_i64, c_i32, c_i32, c_i32,
                                       c_i32, c_void, c_void, c_i64, c_void]),
     "fitgnn_gemm_head_rows_peers": (c_i32, [c_void, c_void, c_i64, c_void, c_void, c_i64, c_void, c_i64, c_i32, c_i32, c_i32,

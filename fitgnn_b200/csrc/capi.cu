@@ -21,7 +21,7 @@ int row_softmax(float* Y, int64_t ldy, int64_t M, int N, int head, cudaStream_t 
 int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi, const void* W_lo, int64_t ldw,
                 const float* bias, int64_t M, int K, int N, int act, int head, float* Y, void* Y_lo, int64_t ldy,
                 const uint64_t* agg_desc, const float* agg_dinv, const int32_t* row_map, float* const* peers, int n_peers,
-                cudaStream_t st);
+                const float* row_scale, int agg_defer_scale, cudaStream_t st);
 
 int gcn_layer_fused(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X, int64_t ldx, int width,
                     const int32_t* src_index, const int32_t* out_rows, int64_t M, const void* W_hi, const void* W_lo,
@@ -53,10 +53,12 @@ extern "C" int fitgnn_device_info(int* sm_count, int* cc) {
   return FITGNN_OK;
 }
 
-extern "C" int fitgnn_gemm_bias_act_split(int precision, const void* A, const void* A_lo, int64_t lda, const void* W,
-                                          const void* W_lo, int64_t ldw, const float* bias, int64_t M, int K, int N,
-                                          int act, int head, void* Yv, void* Y_lo, int64_t ldy, void* stream) {
+extern "C" int fitgnn_gemm_rowscale_bias_act_split(int precision, const void* A, const void* A_lo, int64_t lda,
+                                                   const void* W, const void* W_lo, int64_t ldw, const float* row_scale,
+                                                   const float* bias, int64_t M, int K, int N, int act, int head, void* Yv,
+                                                   void* Y_lo, int64_t ldy, void* stream) {
   float* Y = static_cast<float*>(Yv);
+  FG_REQUIRE(!row_scale || precision == FITGNN_GEMM_BF16X3, FITGNN_EUNSUP, "gemm: row_scale needs FITGNN_GEMM_BF16X3");
   FG_REQUIRE(A && W && Y && M >= 0 && K > 0 && N > 0, FITGNN_EINVAL, "gemm: bad arguments (M=%lld K=%d N=%d)",
              (long long)M, K, N);
   FG_REQUIRE(lda >= K && ldw >= K && ldy >= N, FITGNN_EINVAL, "gemm: leading dimension smaller than the extent");
@@ -72,23 +74,31 @@ extern "C" int fitgnn_gemm_bias_act_split(int precision, const void* A, const vo
   }
   if (precision == FITGNN_GEMM_BF16X3) {
     FG_REQUIRE(A_lo && W_lo, FITGNN_EINVAL, "gemm: BF16X3 needs the lo planes");
-    return gemm_bf16x3(A, A_lo, lda, W, W_lo, ldw, bias, M, K, N, act, head, Y, Y_lo, ldy, nullptr, nullptr, nullptr, nullptr, 0, st);
+    return gemm_bf16x3(A, A_lo, lda, W, W_lo, ldw, bias, M, K, N, act, head, Y, Y_lo, ldy, nullptr, nullptr, nullptr, nullptr, 0,
+                       row_scale, 0, st);
   }
   set_error("gemm: unknown precision %d", precision);
   return FITGNN_EINVAL;
 }
 
+extern "C" int fitgnn_gemm_bias_act_split(int precision, const void* A, const void* A_lo, int64_t lda, const void* W,
+                                          const void* W_lo, int64_t ldw, const float* bias, int64_t M, int K, int N,
+                                          int act, int head, void* Yv, void* Y_lo, int64_t ldy, void* stream) {
+  return fitgnn_gemm_rowscale_bias_act_split(precision, A, A_lo, lda, W, W_lo, ldw, nullptr, bias, M, K, N, act, head, Yv, Y_lo,
+                                             ldy, stream);
+}
+
 extern "C" int fitgnn_gcn_transform_aggregate(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi,
                                               const void* W_lo, int64_t ldw, const float* bias, int64_t M, int K, int N,
-                                              int act, const uint64_t* agg_desc, const float* dinv, void* Y, void* Y_lo,
-                                              int64_t ldy, void* stream) {
+                                              int act, const uint64_t* agg_desc, const float* dinv, int defer_row_scale,
+                                              void* Y, void* Y_lo, int64_t ldy, void* stream) {
   FG_REQUIRE(A_hi && A_lo && W_hi && W_lo && Y && agg_desc && dinv && M >= 0 && K > 0 && N > 0, FITGNN_EINVAL,
              "gcn_transform_aggregate: bad arguments (M=%lld K=%d N=%d)", (long long)M, K, N);
   FG_REQUIRE(lda >= K && ldw >= K && ldy >= N, FITGNN_EINVAL, "gcn_transform_aggregate: leading dimension too small");
   FG_REQUIRE(act == FITGNN_ACT_NONE || act == FITGNN_ACT_ELU, FITGNN_EINVAL, "gcn_transform_aggregate: unknown act %d", act);
   if (M == 0) return FITGNN_OK;
   return gemm_bf16x3(A_hi, A_lo, lda, W_hi, W_lo, ldw, bias, M, K, N, act, FITGNN_HEAD_IDENTITY, static_cast<float*>(Y),
-                     Y_lo, ldy, agg_desc, dinv, nullptr, nullptr, 0, as_stream(stream));
+                     Y_lo, ldy, agg_desc, dinv, nullptr, nullptr, 0, nullptr, defer_row_scale, as_stream(stream));
 }
 
 extern "C" int fitgnn_gemm_head_rows(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi, const void* W_lo,
@@ -102,7 +112,7 @@ extern "C" int fitgnn_gemm_head_rows(const void* A_hi, const void* A_lo, int64_t
              head);
   if (M == 0) return FITGNN_OK;
   return gemm_bf16x3(A_hi, A_lo, lda, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y, nullptr, ldy, nullptr, nullptr,
-                     row_map, nullptr, 0, as_stream(stream));
+                     row_map, nullptr, 0, nullptr, 0, as_stream(stream));
 }
 
 extern "C" int fitgnn_gemm_head_rows_peers(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi,
@@ -120,7 +130,7 @@ extern "C" int fitgnn_gemm_head_rows_peers(const void* A_hi, const void* A_lo, i
              "gemm_head_rows_peers: unknown head %d", head);
   if (M == 0) return FITGNN_OK;
   return gemm_bf16x3(A_hi, A_lo, lda, W_hi, W_lo, ldw, bias, M, K, N, act, head, nullptr, nullptr, ldy, nullptr, nullptr,
-                     row_map, host_peer_bases, n_peers, as_stream(stream));
+                     row_map, host_peer_bases, n_peers, nullptr, 0, as_stream(stream));
 }
 
 extern "C" int fitgnn_gemm_bias_act(int precision, const void* A, const void* A_lo, int64_t lda, const void* W,

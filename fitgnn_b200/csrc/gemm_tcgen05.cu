@@ -66,6 +66,11 @@ struct EpiArgs {
   // to peer memory run at NVLink speed (16-byte per-thread stores reach ~120 GB/s).  Set by the launcher when
   // N <= 64, ldy == pad4(N) and all bases are 16-byte aligned.
   int bulk_rows;
+  // row_scale: y = act(row_scale[m] * (A·W^T)[m,:] + bias) — a per-row factor folded into the bias add as one FFMA.
+  // agg_defer_scale: the AGG epilogue stores dinv[r]*h[r] + sum dinv[c]*h[c] WITHOUT the leading dinv[r]; the consumer
+  // (the next transform, through its row_scale) applies it — a row scaling commutes with the GEMM.
+  const float* row_scale;
+  int agg_defer_scale;
 };
 constexpr int EPI_WARP0 = 2;
 constexpr int ACC_STAGES = 2;
@@ -558,15 +563,19 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
     int64_t it = 0;
     // aggregation descriptor + dinv of this thread's row, fetched one tile ahead of its use
     unsigned long long desc_next = 0ull;
-    float dr_next = 0.f;
+    float dr_next = 0.f, rs_next = 1.f;
     auto load_agg = [&](int64_t t) {
       desc_next = 0ull;
       dr_next = 0.f;
-      if (AGG && t < tiles) {
+      rs_next = 1.f;
+      if ((AGG || ea.row_scale) && t < tiles) {
         const int64_t mm = tile_row0(t) + row_in_tile;
         if (mm < M) {
-          desc_next = __ldg(ea.agg_desc + mm);
-          dr_next = __ldg(ea.agg_dinv + mm);
+          if (AGG) {
+            desc_next = __ldg(ea.agg_desc + mm);
+            dr_next = __ldg(ea.agg_dinv + mm);
+          }
+          if (ea.row_scale) rs_next = __ldg(ea.row_scale + mm);
         }
       }
     };
@@ -578,6 +587,7 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
       const int n0 = (int)(t % n_tiles) * BLOCK_N;
       const unsigned long long desc = desc_next;
       const float dr = dr_next;
+      const float rs = rs_next;
       load_agg(t + t_step);
       const int agg_cnt = (int)(desc & 15ull);
       const int agg_max = AGG ? __reduce_max_sync(0xffffffffu, agg_cnt) : 0;
@@ -682,7 +692,19 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 16; ++j) { v[j] = lo16[j]; v[16 + j] = 0.f; }
         }
-        if (bias) {
+        if (ea.row_scale) {  // act(rs * acc + bias): the scale rides on the bias add
+          if (bias && n0 + c0 + 32 <= N && bias_vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
+              v[j] = fmaf(v[j], rs, b4.x); v[j + 1] = fmaf(v[j + 1], rs, b4.y);
+              v[j + 2] = fmaf(v[j + 2], rs, b4.z); v[j + 3] = fmaf(v[j + 3], rs, b4.w);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], rs, (bias && n0 + c0 + j < N) ? __ldg(bias + n0 + c0 + j) : 0.f);
+          }
+        } else if (bias) {
           if (n0 + c0 + 32 <= N && bias_vec) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -721,8 +743,10 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
                 if (on) v[h0 + j] += tv;
               }
             }
+            if (!ea.agg_defer_scale) {
 #pragma unroll
-            for (int j = 0; j < AGG_W; ++j) v[h0 + j] *= dr;
+              for (int j = 0; j < AGG_W; ++j) v[h0 + j] *= dr;
+            }
           }
         }
         if (use_fast_head) {
@@ -992,7 +1016,7 @@ static int launch(const GatherArgs& ga, const EpiArgs& ea, const CUtensorMap& a_
 int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi, const void* W_lo, int64_t ldw,
                 const float* bias, int64_t M, int K, int N, int act, int head, float* Y, void* Y_lo, int64_t ldy,
                 const uint64_t* agg_desc, const float* agg_dinv, const int32_t* row_map, float* const* peers, int n_peers,
-                cudaStream_t st) {
+                const float* row_scale, int agg_defer_scale, cudaStream_t st) {
   FG_REQUIRE(!Y_lo || head == FITGNN_HEAD_IDENTITY, FITGNN_EUNSUP, "gemm_bf16x3: split output cannot carry a head");
   FG_REQUIRE(n_peers >= 0 && n_peers <= 8 && (n_peers == 0 || (peers && row_map)), FITGNN_EINVAL,
              "gemm_bf16x3: peer stores need 1..8 peer bases and a row map");
@@ -1012,7 +1036,8 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
   FG_TRY(tc::make_map(&a_hi, A_hi, M, K, lda, tc::BLOCK_M));
   FG_TRY(tc::make_map(&a_lo, A_lo, M, K, lda, tc::BLOCK_M));
   const tc::GatherArgs ga{};
-  tc::EpiArgs ea{reinterpret_cast<const unsigned long long*>(agg_desc), agg_dinv, row_map, {}, n_peers, 0};
+  tc::EpiArgs ea{reinterpret_cast<const unsigned long long*>(agg_desc), agg_dinv, row_map, {}, n_peers, 0, row_scale,
+                 agg_defer_scale};
   for (int p = 0; p < n_peers; ++p) ea.peers[p] = peers[p];
   if (n_peers > 0) Y = peers[0];  // alignment checks / unused fallbacks refer to a real buffer
   if (row_map && N <= 64 && ldy == (N + 3) / 4 * 4 && getenv("FITGNN_HEAD_BULK") == nullptr) {
@@ -1070,7 +1095,7 @@ int gcn_layer_fused(const int32_t* rowptr, const int32_t* col, const float* dinv
   tc::GatherArgs ga{rowptr, col, dinv, X, src_index, out_rows, ldx, width / 4};
   CUtensorMap dummy;
   FG_TRY(tc::make_map(&dummy, W_hi, N, K, ldw, 16));  // placeholder for the unused A maps
-  const tc::EpiArgs ea{nullptr, nullptr, nullptr, {}, 0, 0};
+  const tc::EpiArgs ea{nullptr, nullptr, nullptr, {}, 0, 0, nullptr, 0};
   return tc::launch<256, true, false>(ga, ea, dummy, dummy, W_hi, W_lo, ldw, bias, M, K, N, act, FITGNN_HEAD_IDENTITY, Y,
                                       Y_lo, ldy, sms, st);
 }

@@ -82,6 +82,7 @@ class PackedForward:
         self._nnz_cache = {}
         # group-aligned pack + aggregation fused into the transform epilogues (see module docstring)
         self.apack = None
+        self._planes0 = None
         eligible = (self.precision == ops.GEMM_BF16X3 and self.L >= 2 and not self.transform_first and with_head
                     and self.out_rows is None and self.H > 128 and self.H % 8 == 0 and pack.n_rows > 0)
         if fuse_aggregate and eligible:
@@ -89,6 +90,14 @@ class PackedForward:
             if ap is not None and ap.agg_ok:
                 self.apack = ap
                 self.hubs_aligned = ops.find_hubs(ap.rowptr, None, ap.n_rows)
+                import os
+                tricks = os.environ.get("FITGNN_ENGINE_TRICKS", "1") != "0"
+                self.defer_scale = tricks
+                self.fold_bias = tricks and self.Fp > ops.pad4(self.F)
+                if self.fold_bias:  # layer-0 weights with the bias in the spare K column (see _forward_aligned)
+                    w0 = state_dict["conv.0.lin.weight"].detach().to(**f32)
+                    w0 = torch.nn.functional.pad(w0, (0, ops.pad4(self.F) - self.F))
+                    self.W0_fold = self._prep_weight(torch.cat([w0, self.b[0][:, None]], 1))
         if fuse_aggregate is True and self.apack is None:
             raise ValueError("fuse_aggregate=True but the pack / model is not eligible for the fused aggregation")
 
@@ -151,11 +160,12 @@ class PackedForward:
             w = torch.nn.functional.pad(w, (0, kp - w.shape[1]))
         return w.contiguous()
 
-    def _gemm(self, A, W, bias, act, head=ops.HEAD_IDENTITY, N=None, K=None, name="gemm", out=None, split_out=False):
+    def _gemm(self, A, W, bias, act, head=ops.HEAD_IDENTITY, N=None, K=None, name="gemm", out=None, split_out=False,
+              row_scale=None):
         self.launches += 1 + (1 if (head != ops.HEAD_IDENTITY and self.precision == ops.GEMM_FP32) else 0)
         M = (A[0] if isinstance(A, tuple) else A).shape[0]
         return self._timed(name, lambda: ops.gemm_bias_act(A, W, bias, act, head, precision=self.precision, N=N, K=K,
-                                                           out=out, split_out=split_out),
+                                                           out=out, split_out=split_out, row_scale=row_scale),
                            nbytes=4 * (M * K + K * N + M * N), flops=2 * M * K * N)
 
     def _spmm(self, X, width, src_index, bias, act, last, split, name="spmm", pack=None, out=None):
@@ -206,21 +216,35 @@ class PackedForward:
         """spmm0 -> [transform + next layer's aggregation]* -> last transform -> head with the padding rows dropped."""
         ap = self.apack
         M = ap.n_rows
-        # X may come un-padded ([n, F] with F % 4 == 0): the planes keep the 8-element pitch the TMA maps need, the
-        # transform runs with K = F and the TMA unit zero-fills the columns beyond it
-        K = X.shape[1]
-        planes = (torch.empty(M, self.Fp, dtype=torch.bfloat16, device=X.device),
-                  torch.empty(M, self.Fp, dtype=torch.bfloat16, device=X.device))
-        A = self._spmm(X, K, ap.gid, None, ops.ACT_NONE, False, split=True, name="spmm0", pack=ap, out=planes)
+        # X may come un-padded ([n, F]) or with the K-padded pitch: the SpMM reads F columns either way; the planes keep
+        # the 8-element pitch the TMA maps need and the TMA unit zero-fills whatever lies beyond K.
+        # Bias fold: when the pitch leaves a spare column (Fp > F) the planes carry a constant 1 there and the weight planes
+        # carry the bias, so the layer-0 epilogue has no bias add (K = F + 1).  The planes are allocated once (the SpMM never
+        # touches columns >= F), so a PackedForward must be driven from one stream at a time.
+        Wd = ops.pad4(self.F)  # columns the SpMM reads / writes (X has at least that many: see __call__)
+        fold = self.fold_bias
+        if self._planes0 is None or self._planes0[0].device != X.device:
+            hi = torch.zeros(M, self.Fp, dtype=torch.bfloat16, device=X.device)
+            lo = torch.zeros(M, self.Fp, dtype=torch.bfloat16, device=X.device)
+            if fold:
+                hi[:, Wd] = 1.0
+            self._planes0 = (hi, lo)
+        A = self._spmm(X, Wd, ap.gid, None, ops.ACT_NONE, False, split=True, name="spmm0", pack=ap, out=self._planes0)
+        K = Wd + 1 if fold else Wd
         for i in range(self.L - 1):
             Ai, Ki = A, K
+            Wi, bi = (self.W0_fold, None) if (i == 0 and fold) else (self.W[i], self.b[i])
+            # the leading dinv[r] of the aggregation moves into the next transform's epilogue (one FFMA with its bias) when
+            # that consumer is the plain last transform
+            defer = self.defer_scale and i == self.L - 2
             self.launches += 1
             A = self._timed(f"gemm{i}_agg", lambda: ops.gcn_transform_aggregate(
-                Ai, self.W[i], self.b[i], ops.ACT_ELU, ap.agg_desc, ap.dinv, K=Ki, N=self.H),
+                Ai, Wi, bi, ops.ACT_ELU, ap.agg_desc, ap.dinv, K=Ki, N=self.H, defer_row_scale=defer),
                 nbytes=4 * (M * Ki + Ki * self.H + M * self.H) + 12 * M, flops=2 * M * Ki * self.H)
             K = self.H
         i = self.L - 1
-        h = self._gemm(A, self.W[i], self.b[i], ops.ACT_ELU, N=self.H, K=K, name=f"gemm{i}", split_out=True)
+        h = self._gemm(A, self.W[i], self.b[i], ops.ACT_ELU, N=self.H, K=K, name=f"gemm{i}", split_out=True,
+                       row_scale=ap.dinv if self.defer_scale else None)
         view = None
         self.launches += 1
         nb = 4 * (M * self.H + self.H * self.C + self.n_out * self.C) + 4 * M

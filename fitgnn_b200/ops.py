@@ -102,9 +102,10 @@ def find_hubs(rowptr, out_rows, n_out, hub_deg=256, cap=None):
 
 # ----------------------------------------------------------------------------------------- dense
 def gemm_bias_act(A, W, bias=None, act=ACT_NONE, head=HEAD_IDENTITY, out=None, K=None, N=None, precision=GEMM_FP32,
-                  split_out=False):
-    """Y = head(act(A·W^T + bias)).  FP32: A [M,K] fp32, W [N,K] fp32.  BF16X3: A=(hi,lo), W=(hi,lo) bf16 planes.
-    split_out=True (BF16X3 only) returns the result as bf16 (hi, lo) planes for the next tensor-core GEMM."""
+                  split_out=False, row_scale=None):
+    """Y = head(act(row_scale[:, None] * (A·W^T) + bias)).  FP32: A [M,K] fp32, W [N,K] fp32.  BF16X3: A=(hi,lo),
+    W=(hi,lo) bf16 planes.  split_out=True (BF16X3 only) returns the result as bf16 (hi, lo) planes for the next
+    tensor-core GEMM.  row_scale ([M] fp32, BF16X3 only) is folded into the bias add."""
     if precision == GEMM_FP32:
         a_hi, a_lo, w_hi, w_lo = A, None, W, None
         assert A.dtype == torch.float32 and W.dtype == torch.float32
@@ -118,15 +119,15 @@ def gemm_bias_act(A, W, bias=None, act=ACT_NONE, head=HEAD_IDENTITY, out=None, K
         if out is None:
             out = (torch.empty(M, N, dtype=torch.bfloat16, device=a_hi.device),
                    torch.empty(M, N, dtype=torch.bfloat16, device=a_hi.device))
-        check(lib().fitgnn_gemm_bias_act_split(precision, ptr(a_hi), ptr(a_lo), a_hi.stride(0), ptr(w_hi), ptr(w_lo),
-                                               w_hi.stride(0), ptr(bias), M, K, N, act, head, ptr(out[0]), ptr(out[1]),
-                                               out[0].stride(0), stream_ptr()))
+        check(lib().fitgnn_gemm_rowscale_bias_act_split(precision, ptr(a_hi), ptr(a_lo), a_hi.stride(0), ptr(w_hi),
+                                                        ptr(w_lo), w_hi.stride(0), ptr(row_scale), ptr(bias), M, K, N, act,
+                                                        head, ptr(out[0]), ptr(out[1]), out[0].stride(0), stream_ptr()))
         return out
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=a_hi.device)
-    check(lib().fitgnn_gemm_bias_act(precision, ptr(a_hi), ptr(a_lo), a_hi.stride(0), ptr(w_hi), ptr(w_lo),
-                                     w_hi.stride(0), ptr(bias), M, K, N, act, head, ptr(out), out.stride(0),
-                                     stream_ptr()))
+    check(lib().fitgnn_gemm_rowscale_bias_act_split(precision, ptr(a_hi), ptr(a_lo), a_hi.stride(0), ptr(w_hi), ptr(w_lo),
+                                                    w_hi.stride(0), ptr(row_scale), ptr(bias), M, K, N, act, head, ptr(out),
+                                                    None, out.stride(0), stream_ptr()))
     return out
 
 
@@ -150,7 +151,7 @@ def gcn_layer_fused(rowptr, col, dinv, X, width, W, bias=None, act=ACT_NONE, src
     return out
 
 
-def gcn_transform_aggregate(A, W, bias, act, agg_desc, dinv, K=None, N=None, split_out=True):
+def gcn_transform_aggregate(A, W, bias, act, agg_desc, dinv, K=None, N=None, split_out=True, defer_row_scale=False):
     """G = Â_local·act(A·W^T + bias) on a group-aligned pack: the next layer's propagate fused into the tensor-core
     transform's epilogue.  A, W = bf16 (hi, lo) planes; agg_desc / dinv come from Pack.aligned()."""
     (a_hi, a_lo), (w_hi, w_lo) = A, W
@@ -167,8 +168,8 @@ def gcn_transform_aggregate(A, W, bias, act, agg_desc, dinv, K=None, N=None, spl
         out = torch.empty(M, N, dtype=torch.float32, device=a_hi.device)
         y, ylo, ldy = out, None, N
     check(lib().fitgnn_gcn_transform_aggregate(ptr(a_hi), ptr(a_lo), a_hi.stride(0), ptr(w_hi), ptr(w_lo), w_hi.stride(0),
-                                               ptr(bias), M, K, N, act, ptr(agg_desc), ptr(dinv), ptr(y), ptr(ylo), ldy,
-                                               stream_ptr()))
+                                               ptr(bias), M, K, N, act, ptr(agg_desc), ptr(dinv), int(defer_row_scale),
+                                               ptr(y), ptr(ylo), ldy, stream_ptr()))
     return out
 
 

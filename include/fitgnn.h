@@ -212,11 +212,20 @@ int fitgnn_pack_align_fill(const fitgnn_pack* in, const int32_t* new_sub_ptr, in
 /* G = Â_local · act(A·W^T + bias) on a group-aligned pack (FITGNN_GEMM_BF16X3 operands, N > 128):
  *   G[r,:] = dinv[r] * ( dinv[r]*h[r,:] + sum_{c in agg_desc(r)} dinv[c]*h[c,:] ),  h = act(A·W^T + bias)
  * = the next GCNConv's propagate (gcn_norm weights, self loop included) applied to this layer's activated output.
- * Y fp32 [M, ldy], or bf16 hi/lo planes when Y_lo != NULL.  Padding rows (dinv = 0) are written as zeros. */
+ * Y fp32 [M, ldy], or bf16 hi/lo planes when Y_lo != NULL.  Padding rows (dinv = 0) are written as zeros; the
+ * padding rows of A must hold finite values.  defer_row_scale != 0 stores the sum WITHOUT the leading dinv[r]: a row
+ * scaling commutes with the next transform, whose epilogue applies it for free (fitgnn_gemm_rowscale_bias_act_split). */
 int fitgnn_gcn_transform_aggregate(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi,
                                    const void* W_lo, int64_t ldw, const float* bias, int64_t M, int K,
-                                   int N, int act, const uint64_t* agg_desc, const float* dinv, void* Y,
-                                   void* Y_lo, int64_t ldy, void* stream);
+                                   int N, int act, const uint64_t* agg_desc, const float* dinv,
+                                   int defer_row_scale, void* Y, void* Y_lo, int64_t ldy, void* stream);
+/* fitgnn_gemm_bias_act_split with a per-row factor:  Y = head(act(row_scale[m] * (A·W^T)[m,:] + bias)).
+ * row_scale may be NULL (= 1); non-NULL needs FITGNN_GEMM_BF16X3. */
+int fitgnn_gemm_rowscale_bias_act_split(int precision, const void* A, const void* A_lo, int64_t lda,
+                                        const void* W, const void* W_lo, int64_t ldw,
+                                        const float* row_scale, const float* bias, int64_t M, int K,
+                                        int N, int act, int head, void* Y, void* Y_lo, int64_t ldy,
+                                        void* stream);
 /* fitgnn_gemm_bias_act (BF16X3) whose output row m is written to Y row row_map[m] and skipped when row_map[m] < 0:
  * drops the padding rows of an aligned pack / scatters lt1's output (network.py:34-35) straight into the caller's
  * row order.  When ldy is N rounded up to a multiple of 4, the pitch-padding columns [N, ldy) of written rows are
