@@ -50,6 +50,10 @@ def parse():
                    help="placement of the subgraphs in the group-aligned pack (see include/fitgnn.h)")
     p.add_argument("--no-fuse-aggregate", action="store_true",
                    help="classic schedule: stand-alone SpMM per layer instead of the aggregation fused into the transform")
+    p.add_argument("--features", default="auto", choices=["auto", "packed", "table"],
+                   help="layout of the input features: 'packed' = one row per pack row in pack order (what the reference's "
+                        "collated batch.x holds, built once with the pack); 'table' = node-ordered [N, F] table gathered "
+                        "through gid every step; auto = packed in mode none with one chunk per rank, else table")
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--collective", default="auto", choices=["auto", "p2p", "mc", "ce", "nccl"],
                    help="N>1 output exchange: p2p = head kernel stores into every rank's gather buffer over NVLink "
@@ -287,6 +291,14 @@ def main_ours(args):
     if shard.table_ids is not None:  # N > 1: this rank's rows of the feature table only (its own nodes in mode none)
         Xd = Xd[shard.table_ids].contiguous()
 
+    # pack-ordered features: the reference's models receive one copy of x per subgraph row, collated in subgraph order
+    # (utils.py:248, run.py:336); the layout is produced once, with the pack (mode none: N rows either way, the same bytes)
+    packed = args.features == "packed" or (args.features == "auto" and args.mode == "none" and len(fwds) == 1)
+    if packed and len(fwds) != 1:
+        raise SystemExit("bench: --features packed needs --chunks 1")
+    X_table = Xd
+    if packed:
+        Xd = fwd.pack_features(X_table)
     Cp = (C + 3) // 4 * 4  # logits row pitch padded to 16 bytes (aligned stores in the head kernel); columns >= C unused
     gbuf = shard.gather_buffer(Cp, device) if world > 1 else None
 
@@ -314,11 +326,11 @@ def main_ours(args):
         if collective == "ce":
             pg.acquire(b)
             for c, f in enumerate(fwds):
-                f(Xin, out=shard.slot(pg.tensors[b], c))
+                f(Xin, out=shard.slot(pg.tensors[b], c), packed=packed)
             pg.exchange_async(b)  # completes behind the next step; the timed region ends with pg.wait on both buffers
             return pg.tensors[b]
         for c, f in enumerate(fwds):
-            f(Xin, peer_ptrs=pg.slot_ptrs(b, c, multicast=(collective == "mc")))
+            f(Xin, peer_ptrs=pg.slot_ptrs(b, c, multicast=(collective == "mc")), packed=packed)
         pg.barrier()
         return pg.tensors[b]
 
@@ -334,7 +346,7 @@ def main_ours(args):
         head kernel, so it overlaps the compute of chunk c+1; the current stream then waits for all of them."""
         works = []
         for c, f in enumerate(fwds):
-            f(Xin, out=shard.slot(buf, c))  # the head kernel writes straight into this rank's slot
+            f(Xin, out=shard.slot(buf, c), packed=packed)  # the head kernel writes straight into this rank's slot
             works.append(shard.all_gather_(buf, c, async_op=True))
         for w in works:
             w.wait()
@@ -344,7 +356,7 @@ def main_ours(args):
         if pg is not None:
             step_no[0] += 1
             return run_p2p(Xd, step_no[0] % 2)
-        return run_chunks(Xd, gbuf) if world > 1 else fwd(Xd)
+        return run_chunks(Xd, gbuf) if world > 1 else fwd(Xd, packed=packed)
 
     def barrier():
         if world > 1:
@@ -430,6 +442,16 @@ def main_ours(args):
         del gathered, ref_rows, full, res
         barrier()
 
+    # ---- N = 1: the pack-ordered input gives the same logits, bit for bit, as the node-ordered table gathered through gid
+    packed_check = None
+    if world == 1 and packed:
+        a_ = fwd(Xd, packed=True).clone()
+        b_ = fwd(X_table)
+        t_tab, _ = _time_cuda(lambda: fwd(X_table), reps=3, warm=1)
+        packed_check = {"packed_vs_table_max_abs_err": float((a_ - b_).abs().max().item()),
+                        "forward_ms_table_features": t_tab}
+        del a_, b_
+
     # ---- end to end through the public API with HOST buffers: every step copies X from pinned host memory to the
     # device, runs the forward (+ all-gather) and copies this rank's logits back to pinned host memory.  Steps are
     # software-pipelined over three streams with double buffers (H2D of step i+1 and D2H of step i-1 overlap the
@@ -470,7 +492,7 @@ def main_ours(args):
                     elif world > 1:
                         run_chunks(X_in[b], o_dev[b])
                     else:
-                        fwd(X_in[b], out=o_dev[b])
+                        fwd(X_in[b], out=o_dev[b], packed=packed)
                     ev_cmp[b].record(s_cmp)
                 with torch.cuda.stream(s_out):
                     s_out.wait_event(ev_cmp[b])
@@ -557,7 +579,8 @@ def main_ours(args):
     line = {"metric": METRIC, "value": n / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32" if precision == "fp32" else "bf16x3(f32 accumulate)", "data": "synthetic",
-            "config": config_of(args, n, F, C, k), "roofline": roofline_of(dom), "roofline_spmm": spmm_roof,
+            "config": dict(config_of(args, n, F, C, k), features="pack-ordered rows" if packed else "node-ordered table + gid"),
+            "roofline": roofline_of(dom), "roofline_spmm": spmm_roof,
             "schedule": ("spmm0 -> [transform + next layer's aggregation in the epilogue] -> transform -> head (group-aligned "
                          f"pack, {fwd.apack.n_rows} rows incl. padding)") if fused else "spmm + transform per layer -> head",
             "kernels": kernels, "gpu_launches": gpu_launches, "clocks": sampler.summary(mark0, mark1),
@@ -567,6 +590,8 @@ def main_ours(args):
                           "gathered_vs_single_gpu_max_abs_err_all_ranks": verify, "rank_kernel_ms": rank_kernel_ms,
                           "all_gather_bytes": int(n * Cp * 4) if world > 1 else 0,
                           "exposed_ms": (ms - max(rank_kernel_ms)) if rank_kernel_ms else 0.0}}
+    if packed_check:
+        line["features_check"] = packed_check
     if projection:
         line["projection"] = projection
     if e2e:

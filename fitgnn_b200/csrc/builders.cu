@@ -417,7 +417,7 @@ extern "C" int fitgnn_csr_plan(const int64_t* edge_index, int64_t E, int64_t n, 
   if (E + n > 0) {
     csr_keys_kernel<<<nblk(E + n), BT, 0, st>>>(edge_index, E, n, keys, ctr);
     FG_LAUNCH_CHECK();
-    FG_TRY(sort_u64(keys, nullptr, E + n, 32 + bits_for((uint64_t)n), b.here(), b.left(), st));
+    FG_TRY(sort_u64_mask(keys, nullptr, E + n, field_mask((uint64_t)n, (uint64_t)n), b.here(), b.left(), st));
   }
   int32_t h[C_N];
   FG_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -593,7 +593,7 @@ extern "C" int fitgnn_pack_plan(const int64_t* edge_index, int64_t E, int64_t N,
     }
     self_keys_kernel<<<nblk(N), BT, 0, st>>>(w.keys + E, N);
     FG_LAUNCH_CHECK();
-    FG_TRY(sort_u64(w.keys, nullptr, E + N, 32 + bits_for((uint64_t)N), w.scratch, w.scratch_bytes, st));
+    FG_TRY(sort_u64_mask(w.keys, nullptr, E + N, field_mask((uint64_t)N, (uint64_t)N), w.scratch, w.scratch_bytes, st));
     FG_TRY(read_ctr(w.ctr, h, st));
     FG_REQUIRE(h[C_ERR] == 0, FITGNN_EINVAL, "pack_plan: edge_index holds node ids outside [0,%lld)", (long long)N);
     plan->n_rows = N; plan->nnz = E + N - h[C_DROP]; plan->n_sub = k; plan->n_core = N; plan->n_src = N;
@@ -604,7 +604,7 @@ extern "C" int fitgnn_pack_plan(const int64_t* edge_index, int64_t E, int64_t N,
     const int64_t M = N + E;
     extra_member_keys_kernel<<<nblk(M), BT, 0, st>>>(edge_index, E, N, k, part, w.mkeys, w.ctr);
     FG_LAUNCH_CHECK();
-    FG_TRY(sort_u64(w.mkeys, nullptr, M, 32 + bits_for((uint64_t)k), w.scratch, w.scratch_bytes, st));
+    FG_TRY(sort_u64_mask(w.mkeys, nullptr, M, field_mask((uint64_t)k, (uint64_t)N), w.scratch, w.scratch_bytes, st));
     FG_TRY(read_ctr(w.ctr, h, st));
     FG_REQUIRE(h[C_ERR] == 0, FITGNN_EINVAL, "pack_plan: edge_index holds node ids outside [0,%lld)", (long long)N);
     const int64_t n_valid = M - h[C_DROP];
@@ -621,7 +621,7 @@ extern "C" int fitgnn_pack_plan(const int64_t* edge_index, int64_t E, int64_t N,
     if (E > 0) {
       src_keys_kernel<<<nblk(E), BT, 0, st>>>(edge_index, E, N, w.out_keys, w.ctr);
       FG_LAUNCH_CHECK();
-      FG_TRY(sort_u64(w.out_keys, nullptr, E, 32 + bits_for((uint64_t)N), w.scratch, w.scratch_bytes, st));
+      FG_TRY(sort_u64_mask(w.out_keys, nullptr, E, field_mask((uint64_t)N, (uint64_t)N), w.scratch, w.scratch_bytes, st));
       FG_TRY(read_ctr(w.ctr, h, st));
       E2 = E - h[C_A];
     }
@@ -745,7 +745,7 @@ extern "C" int fitgnn_pack_fill(const fitgnn_plan* plan, const fitgnn_pack* out,
     FG_LAUNCH_CHECK();
     self_keys_kernel<<<nblk(n_rows), BT, 0, st>>>(keys + e_prime, n_rows);
     FG_LAUNCH_CHECK();
-    FG_TRY(sort_u64(keys, nullptr, nnz, 32 + bits_for((uint64_t)n_rows), b2.here(), b2.left(), st));
+    FG_TRY(sort_u64_mask(keys, nullptr, nnz, field_mask((uint64_t)n_rows, (uint64_t)n_rows), b2.here(), b2.left(), st));
     FG_TRY(finish_csr(keys, nnz, n_rows, rowptr, col, dinv, st));
     copy_i32_kernel<<<nblk(k + 1), BT, 0, st>>>(w.sub_ptr, sub_ptr, k + 1);
     extra_rows_kernel<<<nblk(n_rows), BT, 0, st>>>(w.rowkeys, n_rows, w.sub_ptr, part, w.members, w.member_ptr, gid,
@@ -777,7 +777,7 @@ extern "C" int fitgnn_pack_fill(const fitgnn_plan* plan, const fitgnn_pack* out,
   }
   self_keys_kernel<<<nblk(n_rows), BT, 0, st>>>(keys + n_intra + 2 * T + n_cc, n_rows);
   FG_LAUNCH_CHECK();
-  FG_TRY(sort_u64(keys, nullptr, nnz, 32 + bits_for((uint64_t)n_rows), b2.here(), b2.left(), st));
+  FG_TRY(sort_u64_mask(keys, nullptr, nnz, field_mask((uint64_t)n_rows, (uint64_t)n_rows), b2.here(), b2.left(), st));
   FG_TRY(finish_csr(keys, nnz, n_rows, rowptr, col, dinv, st));
   copy_i32_kernel<<<nblk(k + 1), BT, 0, st>>>(w.sub_ptr, sub_ptr, k + 1);
   cluster_rows_kernel<<<nblk(N + Pn), BT, 0, st>>>(N, Pn, cb, w.members, part, w.member_ptr, w.sub_ptr, w.pair_sc,

@@ -94,6 +94,16 @@ int scan_i32(const int32_t* in, int64_t n_in, int32_t* out, int64_t n_out, void*
 size_t sort_ws_bytes(int64_t n);
 int sort_u64(uint64_t* keys, uint32_t* vals, int64_t n, int key_bits, void* ws, size_t ws_bytes,
              cudaStream_t st);
+// same, on the bits set in `mask` only (bits outside the mask must be equal in all keys, or irrelevant to the order)
+int sort_u64_mask(uint64_t* keys, uint32_t* vals, int64_t n, uint64_t mask, void* ws, size_t ws_bytes,
+                  cudaStream_t st);
+// mask of a (hi << 32 | lo) key whose fields hold values in [0, hi_max] and [0, lo_max]
+static inline uint64_t field_mask(uint64_t hi_max, uint64_t lo_max) {
+  const int hb = bits_for(hi_max), lb = bits_for(lo_max);
+  const uint64_t lo = lb >= 32 ? 0xffffffffull : ((1ull << lb) - 1ull);
+  const uint64_t hi = hb >= 32 ? 0xffffffffull : ((1ull << hb) - 1ull);
+  return (hi << 32) | lo;
+}
 // ptr[r] = first index i with (keys[i] >> shift) >= r, for r in [0, n_rows]; keys sorted, n_keys valid
 int segment_ptr_from_sorted(const uint64_t* keys, int64_t n_keys, int shift, int64_t n_rows, int32_t* ptr,
                             cudaStream_t st);

@@ -105,7 +105,7 @@ __global__ void low32_kernel(const uint64_t* __restrict__ keys, int64_t n, int32
 // Ac = P_bin·A·P_bin^T minus diagonal: relabel edges to (part[src], part[dst]) keys, sort, run-length
 // ---------------------------------------------------------------------------------------------
 __global__ void adj_keys_kernel(const int64_t* __restrict__ edge_index, int64_t E, int64_t N,
-                                const int32_t* __restrict__ part, int64_t k, uint64_t* __restrict__ keys,
+                                const int32_t* __restrict__ part, int64_t k, int kb, uint64_t* __restrict__ keys,
                                 int32_t* __restrict__ n_drop) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
@@ -121,12 +121,12 @@ __global__ void adj_keys_kernel(const int64_t* __restrict__ edge_index, int64_t 
       a = b = 0;
     }
   }
-  if (a == b) {
-    keys[e] = (uint64_t)k << 32;  // sorts after every real key
-    atomicAdd(n_drop, 1);
-  } else {
-    keys[e] = ((uint64_t)a << 32) | (uint64_t)b;
-  }
+  // compact key (row << kb | col), kb = bits of k: 2·kb significant bits instead of 32 + kb -> fewer sort passes
+  const bool drop = a == b;
+  keys[e] = drop ? (uint64_t)k << kb /* sorts after every real key */ : ((uint64_t)a << kb) | (uint64_t)b;
+  // one atomic per warp for the dropped (intra-cluster / self-loop) edges
+  const unsigned m = __ballot_sync(__activemask(), drop);
+  if (drop && (m & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(n_drop, __popc(m));
 }
 
 __global__ void boundary_flags_kernel(const uint64_t* __restrict__ keys, int64_t n, int32_t* __restrict__ flags) {
@@ -135,15 +135,15 @@ __global__ void boundary_flags_kernel(const uint64_t* __restrict__ keys, int64_t
 }
 
 // pos = exclusive scan of flags; run starts write their (row, col) and the run length
-__global__ void adj_emit_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ pos, int64_t n,
+__global__ void adj_emit_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ pos, int64_t n, int kb,
                                 int64_t* __restrict__ out_row, int64_t* __restrict__ out_col,
                                 int32_t* __restrict__ run_start) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (i == 0 || keys[i] != keys[i - 1]) {
     const int32_t p = pos[i];
-    out_row[p] = (int64_t)(keys[i] >> 32);
-    out_col[p] = (int64_t)(keys[i] & 0xffffffffull);
+    out_row[p] = (int64_t)(keys[i] >> kb);
+    out_col[p] = (int64_t)(keys[i] & ((1ull << kb) - 1ull));
     run_start[p] = (int32_t)i;
   }
 }
@@ -201,7 +201,8 @@ extern "C" int fitgnn_group_by_part(const int32_t* part, int64_t N, int64_t k, i
   if (N > 0) {
     part_keys_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(part, N, k, keys, err);
     FG_LAUNCH_CHECK();
-    FG_TRY(sort_u64(keys, nullptr, N, 32 + bits_for((uint64_t)k), b.here(), b.left(), st));
+    // the id field already ascends with the index and the sort is stable: only the part field needs passes
+    FG_TRY(sort_u64_mask(keys, nullptr, N, field_mask((uint64_t)k, 0) & ~0xffffffffull, b.here(), b.left(), st));
     low32_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(keys, N, members);
     FG_LAUNCH_CHECK();
   }
@@ -252,10 +253,11 @@ extern "C" int fitgnn_project_adj_plan(const int64_t* edge_index, int64_t E, int
   FG_REQUIRE(b.ok, FITGNN_EWS, "project_adj_plan: workspace too small");
   FG_CUDA(cudaMemsetAsync(counter, 0, 4 * sizeof(int32_t), st));
   int64_t n_valid = 0, nnz = 0;
+  const int kb = bits_for((uint64_t)k);  // k < 2^31 -> 2·kb <= 62
   if (E > 0) {
-    adj_keys_kernel<<<(unsigned)ceil_div(E, 256), 256, 0, st>>>(edge_index, E, N, part, k, keys, counter);
+    adj_keys_kernel<<<(unsigned)ceil_div(E, 256), 256, 0, st>>>(edge_index, E, N, part, k, kb, keys, counter);
     FG_LAUNCH_CHECK();
-    FG_TRY(sort_u64(keys, nullptr, E, 32 + bits_for((uint64_t)k), b.here(), b.left(), st));
+    FG_TRY(sort_u64(keys, nullptr, E, 2 * kb, b.here(), b.left(), st));
     int32_t hc[2] = {0, 0};
     FG_CUDA(cudaMemcpyAsync(hc, counter, sizeof(hc), cudaMemcpyDeviceToHost, st));
     FG_CUDA(cudaStreamSynchronize(st));
@@ -271,7 +273,7 @@ extern "C" int fitgnn_project_adj_plan(const int64_t* edge_index, int64_t E, int
       nnz = total;
     }
   }
-  const int64_t h[8] = {E, n_valid, nnz, 0, 0, 0, 0, 0};
+  const int64_t h[8] = {E, n_valid, nnz, kb, 0, 0, 0, 0};
   FG_CUDA(cudaMemcpyAsync(hdr, h, sizeof(h), cudaMemcpyHostToDevice, st));
   FG_CUDA(cudaStreamSynchronize(st));
   *host_nnz = nnz;
@@ -289,6 +291,7 @@ extern "C" int fitgnn_project_adj_fill(void* ws, size_t ws_bytes, int64_t k, int
   FG_CUDA(cudaMemcpyAsync(h, hdr, sizeof(h), cudaMemcpyDeviceToHost, st));
   FG_CUDA(cudaStreamSynchronize(st));
   const int64_t E = h[0], n_valid = h[1], nnz = h[2];
+  const int kb = (int)h[3];
   const size_t e = (size_t)(E > 0 ? E : 1);
   uint64_t* keys = b.take<uint64_t>(e);
   int32_t* pos = b.take<int32_t>(e + 1);
@@ -296,7 +299,7 @@ extern "C" int fitgnn_project_adj_fill(void* ws, size_t ws_bytes, int64_t k, int
   FG_REQUIRE(b.ok, FITGNN_EWS, "project_adj_fill: workspace too small");
   if (nnz > 0) {
     FG_REQUIRE(out_row && out_col && out_cnt, FITGNN_EINVAL, "project_adj_fill: null output");
-    adj_emit_kernel<<<(unsigned)ceil_div(n_valid, 256), 256, 0, st>>>(keys, pos, n_valid, out_row, out_col, run_start);
+    adj_emit_kernel<<<(unsigned)ceil_div(n_valid, 256), 256, 0, st>>>(keys, pos, n_valid, kb, out_row, out_col, run_start);
     FG_LAUNCH_CHECK();
     adj_count_kernel<<<(unsigned)ceil_div(nnz, 256), 256, 0, st>>>(run_start, nnz, n_valid, out_cnt);
     FG_LAUNCH_CHECK();

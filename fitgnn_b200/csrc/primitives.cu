@@ -94,77 +94,166 @@ int scan_i32(const int32_t* in, int64_t n_in, int32_t* out, int64_t n_out, void*
 }
 
 // ------------------------------------------------------------------------------------------
-// LSD radix sort, 8-bit digits, stable.  Per pass: per-tile digit histogram -> exclusive scan
-// over [digit][tile] -> stable scatter (warp match_any ranks + cross-warp prefix in smem).
+// LSD radix sort, digits of <= 8 bits, stable.  Per pass: per-tile digit histogram -> exclusive scan over
+// [digit][tile] -> stable scatter.  The passes cover only the bits set in `mask` (contiguous runs of set bits, each
+// split into near-equal digits), so a (hi << 32 | lo) key with 22 + 21 significant bits takes 6 passes, not 7.
+//
+// Scatter: a warp owns 512 consecutive keys of the tile (16 register-resident keys per thread, all loads in flight
+// at once), ranks them with match_any against its private digit counters (warp-level syncs only), one block-level
+// prefix over (digit, warp) turns the ranks into tile-local sorted positions, the keys are exchanged through shared
+// memory and leave in runs of consecutive addresses per digit (coalesced stores; ~16 keys = 128 bytes per run).
 // ------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
-constexpr int RS_ROUNDS = 16;
-constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
 constexpr int RS_WARPS = RS_THREADS / 32;
 
+// Per-tile digit histogram.  No warp collectives and no shared atomics: ncu showed MATCH.ANY (and VOTE) bound on the ADU
+// pipe (~57 cycles per warp instruction and SM, pipe_adu 98 % busy) and ATOMS at 2 cycles per lane.  Every thread counts
+// its 16 keys into PRIVATE byte counters (four digits per 32-bit word, column `tid` of cnt[word][256]: bank = tid % 32,
+// conflict-free plain LDS/STS; a count is at most 16), then word w's column is summed with packed 16-bit adds by thread
+// w, walking the columns skewed by its own index so that the lanes of a warp stay on distinct banks.
 __global__ void __launch_bounds__(RS_THREADS)
-rs_hist_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift, int32_t* __restrict__ hist,
+rs_hist_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift, int nbits, int32_t* __restrict__ hist,
                int ntiles) {
-  __shared__ int32_t h[256];
-  h[threadIdx.x] = 0;
-  __syncthreads();
+  extern __shared__ uint32_t rs_cnt[];  // [nwords][RS_THREADS]
+  const int tid = threadIdx.x;
+  const uint32_t dmask = (1u << nbits) - 1u;
+  const int ndig = 1 << nbits, nwords = ndig >= 4 ? ndig >> 2 : 1;
+  for (int i = 0; i < nwords; ++i) rs_cnt[i * RS_THREADS + tid] = 0;  // own column only: no barrier needed yet
   const int64_t base = (int64_t)blockIdx.x * RS_TILE;
-#pragma unroll 4
-  for (int r = 0; r < RS_ROUNDS; ++r) {
-    int64_t idx = base + r * RS_THREADS + threadIdx.x;
-    if (idx < n) atomicAdd(&h[(int)((keys[idx] >> shift) & 255u)], 1);
+  uint64_t key[RS_ITEMS];
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const int64_t idx = base + r * RS_THREADS + tid;
+    key[r] = idx < n ? keys[idx] : 0ull;
+  }
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    if (base + r * RS_THREADS + tid < n) {
+      const uint32_t d = (uint32_t)(key[r] >> shift) & dmask;
+      rs_cnt[(d >> 2) * RS_THREADS + tid] += 1u << ((d & 3u) * 8u);
+    }
   }
   __syncthreads();
-  hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
+  if (tid < nwords) {
+    uint32_t even = 0, odd = 0;  // 16-bit fields: digits (4w, 4w+2) and (4w+1, 4w+3); 256 columns x 16 keys fit
+#pragma unroll 8
+    for (int i = 0; i < RS_THREADS; ++i) {
+      const uint32_t v = rs_cnt[tid * RS_THREADS + ((i + tid) & (RS_THREADS - 1))];
+      even += v & 0x00ff00ffu;
+      odd += (v >> 8) & 0x00ff00ffu;
+    }
+    const int d0 = tid * 4;
+    const int32_t c[4] = {(int32_t)(even & 0xffffu), (int32_t)(odd & 0xffffu), (int32_t)(even >> 16), (int32_t)(odd >> 16)};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (d0 + j < ndig) hist[(size_t)(d0 + j) * ntiles + blockIdx.x] = c[j];
+  }
+  // digits >= ndig never occur: their rows of the [256][ntiles] table must read as zero for the scan
+  for (int d = ndig + tid; d < 256; d += RS_THREADS) hist[(size_t)d * ntiles + blockIdx.x] = 0;
+}
+
+constexpr size_t rs_hist_smem(int nbits) { return (size_t)((1 << nbits) >= 4 ? (1 << nbits) >> 2 : 1) * RS_THREADS * 4; }
+
+constexpr size_t rs_scatter_smem(bool has_vals) {
+  return (size_t)RS_TILE * 8 + (size_t)(RS_WARPS * 256 + 256 + 256 + 32) * 4 + (has_vals ? (size_t)RS_TILE * 4 : 0);
 }
 
 template <bool HAS_VALS>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, HAS_VALS ? 2 : 3)
 rs_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                   uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift,
-                  const int32_t* __restrict__ offs, int ntiles) {
-  __shared__ int32_t base[256];
-  __shared__ int32_t wcount[RS_WARPS][256];
+                  int nbits, const int32_t* __restrict__ offs, int ntiles) {
+  const uint32_t dmask = (1u << nbits) - 1u;
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  uint64_t* skeys = reinterpret_cast<uint64_t*>(rs_smem);   // [RS_TILE] keys at their tile-local sorted position
+  int32_t* wcount = reinterpret_cast<int32_t*>(skeys + RS_TILE);  // [RS_WARPS][256]
+  int32_t* lstart = wcount + RS_WARPS * 256;                // [256] tile-local start of each digit
+  int32_t* gbase = lstart + 256;                            // [256] global start minus tile-local start
+  int32_t* wsum = gbase + 256;                              // [32]
+  uint32_t* svals = reinterpret_cast<uint32_t*>(wsum + 32); // [RS_TILE] (HAS_VALS)
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  base[tid] = offs[(size_t)tid * ntiles + blockIdx.x];
-#pragma unroll
-  for (int i = 0; i < RS_WARPS; ++i) wcount[i][tid] = 0;
-  __syncthreads();
   const int64_t tile_base = (int64_t)blockIdx.x * RS_TILE;
-  for (int r = 0; r < RS_ROUNDS; ++r) {
-    const int64_t idx = tile_base + r * RS_THREADS + tid;
-    if (tile_base + (int64_t)r * RS_THREADS >= n) break;  // uniform across the block
-    const bool valid = idx < n;
-    uint64_t key = 0;
-    uint32_t val = 0;
-    if (valid) {
-      key = keys_in[idx];
-      if (HAS_VALS) val = vals_in[idx];
-    }
-    const int d = valid ? (int)((key >> shift) & 255u) : 256 + lane;  // invalid lanes never match
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
-    const int rank = __popc(peers & ((1u << lane) - 1u));
-    if (valid && rank == 0) wcount[w][d] = __popc(peers);
-    __syncthreads();
-    // thread `tid` owns digit `tid`: exclusive prefix of the per-warp counts
-    int32_t run = 0;
+  const int count = (int)((n - tile_base) < (int64_t)RS_TILE ? (n - tile_base) : (int64_t)RS_TILE);
+  const int wbase = w * (RS_ITEMS * 32);
+  int32_t* mycount = wcount + w * 256;
+
+  uint64_t key[RS_ITEMS];
+  uint32_t val[RS_ITEMS];
+  int rank[RS_ITEMS];
 #pragma unroll
-    for (int i = 0; i < RS_WARPS; ++i) {
-      int32_t c = wcount[i][tid];
-      wcount[i][tid] = run;
-      run += c;
-    }
-    __syncthreads();
-    if (valid) {
-      const int32_t dst = base[d] + wcount[w][d] + rank;
-      keys_out[dst] = key;
-      if (HAS_VALS) vals_out[dst] = val;
-    }
-    __syncthreads();
-    base[tid] += run;
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const int p = wbase + r * 32 + lane;
+    key[r] = p < count ? keys_in[tile_base + p] : 0ull;
+    if (HAS_VALS) val[r] = p < count ? vals_in[tile_base + p] : 0u;
+  }
+  const int32_t my_goff = offs[(size_t)tid * ntiles + blockIdx.x];
 #pragma unroll
-    for (int i = 0; i < RS_WARPS; ++i) wcount[i][tid] = 0;
-    __syncthreads();
+  for (int i = 0; i < RS_WARPS; ++i) wcount[i * 256 + tid] = 0;
+  __syncthreads();
+
+  // rank inside the warp's 512 keys: keys of earlier rounds first, then lower lanes (= input order)
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const bool valid = wbase + r * 32 + lane < count;
+    const int d = valid ? (int)((uint32_t)(key[r] >> shift) & dmask) : 256 + lane;  // invalid lanes never match
+    const unsigned peers = __match_any_sync(0xffffffffu, d);  // ADU-bound (see rs_hist_kernel), ~0.86 ms per 123 M keys
+    const int below = __popc(peers & ((1u << lane) - 1u));
+    int prev = 0;
+    if (valid) prev = mycount[d];
+    __syncwarp();
+    if (valid && below == 0) mycount[d] = prev + __popc(peers);
+    __syncwarp();
+    rank[r] = prev + below;
+  }
+  __syncthreads();
+
+  // thread `tid` owns digit `tid`: exclusive prefix over the warps, then over the digits
+  int run = 0;
+#pragma unroll
+  for (int i = 0; i < RS_WARPS; ++i) {
+    const int c = wcount[i * 256 + tid];
+    wcount[i * 256 + tid] = run;
+    run += c;
+  }
+  int incl = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[w] = incl;
+  __syncthreads();
+  int woff = 0;
+#pragma unroll
+  for (int i = 0; i < RS_WARPS; ++i) woff += (i < w) ? wsum[i] : 0;
+  const int excl = woff + incl - run;
+  lstart[tid] = excl;
+  gbase[tid] = my_goff - excl;
+  __syncthreads();
+
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    if (wbase + r * 32 + lane < count) {
+      const int d = (int)((uint32_t)(key[r] >> shift) & dmask);
+      const int pos = lstart[d] + mycount[d] + rank[r];
+      skeys[pos] = key[r];
+      if (HAS_VALS) svals[pos] = val[r];
+    }
+  }
+  __syncthreads();
+
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; ++i) {
+    const int p = i * RS_THREADS + tid;
+    if (p < count) {
+      const uint64_t k = skeys[p];
+      const int d = (int)((uint32_t)(k >> shift) & dmask);
+      const int32_t dst = gbase[d] + p;
+      keys_out[dst] = k;
+      if (HAS_VALS) vals_out[dst] = svals[p];
+    }
   }
 }
 
@@ -175,11 +264,37 @@ size_t sort_ws_bytes(int64_t n) {
          scan_ws_bytes(tiles * 256) + 1024;
 }
 
-int sort_u64(uint64_t* keys, uint32_t* vals, int64_t n, int key_bits, void* ws, size_t ws_bytes,
-             cudaStream_t st) {
-  if (n <= 1) return FITGNN_OK;
-  FG_REQUIRE(key_bits >= 1 && key_bits <= 64, FITGNN_EINVAL, "sort: key_bits=%d", key_bits);
+// pass plan: every contiguous run of set bits in `mask` is split into ceil(len / 8) digits of near-equal width
+static int plan_passes(uint64_t mask, int* shifts, int* widths) {
+  int np = 0;
+  int b = 0;
+  while (b < 64) {
+    if (!((mask >> b) & 1ull)) { ++b; continue; }
+    int e = b;
+    while (e < 64 && ((mask >> e) & 1ull)) ++e;
+    const int len = e - b, parts = (len + 7) / 8;
+    int at = b;
+    for (int i = 0; i < parts; ++i) {
+      const int wd = len / parts + (i < len % parts ? 1 : 0);
+      shifts[np] = at; widths[np] = wd; ++np;
+      at += wd;
+    }
+    b = e;
+  }
+  return np;
+}
+
+int sort_u64_mask(uint64_t* keys, uint32_t* vals, int64_t n, uint64_t mask, void* ws, size_t ws_bytes,
+                  cudaStream_t st) {
+  if (n <= 1 || mask == 0) return FITGNN_OK;
   FG_REQUIRE(n < (1ll << 31) - RS_TILE, FITGNN_ERANGE, "sort: n=%lld exceeds int32 offsets", (long long)n);
+  FG_CUDA(cudaFuncSetAttribute(rs_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_hist_smem(8)));
+  if (vals)
+    FG_CUDA(cudaFuncSetAttribute(rs_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)rs_scatter_smem(true)));
+  else
+    FG_CUDA(cudaFuncSetAttribute(rs_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)rs_scatter_smem(false)));
   const int64_t tiles = ceil_div(n, RS_TILE);
   Bump b(ws, ws_bytes);
   uint64_t* kalt = b.take<uint64_t>((size_t)n);
@@ -190,18 +305,20 @@ int sort_u64(uint64_t* keys, uint32_t* vals, int64_t n, int key_bits, void* ws, 
   uint64_t* kout = kalt;
   uint32_t* vin = vals;
   uint32_t* vout = valt;
-  const int passes = (key_bits + 7) / 8;
+  int shifts[64], widths[64];
+  const int passes = plan_passes(mask, shifts, widths);
   for (int p = 0; p < passes; ++p) {
-    const int shift = p * 8;
-    rs_hist_kernel<<<(unsigned)tiles, RS_THREADS, 0, st>>>(kin, n, shift, hist, (int)tiles);
+    const int shift = shifts[p];
+    const int nbits = widths[p];
+    rs_hist_kernel<<<(unsigned)tiles, RS_THREADS, rs_hist_smem(nbits), st>>>(kin, n, shift, nbits, hist, (int)tiles);
     FG_LAUNCH_CHECK();
     FG_TRY(scan_i32(hist, tiles * 256, hist, tiles * 256, b.here(), b.left(), st));
     if (vals)
-      rs_scatter_kernel<true><<<(unsigned)tiles, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, hist,
-                                                                      (int)tiles);
+      rs_scatter_kernel<true><<<(unsigned)tiles, RS_THREADS, rs_scatter_smem(true), st>>>(
+          kin, vin, kout, vout, n, shift, nbits, hist, (int)tiles);
     else
-      rs_scatter_kernel<false><<<(unsigned)tiles, RS_THREADS, 0, st>>>(kin, nullptr, kout, nullptr, n, shift,
-                                                                       hist, (int)tiles);
+      rs_scatter_kernel<false><<<(unsigned)tiles, RS_THREADS, rs_scatter_smem(false), st>>>(
+          kin, nullptr, kout, nullptr, n, shift, nbits, hist, (int)tiles);
     FG_LAUNCH_CHECK();
     uint64_t* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
@@ -211,6 +328,12 @@ int sort_u64(uint64_t* keys, uint32_t* vals, int64_t n, int key_bits, void* ws, 
     if (vals) FG_CUDA(cudaMemcpyAsync(vals, vin, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
   }
   return FITGNN_OK;
+}
+
+int sort_u64(uint64_t* keys, uint32_t* vals, int64_t n, int key_bits, void* ws, size_t ws_bytes,
+             cudaStream_t st) {
+  FG_REQUIRE(key_bits >= 1 && key_bits <= 64, FITGNN_EINVAL, "sort: key_bits=%d", key_bits);
+  return sort_u64_mask(keys, vals, n, key_bits == 64 ? ~0ull : ((1ull << key_bits) - 1ull), ws, ws_bytes, st);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -317,6 +317,113 @@ spmm_hub_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// group-local aggregation on a GROUP-ALIGNED pack (align.cu): every CSR entry of a row lies inside the row's own
+// group of 32 rows.  One warp per group:
+//   1. stage the group's 32 source rows in shared memory ONCE (cp.async, 16-byte pieces: a contiguous 12.8 KB
+//      stream when the features come pack-ordered, 32 row gathers through gid otherwise) -> HBM sees each byte once
+//      (the generic pipelined kernel re-fetches a source row once per referencing row through L1/L2);
+//   2. LANE = ROW: each lane keeps the smem offsets and weights dinv[col] of its row's first SG_SLOTS entries in
+//      registers and walks the float4 columns; per column one LDS.128 + 4 FFMA per entry, all 32 lanes busy
+//      (warp-per-row used 25 of 32 lanes for 100-wide rows and spent ~150 instructions per row on index handling:
+//      ncu r1t, 377 M instructions, issue-bound at 20 % occupancy);
+//   3. a column's results go back IN PLACE (the 16 bytes of xs[row][q] become the row's bf16 hi/lo quad or fp32
+//      float4: column q is dead once every lane has read it), so no second tile is needed;
+//   4. copy-out row by row: coalesced 8/16-byte stores.
+// Same accumulation order as spmm_pipe_kernel (CSR order, fmaf chain, then dinv[r]) -> bit-identical results.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SG_SLOTS = 8;  // CSR entries per row cached in registers; longer rows read the rest from global memory
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(32)
+spmm_group_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ dinv,
+                  const float* __restrict__ X, int64_t ldx, int nq, const int32_t* __restrict__ src_index,
+                  int64_t n_rows, void* Y, void* Ylo, int64_t ldy, int64_t n_groups) {
+  extern __shared__ __align__(16) unsigned char sg_smem[];
+  float4* xs = reinterpret_cast<float4*>(sg_smem);  // [32][nq]
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x;
+  const bool contiguous = src_index == nullptr && ldx == 4 * (int64_t)nq;
+  for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+    const int64_t R0 = g * 32;
+    const int64_t r = R0 + lane;
+    const bool live = r < n_rows;
+    const int rows_here = (int)(n_rows - R0 < 32 ? n_rows - R0 : 32);
+    const int rp = __ldg(rowptr + (live ? r : n_rows));
+    const int deg = live ? __ldg(rowptr + r + 1) - rp : 0;
+    const float dr = live ? __ldg(dinv + r) : 0.f;
+    // 1. stage the source rows
+    if (contiguous) {
+      const float* Xg = X + R0 * ldx;
+      for (int t = lane; t < rows_here * nq; t += 32) cp_async16(xs + t, Xg + 4 * t);
+    } else {
+      const int64_t srow = live ? (src_index ? (int64_t)__ldg(src_index + r) : r) : 0;
+      for (int i = 0; i < rows_here; ++i) {
+        const int64_t s = __shfl_sync(FULL, srow, i);
+        if (lane < nq) cp_async16(xs + i * nq + lane, X + s * ldx + 4 * lane);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    // 2. this lane's row: smem offsets + weights of its first entries
+    int off[SG_SLOTS];
+    float w[SG_SLOTS];
+#pragma unroll
+    for (int s_ = 0; s_ < SG_SLOTS; ++s_) {
+      const int c = s_ < deg ? ((__ldg(col + rp + s_) - (int)R0) & 31) : lane;  // precondition: group-aligned pack
+      off[s_] = c * nq;
+      w[s_] = __shfl_sync(FULL, dr, c);
+    }
+    const int maxdeg = __reduce_max_sync(FULL, deg);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    for (int q = 0; q < nq; ++q) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int s_ = 0; s_ < SG_SLOTS; ++s_)
+        if (s_ < maxdeg && s_ < deg) fma4(acc, w[s_], xs[off[s_] + q]);
+      for (int s_ = SG_SLOTS; s_ < maxdeg; ++s_) {  // rows longer than the register cache (rare)
+        const int c = s_ < deg ? ((__ldg(col + rp + s_) - (int)R0) & 31) : lane;
+        const float wv = __shfl_sync(FULL, dr, c);
+        if (s_ < deg) fma4(acc, wv, xs[c * nq + q]);
+      }
+      const float4 o = make_float4(acc.x * dr, acc.y * dr, acc.z * dr, acc.w * dr);
+      __syncwarp();  // every lane has read column q
+      if (SPLIT) {
+        uint4 pk;  // (hi quad, lo quad)
+        split_bf16x2(o.x, o.y, pk.x, pk.z);
+        split_bf16x2(o.z, o.w, pk.y, pk.w);
+        *reinterpret_cast<uint4*>(xs + lane * nq + q) = pk;
+      } else {
+        xs[lane * nq + q] = o;
+      }
+    }
+    __syncwarp();
+    // 4. copy-out
+    if (lane < nq) {
+      for (int i = 0; i < rows_here; ++i) {
+        const float4 v = xs[i * nq + lane];
+        const int64_t yo = (R0 + i) * ldy + 4 * lane;
+        if (SPLIT) {
+          *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(Y) + yo) =
+              make_uint2(__float_as_uint(v.x), __float_as_uint(v.y));
+          *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(Ylo) + yo) =
+              make_uint2(__float_as_uint(v.z), __float_as_uint(v.w));
+        } else {
+          *reinterpret_cast<float4*>(static_cast<float*>(Y) + yo) = v;
+        }
+      }
+    }
+    __syncwarp();  // the next group's staging overwrites xs
+  }
+}
+
+static size_t spmm_group_smem(int nq) { return (size_t)32 * nq * 16; }
+
 // hub detection: hub_list[atomic slot] = i for output rows with degree >= hub_deg
 __global__ void spmm_find_hubs_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ out_rows,
                                       int64_t n_out, int hub_deg, int32_t* hub_list, int32_t* hub_count,
@@ -405,4 +512,34 @@ extern "C" int fitgnn_spmm_symnorm(const int32_t* rowptr, const int32_t* col, co
                                    void* stream) {
   return fitgnn_spmm_symnorm_hub(rowptr, col, dinv, X, ldx, width, src_index, bias, act, out_rows, n_out, Y, Y_lo,
                                  ldy, nullptr, 0, 0, stream);
+}
+
+extern "C" int fitgnn_spmm_symnorm_grouped(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X,
+                                           int64_t ldx, int width, const int32_t* src_index, int64_t n_rows, int group,
+                                           void* Y, void* Y_lo, int64_t ldy, void* stream) {
+  FG_REQUIRE(rowptr && col && dinv && X && Y, FITGNN_EINVAL, "spmm_grouped: null pointer");
+  FG_REQUIRE(n_rows >= 0 && width > 0, FITGNN_EINVAL, "spmm_grouped: n_rows=%lld width=%d", (long long)n_rows, width);
+  FG_REQUIRE(group == 32, FITGNN_EUNSUP, "spmm_grouped: group must be 32 (got %d)", group);
+  FG_REQUIRE(width % 4 == 0 && width <= 128 && ldx % 4 == 0 && ldy % 4 == 0, FITGNN_EUNSUP,
+             "spmm_grouped: width (%d) must be a multiple of 4 and <= 128, ldx (%lld) / ldy (%lld) multiples of 4", width,
+             (long long)ldx, (long long)ldy);
+  FG_REQUIRE(((uintptr_t)X % 16) == 0 && ((uintptr_t)Y % 8) == 0 && ((uintptr_t)Y_lo % 8) == 0, FITGNN_EUNSUP,
+             "spmm_grouped: X must be 16-byte, Y 8-byte aligned");
+  if (n_rows == 0) return FITGNN_OK;
+  cudaStream_t st = as_stream(stream);
+  const int nq = width / 4;
+  const int64_t n_groups = ceil_div(n_rows, 32);
+  const size_t smem = spmm_group_smem(nq);
+  const unsigned blocks = (unsigned)(n_groups < 148ll * 64 ? n_groups : 148ll * 64);
+  if (Y_lo) {
+    FG_CUDA(cudaFuncSetAttribute(spmm_group_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    spmm_group_kernel<true><<<blocks, 32, smem, st>>>(rowptr, col, dinv, X, ldx, nq, src_index, n_rows, Y, Y_lo, ldy,
+                                                      n_groups);
+  } else {
+    FG_CUDA(cudaFuncSetAttribute(spmm_group_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    spmm_group_kernel<false><<<blocks, 32, smem, st>>>(rowptr, col, dinv, X, ldx, nq, src_index, n_rows, Y, Y_lo, ldy,
+                                                       n_groups);
+  }
+  FG_LAUNCH_CHECK();
+  return FITGNN_OK;
 }

@@ -92,6 +92,7 @@ class PackedForward:
                 self.hubs_aligned = ops.find_hubs(ap.rowptr, None, ap.n_rows)
                 import os
                 tricks = os.environ.get("FITGNN_ENGINE_TRICKS", "1") != "0"
+                self.grouped_spmm = os.environ.get("FITGNN_SPMM_GROUPED", "1") != "0"
                 self.defer_scale = tricks
                 self.fold_bias = tricks and self.Fp > ops.pad4(self.F)
                 if self.fold_bias:  # layer-0 weights with the bias in the spare K column (see _forward_aligned)
@@ -146,6 +147,13 @@ class PackedForward:
         if last and self.out_rows is not None:
             b += 4 * r_out
         return b
+
+    def _spmm_bytes_aligned(self, width, src_index, n_src_rows):
+        """Algorithmic bytes of the layer-0 aggregation on the group-aligned pack (same formula as _spmm_bytes)."""
+        ap = self.apack
+        b = 4 * (ap.n_rows + 1) + 4 * ap.nnz + 4 * ap.n_rows + 4 * (n_src_rows if src_index is not None else ap.n_rows) * width \
+            + 4 * ap.n_rows * width
+        return b + (4 * ap.n_rows if src_index is not None else 0)
 
     # -- helpers -------------------------------------------------------------------------------
     def _kpad(self, k):
@@ -212,7 +220,18 @@ class PackedForward:
         Xp[:, : X.shape[1]].copy_(X)
         return Xp
 
-    def _forward_aligned(self, X, out, peer_ptrs=None):
+    def pack_features(self, X):
+        """Node-ordered feature table [n_src, F] -> one row per pack row, in the row order of the pack this forward
+        runs on (the group-aligned pack when the fused schedule is active).  This is the layout the reference feeds its
+        models: every subgraph carries its own copy of x (utils.py:248, :266) and the loader collates them in subgraph
+        order (run.py:336).  Done once per graph, like the pack itself; `__call__(Xp, packed=True)` then streams the
+        rows instead of gathering them through gid.  Padding rows (never read) get row 0."""
+        ap = self.apack if self.apack is not None else self.pack
+        if X.shape[1] % 4 != 0:
+            X = torch.nn.functional.pad(X, (0, ops.pad4(X.shape[1]) - X.shape[1]))
+        return X[ap.gid.long().clamp_(min=0)].contiguous()
+
+    def _forward_aligned(self, X, out, peer_ptrs=None, packed=False):
         """spmm0 -> [transform + next layer's aggregation]* -> last transform -> head with the padding rows dropped."""
         ap = self.apack
         M = ap.n_rows
@@ -229,7 +248,15 @@ class PackedForward:
             if fold:
                 hi[:, Wd] = 1.0
             self._planes0 = (hi, lo)
-        A = self._spmm(X, Wd, ap.gid, None, ops.ACT_NONE, False, split=True, name="spmm0", pack=ap, out=self._planes0)
+        src = None if packed else ap.gid
+        if self.grouped_spmm and Wd <= 128:
+            # group-local aggregation: the group's 32 source rows are staged in shared memory once (spmm.cu)
+            self.launches += 1
+            A = self._timed("spmm0", lambda: ops.spmm_symnorm_grouped(ap.rowptr, ap.col, ap.dinv, X, Wd, src, split=True,
+                                                                      out=self._planes0),
+                            nbytes=self._spmm_bytes_aligned(Wd, src, X.shape[0]))
+        else:
+            A = self._spmm(X, Wd, src, None, ops.ACT_NONE, False, split=True, name="spmm0", pack=ap, out=self._planes0)
         K = Wd + 1 if fold else Wd
         for i in range(self.L - 1):
             Ai, Ki = A, K
@@ -262,21 +289,25 @@ class PackedForward:
 
     # -- forward -------------------------------------------------------------------------------
     @torch.no_grad()
-    def __call__(self, X, out=None, peer_ptrs=None):
-        """X: [n_src, F] fp32 CUDA — every node once (+ one row per cluster for cluster mode, i.e. C·X).
+    def __call__(self, X, out=None, peer_ptrs=None, packed=False):
+        """X: [n_src, F] fp32 CUDA — every node once (+ one row per cluster for cluster mode, i.e. C·X); with
+        packed=True: the output of pack_features (one row per pack row, no gid indirection).
         Returns [n_out, C] (or the last hidden [n_out, H] when with_head=False), rows in pack order.
         `out` ([n_out, C] fp32, e.g. this rank's slot of an all-gather buffer) receives the head output in place.
         `peer_ptrs` (dist.PeerGather.slot_ptrs; fused-aggregation schedule only): the head stores its rows into that slot
         of every rank's gather buffer instead (pitch pad4(C)) and nothing is returned."""
         assert peer_ptrs is None or self.apack is not None, "peer stores need the group-aligned schedule" 
         p = self.pack
-        assert X.is_cuda and X.dtype == torch.float32 and X.shape[0] == p.n_src and X.shape[1] in (self.F, self.Fp)
+        assert X.is_cuda and X.dtype == torch.float32
+        n_in = (self.apack if self.apack is not None else p).n_rows if packed else p.n_src
+        assert X.shape[0] == n_in and X.shape[1] in (self.F, ops.pad4(self.F), self.Fp), tuple(X.shape)
         bf = self.precision == ops.GEMM_BF16X3
         if self.apack is not None:
             if not (X.is_contiguous() and X.shape[1] % 4 == 0):
                 X = self.pad_features(X)
-            return self._forward_aligned(X, out, peer_ptrs)
+            return self._forward_aligned(X, out, peer_ptrs, packed)
         X = self.pad_features(X)
+        gid0 = None if packed else p.gid
         h = None
         for i in range(self.L):
             last = i == self.L - 1
@@ -285,15 +316,15 @@ class PackedForward:
                 if bf:
                     self.launches += 1
                 Z = self._gemm(A, self.W[0], None, ops.ACT_NONE, N=self.H, K=self.Fp, name="gemm0_unique_rows")
-                h = self._spmm(Z, self.H, p.gid, self.b[0], ops.ACT_ELU, last, split=False, name="spmm0")
-            elif i == 0 and bf and self.fused_layer0 is not False and self.Fp <= 128 and self.H > 128:
+                h = self._spmm(Z, self.H, gid0, self.b[0], ops.ACT_ELU, last, split=False, name="spmm0")
+            elif i == 0 and bf and self.fused_layer0 is not False and self.Fp <= 128 and self.H > 128 and not packed:
                 h = self._fused_layer0(X, last)
                 if h is None:  # not eligible for this shape: SpMM + GEMM below
-                    A = self._spmm(X, self.Fp, p.gid, None, ops.ACT_NONE, last, split=bf, name="spmm0")
+                    A = self._spmm(X, self.Fp, gid0, None, ops.ACT_NONE, last, split=bf, name="spmm0")
                     h = self._gemm(A, self.W[0], self.b[0], ops.ACT_ELU, N=self.H, K=self.Fp, name="gemm0",
                                    split_out=bf and last and self.with_head and self.H % 8 == 0)
             else:
-                src, width, idx = (X, self.Fp, p.gid) if i == 0 else (h, self.H, None)
+                src, width, idx = (X, self.Fp, gid0) if i == 0 else (h, self.H, None)
                 A = self._spmm(src, width, idx, None, ops.ACT_NONE, last, split=bf, name=f"spmm{i}")
                 # the last conv layer feeds only the head GEMM: emit its bf16 hi/lo planes straight from the epilogue
                 to_head = bf and last and self.with_head and self.H % 8 == 0

@@ -86,6 +86,26 @@ def spmm_symnorm(rowptr, col, dinv, X, width=None, src_index=None, bias=None, ac
     return out
 
 
+def spmm_symnorm_grouped(rowptr, col, dinv, X, width=None, src_index=None, out=None, split=False, group=32):
+    """Y = Â·X[src_index] on a group-aligned pack (Pack.aligned): fitgnn_spmm_symnorm_grouped, bit-identical to
+    spmm_symnorm without bias / activation / row selection.  Raises FitgnnError(EUNSUP) for width > 128."""
+    assert X.dtype == torch.float32 and X.dim() == 2
+    width = X.shape[1] if width is None else width
+    n = rowptr.numel() - 1
+    if split:
+        if out is None:
+            out = (torch.empty(n, width, dtype=torch.bfloat16, device=X.device),
+                   torch.empty(n, width, dtype=torch.bfloat16, device=X.device))
+        y, ylo, ldy = out[0], out[1], out[0].stride(0)
+    else:
+        if out is None:
+            out = torch.empty(n, width, dtype=torch.float32, device=X.device)
+        y, ylo, ldy = out, None, out.stride(0)
+    check(lib().fitgnn_spmm_symnorm_grouped(ptr(rowptr), ptr(col), ptr(dinv), ptr(X), X.stride(0), width, ptr(src_index),
+                                            n, group, ptr(y), ptr(ylo), ldy, stream_ptr()))
+    return out
+
+
 def find_hubs(rowptr, out_rows, n_out, hub_deg=256, cap=None):
     """Output rows with >= hub_deg entries -> (hub_list, n_hub, hub_deg).  Synchronises once (build time)."""
     cap = int(cap if cap is not None else max(1024, n_out // 64))

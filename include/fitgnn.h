@@ -136,6 +136,14 @@ int fitgnn_spmm_symnorm(const int32_t* rowptr, const int32_t* col, const float* 
                         const float* X, int64_t ldx, int width, const int32_t* src_index,
                         const float* bias, int act, const int32_t* out_rows, int64_t n_out,
                         void* Y, void* Y_lo, int64_t ldy, void* stream);
+/* The same aggregation (no bias / activation, every row an output row) for a GROUP-ALIGNED pack
+ * (fitgnn_pack_align_*): every CSR entry of a row lies in the row's own group of `group` = 32 rows, so one warp stages
+ * the group's source rows in shared memory once and HBM sees every byte once.  width <= 128.  Results are bit-identical
+ * to fitgnn_spmm_symnorm.  FITGNN_EUNSUP for other shapes (callers fall back to fitgnn_spmm_symnorm); entries that
+ * point outside their group are a precondition violation (they are wrapped into the group, never out of bounds). */
+int fitgnn_spmm_symnorm_grouped(const int32_t* rowptr, const int32_t* col, const float* dinv,
+                                const float* X, int64_t ldx, int width, const int32_t* src_index,
+                                int64_t n_rows, int group, void* Y, void* Y_lo, int64_t ldy, void* stream);
 /* Same with the high-degree rows split across a CTA: hub_list (from fitgnn_spmm_hubs) holds the output
  * indices i whose row has >= hub_deg entries; the warp-per-row pass skips them. */
 int fitgnn_spmm_hubs(const int32_t* rowptr, const int32_t* out_rows, int64_t n_out, int hub_deg,

@@ -191,3 +191,68 @@ def test_forward_fused_aggregation_matches_classic_and_oracle(fg, n, k, F, H, C,
     buf = torch.zeros(pack.n_rows, (C + 3) // 4 * 4, device=dev())
     fused(X, out=buf)
     assert torch.equal(buf[:, :C], a)
+
+
+@pytest.mark.parametrize("precision,fuse", [("bf16x3", True), ("bf16x3", False), ("fp32", False)])
+@pytest.mark.parametrize("mode,F", [("none", 100), ("none", 30), ("extra", 50)])
+def test_pack_ordered_features_equal_table_features(fg, mode, F, precision, fuse):
+    """PackedForward.pack_features: one row per pack row (the reference's collated batch.x, utils.py:248 + run.py:336)
+    must give bit-identical logits to the node-ordered table gathered through gid."""
+    if fuse and mode != "none":
+        pytest.skip("the fused aggregation needs every row to be an output row")
+    n, k = 2500, 1100
+    ei, part, k = small_subgraph_graph(n, k, 21, max_size=12)
+    pack = fg.build_pack(torch.tensor(ei, device=dev()), torch.tensor(part), k, mode)
+    X = fg.synth.features(n, F, seed=3).to(dev())
+    sd = fo.init_state_dict(F, 256, 6, num_layers=2, seed=4)
+    fwd = fg.PackedForward(pack, sd, precision=precision, fuse_aggregate=fuse)
+    assert (fwd.apack is not None) == fuse
+    Xp = fwd.pack_features(X)
+    rows = (fwd.apack if fuse else pack).n_rows
+    assert Xp.shape[0] == rows and Xp.shape[1] % 4 == 0 and Xp.is_contiguous()
+    a = fwd(Xp, packed=True).clone()
+    b = fwd(X)
+    assert torch.equal(a, b)
+    with pytest.raises(AssertionError):
+        fwd(X[:-1], packed=False)
+
+
+@pytest.mark.parametrize("split", [True, False])
+@pytest.mark.parametrize("packed", [True, False])
+@pytest.mark.parametrize("n,k,seed,max_size,width", [(40, 20, 0, None, 4), (5000, 2300, 1, None, 100), (3000, 400, 2, 13, 128),
+                                                     (64, 2, 3, 32, 36), (33, 33, 4, None, 100), (20000, 9000, 5, 12, 100)])
+def test_grouped_spmm_is_bit_identical_to_generic_spmm(fg, n, k, seed, max_size, width, packed, split):
+    """fitgnn_spmm_symnorm_grouped (one warp per 32-row group, source rows staged in shared memory) against
+    fitgnn_spmm_symnorm on the same group-aligned pack: same accumulation order -> identical bits; both feature layouts
+    (pack-ordered rows / node table through gid), fp32 and bf16 hi/lo outputs, padding rows, a ragged last group."""
+    ei, part, k = small_subgraph_graph(n, k, seed, max_size=max_size)
+    pack = fg.build_pack(torch.tensor(ei, device=dev()), torch.tensor(part), k, "none")
+    ap = pack.aligned(32, "degree")
+    assert ap is not None
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    X = torch.randn(n, width, generator=g, device=dev())
+    src = None if packed else ap.gid
+    Xin = X[ap.gid.long()].contiguous() if packed else X
+    want = fg.ops.spmm_symnorm(ap.rowptr, ap.col, ap.dinv, Xin, width, src, split=split)
+    got = fg.ops.spmm_symnorm_grouped(ap.rowptr, ap.col, ap.dinv, Xin, width, src, split=split)
+    if split:
+        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+    else:
+        assert torch.equal(got, want)
+        # and against the fp64 dense restatement of D^-1/2 (A+I) D^-1/2 on the aligned CSR
+        rp, col, dinv = ap.rowptr.cpu().numpy(), ap.col.cpu().numpy(), ap.dinv.cpu().numpy().astype(np.float64)
+        Xn = Xin.cpu().numpy().astype(np.float64)
+        if not packed:
+            Xn = Xn[ap.gid.cpu().numpy()]
+        ref = np.zeros((ap.n_rows, width))
+        rows = np.repeat(np.arange(ap.n_rows), np.diff(rp))
+        np.add.at(ref, rows, (dinv[rows] * dinv[col])[:, None] * Xn[col])
+        assert np.abs(got.cpu().numpy() - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+
+
+def test_grouped_spmm_rejects_wide_rows(fg):
+    ei, part, k = small_subgraph_graph(200, 90, 0, max_size=10)
+    ap = fg.build_pack(torch.tensor(ei, device=dev()), torch.tensor(part), k, "none").aligned(32, "order")
+    X = torch.zeros(ap.n_rows, 132, device=dev())
+    with pytest.raises(Exception, match="EUNSUP|width"):
+        fg.ops.spmm_symnorm_grouped(ap.rowptr, ap.col, ap.dinv, X, 132, None)
