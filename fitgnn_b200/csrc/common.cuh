@@ -91,6 +91,10 @@ size_t scan_ws_bytes(int64_t n);
 // out[i] = sum_{j<i} in[j] for i < n_out, with in[j] = 0 for j >= n_in (so n_out = n_in+1 yields the total)
 int scan_i32(const int32_t* in, int64_t n_in, int32_t* out, int64_t n_out, void* ws, size_t ws_bytes,
              cudaStream_t st);
+// out[i] = number of run starts among sorted keys[0..i) (run start: i == 0 or keys[i] != keys[i-1]); n_out = n_keys + 1
+// yields the number of distinct keys in out[n_keys]
+int scan_key_boundaries(const uint64_t* keys, int64_t n_keys, int32_t* out, int64_t n_out, void* ws, size_t ws_bytes,
+                        cudaStream_t st);
 size_t sort_ws_bytes(int64_t n);
 int sort_u64(uint64_t* keys, uint32_t* vals, int64_t n, int key_bits, void* ws, size_t ws_bytes,
              cudaStream_t st);

@@ -104,34 +104,48 @@ __global__ void low32_kernel(const uint64_t* __restrict__ keys, int64_t n, int32
 // ---------------------------------------------------------------------------------------------
 // Ac = P_bin·A·P_bin^T minus diagonal: relabel edges to (part[src], part[dst]) keys, sort, run-length
 // ---------------------------------------------------------------------------------------------
-__global__ void adj_keys_kernel(const int64_t* __restrict__ edge_index, int64_t E, int64_t N,
-                                const int32_t* __restrict__ part, int64_t k, int kb, uint64_t* __restrict__ keys,
-                                int32_t* __restrict__ n_drop) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
-  const int64_t u = edge_index[e], v = edge_index[E + e];
-  int32_t a = 0, b = 0;
-  if (u < 0 || u >= N || v < 0 || v >= N) {
-    atomicExch(n_drop + 1, 1);
-  } else {
-    a = part[u];
-    b = part[v];
-    if (a < 0 || a >= k || b < 0 || b >= k) {
-      atomicExch(n_drop + 1, 1);
-      a = b = 0;
+// ADJ_EPT edges per thread, the part[] gathers of all of them in flight together; one counter atomic per warp
+constexpr int ADJ_EPT = 4;
+__global__ void __launch_bounds__(256)
+adj_keys_kernel(const int64_t* __restrict__ edge_index, int64_t E, int64_t N, const int32_t* __restrict__ part, int64_t k,
+                int kb, uint64_t* __restrict__ keys, int32_t* __restrict__ n_drop) {
+  const int64_t base = (int64_t)blockIdx.x * (256 * ADJ_EPT) + threadIdx.x;
+  int64_t u[ADJ_EPT], v[ADJ_EPT];
+#pragma unroll
+  for (int j = 0; j < ADJ_EPT; ++j) {
+    const int64_t e = base + (int64_t)j * 256;
+    u[j] = e < E ? edge_index[e] : 0;
+    v[j] = e < E ? edge_index[E + e] : 0;
+  }
+  int32_t a[ADJ_EPT], b[ADJ_EPT];
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < ADJ_EPT; ++j) {
+    const bool live = base + (int64_t)j * 256 < E;
+    const bool inr = live && u[j] >= 0 && u[j] < N && v[j] >= 0 && v[j] < N;
+    bad |= live && !inr;
+    a[j] = inr ? __ldg(part + u[j]) : 0;
+    b[j] = inr ? __ldg(part + v[j]) : 0;
+  }
+  int dropped = 0;
+#pragma unroll
+  for (int j = 0; j < ADJ_EPT; ++j) {
+    const int64_t e = base + (int64_t)j * 256;
+    if (e < E) {
+      if (a[j] < 0 || a[j] >= k || b[j] < 0 || b[j] >= k) {
+        bad = true;
+        a[j] = b[j] = 0;
+      }
+      // compact key (row << kb | col), kb = bits of k: 2·kb significant bits instead of 32 + kb -> fewer sort passes;
+      // intra-cluster edges / self loops -> k << kb, which sorts after every real key
+      const bool drop = a[j] == b[j];
+      keys[e] = drop ? (uint64_t)k << kb : ((uint64_t)a[j] << kb) | (uint64_t)b[j];
+      dropped += drop ? 1 : 0;
     }
   }
-  // compact key (row << kb | col), kb = bits of k: 2·kb significant bits instead of 32 + kb -> fewer sort passes
-  const bool drop = a == b;
-  keys[e] = drop ? (uint64_t)k << kb /* sorts after every real key */ : ((uint64_t)a << kb) | (uint64_t)b;
-  // one atomic per warp for the dropped (intra-cluster / self-loop) edges
-  const unsigned m = __ballot_sync(__activemask(), drop);
-  if (drop && (m & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(n_drop, __popc(m));
-}
-
-__global__ void boundary_flags_kernel(const uint64_t* __restrict__ keys, int64_t n, int32_t* __restrict__ flags) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+  if (bad) atomicExch(n_drop + 1, 1);
+  dropped = __reduce_add_sync(0xffffffffu, dropped);
+  if ((threadIdx.x & 31) == 0 && dropped) atomicAdd(n_drop, dropped);
 }
 
 // pos = exclusive scan of flags; run starts write their (row, col) and the run length
@@ -255,7 +269,7 @@ extern "C" int fitgnn_project_adj_plan(const int64_t* edge_index, int64_t E, int
   int64_t n_valid = 0, nnz = 0;
   const int kb = bits_for((uint64_t)k);  // k < 2^31 -> 2·kb <= 62
   if (E > 0) {
-    adj_keys_kernel<<<(unsigned)ceil_div(E, 256), 256, 0, st>>>(edge_index, E, N, part, k, kb, keys, counter);
+    adj_keys_kernel<<<(unsigned)ceil_div(E, 256 * ADJ_EPT), 256, 0, st>>>(edge_index, E, N, part, k, kb, keys, counter);
     FG_LAUNCH_CHECK();
     FG_TRY(sort_u64(keys, nullptr, E, 2 * kb, b.here(), b.left(), st));
     int32_t hc[2] = {0, 0};
@@ -264,9 +278,8 @@ extern "C" int fitgnn_project_adj_plan(const int64_t* edge_index, int64_t E, int
     FG_REQUIRE(hc[1] == 0, FITGNN_EINVAL, "project_adj_plan: edge_index / part hold ids out of range");
     n_valid = E - hc[0];
     if (n_valid > 0) {
-      boundary_flags_kernel<<<(unsigned)ceil_div(n_valid, 256), 256, 0, st>>>(keys, n_valid, flags);
-      FG_LAUNCH_CHECK();
-      FG_TRY(scan_i32(flags, n_valid, flags, n_valid + 1, b.here(), b.left(), st));
+      // exclusive scan of the run-boundary flags, formed on the fly from the sorted keys
+      FG_TRY(scan_key_boundaries(keys, n_valid, flags, n_valid + 1, b.here(), b.left(), st));
       int32_t total = 0;
       FG_CUDA(cudaMemcpyAsync(&total, flags + n_valid, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
       FG_CUDA(cudaStreamSynchronize(st));

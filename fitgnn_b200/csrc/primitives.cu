@@ -12,17 +12,31 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
+// FROM_KEYS: the scanned value is the run-boundary flag of sorted keys, (i == 0 || keys[i] != keys[i-1]), formed on the fly
+// (saves writing and re-reading a flag array)
+template <bool FROM_KEYS>
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_tile_kernel(const int32_t* in, int64_t n_in, int32_t* out, int64_t n_out,
+scan_tile_kernel(const void* in_, int64_t n_in, int32_t* out, int64_t n_out,
                  int32_t* __restrict__ tile_sums) {
+  const int32_t* in = static_cast<const int32_t*>(in_);
+  const uint64_t* keys = static_cast<const uint64_t*>(in_);
   __shared__ int32_t warp_sums[SCAN_THREADS / 32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
   int32_t v[SCAN_ITEMS];
   int32_t sum = 0;
 #pragma unroll
+  uint64_t prev = 0;
+  if (FROM_KEYS && base > 0 && base - 1 < n_in) prev = keys[base - 1];
+#pragma unroll
   for (int i = 0; i < SCAN_ITEMS; ++i) {
-    v[i] = (base + i < n_in) ? in[base + i] : 0;
+    if (FROM_KEYS) {
+      const uint64_t cur = (base + i < n_in) ? keys[base + i] : 0ull;
+      v[i] = (base + i < n_in) ? ((base + i == 0 || cur != prev) ? 1 : 0) : 0;
+      prev = cur;
+    } else {
+      v[i] = (base + i < n_in) ? in[base + i] : 0;
+    }
     sum += v[i];
   }
   int32_t incl = sum;
@@ -72,20 +86,33 @@ size_t scan_ws_bytes(int64_t n) {
   return total + 256;
 }
 
+template <bool FROM_KEYS>
+static int scan_impl(const void* in, int64_t n_in, int32_t* out, int64_t n_out, void* ws, size_t ws_bytes, cudaStream_t st);
+
 int scan_i32(const int32_t* in, int64_t n_in, int32_t* out, int64_t n_out, void* ws, size_t ws_bytes,
              cudaStream_t st) {
+  return scan_impl<false>(in, n_in, out, n_out, ws, ws_bytes, st);
+}
+
+int scan_key_boundaries(const uint64_t* keys, int64_t n_keys, int32_t* out, int64_t n_out, void* ws, size_t ws_bytes,
+                        cudaStream_t st) {
+  return scan_impl<true>(keys, n_keys, out, n_out, ws, ws_bytes, st);
+}
+
+template <bool FROM_KEYS>
+static int scan_impl(const void* in, int64_t n_in, int32_t* out, int64_t n_out, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (n_out <= 0) return FITGNN_OK;
   const int64_t tiles = ceil_div(n_out, SCAN_TILE);
   FG_REQUIRE(tiles < (1ll << 31), FITGNN_ERANGE, "scan: too many elements (%lld)", (long long)n_out);
   if (tiles == 1) {
-    scan_tile_kernel<<<1, SCAN_THREADS, 0, st>>>(in, n_in, out, n_out, nullptr);
+    scan_tile_kernel<FROM_KEYS><<<1, SCAN_THREADS, 0, st>>>(in, n_in, out, n_out, nullptr);
     FG_LAUNCH_CHECK();
     return FITGNN_OK;
   }
   Bump b(ws, ws_bytes);
   int32_t* sums = b.take<int32_t>((size_t)tiles);
   FG_REQUIRE(b.ok, FITGNN_EWS, "scan: workspace too small");
-  scan_tile_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, n_in, out, n_out, sums);
+  scan_tile_kernel<FROM_KEYS><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, n_in, out, n_out, sums);
   FG_LAUNCH_CHECK();
   FG_TRY(scan_i32(sums, tiles, sums, tiles, b.here(), b.left(), st));
   scan_add_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(out, n_out, sums);

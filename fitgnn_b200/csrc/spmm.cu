@@ -339,6 +339,12 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
 
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+
 template <bool SPLIT>
 __global__ void __launch_bounds__(32)
 spmm_group_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ dinv,
@@ -346,6 +352,7 @@ spmm_group_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
                   int64_t n_rows, void* Y, void* Ylo, int64_t ldy, int64_t n_groups) {
   extern __shared__ __align__(16) unsigned char sg_smem[];
   float4* xs = reinterpret_cast<float4*>(sg_smem);  // [32][nq]
+  const uint32_t xs_u32 = (uint32_t)__cvta_generic_to_shared(xs);
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x;
   const bool contiguous = src_index == nullptr && ldx == 4 * (int64_t)nq;
@@ -369,27 +376,37 @@ spmm_group_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    // 2. this lane's row: smem offsets + weights of its first entries
-    int off[SG_SLOTS];
+    // 2. this lane's row: smem byte addresses + weights of its first entries.  Unused slots point at the lane's own row
+    //    with weight 0 (finite * 0 adds nothing; the row's own x is part of its sum anyway), so the slot loop below has
+    //    no lane-dependent branch: the first version predicated the LDS + FFMAs on (slot < deg) and the compiler
+    //    emitted BSSY/BSYNC/BRA around every slot (ncu r1u: 3,330 instructions per group, 2/3 of them overhead).
+    uint32_t addr[SG_SLOTS];
     float w[SG_SLOTS];
 #pragma unroll
     for (int s_ = 0; s_ < SG_SLOTS; ++s_) {
-      const int c = s_ < deg ? ((__ldg(col + rp + s_) - (int)R0) & 31) : lane;  // precondition: group-aligned pack
-      off[s_] = c * nq;
-      w[s_] = __shfl_sync(FULL, dr, c);
+      const bool on = s_ < deg;
+      const int c = on ? ((__ldg(col + rp + s_) - (int)R0) & 31) : lane;  // precondition: group-aligned pack
+      const float wc = __shfl_sync(FULL, dr, c);
+      addr[s_] = xs_u32 + (uint32_t)(c * nq) * 16u;
+      w[s_] = on ? wc : 0.f;
     }
+    const uint32_t mine = xs_u32 + (uint32_t)(lane * nq) * 16u;
     const int maxdeg = __reduce_max_sync(FULL, deg);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     for (int q = 0; q < nq; ++q) {
+      const uint32_t qo = (uint32_t)q * 16u;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int s_ = 0; s_ < SG_SLOTS; ++s_)
-        if (s_ < maxdeg && s_ < deg) fma4(acc, w[s_], xs[off[s_] + q]);
+      for (int s_ = 0; s_ < SG_SLOTS; ++s_) {
+        if (s_ >= maxdeg) break;  // warp-uniform
+        fma4(acc, w[s_], lds128(addr[s_] + qo));
+      }
       for (int s_ = SG_SLOTS; s_ < maxdeg; ++s_) {  // rows longer than the register cache (rare)
-        const int c = s_ < deg ? ((__ldg(col + rp + s_) - (int)R0) & 31) : lane;
-        const float wv = __shfl_sync(FULL, dr, c);
-        if (s_ < deg) fma4(acc, wv, xs[c * nq + q]);
+        const bool on = s_ < deg;
+        const int c = on ? ((__ldg(col + rp + s_) - (int)R0) & 31) : lane;
+        const float wc = __shfl_sync(FULL, dr, c);
+        fma4(acc, on ? wc : 0.f, lds128(xs_u32 + (uint32_t)(c * nq) * 16u + qo));
       }
       const float4 o = make_float4(acc.x * dr, acc.y * dr, acc.z * dr, acc.w * dr);
       __syncwarp();  // every lane has read column q
@@ -397,9 +414,11 @@ spmm_group_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
         uint4 pk;  // (hi quad, lo quad)
         split_bf16x2(o.x, o.y, pk.x, pk.z);
         split_bf16x2(o.z, o.w, pk.y, pk.w);
-        *reinterpret_cast<uint4*>(xs + lane * nq + q) = pk;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(mine + qo), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w)
+                     : "memory");
       } else {
-        xs[lane * nq + q] = o;
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(mine + qo), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
+                     : "memory");
       }
     }
     __syncwarp();
