@@ -12,8 +12,14 @@ PARITY PINNING
     (fixtures: tests/golden/*.npz, generator: tests/golden/make_golden.py).
   * The GCNConv arithmetic lives in torch_geometric, which is not installed and not vendored by the
     reference (requirements.txt:2, unpinned; code needs PyG >= 2.1).  `gcn_norm` / `gcn_conv` restate the
-    published PyG algorithm and are checked against the hand-computed known-answer vector of
-    SURVEY.md §8c and an fp64 dense D^-1/2 (A+I) D^-1/2 restatement — "parity unpinned" for that operator.
+    published PyG algorithm.  They are pinned on SIMPLE graphs (undirected, no self loops, no duplicates,
+    isolated nodes included) against the reference tree's own implementation of the same operator —
+    `normalize_adj` (Baselines/GCOND/models/mycheby.py:393-414) and the dense `GraphConvolution` layer
+    (Baselines/GCOND/models/gcn.py:15-52), executed unmodified (tests/golden/make_golden_gcn_norm.py ->
+    tests/golden/gcn_norm_gcond.npz) — and checked against the hand-computed known-answer vector of
+    SURVEY.md §8c.  PyG's treatment of duplicate edges (counted twice) and of pre-existing self loops
+    (replaced by one) has no executable counterpart in the reference tree: "parity unpinned" for those two
+    rules only.
 """
 from __future__ import annotations
 

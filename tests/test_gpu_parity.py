@@ -107,6 +107,28 @@ def test_gcnconv_known_answer(fg):
     np.testing.assert_array_equal(out[:, 3], 0)
 
 
+def test_gcnconv_matches_reference_tree_gcn_layer(fg):
+    """The CUDA GCNConv against outputs of the reference tree's OWN normalisation + dense GCN layer
+    (Baselines/GCOND/models/mycheby.py:393-414, gcn.py:15-52; fixture tests/golden/gcn_norm_gcond.npz, generated by
+    tests/golden/make_golden_gcn_norm.py from the unmodified reference files).  Tolerance 1e-3 relative (RTOL)."""
+    from tests import golden_io as gio
+    d = gio.load("gcn_norm_gcond")
+    n, ei = int(d["n"]), torch.tensor(d["edge_index"], device=dev())
+    conv = fg.GCNConv(d["X"].shape[1], d["out"].shape[1]).to(dev())
+    with torch.no_grad():
+        conv.lin.weight.copy_(torch.tensor(d["weight_in_out"]).t())
+        conv.bias.copy_(torch.tensor(d["bias"]))
+    out = conv(torch.tensor(d["X"], device=dev()), ei).detach().cpu().numpy()
+    assert_close(out, d["out"])
+    # the CSR the kernels run on reproduces the reference's normalised adjacency entry by entry
+    rowptr, col, dinv = fg.ops.csr_from_coo(ei, n)
+    rp, c, dv = rowptr.cpu().numpy(), col.cpu().numpy(), dinv.cpu().numpy().astype(np.float64)
+    dense = np.zeros((n, n))
+    rows = np.repeat(np.arange(n), np.diff(rp))
+    np.add.at(dense, (rows, c), dv[rows] * dv[c])
+    np.testing.assert_allclose(dense, d["A_norm"], rtol=1e-6, atol=1e-7)
+
+
 @pytest.mark.parametrize("n,e,fin,fout", [(7, 0, 3, 4), (300, 900, 5, 8), (2000, 9000, 100, 512), (1500, 6000, 1433, 512),
                                           (900, 4000, 600, 512), (4000, 30000, 512, 512)])
 def test_gcnconv_matches_fp64(fg, n, e, fin, fout):
