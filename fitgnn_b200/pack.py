@@ -174,3 +174,63 @@ def build_pack(edge_index: torch.Tensor, part: torch.Tensor, k: int, mode: str =
                                  ws2.numel() if ws2 is not None else 0, stream_ptr()))
     torch.cuda.current_stream().synchronize()  # ws / ws2 are released on return
     return p
+
+
+def _field(g, name, default=None):
+    if isinstance(g, dict):
+        return g.get(name, default)
+    return getattr(g, name, default)
+
+
+def pack_from_subgraph_list(graphs, device="cuda"):
+    """Collate a reference-style `subgraph_list` into a pack — the data format on the caller's side of the hot path:
+    the list `coarsening_classification` returns and `main.py:131-172` saves as `..._subgraph_list.pt`
+    (/root/reference/utils.py:248-266), or the `new_graphs` list of `load_data_classification` (utils.py:683-703) that
+    `G_DataLoader(graphs, 128)` re-collates every epoch (run.py:336; `Batch.from_data_list`).  Every element is a PyG
+    `Data` (any object with attributes) or a dict holding `x [n_s, F]`, `edge_index [2, e_s]` (subgraph-local ids) and
+    optionally `mask [n_s]` (M.mask; all True when absent) and `orig_idx [n_s]`.
+
+    Returns (pack, X_packed, node_ids): rows in list order, `X_packed [n_rows, F]` fp32 on the device = the rows of the
+    collated `batch.x` (feed it as `fwd(X_packed)`; `pack.gid` is the identity), `node_ids` = concatenated `orig_idx`
+    (or None).  The CSR goes through the same device builder as the drop-in GCNConv (`fitgnn_csr_*`: self loops
+    replaced by one, duplicates kept), so results equal running the reference model on every list element."""
+    dev = torch.device(device)
+    sizes, xs, eis, masks, ids = [], [], [], [], []
+    off = 0
+    for g in graphs:
+        x = torch.as_tensor(_field(g, "x"))
+        if x.dim() == 1:
+            x = x.view(-1, 1)
+        ei = torch.as_tensor(_field(g, "edge_index")).long().view(2, -1)
+        n_s = x.shape[0]
+        if ei.numel() and (int(ei.min()) < 0 or int(ei.max()) >= n_s):
+            raise ValueError(f"subgraph {len(sizes)}: edge_index refers to a node outside [0, {n_s})")
+        m = _field(g, "mask")
+        masks.append(torch.ones(n_s, dtype=torch.bool) if m is None else torch.as_tensor(m).bool().view(-1).cpu())
+        oi = _field(g, "orig_idx")
+        if oi is not None:  # cluster_node mode: orig_idx covers the real nodes only (utils.py:249); cluster rows get -1
+            oi = torch.as_tensor(oi).long().view(-1).cpu()[:n_s]
+            oi = torch.cat([oi, torch.full((n_s - oi.numel(),), -1, dtype=torch.long)])
+        ids.append(oi)
+        sizes.append(n_s)
+        xs.append(x.float().cpu())
+        eis.append(ei.cpu() + off)
+        off += n_s
+    n_rows, n_sub = off, len(sizes)
+    if n_rows >= 2 ** 31 - 1:
+        raise ValueError("pack_from_subgraph_list: more than 2^31 rows")
+    F = xs[0].shape[1] if xs else 0
+    X = (torch.cat(xs, 0) if xs else torch.zeros(0, F)).to(dev).contiguous()
+    ei = (torch.cat(eis, 1) if eis else torch.zeros(2, 0, dtype=torch.long)).to(dev).contiguous()
+    mask = (torch.cat(masks) if masks else torch.zeros(0, dtype=torch.bool)).to(dev)
+    rowptr, col, dinv = ops.csr_from_coo(ei, n_rows)
+    i32 = dict(dtype=torch.int32, device=dev)
+    sub_ptr = torch.zeros(n_sub + 1, **i32)
+    if n_sub:
+        sub_ptr[1:] = torch.cumsum(torch.tensor(sizes, dtype=torch.int64), 0).to(dev)
+    core_rows = torch.nonzero(mask).view(-1).to(torch.int32)
+    node_ids = None if (not ids or any(i is None for i in ids)) else torch.cat(ids).to(dev)
+    pack = Pack(n_rows=n_rows, nnz=col.numel(), n_sub=n_sub, n_core=core_rows.numel(), n_src=n_rows, n_nodes=n_rows,
+                mode="list", rowptr=rowptr, col=col, dinv=dinv, gid=torch.arange(n_rows, **i32), sub_ptr=sub_ptr,
+                core_rows=core_rows, is_core=mask.to(torch.uint8), mask=mask.to(torch.uint8), part=None)
+    return pack, X, node_ids

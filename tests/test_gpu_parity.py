@@ -282,6 +282,43 @@ def test_projection_bit_exact_and_gc_assembly(fg, case, mode):
         assert np.array_equal(g_.detach().cpu().numpy(), d[f"{mode}_{name}"]), name
 
 
+# ------------------------------------------------------------------------------------------ a14 collation of a subgraph_list
+@pytest.mark.parametrize("case", ["node_small", "node_mid"])
+@pytest.mark.parametrize("mode", MODES)
+def test_pack_from_reference_subgraph_list(fg, case, mode):
+    """pack_from_subgraph_list on the REFERENCE's own subgraph_list (golden fixture: utils.py:248-266 output, the list
+    main.py:131-172 saves and G_DataLoader re-collates, run.py:336): the collated CSR equals the device pack builder's
+    bit for bit, and the whole-list forward equals the reference model run batch by batch (oracle, 1e-3 relative)."""
+    d = gio.load(case)
+    comps, cos, partition = golden_partition(fg, d, mode)
+    ref = gio.subgraphs(d, mode + "_sub")
+    lp, Xp, node_ids = fg.pack_from_subgraph_list(ref, device=dev())
+    pack = fg.build_pack(torch.tensor(d["edge_index"], device=dev()), torch.tensor(partition.part), partition.k, mode)
+    assert (lp.n_rows, lp.nnz, lp.n_sub) == (pack.n_rows, pack.nnz, pack.n_sub)
+    for name in ("rowptr", "col", "dinv", "sub_ptr", "mask"):
+        assert torch.equal(getattr(lp, name), getattr(pack, name)), name
+    assert torch.equal(lp.gid.long(), torch.arange(lp.n_rows, device=dev()))
+    real = node_ids >= 0
+    assert torch.equal(node_ids[real], pack.gid.long()[real]) and bool((pack.gid.long()[~real] >= int(d["n"])).all())
+    X = global_features(d, mode, cos, comps, partition).to(dev())
+    assert torch.equal(Xp, X[pack.gid.long()])  # the collated batch.x == the de-duplicated table gathered through gid
+    sd = gio.state_dict(d) if case == "node_small" else fo.init_state_dict(d["x"].shape[1], int(d["hidden"]),
+                                                                         int(d["n_classes"]), seed=2)
+    for precision in ("fp32", "bf16x3"):
+        out = fg.PackedForward(lp, sd, rows="all", precision=precision)(Xp)
+        want = fo.node_infer_batched(sd, ref, [np.ones(r["x"].shape[0], dtype=bool) for r in ref], "node_cls", 128)
+        assert_close(out.detach().cpu().numpy(), want.numpy())
+    # accepts attribute-style objects (PyG Data) as well as dicts; rejects edges that leave their subgraph
+    class Obj:  # noqa: E306
+        def __init__(self, g):
+            self.x, self.edge_index, self.mask = torch.tensor(g["x"]), torch.tensor(g["edge_index"]), torch.tensor(g["mask"])
+    lp2, Xp2, ids2 = fg.pack_from_subgraph_list([Obj(g) for g in ref[:7]], device=dev())
+    assert ids2 is None and lp2.n_sub == 7 and torch.equal(Xp2, Xp[: lp2.n_rows])
+    bad = dict(x=np.zeros((2, Xp.shape[1]), np.float32), edge_index=np.array([[0], [2]]))
+    with pytest.raises(ValueError):
+        fg.pack_from_subgraph_list([bad], device=dev())
+
+
 # ------------------------------------------------------------------------------------------ a2, a5, a6 forward
 @pytest.mark.parametrize("case", ["node_small", "node_mid"])
 @pytest.mark.parametrize("mode", MODES)
