@@ -44,7 +44,7 @@ SIGNATURES = {
     "fitgnn_spmm_symnorm": (c_i32, [c_void, c_void, c_void, c_void, c_i64, c_i32, c_void, c_void, c_i32, c_void, c_i64,
                                     c_void, c_void, c_i64, c_void]),
     "fitgnn_spmm_symnorm_grouped": (c_i32, [c_void, c_void, c_void, c_void, c_i64, c_i32, c_void, c_i64, c_i32, c_void,
-                                            c_void, c_i64, c_void]),
+                                            c_void, c_i64, c_i32, C.c_float, c_void]),
     "fitgnn_spmm_hubs": (c_i32, [c_void, c_void, c_i64, c_i32, c_void, c_void, c_i32, c_void]),
     "fitgnn_spmm_symnorm_hub": (c_i32, [c_void, c_void, c_void, c_void, c_i64, c_i32, c_void, c_void, c_i32, c_void,
                                         c_i64, c_void, c_void, c_i64, c_void, c_i32, c_i32, c_void]),

@@ -252,8 +252,11 @@ class PackedForward:
         if self.grouped_spmm and Wd <= 128:
             # group-local aggregation: the group's 32 source rows are staged in shared memory once (spmm.cu)
             self.launches += 1
+            # the pad columns of the planes (constant 1 of the bias fold / zeros) are re-written with the same values:
+            # whole-sector stores instead of a DRAM read-modify-write per row
             A = self._timed("spmm0", lambda: ops.spmm_symnorm_grouped(ap.rowptr, ap.col, ap.dinv, X, Wd, src, split=True,
-                                                                      out=self._planes0),
+                                                                      out=self._planes0,
+                                                                      pad_value=(1.0 if fold else 0.0)),
                             nbytes=self._spmm_bytes_aligned(Wd, src, X.shape[0]))
         else:
             A = self._spmm(X, Wd, src, None, ops.ACT_NONE, False, split=True, name="spmm0", pack=ap, out=self._planes0)

@@ -86,9 +86,11 @@ def spmm_symnorm(rowptr, col, dinv, X, width=None, src_index=None, bias=None, ac
     return out
 
 
-def spmm_symnorm_grouped(rowptr, col, dinv, X, width=None, src_index=None, out=None, split=False, group=32):
+def spmm_symnorm_grouped(rowptr, col, dinv, X, width=None, src_index=None, out=None, split=False, group=32,
+                         pad_value=None):
     """Y = Â·X[src_index] on a group-aligned pack (Pack.aligned): fitgnn_spmm_symnorm_grouped, bit-identical to
-    spmm_symnorm without bias / activation / row selection.  Raises FitgnnError(EUNSUP) for width > 128."""
+    spmm_symnorm without bias / activation / row selection.  Raises FitgnnError(EUNSUP) for width > 128.
+    pad_value (split planes with pitch width + 4 only): also write the pad columns, hi[:, width] = pad_value, rest 0."""
     assert X.dtype == torch.float32 and X.dim() == 2
     width = X.shape[1] if width is None else width
     n = rowptr.numel() - 1
@@ -102,7 +104,8 @@ def spmm_symnorm_grouped(rowptr, col, dinv, X, width=None, src_index=None, out=N
             out = torch.empty(n, width, dtype=torch.float32, device=X.device)
         y, ylo, ldy = out, None, out.stride(0)
     check(lib().fitgnn_spmm_symnorm_grouped(ptr(rowptr), ptr(col), ptr(dinv), ptr(X), X.stride(0), width, ptr(src_index),
-                                            n, group, ptr(y), ptr(ylo), ldy, stream_ptr()))
+                                            n, group, ptr(y), ptr(ylo), ldy, int(pad_value is not None),
+                                            float(pad_value or 0.0), stream_ptr()))
     return out
 
 

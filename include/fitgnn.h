@@ -143,7 +143,10 @@ int fitgnn_spmm_symnorm(const int32_t* rowptr, const int32_t* col, const float* 
  * point outside their group are a precondition violation (they are wrapped into the group, never out of bounds). */
 int fitgnn_spmm_symnorm_grouped(const int32_t* rowptr, const int32_t* col, const float* dinv,
                                 const float* X, int64_t ldx, int width, const int32_t* src_index,
-                                int64_t n_rows, int group, void* Y, void* Y_lo, int64_t ldy, void* stream);
+                                int64_t n_rows, int group, void* Y, void* Y_lo, int64_t ldy,
+                                int fill_pad, float pad_value, void* stream);
+/* fill_pad != 0 (bf16 planes with ldy == width + 4 only, ignored otherwise): the four pad columns of every row are written
+ * as well — hi[:, width] = pad_value, all other pad elements 0 — so that the planes are written in whole 32-byte sectors. */
 /* Same with the high-degree rows split across a CTA: hub_list (from fitgnn_spmm_hubs) holds the output
  * indices i whose row has >= hub_deg entries; the warp-per-row pass skips them. */
 int fitgnn_spmm_hubs(const int32_t* rowptr, const int32_t* out_rows, int64_t n_out, int hub_deg,

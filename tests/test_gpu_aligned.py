@@ -256,3 +256,22 @@ def test_grouped_spmm_rejects_wide_rows(fg):
     X = torch.zeros(ap.n_rows, 132, device=dev())
     with pytest.raises(Exception, match="EUNSUP|width"):
         fg.ops.spmm_symnorm_grouped(ap.rowptr, ap.col, ap.dinv, X, 132, None)
+
+
+def test_grouped_spmm_fills_the_pad_columns(fg):
+    """pad_value: planes with pitch width + 4 get their pad columns written too (hi[:, width] = pad_value, rest 0), the
+    data columns stay bit-identical; planes with another pitch are left alone."""
+    ei, part, k = small_subgraph_graph(4000, 1800, 7, max_size=12)
+    ap = fg.build_pack(torch.tensor(ei, device=dev()), torch.tensor(part), k, "none").aligned(32, "degree")
+    width = 100
+    X = torch.randn(ap.n_rows, width, device=dev())
+    want = fg.ops.spmm_symnorm(ap.rowptr, ap.col, ap.dinv, X, width, None, split=True)
+    for pitch in (width + 4, width + 12):
+        hi = torch.full((ap.n_rows, pitch), 7.0, dtype=torch.bfloat16, device=dev())
+        lo = torch.full((ap.n_rows, pitch), 7.0, dtype=torch.bfloat16, device=dev())
+        fg.ops.spmm_symnorm_grouped(ap.rowptr, ap.col, ap.dinv, X, width, None, split=True, out=(hi, lo), pad_value=1.0)
+        assert torch.equal(hi[:, :width], want[0]) and torch.equal(lo[:, :width], want[1])
+        if pitch == width + 4:
+            assert bool((hi[:, width] == 1.0).all()) and bool((hi[:, width + 1:] == 0).all()) and bool((lo[:, width:] == 0).all())
+        else:
+            assert bool((hi[:, width:] == 7.0).all()) and bool((lo[:, width:] == 7.0).all())
