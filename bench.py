@@ -193,7 +193,16 @@ def config_of(args, n, F, C, k):
     return {"workload": f"{args.workload}: ogbn-products-shaped synthetic, {n} nodes, "
                         f"{workload_shape(args.workload)[1]} undirected edges, F={F}, C={C}, planted partition "
                         f"ratio {args.ratio} (k={k}), mode={args.mode}, 2-layer GCN hidden={args.hidden} + lt1 + log_softmax",
-            "subgraphs": k, "mode": args.mode, "l2": "inputs larger than L2 (activations are GBs per layer)"}
+            "subgraphs": k, "mode": args.mode, "l2": "inputs larger than L2 (activations are GBs per layer)",
+            "features": "pack-ordered rows" if features_packed(args) else "node-ordered table + gid"}
+
+
+def features_packed(args, n_chunks=None):
+    """Input layout of the timed forward (see --features): the reference's own layout (one x row per subgraph row, collated
+    in subgraph order) unless asked otherwise / not applicable."""
+    if n_chunks is None:
+        n_chunks = 1 if args.gpus == 1 else args.chunks
+    return args.features == "packed" or (args.features == "auto" and args.mode == "none" and n_chunks == 1)
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
@@ -298,7 +307,7 @@ def main_ours(args):
 
     # pack-ordered features: the reference's models receive one copy of x per subgraph row, collated in subgraph order
     # (utils.py:248, run.py:336); the layout is produced once, with the pack (mode none: N rows either way, the same bytes)
-    packed = args.features == "packed" or (args.features == "auto" and args.mode == "none" and len(fwds) == 1)
+    packed = features_packed(args, len(fwds))
     if packed and len(fwds) != 1:
         raise SystemExit("bench: --features packed needs --chunks 1")
     X_table = Xd
@@ -584,8 +593,7 @@ def main_ours(args):
     line = {"metric": METRIC, "value": n / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32" if precision == "fp32" else "bf16x3(f32 accumulate)", "data": "synthetic",
-            "config": dict(config_of(args, n, F, C, k), features="pack-ordered rows" if packed else "node-ordered table + gid"),
-            "roofline": roofline_of(dom), "roofline_spmm": spmm_roof,
+            "config": config_of(args, n, F, C, k), "roofline": roofline_of(dom), "roofline_spmm": spmm_roof,
             "schedule": ("spmm0 -> [transform + next layer's aggregation in the epilogue] -> transform -> head (group-aligned "
                          f"pack, {fwd.apack.n_rows} rows incl. padding)") if fused else "spmm + transform per layer -> head",
             "kernels": kernels, "gpu_launches": gpu_launches, "clocks": sampler.summary(mark0, mark1),
