@@ -132,3 +132,31 @@ def test_oracle_aligned_layout_invariants():
     assert list(s4) == [32, 31, 30, 0, 35] and n4 == 35
     s5, n5 = fo.aligned_layout(sub_ptr, 32, "order", rowptr)
     assert list(s5) == [0, 3, 4, 32, 62] and n5 == 62
+
+
+def test_bench_reference_arm_contract_on_cpu():
+    """`bench.py --impl reference` (the oracle port of node_infer_Gs_GD timed on the host cores) prints ONE JSON line with
+    the keys the driver reads; run here on the small workload (no GPU involved)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload",
+                          "products-small", "--steps", "1", "--warmup", "0", "--cpu-seconds", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "subgraph-inference nodes/sec" and d["unit"] == "nodes/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "subgraphs" in cb["sample"]
+    assert set(d["config"]) >= {"workload", "subgraphs", "mode", "l2", "features"} and "model" not in d["config"]
+    # ranks other than 0 print nothing and exit 0 (torchrun launches every rank)
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, timeout=120, cwd=root, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
