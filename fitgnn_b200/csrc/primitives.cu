@@ -25,7 +25,6 @@ scan_tile_kernel(const void* in_, int64_t n_in, int32_t* out, int64_t n_out,
   const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
   int32_t v[SCAN_ITEMS];
   int32_t sum = 0;
-#pragma unroll
   uint64_t prev = 0;
   if (FROM_KEYS && base > 0 && base - 1 < n_in) prev = keys[base - 1];
 #pragma unroll
