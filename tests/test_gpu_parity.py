@@ -409,6 +409,32 @@ def test_graph_level_models_match_reference(fg):
     assert_close(mgc.to(dev()).eval()(gc).detach().cpu().numpy(), want.numpy())
 
 
+def test_graph_classification_matches_reference_outputs(fg):
+    """Classify_graph_gs / Classify_graph_gc on the GPU against the REFERENCE's own outputs (graph_cls_small.npz:
+    coarsening_classification(task='graph_cls', cluster_node), colater, network.py:118-135 and :87-95 run unmodified)."""
+    import argparse
+    from oracle.ref_shims import Data
+    d = gio.load("graph_cls_small")
+    sd = gio.state_dict(d)
+    n_g = int(d["n_kept"])
+    set_gs = [[Data(x=torch.tensor(s["x"]), edge_index=torch.tensor(s["edge_index"]), mask=torch.tensor(s["mask"]))
+               for s in gio.subgraphs(d, f"g{g}_sub")] for g in range(n_g)]
+    args = argparse.Namespace(num_layers1=2, num_features=d["g0_x"].shape[1], hidden=int(d["hidden"]),
+                              num_classes=int(d["n_classes"]), layer_name="GCNConv")
+    model = fg.Classify_graph_gs(args)
+    model.load_state_dict(sd)
+    pred = model.to(dev()).eval()(set_gs, torch.tensor(d["batch_tensor"]))
+    assert_close(pred.detach().cpu().numpy(), d["pred_gs"])
+    gx = torch.tensor(np.concatenate([d[f"g{g}_gc_x"] for g in range(n_g)])).float()
+    off, eis = 0, []
+    for g in range(n_g):
+        eis.append(d[f"g{g}_gc_edge"] + off); off += d[f"g{g}_gc_x"].shape[0]
+    gc = Data(x=gx.to(dev()), edge_index=torch.tensor(np.concatenate(eis, 1)).to(dev()), batch=torch.tensor(d["gc_batch"]).to(dev()))
+    model_gc = fg.Classify_graph_gc(args)
+    model_gc.load_state_dict(sd)
+    assert_close(model_gc.to(dev()).eval()(gc).detach().cpu().numpy(), d["pred_gc"])
+
+
 # ------------------------------------------------------------------------------------------ config-shaped + properties
 @pytest.mark.parametrize("mode", MODES)
 def test_cora_shaped_config(fg, mode):
