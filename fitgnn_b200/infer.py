@@ -97,3 +97,30 @@ def graph_level_Gs(state_dict, pack: Pack, X, graph_of_sub: torch.Tensor, task="
     w = state_dict["lt1.weight"].detach().to(dev).float().contiguous()
     b = state_dict["lt1.bias"].detach().to(dev).float().contiguous()
     return ops.gemm_bias_act(pooled, w, b, ops.ACT_NONE, ops.HEAD_SOFTMAX if task == "graph_cls" else ops.HEAD_IDENTITY)
+
+
+def node_metrics(out, labels, task="node_cls", loss_reduction="mean"):
+    """(loss, acc) exactly as `node_infer_Gs_GD` reports them (/root/reference/run.py:99-115) from the selected rows'
+    outputs (log-probabilities [n, C] for node_cls, predictions [n] / [n, 1] for node_reg) and labels, both in the
+    order `node_infer_Gs` returns them: node_cls -> NLLLoss_numpy (utils.py:927-954) + accuracy; node_reg ->
+    L1Loss_numpy (utils.py:972-987) divided by the population std of the labels, acc = 0; with loss_reduction='sum'
+    the summed loss is divided by the number of rows.  Host arithmetic on numpy (the reference does the same)."""
+    import numpy as np
+    o = out.detach().cpu().numpy() if torch.is_tensor(out) else np.asarray(out)
+    y = labels.detach().cpu().numpy() if torch.is_tensor(labels) else np.asarray(labels)
+    if loss_reduction not in ("mean", "sum"):
+        raise ValueError("Reduction must be 'mean' or 'sum'.")
+    red = np.mean if loss_reduction == "mean" else np.sum
+    if task == "node_cls":
+        y = y.reshape(-1).astype(np.int64)
+        if o.ndim != 2 or y.shape[0] != o.shape[0] or not np.all((y >= 0) & (y < o.shape[1])):
+            raise ValueError("node_metrics: log-probabilities must be [n, C] and labels valid class ids of length n")
+        loss = float(red(-o[np.arange(o.shape[0]), y]))
+        acc = float(np.sum(np.argmax(o, axis=1) == y) / len(y))
+    else:
+        o, y = o.reshape(-1).astype(np.float64), y.reshape(-1).astype(np.float64)
+        if o.shape != y.shape:
+            raise ValueError("node_metrics: predictions and labels must have the same number of elements")
+        loss = float(red(np.abs(o - y))) / float(np.std(y))
+        acc = 0
+    return (loss, acc) if loss_reduction == "mean" else (loss / len(o), acc)

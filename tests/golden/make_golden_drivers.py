@@ -1,0 +1,62 @@
+"""Generates tests/golden/drivers_small.npz: the reference's own EVALUATION DRIVER `node_infer_Gs_GD` (run.py:49-115)
+called unmodified — behind oracle/ref_shims.py — on the subgraph lists, split masks and checkpoints already stored in
+node_small.npz (node classification: NLLLoss_numpy + accuracy) and node_reg_small.npz (node regression:
+L1Loss_numpy / std(labels)), for the 'test' and 'val' branches, both loss reductions and all three modes.
+
+    python tests/golden/make_golden_drivers.py          # authoring container only
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import make_golden as mg  # noqa: E402  (installs the shims, imports the reference's utils / network)
+from oracle import ref_shims  # noqa: E402
+from tests import golden_io as gio  # noqa: E402
+
+_cwd = os.getcwd()
+import tempfile  # noqa: E402
+os.chdir(tempfile.mkdtemp())  # run.py creates ./results on import
+import run as ref_run  # noqa: E402  (reference run.py)
+os.chdir(_cwd)
+
+
+def graphs_of(d, mode):
+    out = []
+    for s in gio.subgraphs(d, mode + "_sub"):
+        g = mg.Data(x=torch.tensor(s["x"]), edge_index=torch.tensor(s["edge_index"]), y=torch.tensor(s["y"]))
+        g.train_mask, g.val_mask, g.test_mask = (torch.tensor(s[k]) for k in ("train_mask", "val_mask", "test_mask"))
+        out.append(g)
+    return out
+
+
+def main():
+    out = {}
+    for case, task, Model, Loss in (("node_small", "node_cls", mg.ref_network.Classify_node, mg.ref_utils.NLLLoss_numpy),
+                                    ("node_reg_small", "node_reg", mg.ref_network.Regress_node, mg.ref_utils.L1Loss_numpy)):
+        d = gio.load(case)
+        sd = gio.state_dict(d)
+        C = int(d["n_classes"]) if "n_classes" in d.files else 1
+        for mode in ("none", "extra", "cluster"):
+            graphs = graphs_of(d, mode)
+            for reduction in ("mean", "sum"):
+                args = argparse.Namespace(task=task, num_classes=C, num_features=d["x"].shape[1], hidden=int(d["hidden"]),
+                                          num_layers1=2, layer_name="GCNConv", loss_reduction=reduction)
+                model = Model(args)
+                model.load_state_dict(sd)
+                loader = ref_shims.DataLoader(graphs, batch_size=128, shuffle=False)  # run.py:336
+                for which in ("test", "val"):
+                    with torch.no_grad():
+                        loss, acc, _ = ref_run.node_infer_Gs_GD(args, model, loader, Loss(reduction), which)
+                    out[f"{case}_{mode}_{reduction}_{which}"] = np.array([loss, acc], dtype=np.float64)
+    np.savez_compressed(os.path.join(mg.OUT, "drivers_small.npz"), **out)
+    for k in sorted(out)[:6]:
+        print(k, out[k])
+    print(len(out), "entries")
+
+
+if __name__ == "__main__":
+    main()
