@@ -1,7 +1,8 @@
 """Generates tests/golden/drivers_small.npz: the reference's own EVALUATION DRIVER `node_infer_Gs_GD` (run.py:49-115)
 called unmodified — behind oracle/ref_shims.py — on the subgraph lists, split masks and checkpoints already stored in
 node_small.npz (node classification: NLLLoss_numpy + accuracy) and node_reg_small.npz (node regression:
-L1Loss_numpy / std(labels)), for the 'test' and 'val' branches, both loss reductions and all three modes.
+L1Loss_numpy / std(labels)), for the 'test' and 'val' branches, both loss reductions and all three modes; and the TRAINING
+DRIVER `node_train_Gs_GD` (run.py:177-215): three Adam steps on node_small.npz, dropout disabled (see below).
 
     python tests/golden/make_golden_drivers.py          # authoring container only
 """
@@ -52,6 +53,27 @@ def main():
                     with torch.no_grad():
                         loss, acc, _ = ref_run.node_infer_Gs_GD(args, model, loader, Loss(reduction), which)
                     out[f"{case}_{mode}_{reduction}_{which}"] = np.array([loss, acc], dtype=np.float64)
+    # ---- training driver: node_train_Gs_GD (run.py:177-215), three Adam steps (lr / weight decay: main.py defaults).
+    # The dropout mask of network.py:33 depends on the RNG stream, so the step is recorded with F.dropout replaced by the
+    # identity for the duration of the call (torch.nn.functional is patched, no reference source is touched).
+    d = gio.load("node_small")
+    import torch.nn.functional as F_
+    real_dropout = F_.dropout
+    F_.dropout = lambda x, p=0.5, training=True, inplace=False: x
+    try:
+        for mode in ("none", "extra", "cluster"):
+            args = argparse.Namespace(task="node_cls", num_classes=int(d["n_classes"]), num_features=d["x"].shape[1],
+                                      hidden=int(d["hidden"]), num_layers1=2, layer_name="GCNConv", loss_reduction="mean")
+            model = mg.ref_network.Classify_node(args)
+            model.load_state_dict(gio.state_dict(d))
+            opt = torch.optim.Adam(model.parameters(), lr=0.01, weight_decay=0.0005)
+            loader = ref_shims.DataLoader(graphs_of(d, mode), batch_size=128, shuffle=False)
+            losses = [ref_run.node_train_Gs_GD(model, loader, torch.nn.NLLLoss(reduction="mean"), opt, args) for _ in range(3)]
+            out[f"train_{mode}_losses"] = np.array(losses, dtype=np.float64)
+            for k, v in model.state_dict().items():
+                out[f"train_{mode}_sd_{k}"] = v.detach().numpy()
+    finally:
+        F_.dropout = real_dropout
     np.savez_compressed(os.path.join(mg.OUT, "drivers_small.npz"), **out)
     for k in sorted(out)[:6]:
         print(k, out[k])
