@@ -99,12 +99,27 @@ def graph_level_Gs(state_dict, pack: Pack, X, graph_of_sub: torch.Tensor, task="
     return ops.gemm_bias_act(pooled, w, b, ops.ACT_NONE, ops.HEAD_SOFTMAX if task == "graph_cls" else ops.HEAD_IDENTITY)
 
 
-def node_metrics(out, labels, task="node_cls", loss_reduction="mean"):
-    """(loss, acc) exactly as `node_infer_Gs_GD` reports them (/root/reference/run.py:99-115) from the selected rows'
-    outputs (log-probabilities [n, C] for node_cls, predictions [n] / [n, 1] for node_reg) and labels, both in the
-    order `node_infer_Gs` returns them: node_cls -> NLLLoss_numpy (utils.py:927-954) + accuracy; node_reg ->
-    L1Loss_numpy (utils.py:972-987) divided by the population std of the labels, acc = 0; with loss_reduction='sum'
-    the summed loss is divided by the number of rows.  Host arithmetic on numpy (the reference does the same)."""
+def batch_of_rows(sub_ptr, rows, batch_size=128):
+    """Index of the reference's DataLoader batch (`G_DataLoader(graphs, batch_size)`, run.py:336: consecutive subgraphs)
+    every pack row in `rows` falls into, and the number of batches.  Pure index arithmetic (any device)."""
+    sp = sub_ptr.long()
+    n_sub = sp.numel() - 1
+    sub = torch.searchsorted(sp, rows.long().to(sp.device), right=True) - 1
+    return sub // batch_size, (n_sub + batch_size - 1) // batch_size
+
+
+def node_metrics(out, labels, task="node_cls", loss_reduction="mean", batch_ids=None, n_batches=None):
+    """(loss, acc) exactly as the reference's evaluation drivers report them, from the selected rows' outputs
+    (log-probabilities [n, C] for node_cls, predictions [n] / [n, 1] for node_reg) and labels, both in the order
+    `node_infer_Gs` returns them.
+
+    batch_ids None -> `node_infer_Gs_GD` (/root/reference/run.py:99-115): node_cls = NLLLoss_numpy (utils.py:927-954) +
+    accuracy; node_reg = L1Loss_numpy (utils.py:972-987) divided by the population std of the labels, acc = 0; with
+    loss_reduction='sum' the summed loss is divided by the number of rows.
+    batch_ids given (batch_of_rows) -> `node_infer_Gs_MB` (run.py:117-175): the loss is taken per DataLoader batch and the
+    per-batch values are added up; 'mean' divides by the number of ALL batches `n_batches` (batches without a selected
+    row included), 'sum' by the number of rows; node_reg divides by the UNBIASED std of the labels (torch.std).
+    Host arithmetic on numpy (the reference does the same for GD)."""
     import numpy as np
     o = out.detach().cpu().numpy() if torch.is_tensor(out) else np.asarray(out)
     y = labels.detach().cpu().numpy() if torch.is_tensor(labels) else np.asarray(labels)
@@ -115,12 +130,23 @@ def node_metrics(out, labels, task="node_cls", loss_reduction="mean"):
         y = y.reshape(-1).astype(np.int64)
         if o.ndim != 2 or y.shape[0] != o.shape[0] or not np.all((y >= 0) & (y < o.shape[1])):
             raise ValueError("node_metrics: log-probabilities must be [n, C] and labels valid class ids of length n")
-        loss = float(red(-o[np.arange(o.shape[0]), y]))
+        per_row = -o[np.arange(o.shape[0]), y].astype(np.float64)
         acc = float(np.sum(np.argmax(o, axis=1) == y) / len(y))
     else:
         o, y = o.reshape(-1).astype(np.float64), y.reshape(-1).astype(np.float64)
         if o.shape != y.shape:
             raise ValueError("node_metrics: predictions and labels must have the same number of elements")
-        loss = float(red(np.abs(o - y))) / float(np.std(y))
+        per_row = np.abs(o - y)
         acc = 0
-    return (loss, acc) if loss_reduction == "mean" else (loss / len(o), acc)
+    if batch_ids is None:
+        loss = float(red(per_row))
+        if task != "node_cls":
+            loss /= float(np.std(y))
+        return (loss, acc) if loss_reduction == "mean" else (loss / len(per_row), acc)
+    b = batch_ids.detach().cpu().numpy() if torch.is_tensor(batch_ids) else np.asarray(batch_ids)
+    if b.shape[0] != per_row.shape[0] or n_batches is None:
+        raise ValueError("node_metrics: batch_ids needs one entry per row and n_batches")
+    total = float(sum(red(per_row[b == i]) for i in np.unique(b)))
+    scale = 1.0 if task == "node_cls" else float(np.std(y, ddof=1))
+    denom = n_batches if loss_reduction == "mean" else len(per_row)
+    return total / (denom * scale), acc

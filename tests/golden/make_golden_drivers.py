@@ -53,6 +53,25 @@ def main():
                     with torch.no_grad():
                         loss, acc, _ = ref_run.node_infer_Gs_GD(args, model, loader, Loss(reduction), which)
                     out[f"{case}_{mode}_{reduction}_{which}"] = np.array([loss, acc], dtype=np.float64)
+    # ---- mini-batch evaluation driver: node_infer_Gs_MB (run.py:117-175): per-batch torch losses, averaged over ALL batches
+    for case, task, Model, Loss in (("node_small", "node_cls", mg.ref_network.Classify_node, torch.nn.NLLLoss),
+                                    ("node_reg_small", "node_reg", mg.ref_network.Regress_node, torch.nn.L1Loss)):
+        d = gio.load(case)
+        C = int(d["n_classes"]) if "n_classes" in d.files else 1
+        for mode in ("none", "extra", "cluster"):
+            graphs = graphs_of(d, mode)
+            for reduction in ("mean", "sum"):
+                args = argparse.Namespace(task=task, num_classes=C, num_features=d["x"].shape[1], hidden=int(d["hidden"]),
+                                          num_layers1=2, layer_name="GCNConv", loss_reduction=reduction)
+                model = Model(args)
+                model.load_state_dict(gio.state_dict(d))
+                loader = ref_shims.DataLoader(graphs, batch_size=32, shuffle=False)  # several batches on the small lists
+                for which in ("test", "val"):
+                    with torch.no_grad():
+                        loss, acc, _ = ref_run.node_infer_Gs_MB(args, model, loader, Loss(reduction=reduction), which)
+                    out[f"mb_{case}_{mode}_{reduction}_{which}"] = np.array([loss, acc], dtype=np.float64)
+    out["mb_batch_size"] = np.array(32)
+
     # ---- training driver: node_train_Gs_GD (run.py:177-215), three Adam steps (lr / weight decay: main.py defaults).
     # The dropout mask of network.py:33 depends on the RNG stream, so the step is recorded with F.dropout replaced by the
     # identity for the duration of the call (torch.nn.functional is patched, no reference source is touched).
