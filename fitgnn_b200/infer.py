@@ -150,3 +150,45 @@ def node_metrics(out, labels, task="node_cls", loss_reduction="mean", batch_ids=
     scale = 1.0 if task == "node_cls" else float(np.std(y, ddof=1))
     denom = n_batches if loss_reduction == "mean" else len(per_row)
     return total / (denom * scale), acc
+
+
+def graph_metrics(pred, y, task="graph_reg", batch_size=128, reference_quirks=True):
+    """(loss, acc) as the reference's graph-level evaluation driver `graph_infer_Gs` (/root/reference/run.py:306-328)
+    reports them for predictions `pred` [n_graphs, C] (graph_level_Gs / the graph models) and labels `y` [n_graphs], with
+    the graphs batched `batch_size` at a time in order (T_DataLoader + colater, run.py:577-580).  The loss is taken per
+    batch and averaged over the batches.  graph_cls: CrossEntropyLoss applied to the model's softmax OUTPUT (run.py:583,
+    network.py:131-135 — a log-softmax of probabilities).  graph_reg: L1Loss, divided by the unbiased
+    std of the labels.
+
+    reference_quirks=True reproduces three things the driver does: labels are cast to int64 first (`.type(torch.long)`,
+    run.py:312 — regression targets are truncated), the L1 loss broadcasts predictions [B, 1] against labels [B]
+    (mean over all B x B pairs), and the classification accuracy is that of the LAST batch only (run.py:323).  With
+    False: untruncated labels, row-wise L1, accuracy over all graphs."""
+    import numpy as np
+    p = (pred.detach().cpu().numpy() if torch.is_tensor(pred) else np.asarray(pred)).astype(np.float64)
+    t = (y.detach().cpu().numpy() if torch.is_tensor(y) else np.asarray(y)).reshape(-1)
+    if p.ndim == 1:
+        p = p[:, None]
+    if p.shape[0] != t.shape[0] or batch_size < 1:
+        raise ValueError("graph_metrics: one label per prediction row and batch_size >= 1")
+    if reference_quirks or task == "graph_cls":
+        t = t.astype(np.int64)  # numpy truncates toward zero like torch's float -> long cast
+    n = p.shape[0]
+    bounds = [(a, min(a + batch_size, n)) for a in range(0, n, batch_size)]
+    total, acc = 0.0, 0
+    for a, b in bounds:
+        pb, tb = p[a:b], t[a:b]
+        if task == "graph_cls":
+            z = pb - pb.max(axis=1, keepdims=True)
+            logp = z - np.log(np.exp(z).sum(axis=1, keepdims=True))
+            total += float(np.mean(-logp[np.arange(b - a), tb]))
+        elif reference_quirks:
+            total += float(np.mean(np.abs(pb[:, :1] - tb[None, :].astype(np.float64))))
+        else:
+            total += float(np.mean(np.abs(pb[:, 0] - tb.astype(np.float64))))
+    if task == "graph_cls":
+        a, b = bounds[-1] if reference_quirks else (0, n)
+        acc = float(np.sum(np.argmax(p[a:b], axis=1) == t[a:b]) / (b - a))
+    else:
+        total /= float(np.std(t.astype(np.float32 if reference_quirks else np.float64), ddof=1))
+    return total / len(bounds), acc

@@ -72,6 +72,34 @@ def main():
                     out[f"mb_{case}_{mode}_{reduction}_{which}"] = np.array([loss, acc], dtype=np.float64)
     out["mb_batch_size"] = np.array(32)
 
+    # ---- graph-level evaluation driver: graph_infer_Gs (run.py:306-328) over T_DataLoader(..., collate_fn=colater())
+    # batches (run.py:577-580, :709-712), with the loss functions graph_classification / graph_regression construct
+    # (CrossEntropyLoss on the model's softmax output, run.py:583; L1Loss, run.py:716)
+    from torch.utils.data import DataLoader as T_DataLoader
+    for case, task, Model, loss_fn in (("graph_small", "graph_reg", mg.ref_network.Regress_graph_gs, torch.nn.L1Loss()),
+                                       ("graph_cls_small", "graph_cls", mg.ref_network.Classify_graph_gs,
+                                        torch.nn.CrossEntropyLoss())):
+        d = gio.load(case)
+        data_list = []
+        for g in range(int(d["n_kept"])):
+            subs = [mg.Data(x=torch.tensor(s_["x"]), edge_index=torch.tensor(s_["edge_index"]), mask=torch.tensor(s_["mask"]))
+                    for s_ in gio.subgraphs(d, f"g{g}_sub")]
+            graph = mg.Data(x=torch.tensor(d[f"g{g}_x"]), edge_index=torch.tensor(d[f"g{g}_ei"]), y=torch.tensor(d[f"g{g}_y"]))
+            Gc = mg.Data(x=torch.tensor(d[f"g{g}_gc_x"]), edge_index=torch.tensor(d[f"g{g}_gc_edge"]))
+            data_list.append([graph, Gc, subs])
+        args = argparse.Namespace(task=task, num_classes=int(d["n_classes"]) if "n_classes" in d.files else 1,
+                                  num_features=d["g0_x"].shape[1], hidden=int(d["hidden"]), num_layers1=2,
+                                  layer_name="GCNConv", multi_prop=False)
+        model = Model(args)
+        model.load_state_dict(gio.state_dict(d))
+        loader = T_DataLoader(data_list, batch_size=3, shuffle=False, collate_fn=mg.ref_utils.colater())
+        import warnings
+        with torch.no_grad(), warnings.catch_warnings():
+            warnings.simplefilter("ignore")  # L1Loss broadcasts [B,1] against [B] in the reference (see infer.graph_metrics)
+            loss, acc = ref_run.graph_infer_Gs(args, model, loader, loss_fn)
+        out[f"graph_{case}"] = np.array([loss, acc], dtype=np.float64)
+    out["graph_batch_size"] = np.array(3)
+
     # ---- training driver: node_train_Gs_GD (run.py:177-215), three Adam steps (lr / weight decay: main.py defaults).
     # The dropout mask of network.py:33 depends on the RNG stream, so the step is recorded with F.dropout replaced by the
     # identity for the duration of the call (torch.nn.functional is patched, no reference source is touched).
