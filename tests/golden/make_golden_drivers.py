@@ -119,6 +119,24 @@ def main():
             out[f"train_{mode}_losses"] = np.array(losses, dtype=np.float64)
             for k, v in model.state_dict().items():
                 out[f"train_{mode}_sd_{k}"] = v.detach().numpy()
+        # node_train_Gc / node_val_Gc (run.py:26-47): the same model trained on the COARSENED graph Gc of the fixture
+        # (load_data_classification outputs stored in node_small.npz), three Adam steps + the validation loss after them
+        for mode in ("none", "cluster"):
+            args = argparse.Namespace(task="node_cls", num_classes=int(d["n_classes"]), num_features=d["x"].shape[1],
+                                      hidden=int(d["hidden"]), num_layers1=2, layer_name="GCNConv", loss_reduction="mean")
+            model = mg.ref_network.Classify_node(args)
+            model.load_state_dict(gio.state_dict(d))
+            opt = torch.optim.Adam(model.parameters(), lr=0.01, weight_decay=0.0005)
+            gx, ge = torch.tensor(d[f"{mode}_gc_x"]), torch.tensor(d[f"{mode}_gc_edge"])
+            ty, tm = torch.tensor(d[f"{mode}_gc_train_y"]), torch.tensor(d[f"{mode}_gc_train_m"])
+            vy, vm = torch.tensor(d[f"{mode}_gc_val_y"]), torch.tensor(d[f"{mode}_gc_val_m"])
+            lf = torch.nn.NLLLoss(reduction="mean")
+            losses = [ref_run.node_train_Gc(model, gx, ge, tm, ty, lf, opt) for _ in range(3)]
+            with torch.no_grad():
+                vloss = ref_run.node_val_Gc(model, gx, ge, vm, vy, lf)
+            out[f"train_gc_{mode}_losses"] = np.array(losses + [vloss], dtype=np.float64)
+            for k, v in model.state_dict().items():
+                out[f"train_gc_{mode}_sd_{k}"] = v.detach().numpy()
     finally:
         F_.dropout = real_dropout
     np.savez_compressed(os.path.join(mg.OUT, "drivers_small.npz"), **out)
