@@ -100,6 +100,36 @@ def main():
         out[f"graph_{case}"] = np.array([loss, acc], dtype=np.float64)
     out["graph_batch_size"] = np.array(3)
 
+    # ---- the inference script's own model classes Net1 / Net2 (inference.py:72-116).  inference.py is a script (argparse and
+    # dataset downloads at module level), so the two class definitions are cut out with `ast` and executed with the names
+    # they use (GCNConv = the shim the whole fixture set uses, F, torch); the checkpoints of Classify_node / Regress_node load
+    # into them by key (inference.py:668-670), and the per-sample loop (inference.py:672-688) reads row j of one subgraph.
+    import ast
+    import torch.nn.functional as F_inf
+    src = open(os.path.join(ref_shims.REFERENCE_ROOT, "inference.py")).read()
+    ns = {"torch": torch, "F": F_inf, "GCNConv": sys.modules["torch_geometric.nn"].GCNConv}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.ClassDef) and node.name in ("Net1", "Net2"):
+            exec(compile(ast.Module(body=[node], type_ignores=[]), "inference.py", "exec"), ns)
+    d = gio.load("node_small")
+    net1 = ns["Net1"](d["x"].shape[1], int(d["hidden"]), 2, int(d["n_classes"]))
+    net1.load_state_dict(gio.state_dict(d))  # strict: identical keys
+    net1.eval()
+    subs = gio.subgraphs(d, "extra_sub")
+    with torch.no_grad():
+        out["net1_per_query"] = np.stack([net1(torch.tensor(subs[i]["x"]), torch.tensor(subs[i]["edge_index"]))[j].numpy()
+                                          for i, j in ((0, 0), (3, 1), (17, 0), (40, 2), (98, 0))])
+    out["net1_queries"] = np.array([(0, 0), (3, 1), (17, 0), (40, 2), (98, 0)])
+    d = gio.load("node_reg_small")
+    net2 = ns["Net2"](d["x"].shape[1], int(d["hidden"]), 2)
+    net2.load_state_dict(gio.state_dict(d))
+    net2.eval()
+    subs = gio.subgraphs(d, "cluster_sub")
+    with torch.no_grad():
+        out["net2_per_query"] = np.stack([net2(torch.tensor(subs[i]["x"]), torch.tensor(subs[i]["edge_index"]))[j].numpy()
+                                          for i, j in ((0, 0), (5, 1), (20, 0), (60, 1))])
+    out["net2_queries"] = np.array([(0, 0), (5, 1), (20, 0), (60, 1)])
+
     # ---- training driver: node_train_Gs_GD (run.py:177-215), three Adam steps (lr / weight decay: main.py defaults).
     # The dropout mask of network.py:33 depends on the RNG stream, so the step is recorded with F.dropout replaced by the
     # identity for the duration of the call (torch.nn.functional is patched, no reference source is touched).
