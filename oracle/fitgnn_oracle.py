@@ -9,15 +9,18 @@ PARITY PINNING
   * coarsening matrix C, partition, coarsened adjacency Ac, C·X, the subgraph lists (none / extra_node /
     cluster_node), per-subgraph split masks and the Gc assembly are pinned against the reference's OWN
     code, executed unmodified from /root/reference behind `oracle/ref_shims.py`
-    (fixtures: tests/golden/*.npz, generator: tests/golden/make_golden.py).
+    (fixtures: tests/golden/*.npz, generators: tests/golden/make_golden*.py, index: tests/golden/README.md);
+    so are the drivers of run.py (node_infer_Gs_GD / _MB, graph_infer_Gs, node_train_Gs_GD, node_train_Gc).
   * The GCNConv arithmetic lives in torch_geometric, which is not installed and not vendored by the
     reference (requirements.txt:2, unpinned; code needs PyG >= 2.1).  `gcn_norm` / `gcn_conv` restate the
     published PyG algorithm.  They are pinned on SIMPLE graphs (undirected, no self loops, no duplicates,
     isolated nodes included) against the reference tree's own implementation of the same operator —
     `normalize_adj` (Baselines/GCOND/models/mycheby.py:393-414) and the dense `GraphConvolution` layer
     (Baselines/GCOND/models/gcn.py:15-52), executed unmodified (tests/golden/make_golden_gcn_norm.py ->
-    tests/golden/gcn_norm_gcond.npz) — and checked against the hand-computed known-answer vector of
-    SURVEY.md §8c.  PyG's treatment of duplicate edges (counted twice) and of pre-existing self loops
+    tests/golden/gcn_norm_gcond.npz), on a seeded graph and, through network.py's own model classes, on every
+    subgraph of the node fixtures in all three modes (tests/golden/make_golden_independent_conv.py ->
+    independent_conv.npz: no oracle code on that path) — and checked against the hand-computed known-answer
+    vector of SURVEY.md §8c.  PyG's treatment of duplicate edges (counted twice) and of pre-existing self loops
     (replaced by one) has no executable counterpart in the reference tree: "parity unpinned" for those two
     rules only.
 """
