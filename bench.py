@@ -25,6 +25,7 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+PROFILER_RANGE = False  # --profiler-range together with --only-modes: cudaProfilerStart/Stop around the blocks' timed steps
 METRIC = "subgraph-inference nodes/sec"
 UNIT = "nodes/s"
 
@@ -62,6 +63,13 @@ def parse():
                         "mc = like p2p but ONE store to the NVLS multicast address (replicated by the NVSwitch); "
                         "auto = p2p up to 4 GPUs, ce above (measured)")
     p.add_argument("--chunks", type=int, default=1, help="N>1: chunks per rank; chunk c's all-gather overlaps chunk c+1")
+    p.add_argument("--modes", default="none_heavy_tail,cluster",
+                   help="N=1: extra blocks measured after the headline (comma separated, '' = none): none_heavy_tail = same "
+                        "graph shape with power-law subgraph sizes (hybrid fused + classic schedule); cluster = the headline "
+                        "graph with cluster_node augmentation (sharded pack, streamed forward)")
+    p.add_argument("--only-modes", action="store_true", help="skip the headline measurement (profiling the --modes blocks)")
+    p.add_argument("--mode-steps", type=int, default=0, help="timed steps of the --modes blocks (0 = min(--steps, 5))")
+    p.add_argument("--max-rows", type=int, default=1 << 22, help="rows per shard of the streamed forward (--modes blocks)")
     return p.parse_args()
 
 
@@ -151,13 +159,18 @@ def cpu_reference(args, ei, part, X, sd, k, seconds, steps=1, warmup=0):
         batches = [fo.collate(subs[b:b + 128]) for b in range(0, len(subs), 128)]
         return batches, sum(s["x"].shape[0] for s in subs)
 
+    keep = {}
+
     def run(batches):
         t = 0.0
+        outs = []
         with torch.no_grad():
             for x, e in batches:
                 t0 = time.perf_counter()
-                fo.classify_node(sd_c, x, e)
+                o = fo.classify_node(sd_c, x, e)
                 t += time.perf_counter() - t0
+                outs.append(o)
+        keep["logits"] = outs
         return t
 
     cal, cal_nodes = prep(np.arange(0, min(k, 8 * 128)))
@@ -169,9 +182,30 @@ def cpu_reference(args, ei, part, X, sd, k, seconds, steps=1, warmup=0):
         run(batches)
     times = [run(batches) for _ in range(max(1, steps))]
     t = float(np.median(times))
-    return dict(value=nodes / t, unit=UNIT, cores=cores, kind="port",
+    base = dict(value=nodes / t, unit=UNIT, cores=cores, kind="port",
                 sample=f"first {len(batches)} batches x 128 subgraphs ({nodes} nodes) of the same graph, "
-                       f"torch {torch.__version__} CPU fp32 no_grad, median of {len(times)}"), t, nodes
+                       f"torch {torch.__version__} CPU fp32 no_grad, median of {len(times)}")
+    base["_logits"] = torch.cat(keep["logits"], 0)  # rows = the first `nodes` rows of the pack order (popped by the caller)
+    return base, t, nodes
+
+
+PARITY_RTOL = 1e-3  # north_star: logits within 1e-3 relative of the reference path
+
+
+def parity_block(got, want, what):
+    """GPU logits vs the CPU arm's logits of the same rows: max |diff| relative to max(1, max |want|) (the measure the
+    parity tests use) and the element-wise bound |diff| <= rtol*|want| + 1e-2*rtol*max|want|.  Fails the run beyond 1e-3."""
+    got = got.detach().double().cpu()
+    want = want.detach().double().cpu()
+    assert got.shape == want.shape, (tuple(got.shape), tuple(want.shape))
+    scale = max(1.0, float(want.abs().max())) if want.numel() else 1.0
+    err = (got - want).abs()
+    ok = bool((err <= PARITY_RTOL * want.abs() + 1e-2 * PARITY_RTOL * scale).all())
+    blk = {"against": what, "rows": int(want.shape[0]), "max_abs_err": float(err.max()) if want.numel() else 0.0,
+           "max_rel_err": (float(err.max()) / scale) if want.numel() else 0.0, "rtol": PARITY_RTOL, "ok": ok}
+    if not ok or blk["max_rel_err"] > PARITY_RTOL:
+        raise SystemExit(f"bench: PARITY FAILURE {json.dumps(blk)}")
+    return blk
 
 
 def main_reference(args):
@@ -181,6 +215,7 @@ def main_reference(args):
     device = "cuda" if torch.cuda.is_available() else "cpu"  # generation only; nothing timed runs on the GPU
     n, F, C, ei, part, cw, k, X, sd = generate(args, device)
     base, t, nodes = cpu_reference(args, ei, part, X, sd, k, args.cpu_seconds, steps=args.steps, warmup=min(args.warmup, 1))
+    base.pop("_logits", None)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -260,6 +295,143 @@ def spmm_standalone_bench(fg, pack, H, traffic=None):
             "note": "stand-alone launch on the same pack; the default schedule fuses this aggregation into gemm0's epilogue"}
 
 
+def _time_forward(fwd, Xp, out, steps, warmup, sampler):
+    """W untimed + K timed forwards on the current stream (CUDA events), per-kernel events inside."""
+    for _ in range(max(warmup, 3)):
+        fwd(Xp, out=out)
+    torch.cuda.synchronize()
+    fwd.enable_profile(True)
+    l0 = fwd.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m0 = sampler.mark() if sampler else 0
+    if PROFILER_RANGE:
+        torch.cuda.cudart().cudaProfilerStart()
+    e0.record()
+    for _ in range(steps):
+        fwd(Xp, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    if PROFILER_RANGE:
+        torch.cuda.cudart().cudaProfilerStop()
+    m1 = sampler.mark() if sampler else 0
+    ms = e0.elapsed_time(e1) / steps
+    prof = fwd.profile_summary()
+    fwd.enable_profile(False)
+    return ms, prof, fwd.launches - l0, (sampler.summary(m0, m1) if sampler else None)
+
+
+def _kernel_table(prof, steps):
+    """per-step kernel times: profile_summary() holds the mean launch duration per part; a streamed forward launches every
+    op once per part and step, so ms is already 'per step' after summing over the parts."""
+    hbm_peak, _, _ = measured_peaks()
+    tot = max(1e-9, sum(r["ms"] for r in prof.values()))
+    out = {}
+    for name, r in prof.items():
+        out[name] = {"ms": r["ms"], "algo_GB": r["bytes"] / 1e9, "GBps": r["bytes"] / (r["ms"] * 1e-3) / 1e9,
+                     "TFLOPs": (r["flops"] / (r["ms"] * 1e-3) / 1e12) if r["flops"] else 0.0, "share": r["ms"] / tot,
+                     "launches_per_step": r["launches"] // max(1, steps)}
+    return out
+
+
+def _spmm_roofline(kernels, prefer=None):
+    """The SpMM with the largest algorithmic traffic of a mode block (the one the block's time hinges on)."""
+    hbm_peak, _, _ = measured_peaks()
+    names = [k_ for k_ in kernels if "spmm" in k_]
+    if not names:
+        return None
+    nm = prefer if prefer in kernels else max(names, key=lambda k_: kernels[k_]["algo_GB"])
+    r = kernels[nm]
+    return {"kernel": nm, "bound": "hbm", "achieved": r["GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": r["GBps"] / hbm_peak,
+            "frac_of_nominal_8000": r["GBps"] / 8000.0, "algorithmic_bytes": int(r["algo_GB"] * 1e9), "ms": r["ms"],
+            "traffic": None, "peak_source": "measured (hbm_gbs)"}
+
+
+def mode_none_heavy_tail(args, fg, device, n, e_und, F, C, sd, precision, steps, sampler):
+    """Mode 'none' on the same graph shape with heavy-tailed subgraph sizes (power law, max 500: what real coarsenings look
+    like): subgraphs <= 32 rows run the fused group-aligned schedule, the rest the classic SpMM + GEMM one."""
+    from oracle import fitgnn_oracle as fo
+    ei, part, cw, k = fg.synth.planted_partition(n, e_und, args.ratio, seed=args.seed + 1, device=device, sizes="powerlaw")
+    part = fg.synth.relabel_partition_reference_order(part)
+    X = fg.synth.features(n, F, seed=args.seed + 1, device=device)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    pack = fg.build_pack(ei, part, k, "none")
+    torch.cuda.synchronize(); build_ms = (time.perf_counter() - t0) * 1e3
+    sizes = torch.bincount(part.long(), minlength=k).float()
+    fwd = fg.StreamedForward(pack, sd, precision=precision)
+    Xp = fwd.table_features(X)
+    out = torch.empty(fwd.n_out, (C + 3) // 4 * 4, device=device)
+    ms, prof, launches, clocks = _time_forward(fwd, Xp, out, steps, args.warmup, sampler)
+    kernels = _kernel_table(prof, steps)
+    # parity: the first 64 x 128 subgraphs through the reference's batched CPU path
+    n_sub = min(k, 64 * 128)
+    subs = fo.subgraphs_from_partition(ei.cpu().numpy(), X.cpu().numpy(), part.cpu().numpy(), np.arange(n_sub))
+    sel = [np.ones(s_["x"].shape[0], dtype=bool) for s_ in subs]
+    want = fo.node_infer_batched({k_: v.cpu() for k_, v in sd.items()}, subs, sel, "node_cls", 128)
+    blk = {"workload": f"products shape ({n} nodes, {e_und} undirected edges), power-law subgraph sizes (alpha 1.8, max 500), mode none",
+           "ms_per_step": ms, "value": n / (ms * 1e-3), "unit": UNIT, "steps": steps, "subgraphs": k,
+           "subgraph_rows": {"mean": float(sizes.mean()), "p99": float(torch.quantile(sizes[: 1 << 24], 0.99)), "max": int(sizes.max()),
+                             "rows_in_subgraphs_over_32": float(sizes[sizes > 32].sum() / sizes.sum())},
+           "schedule": {kind: int(sum(f.pack.n_rows for f, k_ in zip(fwd.parts, fwd.kinds) if k_ == kind)) for kind in set(fwd.kinds)},
+           "pack": {"rows": pack.n_rows, "nnz": pack.nnz, "build_ms": build_ms},
+           "hub_rows": int(sum(f.hubs_all[1] for f in fwd.parts)), "gpu_launches": launches, "kernels": kernels,
+           "roofline_spmm": _spmm_roofline(kernels, "c_spmm1"), "clocks": clocks,
+           "parity": parity_block(out[: want.shape[0], :C], want, f"oracle CPU path, first {n_sub} subgraphs")}
+    return blk
+
+
+def mode_cluster(args, fg, device, n, F, C, ei, part, cw, k, X, sd, precision, steps, sampler):
+    """cluster_node augmentation (utils.py:190-233; the only ogbn-products row the reference ran, memory_usage.csv:42) on the
+    headline graph: N + nnz(Ac) pack rows, built as shards of --max-rows rows and streamed through the classic schedule."""
+    import scipy.sparse as sp_
+    from oracle import fitgnn_oracle as fo
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    row, col, cnt, ac_rowptr = fg.ops.project_adj(ei, part, k)
+    del cnt
+    ac_col = col.to(torch.int32)
+    members, member_ptr = fg.ops.group_by_part(part, k)
+    Xc = fg.ops.project_features(members, member_ptr, cw, X)
+    Xtab = torch.cat([X, Xc], 0)  # de-duplicated feature table: every node once + one C·X row per cluster
+    del members, member_ptr
+    torch.cuda.synchronize(); proj_ms = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    stream = fg.build_pack_stream(ei, part, k, "cluster", max_rows=args.max_rows, ac_rowptr=ac_rowptr, ac_col=ac_col)
+    torch.cuda.synchronize(); build_ms = (time.perf_counter() - t0) * 1e3
+    fwd = fg.StreamedForward(stream, sd, precision=precision)
+    Xp = fwd.table_features(Xtab)
+    out = torch.empty(fwd.n_out, (C + 3) // 4 * 4, device=device)
+    ms, prof, launches, clocks = _time_forward(fwd, Xp, out, steps, args.warmup, sampler)
+    kernels = _kernel_table(prof, steps)
+    # parity on the first 256 subgraphs: the oracle's subgraph builder needs the out-edges of their core nodes and the
+    # rows of Ac of their adjacent clusters only, so it is handed exactly those (same subgraphs, seconds instead of minutes)
+    n_sub = min(k, 256)
+    part_l = part.long()
+    src_in = part_l[ei[0]] < n_sub
+    ei_s = ei[:, src_in].cpu().numpy()
+    nb = torch.unique(part_l[ei[1][src_in]])
+    in_nb = torch.zeros(k, dtype=torch.bool, device=device)
+    in_nb[nb] = True
+    keep = in_nb[row] & in_nb[col]
+    adj = sp_.csr_matrix((np.ones(int(keep.sum()), dtype=bool), (row[keep].cpu().numpy(), col[keep].cpu().numpy())), shape=(k, k))
+    co = dict(part=part_l.cpu().numpy(), CX=Xc.cpu().numpy(), adj=adj)
+    subs = fo.build_subgraphs(ei_s, X.cpu().numpy(), np.zeros(n, dtype=np.int64), [np.arange(n)], [co], "cluster",
+                              only=set(range(n_sub)))[:n_sub]
+    sel = []
+    for s_ in subs:
+        m = np.zeros(s_["x"].shape[0], dtype=bool)
+        m[: len(s_["core"])] = True
+        sel.append(m)
+    want = fo.node_infer_batched({k_: v.cpu() for k_, v in sd.items()}, subs, sel, "node_cls", 128)
+    rows_per_sub = stream.n_rows / k
+    blk = {"workload": f"headline graph, cluster_node augmentation (utils.py:190-233), {len(stream.packs)} shards of <= {args.max_rows} rows",
+           "ms_per_step": ms, "value": n / (ms * 1e-3), "unit": UNIT, "steps": steps, "subgraphs": k,
+           "pack": {"rows": stream.n_rows, "nnz": stream.nnz, "shards": len(stream.packs), "rows_per_subgraph": rows_per_sub,
+                    "bytes": stream.nbytes(), "build_ms": build_ms, "projection_ms": proj_ms, "nnz_ac": int(row.numel())},
+           "hub_rows": int(sum(f.hubs_all[1] for f in fwd.parts)), "gpu_launches": launches, "kernels": kernels,
+           "roofline_spmm": _spmm_roofline(kernels), "roofline_spmm_last_layer": _spmm_roofline(kernels, "spmm1"), "clocks": clocks,
+           "parity": parity_block(out[: want.shape[0], :C], want, f"oracle CPU path (reference subgraph builder), first {n_sub} subgraphs")}
+    return blk
+
+
 def main_ours(args):
     import torch.distributed as dist
 
@@ -276,6 +448,18 @@ def main_ours(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
     n, F, C, ei, part, cw, k, X, sd = generate(args, device)
+    if args.only_modes:  # profiling entry: just the --modes blocks, printed as the JSON line
+        assert world == 1, "--only-modes is a single-GPU run"
+        precision = args.precision if args.precision != "auto" else os.environ.get("FITGNN_PRECISION", "bf16x3")
+        k_steps = args.mode_steps or min(args.steps, 5)
+        res = {}
+        for m in [m_ for m_ in args.modes.split(",") if m_]:
+            if m == "none_heavy_tail":
+                res[m] = mode_none_heavy_tail(args, fg, device, n, workload_shape(args.workload)[1], F, C, sd, precision, k_steps, None)
+            else:
+                res[m] = mode_cluster(args, fg, device, n, F, C, ei, part, cw, k, X, sd, precision, k_steps, None)
+        print(json.dumps({"modes": res}))
+        return
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     pack = fg.build_pack(ei, part, k, args.mode)
@@ -286,10 +470,10 @@ def main_ours(args):
     pack = fg.build_pack(ei, part, k, args.mode)
     torch.cuda.synchronize()
     pack_build_ms = (time.perf_counter() - t0) * 1e3
-    ei_keep = ei if (rank == 0 and world == 1 and not (args.no_cpu_baseline and args.no_projection)) else None
+    ei_keep = ei if (rank == 0 and world == 1 and not (args.no_cpu_baseline and args.no_projection and "cluster" not in args.modes)) else None
     del ei
     if args.mode == "cluster":
-        raise SystemExit("bench: cluster mode needs the C·X rows appended to X; use tests for that mode")
+        raise SystemExit("bench: the headline is mode none/extra; cluster_node runs as a block: --modes cluster [--only-modes]")
     n_chunks = 1 if world == 1 else args.chunks
     shard = ShardedPack(pack, world, rank, args.hidden, F, n_chunks=n_chunks, local_table=world > 1)
     precision = args.precision
@@ -611,7 +795,37 @@ def main_ours(args):
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:
         base, _, _ = cpu_reference(args, ei_keep, part, X, sd, k, args.cpu_seconds)
+        want = base.pop("_logits")
         line["cpu_baseline"] = base
+        # the headline run against the reference path: GPU logits of the rows the CPU arm computed (pack order = batch order)
+        got = fwd(Xd, packed=packed)
+        line["parity"] = parity_block(got[: want.shape[0], :C], want, "cpu_baseline logits (oracle port of run.py:49-115), same rows")
+        del got, want
+    modes = [m for m in args.modes.split(",") if m] if world == 1 else []
+    if modes:
+        # free the headline's buffers first: the cluster_node pack alone is ~15 GB, its activations ~10 GB per shard
+        fwds = fwd = shard = Xd = X_table = X_full = out = o_dev = gbuf = None
+        if e2e:
+            del X_in, X_host, o_host
+        pack = None
+        torch.cuda.empty_cache()
+        k_steps = args.mode_steps or min(args.steps, 5)
+        sampler2 = ClockSampler(local_rank)
+        sampler2.start()
+        t_wait = time.time()
+        while not sampler2.rows and time.time() - t_wait < 10.0:
+            time.sleep(0.05)
+        line["modes"] = {}
+        for m in modes:
+            if m == "none_heavy_tail":
+                line["modes"][m] = mode_none_heavy_tail(args, fg, device, n, workload_shape(args.workload)[1], F, C, sd, precision,
+                                                        k_steps, sampler2)
+            elif m == "cluster":
+                line["modes"][m] = mode_cluster(args, fg, device, n, F, C, ei_keep, part, cw, k, X, sd, precision, k_steps, sampler2)
+            else:
+                raise SystemExit(f"bench: unknown --modes entry {m!r}")
+            torch.cuda.empty_cache()
+        sampler2.stop()
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -619,6 +833,7 @@ def main_ours(args):
 
 if __name__ == "__main__":
     a = parse()
+    PROFILER_RANGE = a.profiler_range and a.only_modes
     if a.impl == "reference":
         main_reference(a)
     else:

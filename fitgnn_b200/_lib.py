@@ -24,6 +24,12 @@ class PackStruct(C.Structure):
                 ("core_rows", c_void), ("is_core", c_void), ("mask", c_void)]
 
 
+class WeightsStruct(C.Structure):
+    _fields_ = [("n_layers", C.c_int), ("in_features", C.c_int), ("hidden", C.c_int), ("n_classes", C.c_int),
+                ("conv_weight", C.POINTER(c_void)), ("conv_bias", C.POINTER(c_void)), ("lt1_weight", c_void),
+                ("lt1_bias", c_void)]
+
+
 class PlanStruct(C.Structure):
     _fields_ = [("n_rows", c_i64), ("nnz", c_i64), ("n_sub", c_i64), ("n_core", c_i64), ("n_src", c_i64),
                 ("fill_ws_bytes", c_i64), ("priv", c_i64 * 27)]
@@ -34,6 +40,8 @@ SIGNATURES = {
     "fitgnn_abi_version": (c_i32, []),
     "fitgnn_last_error": (c_i32, [C.c_char_p, c_size]),
     "fitgnn_device_info": (c_i32, [C.POINTER(c_i32), C.POINTER(c_i32)]),
+    "fitgnn_tuning_set": (c_i32, [C.c_char_p, c_i32]),
+    "fitgnn_tuning_get": (c_i32, [C.c_char_p, C.POINTER(c_i32)]),
     "fitgnn_csr_workspace_bytes": (c_size, [c_i64, c_i64]),
     "fitgnn_csr_plan": (c_i32, [c_void, c_i64, c_i64, c_void, c_size, C.POINTER(c_i64), c_void]),
     "fitgnn_csr_fill": (c_i32, [c_i64, c_void, c_size, c_void, c_void, c_void, c_void]),
@@ -45,9 +53,16 @@ SIGNATURES = {
                                     c_void, c_void, c_i64, c_void]),
     "fitgnn_spmm_symnorm_grouped": (c_i32, [c_void, c_void, c_void, c_void, c_i64, c_i32, c_void, c_i64, c_i32, c_void,
                                             c_void, c_i64, c_i32, C.c_float, c_void]),
+    "fitgnn_spmm_symnorm_blocked": (c_i32, [c_void, c_void, c_void, c_void, c_i64, c_i32, c_void, c_void, c_i64, c_void,
+                                            c_i32, c_void, c_void, c_i64, c_void]),
     "fitgnn_spmm_hubs": (c_i32, [c_void, c_void, c_i64, c_i32, c_void, c_void, c_i32, c_void]),
     "fitgnn_spmm_symnorm_hub": (c_i32, [c_void, c_void, c_void, c_void, c_i64, c_i32, c_void, c_void, c_i32, c_void,
                                         c_i64, c_void, c_void, c_i64, c_void, c_i32, c_i32, c_void]),
+    "fitgnn_spmm_symnorm_devhub": (c_i32, [c_void, c_void, c_void, c_void, c_i64, c_i32, c_void, c_void, c_i32, c_void,
+                                           c_i64, c_void, c_void, c_i64, c_void, c_void, c_i32, c_i32, c_void]),
+    "fitgnn_gcn_forward_workspace_bytes": (c_size, [C.POINTER(PackStruct), C.POINTER(WeightsStruct), c_i32]),
+    "fitgnn_gcn_forward": (c_i32, [C.POINTER(PackStruct), c_void, c_i64, C.POINTER(WeightsStruct), c_i32, c_i32, c_void,
+                                   c_i64, c_void, c_size, c_void]),
     "fitgnn_gemm_bias_act": (c_i32, [c_i32, c_void, c_void, c_i64, c_void, c_void, c_i64, c_void, c_i64, c_i32, c_i32,
                                      c_i32, c_i32, c_void, c_i64, c_void]),
     "fitgnn_gemm_bias_act_split": (c_i32, [c_i32, c_void, c_void, c_i64, c_void, c_void, c_i64, c_void, c_i64, c_i32,
@@ -110,6 +125,14 @@ def last_error() -> str:
     buf = C.create_string_buffer(512)
     lib().fitgnn_last_error(buf, 512)
     return buf.value.decode(errors="replace")
+
+
+def set_tuning(name: str, value: int) -> int:
+    """Set a kernel-tuning switch (include/fitgnn.h fitgnn_tuning_set); returns the previous value."""
+    old = C.c_int(0)
+    check(lib().fitgnn_tuning_get(name.encode(), C.byref(old)))
+    check(lib().fitgnn_tuning_set(name.encode(), int(value)))
+    return old.value
 
 
 _CODES = {-1: "EINVAL", -2: "ECUDA", -3: "ERANGE", -4: "EWS", -5: "EUNSUP"}

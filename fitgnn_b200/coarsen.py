@@ -6,7 +6,8 @@ the hot path runs on the device:
   * partition vector + C weights  <- C.indices / C.data  (subgraph_mapping utils.py:113-121)
   * Xc = C·X                      <- utils.py:161, :738, :827
   * Ac pattern                    <- coarsening_utils.py:138 / utils.py:745-746
-  * Gc assembly                   <- utils.py:705-778 (node tasks), :811-852 (graph tasks)
+  * Gc assembly                   <- utils.py:705-778 (node tasks: assemble_gc_classification),
+                                     :811-852 (graph tasks: load_graph_data / load_graph_data_batch)
 """
 from __future__ import annotations
 
@@ -125,3 +126,45 @@ def assemble_gc_classification(proj, partition: Partition, comps, edge_index, X,
             node_off += len(comp)
     return (torch.cat(feats), torch.cat(tl), torch.cat(tm), torch.cat(vl), torch.cat(vm),
             torch.stack([torch.cat(rows), torch.cat(cols)]))
+
+
+def load_graph_data(edge_index: torch.Tensor, X: torch.Tensor, y, partition: Partition, comps=None):
+    """`load_graph_data(data, C_LIST, GC_LIST, candidate)` /root/reference/utils.py:811-852 (called per graph at
+    main.py:370-381): the coarsened graph of ONE graph for the graph-level *_gc models.  Components in candidate order
+    (size-descending): a component with > 1 node contributes `C.dot(H_features)` and `GC.W.tocoo()` row/col shifted by
+    the running supernode count; a single-node component contributes its own feature row (its H.W is empty).  With the
+    partition numbered component by component (partition_from_components: a single-node component is its own cluster with
+    C weight 1) that is exactly the device projection of the whole graph: x = Xc, edge_index = the row-major pattern of
+    Ac.  Raises like the reference when the FIRST candidate is a single node (utils.py:841).
+    Returns dict(x [k, F] fp32, edge_index [2, nnz(Ac)] int64, y)."""
+    if comps is not None and len(comps) and len(comps[0]) <= 1:
+        raise Exception("The graph does not need coarsening.")
+    proj = project(edge_index, X, partition)
+    return dict(x=proj["Xc"], edge_index=torch.stack([proj["ac_row"], proj["ac_col"]]), y=y)
+
+
+def load_graph_data_batch(edge_indices, xs, partitions, device="cuda"):
+    """load_graph_data for a whole dataset in ONE projection (main.py:370-381 loops it per graph; the results are then
+    collated by colater / PyG Batch, utils.py:893-908): the graphs are concatenated into one block-diagonal graph (node
+    and cluster ids offset), projected once on the device, and returned in the collated form the *_gc models take —
+    dict(x [sum k_g, F], edge_index [2, sum nnz_g] (already offset), batch [sum k_g] graph of every supernode,
+    ptr [n_graphs + 1] supernode offsets).  Graph g's own Gc is rows ptr[g]:ptr[g+1] and the edges between them."""
+    dev = torch.device(device)
+    n_off, k_off, eis, parts, cws, ptr = 0, 0, [], [], [], [0]
+    for ei, x, p in zip(edge_indices, xs, partitions):
+        eis.append(torch.as_tensor(ei).long() + n_off)
+        parts.append(torch.as_tensor(p.part).long() + k_off)
+        cws.append(torch.as_tensor(p.cweight, dtype=torch.float64))
+        n_off += int(torch.as_tensor(x).shape[0])
+        k_off += int(p.k)
+        ptr.append(k_off)
+    X = torch.cat([torch.as_tensor(x).float().view(torch.as_tensor(x).shape[0], -1) for x in xs]).to(dev).contiguous()
+    ei = torch.cat(eis, 1).to(dev).contiguous()
+    part = torch.cat(parts).to(device=dev, dtype=torch.int32).contiguous()
+    cw = torch.cat(cws).to(dev)
+    members, member_ptr = ops.group_by_part(part, k_off)
+    Xc = ops.project_features(members, member_ptr, cw, X)
+    row, col, cnt, _ = ops.project_adj(ei, part, k_off, want_rowptr=False)
+    ptr_t = torch.tensor(ptr, device=dev)
+    batch = torch.repeat_interleave(torch.arange(len(ptr) - 1, device=dev), ptr_t[1:] - ptr_t[:-1])
+    return dict(x=Xc, edge_index=torch.stack([row, col]), batch=batch, ptr=ptr_t, cnt=cnt)

@@ -1,6 +1,7 @@
 // C-ABI plumbing: error state, version/device queries and the dense-transform dispatcher.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -13,6 +14,39 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+int sm_count() {
+  static int cached[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!cached[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && e[0]) ? atoi(e) : dflt;
+}
+static Tuning& tuning_mut() {
+  static Tuning t{env_int("FITGNN_GEMM_WS", 1),   getenv("FITGNN_HEAD_BULK") ? 0 : 1, env_int("FITGNN_AGG_WIDE", 0),
+                  env_int("FITGNN_GEMM_WIDE", 0), env_int("FITGNN_GEMM_PAIR", 1)};
+  return t;
+}
+const Tuning& tuning() { return tuning_mut(); }
+static int* tuning_field(const char* name) {
+  Tuning& t = tuning_mut();
+  if (!name) return nullptr;
+  if (!strcmp(name, "gemm_ws")) return &t.gemm_ws;
+  if (!strcmp(name, "head_bulk")) return &t.head_bulk;
+  if (!strcmp(name, "agg_wide")) return &t.agg_wide;
+  if (!strcmp(name, "gemm_wide")) return &t.gemm_wide;
+  if (!strcmp(name, "gemm_pair")) return &t.gemm_pair;
+  return nullptr;
 }
 
 int gemm_fp32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, int64_t M, int K, int N,
@@ -41,6 +75,19 @@ extern "C" int fitgnn_last_error(char* buf, size_t n) {
     buf[c] = 0;
   }
   return (int)len;
+}
+
+extern "C" int fitgnn_tuning_set(const char* name, int value) {
+  int* f = tuning_field(name);
+  FG_REQUIRE(f, FITGNN_EINVAL, "tuning_set: unknown switch '%s'", name ? name : "(null)");
+  *f = value;
+  return FITGNN_OK;
+}
+extern "C" int fitgnn_tuning_get(const char* name, int* value) {
+  int* f = tuning_field(name);
+  FG_REQUIRE(f && value, FITGNN_EINVAL, "tuning_get: unknown switch '%s'", name ? name : "(null)");
+  *value = *f;
+  return FITGNN_OK;
 }
 
 extern "C" int fitgnn_device_info(int* sm_count, int* cc) {

@@ -64,6 +64,19 @@ struct Bump {
 
 static inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 
+// SM count of the current device (queried once per device; grids are sized in multiples of it)
+int sm_count();
+// kernel-tuning switches, read from the environment ONCE per process (FITGNN_GEMM_WS, FITGNN_HEAD_BULK,
+// FITGNN_AGG_WIDE, FITGNN_GEMM_WIDE, FITGNN_GEMM_PAIR)
+struct Tuning {
+  int gemm_ws;    // 0 = force the streaming smem plan (default 1)
+  int head_bulk;  // 0 = per-thread stores in row-mapped heads (default 1)
+  int agg_wide;   // 1 = 128-column / 16-epilogue-warp tile for the fused aggregation (default 0)
+  int gemm_wide;  // 1 = same tile for small-K wide-output transforms (default 0)
+  int gemm_pair;  // 0 = no CTA pairs (default 1)
+};
+const Tuning& tuning();
+
 #ifdef __CUDACC__
 // ---- device helpers shared by the SpMM and GEMM epilogues -------------------------------------------------------
 // two fp32 -> packed bf16x2 (round to nearest even), `a` in the low half: one F2FP on the ALU pipe instead of two

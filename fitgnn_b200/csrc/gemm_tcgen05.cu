@@ -970,14 +970,12 @@ static int launch(const GatherArgs& ga, const EpiArgs& ea, const CUtensorMap& a_
     grid = (sms / n_tiles) * n_tiles;
     smem = w_bytes + (size_t)n_stages * 2 * A_PLANE_BYTES + FIXED;
   }
-  if (const char* e = getenv("FITGNN_GEMM_WS")) {  // tuning override: 0 = force streaming plan
-    if (e[0] == '0' && w_stationary) {
-      w_stationary = 0;
-      n_stages = (int)((SMEM_LIMIT - FIXED) / stage_bytes(BLOCK_N));
-      if (n_stages > 8) n_stages = 8;
-      grid = (int)(tiles < sms ? tiles : sms);
-      smem = (size_t)n_stages * stage_bytes(BLOCK_N) + FIXED;
-    }
+  if (!tuning().gemm_ws && w_stationary) {  // tuning override: force the streaming plan
+    w_stationary = 0;
+    n_stages = (int)((SMEM_LIMIT - FIXED) / stage_bytes(BLOCK_N));
+    if (n_stages > 8) n_stages = 8;
+    grid = (int)(tiles < sms ? tiles : sms);
+    smem = (size_t)n_stages * stage_bytes(BLOCK_N) + FIXED;
   }
   if (GATHER) {
     // the gather warps fill all k-blocks of a tile at once: needs the W-stationary plan with n_stages % k_blocks == 0
@@ -1038,12 +1036,7 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
   FG_REQUIRE(head == FITGNN_HEAD_IDENTITY || N <= 256, FITGNN_EUNSUP,
              "gemm_bf16x3: a fused (log-)softmax head needs N <= 256 (got %d)", N);
   FG_REQUIRE(M < (1ll << 31) - 128, FITGNN_ERANGE, "gemm_bf16x3: M exceeds the TMA coordinate range");
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    FG_CUDA(cudaGetDevice(&dev));
-    FG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int sms = sm_count();
   CUtensorMap a_hi, a_lo;
   FG_TRY(tc::make_map(&a_hi, A_hi, M, K, lda, tc::BLOCK_M));
   FG_TRY(tc::make_map(&a_lo, A_lo, M, K, lda, tc::BLOCK_M));
@@ -1052,7 +1045,7 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
                  agg_defer_scale};
   for (int p = 0; p < n_peers; ++p) ea.peers[p] = peers[p];
   if (n_peers > 0) Y = peers[0];  // alignment checks / unused fallbacks refer to a real buffer
-  if (row_map && N <= 64 && ldy == (N + 3) / 4 * 4 && getenv("FITGNN_HEAD_BULK") == nullptr) {
+  if (row_map && N <= 64 && ldy == (N + 3) / 4 * 4 && tuning().head_bulk) {
     bool aligned = ((uintptr_t)Y & 15) == 0;
     for (int p = 0; p < n_peers; ++p) aligned = aligned && ((uintptr_t)peers[p] & 15) == 0;
     ea.bulk_rows = aligned ? 1 : 0;
@@ -1061,8 +1054,7 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
     // Tuning switch: 128-column tiles with 16 epilogue warps (4 per scheduler).  The small-K aggregation epilogue is
     // instruction-bound, yet the wide variant measured SLOWER (2.05 vs 1.91 ms on the products workload: twice as many
     // tiles, each warp handling a single box per tile), so the 256-column / 8-warp tile stays the default.
-    const bool wide = getenv("FITGNN_AGG_WIDE") ? atoi(getenv("FITGNN_AGG_WIDE")) != 0 : false;
-    if (wide)
+    if (tuning().agg_wide == 1)
       return tc::launch<128, false, true, tc::EPI_WARPS_WIDE>(ga, ea, a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y,
                                                               Y_lo, ldy, sms, st);
     return tc::launch<256, false, true>(ga, ea, a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y, Y_lo, ldy, sms, st);
@@ -1075,12 +1067,11 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
   if (N <= 64) FG_TC(64);
   if (N <= 128) FG_TC(128);
   // small-K wide-output transforms are epilogue-bound as well (tuning switch; see the AGG dispatch above)
-  if (K <= 128 && head == FITGNN_HEAD_IDENTITY && getenv("FITGNN_GEMM_WIDE") && atoi(getenv("FITGNN_GEMM_WIDE")) != 0)
+  if (K <= 128 && head == FITGNN_HEAD_IDENTITY && tuning().gemm_wide)
     return tc::launch<128, false, false, tc::EPI_WARPS_WIDE>(ga, ea, a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y,
                                                              Y_lo, ldy, sms, st);
   // large-K wide transforms: CTA pairs (cta_group::2) halve the B bytes every SM has to ingest
-  if (K > 128 && head == FITGNN_HEAD_IDENTITY && !row_map && M >= 4096 &&
-      (getenv("FITGNN_GEMM_PAIR") ? atoi(getenv("FITGNN_GEMM_PAIR")) != 0 : true))
+  if (K > 128 && head == FITGNN_HEAD_IDENTITY && !row_map && M >= 4096 && tuning().gemm_pair)
     return tc::launch<256, false, false, tc::EPI_WARPS, true>(ga, ea, a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y,
                                                               Y_lo, ldy, sms, st);
   FG_TC(256);
@@ -1097,12 +1088,7 @@ int gcn_layer_fused(const int32_t* rowptr, const int32_t* col, const float* dinv
              "gcn_layer_fused: feature width must be a multiple of 4 and <= 128 (got %d)", width);
   FG_REQUIRE(N > 128, FITGNN_EUNSUP, "gcn_layer_fused: only the wide-output tile (N > 128) is instantiated");
   FG_REQUIRE(M < (1ll << 31) - 128, FITGNN_ERANGE, "gcn_layer_fused: M exceeds the coordinate range");
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    FG_CUDA(cudaGetDevice(&dev));
-    FG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int sms = sm_count();
   const int K = (width + 7) / 8 * 8;
   tc::GatherArgs ga{rowptr, col, dinv, X, src_index, out_rows, ldx, width / 4};
   CUtensorMap dummy;

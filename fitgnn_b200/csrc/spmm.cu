@@ -284,10 +284,15 @@ __global__ void __launch_bounds__(SPMM_THREADS)
 spmm_hub_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ dinv,
                 const float* __restrict__ X, int64_t ldx, int nq, const int32_t* __restrict__ src_index,
                 const float* __restrict__ bias, int act, const int32_t* __restrict__ out_rows,
-                const int32_t* __restrict__ hub_list, void* Y, void* Ylo, int64_t ldy) {
+                const int32_t* __restrict__ hub_list, int n_hub, const int32_t* __restrict__ hub_count_dev, void* Y,
+                void* Ylo, int64_t ldy) {
   __shared__ float4 part[SPMM_WARPS][NV][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t i = __ldg(hub_list + blockIdx.x);
+  // the number of hub rows is either known on the host (n_hub) or lives on the device (hub_count_dev, capped at n_hub:
+  // fitgnn_gcn_forward finds the hubs and launches this kernel without a host round trip)
+  const int n_list = hub_count_dev ? min(__ldg(hub_count_dev), n_hub) : n_hub;
+  for (int hb = blockIdx.x; hb < n_list; hb += gridDim.x) {
+  const int64_t i = __ldg(hub_list + hb);
   const int r = out_rows ? __ldg(out_rows + i) : (int)i;
   const int beg = __ldg(rowptr + r), end = __ldg(rowptr + r + 1);
   const float dr = __ldg(dinv + r);
@@ -314,6 +319,7 @@ spmm_hub_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
       epilogue<NV, SPLIT>(acc, dr, bias, act, Y, Ylo, i * ldy, q0, nq, lane);
     }
     __syncthreads();
+  }
   }
 }
 
@@ -451,6 +457,111 @@ spmm_group_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
 
 static size_t spmm_group_smem(int nq) { return (size_t)32 * nq * 16; }
 
+// ---------------------------------------------------------------------------------------------------------
+// block-staged aggregation (the "shared-memory staging" of the pack's dense neighbourhoods).
+// The pack is block-diagonal: every CSR entry of a row points into the row's own subgraph.  When rows have many
+// entries (cluster_node subgraphs: ~25 per row; heavy-tailed subgraphs: 3-4 per row) the pipelined kernel above fetches
+// every source row once per ENTRY through L1/L2 — 10^12 bytes of L2 traffic per layer-0 aggregation of the
+// ogbn-products-shaped cluster_node pack, which made that kernel the slowest of the forward (ncu/bench r2b: 155 ms at
+// 0.58 TB/s algorithmic).  Here a CTA takes a BLOCK of consecutive pack rows that is closed under adjacency (whole
+// subgraphs, blk_ptr from the host side), stages the block's source rows — one column slice of them — in shared memory
+// ONCE (cp.async, through src_index when the features are de-duplicated), and every row of the block then aggregates
+// from shared memory: HBM and L2 see each source row once per slice, the per-entry traffic is LDS.128.
+// LPR lanes own a row (16 for 64-column slices of wide rows, 32 for rows up to 128 floats); arithmetic order = CSR
+// order, fmaf chain, then dinv[r]: bit-identical to spmm_pipe_kernel.  Blocks larger than the staging capacity take the
+// same loop with loads from global memory (correct for any block, just not staged).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SB_THREADS = 256;
+
+template <int LPR, bool SPLIT>
+__global__ void __launch_bounds__(SB_THREADS)
+spmm_block_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ dinv,
+                  const float* __restrict__ X, int64_t ldx, int nq, const int32_t* __restrict__ src_index,
+                  const int32_t* __restrict__ blk_ptr, int64_t n_blk, int nq_slice, int n_slices, int rows_cap,
+                  const float* __restrict__ bias, int act, void* Y, void* Ylo, int64_t ldy) {
+  extern __shared__ __align__(16) unsigned char sb_smem[];
+  float4* xs = reinterpret_cast<float4*>(sb_smem);                                   // [rows_cap][nq_slice]
+  float* ds = reinterpret_cast<float*>(sb_smem + (size_t)rows_cap * nq_slice * 16);  // [rows_cap] dinv of the block rows
+  const uint32_t xs_u32 = (uint32_t)__cvta_generic_to_shared(xs);
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int GROUPS = SB_THREADS / LPR;  // row groups per CTA
+  const int sub = threadIdx.x & (LPR - 1);
+  const int grp = threadIdx.x / LPR;
+  const int64_t items = n_blk * n_slices;
+  for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+    const int64_t b = it / n_slices;
+    const int sl = (int)(it % n_slices);
+    const int base = __ldg(blk_ptr + b);
+    const int rows_b = __ldg(blk_ptr + b + 1) - base;
+    if (rows_b <= 0) continue;  // CTA-uniform
+    const int q0 = sl * nq_slice;                       // first float4 column of this slice
+    const int nqs = min(nq_slice, nq - q0);             // float4 columns in this slice
+    const bool staged = rows_b <= rows_cap;             // CTA-uniform
+    if (staged) {
+      for (int i = grp; i < rows_b; i += GROUPS) {
+        const int64_t srow = src_index ? (int64_t)__ldg(src_index + base + i) : (int64_t)(base + i);
+        if (sub < nqs) cp_async16(xs + (size_t)i * nq_slice + sub, X + srow * ldx + 4 * (q0 + sub));
+      }
+      for (int i = threadIdx.x; i < rows_b; i += SB_THREADS) ds[i] = __ldg(dinv + base + i);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+    }
+    // warp-uniform row loop (the groups of a warp use warp-wide collectives): a group past the block's last row idles
+    constexpr int GPW = 32 / LPR;
+    const int gw = grp % GPW;
+    for (int i0 = grp - gw; i0 < rows_b; i0 += GROUPS) {
+      const int i = i0 + gw;
+      const bool live = i < rows_b;
+      const int r = base + (live ? i : 0);
+      const int beg = live ? __ldg(rowptr + r) : 0, end = live ? __ldg(rowptr + r + 1) : 0;
+      const float dr = staged ? ds[live ? i : 0] : __ldg(dinv + r);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      // the LPR lanes of a group walk the row's entries LPR at a time; the groups of one warp run in lockstep, so the inner
+      // trip count is the warp's maximum and a group past its own count adds w = 0 times a valid row
+      for (int e0 = beg; __any_sync(FULL, e0 < end); e0 += LPR) {
+        const bool has = e0 + sub < end;
+        const int c = has ? __ldg(col + e0 + sub) - base : 0;  // block-local source row (precondition: closed block)
+        float w = 0.f;
+        int64_t goff = 0;
+        if (has) {
+          if (staged) {
+            w = ds[c];
+          } else {
+            w = __ldg(dinv + base + c);
+            goff = (src_index ? (int64_t)__ldg(src_index + base + c) : (int64_t)(base + c)) * ldx;
+          }
+        }
+        const int cnt = max(0, min(LPR, end - e0));
+        const int maxcnt = __reduce_max_sync(FULL, cnt);
+        for (int j = 0; j < maxcnt; ++j) {
+          const float wj = __shfl_sync(FULL, w, j, LPR);
+          if (staged) {
+            const int cj = __shfl_sync(FULL, c, j, LPR);
+            if (sub < nqs) fma4(acc, wj, lds128(xs_u32 + ((uint32_t)cj * (uint32_t)nq_slice + (uint32_t)sub) * 16u));
+          } else {
+            const int64_t oj = __shfl_sync(FULL, goff, j, LPR);
+            if (sub < nqs) fma4(acc, wj, ldg4(X + oj + 4 * (q0 + sub)));
+          }
+        }
+      }
+      if (live && sub < nqs) {
+        const int q = q0 + sub;
+        float4 o = make_float4(acc.x * dr, acc.y * dr, acc.z * dr, acc.w * dr);
+        if (bias) {
+          const float4 bq = ldg4(bias + 4 * q);
+          o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w;
+        }
+        if (act == FITGNN_ACT_ELU) {
+          o.x = elu1(o.x); o.y = elu1(o.y); o.z = elu1(o.z); o.w = elu1(o.w);
+        }
+        store_row4<SPLIT>(Y, Ylo, (int64_t)r * ldy + 4 * q, o);
+      }
+    }
+    if (staged) __syncthreads();  // the next item's staging overwrites xs / ds
+  }
+}
+
 // hub detection: hub_list[atomic slot] = i for output rows with degree >= hub_deg
 __global__ void spmm_find_hubs_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ out_rows,
                                       int64_t n_out, int hub_deg, int32_t* hub_list, int32_t* hub_count,
@@ -468,18 +579,19 @@ template <int NV, int LPR, bool SPLIT>
 static int launch_spmm(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X, int64_t ldx,
                        int nq, const int32_t* src_index, const float* bias, int act, const int32_t* out_rows,
                        int64_t n_out, void* Y, void* Ylo, int64_t ldy, const int32_t* hub_list, int n_hub,
-                       int hub_deg, cudaStream_t st) {
+                       int hub_deg, cudaStream_t st, const int32_t* hub_count_dev = nullptr) {
   constexpr int G = 32 / LPR;
   // long enough runs per warp for the prefetch pipeline to pay, but keep >= ~4 CTAs per SM on small inputs
   int rpw = FG_SPMM_RPW;
-  while (rpw > 1 && ceil_div(n_out, (int64_t)G * rpw * SPMM_WARPS) < 148 * 4) rpw >>= 1;
+  while (rpw > 1 && ceil_div(n_out, (int64_t)G * rpw * SPMM_WARPS) < (int64_t)sm_count() * 4) rpw >>= 1;
   const int64_t blocks = ceil_div(n_out, (int64_t)G * rpw * SPMM_WARPS);
   spmm_pipe_kernel<NV, LPR, SPLIT><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(
       rowptr, col, dinv, X, ldx, nq, src_index, bias, act, out_rows, n_out, Y, Ylo, ldy, hub_deg, rpw);
   FG_LAUNCH_CHECK();
   if (n_hub > 0) {
-    spmm_hub_kernel<4, SPLIT><<<(unsigned)n_hub, SPMM_THREADS, 0, st>>>(rowptr, col, dinv, X, ldx, nq, src_index,
-                                                                         bias, act, out_rows, hub_list, Y, Ylo, ldy);
+    const unsigned hub_blocks = hub_count_dev ? (unsigned)min((int64_t)n_hub, (int64_t)sm_count() * 4) : (unsigned)n_hub;
+    spmm_hub_kernel<4, SPLIT><<<hub_blocks, SPMM_THREADS, 0, st>>>(rowptr, col, dinv, X, ldx, nq, src_index, bias, act, out_rows,
+                                                                   hub_list, n_hub, hub_count_dev, Y, Ylo, ldy);
     FG_LAUNCH_CHECK();
   }
   return FITGNN_OK;
@@ -501,11 +613,34 @@ extern "C" int fitgnn_spmm_hubs(const int32_t* rowptr, const int32_t* out_rows, 
   return FITGNN_OK;
 }
 
-// The public entry point without a hub list: every row takes the warp-per-row path.
+static int spmm_dispatch(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X, int64_t ldx, int width,
+                         const int32_t* src_index, const float* bias, int act, const int32_t* out_rows, int64_t n_out, void* Y,
+                         void* Y_lo, int64_t ldy, const int32_t* hub_list, int n_hub, int hub_deg,
+                         const int32_t* hub_count_dev, void* stream);
+
 extern "C" int fitgnn_spmm_symnorm_hub(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X,
                                        int64_t ldx, int width, const int32_t* src_index, const float* bias, int act,
                                        const int32_t* out_rows, int64_t n_out, void* Y, void* Y_lo, int64_t ldy,
                                        const int32_t* hub_list, int n_hub, int hub_deg, void* stream) {
+  return spmm_dispatch(rowptr, col, dinv, X, ldx, width, src_index, bias, act, out_rows, n_out, Y, Y_lo, ldy, hub_list, n_hub,
+                       hub_deg, nullptr, stream);
+}
+
+// hub list whose length lives on the device (fitgnn_spmm_hubs wrote hub_count): at most hub_cap entries are used; no host sync
+extern "C" int fitgnn_spmm_symnorm_devhub(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X,
+                                          int64_t ldx, int width, const int32_t* src_index, const float* bias, int act,
+                                          const int32_t* out_rows, int64_t n_out, void* Y, void* Y_lo, int64_t ldy,
+                                          const int32_t* hub_list, const int32_t* hub_count, int hub_cap, int hub_deg,
+                                          void* stream) {
+  FG_REQUIRE(hub_list && hub_count && hub_cap > 0 && hub_deg > 0, FITGNN_EINVAL, "spmm_devhub: bad hub arguments");
+  return spmm_dispatch(rowptr, col, dinv, X, ldx, width, src_index, bias, act, out_rows, n_out, Y, Y_lo, ldy, hub_list, hub_cap,
+                       hub_deg, hub_count, stream);
+}
+
+static int spmm_dispatch(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X, int64_t ldx, int width,
+                         const int32_t* src_index, const float* bias, int act, const int32_t* out_rows, int64_t n_out, void* Y,
+                         void* Y_lo, int64_t ldy, const int32_t* hub_list, int n_hub, int hub_deg,
+                         const int32_t* hub_count_dev, void* stream) {
   FG_REQUIRE(rowptr && col && dinv && X && Y, FITGNN_EINVAL, "spmm: null pointer");
   FG_REQUIRE(n_out >= 0 && width > 0, FITGNN_EINVAL, "spmm: n_out=%lld width=%d", (long long)n_out, width);
   FG_REQUIRE(width % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, FITGNN_EUNSUP,
@@ -522,9 +657,9 @@ extern "C" int fitgnn_spmm_symnorm_hub(const int32_t* rowptr, const int32_t* col
   if (n_hub == 0) hub_deg = 0x7fffffff;
 #define FG_SPMM(NV, LPR)                                                                                          \
   return split ? launch_spmm<NV, LPR, true>(rowptr, col, dinv, X, ldx, nq, src_index, bias, act, out_rows, n_out, \
-                                            Y, Y_lo, ldy, hub_list, n_hub, hub_deg, st)                          \
+                                            Y, Y_lo, ldy, hub_list, n_hub, hub_deg, st, hub_count_dev)           \
                : launch_spmm<NV, LPR, false>(rowptr, col, dinv, X, ldx, nq, src_index, bias, act, out_rows,      \
-                                             n_out, Y, Y_lo, ldy, hub_list, n_hub, hub_deg, st)
+                                             n_out, Y, Y_lo, ldy, hub_list, n_hub, hub_deg, st, hub_count_dev)
   if (nq <= 8) { FG_SPMM(1, 8); }
   if (nq <= 16) { FG_SPMM(2, 8); }
   if (nq <= 32) { FG_SPMM(4, 8); }
@@ -539,6 +674,46 @@ extern "C" int fitgnn_spmm_symnorm(const int32_t* rowptr, const int32_t* col, co
                                    void* stream) {
   return fitgnn_spmm_symnorm_hub(rowptr, col, dinv, X, ldx, width, src_index, bias, act, out_rows, n_out, Y, Y_lo,
                                  ldy, nullptr, 0, 0, stream);
+}
+
+extern "C" int fitgnn_spmm_symnorm_blocked(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X,
+                                           int64_t ldx, int width, const int32_t* src_index, const int32_t* blk_ptr,
+                                           int64_t n_blk, const float* bias, int act, void* Y, void* Y_lo, int64_t ldy,
+                                           void* stream) {
+  FG_REQUIRE(rowptr && col && dinv && X && Y && blk_ptr, FITGNN_EINVAL, "spmm_blocked: null pointer");
+  FG_REQUIRE(n_blk >= 0 && width > 0, FITGNN_EINVAL, "spmm_blocked: n_blk=%lld width=%d", (long long)n_blk, width);
+  FG_REQUIRE(width % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, FITGNN_EUNSUP,
+             "spmm_blocked: width (%d), ldx (%lld), ldy (%lld) must be multiples of 4", width, (long long)ldx, (long long)ldy);
+  FG_REQUIRE(((uintptr_t)X % 16) == 0 && ((uintptr_t)Y % 8) == 0 && (!bias || ((uintptr_t)bias % 16) == 0), FITGNN_EUNSUP,
+             "spmm_blocked: X/bias must be 16-byte aligned");
+  FG_REQUIRE(act == FITGNN_ACT_NONE || act == FITGNN_ACT_ELU, FITGNN_EINVAL, "spmm_blocked: unknown act %d", act);
+  if (n_blk == 0) return FITGNN_OK;
+  cudaStream_t st = as_stream(stream);
+  const int nq = width / 4;
+  // rows up to 128 floats: one slice, a warp per row; wider rows: 64-column slices, a half warp per row
+  const int lpr = nq <= 32 ? 32 : 16;
+  const int nq_slice = nq <= 32 ? nq : 16;
+  const int n_slices = (int)ceil_div(nq, nq_slice);
+  constexpr size_t SMEM = 72 * 1024;  // three CTAs per SM: one stages while the others aggregate
+  const int rows_cap = (int)(SMEM / ((size_t)nq_slice * 16 + 4));
+  const int64_t items = n_blk * n_slices;
+  const int64_t max_blocks = (int64_t)sm_count() * 3;
+  const unsigned blocks = (unsigned)(items < max_blocks ? items : max_blocks);
+  const bool split = Y_lo != nullptr;
+#define FG_SB(LPR_, SPLIT_)                                                                                               \
+  do {                                                                                                                    \
+    FG_CUDA(cudaFuncSetAttribute(spmm_block_kernel<LPR_, SPLIT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM)); \
+    spmm_block_kernel<LPR_, SPLIT_><<<blocks, SB_THREADS, SMEM, st>>>(rowptr, col, dinv, X, ldx, nq, src_index, blk_ptr, n_blk, \
+                                                                      nq_slice, n_slices, rows_cap, bias, act, Y, Y_lo, ldy);  \
+  } while (0)
+  if (lpr == 32) {
+    if (split) FG_SB(32, true); else FG_SB(32, false);
+  } else {
+    if (split) FG_SB(16, true); else FG_SB(16, false);
+  }
+#undef FG_SB
+  FG_LAUNCH_CHECK();
+  return FITGNN_OK;
 }
 
 extern "C" int fitgnn_spmm_symnorm_grouped(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X,
@@ -557,7 +732,8 @@ extern "C" int fitgnn_spmm_symnorm_grouped(const int32_t* rowptr, const int32_t*
   const int nq = width / 4;
   const int64_t n_groups = ceil_div(n_rows, 32);
   const size_t smem = spmm_group_smem(nq);
-  const unsigned blocks = (unsigned)(n_groups < 148ll * 64 ? n_groups : 148ll * 64);
+  const int64_t max_blocks = (int64_t)sm_count() * 64;
+  const unsigned blocks = (unsigned)(n_groups < max_blocks ? n_groups : max_blocks);
   // pad fill: bf16 planes whose pitch leaves exactly one quad of pad columns; column `width` of the hi plane gets
   // pad_value (rounded to bf16), every other pad element zero
   const int do_pad = (fill_pad && Y_lo && ldy == width + 4 && width < 128) ? 1 : 0;

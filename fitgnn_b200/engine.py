@@ -33,8 +33,15 @@ class PackedForward:
     conv.{i}.bias, lt1.weight, lt1.bias — network.py:11-22).  `rows` selects the output rows:
     'core' (node tasks), 'mask' (graph tasks: x[mask], network.py:129) or 'all'."""
 
-    def __init__(self, pack: Pack, state_dict, head="log_softmax", rows="core", precision="fp32",
-                 with_head=True, fuse_layer0=False, fuse_aggregate="auto", align_policy="degree"):
+    def __init__(self, pack: Pack, state_dict, head="log_softmax", rows="core", precision="bf16x3",
+                 with_head=True, fuse_layer0=False, fuse_aggregate="auto", align_policy="degree", out_map=None,
+                 blocked_spmm="auto"):
+        """precision: 'bf16x3' (default: tcgen05 tensor cores on a bf16 hi/lo split of both operands, fp32 accumulate,
+        ~2^-17 relative operand error) or 'fp32' (exact-fp32 CUDA-core GEMM: the numerics anchor, explicit opt-in).
+        out_map (int32 [n_out]): output row i is written to row out_map[i] of the `out` tensor passed to __call__
+        (which then is required) — how StreamedForward lets several forwards fill one result in subgraph_list order."""
+        if precision not in ("bf16x3", "fp32"):
+            raise ValueError(f"precision={precision!r}")
         self.pack = pack
         dev = pack.device
         self.precision = ops.GEMM_BF16X3 if precision == "bf16x3" else ops.GEMM_FP32
@@ -74,6 +81,13 @@ class PackedForward:
         self.hubs_all = ops.find_hubs(pack.rowptr, None, pack.n_rows)
         self.hubs_out = self.hubs_all if self.out_rows is None else ops.find_hubs(pack.rowptr, self.out_rows, self.n_out)
         self.launches = 0
+        # block-staged SpMM (spmm.cu spmm_block_kernel) for the all-rows aggregations of packs whose rows have several
+        # entries each: the sources of a block of whole subgraphs are staged in shared memory once instead of being fetched
+        # through L2 once per entry.  'auto': from 2 entries per row on average (below that there is nothing to re-use).
+        self._blk = None
+        if blocked_spmm is True or (blocked_spmm == "auto" and pack.n_rows > 0 and pack.nnz >= 2.0 * pack.n_rows):
+            if bool((pack.sub_ptr[1:] >= pack.sub_ptr[:-1]).all()):
+                self._blk = ops.row_blocks(pack.sub_ptr, pack.n_rows)
         # fitgnn_gcn_layer_fused for layer 0 (gather warps inside the GEMM).  Correct but measured SLOWER than
         # SpMM + GEMM on B200 (5.1 ms vs 2.1 ms on the products workload: 4 gather warps per SM cannot hide the gather
         # latency that the stand-alone SpMM hides with 24 warps per SM), hence opt-in.
@@ -101,6 +115,18 @@ class PackedForward:
                     self.W0_fold = self._prep_weight(torch.cat([w0, self.b[0][:, None]], 1))
         if fuse_aggregate is True and self.apack is None:
             raise ValueError("fuse_aggregate=True but the pack / model is not eligible for the fused aggregation")
+        self.out_map = None
+        if out_map is not None:
+            assert with_head, "out_map needs the head"
+            self.out_map = out_map.to(device=dev, dtype=torch.int32).contiguous()
+            assert self.out_map.numel() == self.n_out
+        # row map of the group-aligned head: aligned row -> output row (padding rows dropped)
+        self._head_map = None
+        if self.apack is not None:
+            self._head_map = self.apack.orig_row
+            if self.out_map is not None:
+                o = self.apack.orig_row.long()
+                self._head_map = torch.where(o >= 0, self.out_map.long()[o.clamp(min=0)], o).to(torch.int32).contiguous()
 
     # -- per-kernel timing for the roofline report (CUDA events on the launching stream) ---------
     def enable_profile(self, on=True):
@@ -182,8 +208,13 @@ class PackedForward:
         hubs = self.hubs_out if last else self.hubs_all
         if pack is not None:
             hubs = self.hubs_aligned
-        self.launches += 1 + (1 if hubs[1] > 0 else 0)
         n_src_rows = X.shape[0] if src_index is not None else p.n_rows
+        if rows is None and pack is None and self._blk is not None:
+            self.launches += 1
+            return self._timed(name, lambda: ops.spmm_symnorm_blocked(p.rowptr, p.col, p.dinv, X, self._blk, width, src_index,
+                                                                      bias, act, out=out, split=split),
+                               nbytes=self._spmm_bytes(width, src_index, last, n_src_rows))
+        self.launches += 1 + (1 if hubs[1] > 0 else 0)
         return self._timed(name, lambda: ops.spmm_symnorm(p.rowptr, p.col, p.dinv, X, width, src_index, bias, act, rows,
                                                           split=split, hubs=hubs, out=out),
                            nbytes=self._spmm_bytes(width, src_index, last, n_src_rows))
@@ -279,14 +310,14 @@ class PackedForward:
         self.launches += 1
         nb = 4 * (M * self.H + self.H * self.C + self.n_out * self.C) + 4 * M
         if peer_ptrs is not None:  # rows go straight into this rank's slot of every rank's gather buffer
-            self._timed("head", lambda: ops.gemm_head_rows_peers(h, self.Wl, self.bl, ops.ACT_NONE, self.head, ap.orig_row,
+            self._timed("head", lambda: ops.gemm_head_rows_peers(h, self.Wl, self.bl, ops.ACT_NONE, self.head, self._head_map,
                                                                  peer_ptrs, ops.pad4(self.C), K=self.H, N=self.C),
                         nbytes=nb + 4 * (len(peer_ptrs) - 1) * self.n_out * self.C, flops=2 * M * self.H * self.C)
             return None
         if out is None:
             out = torch.empty(self.n_out, ops.pad4(self.C), dtype=torch.float32, device=X.device)
             view = out[:, : self.C]
-        self._timed("head", lambda: ops.gemm_head_rows(h, self.Wl, self.bl, ops.ACT_NONE, self.head, ap.orig_row, out,
+        self._timed("head", lambda: ops.gemm_head_rows(h, self.Wl, self.bl, ops.ACT_NONE, self.head, self._head_map, out,
                                                        K=self.H, N=self.C), nbytes=nb, flops=2 * M * self.H * self.C)
         return out if view is None else view
 
@@ -299,7 +330,8 @@ class PackedForward:
         `out` ([n_out, C] fp32, e.g. this rank's slot of an all-gather buffer) receives the head output in place.
         `peer_ptrs` (dist.PeerGather.slot_ptrs; fused-aggregation schedule only): the head stores its rows into that slot
         of every rank's gather buffer instead (pitch pad4(C)) and nothing is returned."""
-        assert peer_ptrs is None or self.apack is not None, "peer stores need the group-aligned schedule" 
+        assert peer_ptrs is None or self.apack is not None, "peer stores need the group-aligned schedule"
+        assert self.out_map is None or (out is not None and peer_ptrs is None), "out_map needs the `out` tensor"
         p = self.pack
         assert X.is_cuda and X.dtype == torch.float32
         n_in = (self.apack if self.apack is not None else p).n_rows if packed else p.n_src
@@ -339,6 +371,17 @@ class PackedForward:
             h = self._timed("split_head", lambda: ops.split_bf16(h), nbytes=8 * h.numel())
             self.launches += 1
         view = None
+        if self.out_map is not None:  # rows go to out[out_map]
+            if bf:
+                self.launches += 1
+                self._timed("head", lambda: ops.gemm_head_rows(h, self.Wl, self.bl, ops.ACT_NONE, self.head, self.out_map, out,
+                                                               K=self.H, N=self.C),
+                            nbytes=4 * (self.n_out * self.H + self.H * self.C + self.n_out * self.C) + 4 * self.n_out,
+                            flops=2 * self.n_out * self.H * self.C)
+            else:
+                res = self._gemm(h, self.Wl, self.bl, ops.ACT_NONE, self.head, N=self.C, K=self.H, name="head")
+                out[self.out_map.long(), : self.C] = res
+            return out
         if out is None and self.C % 4 != 0:
             # 16-byte aligned row pitch -> coalesced / TMA stores in the head epilogue; callers get the [:, :C] view
             out = torch.empty(self.n_out, ops.pad4(self.C), dtype=torch.float32, device=X.device)

@@ -14,7 +14,7 @@ from .engine import PackedForward
 from .pack import Pack
 
 
-def node_infer_Gs(state_dict, pack: Pack, X, select_mask=None, task="node_cls", precision="fp32",
+def node_infer_Gs(state_dict, pack: Pack, X, select_mask=None, task="node_cls", precision="bf16x3",
                   reference_quirks=True):
     """Whole-pack inference.  Returns (out [n_selected, C], node_ids [n_selected]) with rows in the order the
     reference concatenates them.  select_mask: global bool mask (test_mask / val_mask) or None for every node."""
@@ -28,9 +28,10 @@ def node_infer_Gs(state_dict, pack: Pack, X, select_mask=None, task="node_cls", 
     return out, ids
 
 
-def select_subgraphs(pack: Pack, sub_ids: torch.Tensor) -> Pack:
+def select_subgraphs(pack: Pack, sub_ids: torch.Tensor, return_rows: bool = False):
     """The pack restricted to the given subgraphs (kept in the given order); block-diagonal, so columns only
-    need re-basing.  Index plumbing on the device, no host loop."""
+    need re-basing.  Index plumbing on the device, no host loop.  return_rows: also return the source-pack row of every
+    row of the result (int64)."""
     dev = pack.device
     sub_ids = sub_ids.to(dev).long()
     sp = pack.sub_ptr.long()
@@ -51,14 +52,15 @@ def select_subgraphs(pack: Pack, sub_ids: torch.Tensor) -> Pack:
     col = pack.col.long()[eidx] + shift[erow]
     is_core = pack.is_core[rows]
     core_rows = torch.nonzero(is_core).view(-1)
-    return Pack(n_rows=n_rows, nnz=nnz, n_sub=sub_ids.numel(), n_core=core_rows.numel(), n_src=pack.n_src,
-                n_nodes=pack.n_nodes, mode=pack.mode, rowptr=new_rowptr.to(torch.int32), col=col.to(torch.int32),
-                dinv=pack.dinv[rows].contiguous(), gid=pack.gid[rows].contiguous(),
-                sub_ptr=new_sub_ptr.to(torch.int32), core_rows=core_rows.to(torch.int32),
-                is_core=is_core.contiguous(), mask=pack.mask[rows].contiguous(), part=pack.part)
+    sub = Pack(n_rows=n_rows, nnz=nnz, n_sub=sub_ids.numel(), n_core=core_rows.numel(), n_src=pack.n_src,
+               n_nodes=pack.n_nodes, mode=pack.mode, rowptr=new_rowptr.to(torch.int32), col=col.to(torch.int32),
+               dinv=pack.dinv[rows].contiguous(), gid=pack.gid[rows].contiguous(),
+               sub_ptr=new_sub_ptr.to(torch.int32), core_rows=core_rows.to(torch.int32),
+               is_core=is_core.contiguous(), mask=pack.mask[rows].contiguous(), part=pack.part)
+    return (sub, rows) if return_rows else sub
 
 
-def per_query(state_dict, pack: Pack, X, query_nodes: torch.Tensor, task="node_cls", precision="fp32"):
+def per_query(state_dict, pack: Pack, X, query_nodes: torch.Tensor, task="node_cls", precision="bf16x3"):
     """Outputs for the queried nodes, each computed on its own subgraph only (inference.py:672-688), all
     queried subgraphs batched into one small pack.  Returns [n_queries, C] in query order."""
     dev = pack.device
@@ -73,7 +75,7 @@ def per_query(state_dict, pack: Pack, X, query_nodes: torch.Tensor, task="node_c
     return out[lookup[q]]
 
 
-def graph_level_Gs(state_dict, pack: Pack, X, graph_of_sub: torch.Tensor, task="graph_reg", precision="fp32"):
+def graph_level_Gs(state_dict, pack: Pack, X, graph_of_sub: torch.Tensor, task="graph_reg", precision="bf16x3"):
     """Graph-level models on subgraphs (Classify_graph_gs / Regress_graph_gs, /root/reference/network.py:118-135,
     :189-204) for a whole dataset at once: `pack` holds the subgraphs of ALL graphs (subgraphs numbered graph by graph,
     as main.py:370-381 builds them), `graph_of_sub[s]` is the graph each subgraph belongs to (non-decreasing).

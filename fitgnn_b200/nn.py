@@ -20,6 +20,21 @@ from .autograd import CsrPair, gcn_conv
 from .engine import PackedForward
 from .pack import Pack
 
+# Arithmetic of the dense transforms on the inference (no-grad) path of the drop-in classes: 'bf16x3' = tcgen05 tensor
+# cores on a bf16 hi/lo split of both operands with fp32 accumulation (default), 'fp32' = exact-fp32 CUDA-core GEMM
+# (explicit opt-in: the numerics anchor).  The autograd path (training) uses the fp32 kernels.
+_PRECISION = "bf16x3"
+
+
+def set_precision(precision: str) -> str:
+    """Select the GEMM arithmetic of GCNConv / the model classes' no-grad forward; returns the previous setting."""
+    global _PRECISION
+    if precision not in ("bf16x3", "fp32"):
+        raise ValueError(f"precision={precision!r}")
+    old, _PRECISION = _PRECISION, precision
+    return old
+
+
 _CSR_CACHE: dict = {}  # id(edge_index) -> (weakref to the tensor, version, n, CsrPair)
 _CSR_CACHE_MAX = 64
 
@@ -46,13 +61,13 @@ def _csr_for(edge_index, n):
     return csr
 
 
-def _as_f32_padded(x):
-    """fp32, contiguous, row pitch a multiple of 4 floats (16-byte vector loads)."""
+def _as_f32_padded(x, align=4):
+    """fp32, contiguous, row pitch a multiple of `align` floats (16-byte vector loads; 8 for the bf16 planes' pitch)."""
     if x.dtype != torch.float32:
         x = x.float()
     f = x.shape[1]
-    if f % 4 != 0:
-        xp = torch.zeros(x.shape[0], ops.pad4(f), dtype=torch.float32, device=x.device)
+    if f % align != 0:
+        xp = torch.zeros(x.shape[0], (f + align - 1) // align * align, dtype=torch.float32, device=x.device)
         xp[:, :f] = x
         return xp
     return x.contiguous()
@@ -96,13 +111,21 @@ class GCNConv(torch.nn.Module):
         if torch.is_grad_enabled() and (x.requires_grad or self.lin.weight.requires_grad or self.bias.requires_grad):
             return gcn_conv(x, self.lin.weight, self.bias, csr, act)
         rowptr, col, dinv = csr.rowptr, csr.col, csr.dinv
+        b = self.bias.detach().contiguous()
+        if _PRECISION == "bf16x3":  # tensor cores (network.py:31 call pattern, one conv per call)
+            xp = _as_f32_padded(x.detach(), 8)
+            if self.in_channels > self.out_channels:  # transform, then aggregate the narrower rows
+                z = ops.linear_tc(xp, self.lin.weight)
+                return ops.spmm_symnorm(rowptr, col, dinv, z, bias=b, act=act)
+            # aggregate-first: Â(XW^T) = (ÂX)W^T; the SpMM emits the transform's bf16 hi/lo operand planes directly
+            a = ops.spmm_symnorm(rowptr, col, dinv, xp, split=True)
+            return ops.linear_tc(None, self.lin.weight, b, act, x_planes=a)
         xp = _as_f32_padded(x.detach())
         w = _pad_weight(self.lin.weight)
-        b = self.bias.detach().contiguous()
-        if self.in_channels > self.out_channels:  # transform, then aggregate the narrower rows
+        if self.in_channels > self.out_channels:
             z = ops.gemm_bias_act(xp, w, None, ops.ACT_NONE, K=xp.shape[1])
             return ops.spmm_symnorm(rowptr, col, dinv, z, bias=b, act=act)
-        a = ops.spmm_symnorm(rowptr, col, dinv, xp)  # aggregate-first: Â(XW^T) = (ÂX)W^T
+        a = ops.spmm_symnorm(rowptr, col, dinv, xp)
         return ops.gemm_bias_act(a, w, b, act, K=xp.shape[1])
 
     def extra_repr(self):
@@ -147,18 +170,20 @@ class _ConvStack(torch.nn.Module):
         return x
 
     def _lt1(self, x, head):
-        if torch.is_grad_enabled() and (x.requires_grad or self.lt1.weight.requires_grad):
+        if torch.is_grad_enabled() and (x.requires_grad or self.lt1.weight.requires_grad or self.lt1.bias.requires_grad):
             y = self.lt1(x)  # differentiable tail (F.linear + softmax family), network.py:34-35
             if head == ops.HEAD_LOG_SOFTMAX:
                 return torch.nn.functional.log_softmax(y, dim=1)
             return torch.nn.functional.softmax(y, dim=1) if head == ops.HEAD_SOFTMAX else y
         w = self.lt1.weight.detach().contiguous()
+        if _PRECISION == "bf16x3" and x.shape[1] % 8 == 0:
+            return ops.linear_tc(x.contiguous(), w, self.lt1.bias.detach().contiguous(), ops.ACT_NONE, head)
         return ops.gemm_bias_act(x, w, self.lt1.bias.detach().contiguous(), ops.ACT_NONE, head)
 
-    def packed(self, pack: Pack, head=None, rows=None, precision="fp32") -> PackedForward:
+    def packed(self, pack: Pack, head=None, rows=None, precision=None) -> PackedForward:
         """Fast path: the prepared whole-pack forward with this module's current parameters."""
-        return PackedForward(pack, self.state_dict(), head=head or self._head, rows=rows or self._rows,
-                             precision=precision)
+        return PackedForward(pack, self.state_dict(), head=head if head is not None else self._head,
+                             rows=rows if rows is not None else self._rows, precision=precision or _PRECISION)
 
 
 class Classify_node(_ConvStack):

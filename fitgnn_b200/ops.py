@@ -109,6 +109,39 @@ def spmm_symnorm_grouped(rowptr, col, dinv, X, width=None, src_index=None, out=N
     return out
 
 
+def row_blocks(sub_ptr, n_rows, window=64):
+    """blk_ptr for spmm_symnorm_blocked: block b = the subgraphs whose first row lies in [b*window, (b+1)*window) — unions
+    of whole subgraphs, so closed under adjacency; a block has fewer than window + (largest subgraph) rows, empty blocks
+    (inside a subgraph that spans several windows) are skipped by the kernel.  sub_ptr must be non-decreasing."""
+    sp = sub_ptr.long()
+    nb = (int(n_rows) + window - 1) // window
+    first = torch.searchsorted(sp[:-1].contiguous(), torch.arange(nb, device=sp.device) * window)
+    blk = torch.cat([sp[first.clamp(max=sp.numel() - 1)], sp[-1:]])
+    return blk.to(torch.int32).contiguous()
+
+
+def spmm_symnorm_blocked(rowptr, col, dinv, X, blk_ptr, width=None, src_index=None, bias=None, act=ACT_NONE, out=None,
+                         split=False):
+    """Y = act(Â·X[src_index] + bias) for every row, sources staged block by block in shared memory
+    (fitgnn_spmm_symnorm_blocked; blk_ptr from row_blocks).  Bit-identical to spmm_symnorm."""
+    assert X.dtype == torch.float32 and X.dim() == 2 and blk_ptr.dtype == torch.int32
+    width = X.shape[1] if width is None else width
+    n = rowptr.numel() - 1
+    if split:
+        if out is None:
+            out = (torch.empty(n, width, dtype=torch.bfloat16, device=X.device),
+                   torch.empty(n, width, dtype=torch.bfloat16, device=X.device))
+        y, ylo, ldy = out[0], out[1], out[0].stride(0)
+    else:
+        if out is None:
+            out = torch.empty(n, width, dtype=torch.float32, device=X.device)
+        y, ylo, ldy = out, None, out.stride(0)
+    check(lib().fitgnn_spmm_symnorm_blocked(ptr(rowptr), ptr(col), ptr(dinv), ptr(X), X.stride(0), width, ptr(src_index),
+                                            ptr(blk_ptr), blk_ptr.numel() - 1, ptr(bias), act, ptr(y), ptr(ylo), ldy,
+                                            stream_ptr()))
+    return out
+
+
 def find_hubs(rowptr, out_rows, n_out, hub_deg=256, cap=None):
     """Output rows with >= hub_deg entries -> (hub_list, n_hub, hub_deg).  Synchronises once (build time)."""
     cap = int(cap if cap is not None else max(1024, n_out // 64))
@@ -152,6 +185,21 @@ def gemm_bias_act(A, W, bias=None, act=ACT_NONE, head=HEAD_IDENTITY, out=None, K
                                                     w_hi.stride(0), ptr(row_scale), ptr(bias), M, K, N, act, head, ptr(out),
                                                     None, out.stride(0), stream_ptr()))
     return out
+
+
+def pad8(n):
+    return (int(n) + 7) // 8 * 8
+
+
+def linear_tc(x, weight, bias=None, act=ACT_NONE, head=HEAD_IDENTITY, x_planes=None):
+    """head(act(x · weight^T + bias)) on the tensor cores from fp32 operands: both are split into bf16 hi/lo planes
+    (K padded to 8) and run through FITGNN_GEMM_BF16X3.  x: [M, K] fp32 (ignored when x_planes — already split, pitch
+    pad8(K) — is given); weight: [N, K] fp32 as lin.weight."""
+    N, K = weight.shape
+    Kp = pad8(K)
+    w_pl = split_bf16(weight.detach().contiguous(), ldo=Kp)
+    a_pl = x_planes if x_planes is not None else split_bf16(x, cols=K, ldo=Kp)
+    return gemm_bias_act(a_pl, w_pl, bias, act, head, K=Kp, N=N, precision=GEMM_BF16X3)
 
 
 def gcn_layer_fused(rowptr, col, dinv, X, width, W, bias=None, act=ACT_NONE, src_index=None, out_rows=None, N=None,
@@ -222,6 +270,39 @@ def gemm_head_rows_peers(A, W, bias, act, head, row_map, peer_ptrs, ldy, K=None,
                                             stream_ptr()))
 
 
+def gcn_forward(pack, X, state_dict, head=HEAD_LOG_SOFTMAX, precision=GEMM_BF16X3, out=None):
+    """The whole forward over one pack in ONE C call (include/fitgnn.h fitgnn_gcn_forward): conv stack + lt1 + head on the
+    core rows, classic schedule.  pack: fitgnn_b200.pack.Pack; X: [n_src, F] fp32 feature table; state_dict: the
+    reference's keys (conv.{i}.lin.weight, conv.{i}.bias, lt1.weight, lt1.bias).  Returns [n_core, C]."""
+    from ._lib import WeightsStruct
+    dev = X.device
+    L = len({k.split(".")[1] for k in state_dict if k.startswith("conv.")})
+    f32 = dict(dtype=torch.float32, device=dev)
+    cw = [state_dict[f"conv.{i}.lin.weight"].detach().to(**f32).contiguous() for i in range(L)]
+    cb = [state_dict[f"conv.{i}.bias"].detach().to(**f32).contiguous() for i in range(L)]
+    lw = state_dict["lt1.weight"].detach().to(**f32).contiguous()
+    lb = state_dict["lt1.bias"].detach().to(**f32).contiguous()
+    F_, H, Cn = cw[0].shape[1], cw[0].shape[0], lw.shape[0]
+    assert X.dtype == torch.float32 and X.shape[0] == pack.n_src and X.shape[1] >= F_
+    if X.shape[1] % 4 != 0 or not X.is_contiguous():
+        Xp = torch.zeros(X.shape[0], pad4(X.shape[1]), **f32)
+        Xp[:, : X.shape[1]].copy_(X)
+        X = Xp
+    wptr = (C.c_void_p * L)(*[C.c_void_p(t.data_ptr()) for t in cw])
+    bptr = (C.c_void_p * L)(*[C.c_void_p(t.data_ptr()) for t in cb])
+    ws_ = WeightsStruct(L, F_, H, Cn, wptr, bptr, lw.data_ptr(), lb.data_ptr())
+    st = pack.struct()
+    nbytes = lib().fitgnn_gcn_forward_workspace_bytes(C.byref(st), C.byref(ws_), precision)
+    if nbytes == 0:
+        raise _lib.FitgnnError(f"fitgnn_gcn_forward_workspace_bytes: {_lib.last_error()}")
+    ws = _ws(nbytes, dev)
+    if out is None:
+        out = torch.empty(pack.n_core, pad4(Cn), **f32)
+    check(lib().fitgnn_gcn_forward(C.byref(st), ptr(X), X.stride(0), C.byref(ws_), head, precision, ptr(out), out.stride(0),
+                                   ptr(ws), ws.numel(), stream_ptr()))
+    return out[:, :Cn]
+
+
 def raw_tensor(ptr_value, shape, device, owner=None):
     """fp32 torch view of a raw device address (library-allocated or peer-mapped memory); `owner` is kept alive by it."""
     class _Raw:
@@ -282,13 +363,57 @@ def split_bf16(X, cols=None, ldo=None):
     return hi, lo
 
 
-def segment_pool(X, rows, seg_ptr, pool, width=None):
+def _segment_pool_raw(X, rows, seg_ptr, pool, width=None):
     width = X.shape[1] if width is None else width
     n_seg = seg_ptr.numel() - 1
     out = torch.empty(n_seg, width, dtype=torch.float32, device=X.device)
     check(lib().fitgnn_segment_pool(ptr(X), X.stride(0), width, ptr(rows), ptr(seg_ptr), n_seg, pool, ptr(out),
                                     out.stride(0), stream_ptr()))
     return out
+
+
+class _SegmentPoolFn(torch.autograd.Function):
+    """global_max_pool / global_mean_pool (network.py:93,131,164,202) with their gradients: mean spreads g / count over the
+    segment's rows, max routes g to the first row attaining the maximum (index plumbing in torch)."""
+
+    @staticmethod
+    def forward(ctx, X, rows, seg_ptr, pool):
+        Xc = X.detach().contiguous()
+        out = _segment_pool_raw(Xc, rows, seg_ptr, pool)
+        ctx.pool, ctx.n_rows = pool, X.shape[0]
+        ctx.save_for_backward(Xc, rows if rows is not None else torch.empty(0, dtype=torch.int32, device=X.device), seg_ptr, out)
+        ctx.has_rows = rows is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        X, rows, seg_ptr, out = ctx.saved_tensors
+        n_seg = seg_ptr.numel() - 1
+        counts = (seg_ptr[1:] - seg_ptr[:-1]).long()
+        R = int(seg_ptr[-1])
+        sel = rows.long() if ctx.has_rows else torch.arange(R, device=X.device)
+        seg_of = torch.repeat_interleave(torch.arange(n_seg, device=X.device), counts)
+        g = g.contiguous()
+        if ctx.pool == POOL_MEAN:
+            gr = g[seg_of] / counts[seg_of].clamp(min=1).to(g.dtype)[:, None]
+        else:
+            xr = X[sel]
+            idx = torch.arange(R, device=X.device)[:, None].expand(R, X.shape[1])
+            cand = torch.where(xr == out[seg_of], idx, torch.full_like(idx, R))
+            first = torch.full((n_seg, X.shape[1]), R, dtype=torch.long, device=X.device)
+            first.scatter_reduce_(0, seg_of[:, None].expand(R, X.shape[1]), cand, reduce="amin")
+            gr = torch.where(idx == first[seg_of], g[seg_of], torch.zeros((), dtype=g.dtype, device=g.device))
+        gx = torch.zeros(ctx.n_rows, X.shape[1], dtype=g.dtype, device=g.device)
+        gx.index_add_(0, sel, gr)
+        return gx, None, None, None
+
+
+def segment_pool(X, rows, seg_ptr, pool, width=None):
+    """Segment max / mean over the selected rows (fitgnn_segment_pool); differentiable w.r.t. X when X requires grad."""
+    if torch.is_grad_enabled() and X.requires_grad:
+        assert width is None or width == X.shape[1]
+        return _SegmentPoolFn.apply(X, rows, seg_ptr, pool)
+    return _segment_pool_raw(X, rows, seg_ptr, pool, width)
 
 
 # ----------------------------------------------------------------------------------------- projection

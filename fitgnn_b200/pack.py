@@ -176,6 +176,107 @@ def build_pack(edge_index: torch.Tensor, part: torch.Tensor, k: int, mode: str =
     return p
 
 
+def subgraph_row_counts(part: torch.Tensor, k: int, mode: str, ac_rowptr: torch.Tensor | None = None) -> torch.Tensor:
+    """Rows every subgraph will have in the pack, known before it is built: its cluster's nodes, plus (cluster mode) one
+    cluster node per adjacent cluster = the row length of Ac (utils.py:195-213).  int64 [k] on part's device."""
+    rows = torch.bincount(part.long(), minlength=k)
+    if mode == "cluster":
+        rp = ac_rowptr.long()
+        rows = rows + (rp[1:] - rp[:-1])
+    elif mode != "none":
+        raise NotImplementedError("subgraph_row_counts: mode 'extra' row counts need the frontier (build the pack)")
+    return rows
+
+
+def build_pack_range(edge_index: torch.Tensor, part: torch.Tensor, k: int, mode: str, sub_begin: int, sub_end: int,
+                     ac_rowptr: torch.Tensor | None = None, ac_col: torch.Tensor | None = None) -> Pack:
+    """The pack of subgraphs [sub_begin, sub_end) only — a shard of the reference's subgraph_list (the reference streams
+    its list through the model 128 subgraphs at a time, run.py:336; at ogbn-products scale the cluster_node pack of ALL
+    subgraphs has ~10^8 rows and more than 2^31 CSR entries, so it only exists as such shards).  Modes 'none' and
+    'cluster': every edge of a subgraph derives from an out-edge of one of its core nodes (induced core edges,
+    node<->cluster-node edges utils.py:214-222) or from Ac (utils.py:224-232), so the builder runs on the out-edges of
+    the range's core nodes; the subgraphs outside the range come out as bare core rows and are dropped.
+    Row / subgraph numbering is local to the shard; gid / part stay global."""
+    from .infer import select_subgraphs
+    if mode not in ("none", "cluster"):
+        raise NotImplementedError("build_pack_range: mode 'extra' induces edges between non-core nodes; build the whole pack")
+    part = part.to(device=edge_index.device, dtype=torch.int32).contiguous()
+    if mode == "cluster" and ac_rowptr is None:  # Ac comes from ALL edges, not from the range's
+        _, c, _, ac_rowptr = ops.project_adj(edge_index.contiguous(), part, k)
+        ac_col = c.to(torch.int32)
+    ps = part[edge_index[0]]
+    sel = (ps >= sub_begin) & (ps < sub_end)
+    ei_r = edge_index[:, sel].contiguous()
+    del ps, sel
+    full = build_pack(ei_r, part, k, mode, ac_rowptr, ac_col)
+    del ei_r
+    return select_subgraphs(full, torch.arange(sub_begin, sub_end, device=edge_index.device))
+
+
+@dataclass
+class PackStream:
+    """A pack held as consecutive shards of at most `max_rows` rows each (whole subgraphs): `packs[i]` covers subgraphs
+    [bounds[i], bounds[i+1]).  Outputs of a streamed forward are the shards' outputs concatenated = subgraph_list order."""
+    packs: list
+    bounds: list
+    mode: str
+    n_nodes: int
+    n_src: int
+
+    @property
+    def n_rows(self):
+        return sum(p.n_rows for p in self.packs)
+
+    @property
+    def nnz(self):
+        return sum(p.nnz for p in self.packs)
+
+    @property
+    def n_sub(self):
+        return self.bounds[-1]
+
+    @property
+    def n_core(self):
+        return sum(p.n_core for p in self.packs)
+
+    @property
+    def device(self):
+        return self.packs[0].device
+
+    @property
+    def core_gid(self):
+        return torch.cat([p.core_gid for p in self.packs])
+
+    def nbytes(self):
+        return sum(p.nbytes() for p in self.packs)
+
+
+def build_pack_stream(edge_index: torch.Tensor, part: torch.Tensor, k: int, mode: str = "none", max_rows: int = 1 << 22,
+                      ac_rowptr: torch.Tensor | None = None, ac_col: torch.Tensor | None = None) -> PackStream:
+    """Build the pack as shards of at most ~max_rows rows (runs of consecutive subgraphs; a single larger subgraph gets a
+    shard of its own).  With one shard this is build_pack."""
+    dev = edge_index.device
+    part = part.to(device=dev, dtype=torch.int32).contiguous()
+    if mode == "cluster" and ac_rowptr is None:
+        _, c, _, ac_rowptr = ops.project_adj(edge_index.contiguous(), part, k)
+        ac_col = c.to(torch.int32)
+        del c
+    if mode == "extra":
+        p = build_pack(edge_index, part, k, mode)
+        return PackStream([p], [0, k], mode, p.n_nodes, p.n_src)
+    csum = torch.cumsum(subgraph_row_counts(part, k, mode, ac_rowptr), 0)
+    if int(csum[-1]) <= max_rows:
+        p = build_pack(edge_index, part, k, mode, ac_rowptr, ac_col)
+        return PackStream([p], [0, k], mode, p.n_nodes, p.n_src)
+    bounds = [0]
+    while bounds[-1] < k:
+        base = int(csum[bounds[-1] - 1]) if bounds[-1] > 0 else 0
+        nxt = int(torch.searchsorted(csum, torch.tensor([base + max_rows], device=dev), right=True).item())
+        bounds.append(min(k, max(nxt, bounds[-1] + 1)))
+    packs = [build_pack_range(edge_index, part, k, mode, a, b, ac_rowptr, ac_col) for a, b in zip(bounds[:-1], bounds[1:])]
+    return PackStream(packs, bounds, mode, packs[0].n_nodes, packs[0].n_src)
+
+
 def _field(g, name, default=None):
     if isinstance(g, dict):
         return g.get(name, default)

@@ -117,20 +117,49 @@ def features(n, F, seed=0, kind="dense", device="cpu"):
     return x / x.sum(1, keepdim=True).clamp(min=1e-12)
 
 
-def planted_partition(n, n_undirected, ratio, seed=0, device="cuda", locality=256, intra_extra=0.5):
+def powerlaw_sizes(n, alpha, max_size, generator, device):
+    """Cluster sizes drawn from a truncated power law P(s) ~ s^-alpha, s in [1, max_size], cut so that they sum to n.
+    alpha = 1.8, max_size = 500 gives mean ~7, p99 ~190 — the heavy tail real coarsenings show (core size mean
+    10 / p99 178 / max 490 on the Physics-shaped graph), unlike the near-Poisson sizes of a uniform assignment."""
+    s = torch.arange(1, max_size + 1, device=device, dtype=torch.float64)
+    cdf = torch.cumsum(s ** -alpha, 0)
+    cdf = cdf / cdf[-1]
+    mean = float((s * (s ** -alpha)).sum() / (s ** -alpha).sum())
+    sizes = torch.zeros(0, dtype=torch.long, device=device)
+    while int(sizes.sum()) < n:
+        m = int(1.1 * (n - int(sizes.sum())) / mean) + 16
+        u = torch.rand(m, generator=generator, device=device, dtype=torch.float64)
+        sizes = torch.cat([sizes, torch.searchsorted(cdf, u).clamp(max=max_size - 1) + 1])
+    csum = torch.cumsum(sizes, 0)
+    k = int(torch.searchsorted(csum, torch.tensor([n], device=device)).item()) + 1
+    sizes = sizes[:k].clone()
+    sizes[-1] -= int(csum[k - 1]) - n  # the last cluster takes what is left
+    return sizes
+
+
+def planted_partition(n, n_undirected, ratio, seed=0, device="cuda", locality=256, intra_extra=0.5, sizes="uniform",
+                      alpha=1.8, max_size=500):
     """ogbn-products-shaped graph with clusters known by construction, generated on `device`.
 
-    ~ratio*n clusters with multinomial sizes (mean 1/ratio); every cluster is connected by a random tree plus
-    `intra_extra`*(size-1) extra internal edges; the remaining undirected edges join a node to a node of a
-    nearby cluster (|offset| ~ Laplace(locality) in cluster-contiguous order), which gives the coarsened graph
+    sizes='uniform': ~ratio*n clusters with multinomial sizes (mean 1/ratio); sizes='powerlaw': heavy-tailed sizes
+    (`powerlaw_sizes(n, alpha, max_size)`; `ratio` is ignored, k follows from the size law).  Every cluster is connected
+    by a random tree plus `intra_extra`*(size-1) extra internal edges; the remaining undirected edges join a node to a
+    node of a nearby cluster (|offset| ~ Laplace(locality) in cluster-contiguous order), which gives the coarsened graph
     a banded, community-like pattern.  Node ids are then shuffled so that nothing is pre-sorted.
     Returns (edge_index int64 [2, 2E] both directions, part int32 [n], cweight float64 [n], k)."""
     g = torch.Generator(device=device).manual_seed(seed)
-    k0 = max(1, int(round(ratio * n)))
-    cid = torch.sort(torch.randint(0, k0, (n,), generator=g, device=device)).values
-    uniq, part_sorted = torch.unique_consecutive(cid, return_inverse=True)
-    k = uniq.numel()
-    sizes = torch.bincount(part_sorted, minlength=k)
+    if sizes == "powerlaw":
+        sizes = powerlaw_sizes(n, alpha, max_size, g, device)
+        k = sizes.numel()
+        part_sorted = torch.repeat_interleave(torch.arange(k, device=device), sizes)
+    elif sizes == "uniform":
+        k0 = max(1, int(round(ratio * n)))
+        cid = torch.sort(torch.randint(0, k0, (n,), generator=g, device=device)).values
+        uniq, part_sorted = torch.unique_consecutive(cid, return_inverse=True)
+        k = uniq.numel()
+        sizes = torch.bincount(part_sorted, minlength=k)
+    else:
+        raise ValueError(f"sizes={sizes!r}")
     start = torch.cumsum(sizes, 0) - sizes
     pos_in = torch.arange(n, device=device) - start[part_sorted]
     # random tree inside each cluster: node -> a random earlier node of the same cluster

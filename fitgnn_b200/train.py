@@ -29,32 +29,62 @@ def forward_on_pack(model, pack: Pack, X, csr: CsrPair | None = None):
     return torch.nn.functional.log_softmax(y, dim=1) if model._head == "log_softmax" else y
 
 
-def allreduce_gradients(model, world_size: int, group=None):
-    """One all-reduce (average) of the flat gradient buffer per optimiser step."""
-    if world_size <= 1:
-        return
-    import torch.distributed as dist
+def allreduce_gradients(model, world_size: int, group=None, local_count=None):
+    """One all-reduce of the flat gradient buffer per optimiser step.
+
+    local_count given (the GD semantics of node_train_Gs_GD, run.py:199-204 — ONE loss over all selected nodes of all
+    subgraphs): every rank has back-propagated the SUM of its rows' losses; the gradients and the row counts are summed
+    over the ranks in the same buffer and divided by the global count, which is exactly the gradient of the mean loss
+    over all rows, however unevenly the rows are spread (a rank without rows contributes zeros).  Returns the global count.
+    local_count None: plain average of the ranks' gradients (each rank back-propagated its own mean loss)."""
     grads = [p.grad for p in model.parameters() if p.grad is not None]
-    flat = torch.cat([g.reshape(-1) for g in grads])
+    if world_size <= 1:
+        if local_count is not None:
+            n = float(local_count)
+            for g in grads:
+                g /= max(n, 1.0)
+            return n
+        return None
+    import torch.distributed as dist
+    extra = [] if local_count is None else [torch.as_tensor([float(local_count)], dtype=grads[0].dtype, device=grads[0].device)]
+    flat = torch.cat([g.reshape(-1) for g in grads] + extra)
     dist.all_reduce(flat, group=group)
-    flat /= world_size
+    n = None
+    if local_count is None:
+        flat /= world_size
+    else:
+        n = float(flat[-1])
+        flat = flat[:-1] / max(n, 1.0)
     off = 0
     for g in grads:
         g.copy_(flat[off: off + g.numel()].view_as(g))
         off += g.numel()
+    return n
 
 
-def train_step_Gs(model, pack: Pack, X, y, train_mask, optimizer, loss_fn=None, world_size=1, csr=None):
-    """node_train_Gs_GD (run.py:177-215): loss over every train node of the (rank-local) pack, backward, step.
-    y / train_mask are global ([N]); extra / cluster rows never contribute (Pack.split_masks)."""
+def train_step_Gs(model, pack: Pack, X, y, train_mask, optimizer, loss_fn=None, world_size=1, csr=None, group=None):
+    """node_train_Gs_GD (run.py:177-215): ONE loss over every train node of every subgraph, backward, step.
+    y / train_mask are global ([N]); extra / cluster rows never contribute (Pack.split_masks).  With world_size > 1 the
+    pack is this rank's shard: the rank back-propagates the SUM of its rows' losses and `allreduce_gradients` divides by the
+    global row count, so the step equals the single-process one for any distribution of the train rows over the ranks
+    (including ranks that hold none).  loss_fn(out_rows, targets) must be mean-reduced (default: nll_loss).
+    Returns the mean loss over all ranks' rows."""
     model.train()
     optimizer.zero_grad()
     out = forward_on_pack(model, pack, X, csr)
     rows = pack.split_masks(train_mask)
     tgt = y.to(out.device)[pack.gid.long().clamp(max=y.numel() - 1)]
     loss_fn = loss_fn or torch.nn.functional.nll_loss
-    loss = loss_fn(out[rows], tgt[rows])
-    loss.backward()
-    allreduce_gradients(model, world_size)
+    n_local = int(rows.sum())
+    if n_local > 0:
+        loss_sum = loss_fn(out[rows], tgt[rows]) * n_local
+    else:
+        loss_sum = out.sum() * 0.0  # keeps the graph (zero gradients) so that every rank joins the all-reduce
+    loss_sum.backward()
+    total = torch.stack([loss_sum.detach().float(), torch.tensor(float(n_local), device=out.device)])
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.all_reduce(total, group=group)
+    allreduce_gradients(model, world_size, group, local_count=n_local)
     optimizer.step()
-    return float(loss.detach())
+    return float(total[0] / total[1].clamp(min=1.0))

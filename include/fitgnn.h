@@ -91,6 +91,11 @@ int fitgnn_abi_version(void);
 int fitgnn_last_error(char* buf, size_t n);
 /* SM count and compute capability (major*10+minor) of the current device */
 int fitgnn_device_info(int* sm_count, int* cc);
+/* Kernel-tuning switches (A/B measurements only; results never depend on them).  Initial values come from the
+ * environment, read ONCE per process: FITGNN_GEMM_WS, FITGNN_HEAD_BULK, FITGNN_AGG_WIDE, FITGNN_GEMM_WIDE,
+ * FITGNN_GEMM_PAIR.  name = the lower-case suffix ("gemm_pair", ...). */
+int fitgnn_tuning_set(const char* name, int value);
+int fitgnn_tuning_get(const char* name, int* value);
 
 /* ------------------------------------------------------------------------------------------
  * Generic per-call CSR (drop-in GCNConv path).  Replaces gcn_norm inside GCNConv.__call__
@@ -147,6 +152,17 @@ int fitgnn_spmm_symnorm_grouped(const int32_t* rowptr, const int32_t* col, const
                                 int fill_pad, float pad_value, void* stream);
 /* fill_pad != 0 (bf16 planes with ldy == width + 4 only, ignored otherwise): the four pad columns of every row are written
  * as well — hi[:, width] = pad_value, all other pad elements 0 — so that the planes are written in whole 32-byte sectors. */
+/* The same aggregation (every row an output row) with SHARED-MEMORY STAGING of the sources: blk_ptr[n_blk + 1] (device)
+ * cuts the pack rows into consecutive blocks that are closed under adjacency (unions of whole subgraphs, e.g. from
+ * sub_ptr); a CTA stages a block's source rows (through src_index when given) in shared memory once and all rows of the
+ * block aggregate from there, so HBM / L2 see every source row once instead of once per CSR entry — the kernel for packs
+ * whose rows have many entries (cluster_node subgraphs, utils.py:190-233: ~25 per row at ogbn-products scale).  Any
+ * width (wide rows go in 64-column slices); blocks beyond the staging capacity are read from global memory.
+ * Bit-identical to fitgnn_spmm_symnorm.  Entries leaving their block are a precondition violation. */
+int fitgnn_spmm_symnorm_blocked(const int32_t* rowptr, const int32_t* col, const float* dinv,
+                                const float* X, int64_t ldx, int width, const int32_t* src_index,
+                                const int32_t* blk_ptr, int64_t n_blk, const float* bias, int act,
+                                void* Y, void* Y_lo, int64_t ldy, void* stream);
 /* Same with the high-degree rows split across a CTA: hub_list (from fitgnn_spmm_hubs) holds the output
  * indices i whose row has >= hub_deg entries; the warp-per-row pass skips them. */
 int fitgnn_spmm_hubs(const int32_t* rowptr, const int32_t* out_rows, int64_t n_out, int hub_deg,
@@ -157,6 +173,15 @@ int fitgnn_spmm_symnorm_hub(const int32_t* rowptr, const int32_t* col, const flo
                             const float* bias, int act, const int32_t* out_rows, int64_t n_out,
                             void* Y, void* Y_lo, int64_t ldy, const int32_t* hub_list, int n_hub,
                             int hub_deg, void* stream);
+
+/* Same with a hub list whose LENGTH lives on the device (hub_count as written by fitgnn_spmm_hubs; at most hub_cap entries
+ * are used, so hub_cap must bound the number of hub rows: nnz / hub_deg + 1 always does): no host synchronisation between
+ * finding the hubs and using them (fitgnn_gcn_forward, CUDA-graph capture). */
+int fitgnn_spmm_symnorm_devhub(const int32_t* rowptr, const int32_t* col, const float* dinv,
+                               const float* X, int64_t ldx, int width, const int32_t* src_index,
+                               const float* bias, int act, const int32_t* out_rows, int64_t n_out,
+                               void* Y, void* Y_lo, int64_t ldy, const int32_t* hub_list,
+                               const int32_t* hub_count /*[1] device*/, int hub_cap, int hub_deg, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Dense transform.  Replaces GCNConv.lin / lt1 (F.linear, network.py:31,34):
@@ -267,6 +292,35 @@ int fitgnn_peer_free(void* dev_ptr);
 /* fp32 [rows, cols] (ld = ldx) -> bf16 hi/lo planes [rows, ldo] (columns >= cols zero filled) */
 int fitgnn_split_bf16(const float* X, int64_t ldx, int64_t rows, int cols, void* hi, void* lo,
                       int64_t ldo, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The whole forward in one call.  Replaces, for every subgraph of the pack at once, Classify_node.forward /
+ * Regress_node.forward (network.py:29-35, :58-64; Net1 / Net2 inference.py:87-93, :110-116) as driven by
+ * node_infer_Gs_GD (run.py:59-77) and the per-query loop (inference.py:672-688):
+ *   n_layers x ( GCNConv -> ELU ) -> lt1 -> head, evaluated on the pack, returning the CORE rows (the rows the callers
+ *   read, run.py:73) in pack order: out[i, :] belongs to pack row core_rows[i] = node gid[core_rows[i]].
+ * weights: the model's parameters as the reference's state_dict holds them (conv.{i}.lin.weight [out, in] row-major,
+ *   conv.{i}.bias [out], lt1.weight [n_classes, hidden], lt1.bias) — DEVICE pointers; conv_weight / conv_bias are HOST
+ *   arrays of n_layers device pointers.
+ * X: de-duplicated feature table [n_src, ldx] fp32 (every node once, + one C·X row per cluster in cluster mode), ldx a
+ *   multiple of 4 and >= in_features rounded up to 4, padding columns zero.
+ * precision: FITGNN_GEMM_BF16X3 (tensor cores, hidden %% 8 == 0) or FITGNN_GEMM_FP32.  head: FITGNN_HEAD_*.
+ * Schedule: layer 0 transform-first on the de-duplicated rows when in_features > hidden, else aggregate-first; later
+ *   layers aggregate-first; the last layer and the head only on the core rows.  Stream-ordered, no host synchronisation,
+ *   no allocation (workspace of fitgnn_gcn_forward_workspace_bytes bytes, 256-byte aligned), CUDA-graph capturable.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct fitgnn_weights {
+  int n_layers;                     /* args.num_layers1 (network.py:11) */
+  int in_features, hidden, n_classes;
+  const float* const* conv_weight;  /* host array [n_layers] of device pointers */
+  const float* const* conv_bias;    /* host array [n_layers] of device pointers (an entry may be NULL) */
+  const float* lt1_weight;          /* device [n_classes, hidden] */
+  const float* lt1_bias;            /* device [n_classes] or NULL */
+} fitgnn_weights;
+size_t fitgnn_gcn_forward_workspace_bytes(const fitgnn_pack* pack, const fitgnn_weights* weights, int precision);
+int fitgnn_gcn_forward(const fitgnn_pack* pack, const float* X, int64_t ldx, const fitgnn_weights* weights,
+                       int head, int precision, float* out /*[n_core, ld_out]*/, int64_t ld_out, void* ws,
+                       size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Graph-level pooling.  Replaces x[mask] + torch.cat + global_max_pool / global_mean_pool

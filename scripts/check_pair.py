@@ -5,7 +5,7 @@ import fitgnn_b200 as fg
 from fitgnn_b200 import ops
 dev = torch.device("cuda:0")
 def run(A_pl, W_pl, b, pair, split, N, K):
-    os.environ["FITGNN_GEMM_PAIR"] = "1" if pair else "0"
+    fg._lib.set_tuning("gemm_pair", 1 if pair else 0)
     return ops.gemm_bias_act(A_pl, W_pl, b, ops.ACT_ELU, precision=ops.GEMM_BF16X3, N=N, K=K, split_out=split)
 ok = True
 for (M, K, N) in [(4096, 512, 512), (5000, 512, 512), (4224, 192, 384), (100003, 512, 512), (8192, 1024, 256)]:
@@ -34,7 +34,7 @@ W = torch.randn(N, K) / K ** 0.5
 W_pl = ops.split_bf16(W.to(dev)); bd = torch.zeros(N, device=dev)
 out = (torch.empty(M, N, dtype=torch.bfloat16, device=dev), torch.empty(M, N, dtype=torch.bfloat16, device=dev))
 for pair in (0, 1, 0, 1):
-    os.environ["FITGNN_GEMM_PAIR"] = str(pair)
+    fg._lib.set_tuning("gemm_pair", int(pair))
     for _ in range(2):
         ops.gemm_bias_act(A_pl, W_pl, bd, ops.ACT_ELU, precision=ops.GEMM_BF16X3, N=N, K=K, split_out=True, out=out)
     torch.cuda.synchronize()

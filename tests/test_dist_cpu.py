@@ -92,3 +92,41 @@ def test_rank_local_feature_tables(mode):
                 assert torch.equal(la.col, lb.col) and torch.equal(la.rowptr, lb.rowptr)
         if mode == "none":  # every node's features live on exactly one rank
             assert sorted(torch.cat([s.table_ids for s in local]).tolist()) == list(range(pack.n_nodes))
+
+
+def _grad_worker(rank, world, port, ret):
+    """Uneven shards (rank 1 may hold NO train rows): sum-loss backward + allreduce_gradients(local_count) on every rank
+    must equal the gradient of ONE mean loss over all rows (node_train_Gs_GD, run.py:199-204)."""
+    import torch.distributed as dist
+    from fitgnn_b200.train import allreduce_gradients
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(0)
+    X = torch.randn(50, 6, generator=g)
+    y = torch.randint(0, 3, (50,), generator=g)
+    ok = True
+    for split in (35, 50, 1):  # rows [0, split) on rank 0, the rest on rank 1 (split = 50: rank 1 holds none)
+        torch.manual_seed(1)
+        model = torch.nn.Sequential(torch.nn.Linear(6, 8), torch.nn.ELU(), torch.nn.Linear(8, 3))
+        ref = [p.detach().clone() for p in model.parameters()]
+        # single-process reference gradient: one mean loss over all 50 rows
+        loss = torch.nn.functional.nll_loss(torch.log_softmax(model(X), 1), y)
+        want = torch.autograd.grad(loss, list(model.parameters()))
+        lo, hi = (0, split) if rank == 0 else (split, 50)
+        model.zero_grad()
+        out = torch.log_softmax(model(X[lo:hi]), 1)
+        n_local = hi - lo
+        loss_sum = torch.nn.functional.nll_loss(out, y[lo:hi]) * n_local if n_local > 0 else out.sum() * 0.0
+        loss_sum.backward()
+        n = allreduce_gradients(model, world, local_count=n_local)
+        ok = ok and n == 50.0
+        for p, w, r in zip(model.parameters(), want, ref):
+            ok = ok and bool(torch.isfinite(p.grad).all()) and torch.allclose(p.grad, w, rtol=1e-5, atol=1e-6)
+    ret[rank] = ok
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2_matches_single_process_mean_loss():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ret = mp.Manager().dict()
+    mp.spawn(_grad_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]

@@ -134,7 +134,7 @@ def test_fused_gcn_layer_matches_spmm_plus_gemm(fg, n, F, H, mode):
 
 
 @pytest.mark.parametrize("M,K,N", [(4096, 512, 512), (5000, 512, 512), (4224, 192, 384), (100003, 512, 512), (8192, 1024, 256)])
-def test_cta_pair_gemm_bit_identical_to_single_cta(fg, M, K, N, monkeypatch):
+def test_cta_pair_gemm_bit_identical_to_single_cta(fg, M, K, N):
     """cta_group::2 kernel (two SMs share a 256-row MMA, each staging half of the B tile) against the single-CTA kernel
     (same MMA order per output element -> bit-identical) and fp64."""
     g = torch.Generator().manual_seed(M)
@@ -143,10 +143,13 @@ def test_cta_pair_gemm_bit_identical_to_single_cta(fg, M, K, N, monkeypatch):
     b = torch.randn(N, generator=g) * 0.1
     A_pl, W_pl, bd = fg.ops.split_bf16(A.to(DEV)), fg.ops.split_bf16(W.to(DEV)), b.to(DEV)
     for split in (False, True):
-        monkeypatch.setenv("FITGNN_GEMM_PAIR", "0")
-        y1 = fg.ops.gemm_bias_act(A_pl, W_pl, bd, fg.ops.ACT_ELU, precision=fg.ops.GEMM_BF16X3, split_out=split)
-        monkeypatch.setenv("FITGNN_GEMM_PAIR", "1")
-        y2 = fg.ops.gemm_bias_act(A_pl, W_pl, bd, fg.ops.ACT_ELU, precision=fg.ops.GEMM_BF16X3, split_out=split)
+        old = fg._lib.set_tuning("gemm_pair", 0)
+        try:
+            y1 = fg.ops.gemm_bias_act(A_pl, W_pl, bd, fg.ops.ACT_ELU, precision=fg.ops.GEMM_BF16X3, split_out=split)
+            fg._lib.set_tuning("gemm_pair", 1)
+            y2 = fg.ops.gemm_bias_act(A_pl, W_pl, bd, fg.ops.ACT_ELU, precision=fg.ops.GEMM_BF16X3, split_out=split)
+        finally:
+            fg._lib.set_tuning("gemm_pair", old)
         if split:
             assert torch.equal(y1[0], y2[0]) and torch.equal(y1[1], y2[1])
             got = y2[0].float() + y2[1].float()

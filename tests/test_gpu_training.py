@@ -119,3 +119,55 @@ def test_packed_train_step_and_pack_roundtrip(fg, tmp_path):
     torch.manual_seed(0)
     losses = [fg.train.train_step_Gs(model, again, X, y, tm, opt) for _ in range(15)]
     assert losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("task", ["graph_reg", "graph_cls"])
+def test_graph_level_models_train_every_parameter(fg, task):
+    """Regress/Classify_graph_gs and _gc under grad: the pooled tensor keeps its grad_fn (segment pooling is an autograd
+    Function), so loss.backward() reaches the conv weights — gradients against torch-CPU autograd through the oracle's
+    graph_gs_forward / graph_gc_forward (network.py:118-135, :189-204, :87-95, :158-166)."""
+    from oracle.ref_shims import Data
+    d = gio.load("graph_small")
+    n_g = int(d["n_kept"])
+    C = 1 if task == "graph_reg" else 3
+    sd = fo.init_state_dict(1, 16, C, seed=9)
+    args = argparse.Namespace(num_layers1=2, num_features=1, hidden=16, num_classes=C, layer_name="GCNConv")
+    set_gs = [[Data(x=torch.tensor(s["x"]), edge_index=torch.tensor(s["edge_index"]), mask=torch.tensor(s["mask"]))
+               for s in gio.subgraphs(d, f"g{g}_sub")] for g in range(n_g)]
+    bt = torch.tensor(d["batch_tensor"])
+    g_ = torch.Generator().manual_seed(0)
+    tgt = torch.rand(n_g, C, generator=g_)
+    # --- *_gs
+    Model = fg.Regress_graph_gs if task == "graph_reg" else fg.Classify_graph_gs
+    model = Model(args); model.load_state_dict(sd); model = model.to(DEV).eval()  # eval: dropout off, gradients on
+    pred = model(set_gs, bt)
+    assert pred.requires_grad
+    loss = ((pred - tgt.to(DEV)) ** 2).sum()
+    loss.backward()
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    want = fo.graph_gs_forward(params, [[dict(x=g.x, edge_index=g.edge_index, mask=g.mask) for g in gs] for gs in set_gs], bt, task)
+    lo = ((want - tgt) ** 2).sum()
+    lo.backward()
+    close(loss, lo)
+    for k, v in model.named_parameters():
+        assert v.grad is not None and float(v.grad.abs().max()) > 0, k
+        close(v.grad, params[k].grad, rtol=2e-3)
+    # --- *_gc
+    gx = torch.tensor(np.concatenate([d[f"g{g}_gc_x"] for g in range(n_g)])).float()
+    off, eis = 0, []
+    for g in range(n_g):
+        eis.append(d[f"g{g}_gc_edge"] + off); off += d[f"g{g}_gc_x"].shape[0]
+    ei = torch.tensor(np.concatenate(eis, 1))
+    batch = torch.tensor(d["gc_batch"])
+    ModelC = fg.Regress_graph_gc if task == "graph_reg" else fg.Classify_graph_gc
+    mc = ModelC(args); mc.load_state_dict(sd); mc = mc.to(DEV).eval()
+    pred = mc(Data(x=gx.to(DEV), edge_index=ei.to(DEV), batch=batch.to(DEV)))
+    loss = ((pred - tgt.to(DEV)) ** 2).sum()
+    loss.backward()
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    lo = ((fo.graph_gc_forward(params, gx, ei, batch, task) - tgt) ** 2).sum()
+    lo.backward()
+    close(loss, lo)
+    for k, v in mc.named_parameters():
+        assert v.grad is not None, k
+        close(v.grad, params[k].grad, rtol=2e-3)
