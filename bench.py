@@ -56,17 +56,17 @@ def parse():
                         "collated batch.x holds, built once with the pack); 'table' = node-ordered [N, F] table gathered "
                         "through gid every step; auto = packed in mode none with one chunk per rank, else table")
     p.add_argument("--seed", type=int, default=0)
-    p.add_argument("--collective", default="auto", choices=["auto", "p2p", "mc", "ce", "nccl"],
+    p.add_argument("--collective", default="auto", choices=["auto", "p2p", "ce", "nccl"],
                    help="N>1 output exchange: p2p = head kernel stores into every rank's gather buffer over NVLink "
                         "(+ a one-element all-reduce as barrier); ce = head into the local slot, copy-engine pushes to the "
                         "peers on a side stream overlapping the next step's compute; nccl = local slot, then all_gather; "
-                        "mc = like p2p but ONE store to the NVLS multicast address (replicated by the NVSwitch); "
                         "auto = p2p up to 4 GPUs, ce above (measured)")
     p.add_argument("--chunks", type=int, default=1, help="N>1: chunks per rank; chunk c's all-gather overlaps chunk c+1")
-    p.add_argument("--modes", default="none_heavy_tail,cluster",
+    p.add_argument("--modes", default="none_heavy_tail,cluster,train",
                    help="N=1: extra blocks measured after the headline (comma separated, '' = none): none_heavy_tail = same "
                         "graph shape with power-law subgraph sizes (hybrid fused + classic schedule); cluster = the headline "
-                        "graph with cluster_node augmentation (sharded pack, streamed forward)")
+                        "graph with cluster_node augmentation (sharded pack, streamed forward); train = one GD training step "
+                        "(forward + backward + Adam) on the headline pack")
     p.add_argument("--only-modes", action="store_true", help="skip the headline measurement (profiling the --modes blocks)")
     p.add_argument("--mode-steps", type=int, default=0, help="timed steps of the --modes blocks (0 = min(--steps, 5))")
     p.add_argument("--max-rows", type=int, default=1 << 22, help="rows per shard of the streamed forward (--modes blocks)")
@@ -432,6 +432,48 @@ def mode_cluster(args, fg, device, n, F, C, ei, part, cw, k, X, sd, precision, s
     return blk
 
 
+def mode_train(args, fg, device, n, F, C, ei, part, k, X, precision, steps, sampler):
+    """One optimiser step of node_train_Gs_GD (run.py:177-215) on the headline pack: forward over ALL subgraphs in train mode
+    (conv -> ELU -> Philox dropout fused), one loss over the train rows, backward on the tensor cores (dW = Gᵀ·A through
+    fitgnn_gemm_tn, dX through the NT kernel, Âᵀ through the reversed CSR), one fused Adam kernel over the flat parameters."""
+    import types
+    pack = fg.build_pack(ei, part, k, "none")
+    margs = types.SimpleNamespace(num_layers1=2, num_features=F, hidden=args.hidden, num_classes=C, layer_name="GCNConv")
+    torch.manual_seed(args.seed)
+    model = fg.Classify_node(margs).to(device)
+    opt = fg.train.FusedAdam(model.parameters(), lr=0.01, weight_decay=0.0005)  # main.py:193-194 defaults
+    g = torch.Generator(device=device).manual_seed(args.seed)
+    y = torch.randint(0, C, (n,), generator=g, device=device)
+    train_mask = torch.rand(n, generator=g, device=device) < 0.1
+    csr = fg.train.pack_csr(pack)
+    csr.transposed()
+    losses = [fg.train.train_step_Gs(model, pack, X, y, train_mask, opt, csr=csr) for _ in range(2)]
+    torch.cuda.synchronize()
+    m0 = sampler.mark() if sampler else 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        losses.append(fg.train.train_step_Gs(model, pack, X, y, train_mask, opt, csr=csr))
+    e1.record()
+    torch.cuda.synchronize()
+    m1 = sampler.mark() if sampler else 0
+    ms = e0.elapsed_time(e1) / steps
+    # the weight-gradient GEMM of the hidden layer on its own: dW[512, 512] = Gᵀ·A over all rows
+    G = torch.randn(n, args.hidden, device=device)
+    A = torch.randn(n, args.hidden, device=device)
+    t_tn, _ = _time_cuda(lambda: fg.ops.gemm_tn(G, A), reps=3, warm=1)
+    flops = 2.0 * n * args.hidden * args.hidden
+    _, tc_peak, _ = measured_peaks()
+    del G, A
+    return {"workload": "headline pack, one GD training step (forward in train mode + loss over 10% train rows + backward + Adam)",
+            "ms_per_step": ms, "value": n / (ms * 1e-3), "unit": "nodes/s per optimiser step", "steps": steps,
+            "loss_first_last": [losses[0], losses[-1]], "precision": precision,
+            "gemm_tn": {"shape": [n, args.hidden, args.hidden], "ms": t_tn, "logical_TFLOPs": flops / t_tn / 1e9,
+                        "bf16_mma_TFLOPs": 3 * flops / t_tn / 1e9, "frac_of_bf16_peak": 3 * flops / t_tn / 1e9 / tc_peak,
+                        "includes": "transposing bf16 hi/lo split of both operands + batched split-K tcgen05 GEMM + reduction"},
+            "clocks": sampler.summary(m0, m1) if sampler else None}
+
+
 def main_ours(args):
     import torch.distributed as dist
 
@@ -456,8 +498,11 @@ def main_ours(args):
         for m in [m_ for m_ in args.modes.split(",") if m_]:
             if m == "none_heavy_tail":
                 res[m] = mode_none_heavy_tail(args, fg, device, n, workload_shape(args.workload)[1], F, C, sd, precision, k_steps, None)
+            elif m == "train":
+                res[m] = mode_train(args, fg, device, n, F, C, ei, part, k, X, precision, k_steps, None)
             else:
                 res[m] = mode_cluster(args, fg, device, n, F, C, ei, part, cw, k, X, sd, precision, k_steps, None)
+            torch.cuda.empty_cache()
         print(json.dumps({"modes": res}))
         return
     torch.cuda.synchronize()
@@ -470,7 +515,7 @@ def main_ours(args):
     pack = fg.build_pack(ei, part, k, args.mode)
     torch.cuda.synchronize()
     pack_build_ms = (time.perf_counter() - t0) * 1e3
-    ei_keep = ei if (rank == 0 and world == 1 and not (args.no_cpu_baseline and args.no_projection and "cluster" not in args.modes)) else None
+    ei_keep = ei if (rank == 0 and world == 1 and not (args.no_cpu_baseline and args.no_projection and not args.modes)) else None
     del ei
     if args.mode == "cluster":
         raise SystemExit("bench: the headline is mode none/extra; cluster_node runs as a block: --modes cluster [--only-modes]")
@@ -505,7 +550,7 @@ def main_ours(args):
     if world > 1 and args.collective != "nccl" and all(f.apack is not None for f in fwds):
         try:
             from fitgnn_b200.dist import PeerGather
-            pg = PeerGather(shard, Cp, device, n_buffers=2, backend="symm" if args.collective == "mc" else "ipc")
+            pg = PeerGather(shard, Cp, device, n_buffers=2, backend="ipc")
             # measured on 8xB200 (profiles/r1_multi_gpu.md): the fused peer stores win up to 4 GPUs; at 8 the head becomes
             # NVLink-bound (7 x its slot per rank) and the overlapped copy-engine exchange is ahead; the multicast store
             # does not help an all-gather (every rank still has to RECEIVE all the other slots)
@@ -528,7 +573,7 @@ def main_ours(args):
             pg.exchange_async(b)  # completes behind the next step; the timed region ends with pg.wait on both buffers
             return pg.tensors[b]
         for c, f in enumerate(fwds):
-            f(Xin, peer_ptrs=pg.slot_ptrs(b, c, multicast=(collective == "mc")), packed=packed)
+            f(Xin, peer_ptrs=pg.slot_ptrs(b, c), packed=packed)
         pg.barrier()
         return pg.tensors[b]
 
@@ -822,6 +867,8 @@ def main_ours(args):
                                                         k_steps, sampler2)
             elif m == "cluster":
                 line["modes"][m] = mode_cluster(args, fg, device, n, F, C, ei_keep, part, cw, k, X, sd, precision, k_steps, sampler2)
+            elif m == "train":
+                line["modes"][m] = mode_train(args, fg, device, n, F, C, ei_keep, part, k, X, precision, k_steps, sampler2)
             else:
                 raise SystemExit(f"bench: unknown --modes entry {m!r}")
             torch.cuda.empty_cache()

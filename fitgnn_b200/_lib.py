@@ -54,7 +54,7 @@ SIGNATURES = {
     "fitgnn_spmm_symnorm_grouped": (c_i32, [c_void, c_void, c_void, c_void, c_i64, c_i32, c_void, c_i64, c_i32, c_void,
                                             c_void, c_i64, c_i32, C.c_float, c_void]),
     "fitgnn_spmm_symnorm_blocked": (c_i32, [c_void, c_void, c_void, c_void, c_i64, c_i32, c_void, c_void, c_i64, c_void,
-                                            c_i32, c_void, c_void, c_i64, c_void]),
+                                            c_void, c_i32, c_void, c_void, c_i64, c_void]),
     "fitgnn_spmm_hubs": (c_i32, [c_void, c_void, c_i64, c_i32, c_void, c_void, c_i32, c_void]),
     "fitgnn_spmm_symnorm_hub": (c_i32, [c_void, c_void, c_void, c_void, c_i64, c_i32, c_void, c_void, c_i32, c_void,
                                         c_i64, c_void, c_void, c_i64, c_void, c_i32, c_i32, c_void]),
@@ -63,6 +63,13 @@ SIGNATURES = {
     "fitgnn_gcn_forward_workspace_bytes": (c_size, [C.POINTER(PackStruct), C.POINTER(WeightsStruct), c_i32]),
     "fitgnn_gcn_forward": (c_i32, [C.POINTER(PackStruct), c_void, c_i64, C.POINTER(WeightsStruct), c_i32, c_i32, c_void,
                                    c_i64, c_void, c_size, c_void]),
+    "fitgnn_gemm_tn_workspace_bytes": (c_size, [c_i64, c_i32, c_i32]),
+    "fitgnn_gemm_tn": (c_i32, [c_void, c_i64, c_void, c_i64, c_i64, c_i32, c_i32, c_void, c_i64, c_void, c_size, c_void]),
+    "fitgnn_dropout": (c_i32, [c_void, c_i64, c_i64, c_i32, C.c_float, C.c_uint64, C.c_uint64, c_void, c_i64, c_void]),
+    "fitgnn_elu_dropout_backward": (c_i32, [c_void, c_i64, c_void, c_i64, c_i64, c_i32, c_i32, C.c_float, C.c_uint64,
+                                            C.c_uint64, c_void, c_i64, c_void]),
+    "fitgnn_adam_step": (c_i32, [c_void, c_void, c_void, c_void, c_i64, C.c_float, C.c_float, C.c_float, C.c_float,
+                                 C.c_float, c_i64, c_void]),
     "fitgnn_gemm_bias_act": (c_i32, [c_i32, c_void, c_void, c_i64, c_void, c_void, c_i64, c_void, c_i64, c_i32, c_i32,
                                      c_i32, c_i32, c_void, c_i64, c_void]),
     "fitgnn_gemm_bias_act_split": (c_i32, [c_i32, c_void, c_void, c_i64, c_void, c_void, c_i64, c_void, c_i64, c_i32,

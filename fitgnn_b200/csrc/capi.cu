@@ -55,7 +55,8 @@ int row_softmax(float* Y, int64_t ldy, int64_t M, int N, int head, cudaStream_t 
 int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi, const void* W_lo, int64_t ldw,
                 const float* bias, int64_t M, int K, int N, int act, int head, float* Y, void* Y_lo, int64_t ldy,
                 const uint64_t* agg_desc, const float* agg_dinv, const int32_t* row_map, float* const* peers, int n_peers,
-                const float* row_scale, int agg_defer_scale, cudaStream_t st);
+                const float* row_scale, int agg_defer_scale, cudaStream_t st, int64_t m_batch_rows = 0, int w_batch_rows = 0,
+                int64_t w_rows_total = 0);
 
 int gcn_layer_fused(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X, int64_t ldx, int width,
                     const int32_t* src_index, const int32_t* out_rows, int64_t M, const void* W_hi, const void* W_lo,

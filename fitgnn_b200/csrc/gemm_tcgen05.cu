@@ -71,6 +71,12 @@ struct EpiArgs {
   // (the next transform, through its row_scale) applies it — a row scaling commutes with the GEMM.
   const float* row_scale;
   int agg_defer_scale;
+  // Batched product (split-K of the training path's dW = G^T·A, fitgnn_gemm_tn): the M rows are n_batches stacked blocks of
+  // m_batch_rows rows (a multiple of the tile height), and the tiles of block s multiply W rows [s * w_batch_rows,
+  // s * w_batch_rows + N): Y_s = A_s · W_s^T.  m_batch_rows = 0: plain GEMM.  w_rows_total = rows of the stacked W.
+  int64_t m_batch_rows;
+  int w_batch_rows;
+  int64_t w_rows_total;
 };
 constexpr int EPI_WARP0 = 2;
 constexpr int ACC_STAGES = 2;
@@ -297,6 +303,10 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
   const int64_t tiles = m_tiles * n_tiles;
   // first row THIS CTA owns in tile t
   auto tile_row0 = [&](int64_t t) { return (t / n_tiles) * TILE_M + (int64_t)cta_rank * BLOCK_M; };
+  // batched product: first W row of the batch tile t belongs to
+  auto w_batch_off = [&](int64_t t) -> int {
+    return ea.m_batch_rows ? (int)(((t / n_tiles) * TILE_M) / ea.m_batch_rows) * ea.w_batch_rows : 0;
+  };
   // tile walk: streaming = round robin over (m, n) with n fastest; W-stationary = this CTA's n-block is fixed
   // (blockIdx % n_tiles) and it strides over the m-blocks
   const int ctas_per_n = (int)gridDim.x / n_tiles;
@@ -361,7 +371,7 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
       for (int64_t t = CTA2 ? tile_at(0) : t_first; t < tiles && !GATHER;
            t = CTA2 ? tile_at(++wi) : t + t_step) {  // gather mode: A is produced by the gather warps
         const int m0 = (int)tile_row0(t);
-        const int n0 = (int)(t % n_tiles) * BLOCK_N;
+        const int n0 = (int)(t % n_tiles) * BLOCK_N + w_batch_off(t);  // W row of this tile (epilogue columns: t % n_tiles)
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t dst = smem_base + stage * stage_bytes_rt;
@@ -931,8 +941,9 @@ static int launch(const GatherArgs& ga, const EpiArgs& ea, const CUtensorMap& a_
                   const float* bias, int64_t M, int K, int N, int act, int head, float* Y, void* Y_lo, int64_t ldy,
                   int sms, cudaStream_t st) {
   CUtensorMap w_hi, w_lo;
-  FG_TRY(make_map(&w_hi, W_hi, N, K, ldw, CTA2 ? BLOCK_N / 2 : BLOCK_N));  // a CTA of a pair stages half of the B tile
-  FG_TRY(make_map(&w_lo, W_lo, N, K, ldw, CTA2 ? BLOCK_N / 2 : BLOCK_N));
+  const int64_t w_rows = ea.m_batch_rows ? ea.w_rows_total : (int64_t)N;
+  FG_TRY(make_map(&w_hi, W_hi, w_rows, K, ldw, CTA2 ? BLOCK_N / 2 : BLOCK_N));  // a CTA of a pair stages half of the B tile
+  FG_TRY(make_map(&w_lo, W_lo, w_rows, K, ldw, CTA2 ? BLOCK_N / 2 : BLOCK_N));
   CUtensorMap y_map, y_lo_map;
   int tma_store = ((ldy * 4) % 16 == 0 && ((uintptr_t)Y & 15) == 0) ? 1 : 0;
   y_map = w_hi;  // placeholders when unused
@@ -963,7 +974,7 @@ static int launch(const GatherArgs& ga, const EpiArgs& ea, const CUtensorMap& a_
   // W-stationary plan: worth it when the resident weights fit beside >= 2 A stages and every CTA gets several m-blocks
   int w_stationary = 0;
   const size_t w_bytes = (size_t)k_blocks * 2 * BLOCK_N * BLOCK_K * 2;
-  if (w_bytes + 2 * 2 * A_PLANE_BYTES + FIXED <= SMEM_LIMIT && sms >= n_tiles && m_tiles >= 4 * (sms / n_tiles)) {
+  if (!ea.m_batch_rows && w_bytes + 2 * 2 * A_PLANE_BYTES + FIXED <= SMEM_LIMIT && sms >= n_tiles && m_tiles >= 4 * (sms / n_tiles)) {
     w_stationary = 1;
     n_stages = (int)((SMEM_LIMIT - FIXED - w_bytes) / (2 * A_PLANE_BYTES));
     if (n_stages > 8) n_stages = 8;
@@ -1026,7 +1037,11 @@ static int launch(const GatherArgs& ga, const EpiArgs& ea, const CUtensorMap& a_
 int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi, const void* W_lo, int64_t ldw,
                 const float* bias, int64_t M, int K, int N, int act, int head, float* Y, void* Y_lo, int64_t ldy,
                 const uint64_t* agg_desc, const float* agg_dinv, const int32_t* row_map, float* const* peers, int n_peers,
-                const float* row_scale, int agg_defer_scale, cudaStream_t st) {
+                const float* row_scale, int agg_defer_scale, cudaStream_t st, int64_t m_batch_rows, int w_batch_rows,
+                int64_t w_rows_total) {
+  FG_REQUIRE(m_batch_rows == 0 || (m_batch_rows % 256 == 0 && M % m_batch_rows == 0 && w_batch_rows >= N && !agg_desc &&
+                                   !row_map && head == FITGNN_HEAD_IDENTITY && w_rows_total >= (M / m_batch_rows) * w_batch_rows),
+             FITGNN_EINVAL, "gemm_bf16x3: bad batching (m_batch_rows must be a multiple of 256 dividing M)");
   FG_REQUIRE(!Y_lo || head == FITGNN_HEAD_IDENTITY, FITGNN_EUNSUP, "gemm_bf16x3: split output cannot carry a head");
   FG_REQUIRE(n_peers >= 0 && n_peers <= 8 && (n_peers == 0 || (peers && row_map)), FITGNN_EINVAL,
              "gemm_bf16x3: peer stores need 1..8 peer bases and a row map");
@@ -1042,7 +1057,7 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
   FG_TRY(tc::make_map(&a_lo, A_lo, M, K, lda, tc::BLOCK_M));
   const tc::GatherArgs ga{};
   tc::EpiArgs ea{reinterpret_cast<const unsigned long long*>(agg_desc), agg_dinv, row_map, {}, n_peers, 0, row_scale,
-                 agg_defer_scale};
+                 agg_defer_scale, m_batch_rows, w_batch_rows, w_rows_total};
   for (int p = 0; p < n_peers; ++p) ea.peers[p] = peers[p];
   if (n_peers > 0) Y = peers[0];  // alignment checks / unused fallbacks refer to a real buffer
   if (row_map && N <= 64 && ldy == (N + 3) / 4 * 4 && tuning().head_bulk) {
@@ -1093,7 +1108,7 @@ int gcn_layer_fused(const int32_t* rowptr, const int32_t* col, const float* dinv
   tc::GatherArgs ga{rowptr, col, dinv, X, src_index, out_rows, ldx, width / 4};
   CUtensorMap dummy;
   FG_TRY(tc::make_map(&dummy, W_hi, N, K, ldw, 16));  // placeholder for the unused A maps
-  const tc::EpiArgs ea{nullptr, nullptr, nullptr, {}, 0, 0, nullptr, 0};
+  const tc::EpiArgs ea{nullptr, nullptr, nullptr, {}, 0, 0, nullptr, 0, 0, 0, 0};
   return tc::launch<256, true, false>(ga, ea, dummy, dummy, W_hi, W_lo, ldw, bias, M, K, N, act, FITGNN_HEAD_IDENTITY, Y,
                                       Y_lo, ldy, sms, st);
 }

@@ -472,21 +472,135 @@ static size_t spmm_group_smem(int nq) { return (size_t)32 * nq * 16; }
 // same loop with loads from global memory (correct for any block, just not staged).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int SB_THREADS = 256;
+constexpr int SB_LPR = 8;  // lanes per row: a warp works on 4 rows at once (4 independent accumulation chains)
+#ifndef FG_SB_CTAS
+#define FG_SB_CTAS 4       // resident CTAs per SM the kernel is compiled for (register cap) and sized for (shared memory)
+#endif
+constexpr size_t SB_SMEM = (FG_SB_CTAS == 4 ? 56 : 72) * 1024;
 
-template <int LPR, bool SPLIT>
-__global__ void __launch_bounds__(SB_THREADS)
-spmm_block_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ dinv,
-                  const float* __restrict__ X, int64_t ldx, int nq, const int32_t* __restrict__ src_index,
-                  const int32_t* __restrict__ blk_ptr, int64_t n_blk, int nq_slice, int n_slices, int rows_cap,
-                  const float* __restrict__ bias, int act, void* Y, void* Ylo, int64_t ldy) {
-  extern __shared__ __align__(16) unsigned char sb_smem[];
-  float4* xs = reinterpret_cast<float4*>(sb_smem);                                   // [rows_cap][nq_slice]
-  float* ds = reinterpret_cast<float*>(sb_smem + (size_t)rows_cap * nq_slice * 16);  // [rows_cap] dinv of the block rows
-  const uint32_t xs_u32 = (uint32_t)__cvta_generic_to_shared(xs);
+// shared memory a staged pass needs: features [rows][wq float4], dinv [rows], row ranges [rows + 1], column indices (u16)
+__host__ __device__ inline size_t sb_bytes(int rows, int wq, int n_ent) {
+  return (size_t)rows * wq * 16 + 128 /* slack: lanes past wq read (and drop) up to 7 float4 beyond the last row */ +
+         (size_t)rows * 4 + (size_t)(rows + 1) * 4 + 16 + (((size_t)n_ent * 2 + 15) & ~(size_t)15);
+}
+
+// One staged pass over float4 columns [qa, qa + wq) of the rows [base, base + rows_b): stage features, dinv, row ranges and
+// the block-local column indices in shared memory, aggregate every row from there, store.  PV = float4 per lane (wq <= 8 * PV).
+template <int PV, bool SPLIT>
+__device__ __forceinline__ void sb_staged_pass(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                               const float* __restrict__ dinv, const float* __restrict__ X, int64_t ldx,
+                                               const int32_t* __restrict__ src_index, const int32_t* __restrict__ row_order,
+                                               int base, int rows_b, int ebase, int n_ent, int qa, int wq,
+                                               const float* __restrict__ bias, int act, void* Y, void* Ylo, int64_t ldy,
+                                               unsigned char* smem) {
+  constexpr int LPR = SB_LPR;
   constexpr unsigned FULL = 0xffffffffu;
-  constexpr int GROUPS = SB_THREADS / LPR;  // row groups per CTA
+  constexpr int GROUPS = SB_THREADS / LPR;
+  constexpr int GPW = 32 / LPR;
+  float4* xs = reinterpret_cast<float4*>(smem);  // [rows_b][wq]
+  float* ds = reinterpret_cast<float*>(smem + (size_t)rows_b * wq * 16 + 128);
+  int32_t* rp = reinterpret_cast<int32_t*>(ds + rows_b);  // [rows_b + 1] row ranges relative to ebase
+  uint16_t* cs = reinterpret_cast<uint16_t*>(rp + rows_b + 1);
+  cs = reinterpret_cast<uint16_t*>(((uintptr_t)cs + 15) & ~(uintptr_t)15);
+  const uint32_t xs_u32 = (uint32_t)__cvta_generic_to_shared(xs);
+  const uint32_t cs_u32 = (uint32_t)__cvta_generic_to_shared(cs);
+  const uint32_t ds_u32 = (uint32_t)__cvta_generic_to_shared(ds);
   const int sub = threadIdx.x & (LPR - 1);
   const int grp = threadIdx.x / LPR;
+  const int gw = grp % GPW;
+  for (int i = grp; i < rows_b; i += GROUPS) {
+    const int64_t srow = src_index ? (int64_t)__ldg(src_index + base + i) : (int64_t)(base + i);
+    const float* xr = X + srow * ldx + 4 * qa;
+#pragma unroll
+    for (int v = 0; v < PV; ++v) {
+      const int q = sub + LPR * v;
+      if (q < wq) cp_async16(xs + (size_t)i * wq + q, xr + 4 * q);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = threadIdx.x; i < rows_b; i += SB_THREADS) ds[i] = __ldg(dinv + base + i);
+  for (int i = threadIdx.x; i <= rows_b; i += SB_THREADS) rp[i] = __ldg(rowptr + base + i) - ebase;
+  for (int e = threadIdx.x; e < n_ent; e += SB_THREADS) cs[e] = (uint16_t)(__ldg(col + ebase + e) - base);  // closed block
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  // warp-uniform loop over the block's rows in `row_order` (degree-sorted inside the block, so the 4 rows a warp works on
+  // have similar lengths); a group past the last row idles
+  for (int k0 = grp - gw; k0 < rows_b; k0 += GROUPS) {
+    const int k = k0 + gw;
+    const bool live = k < rows_b;
+    const int i = live ? (row_order ? __ldg(row_order + base + k) - base : k) : 0;
+    const int beg = live ? rp[i] : 0, end = live ? rp[i + 1] : 0;
+    const float dr = ds[i];
+    const int len = end - beg;
+    const int maxlen = __reduce_max_sync(FULL, len);
+    float4 acc[PV];
+#pragma unroll
+    for (int v = 0; v < PV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // every lane of a group reads the same (index, weight) from shared memory (broadcast); past the row's end the entry is
+    // (row 0, weight 0): a valid, finite row times zero
+    for (int j = 0; j < maxlen; j += 2) {
+      const bool on0 = j < len, on1 = j + 1 < len;
+      uint32_t c0 = 0, c1 = 0;
+      float w0 = 0.f, w1 = 0.f;
+      if (on0) {
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(c0) : "r"(cs_u32 + 2u * (uint32_t)(beg + j)));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w0) : "r"(ds_u32 + 4u * c0));
+      }
+      if (on1) {
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(c1) : "r"(cs_u32 + 2u * (uint32_t)(beg + j + 1)));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w1) : "r"(ds_u32 + 4u * c1));
+      }
+      const uint32_t a0 = xs_u32 + (c0 * (uint32_t)wq + (uint32_t)sub) * 16u;
+      const uint32_t a1 = xs_u32 + (c1 * (uint32_t)wq + (uint32_t)sub) * 16u;
+      float4 x0[PV], x1[PV];
+#pragma unroll
+      for (int v = 0; v < PV; ++v) {
+        x0[v] = lds128(a0 + (uint32_t)(LPR * v) * 16u);
+        x1[v] = lds128(a1 + (uint32_t)(LPR * v) * 16u);
+      }
+#pragma unroll
+      for (int v = 0; v < PV; ++v) fma4(acc[v], w0, x0[v]);
+#pragma unroll
+      for (int v = 0; v < PV; ++v) fma4(acc[v], w1, x1[v]);
+    }
+    if (live) {
+      const int r = base + i;
+#pragma unroll
+      for (int v = 0; v < PV; ++v) {
+        const int qs = sub + LPR * v;
+        if (qs < wq) {
+          const int q = qa + qs;
+          float4 o = make_float4(acc[v].x * dr, acc[v].y * dr, acc[v].z * dr, acc[v].w * dr);
+          if (bias) {
+            const float4 bq = ldg4(bias + 4 * q);
+            o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w;
+          }
+          if (act == FITGNN_ACT_ELU) {
+            o.x = elu1(o.x); o.y = elu1(o.y); o.z = elu1(o.z); o.w = elu1(o.w);
+          }
+          store_row4<SPLIT>(Y, Ylo, (int64_t)r * ldy + 4 * q, o);
+        }
+      }
+    }
+  }
+  __syncthreads();  // the next pass / item overwrites the staging area
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(SB_THREADS, FG_SB_CTAS)
+spmm_block_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ dinv,
+                  const float* __restrict__ X, int64_t ldx, int nq, const int32_t* __restrict__ src_index,
+                  const int32_t* __restrict__ blk_ptr, int64_t n_blk, const int32_t* __restrict__ row_order, int n_slices,
+                  const float* __restrict__ bias, int act, void* Y, void* Ylo, int64_t ldy) {
+  constexpr int LPR = SB_LPR;
+  constexpr int NQS = 32;  // float4 columns per static slice (128 floats)
+  extern __shared__ __align__(16) unsigned char sb_smem[];
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int GROUPS = SB_THREADS / LPR;
+  constexpr int GPW = 32 / LPR;
+  const int sub = threadIdx.x & (LPR - 1);
+  const int grp = threadIdx.x / LPR;
+  const int gw = grp % GPW;
   const int64_t items = n_blk * n_slices;
   for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
     const int64_t b = it / n_slices;
@@ -494,71 +608,76 @@ spmm_block_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
     const int base = __ldg(blk_ptr + b);
     const int rows_b = __ldg(blk_ptr + b + 1) - base;
     if (rows_b <= 0) continue;  // CTA-uniform
-    const int q0 = sl * nq_slice;                       // first float4 column of this slice
-    const int nqs = min(nq_slice, nq - q0);             // float4 columns in this slice
-    const bool staged = rows_b <= rows_cap;             // CTA-uniform
-    if (staged) {
-      for (int i = grp; i < rows_b; i += GROUPS) {
-        const int64_t srow = src_index ? (int64_t)__ldg(src_index + base + i) : (int64_t)(base + i);
-        if (sub < nqs) cp_async16(xs + (size_t)i * nq_slice + sub, X + srow * ldx + 4 * (q0 + sub));
+    const int q0 = sl * NQS;            // first float4 column of this slice
+    const int nqs = min(NQS, nq - q0);  // float4 columns in this slice
+    const int ebase = __ldg(rowptr + base);
+    const int n_ent = __ldg(rowptr + base + rows_b) - ebase;
+    // Passes: the fewest column ranges of equal width whose staging fits the shared memory (the CSR part is re-staged per
+    // pass: 2 bytes per entry against 16 * width bytes of features per row).  All CTA-uniform.
+    int n_pass = 0;
+    if (rows_b <= 65535) {
+      for (int t = 1; t <= nqs; ++t) {
+        const int w = (nqs + t - 1) / t;
+        if (sb_bytes(rows_b, w, n_ent) <= SB_SMEM) { n_pass = t; break; }
       }
-      for (int i = threadIdx.x; i < rows_b; i += SB_THREADS) ds[i] = __ldg(dinv + base + i);
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncthreads();
     }
-    // warp-uniform row loop (the groups of a warp use warp-wide collectives): a group past the block's last row idles
-    constexpr int GPW = 32 / LPR;
-    const int gw = grp % GPW;
+    if (n_pass != 0) {
+      const int w = (nqs + n_pass - 1) / n_pass;
+      for (int qa = 0; qa < nqs; qa += w) {
+        const int wq = min(w, nqs - qa);
+        if (wq > 24) sb_staged_pass<4, SPLIT>(rowptr, col, dinv, X, ldx, src_index, row_order, base, rows_b, ebase, n_ent, q0 + qa, wq, bias, act, Y, Ylo, ldy, sb_smem);
+        else if (wq > 16) sb_staged_pass<3, SPLIT>(rowptr, col, dinv, X, ldx, src_index, row_order, base, rows_b, ebase, n_ent, q0 + qa, wq, bias, act, Y, Ylo, ldy, sb_smem);
+        else if (wq > 8) sb_staged_pass<2, SPLIT>(rowptr, col, dinv, X, ldx, src_index, row_order, base, rows_b, ebase, n_ent, q0 + qa, wq, bias, act, Y, Ylo, ldy, sb_smem);
+        else sb_staged_pass<1, SPLIT>(rowptr, col, dinv, X, ldx, src_index, row_order, base, rows_b, ebase, n_ent, q0 + qa, wq, bias, act, Y, Ylo, ldy, sb_smem);
+      }
+      continue;
+    }
+    // block beyond any staging capacity: the same aggregation straight from global memory
     for (int i0 = grp - gw; i0 < rows_b; i0 += GROUPS) {
       const int i = i0 + gw;
       const bool live = i < rows_b;
       const int r = base + (live ? i : 0);
       const int beg = live ? __ldg(rowptr + r) : 0, end = live ? __ldg(rowptr + r + 1) : 0;
-      const float dr = staged ? ds[live ? i : 0] : __ldg(dinv + r);
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      // the LPR lanes of a group walk the row's entries LPR at a time; the groups of one warp run in lockstep, so the inner
-      // trip count is the warp's maximum and a group past its own count adds w = 0 times a valid row
+      const float dr = __ldg(dinv + r);
+      float4 acc[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int e0 = beg; __any_sync(FULL, e0 < end); e0 += LPR) {
         const bool has = e0 + sub < end;
-        const int c = has ? __ldg(col + e0 + sub) - base : 0;  // block-local source row (precondition: closed block)
-        float w = 0.f;
-        int64_t goff = 0;
-        if (has) {
-          if (staged) {
-            w = ds[c];
-          } else {
-            w = __ldg(dinv + base + c);
-            goff = (src_index ? (int64_t)__ldg(src_index + base + c) : (int64_t)(base + c)) * ldx;
-          }
-        }
+        const int c = has ? __ldg(col + e0 + sub) : 0;
+        const float w = has ? __ldg(dinv + c) : 0.f;
+        const int64_t goff = (src_index ? (int64_t)__ldg(src_index + c) : (int64_t)c) * ldx;
         const int cnt = max(0, min(LPR, end - e0));
         const int maxcnt = __reduce_max_sync(FULL, cnt);
         for (int j = 0; j < maxcnt; ++j) {
           const float wj = __shfl_sync(FULL, w, j, LPR);
-          if (staged) {
-            const int cj = __shfl_sync(FULL, c, j, LPR);
-            if (sub < nqs) fma4(acc, wj, lds128(xs_u32 + ((uint32_t)cj * (uint32_t)nq_slice + (uint32_t)sub) * 16u));
-          } else {
-            const int64_t oj = __shfl_sync(FULL, goff, j, LPR);
-            if (sub < nqs) fma4(acc, wj, ldg4(X + oj + 4 * (q0 + sub)));
+          const int64_t oj = __shfl_sync(FULL, goff, j, LPR);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const int q = sub + LPR * v;
+            if (q < nqs) fma4(acc[v], wj, ldg4(X + oj + 4 * (q0 + q)));
           }
         }
       }
-      if (live && sub < nqs) {
-        const int q = q0 + sub;
-        float4 o = make_float4(acc.x * dr, acc.y * dr, acc.z * dr, acc.w * dr);
-        if (bias) {
-          const float4 bq = ldg4(bias + 4 * q);
-          o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w;
+      if (live) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int qs = sub + LPR * v;
+          if (qs < nqs) {
+            const int q = q0 + qs;
+            float4 o = make_float4(acc[v].x * dr, acc[v].y * dr, acc[v].z * dr, acc[v].w * dr);
+            if (bias) {
+              const float4 bq = ldg4(bias + 4 * q);
+              o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w;
+            }
+            if (act == FITGNN_ACT_ELU) {
+              o.x = elu1(o.x); o.y = elu1(o.y); o.z = elu1(o.z); o.w = elu1(o.w);
+            }
+            store_row4<SPLIT>(Y, Ylo, (int64_t)r * ldy + 4 * q, o);
+          }
         }
-        if (act == FITGNN_ACT_ELU) {
-          o.x = elu1(o.x); o.y = elu1(o.y); o.z = elu1(o.z); o.w = elu1(o.w);
-        }
-        store_row4<SPLIT>(Y, Ylo, (int64_t)r * ldy + 4 * q, o);
       }
     }
-    if (staged) __syncthreads();  // the next item's staging overwrites xs / ds
   }
 }
 
@@ -678,8 +797,8 @@ extern "C" int fitgnn_spmm_symnorm(const int32_t* rowptr, const int32_t* col, co
 
 extern "C" int fitgnn_spmm_symnorm_blocked(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X,
                                            int64_t ldx, int width, const int32_t* src_index, const int32_t* blk_ptr,
-                                           int64_t n_blk, const float* bias, int act, void* Y, void* Y_lo, int64_t ldy,
-                                           void* stream) {
+                                           int64_t n_blk, const int32_t* row_order, const float* bias, int act, void* Y,
+                                           void* Y_lo, int64_t ldy, void* stream) {
   FG_REQUIRE(rowptr && col && dinv && X && Y && blk_ptr, FITGNN_EINVAL, "spmm_blocked: null pointer");
   FG_REQUIRE(n_blk >= 0 && width > 0, FITGNN_EINVAL, "spmm_blocked: n_blk=%lld width=%d", (long long)n_blk, width);
   FG_REQUIRE(width % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, FITGNN_EUNSUP,
@@ -690,28 +809,20 @@ extern "C" int fitgnn_spmm_symnorm_blocked(const int32_t* rowptr, const int32_t*
   if (n_blk == 0) return FITGNN_OK;
   cudaStream_t st = as_stream(stream);
   const int nq = width / 4;
-  // rows up to 128 floats: one slice, a warp per row; wider rows: 64-column slices, a half warp per row
-  const int lpr = nq <= 32 ? 32 : 16;
-  const int nq_slice = nq <= 32 ? nq : 16;
-  const int n_slices = (int)ceil_div(nq, nq_slice);
-  constexpr size_t SMEM = 72 * 1024;  // three CTAs per SM: one stages while the others aggregate
-  const int rows_cap = (int)(SMEM / ((size_t)nq_slice * 16 + 4));
+  // static slices of 128 floats (32 float4); inside a slice the kernel picks the staging pitch per block
+  const int n_slices = (int)ceil_div(nq, 32);
   const int64_t items = n_blk * n_slices;
-  const int64_t max_blocks = (int64_t)sm_count() * 3;
+  const int64_t max_blocks = (int64_t)sm_count() * FG_SB_CTAS;
   const unsigned blocks = (unsigned)(items < max_blocks ? items : max_blocks);
-  const bool split = Y_lo != nullptr;
-#define FG_SB(LPR_, SPLIT_)                                                                                               \
-  do {                                                                                                                    \
-    FG_CUDA(cudaFuncSetAttribute(spmm_block_kernel<LPR_, SPLIT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM)); \
-    spmm_block_kernel<LPR_, SPLIT_><<<blocks, SB_THREADS, SMEM, st>>>(rowptr, col, dinv, X, ldx, nq, src_index, blk_ptr, n_blk, \
-                                                                      nq_slice, n_slices, rows_cap, bias, act, Y, Y_lo, ldy);  \
-  } while (0)
-  if (lpr == 32) {
-    if (split) FG_SB(32, true); else FG_SB(32, false);
+  if (Y_lo) {
+    FG_CUDA(cudaFuncSetAttribute(spmm_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_SMEM));
+    spmm_block_kernel<true><<<blocks, SB_THREADS, SB_SMEM, st>>>(rowptr, col, dinv, X, ldx, nq, src_index, blk_ptr, n_blk,
+                                                                 row_order, n_slices, bias, act, Y, Y_lo, ldy);
   } else {
-    if (split) FG_SB(16, true); else FG_SB(16, false);
+    FG_CUDA(cudaFuncSetAttribute(spmm_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_SMEM));
+    spmm_block_kernel<false><<<blocks, SB_THREADS, SB_SMEM, st>>>(rowptr, col, dinv, X, ldx, nq, src_index, blk_ptr, n_blk,
+                                                                  row_order, n_slices, bias, act, Y, Y_lo, ldy);
   }
-#undef FG_SB
   FG_LAUNCH_CHECK();
   return FITGNN_OK;
 }

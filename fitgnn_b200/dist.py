@@ -171,6 +171,7 @@ class PeerGather:
         self.pstreams = [torch.cuda.Stream(device=device) for _ in range(max(shard.world - 1, 0))]
         self._ready = [torch.cuda.Event() for _ in range(n_buffers)]
         self._done = [torch.cuda.Event() for _ in range(n_buffers)]
+        self._consumed = [None] * n_buffers  # see release()
         for e in self._done:
             e.record(torch.cuda.current_stream())
 
@@ -179,13 +180,15 @@ class PeerGather:
         return all(b != 0 for b in self.mc_bases)
 
     def slot_ptrs(self, i: int, chunk: int = 0, multicast: bool = False):
-        """Addresses of slot (chunk, my rank) in buffer i of every rank (own rank first), or — multicast — the single
-        NVLS address whose stores land in that slot on every rank (this one included)."""
+        """Addresses of slot (chunk, my rank) in buffer i of every rank (own rank first).
+        multicast=True is refused: the head kernel writes with ordinary st / cp.async.bulk stores, and PTX defines accesses
+        to a multimem (NVLS multicast) address only for multimem.ld_reduce / multimem.st / multimem.red — the round-1 'mc'
+        exchange worked empirically but relied on undefined behaviour, and it did not beat the peer stores anyway (an
+        all-gather is ingress-bound: every rank still receives all the other slots; profiles/r1_multi_gpu.md)."""
         s = self.shard
         off = 4 * ((chunk * s.world + s.rank) * s.max_count) * self.C
         if multicast:
-            assert self.has_multicast, "no multicast mapping (backend 'symm' on an NVSwitch box needed)"
-            return [self.mc_bases[i] + off]
+            raise NotImplementedError("multicast stores need multimem.st in the head kernel; use the p2p / ce exchange")
         order = [s.rank] + [r for r in range(s.world) if r != s.rank]
         return [self.bases[i][r] + off for r in order]
 
@@ -227,6 +230,11 @@ class PeerGather:
         with torch.cuda.stream(self.xstream):
             for ps in self.pstreams:
                 self.xstream.wait_stream(ps)
+            # buffer-reuse ordering: the peers overwrite THIS rank's copy of the other buffers two steps from now, and what
+            # orders their pushes after this rank's reads is this barrier — so it must follow every read released so far
+            for ev in self._consumed:
+                if ev is not None:
+                    self.xstream.wait_event(ev)
             self.barrier()
             self._done[i].record(self.xstream)
 
@@ -236,6 +244,15 @@ class PeerGather:
 
     def wait(self, i: int):
         torch.cuda.current_stream().wait_event(self._done[i])
+
+    def release(self, i: int):
+        """Call on the consumer's stream after its LAST read of buffer i (as gathered by step s): records the event the
+        next barrier waits on, so no peer can push step s+2's rows into this rank's buffer i while it is still being read.
+        Protocol per step: acquire(b) -> head kernels -> exchange_async(b) ... wait(b) -> reads -> release(b).  A consumer
+        that does not call release() must finish reading buffer i (stream-ordered) before exchange_async of the next step."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._consumed[i] = ev
 
     def close(self):
         self._peer_slots = {}

@@ -83,11 +83,13 @@ class PackedForward:
         self.launches = 0
         # block-staged SpMM (spmm.cu spmm_block_kernel) for the all-rows aggregations of packs whose rows have several
         # entries each: the sources of a block of whole subgraphs are staged in shared memory once instead of being fetched
-        # through L2 once per entry.  'auto': from 2 entries per row on average (below that there is nothing to re-use).
+        # through L2 once per entry.  'auto': from 8 entries per row on average — cluster_node packs (measured r2c/r2d: with
+        # 2-4 entries per row the pipelined gather kernel is faster, its source rows are re-hit in L1/L2 anyway).
         self._blk = None
-        if blocked_spmm is True or (blocked_spmm == "auto" and pack.n_rows > 0 and pack.nnz >= 2.0 * pack.n_rows):
+        if blocked_spmm is True or (blocked_spmm == "auto" and pack.n_rows > 0 and pack.nnz >= 8.0 * pack.n_rows):
             if bool((pack.sub_ptr[1:] >= pack.sub_ptr[:-1]).all()):
-                self._blk = ops.row_blocks(pack.sub_ptr, pack.n_rows)
+                self._blk = ops.row_blocks(pack.sub_ptr, pack.n_rows, window=16)
+                self._blk_order = ops.block_row_order(pack.rowptr, self._blk)
         # fitgnn_gcn_layer_fused for layer 0 (gather warps inside the GEMM).  Correct but measured SLOWER than
         # SpMM + GEMM on B200 (5.1 ms vs 2.1 ms on the products workload: 4 gather warps per SM cannot hide the gather
         # latency that the stand-alone SpMM hides with 24 warps per SM), hence opt-in.
@@ -212,7 +214,8 @@ class PackedForward:
         if rows is None and pack is None and self._blk is not None:
             self.launches += 1
             return self._timed(name, lambda: ops.spmm_symnorm_blocked(p.rowptr, p.col, p.dinv, X, self._blk, width, src_index,
-                                                                      bias, act, out=out, split=split),
+                                                                      bias, act, out=out, split=split,
+                                                                      row_order=self._blk_order),
                                nbytes=self._spmm_bytes(width, src_index, last, n_src_rows))
         self.launches += 1 + (1 if hubs[1] > 0 else 0)
         return self._timed(name, lambda: ops.spmm_symnorm(p.rowptr, p.col, p.dinv, X, width, src_index, bias, act, rows,

@@ -102,14 +102,19 @@ class GCNConv(torch.nn.Module):
         torch.nn.init.xavier_uniform_(self.lin.weight)  # PyG: glorot
         torch.nn.init.zeros_(self.bias)
 
-    def forward(self, x, edge_index, act: int = ops.ACT_NONE):
+    def forward(self, x, edge_index, act: int = ops.ACT_NONE, dropout_p: float = 0.0):
+        """act / dropout_p: the F.elu / F.dropout that follow the conv in every reference model (network.py:32-33), fused
+        into the operator (epilogue; Philox mask regenerated in the backward).  Defaults = the plain PyG operator."""
         _require_cuda(x)
         if self.out_channels % 4 != 0:
             raise RuntimeError("fitgnn_b200.GCNConv needs out_channels % 4 == 0")
         n = x.shape[0]
         csr = _csr_for(edge_index, n)
         if torch.is_grad_enabled() and (x.requires_grad or self.lin.weight.requires_grad or self.bias.requires_grad):
-            return gcn_conv(x, self.lin.weight, self.bias, csr, act)
+            return gcn_conv(x, self.lin.weight, self.bias, csr, act, dropout_p)
+        if dropout_p > 0.0:  # train mode without gradients (the reference's loops never do this, but F.dropout would)
+            y = self.forward(x, edge_index, act)
+            return ops.dropout(y, dropout_p, int(torch.randint(0, 2 ** 62, (1,)).item()))
         rowptr, col, dinv = csr.rowptr, csr.col, csr.dinv
         b = self.bias.detach().contiguous()
         if _PRECISION == "bf16x3":  # tensor cores (network.py:31 call pattern, one conv per call)
@@ -164,9 +169,7 @@ class _ConvStack(torch.nn.Module):
     def _convs(self, x, edge_index):
         # network.py:30-33: conv -> F.elu -> F.dropout(training=self.training); ELU is fused into the conv epilogue
         for i in range(self.num_layers):
-            x = self.conv[i](x, edge_index, act=ops.ACT_ELU)
-            if self.training:
-                x = torch.nn.functional.dropout(x, training=True)
+            x = self.conv[i](x, edge_index, act=ops.ACT_ELU, dropout_p=0.5 if self.training else 0.0)  # F.dropout default p
         return x
 
     def _lt1(self, x, head):

@@ -120,8 +120,19 @@ def row_blocks(sub_ptr, n_rows, window=64):
     return blk.to(torch.int32).contiguous()
 
 
+def block_row_order(rowptr, blk_ptr):
+    """row_order for spmm_symnorm_blocked: the rows of every block sorted by row length (descending, stable), blocks in
+    place.  int32 [n_rows]."""
+    n = rowptr.numel() - 1
+    deg = (rowptr[1:] - rowptr[:-1]).long()
+    rows = torch.arange(n, device=rowptr.device)
+    blk = torch.searchsorted(blk_ptr[1:].long().contiguous(), rows, right=True)
+    key = blk * (int(deg.max()) + 1 if n else 1) + (int(deg.max()) - deg if n else deg)
+    return torch.sort(key, stable=True).indices.to(torch.int32).contiguous()
+
+
 def spmm_symnorm_blocked(rowptr, col, dinv, X, blk_ptr, width=None, src_index=None, bias=None, act=ACT_NONE, out=None,
-                         split=False):
+                         split=False, row_order=None):
     """Y = act(Â·X[src_index] + bias) for every row, sources staged block by block in shared memory
     (fitgnn_spmm_symnorm_blocked; blk_ptr from row_blocks).  Bit-identical to spmm_symnorm."""
     assert X.dtype == torch.float32 and X.dim() == 2 and blk_ptr.dtype == torch.int32
@@ -137,8 +148,8 @@ def spmm_symnorm_blocked(rowptr, col, dinv, X, blk_ptr, width=None, src_index=No
             out = torch.empty(n, width, dtype=torch.float32, device=X.device)
         y, ylo, ldy = out, None, out.stride(0)
     check(lib().fitgnn_spmm_symnorm_blocked(ptr(rowptr), ptr(col), ptr(dinv), ptr(X), X.stride(0), width, ptr(src_index),
-                                            ptr(blk_ptr), blk_ptr.numel() - 1, ptr(bias), act, ptr(y), ptr(ylo), ldy,
-                                            stream_ptr()))
+                                            ptr(blk_ptr), blk_ptr.numel() - 1, ptr(row_order), ptr(bias), act, ptr(y),
+                                            ptr(ylo), ldy, stream_ptr()))
     return out
 
 
@@ -301,6 +312,53 @@ def gcn_forward(pack, X, state_dict, head=HEAD_LOG_SOFTMAX, precision=GEMM_BF16X
     check(lib().fitgnn_gcn_forward(C.byref(st), ptr(X), X.stride(0), C.byref(ws_), head, precision, ptr(out), out.stride(0),
                                    ptr(ws), ws.numel(), stream_ptr()))
     return out[:, :Cn]
+
+
+# ----------------------------------------------------------------------------------------- training path
+def gemm_tn(G, A):
+    """dW [out, in] = G[R, out]^T · A[R, in] on the tensor cores (fitgnn_gemm_tn): the weight gradient of a linear layer."""
+    assert G.dtype == torch.float32 and A.dtype == torch.float32 and G.shape[0] == A.shape[0] and G.dim() == 2 and A.dim() == 2
+    if G.stride(1) != 1:
+        G = G.contiguous()
+    if A.stride(1) != 1:
+        A = A.contiguous()
+    R, out, inn = G.shape[0], G.shape[1], A.shape[1]
+    dW = torch.empty(out, inn, dtype=torch.float32, device=G.device)
+    if R == 0:
+        return dW.zero_()
+    ws = _ws(lib().fitgnn_gemm_tn_workspace_bytes(R, out, inn), G.device)
+    check(lib().fitgnn_gemm_tn(ptr(G), G.stride(0), ptr(A), A.stride(0), R, out, inn, ptr(dW), dW.stride(0), ptr(ws), ws.numel(),
+                               stream_ptr()))
+    return dW
+
+
+def dropout(X, p, seed, offset=0, out=None):
+    """X * mask / (1 - p) with the Philox mask of (seed, offset) (fitgnn_dropout; F.dropout of network.py:33)."""
+    assert X.dtype == torch.float32 and X.dim() == 2 and X.stride(1) == 1
+    if out is None:
+        out = torch.empty(X.shape, dtype=torch.float32, device=X.device)
+    check(lib().fitgnn_dropout(ptr(X), X.stride(0), X.shape[0], X.shape[1], float(p), int(seed), int(offset), ptr(out),
+                               out.stride(0), stream_ptr()))
+    return out
+
+
+def elu_dropout_backward(G, H, act=ACT_ELU, p=0.0, seed=0, offset=0):
+    """G * mask/(1-p) * act'(H): gradient w.r.t. the pre-activation of x = dropout(act(z)) given H = act(z)."""
+    assert G.dtype == torch.float32 and H.dtype == torch.float32 and G.shape == H.shape and G.dim() == 2
+    G = G if G.stride(1) == 1 else G.contiguous()
+    H = H if H.stride(1) == 1 else H.contiguous()
+    out = torch.empty(G.shape, dtype=torch.float32, device=G.device)
+    check(lib().fitgnn_elu_dropout_backward(ptr(G), G.stride(0), ptr(H), H.stride(0), G.shape[0], G.shape[1], act, float(p),
+                                            int(seed), int(offset), ptr(out), out.stride(0), stream_ptr()))
+    return out
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, step, lr=0.01, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    """One fused Adam step over flat fp32 buffers (fitgnn_adam_step, torch.optim.Adam semantics)."""
+    n = param.numel()
+    assert all(t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n for t in (param, grad, exp_avg, exp_avg_sq))
+    check(lib().fitgnn_adam_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), n, float(lr), float(betas[0]),
+                                 float(betas[1]), float(eps), float(weight_decay), int(step), stream_ptr()))
 
 
 def raw_tensor(ptr_value, shape, device, owner=None):

@@ -21,10 +21,8 @@ def forward_on_pack(model, pack: Pack, X, csr: CsrPair | None = None):
     from .autograd import gcn_conv
     csr = csr or pack_csr(pack)
     x = X[pack.gid.long()]
-    for i in range(model.num_layers):
-        x = gcn_conv(x, model.conv[i].lin.weight, model.conv[i].bias, csr, ops.ACT_ELU)
-        if model.training:
-            x = torch.nn.functional.dropout(x, training=True)  # network.py:33 (p = 0.5)
+    for i in range(model.num_layers):  # conv -> ELU -> dropout (network.py:31-33, p = 0.5 in train mode), one fused operator
+        x = gcn_conv(x, model.conv[i].lin.weight, model.conv[i].bias, csr, ops.ACT_ELU, 0.5 if model.training else 0.0)
     y = model.lt1(x)
     return torch.nn.functional.log_softmax(y, dim=1) if model._head == "log_softmax" else y
 
@@ -62,6 +60,68 @@ def allreduce_gradients(model, world_size: int, group=None, local_count=None):
     return n
 
 
+class FusedAdam:
+    """torch.optim.Adam over ONE flat buffer: the model's parameters are re-pointed at views of a single fp32 buffer and
+    so are their gradients, so that (a) the optimiser step is one kernel (fitgnn_adam_step) instead of one per parameter
+    and (b) the multi-GPU gradient all-reduce runs on the flat gradient buffer in place — no gather / scatter copies.
+    Same update rule and defaults as the reference's optimiser (torch.optim.Adam(lr, weight_decay), run.py:341)."""
+
+    def __init__(self, params, lr=0.01, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.params = [p for p in params if p.requires_grad]
+        assert self.params and all(p.is_cuda and p.dtype == torch.float32 for p in self.params)
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            self.flat[off: off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[off: off + k].view_as(p)
+            p.grad = self.grad[off: off + k].view_as(p)
+            off += k
+        self.lr, self.betas, self.eps, self.weight_decay, self.t = lr, betas, eps, weight_decay, 0
+
+    def zero_grad(self, set_to_none=False):
+        self.grad.zero_()
+        off = 0
+        for p in self.params:  # autograd accumulates in place as long as .grad is our view
+            if p.grad is None or p.grad.data_ptr() != self.grad[off: off + 1].data_ptr():
+                p.grad = self.grad[off: off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def step(self):
+        from . import ops
+        off = 0
+        for p in self.params:  # a gradient autograd replaced instead of accumulating into our view is copied in
+            k = p.numel()
+            if p.grad is not None and p.grad.data_ptr() != self.grad[off: off + 1].data_ptr():
+                self.grad[off: off + k].copy_(p.grad.reshape(-1))
+            off += k
+        self.t += 1
+        ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.t, self.lr, self.betas, self.eps, self.weight_decay)
+
+
+def allreduce_flat_(flat_grad, world_size: int, group=None, local_count=None):
+    """allreduce_gradients on a flat gradient buffer, in place (FusedAdam): one collective, no copies; the row count rides
+    in a second tiny all-reduce."""
+    n = float(local_count) if local_count is not None else None
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.all_reduce(flat_grad, group=group)
+        if local_count is None:
+            flat_grad /= world_size
+            return None
+        cnt = torch.tensor([float(local_count)], device=flat_grad.device)
+        dist.all_reduce(cnt, group=group)
+        n = float(cnt)
+    if n is not None:
+        flat_grad /= max(n, 1.0)
+    return n
+
+
 def train_step_Gs(model, pack: Pack, X, y, train_mask, optimizer, loss_fn=None, world_size=1, csr=None, group=None):
     """node_train_Gs_GD (run.py:177-215): ONE loss over every train node of every subgraph, backward, step.
     y / train_mask are global ([N]); extra / cluster rows never contribute (Pack.split_masks).  With world_size > 1 the
@@ -85,6 +145,9 @@ def train_step_Gs(model, pack: Pack, X, y, train_mask, optimizer, loss_fn=None, 
     if world_size > 1:
         import torch.distributed as dist
         dist.all_reduce(total, group=group)
-    allreduce_gradients(model, world_size, group, local_count=n_local)
+    if isinstance(optimizer, FusedAdam):
+        allreduce_flat_(optimizer.grad, world_size, group, n_local)
+    else:
+        allreduce_gradients(model, world_size, group, local_count=n_local)
     optimizer.step()
     return float(total[0] / total[1].clamp(min=1.0))

@@ -161,8 +161,11 @@ int fitgnn_spmm_symnorm_grouped(const int32_t* rowptr, const int32_t* col, const
  * Bit-identical to fitgnn_spmm_symnorm.  Entries leaving their block are a precondition violation. */
 int fitgnn_spmm_symnorm_blocked(const int32_t* rowptr, const int32_t* col, const float* dinv,
                                 const float* X, int64_t ldx, int width, const int32_t* src_index,
-                                const int32_t* blk_ptr, int64_t n_blk, const float* bias, int act,
-                                void* Y, void* Y_lo, int64_t ldy, void* stream);
+                                const int32_t* blk_ptr, int64_t n_blk, const int32_t* row_order,
+                                const float* bias, int act, void* Y, void* Y_lo, int64_t ldy, void* stream);
+/* row_order (device, [n_rows], may be NULL = identity): a permutation of the pack rows that keeps every block's rows
+ * together (positions blk_ptr[b]..blk_ptr[b+1] hold block b's rows) — e.g. sorted by row length inside each block, so
+ * that the rows a warp works on at the same time have similar lengths.  Results do not depend on it. */
 /* Same with the high-degree rows split across a CTA: hub_list (from fitgnn_spmm_hubs) holds the output
  * indices i whose row has >= hub_deg entries; the warp-per-row pass skips them. */
 int fitgnn_spmm_hubs(const int32_t* rowptr, const int32_t* out_rows, int64_t n_out, int hub_deg,
@@ -321,6 +324,30 @@ size_t fitgnn_gcn_forward_workspace_bytes(const fitgnn_pack* pack, const fitgnn_
 int fitgnn_gcn_forward(const fitgnn_pack* pack, const float* X, int64_t ldx, const fitgnn_weights* weights,
                        int head, int precision, float* out /*[n_core, ld_out]*/, int64_t ld_out, void* ws,
                        size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Training path (node_train_Gs_GD run.py:177-215, node_train_Gc run.py:26-37; dropout network.py:33; Adam main.py:193-194).
+ * fitgnn_gemm_tn: the weight gradient of GCNConv.lin / lt1 on the tensor cores,
+ *     dW[out, in] = sum_r G[r, out] * A[r, in]        (G = gradient w.r.t. the layer's pre-activation, A = its input)
+ *   both operands row-major fp32 [R, *]; internally a transposing bf16 hi/lo split (the contraction runs over the rows),
+ *   a batched split-K FITGNN_GEMM_BF16X3 product and a fixed-order reduction of the partial sums (deterministic).
+ * fitgnn_dropout: Y = X * mask / (1 - p), mask from Philox4x32-10 keyed by (seed, offset + element / 4): the backward
+ *   regenerates the same mask from the same (seed, offset), nothing is stored.  Element index = row * cols + col.
+ * fitgnn_elu_dropout_backward: GZ = G * mask / (1 - p) * act'(H) with H the activation's OUTPUT before the dropout
+ *   (ELU'(z) = 1 for z > 0, else elu(z) + 1); p = 0 -> no mask; act = FITGNN_ACT_NONE -> act' = 1.
+ * fitgnn_adam_step: torch.optim.Adam (no amsgrad) on a flat buffer: g += weight_decay * p; m, v moments; bias correction with
+ *   `step` (1-based).
+ * ---------------------------------------------------------------------------------------- */
+size_t fitgnn_gemm_tn_workspace_bytes(int64_t R, int out, int in);
+int fitgnn_gemm_tn(const float* G, int64_t ldg, const float* A, int64_t lda, int64_t R, int out, int in,
+                   float* dW, int64_t lddw, void* ws, size_t ws_bytes, void* stream);
+int fitgnn_dropout(const float* X, int64_t ldx, int64_t rows, int cols, float p, uint64_t seed,
+                   uint64_t offset, float* Y, int64_t ldy, void* stream);
+int fitgnn_elu_dropout_backward(const float* G, int64_t ldg, const float* H, int64_t ldh, int64_t rows,
+                                int cols, int act, float p, uint64_t seed, uint64_t offset, float* GZ,
+                                int64_t ldo, void* stream);
+int fitgnn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, int64_t step, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Graph-level pooling.  Replaces x[mask] + torch.cat + global_max_pool / global_mean_pool

