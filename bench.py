@@ -56,11 +56,15 @@ def parse():
                         "collated batch.x holds, built once with the pack); 'table' = node-ordered [N, F] table gathered "
                         "through gid every step; auto = packed in mode none with one chunk per rank, else table")
     p.add_argument("--seed", type=int, default=0)
-    p.add_argument("--collective", default="auto", choices=["auto", "p2p", "ce", "nccl"],
-                   help="N>1 output exchange: p2p = head kernel stores into every rank's gather buffer over NVLink "
+    p.add_argument("--collective", default="auto", choices=["auto", "push", "p2p", "ce", "nccl"],
+                   help="N>1 output exchange: push = head into the local slot, then ONE small kernel bulk-stores the slot to all "
+                        "peers on a side stream, overlapping the next step's compute (measured slower: it takes SMs from the "
+                        "persistent GEMMs); "
+                        "p2p = head kernel stores into every rank's gather buffer over NVLink "
                         "(+ a one-element all-reduce as barrier); ce = head into the local slot, copy-engine pushes to the "
                         "peers on a side stream overlapping the next step's compute; nccl = local slot, then all_gather; "
                         "auto = p2p up to 4 GPUs, ce above (measured)")
+    p.add_argument("--push-ctas", type=int, default=16, help="CTAs of the peer-push kernel (--collective push)")
     p.add_argument("--chunks", type=int, default=1, help="N>1: chunks per rank; chunk c's all-gather overlaps chunk c+1")
     p.add_argument("--modes", default="none_heavy_tail,cluster,train",
                    help="N=1: extra blocks measured after the headline (comma separated, '' = none): none_heavy_tail = same "
@@ -528,6 +532,12 @@ def main_ours(args):
                              fuse_aggregate=False if args.no_fuse_aggregate else "auto", align_policy=args.align_policy)
             for lp in shard.locals]
     fwd = fwds[0]
+    align_ms = None
+    if fwd.apack is not None and world == 1:  # the group alignment the fused schedule needs (done once per pack, timed on its own)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        _ap = pack.aligned(32, args.align_policy)
+        torch.cuda.synchronize(); align_ms = (time.perf_counter() - t0) * 1e3
+        del _ap
     # the group-aligned schedule takes the feature table un-padded ([n, 100]); the classic one wants the K-padded pitch
     Xd = X if (fwd.apack is not None and F % 4 == 0) else fwd.pad_features(X)
     X_full = Xd
@@ -554,6 +564,9 @@ def main_ours(args):
             # measured on 8xB200 (profiles/r1_multi_gpu.md): the fused peer stores win up to 4 GPUs; at 8 the head becomes
             # NVLink-bound (7 x its slot per rank) and the overlapped copy-engine exchange is ahead; the multicast store
             # does not help an all-gather (every rank still has to RECEIVE all the other slots)
+            # measured (profiles/r1_multi_gpu.md, profiles/r2_multi_gpu.md): the fused peer stores win up to 4 GPUs; at 8 the head
+            # becomes NVLink-egress-bound and the overlapped copy-engine exchange is ahead.  The SM-driven push kernel ('push')
+            # loses to both: every CTA it occupies delays one CTA of the persistent 148-CTA GEMMs by the whole push
             collective = args.collective if args.collective != "auto" else ("p2p" if world <= 4 else "ce")
         except Exception as e:  # IPC not permitted in this container, ...
             if args.collective == "p2p":
@@ -566,11 +579,12 @@ def main_ours(args):
             pg, collective = None, "nccl"
 
     def run_p2p(Xin, b):
-        if collective == "ce":
+        if collective in ("ce", "push"):
             pg.acquire(b)
             for c, f in enumerate(fwds):
                 f(Xin, out=shard.slot(pg.tensors[b], c), packed=packed)
-            pg.exchange_async(b)  # completes behind the next step; the timed region ends with pg.wait on both buffers
+            # completes behind the next step; the timed region ends with pg.wait on both buffers
+            pg.exchange_async(b, engine=collective, push_ctas=args.push_ctas)
             return pg.tensors[b]
         for c, f in enumerate(fwds):
             f(Xin, peer_ptrs=pg.slot_ptrs(b, c), packed=packed)
@@ -578,7 +592,7 @@ def main_ours(args):
         return pg.tensors[b]
 
     def drain():
-        if pg is not None and collective == "ce":
+        if pg is not None and collective in ("ce", "push"):
             for b in range(2):
                 pg.wait(b)
 
@@ -826,7 +840,7 @@ def main_ours(args):
             "schedule": ("spmm0 -> [transform + next layer's aggregation in the epilogue] -> transform -> head (group-aligned "
                          f"pack, {fwd.apack.n_rows} rows incl. padding)") if fused else "spmm + transform per layer -> head",
             "kernels": kernels, "gpu_launches": gpu_launches, "clocks": sampler.summary(mark0, mark1),
-            "pack": {"rows": pack.n_rows, "nnz": pack.nnz, "subgraphs": pack.n_sub, "build_ms": pack_build_ms, "build_first_call_ms": pack_build_first_ms,
+            "pack": {"rows": pack.n_rows, "nnz": pack.nnz, "subgraphs": pack.n_sub, "build_ms": pack_build_ms, "build_first_call_ms": pack_build_first_ms, "align_ms": align_ms,
                      "bytes": pack.nbytes(), "rank_loads": shard.loads},
             "multi_gpu": {"chunks_per_rank": n_chunks, "collective": collective,
                           "gathered_vs_single_gpu_max_abs_err_all_ranks": verify, "rank_kernel_ms": rank_kernel_ms,

@@ -55,6 +55,8 @@ SIGNATURES = {
                                             c_void, c_i64, c_i32, C.c_float, c_void]),
     "fitgnn_spmm_symnorm_blocked": (c_i32, [c_void, c_void, c_void, c_void, c_i64, c_i32, c_void, c_void, c_i64, c_void,
                                             c_void, c_i32, c_void, c_void, c_i64, c_void]),
+    "fitgnn_spmm_symnorm_mma": (c_i32, [c_void, c_void, c_void, c_void, c_i64, c_i32, c_void, c_void, c_i64, c_void,
+                                        c_i32, c_void, c_void, c_i64, c_void]),
     "fitgnn_spmm_hubs": (c_i32, [c_void, c_void, c_i64, c_i32, c_void, c_void, c_i32, c_void]),
     "fitgnn_spmm_symnorm_hub": (c_i32, [c_void, c_void, c_void, c_void, c_i64, c_i32, c_void, c_void, c_i32, c_void,
                                         c_i64, c_void, c_void, c_i64, c_void, c_i32, c_i32, c_void]),
@@ -89,6 +91,7 @@ SIGNATURES = {
                                       c_i32, c_void, c_void, c_i64, c_void]),
     "fitgnn_gemm_head_rows_peers": (c_i32, [c_void, c_void, c_i64, c_void, c_void, c_i64, c_void, c_i64, c_i32, c_i32, c_i32,
                                             c_i32, c_void, C.POINTER(c_void), c_i32, c_i64, c_void]),
+    "fitgnn_peer_push": (c_i32, [c_void, C.POINTER(c_void), c_i32, c_size, c_i32, c_void]),
     "fitgnn_peer_alloc": (c_i32, [c_size, C.POINTER(c_void), C.c_char_p]),
     "fitgnn_peer_open": (c_i32, [C.c_char_p, C.POINTER(c_void)]),
     "fitgnn_peer_close": (c_i32, [c_void]),

@@ -208,25 +208,48 @@ class PeerGather:
             self._peer_slots[key] = ops.raw_tensor(self.bases[i][r] + off, (cnt, self.C), self._flag.device, owner=self)
         return self._peer_slots[key]
 
-    def exchange_async(self, i: int):
+    def exchange_async(self, i: int, engine: str = "ce", push_ctas: int = 16):
         """After this rank's head kernels wrote slot (c, rank) of its OWN buffer i on the current stream: push the slots to
-        every peer with device-to-device copies (copy engines over NVLink, no SM time) on a side stream, then the
-        barrier, all behind whatever the current stream does next (the following step's compute).  `wait(i)` makes the
-        current stream wait for buffer i to be complete on every rank; `acquire(i)` must precede the next write of it."""
+        every peer on a side stream, then the barrier, all behind whatever the current stream does next (the following step's
+        compute).  `wait(i)` makes the current stream wait for buffer i to be complete on every rank; `acquire(i)` must
+        precede the next write of it.
+        engine 'ce' (default): per-peer cudaMemcpyAsync on one stream per peer (copy engines, no SM time).
+        engine 'push': ONE small kernel (fitgnn_peer_push, `push_ctas` CTAs) streams the slot through shared memory and
+        bulk-stores it to all peers.  Measured on 2 x B200 (profiles/r2_multi_gpu.md): ~50 GB/s per CTA (396 GB/s with 8,
+        695 GB/s with 32 CTAs; one copy-engine copy: 733 GB/s), and every SM it occupies holds back one CTA of the
+        persistent 148-CTA GEMM kernels for the whole push, so the step gets SLOWER (3.45-4.70 ms against 3.14 ms);
+        kept for schedules whose kernels do not need every SM."""
         s = self.shard
         cur = torch.cuda.current_stream()
         self._ready[i].record(cur)
-        # one side stream per peer: a single copy stream reaches ~200 GB/s, the copy engines together saturate NVLink
-        k = 0
-        for r in range(s.world):
-            if r == s.rank:
-                continue
-            ps = self.pstreams[k]
-            k += 1
+        if engine == "push" and s.world > 1:
+            import ctypes as C
+            from . import ops
+            from ._lib import check, lib
+            ps = self.pstreams[0]
             with torch.cuda.stream(ps):
                 ps.wait_event(self._ready[i])
                 for c in range(s.n_chunks):
-                    self._peer_slot(i, r, c).copy_(s.slot(self.tensors[i], c), non_blocking=True)
+                    src = s.slot(self.tensors[i], c)
+                    nbytes = src.numel() * 4
+                    if nbytes == 0:
+                        continue
+                    dsts = [self._peer_slot(i, r, c).data_ptr() for r in range(s.world) if r != s.rank]
+                    arr = (C.c_void_p * len(dsts))(*[C.c_void_p(d) for d in dsts])
+                    check(lib().fitgnn_peer_push(ops.ptr(src), arr, len(dsts), nbytes, push_ctas,
+                                                 C.c_void_p(ps.cuda_stream)))
+        else:
+            # one side stream per peer: a single copy stream reaches ~200 GB/s, several copy engines together ~310 GB/s
+            k = 0
+            for r in range(s.world):
+                if r == s.rank:
+                    continue
+                ps = self.pstreams[k]
+                k += 1
+                with torch.cuda.stream(ps):
+                    ps.wait_event(self._ready[i])
+                    for c in range(s.n_chunks):
+                        self._peer_slot(i, r, c).copy_(s.slot(self.tensors[i], c), non_blocking=True)
         with torch.cuda.stream(self.xstream):
             for ps in self.pstreams:
                 self.xstream.wait_stream(ps)

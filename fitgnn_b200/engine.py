@@ -35,7 +35,7 @@ class PackedForward:
 
     def __init__(self, pack: Pack, state_dict, head="log_softmax", rows="core", precision="bf16x3",
                  with_head=True, fuse_layer0=False, fuse_aggregate="auto", align_policy="degree", out_map=None,
-                 blocked_spmm="auto"):
+                 blocked_spmm="auto", dense_spmm="lds"):
         """precision: 'bf16x3' (default: tcgen05 tensor cores on a bf16 hi/lo split of both operands, fp32 accumulate,
         ~2^-17 relative operand error) or 'fp32' (exact-fp32 CUDA-core GEMM: the numerics anchor, explicit opt-in).
         out_map (int32 [n_out]): output row i is written to row out_map[i] of the `out` tensor passed to __call__
@@ -86,10 +86,17 @@ class PackedForward:
         # through L2 once per entry.  'auto': from 8 entries per row on average — cluster_node packs (measured r2c/r2d: with
         # 2-4 entries per row the pipelined gather kernel is faster, its source rows are re-hit in L1/L2 anyway).
         self._blk = None
-        if blocked_spmm is True or (blocked_spmm == "auto" and pack.n_rows > 0 and pack.nnz >= 8.0 * pack.n_rows):
+        import os
+        min_deg = float(os.environ.get("FITGNN_BLOCKED_MIN", "8"))  # env: A/B runs of bench.py
+        if blocked_spmm is True or (blocked_spmm == "auto" and pack.n_rows > 0 and pack.nnz >= min_deg * pack.n_rows):
             if bool((pack.sub_ptr[1:] >= pack.sub_ptr[:-1]).all()):
-                self._blk = ops.row_blocks(pack.sub_ptr, pack.n_rows, window=16)
+                self._blk = ops.row_blocks(pack.sub_ptr, pack.n_rows, window=16, compact=True)
                 self._blk_order = ops.block_row_order(pack.rowptr, self._blk)
+        # how the dense (blocked) aggregations run: 'lds' = shared-memory gathers (spmm_block_kernel; default: bit-identical to
+        # the generic kernel and, measured r2k, a little faster: 76.6 vs 81.3 ms on the products cluster pack), 'mma' = per
+        # 128 x 128 piece of the block's 0/1 adjacency one tensor-core product (spmm_mma.cu)
+        import os
+        self._dense_spmm = os.environ.get("FITGNN_DENSE_SPMM", dense_spmm)  # env: A/B runs of bench.py
         # fitgnn_gcn_layer_fused for layer 0 (gather warps inside the GEMM).  Correct but measured SLOWER than
         # SpMM + GEMM on B200 (5.1 ms vs 2.1 ms on the products workload: 4 gather warps per SM cannot hide the gather
         # latency that the stand-alone SpMM hides with 24 warps per SM), hence opt-in.
@@ -211,6 +218,11 @@ class PackedForward:
         if pack is not None:
             hubs = self.hubs_aligned
         n_src_rows = X.shape[0] if src_index is not None else p.n_rows
+        if rows is None and pack is None and self._blk is not None and self._dense_spmm == "mma":
+            self.launches += 1
+            return self._timed(name, lambda: ops.spmm_symnorm_mma(p.rowptr, p.col, p.dinv, X, self._blk, width, src_index, bias,
+                                                                  act, out=out, split=split),
+                               nbytes=self._spmm_bytes(width, src_index, last, n_src_rows))
         if rows is None and pack is None and self._blk is not None:
             self.launches += 1
             return self._timed(name, lambda: ops.spmm_symnorm_blocked(p.rowptr, p.col, p.dinv, X, self._blk, width, src_index,

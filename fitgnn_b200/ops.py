@@ -109,7 +109,7 @@ def spmm_symnorm_grouped(rowptr, col, dinv, X, width=None, src_index=None, out=N
     return out
 
 
-def row_blocks(sub_ptr, n_rows, window=64):
+def row_blocks(sub_ptr, n_rows, window=64, compact=False):
     """blk_ptr for spmm_symnorm_blocked: block b = the subgraphs whose first row lies in [b*window, (b+1)*window) — unions
     of whole subgraphs, so closed under adjacency; a block has fewer than window + (largest subgraph) rows, empty blocks
     (inside a subgraph that spans several windows) are skipped by the kernel.  sub_ptr must be non-decreasing."""
@@ -117,6 +117,10 @@ def row_blocks(sub_ptr, n_rows, window=64):
     nb = (int(n_rows) + window - 1) // window
     first = torch.searchsorted(sp[:-1].contiguous(), torch.arange(nb, device=sp.device) * window)
     blk = torch.cat([sp[first.clamp(max=sp.numel() - 1)], sp[-1:]])
+    if compact:  # drop the empty blocks (windows inside a subgraph that spans several): the kernels skip them, but each costs
+        blk = torch.unique_consecutive(blk)  # a CTA two dependent loads; boundaries stay whole-subgraph boundaries
+        if blk.numel() < 2:
+            blk = torch.stack([sp[0], sp[-1]])
     return blk.to(torch.int32).contiguous()
 
 
@@ -150,6 +154,26 @@ def spmm_symnorm_blocked(rowptr, col, dinv, X, blk_ptr, width=None, src_index=No
     check(lib().fitgnn_spmm_symnorm_blocked(ptr(rowptr), ptr(col), ptr(dinv), ptr(X), X.stride(0), width, ptr(src_index),
                                             ptr(blk_ptr), blk_ptr.numel() - 1, ptr(row_order), ptr(bias), act, ptr(y),
                                             ptr(ylo), ldy, stream_ptr()))
+    return out
+
+
+def spmm_symnorm_mma(rowptr, col, dinv, X, blk_ptr, width=None, src_index=None, bias=None, act=ACT_NONE, out=None, split=False):
+    """Y = act(Â·X[src_index] + bias) for every row with the block-dense tensor-core kernel (fitgnn_spmm_symnorm_mma):
+    per 128 x 128 piece of a block's 0/1 adjacency one small MMA.  ~1e-6 relative to spmm_symnorm."""
+    assert X.dtype == torch.float32 and X.dim() == 2 and blk_ptr.dtype == torch.int32
+    width = X.shape[1] if width is None else width
+    n = rowptr.numel() - 1
+    if split:
+        if out is None:
+            out = (torch.empty(n, width, dtype=torch.bfloat16, device=X.device),
+                   torch.empty(n, width, dtype=torch.bfloat16, device=X.device))
+        y, ylo, ldy = out[0], out[1], out[0].stride(0)
+    else:
+        if out is None:
+            out = torch.empty(n, width, dtype=torch.float32, device=X.device)
+        y, ylo, ldy = out, None, out.stride(0)
+    check(lib().fitgnn_spmm_symnorm_mma(ptr(rowptr), ptr(col), ptr(dinv), ptr(X), X.stride(0), width, ptr(src_index),
+                                        ptr(blk_ptr), blk_ptr.numel() - 1, ptr(bias), act, ptr(y), ptr(ylo), ldy, stream_ptr()))
     return out
 
 
@@ -327,8 +351,9 @@ def gemm_tn(G, A):
     if R == 0:
         return dW.zero_()
     ws = _ws(lib().fitgnn_gemm_tn_workspace_bytes(R, out, inn), G.device)
-    check(lib().fitgnn_gemm_tn(ptr(G), G.stride(0), ptr(A), A.stride(0), R, out, inn, ptr(dW), dW.stride(0), ptr(ws), ws.numel(),
-                               stream_ptr()))
+    # row-strided operands (column slices of wider matrices) are fine: the kernel takes the row pitch
+    check(lib().fitgnn_gemm_tn(C.c_void_p(G.data_ptr()), G.stride(0), C.c_void_p(A.data_ptr()), A.stride(0), R, out, inn,
+                               ptr(dW), dW.stride(0), ptr(ws), ws.numel(), stream_ptr()))
     return dW
 
 
@@ -337,8 +362,8 @@ def dropout(X, p, seed, offset=0, out=None):
     assert X.dtype == torch.float32 and X.dim() == 2 and X.stride(1) == 1
     if out is None:
         out = torch.empty(X.shape, dtype=torch.float32, device=X.device)
-    check(lib().fitgnn_dropout(ptr(X), X.stride(0), X.shape[0], X.shape[1], float(p), int(seed), int(offset), ptr(out),
-                               out.stride(0), stream_ptr()))
+    check(lib().fitgnn_dropout(C.c_void_p(X.data_ptr()), X.stride(0), X.shape[0], X.shape[1], float(p), int(seed), int(offset),
+                               ptr(out), out.stride(0), stream_ptr()))
     return out
 
 
@@ -348,7 +373,8 @@ def elu_dropout_backward(G, H, act=ACT_ELU, p=0.0, seed=0, offset=0):
     G = G if G.stride(1) == 1 else G.contiguous()
     H = H if H.stride(1) == 1 else H.contiguous()
     out = torch.empty(G.shape, dtype=torch.float32, device=G.device)
-    check(lib().fitgnn_elu_dropout_backward(ptr(G), G.stride(0), ptr(H), H.stride(0), G.shape[0], G.shape[1], act, float(p),
+    check(lib().fitgnn_elu_dropout_backward(C.c_void_p(G.data_ptr()), G.stride(0), C.c_void_p(H.data_ptr()), H.stride(0),
+                                            G.shape[0], G.shape[1], act, float(p),
                                             int(seed), int(offset), ptr(out), out.stride(0), stream_ptr()))
     return out
 

@@ -166,6 +166,14 @@ int fitgnn_spmm_symnorm_blocked(const int32_t* rowptr, const int32_t* col, const
 /* row_order (device, [n_rows], may be NULL = identity): a permutation of the pack rows that keeps every block's rows
  * together (positions blk_ptr[b]..blk_ptr[b+1] hold block b's rows) — e.g. sorted by row length inside each block, so
  * that the rows a warp works on at the same time have similar lengths.  Results do not depend on it. */
+/* The same aggregation for DENSE blocks on the tensor cores: inside a block Â = D·M·D with M the 0/1 (small-integer)
+ * adjacency — exact in bf16 — so every 128 x 128 piece of M times the block's D·X rows (bf16 hi/lo planes, 2^-17) is a small
+ * dense MMA with fp32 accumulation; per CSR entry nothing is gathered at all.  For cluster_node packs (utils.py:190-233,
+ * ~25 % dense subgraphs).  Sums run in MMA order: results agree with fitgnn_spmm_symnorm to ~1e-6 relative, not bit for bit. */
+int fitgnn_spmm_symnorm_mma(const int32_t* rowptr, const int32_t* col, const float* dinv,
+                            const float* X, int64_t ldx, int width, const int32_t* src_index,
+                            const int32_t* blk_ptr, int64_t n_blk, const float* bias, int act,
+                            void* Y, void* Y_lo, int64_t ldy, void* stream);
 /* Same with the high-degree rows split across a CTA: hub_list (from fitgnn_spmm_hubs) holds the output
  * indices i whose row has >= hub_deg entries; the warp-per-row pass skips them. */
 int fitgnn_spmm_hubs(const int32_t* rowptr, const int32_t* out_rows, int64_t n_out, int hub_deg,
@@ -288,6 +296,10 @@ int fitgnn_gemm_head_rows_peers(const void* A_hi, const void* A_lo, int64_t lda,
                                 const void* W_lo, int64_t ldw, const float* bias, int64_t M, int K,
                                 int N, int act, int head, const int32_t* row_map,
                                 float* const* host_peer_bases, int n_peers, int64_t ldy, void* stream);
+/* fitgnn_peer_push: copy `bytes` (multiple of 16) from this rank's slot `src` to host_dst[0..n_dst) (the same slot in
+ * the peers' buffers) with a small kernel of n_ctas CTAs (0 = 16) that streams the slot through shared memory with bulk
+ * copies — meant for a side stream, behind the next step's compute (dist.PeerGather 'push' exchange). */
+int fitgnn_peer_push(const void* src, void* const* host_dst, int n_dst, size_t bytes, int n_ctas, void* stream);
 int fitgnn_peer_alloc(size_t bytes, void** dev_ptr, uint8_t* handle_out /*[64] host*/);
 int fitgnn_peer_open(const uint8_t* handle /*[64] host*/, void** dev_ptr);
 int fitgnn_peer_close(void* dev_ptr);

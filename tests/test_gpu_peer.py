@@ -83,17 +83,21 @@ def _rank_main(rank, world, port, ret):
         err = float((got - full).abs().max())
         ret[(rank, step)] = err
         dist.barrier()
-    # copy-engine exchange: head into the local slot, pushes + barrier on the side stream
-    for step in range(3):
+    # overlapped exchange: head into the local slot, then the push kernel / the copy engines + barrier on the side stream
+    for step in range(6):
         b = step % 2
         pgather.acquire(b)
+        pgather.tensors[b].zero_()  # stale data must not survive: only this step's pushes can make the check pass
+        torch.cuda.synchronize()
+        dist.barrier()
         f(X, out=shard.slot(pgather.tensors[b], 0))
-        pgather.exchange_async(b)
+        pgather.exchange_async(b, engine="push" if step < 3 else "ce", push_ctas=3)
         pgather.wait(b)
         torch.cuda.synchronize()
         dist.barrier()
         got = pgather.tensors[b].view(-1, Cp)[shard.node_index(d)][:, :Cc]
         ret[(rank, 10 + step)] = float((got - full).abs().max())
+        pgather.release(b)
         dist.barrier()
     del got
     pgather.tensors = None
@@ -113,4 +117,4 @@ def test_two_ranks_exchange_through_peer_buffers(fg):
     for p in procs:
         p.join(300)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    assert len(ret) == 12 and max(ret.values()) < 1e-5, dict(ret)
+    assert len(ret) == 18 and max(ret.values()) < 1e-5, dict(ret)

@@ -64,7 +64,10 @@ def test_streamed_forward_equals_whole_pack_forward(fg, mode, precision):
     assert len(fwd.parts) >= 4
     got = fwd(Xg)
     assert got.shape == want.shape
-    assert torch.equal(got, want[:, :C])  # same kernels, same per-row arithmetic -> bit-identical
+    if mode == "none":
+        assert torch.equal(got, want[:, :C])  # same kernels, same per-row arithmetic -> bit-identical
+    else:  # dense packs aggregate on the tensor cores: the summation order depends on a subgraph's offset inside its block
+        assert float((got - want[:, :C]).abs().max()) <= 1e-5 * float(want.abs().max())
 
 
 def test_hybrid_heavy_tailed_pack_matches_oracle_and_classic(fg):
@@ -370,10 +373,30 @@ def test_blocked_spmm_cluster_pack_and_engine_switch(fg):
     a = fg.ops.spmm_symnorm(pack.rowptr, pack.col, pack.dinv, Xg, F, pack.gid, split=False)
     c = fg.ops.spmm_symnorm_blocked(pack.rowptr, pack.col, pack.dinv, Xg, blk, F, pack.gid, split=False)
     assert torch.equal(a, c)
+    for width, src, Xin in ((F, pack.gid, Xg), (512, None, torch.randn(pack.n_rows, 512, device=dev())), (36, None, torch.randn(pack.n_rows, 36, device=dev()))):
+        ref = fg.ops.spmm_symnorm(pack.rowptr, pack.col, pack.dinv, Xin, width, src)
+        bias = torch.randn(width, device=dev())
+        for split in (False, True):
+            if split and width % 8:
+                continue
+            m = fg.ops.spmm_symnorm_mma(pack.rowptr, pack.col, pack.dinv, Xin, blk, width, src, split=split)
+            m = (m[0].float() + m[1].float()) if split else m
+            assert float((m - ref).abs().max()) <= 2e-5 * float(ref.abs().max()), (width, split)  # bf16 hi/lo sources: 2^-17
+        refb = fg.ops.spmm_symnorm(pack.rowptr, pack.col, pack.dinv, Xin, width, src, bias, fg.ops.ACT_ELU)
+        mb = fg.ops.spmm_symnorm_mma(pack.rowptr, pack.col, pack.dinv, Xin, blk, width, src, bias, fg.ops.ACT_ELU)
+        assert float((mb - refb).abs().max()) <= 2e-5 * float(refb.abs().max())
+    # blocks with more than 128 rows (tiled M pieces) and duplicate edges (counts > 1)
+    big = fg.ops.row_blocks(pack.sub_ptr, pack.n_rows, window=512)
+    assert int((big[1:] - big[:-1]).max()) > 300
+    ref = fg.ops.spmm_symnorm(pack.rowptr, pack.col, pack.dinv, Xg, F, pack.gid)
+    m = fg.ops.spmm_symnorm_mma(pack.rowptr, pack.col, pack.dinv, Xg, big, F, pack.gid)
+    assert float((m - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
     sd = fg.synth.init_state_dict(F, 512, 47, seed=6)
     on = fg.PackedForward(pack, sd)
+    lds = fg.PackedForward(pack, sd, dense_spmm="lds")
     off = fg.PackedForward(pack, sd, blocked_spmm=False)
     assert on._blk is not None and off._blk is None
+    assert float((lds(Xg) - off(Xg)).abs().max()) <= 1e-5 * float(off(Xg).abs().max())
     # (not bit-identical in general: the generic path hands rows with >= 256 entries to the hub kernel, which sums them
     # in a different order)
     a_, b_ = on(Xg), off(Xg)
