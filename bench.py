@@ -66,11 +66,11 @@ def parse():
                         "auto = p2p up to 4 GPUs, ce above (measured)")
     p.add_argument("--push-ctas", type=int, default=16, help="CTAs of the peer-push kernel (--collective push)")
     p.add_argument("--chunks", type=int, default=1, help="N>1: chunks per rank; chunk c's all-gather overlaps chunk c+1")
-    p.add_argument("--modes", default="none_heavy_tail,cluster,train",
+    p.add_argument("--modes", default="none_heavy_tail,cluster,train,per_query",
                    help="N=1: extra blocks measured after the headline (comma separated, '' = none): none_heavy_tail = same "
                         "graph shape with power-law subgraph sizes (hybrid fused + classic schedule); cluster = the headline "
                         "graph with cluster_node augmentation (sharded pack, streamed forward); train = one GD training step "
-                        "(forward + backward + Adam) on the headline pack")
+                        "(forward + backward + Adam) on the headline pack; per_query = the reference's per-sample latency loop")
     p.add_argument("--only-modes", action="store_true", help="skip the headline measurement (profiling the --modes blocks)")
     p.add_argument("--mode-steps", type=int, default=0, help="timed steps of the --modes blocks (0 = min(--steps, 5))")
     p.add_argument("--max-rows", type=int, default=1 << 22, help="rows per shard of the streamed forward (--modes blocks)")
@@ -478,6 +478,66 @@ def mode_train(args, fg, device, n, F, C, ei, part, k, X, precision, steps, samp
             "clocks": sampler.summary(m0, m1) if sampler else None}
 
 
+def mode_per_query(args, fg, device, n, F, C, ei, part, k, X, sd, precision, sampler):
+    """The reference's own inference-time measurement (inference.py:672-688): ONE subgraph forward per queried node, timer
+    around `model(x, edge_index)` only (the subgraph and its features are on the device before the timer starts), first sample
+    dropped, mean of the rest.  Here: the queried node's subgraph as a one-subgraph pack prepared up front (as `graphs[i]` is),
+    timed = the forward's launches — eagerly, and as a CUDA-graph replay — with a device synchronisation per query (the
+    reference's timer has none); the CPU arm runs the oracle's per-query forward on the same queries."""
+    from oracle import fitgnn_oracle as fo
+    n_q = 64
+    g = torch.Generator(device="cpu").manual_seed(args.seed)
+    q_nodes = torch.randint(0, n, (n_q,), generator=g)
+    pack = fg.build_pack(ei, part, k, "none")
+    subs = part.long()[q_nodes.to(device)]
+    fwds, xs, rows_of = [], [], []
+    for s_ in subs.tolist():
+        sp = fg.infer.select_subgraphs(pack, torch.tensor([s_], device=device))
+        f = fg.PackedForward(sp, sd, head="log_softmax", rows="core", precision=precision, fuse_aggregate=False)
+        fwds.append(f)
+        xs.append(f.pad_features(X[sp.gid.long()].contiguous()))  # the subgraph's own x rows (graphs[i].x)
+        rows_of.append(sp)
+        # the one-subgraph pack reads its features directly: gid := identity
+        import dataclasses
+        f.pack = dataclasses.replace(sp, gid=torch.arange(sp.n_rows, dtype=torch.int32, device=device), n_src=sp.n_rows)
+    def run(i):
+        return fwds[i](xs[i])
+    for i in range(n_q):
+        run(i)
+    torch.cuda.synchronize()
+    t_eager = []
+    for i in range(n_q):
+        t0 = time.perf_counter(); out = run(i); torch.cuda.synchronize(); t_eager.append(time.perf_counter() - t0)
+    graphs = [fwds[i].capture(xs[i]) for i in range(n_q)]
+    torch.cuda.synchronize()
+    t_graph = []
+    for i in range(n_q):
+        t0 = time.perf_counter(); graphs[i].graph.replay(); torch.cuda.synchronize(); t_graph.append(time.perf_counter() - t0)
+    # CPU arm + parity on the same queries
+    ei_c, part_c, X_c = ei.cpu().numpy(), part.cpu().numpy(), X.cpu().numpy()
+    sub_list = fo.subgraphs_from_partition(ei_c, X_c, part_c, subs.cpu().numpy())
+    sd_c = {k_: v.cpu() for k_, v in sd.items()}
+    t_cpu, worst = [], 0.0
+    torch.set_num_threads(os.cpu_count() or 1)
+    for i, sg in enumerate(sub_list):
+        x_, e_ = torch.as_tensor(sg["x"]), torch.as_tensor(sg["edge_index"])
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            want = fo.classify_node(sd_c, x_, e_)
+        t_cpu.append(time.perf_counter() - t0)
+        got = graphs[i].static_out[:, :C].cpu()
+        worst = max(worst, float((got - want).abs().max() / max(1.0, float(want.abs().max()))))
+    if worst > PARITY_RTOL:
+        raise SystemExit(f"bench: PARITY FAILURE per_query max_rel_err {worst}")
+    rows = [int(p_.n_rows) for p_ in rows_of]
+    return {"workload": f"{n_q} random query nodes, one subgraph forward each (inference.py:672-688), mode none",
+            "queries": n_q, "subgraph_rows_mean": float(np.mean(rows)), "subgraph_rows_max": int(max(rows)),
+            "latency_us_eager_mean": float(np.mean(t_eager[1:]) * 1e6), "latency_us_graph_replay_mean": float(np.mean(t_graph[1:]) * 1e6),
+            "launches_per_query": 5, "cpu_latency_us_mean": float(np.mean(t_cpu[1:]) * 1e6), "cpu_cores": os.cpu_count(),
+            "timer": "perf_counter around the forward incl. a device synchronise; first query dropped (inference.py:688)",
+            "parity": {"max_rel_err": worst, "rtol": PARITY_RTOL, "ok": True, "against": "oracle per-query forward, same queries"}}
+
+
 def main_ours(args):
     import torch.distributed as dist
 
@@ -504,6 +564,8 @@ def main_ours(args):
                 res[m] = mode_none_heavy_tail(args, fg, device, n, workload_shape(args.workload)[1], F, C, sd, precision, k_steps, None)
             elif m == "train":
                 res[m] = mode_train(args, fg, device, n, F, C, ei, part, k, X, precision, k_steps, None)
+            elif m == "per_query":
+                res[m] = mode_per_query(args, fg, device, n, F, C, ei, part, k, X, sd, precision, None)
             else:
                 res[m] = mode_cluster(args, fg, device, n, F, C, ei, part, cw, k, X, sd, precision, k_steps, None)
             torch.cuda.empty_cache()
@@ -883,6 +945,8 @@ def main_ours(args):
                 line["modes"][m] = mode_cluster(args, fg, device, n, F, C, ei_keep, part, cw, k, X, sd, precision, k_steps, sampler2)
             elif m == "train":
                 line["modes"][m] = mode_train(args, fg, device, n, F, C, ei_keep, part, k, X, precision, k_steps, sampler2)
+            elif m == "per_query":
+                line["modes"][m] = mode_per_query(args, fg, device, n, F, C, ei_keep, part, k, X, sd, precision, sampler2)
             else:
                 raise SystemExit(f"bench: unknown --modes entry {m!r}")
             torch.cuda.empty_cache()

@@ -8,6 +8,9 @@ for l in open(sys.argv[1]):
                 print(f"   {k:14s} {v['ms']:8.3f} ms {v['GBps']:8.1f} GB/s {v['TFLOPs']:6.1f} TF share {v['share']:.1%}")
             print("   roofline_spmm", round(d["roofline_spmm"]["frac"], 3), d["roofline_spmm"]["kernel"], "clocks", d["clocks"])
         for m, b in d.get("modes", {}).items():
+            if m == "per_query":
+                print("== per_query", {k_: v_ for k_, v_ in b.items() if k_ not in ("workload", "timer")})
+                continue
             if m == "train":
                 print("== train ms %.2f" % b["ms_per_step"], "nodes/s %.3g" % b["value"], "loss", b["loss_first_last"], "gemm_tn", b["gemm_tn"])
                 continue
