@@ -56,7 +56,7 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
                 const float* bias, int64_t M, int K, int N, int act, int head, float* Y, void* Y_lo, int64_t ldy,
                 const uint64_t* agg_desc, const float* agg_dinv, const int32_t* row_map, float* const* peers, int n_peers,
                 const float* row_scale, int agg_defer_scale, cudaStream_t st, int64_t m_batch_rows = 0, int w_batch_rows = 0,
-                int64_t w_rows_total = 0);
+                int64_t w_rows_total = 0, int in_f16 = 0, int out_f16 = 0);
 
 int gcn_layer_fused(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X, int64_t ldx, int width,
                     const int32_t* src_index, const int32_t* out_rows, int64_t M, const void* W_hi, const void* W_lo,
@@ -198,4 +198,51 @@ extern "C" int fitgnn_gcn_layer_fused(const int32_t* rowptr, const int32_t* col,
   if (n_out == 0) return FITGNN_OK;
   return gcn_layer_fused(rowptr, col, dinv, X, ldx, width, src_index, out_rows, n_out, W_hi, W_lo, ldw, bias, N, act,
                          static_cast<float*>(Y), Y_lo, ldy, as_stream(stream));
+}
+
+// ---- FITGNN_GEMM_FP16X2: the A operand is ONE fp16 plane, W an fp16 hi/lo pair (see include/fitgnn.h) ------------------
+extern "C" int fitgnn_gemm_f16(const void* A, int64_t lda, const void* W_hi, const void* W_lo, int64_t ldw,
+                               const float* row_scale, const float* bias, int64_t M, int K, int N, int act, int head, void* Y,
+                               int64_t ldy, int out_f16, const int32_t* row_map, void* stream) {
+  FG_REQUIRE(A && W_hi && W_lo && Y && M >= 0 && K > 0 && N > 0, FITGNN_EINVAL, "gemm_f16: bad arguments (M=%lld K=%d N=%d)",
+             (long long)M, K, N);
+  FG_REQUIRE(lda >= K && ldw >= K && ldy >= N, FITGNN_EINVAL, "gemm_f16: leading dimension smaller than the extent");
+  FG_REQUIRE(act == FITGNN_ACT_NONE || act == FITGNN_ACT_ELU, FITGNN_EINVAL, "gemm_f16: unknown act %d", act);
+  FG_REQUIRE(head >= FITGNN_HEAD_IDENTITY && head <= FITGNN_HEAD_SOFTMAX, FITGNN_EINVAL, "gemm_f16: unknown head %d", head);
+  if (M == 0) return FITGNN_OK;
+  return gemm_bf16x3(A, nullptr, lda, W_hi, W_lo, ldw, bias, M, K, N, act, head, static_cast<float*>(Y), nullptr, ldy, nullptr,
+                     nullptr, row_map, nullptr, 0, row_scale, 0, as_stream(stream), 0, 0, 0, 1, out_f16 ? 1 : 0);
+}
+
+extern "C" int fitgnn_gcn_transform_aggregate_f16(int in_f16, const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi,
+                                                  const void* W_lo, int64_t ldw, const float* bias, int64_t M, int K, int N,
+                                                  int act, const uint64_t* agg_desc, const float* dinv, int defer_row_scale,
+                                                  void* Y, int64_t ldy, void* stream) {
+  FG_REQUIRE(A_hi && W_hi && W_lo && Y && agg_desc && dinv && M >= 0 && K > 0 && N > 0, FITGNN_EINVAL,
+             "gcn_transform_aggregate_f16: bad arguments (M=%lld K=%d N=%d)", (long long)M, K, N);
+  FG_REQUIRE(in_f16 ? !A_lo : A_lo != nullptr, FITGNN_EINVAL, "gcn_transform_aggregate_f16: A_lo must match in_f16");
+  FG_REQUIRE(lda >= K && ldw >= K && ldy >= N, FITGNN_EINVAL, "gcn_transform_aggregate_f16: leading dimension too small");
+  FG_REQUIRE(act == FITGNN_ACT_NONE || act == FITGNN_ACT_ELU, FITGNN_EINVAL, "gcn_transform_aggregate_f16: unknown act %d", act);
+  if (M == 0) return FITGNN_OK;
+  return gemm_bf16x3(A_hi, A_lo, lda, W_hi, W_lo, ldw, bias, M, K, N, act, FITGNN_HEAD_IDENTITY, static_cast<float*>(Y), nullptr,
+                     ldy, agg_desc, dinv, nullptr, nullptr, 0, nullptr, defer_row_scale, as_stream(stream), 0, 0, 0,
+                     in_f16 ? 1 : 0, 1);
+}
+
+extern "C" int fitgnn_gemm_f16_head_rows_peers(const void* A, int64_t lda, const void* W_hi, const void* W_lo, int64_t ldw,
+                                               const float* bias, int64_t M, int K, int N, int act, int head,
+                                               const int32_t* row_map, float* const* host_peer_bases, int n_peers, int64_t ldy,
+                                               void* stream) {
+  FG_REQUIRE(A && W_hi && W_lo && row_map && host_peer_bases && M >= 0 && K > 0 && N > 0, FITGNN_EINVAL,
+             "gemm_f16_head_rows_peers: bad arguments (M=%lld K=%d N=%d)", (long long)M, K, N);
+  FG_REQUIRE(n_peers >= 1 && n_peers <= 8, FITGNN_EINVAL, "gemm_f16_head_rows_peers: 1..8 peers (got %d)", n_peers);
+  for (int p = 0; p < n_peers; ++p)
+    FG_REQUIRE(host_peer_bases[p], FITGNN_EINVAL, "gemm_f16_head_rows_peers: peer base %d is null", p);
+  FG_REQUIRE(lda >= K && ldw >= K && ldy >= N, FITGNN_EINVAL, "gemm_f16_head_rows_peers: leading dimension too small");
+  FG_REQUIRE(act == FITGNN_ACT_NONE || act == FITGNN_ACT_ELU, FITGNN_EINVAL, "gemm_f16_head_rows_peers: unknown act %d", act);
+  FG_REQUIRE(head >= FITGNN_HEAD_IDENTITY && head <= FITGNN_HEAD_SOFTMAX, FITGNN_EINVAL,
+             "gemm_f16_head_rows_peers: unknown head %d", head);
+  if (M == 0) return FITGNN_OK;
+  return gemm_bf16x3(A, nullptr, lda, W_hi, W_lo, ldw, bias, M, K, N, act, head, nullptr, nullptr, ldy, nullptr, nullptr, row_map,
+                     host_peer_bases, n_peers, nullptr, 0, as_stream(stream), 0, 0, 0, 1, 0);
 }

@@ -86,6 +86,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2_rn(float a, float b) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
 }
+// two fp32 -> packed fp16x2 (round to nearest even, overflow saturates to the largest finite fp16), `a` in the low half
+__device__ __forceinline__ uint32_t pack_f16x2_rn(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
 // hi/lo bf16 split of two fp32 values: hi = rn_bf16(x), lo = rn_bf16(x - hi), each packed as bf16x2 (x0 low half)
 __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   hi = pack_bf16x2_rn(x0, x1);

@@ -6,6 +6,7 @@
 // global memory and transposed into shared memory so the inner product reads float4 rows.
 // Also: the row-wise (log-)softmax head and the fp32 -> bf16 hi/lo split.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace fitgnn {
@@ -142,6 +143,20 @@ __global__ void split_bf16_kernel(const float* __restrict__ X, int64_t ldx, int6
   lo[idx] = __float2bfloat16_rn(x - __bfloat162float(h));
 }
 
+// fp32 -> fp16 hi/lo planes (hi = rn(x), lo = rn(x - hi): 22 significant bits; lo == nullptr: the hi plane only)
+__global__ void split_f16_kernel(const float* __restrict__ X, int64_t ldx, int64_t rows, int cols, __half* __restrict__ hi,
+                                 __half* __restrict__ lo, int64_t ldo) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r = idx / ldo;
+  const int c = (int)(idx % ldo);
+  if (r >= rows) return;
+  const float x = c < cols ? X[r * ldx + c] : 0.f;
+  const float xc = fminf(fmaxf(x, -65504.f), 65504.f);  // saturate instead of inf
+  const __half h = __float2half_rn(xc);
+  hi[idx] = h;
+  if (lo) lo[idx] = __float2half_rn(xc - __half2float(h));
+}
+
 int gemm_fp32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, int64_t M, int K, int N,
               int act, float* Y, int64_t ldy, cudaStream_t st) {
   dim3 grid((unsigned)ceil_div(M, GM_BM), (unsigned)ceil_div(N, GM_BN));
@@ -169,6 +184,17 @@ extern "C" int fitgnn_split_bf16(const float* X, int64_t ldx, int64_t rows, int 
   const int64_t total = rows * ldo;
   split_bf16_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, as_stream(stream)>>>(
       X, ldx, rows, cols, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), ldo);
+  FG_LAUNCH_CHECK();
+  return FITGNN_OK;
+}
+
+extern "C" int fitgnn_split_f16(const float* X, int64_t ldx, int64_t rows, int cols, void* hi, void* lo, int64_t ldo,
+                                void* stream) {
+  FG_REQUIRE(X && hi && rows >= 0 && cols >= 0 && ldo >= cols && ldx >= cols, FITGNN_EINVAL, "split_f16: bad arguments");
+  if (rows == 0 || ldo == 0) return FITGNN_OK;
+  const int64_t total = rows * ldo;
+  split_f16_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, as_stream(stream)>>>(X, ldx, rows, cols, static_cast<__half*>(hi),
+                                                                                  static_cast<__half*>(lo), ldo);
   FG_LAUNCH_CHECK();
   return FITGNN_OK;
 }

@@ -77,6 +77,12 @@ struct EpiArgs {
   int64_t m_batch_rows;
   int w_batch_rows;
   int64_t w_rows_total;
+  // Operand / output formats.  a_planes = 2: A is a bf16 hi/lo pair (3 MMAs per k-step: hi*hi + lo*hi + hi*lo, the default).
+  // a_planes = 1 with f16 = 1 (FITGNN_GEMM_FP16X2): A is ONE fp16 plane (11-bit significand), W an fp16 hi/lo pair; 2 MMAs per
+  // k-step (A*W_hi + A*W_lo), no A_lo load.  out_f16 = 1: the result is stored as ONE fp16 plane (the next FP16X2 product's A).
+  int a_planes;
+  int f16;
+  int out_f16;
 };
 constexpr int EPI_WARP0 = 2;
 constexpr int ACC_STAGES = 2;
@@ -156,6 +162,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M x N
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// same with fp16 operands (format code 0)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
@@ -267,7 +278,10 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
   constexpr uint32_t B_PLANE_BYTES = (uint32_t)B_ROWS * BLOCK_K * 2;
   constexpr uint32_t STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;
   constexpr int TMEM_COLS = tmem_cols(ACC_STAGES * BLOCK_N);
-  constexpr uint32_t IDESC = umma_idesc_bf16(CTA2 ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
+  constexpr uint32_t IDESC_BF16 = umma_idesc_bf16(CTA2 ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
+  constexpr uint32_t IDESC_F16 = umma_idesc_f16(CTA2 ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
+  const uint32_t IDESC = ea.f16 ? IDESC_F16 : IDESC_BF16;
+  const bool a_single = ea.a_planes == 1;
   static_assert(!CTA2 || (!GATHER && BLOCK_N % 32 == 0), "CTA pairs: streaming plan, UMMA N multiple of 32 for M=256");
   const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
@@ -375,20 +389,21 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t dst = smem_base + stage * stage_bytes_rt;
+          const uint32_t tx_bytes = stage_bytes_rt - (a_single ? A_PLANE_BYTES : 0u);  // a single-plane A has no lo load
           if (CTA2) {
             // both CTAs' bytes are counted on the LEADER's full barrier (its MMA thread consumes both halves)
             const uint32_t lbar = mapa_rank(full_bar(stage), 0);
-            if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * stage_bytes_rt);
+            if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * tx_bytes);
             tma_load_2d_pair(dst, &map_a_hi, lbar, kb * BLOCK_K, m0);
-            tma_load_2d_pair(dst + A_PLANE_BYTES, &map_a_lo, lbar, kb * BLOCK_K, m0);
+            if (!a_single) tma_load_2d_pair(dst + A_PLANE_BYTES, &map_a_lo, lbar, kb * BLOCK_K, m0);
             tma_load_2d_pair(dst + 2 * A_PLANE_BYTES, &map_w_hi, lbar, kb * BLOCK_K, n0 + (int)cta_rank * B_ROWS);
             tma_load_2d_pair(dst + 2 * A_PLANE_BYTES + B_PLANE_BYTES, &map_w_lo, lbar, kb * BLOCK_K, n0 + (int)cta_rank * B_ROWS);
             if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
             continue;
           }
-          mbar_arrive_expect_tx(full_bar(stage), stage_bytes_rt);
+          mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
           tma_load_2d(dst, &map_a_hi, full_bar(stage), kb * BLOCK_K, m0);
-          tma_load_2d(dst + A_PLANE_BYTES, &map_a_lo, full_bar(stage), kb * BLOCK_K, m0);
+          if (!a_single) tma_load_2d(dst + A_PLANE_BYTES, &map_a_lo, full_bar(stage), kb * BLOCK_K, m0);
           if (!w_stationary) {
             tma_load_2d(dst + 2 * A_PLANE_BYTES, &map_w_hi, full_bar(stage), kb * BLOCK_K, n0);
             tma_load_2d(dst + 2 * A_PLANE_BYTES + B_PLANE_BYTES, &map_w_lo, full_bar(stage), kb * BLOCK_K, n0);
@@ -423,11 +438,11 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
             const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);  // +32 bytes per K=16 step inside the swizzle row
             if (CTA2) {
               umma_bf16_pair(tmem_d, d_a_hi + adv, d_w_hi + adv, IDESC, (kb | k) != 0);
-              umma_bf16_pair(tmem_d, d_a_lo + adv, d_w_hi + adv, IDESC, 1);
+              if (!a_single) umma_bf16_pair(tmem_d, d_a_lo + adv, d_w_hi + adv, IDESC, 1);
               umma_bf16_pair(tmem_d, d_a_hi + adv, d_w_lo + adv, IDESC, 1);
             } else {
               umma_bf16(tmem_d, d_a_hi + adv, d_w_hi + adv, IDESC, (kb | k) != 0);
-              umma_bf16(tmem_d, d_a_lo + adv, d_w_hi + adv, IDESC, 1);
+              if (!a_single) umma_bf16(tmem_d, d_a_lo + adv, d_w_hi + adv, IDESC, 1);
               umma_bf16(tmem_d, d_a_hi + adv, d_w_lo + adv, IDESC, 1);
             }
           }
@@ -798,7 +813,17 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
           // 2 KB boxes of 64-byte rows, chunk c of row r at c ^ ((r >> 1) & 3).
           if (lane == 0) bulk_wait_read<0>();  // the store(s) that last read this buffer have finished reading
           __syncwarp();
-          if (tma_store == 2) {
+          if (tma_store == 3) {  // ONE fp16 plane (64-byte rows, the bf16 planes' swizzle)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t h[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) h[u] = pack_f16x2_rn(v[8 * j + 2 * u], v[8 * j + 2 * u + 1]);
+              const uint32_t a = buf + lane * 64 + ((uint32_t)j ^ (uint32_t)((lane >> 1) & 3)) * 16;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3])
+                           : "memory");
+            }
+          } else if (tma_store == 2) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint32_t hi[4], lo[4];
@@ -948,7 +973,12 @@ static int launch(const GatherArgs& ga, const EpiArgs& ea, const CUtensorMap& a_
   int tma_store = ((ldy * 4) % 16 == 0 && ((uintptr_t)Y & 15) == 0) ? 1 : 0;
   y_map = w_hi;  // placeholders when unused
   y_lo_map = w_hi;
-  if (Y_lo) {
+  if (ea.out_f16) {
+    FG_REQUIRE(!Y_lo && !ea.row_map && (ldy * 2) % 16 == 0 && ((uintptr_t)Y & 15) == 0, FITGNN_EUNSUP,
+               "gemm: fp16-plane output needs a 16-byte aligned plane with a pitch that is a multiple of 8, and no row map");
+    tma_store = 3;
+    FG_TRY(make_store_map_bf16(&y_map, Y, M, N, ldy));  // 16-bit elements: the map does not care which
+  } else if (Y_lo) {
     FG_REQUIRE((ldy * 2) % 16 == 0 && ((uintptr_t)Y & 15) == 0 && ((uintptr_t)Y_lo & 15) == 0, FITGNN_EUNSUP,
                "gemm_bf16x3: split output needs 16-byte aligned planes and a pitch that is a multiple of 8");
     tma_store = 2;
@@ -1038,7 +1068,11 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
                 const float* bias, int64_t M, int K, int N, int act, int head, float* Y, void* Y_lo, int64_t ldy,
                 const uint64_t* agg_desc, const float* agg_dinv, const int32_t* row_map, float* const* peers, int n_peers,
                 const float* row_scale, int agg_defer_scale, cudaStream_t st, int64_t m_batch_rows, int w_batch_rows,
-                int64_t w_rows_total) {
+                int64_t w_rows_total, int in_f16, int out_f16) {
+  FG_REQUIRE(!in_f16 || !A_lo, FITGNN_EINVAL, "gemm: FP16X2 takes ONE fp16 A plane (A_lo must be NULL)");
+  FG_REQUIRE(in_f16 || A_lo, FITGNN_EINVAL, "gemm: BF16X3 needs the A_lo plane");
+  FG_REQUIRE(!out_f16 || (head == FITGNN_HEAD_IDENTITY && !Y_lo && !row_map), FITGNN_EUNSUP,
+             "gemm: an fp16-plane output cannot carry a head, a lo plane or a row map");
   FG_REQUIRE(m_batch_rows == 0 || (m_batch_rows % 256 == 0 && M % m_batch_rows == 0 && w_batch_rows >= N && !agg_desc &&
                                    !row_map && head == FITGNN_HEAD_IDENTITY && w_rows_total >= (M / m_batch_rows) * w_batch_rows),
              FITGNN_EINVAL, "gemm_bf16x3: bad batching (m_batch_rows must be a multiple of 256 dividing M)");
@@ -1054,10 +1088,10 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
   const int sms = sm_count();
   CUtensorMap a_hi, a_lo;
   FG_TRY(tc::make_map(&a_hi, A_hi, M, K, lda, tc::BLOCK_M));
-  FG_TRY(tc::make_map(&a_lo, A_lo, M, K, lda, tc::BLOCK_M));
+  FG_TRY(tc::make_map(&a_lo, A_lo ? A_lo : A_hi, M, K, lda, tc::BLOCK_M));  // unused with a single-plane A
   const tc::GatherArgs ga{};
   tc::EpiArgs ea{reinterpret_cast<const unsigned long long*>(agg_desc), agg_dinv, row_map, {}, n_peers, 0, row_scale,
-                 agg_defer_scale, m_batch_rows, w_batch_rows, w_rows_total};
+                 agg_defer_scale, m_batch_rows, w_batch_rows, w_rows_total, in_f16 ? 1 : 2, in_f16 ? 1 : 0, out_f16 ? 1 : 0};
   for (int p = 0; p < n_peers; ++p) ea.peers[p] = peers[p];
   if (n_peers > 0) Y = peers[0];  // alignment checks / unused fallbacks refer to a real buffer
   if (row_map && N <= 64 && ldy == (N + 3) / 4 * 4 && tuning().head_bulk) {
@@ -1108,7 +1142,7 @@ int gcn_layer_fused(const int32_t* rowptr, const int32_t* col, const float* dinv
   tc::GatherArgs ga{rowptr, col, dinv, X, src_index, out_rows, ldx, width / 4};
   CUtensorMap dummy;
   FG_TRY(tc::make_map(&dummy, W_hi, N, K, ldw, 16));  // placeholder for the unused A maps
-  const tc::EpiArgs ea{nullptr, nullptr, nullptr, {}, 0, 0, nullptr, 0, 0, 0, 0};
+  const tc::EpiArgs ea{nullptr, nullptr, nullptr, {}, 0, 0, nullptr, 0, 0, 0, 0, 2, 0, 0};
   return tc::launch<256, true, false>(ga, ea, dummy, dummy, W_hi, W_lo, ldw, bias, M, K, N, act, FITGNN_HEAD_IDENTITY, Y,
                                       Y_lo, ldy, sms, st);
 }

@@ -40,11 +40,15 @@ class PackedForward:
         ~2^-17 relative operand error) or 'fp32' (exact-fp32 CUDA-core GEMM: the numerics anchor, explicit opt-in).
         out_map (int32 [n_out]): output row i is written to row out_map[i] of the `out` tensor passed to __call__
         (which then is required) — how StreamedForward lets several forwards fill one result in subgraph_list order."""
-        if precision not in ("bf16x3", "fp32"):
+        if precision not in ("bf16x3", "fp32", "fp16x2"):
             raise ValueError(f"precision={precision!r}")
         self.pack = pack
         dev = pack.device
-        self.precision = ops.GEMM_BF16X3 if precision == "bf16x3" else ops.GEMM_FP32
+        # 'fp16x2' (opt-in): bf16x3 for the first layer, then the HIDDEN STATE travels as one fp16 plane (half the bytes, two MMAs
+        # per product instead of three; 2^-11 per element — include/fitgnn.h FITGNN_GEMM_FP16X2).  Fused schedule only: a pack
+        # that is not eligible for it runs plain bf16x3.
+        self.f16_hidden = precision == "fp16x2"
+        self.precision = ops.GEMM_FP32 if precision == "fp32" else ops.GEMM_BF16X3
         self.kalign = 8 if self.precision == ops.GEMM_BF16X3 else 4
         self.L = conv_layers(state_dict)
         assert self.L >= 1
@@ -124,6 +128,12 @@ class PackedForward:
                     self.W0_fold = self._prep_weight(torch.cat([w0, self.b[0][:, None]], 1))
         if fuse_aggregate is True and self.apack is None:
             raise ValueError("fuse_aggregate=True but the pack / model is not eligible for the fused aggregation")
+        if self.f16_hidden and self.apack is None:
+            self.f16_hidden = False
+        if self.f16_hidden:  # layers >= 1 and the head take fp16 hi/lo weights (the first layer's A operand stays bf16 hi/lo)
+            for i in range(1, self.L):
+                self.W[i] = ops.split_f16(state_dict[f"conv.{i}.lin.weight"].detach().to(**f32).contiguous(), ldo=self._kpad(self.H))
+            self.Wl = ops.split_f16(state_dict["lt1.weight"].detach().to(**f32).contiguous(), ldo=self._kpad(self.H))
         self.out_map = None
         if out_map is not None:
             assert with_head, "out_map needs the head"
@@ -314,11 +324,36 @@ class PackedForward:
             # that consumer is the plain last transform
             defer = self.defer_scale and i == self.L - 2
             self.launches += 1
-            A = self._timed(f"gemm{i}_agg", lambda: ops.gcn_transform_aggregate(
-                Ai, Wi, bi, ops.ACT_ELU, ap.agg_desc, ap.dinv, K=Ki, N=self.H, defer_row_scale=defer),
-                nbytes=4 * (M * Ki + Ki * self.H + M * self.H) + 12 * M, flops=2 * M * Ki * self.H)
+            if self.f16_hidden:
+                a_b = 2 if not isinstance(Ai, tuple) else 4  # bytes per element of the A operand
+                A = self._timed(f"gemm{i}_agg", lambda: ops.gcn_transform_aggregate_f16(
+                    Ai, Wi, bi, ops.ACT_ELU, ap.agg_desc, ap.dinv, K=Ki, N=self.H, defer_row_scale=defer),
+                    nbytes=a_b * M * Ki + 4 * Ki * self.H + 2 * M * self.H + 12 * M, flops=2 * M * Ki * self.H)
+            else:
+                A = self._timed(f"gemm{i}_agg", lambda: ops.gcn_transform_aggregate(
+                    Ai, Wi, bi, ops.ACT_ELU, ap.agg_desc, ap.dinv, K=Ki, N=self.H, defer_row_scale=defer),
+                    nbytes=4 * (M * Ki + Ki * self.H + M * self.H) + 12 * M, flops=2 * M * Ki * self.H)
             K = self.H
         i = self.L - 1
+        if self.f16_hidden:
+            self.launches += 2
+            h = self._timed(f"gemm{i}", lambda: ops.gemm_f16(A, self.W[i], self.b[i], ops.ACT_ELU, row_scale=ap.dinv if self.defer_scale else None,
+                                                              out_f16=True, K=K, N=self.H),
+                            nbytes=2 * M * K + 4 * K * self.H + 2 * M * self.H, flops=2 * M * K * self.H)
+            nb16 = 2 * M * self.H + 4 * self.H * self.C + 4 * self.n_out * self.C + 4 * M
+            if peer_ptrs is not None:  # rows go straight into this rank's slot of every rank's gather buffer
+                self._timed("head", lambda: ops.gemm_f16_head_rows_peers(h, self.Wl, self.bl, ops.ACT_NONE, self.head, self._head_map,
+                                                                         peer_ptrs, ops.pad4(self.C), K=self.H, N=self.C),
+                            nbytes=nb16 + 4 * (len(peer_ptrs) - 1) * self.n_out * self.C, flops=2 * M * self.H * self.C)
+                return None
+            view = None
+            if out is None:
+                out = torch.empty(self.n_out, ops.pad4(self.C), dtype=torch.float32, device=X.device)
+                view = out[:, : self.C]
+            self._timed("head", lambda: ops.gemm_f16(h, self.Wl, self.bl, ops.ACT_NONE, self.head, row_map=self._head_map, out=out,
+                                                     K=self.H, N=self.C),
+                        nbytes=nb16, flops=2 * M * self.H * self.C)
+            return out if view is None else view
         h = self._gemm(A, self.W[i], self.b[i], ops.ACT_ELU, N=self.H, K=K, name=f"gemm{i}", split_out=True,
                        row_scale=ap.dinv if self.defer_scale else None)
         view = None

@@ -492,6 +492,64 @@ class _SegmentPoolFn(torch.autograd.Function):
         return gx, None, None, None
 
 
+# ----------------------------------------------------------------------------------------- fp16 hidden state (opt-in)
+def split_f16(X, cols=None, ldo=None, lo=True):
+    """fp32 [rows, cols] -> fp16 (hi, lo) planes [rows, ldo] (lo=False: (hi, None)); padding columns zero."""
+    rows = X.shape[0]
+    cols = X.shape[1] if cols is None else cols
+    ldo = cols if ldo is None else ldo
+    hi = torch.empty(rows, ldo, dtype=torch.float16, device=X.device)
+    lo_t = torch.empty(rows, ldo, dtype=torch.float16, device=X.device) if lo else None
+    check(lib().fitgnn_split_f16(ptr(X), X.stride(0), rows, cols, ptr(hi), ptr(lo_t), ldo, stream_ptr()))
+    return hi, lo_t
+
+
+def gemm_f16(A, W, bias=None, act=ACT_NONE, head=HEAD_IDENTITY, row_scale=None, out_f16=False, row_map=None, out=None,
+             K=None, N=None):
+    """head(act(row_scale * (A·W^T) + bias)) with A ONE fp16 plane [M, K] and W = fp16 (hi, lo) planes (FITGNN_GEMM_FP16X2).
+    out_f16: the result as one fp16 plane (the next product's A); row_map: rows scattered into `out` (fp32, required then)."""
+    w_hi, w_lo = W
+    assert A.dtype == torch.float16 and w_hi.dtype == torch.float16
+    M = A.shape[0]
+    K = A.shape[1] if K is None else K
+    N = w_hi.shape[0] if N is None else N
+    if out is None:
+        assert row_map is None
+        out = torch.empty(M, N if (out_f16 or N % 4 == 0) else pad4(N), dtype=torch.float16 if out_f16 else torch.float32,
+                          device=A.device)
+    check(lib().fitgnn_gemm_f16(ptr(A), A.stride(0), ptr(w_hi), ptr(w_lo), w_hi.stride(0), ptr(row_scale), ptr(bias), M, K, N,
+                                act, head, ptr(out), out.stride(0), int(out_f16), ptr(row_map), stream_ptr()))
+    return out
+
+
+def gemm_f16_head_rows_peers(A, W, bias, act, head, row_map, peer_ptrs, ldy, K=None, N=None):
+    """gemm_head_rows_peers with A one fp16 plane and W = fp16 (hi, lo) planes."""
+    w_hi, w_lo = W
+    M = A.shape[0]
+    K = A.shape[1] if K is None else K
+    N = w_hi.shape[0] if N is None else N
+    assert A.dtype == torch.float16 and row_map.dtype == torch.int32 and row_map.numel() == M
+    bases = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(int(p)) for p in peer_ptrs])
+    check(lib().fitgnn_gemm_f16_head_rows_peers(ptr(A), A.stride(0), ptr(w_hi), ptr(w_lo), w_hi.stride(0), ptr(bias), M, K, N, act,
+                                                head, ptr(row_map), bases, len(peer_ptrs), ldy, stream_ptr()))
+
+
+def gcn_transform_aggregate_f16(A, W, bias, act, agg_desc, dinv, K=None, N=None, defer_row_scale=False):
+    """gcn_transform_aggregate whose result is ONE fp16 plane.  A = bf16 (hi, lo) planes with W = bf16 planes, or A = one
+    fp16 plane with W = fp16 (hi, lo) planes."""
+    w_hi, w_lo = W
+    in_f16 = not isinstance(A, tuple)
+    a_hi, a_lo = (A, None) if in_f16 else A
+    M = a_hi.shape[0]
+    K = a_hi.shape[1] if K is None else K
+    N = w_hi.shape[0] if N is None else N
+    out = torch.empty(M, N, dtype=torch.float16, device=a_hi.device)
+    check(lib().fitgnn_gcn_transform_aggregate_f16(int(in_f16), ptr(a_hi), ptr(a_lo), a_hi.stride(0), ptr(w_hi), ptr(w_lo),
+                                                   w_hi.stride(0), ptr(bias), M, K, N, act, ptr(agg_desc), ptr(dinv),
+                                                   int(defer_row_scale), ptr(out), out.stride(0), stream_ptr()))
+    return out
+
+
 def segment_pool(X, rows, seg_ptr, pool, width=None):
     """Segment max / mean over the selected rows (fitgnn_segment_pool); differentiable w.r.t. X when X requires grad."""
     if torch.is_grad_enabled() and X.requires_grad:

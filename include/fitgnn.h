@@ -52,7 +52,7 @@ enum { FITGNN_POOL_MAX = 0, FITGNN_POOL_MEAN = 1 };
 
 /* GEMM arithmetic.  FP32 = exact fp32 FMA on CUDA cores; BF16X3 = tcgen05 tensor cores on
  * a hi/lo bf16 split of both operands (3 MMAs, ~2^-17 relative operand error). */
-enum { FITGNN_GEMM_FP32 = 0, FITGNN_GEMM_BF16X3 = 1 };
+enum { FITGNN_GEMM_FP32 = 0, FITGNN_GEMM_BF16X3 = 1, FITGNN_GEMM_FP16X2 = 2 /* fitgnn_gemm_f16 & co. only */ };
 
 /*
  * Packed block-diagonal CSR of all subgraphs Gs (replaces the list[Data] built by
@@ -273,6 +273,29 @@ int fitgnn_gemm_rowscale_bias_act_split(int precision, const void* A, const void
                                         const float* row_scale, const float* bias, int64_t M, int K,
                                         int N, int act, int head, void* Y, void* Y_lo, int64_t ldy,
                                         void* stream);
+/* FITGNN_GEMM_FP16X2 — a cheaper operand format for the HIDDEN STATE, opt-in (PackedForward(precision="fp16x2")):
+ * the A operand is ONE fp16 plane (11-bit significand, 2 bytes per element instead of the 4 of a bf16 hi/lo pair), W an fp16
+ * hi/lo pair (fitgnn_split_f16: 22 bits), two MMAs per k-step (A*W_hi + A*W_lo) instead of three, fp32 accumulation.
+ * Relative error of a product: 2^-11 per A element (measured end to end on the products workload: 1.6e-5 of the 1e-3 bound,
+ * profiles/r2_precision_study.md); whether that is acceptable depends on the checkpoint, hence not the default.
+ *   fitgnn_gemm_f16: Y = head(act(row_scale * (A·W^T) + bias)); out_f16 != 0 stores Y as ONE fp16 plane [M, ldy] (the next
+ *     FP16X2 product's A; no head / row map then), else fp32 [M, ldy] (row_map as in fitgnn_gemm_head_rows, may be NULL).
+ *   fitgnn_gcn_transform_aggregate_f16: fitgnn_gcn_transform_aggregate with an fp16-plane OUTPUT; the input is a bf16
+ *     hi/lo pair (in_f16 = 0, W = bf16 planes: the first layer) or an fp16 plane (in_f16 = 1, A_lo = NULL, W = fp16 planes).
+ *   fitgnn_split_f16: fp32 -> fp16 hi/lo planes (lo may be NULL: the hi plane only); values beyond +-65504 saturate. */
+int fitgnn_split_f16(const float* X, int64_t ldx, int64_t rows, int cols, void* hi, void* lo, int64_t ldo, void* stream);
+int fitgnn_gemm_f16(const void* A, int64_t lda, const void* W_hi, const void* W_lo, int64_t ldw,
+                    const float* row_scale, const float* bias, int64_t M, int K, int N, int act, int head,
+                    void* Y, int64_t ldy, int out_f16, const int32_t* row_map, void* stream);
+/* fitgnn_gemm_head_rows_peers with an fp16-plane A operand (FITGNN_GEMM_FP16X2) */
+int fitgnn_gemm_f16_head_rows_peers(const void* A, int64_t lda, const void* W_hi, const void* W_lo, int64_t ldw,
+                                    const float* bias, int64_t M, int K, int N, int act, int head,
+                                    const int32_t* row_map, float* const* host_peer_bases, int n_peers,
+                                    int64_t ldy, void* stream);
+int fitgnn_gcn_transform_aggregate_f16(int in_f16, const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi,
+                                       const void* W_lo, int64_t ldw, const float* bias, int64_t M, int K, int N,
+                                       int act, const uint64_t* agg_desc, const float* dinv, int defer_row_scale,
+                                       void* Y, int64_t ldy, void* stream);
 /* fitgnn_gemm_bias_act (BF16X3) whose output row m is written to Y row row_map[m] and skipped when row_map[m] < 0:
  * drops the padding rows of an aligned pack / scatters lt1's output (network.py:34-35) straight into the caller's
  * row order.  When ldy is N rounded up to a multiple of 4, the pitch-padding columns [N, ldy) of written rows are

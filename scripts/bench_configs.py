@@ -1,7 +1,7 @@
 """Measures the parity-test configurations of BASELINE.json (configs 1-4: Cora / PubMed / Coauthor-Physics / ZINC shaped
 synthetic inputs) on one GPU: pack build, whole-pack forward (eager and CUDA-graph replay), the per-query path, the
 restated reference CPU path on a sample, and the max logit error against the oracle on that sample.
-Writes gpurun_out/configs_r1.md and .json.  Not the headline bench (that is bench.py, config 5)."""
+Writes gpurun_out/configs_r2.md and .json (per-kernel rooflines included).  Not the headline bench (that is bench.py, config 5)."""
 import json
 import os
 import sys
@@ -16,6 +16,9 @@ import fitgnn_b200 as fg  # noqa: E402
 from oracle import fitgnn_oracle as fo  # noqa: E402
 
 DEV = torch.device("cuda:0")
+_pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+_d = json.load(open(_pk)) if os.path.exists(_pk) else {}
+HBM_PEAK, TC_PEAK = _d.get("hbm_gbs", 6650.0), _d.get("bf16_tflops_sustained", 1400.0)
 
 
 def timeit(fn, reps=20, warm=3):
@@ -51,12 +54,25 @@ def node_config(name, mode, sample_batches=8):
     run = fwd.capture(Xg)
     graph_ms = timeit(lambda: run(Xg))
     out = run(Xg).clone()
+    # per-kernel rooflines of the eager forward (CUDA events per launch; algorithmic bytes / flops as in bench.py)
+    fwd.enable_profile(True)
+    for _ in range(5):
+        fwd(Xg)
+    torch.cuda.synchronize()
+    kernels = {}
+    for kname, r in fwd.profile_summary().items():
+        gbs = r["bytes"] / (r["ms"] * 1e-3) / 1e9
+        tfs = r["flops"] / (r["ms"] * 1e-3) / 1e12 if r["flops"] else 0.0
+        tensor = kname.startswith("gemm") and 3 * tfs / TC_PEAK > gbs / HBM_PEAK
+        kernels[kname] = dict(ms=round(r["ms"], 4), GBps=round(gbs, 1), TFLOPs=round(tfs, 1), bound="tensor" if tensor else "hbm",
+                              frac=round(3 * tfs / TC_PEAK if tensor else gbs / HBM_PEAK, 3))
+    fwd.enable_profile(False)
     q = torch.randperm(n, generator=torch.Generator().manual_seed(0))[:100].to(DEV)
     pq_ms = timeit(lambda: fg.infer.per_query(sd, pack, Xg, q, precision="bf16x3"), reps=5, warm=1)
     row = dict(config=name, mode=mode, nodes=n, subgraphs=pack.n_sub, rows=pack.n_rows, nnz=pack.nnz, F=F,
                partition_cpu_s=round(t_part, 2), pack_build_ms=round(build_ms, 2), forward_eager_ms=round(eager_ms, 4),
                forward_graph_ms=round(graph_ms, 4), nodes_per_s=n / (graph_ms * 1e-3),
-               per_query_100_ms=round(pq_ms, 3))
+               per_query_100_ms=round(pq_ms, 3), hub_rows=int(fwd.hubs_all[1]), kernels=kernels)
     # oracle on a sample of consecutive batches (none / extra): CPU time + parity
     if mode != "cluster":
         n_sub = min(pack.n_sub, sample_batches * 128)
@@ -136,10 +152,15 @@ if __name__ == "__main__":
     print(json.dumps(r), flush=True)
     rows.append(r)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "configs_r1.json"), "w"), indent=1)
+    json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "configs_r2.json"), "w"), indent=1)
     cols = ["config", "mode", "nodes", "subgraphs", "rows", "nnz", "pack_build_ms", "forward_eager_ms", "forward_graph_ms",
             "nodes_per_s", "per_query_100_ms", "cpu_nodes_per_s", "max_rel_err"]
-    with open(os.path.join(ROOT, "gpurun_out", "configs_r1.md"), "w") as f:
+    with open(os.path.join(ROOT, "gpurun_out", "configs_r2.md"), "w") as f:
         f.write("| " + " | ".join(cols) + " |\n|" + "---|" * len(cols) + "\n")
         for r in rows:
             f.write("| " + " | ".join(f"{r.get(c, ''):.4g}" if isinstance(r.get(c), float) else str(r.get(c, "")) for c in cols) + " |\n")
+        f.write("\nPer-kernel rooflines (eager forward, CUDA events per launch; frac = of the measured copy peak / sustained bf16 peak x3):\n\n")
+        for r in rows:
+            if "kernels" in r:
+                f.write(f"* {r['config']} / {r['mode']} (hub rows: {r.get('hub_rows')}): " + "; ".join(
+                    f"{k} {v['ms']} ms {v['GBps']} GB/s {v['TFLOPs']} TF ({v['bound']} {v['frac']})" for k, v in r["kernels"].items()) + "\n")

@@ -1,0 +1,62 @@
+"""Which operand format can the hidden state take?  CPU emulation (numpy fp64 reference) of the products-shaped forward
+(2-layer GCN, hidden 512, mode none) with the A operand of the layer-2 transform and of the head rounded to a candidate
+format before the (otherwise exact) product — what a tensor-core kernel with that operand format would compute:
+    fp32         : nothing rounded (the noise floor of fp32 accumulation)
+    bf16x3       : hi + lo bf16 planes (what libfitgnn_b200 does: 3 MMAs, 2^-17 per operand)
+    fp16 (1 plane): 11-bit significand, 2 MMAs against fp16 hi/lo weights      ("fp16x2")
+    tf32 RN      : 11-bit significand on BOTH operands, one kind::tf32 pass     (the verdict's suggestion)
+    bf16 (1 plane): 8-bit significand
+Reported: max |logit - ref| / max(1, max |ref|) over all nodes (the bench's parity measure, bound 1e-3) and the worst
+element-wise ratio |diff| / (1e-3 |ref| + 1e-5 max|ref|) (the tests' criterion; must be <= 1).
+python scripts/precision_study.py [n_nodes]"""
+import os, sys
+import numpy as np
+import scipy.sparse as sp
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import fitgnn_b200 as fg
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
+F, H, C = 100, 512, 47
+ei, part, cw, k = fg.synth.planted_partition(n, int(n * 25.26), 0.5, seed=0, device="cpu")
+part = part.numpy().astype(np.int64); ei = ei.numpy()
+intra = part[ei[0]] == part[ei[1]]
+A = sp.coo_matrix((np.ones(int(intra.sum())), (ei[1][intra], ei[0][intra])), shape=(n, n)).tocsr()
+A = A + sp.identity(n, format="csr")
+dinv = 1.0 / np.sqrt(np.asarray(A.sum(1)).ravel())
+Ahat = sp.diags(dinv) @ A @ sp.diags(dinv)
+X = fg.synth.features(n, F, seed=0).numpy().astype(np.float64)
+sd = {k_: v.numpy().astype(np.float64) for k_, v in fg.synth.init_state_dict(F, H, C, seed=0).items()}
+
+def rnd_bits(x, bits):  # round to nearest, `bits` explicit mantissa bits, fp32 exponent range
+    x32 = x.astype(np.float32)
+    u = x32.view(np.uint32).astype(np.uint64)
+    drop = 23 - bits
+    u = (u + (1 << (drop - 1)) - 1 + ((u >> drop) & 1)) >> drop << drop
+    return u.astype(np.uint32).view(np.float32).astype(np.float64)
+fmt = {
+    "fp32 (nothing rounded, fp32 products)": lambda x: x.astype(np.float32).astype(np.float64),
+    "bf16x3 (hi+lo bf16, shipped)": lambda x: rnd_bits(x, 7) + rnd_bits(x - rnd_bits(x, 7), 7),
+    "fp16 single plane (fp16x2)": lambda x: x.astype(np.float16).astype(np.float64),
+    "tf32 RN, both operands": lambda x: rnd_bits(x, 10),
+    "bf16 single plane": lambda x: rnd_bits(x, 7),
+}
+elu = lambda z: np.where(z > 0, z, np.expm1(np.minimum(z, 0)))
+def forward(r, r_w=lambda w: w):
+    a1 = Ahat @ X
+    h1 = elu(a1 @ sd["conv.0.lin.weight"].T + sd["conv.0.bias"])
+    a2 = r(Ahat @ h1)                                   # operand of the layer-2 transform (emitted by gemm0_agg)
+    h2 = elu(a2 @ r_w(sd["conv.1.lin.weight"]).T + sd["conv.1.bias"])
+    z = r(h2) @ r_w(sd["lt1.weight"]).T + sd["lt1.bias"]  # operand of the head
+    z = z - z.max(1, keepdims=True)
+    return z - np.log(np.exp(z).sum(1, keepdims=True))
+ref = forward(lambda x: x)
+scale = max(1.0, np.abs(ref).max())
+print(f"products-shaped sample: {n} nodes, {k} subgraphs, max |log-prob| = {np.abs(ref).max():.3f}")
+print(f"{'operand format of the hidden state':42s} {'max err / max|ref|':>20s} {'worst element-wise ratio':>26s}")
+for name, r in fmt.items():
+    rw = (lambda w: rnd_bits(w, 10)) if name.startswith("tf32") else (lambda w: w)
+    out = forward(r, rw)
+    err = np.abs(out - ref)
+    ratio = (err / (1e-3 * np.abs(ref) + 1e-5 * scale)).max()
+    print(f"{name:42s} {err.max() / scale:20.3e} {ratio:26.3f}")

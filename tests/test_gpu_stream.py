@@ -429,3 +429,52 @@ def test_pack_from_reference_cache_runs_the_cached_lists(fg, tmp_path):
     gpack, gX, graph_of_sub = fc.pack_from_reference_cache(gc, dev())
     pred = fg.infer.graph_level_Gs(gio.state_dict(g), gpack, gX, graph_of_sub, "graph_reg")
     assert_close(pred.cpu().numpy(), g["pred_gs"])
+
+
+# ------------------------------------------------------------------------------------------ fp16 hidden state (opt-in)
+@pytest.mark.parametrize("M,K,N", [(1000, 512, 512), (5000, 512, 47), (4224, 192, 384), (100003, 512, 512)])
+def test_gemm_fp16x2_matches_fp64_of_the_rounded_operand(fg, M, K, N):
+    """FITGNN_GEMM_FP16X2: A = ONE fp16 plane, W = fp16 hi/lo; the product of the ROUNDED A with the exact W must come out to
+    fp32 accuracy (the only precision given up is the rounding of A to 11 bits, which the caller chose)."""
+    g = torch.Generator().manual_seed(M + N)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g) * 0.1
+    rs = torch.rand(M, generator=g) + 0.5
+    a16, _ = fg.ops.split_f16(A.to(dev()), lo=False)
+    Wp = fg.ops.split_f16(W.to(dev()))
+    want = torch.nn.functional.elu(rs.double()[:1500, None] * (a16[:1500].cpu().double() @ W.double().T) + b.double())
+    got = fg.ops.gemm_f16(a16, Wp, b.to(dev()), fg.ops.ACT_ELU, row_scale=rs.to(dev()))
+    assert got.dtype == torch.float32
+    assert float((got[:1500, :N].cpu().double() - want).abs().max()) <= 2e-5 * float(want.abs().max())
+    if N % 8 == 0:  # fp16-plane output = the fp32 result rounded once
+        got16 = fg.ops.gemm_f16(a16, Wp, b.to(dev()), fg.ops.ACT_ELU, row_scale=rs.to(dev()), out_f16=True)
+        assert got16.dtype == torch.float16 and torch.equal(got16, got[:, :N].half())
+    # the rounding itself: 2^-11 relative per element of A
+    assert float((a16.float().cpu() - A).abs().max()) <= 2.0 ** -11 * float(A.abs().max())
+
+
+def test_fp16_hidden_state_schedule_matches_oracle(fg):
+    """PackedForward(precision='fp16x2') on the headline schedule: logits against the oracle inside the 1e-3 bound with a wide
+    margin (measured ~2e-5 of max |log-prob|), and close to the bf16x3 result; ineligible packs fall back to bf16x3."""
+    n, F, C = 30000, 100, 47
+    ei, part, cw, k = planted(fg, n, 750000, seed=3)
+    X = fg.synth.features(n, F, seed=3, device=dev())
+    sd = fg.synth.init_state_dict(F, 512, C, seed=3)
+    pack = fg.build_pack(ei, part, k, "none")
+    f16 = fg.PackedForward(pack, sd, precision="fp16x2")
+    assert f16.f16_hidden and f16.apack is not None
+    want = oracle_none(ei, X, part, k, sd)
+    got = f16(X).cpu().numpy()
+    assert_close(got, want)
+    assert np.abs(got - want).max() <= 2e-4 * max(1.0, np.abs(want).max())
+    ref = fg.PackedForward(pack, sd, precision="bf16x3")(X).cpu().numpy()
+    assert np.abs(got - ref).max() <= 2e-4 * np.abs(ref).max()
+    # three layers: the middle fused transform takes the fp16 plane as input
+    sd3 = fg.synth.init_state_dict(F, 256, C, num_layers=3, seed=4)
+    g3 = fg.PackedForward(pack, sd3, precision="fp16x2")(X).cpu().numpy()
+    r3 = fg.PackedForward(pack, sd3, precision="bf16x3")(X).cpu().numpy()
+    assert np.abs(g3 - r3).max() <= 3e-4 * np.abs(r3).max()
+    # a pack the fused schedule cannot take (cluster mode) silently runs bf16x3
+    cl = fg.build_pack(ei[:, :100000], part, k, "cluster")
+    assert not fg.PackedForward(cl, sd, precision="fp16x2").f16_hidden
