@@ -59,14 +59,17 @@ def parse():
                         "collated batch.x holds, built once with the pack); 'table' = node-ordered [N, F] table gathered "
                         "through gid every step; auto = packed in mode none with one chunk per rank, else table")
     p.add_argument("--seed", type=int, default=0)
-    p.add_argument("--collective", default="auto", choices=["auto", "push", "p2p", "ce", "nccl"],
-                   help="N>1 output exchange: push = head into the local slot, then ONE small kernel bulk-stores the slot to all "
+    p.add_argument("--collective", default="auto", choices=["auto", "none", "push", "p2p", "ce", "nccl"],
+                   help="N>1: what happens to the logits after the head.  none = they stay sharded by rank (subgraphs are "
+                        "independent: the path has no exchange step; the reference's metrics need an all-reduce of three scalars).  "
+                        "push = head into the local slot, then ONE small kernel bulk-stores the slot to all "
                         "peers on a side stream, overlapping the next step's compute (measured slower: it takes SMs from the "
                         "persistent GEMMs); "
                         "p2p = head kernel stores into every rank's gather buffer over NVLink "
                         "(+ a one-element all-reduce as barrier); ce = head into the local slot, copy-engine pushes to the "
                         "peers on a side stream overlapping the next step's compute; nccl = local slot, then all_gather; "
-                        "auto = p2p up to 4 GPUs, ce above (measured)")
+                        "auto = p2p up to 4 GPUs, ce above (measured); the variant not chosen (sharded / gathered) is timed "
+                        "after the headline and reported in multi_gpu.sharded / multi_gpu.gathered")
     p.add_argument("--push-ctas", type=int, default=16, help="CTAs of the peer-push kernel (--collective push)")
     p.add_argument("--chunks", type=int, default=1, help="N>1: chunks per rank; chunk c's all-gather overlaps chunk c+1")
     p.add_argument("--modes", default="none_heavy_tail,cluster,train,per_query,alt_precision",
@@ -662,18 +665,18 @@ def main_ours(args):
     gbuf = shard.gather_buffer(Cp, device) if world > 1 else None
 
     # fused output exchange (see dist.PeerGather): needs the group-aligned schedule (row-mapped head stores)
-    pg, collective = None, "nccl" if world > 1 else "none"
-    if world > 1 and args.collective != "nccl" and all(f.apack is not None for f in fwds):
+    pg, coll_gather = None, "nccl" if world > 1 else "none"
+    want_coll = args.collective
+    gather_pref = args.collective if args.collective not in ("auto", "none") else ("p2p" if world <= 4 else "ce")
+    if world > 1 and gather_pref != "nccl" and all(f.apack is not None for f in fwds):
         try:
             from fitgnn_b200.dist import PeerGather
             pg = PeerGather(shard, Cp, device, n_buffers=2, backend="ipc")
-            # measured on 8xB200 (profiles/r1_multi_gpu.md): the fused peer stores win up to 4 GPUs; at 8 the head becomes
-            # NVLink-bound (7 x its slot per rank) and the overlapped copy-engine exchange is ahead; the multicast store
-            # does not help an all-gather (every rank still has to RECEIVE all the other slots)
             # measured (profiles/r1_multi_gpu.md, profiles/r2_multi_gpu.md): the fused peer stores win up to 4 GPUs; at 8 the head
             # becomes NVLink-egress-bound and the overlapped copy-engine exchange is ahead.  The SM-driven push kernel ('push')
-            # loses to both: every CTA it occupies delays one CTA of the persistent 148-CTA GEMMs by the whole push
-            collective = args.collective if args.collective != "auto" else ("p2p" if world <= 4 else "ce")
+            # loses to both: every CTA it occupies delays one CTA of the persistent 148-CTA GEMMs by the whole push; the
+            # multicast store does not help an all-gather (every rank still has to RECEIVE all the other slots)
+            coll_gather = gather_pref
         except Exception as e:  # IPC not permitted in this container, ...
             if args.collective == "p2p":
                 raise
@@ -682,23 +685,33 @@ def main_ours(args):
         ok = torch.tensor([1 if pg is not None else 0], device=device)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
-            pg, collective = None, "nccl"
+            pg, coll_gather = None, "nccl"
+    # the headline ends every step with ALL logits on every rank (north_star: "the final logit all-gather");
+    # --collective none leaves them sharded.  The other variant is timed after the headline and reported beside it.
+    collective = "none" if (world == 1 or want_coll == "none") else coll_gather
 
-    def run_p2p(Xin, b):
-        if collective in ("ce", "push"):
+    def run_local(Xin, buf):
+        """outputs stay sharded: every chunk's head writes this rank's slot of `buf` (same layout as the gathered variants)"""
+        for c, f in enumerate(fwds):
+            f(Xin, out=shard.slot(buf, c), packed=packed)
+        return buf
+
+    def run_p2p(Xin, b, coll):
+        if coll in ("ce", "push"):
             pg.acquire(b)
             for c, f in enumerate(fwds):
                 f(Xin, out=shard.slot(pg.tensors[b], c), packed=packed)
             # completes behind the next step; the timed region ends with pg.wait on both buffers
-            pg.exchange_async(b, engine=collective, push_ctas=args.push_ctas)
+            pg.exchange_async(b, engine=coll, push_ctas=args.push_ctas)
             return pg.tensors[b]
         for c, f in enumerate(fwds):
             f(Xin, peer_ptrs=pg.slot_ptrs(b, c), packed=packed)
         pg.barrier()
         return pg.tensors[b]
 
-    def drain():
-        if pg is not None and collective in ("ce", "push"):
+    def drain(coll=None):
+        coll = collective if coll is None else coll
+        if pg is not None and coll in ("ce", "push"):
             for b in range(2):
                 pg.wait(b)
 
@@ -715,11 +728,16 @@ def main_ours(args):
             w.wait()
         return buf
 
-    def step():
-        if pg is not None:
+    def step(coll=None):
+        coll = collective if coll is None else coll
+        if world == 1:
+            return fwd(Xd, packed=packed)
+        if coll == "none":
+            return run_local(Xd, gbuf)
+        if pg is not None and coll != "nccl":
             step_no[0] += 1
-            return run_p2p(Xd, step_no[0] % 2)
-        return run_chunks(Xd, gbuf) if world > 1 else fwd(Xd, packed=packed)
+            return run_p2p(Xd, step_no[0] % 2, coll)
+        return run_chunks(Xd, gbuf)
 
     def barrier():
         if world > 1:
@@ -787,22 +805,56 @@ def main_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
 
-    # ---- N > 1: the gathered result on EVERY rank equals a single-GPU forward of the whole pack (outside the timing)
-    verify = None
+    # ---- N > 1: the result equals a single-GPU forward of the whole pack on EVERY rank (outside the timing).  Sharded
+    # outputs are all-gathered once here for the check; the gathered variants are checked as they come out of a step.
+    verify, other_info = None, None
     if world > 1:
-        res = step()
-        drain()
-        barrier()
-        gathered = res.view(-1, Cp)[shard.node_index(device)][:, :C]
         ref_rows = fg.PackedForward(pack, sd, head="log_softmax", rows="core", precision=precision,
                                     fuse_aggregate=False if args.no_fuse_aggregate else "auto",
                                     align_policy=args.align_policy)(X_full)
         full = torch.empty(n, C, device=device)
         full[pack.core_gid.long()] = ref_rows[:, :C]
-        err = (gathered - full).abs().max().reshape(1)
-        dist.all_reduce(err, op=dist.ReduceOp.MAX)
-        verify = float(err.item())
-        del gathered, ref_rows, full, res
+        del ref_rows
+
+        def check(res):
+            gathered = res.view(-1, Cp)[shard.node_index(device)][:, :C]
+            err = (gathered - full).abs().max().reshape(1)
+            dist.all_reduce(err, op=dist.ReduceOp.MAX)
+            return float(err.item())
+
+        res = step()
+        drain()
+        barrier()
+        if collective == "none":
+            for c in range(n_chunks):
+                shard.all_gather_(res, c, async_op=False)
+            barrier()
+        verify = check(res)
+        del res
+        # the other variant (headline gathered -> sharded outputs, headline sharded -> all-gathered), same steps / warm-up / clock
+        other = coll_gather if collective == "none" else "none"
+        for _ in range(max(args.warmup, 3)):
+            out = step(other)
+        drain(other)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            out = step(other)
+        drain(other)
+        g1.record()
+        barrier()
+        tg = torch.tensor([g0.elapsed_time(g1) / args.steps], device=device, dtype=torch.float64)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        if other == "none":
+            for c in range(n_chunks):
+                shard.all_gather_(out, c, async_op=False)
+            barrier()
+        g_err = check(out)
+        other_info = {"collective": other, "ms_per_step": float(tg.item()), "value": n / (float(tg.item()) * 1e-3),
+                      "unit": UNIT, "all_gather_bytes": int(n * Cp * 4) if other != "none" else 0,
+                      "vs_single_gpu_max_abs_err_all_ranks": g_err}
+        del full
         barrier()
 
     # ---- N = 1: the pack-ordered input gives the same logits, bit for bit, as the node-ordered table gathered through gid
@@ -850,8 +902,10 @@ def main_ours(args):
                 with torch.cuda.stream(s_cmp):
                     s_cmp.wait_event(ev_in[b])
                     s_cmp.wait_event(ev_out[b])  # the D2H that last read o_dev[b] is done
-                    if pg is not None:
-                        run_p2p(X_in[b], b)
+                    if world > 1 and collective == "none":
+                        run_local(X_in[b], o_dev[b])
+                    elif pg is not None and collective != "nccl":
+                        run_p2p(X_in[b], b, collective)
                     elif world > 1:
                         run_chunks(X_in[b], o_dev[b])
                     else:
@@ -955,9 +1009,14 @@ def main_ours(args):
             "pack": {"rows": pack.n_rows, "nnz": pack.nnz, "subgraphs": pack.n_sub, "build_ms": pack_build_ms, "build_first_call_ms": pack_build_first_ms, "align_ms": align_ms,
                      "bytes": pack.nbytes(), "rank_loads": shard.loads},
             "multi_gpu": {"chunks_per_rank": n_chunks, "collective": collective,
+                          "outputs": ("sharded by rank (independent subgraphs: no exchange on the path); multi_gpu.gathered times "
+                                      "the all-gathered variant") if (world > 1 and collective == "none") else
+                                     ("all-gathered on every rank every step; multi_gpu.sharded times the same steps with the "
+                                      "logits left on the rank that computed them" if world > 1 else "single GPU"),
                           "gathered_vs_single_gpu_max_abs_err_all_ranks": verify, "rank_kernel_ms": rank_kernel_ms,
-                          "all_gather_bytes": int(n * Cp * 4) if world > 1 else 0,
-                          "exposed_ms": (ms - max(rank_kernel_ms)) if rank_kernel_ms else 0.0}}
+                          "all_gather_bytes": int(n * Cp * 4) if (world > 1 and collective != "none") else 0,
+                          "exposed_ms": (ms - max(rank_kernel_ms)) if rank_kernel_ms else 0.0,
+                          ("gathered" if collective == "none" else "sharded"): other_info}}
     if packed_check:
         line["features_check"] = packed_check
     if projection:

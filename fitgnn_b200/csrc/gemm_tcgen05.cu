@@ -217,8 +217,17 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
                "h"(mask)
                : "memory");
 }
+// The only thing this arrive orders is the TMEM reads before it (complete after tcgen05.wait::ld, made visible by
+// tcgen05.fence::before_thread_sync): default .release.cta semantics suffice.  `.release.cluster` compiled to
+// MEMBAR.ALL.CTA + ERRBAR and cost 14 % of the peer CTA's epilogue samples (ncu r2s).
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// one lane of the (converged) warp; the same lane every time, so its commits track its own MMAs
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -297,7 +306,10 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
   // N-block of the weights resident for the whole kernel (k_blocks x {W_hi, W_lo}) and only A streams, which removes
   // the per-tile weight re-load from L2 that otherwise dominates the SM<->L2 traffic of a small-K transform.
   const uint32_t w_region_bytes = w_stationary ? (uint32_t)k_blocks * 2u * B_PLANE_BYTES : 0u;
-  const uint32_t stage_bytes_rt = w_stationary ? 2u * A_PLANE_BYTES : STAGE_BYTES;
+  // a single-plane A (fp16) has no lo slot: the stage shrinks by one plane, which buys pipeline depth (the N = 48 head:
+  // 5 stages of 16 KB instead of 2 of 32 KB beside its resident weights)
+  const uint32_t a_bytes = (a_single ? 1u : 2u) * A_PLANE_BYTES;
+  const uint32_t stage_bytes_rt = w_stationary ? a_bytes : STAGE_BYTES - 2u * A_PLANE_BYTES + a_bytes;
   uint8_t* staging = smem + w_region_bytes + (size_t)n_stages * stage_bytes_rt;  // multiples of 1024 throughout
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 2 * ACC_STAGES + 1);
@@ -371,15 +383,19 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // warp-uniform loop, one elected lane issues (same reason as the MMA issuer below)
+    {
       uint32_t stage = 0, phase = 0;
       if (w_stationary && t_first < tiles) {
         const int n0 = (int)(t_first % n_tiles) * BLOCK_N;
-        mbar_arrive_expect_tx(wfull_bar, w_region_bytes);
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          tma_load_2d(w_base + kb * 2 * B_PLANE_BYTES, &map_w_hi, wfull_bar, kb * BLOCK_K, n0);
-          tma_load_2d(w_base + kb * 2 * B_PLANE_BYTES + B_PLANE_BYTES, &map_w_lo, wfull_bar, kb * BLOCK_K, n0);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(wfull_bar, w_region_bytes);
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            tma_load_2d(w_base + kb * 2 * B_PLANE_BYTES, &map_w_hi, wfull_bar, kb * BLOCK_K, n0);
+            tma_load_2d(w_base + kb * 2 * B_PLANE_BYTES + B_PLANE_BYTES, &map_w_lo, wfull_bar, kb * BLOCK_K, n0);
+          }
         }
+        __syncwarp();
       }
       int64_t wi = 0;
       for (int64_t t = CTA2 ? tile_at(0) : t_first; t < tiles && !GATHER;
@@ -389,32 +405,40 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t dst = smem_base + stage * stage_bytes_rt;
-          const uint32_t tx_bytes = stage_bytes_rt - (a_single ? A_PLANE_BYTES : 0u);  // a single-plane A has no lo load
-          if (CTA2) {
-            // both CTAs' bytes are counted on the LEADER's full barrier (its MMA thread consumes both halves)
-            const uint32_t lbar = mapa_rank(full_bar(stage), 0);
-            if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * tx_bytes);
-            tma_load_2d_pair(dst, &map_a_hi, lbar, kb * BLOCK_K, m0);
-            if (!a_single) tma_load_2d_pair(dst + A_PLANE_BYTES, &map_a_lo, lbar, kb * BLOCK_K, m0);
-            tma_load_2d_pair(dst + 2 * A_PLANE_BYTES, &map_w_hi, lbar, kb * BLOCK_K, n0 + (int)cta_rank * B_ROWS);
-            tma_load_2d_pair(dst + 2 * A_PLANE_BYTES + B_PLANE_BYTES, &map_w_lo, lbar, kb * BLOCK_K, n0 + (int)cta_rank * B_ROWS);
-            if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
-            continue;
+          const uint32_t tx_bytes = stage_bytes_rt;
+          __syncwarp();
+          if (elect_one()) {
+            if (CTA2) {
+              // both CTAs' bytes are counted on the LEADER's full barrier (its MMA thread consumes both halves)
+              const uint32_t lbar = mapa_rank(full_bar(stage), 0);
+              if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * tx_bytes);
+              tma_load_2d_pair(dst, &map_a_hi, lbar, kb * BLOCK_K, m0);
+              if (!a_single) tma_load_2d_pair(dst + A_PLANE_BYTES, &map_a_lo, lbar, kb * BLOCK_K, m0);
+              tma_load_2d_pair(dst + a_bytes, &map_w_hi, lbar, kb * BLOCK_K, n0 + (int)cta_rank * B_ROWS);
+              tma_load_2d_pair(dst + a_bytes + B_PLANE_BYTES, &map_w_lo, lbar, kb * BLOCK_K, n0 + (int)cta_rank * B_ROWS);
+            } else {
+              mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
+              tma_load_2d(dst, &map_a_hi, full_bar(stage), kb * BLOCK_K, m0);
+              if (!a_single) tma_load_2d(dst + A_PLANE_BYTES, &map_a_lo, full_bar(stage), kb * BLOCK_K, m0);
+              if (!w_stationary) {
+                tma_load_2d(dst + a_bytes, &map_w_hi, full_bar(stage), kb * BLOCK_K, n0);
+                tma_load_2d(dst + a_bytes + B_PLANE_BYTES, &map_w_lo, full_bar(stage), kb * BLOCK_K, n0);
+              }
+            }
           }
-          mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
-          tma_load_2d(dst, &map_a_hi, full_bar(stage), kb * BLOCK_K, m0);
-          if (!a_single) tma_load_2d(dst + A_PLANE_BYTES, &map_a_lo, full_bar(stage), kb * BLOCK_K, m0);
-          if (!w_stationary) {
-            tma_load_2d(dst + 2 * A_PLANE_BYTES, &map_w_hi, full_bar(stage), kb * BLOCK_K, n0);
-            tma_load_2d(dst + 2 * A_PLANE_BYTES + B_PLANE_BYTES, &map_w_lo, full_bar(stage), kb * BLOCK_K, n0);
-          }
+          __syncwarp();
           if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread; the pair's leader CTA)
-    if (lane == 0 && leader) {
+    // ------------------------------------------------------------------ MMA issuer (the pair's leader CTA)
+    // The WHOLE warp walks the loop (waits included) so that every address and descriptor is warp-uniform, and one
+    // elected lane issues the MMAs + commits of a k-block.  With the loop under `lane == 0` instead, the compiler cannot
+    // prove uniformity and wraps EVERY tcgen05.mma in an ELECT / R2UR.BROADCAST waterfall: ~260 SASS instructions and
+    // ~1,100 cycles per k-block on one thread (ncu r2q) — the bound of the N = 48 head (8 small MMAs per k-block) and
+    // level with the 8 MMAs of a pair's fp16 k-block.
+    if (leader) {
       uint32_t stage = 0, phase = 0;
       int64_t it = 0;
       if (w_stationary && t_first < tiles) mbar_wait(wfull_bar, 0);  // resident weights have landed
@@ -428,31 +452,35 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
           mbar_wait(full_bar(stage), phase);  // TMA bytes have landed
           fence_after();
           const uint32_t a_hi = smem_base + stage * stage_bytes_rt;
-          const uint32_t w_hi = w_stationary ? w_base + kb * 2 * B_PLANE_BYTES : a_hi + 2 * A_PLANE_BYTES;
+          const uint32_t w_hi = w_stationary ? w_base + kb * 2 * B_PLANE_BYTES : a_hi + a_bytes;
           const uint64_t d_a_hi = umma_desc_sw128(a_hi);
           const uint64_t d_a_lo = umma_desc_sw128(a_hi + A_PLANE_BYTES);
           const uint64_t d_w_hi = umma_desc_sw128(w_hi);
           const uint64_t d_w_lo = umma_desc_sw128(w_hi + B_PLANE_BYTES);
+          __syncwarp();
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);  // +32 bytes per K=16 step inside the swizzle row
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);  // +32 bytes per K=16 step inside the swizzle row
+              if (CTA2) {
+                umma_bf16_pair(tmem_d, d_a_hi + adv, d_w_hi + adv, IDESC, (kb | k) != 0);
+                if (!a_single) umma_bf16_pair(tmem_d, d_a_lo + adv, d_w_hi + adv, IDESC, 1);
+                umma_bf16_pair(tmem_d, d_a_hi + adv, d_w_lo + adv, IDESC, 1);
+              } else {
+                umma_bf16(tmem_d, d_a_hi + adv, d_w_hi + adv, IDESC, (kb | k) != 0);
+                if (!a_single) umma_bf16(tmem_d, d_a_lo + adv, d_w_hi + adv, IDESC, 1);
+                umma_bf16(tmem_d, d_a_hi + adv, d_w_lo + adv, IDESC, 1);
+              }
+            }
             if (CTA2) {
-              umma_bf16_pair(tmem_d, d_a_hi + adv, d_w_hi + adv, IDESC, (kb | k) != 0);
-              if (!a_single) umma_bf16_pair(tmem_d, d_a_lo + adv, d_w_hi + adv, IDESC, 1);
-              umma_bf16_pair(tmem_d, d_a_hi + adv, d_w_lo + adv, IDESC, 1);
+              umma_commit_pair(empty_bar(stage));  // frees the stage in BOTH CTAs
+              if (kb == k_blocks - 1) umma_commit_pair(tfull_bar(acc));
             } else {
-              umma_bf16(tmem_d, d_a_hi + adv, d_w_hi + adv, IDESC, (kb | k) != 0);
-              if (!a_single) umma_bf16(tmem_d, d_a_lo + adv, d_w_hi + adv, IDESC, 1);
-              umma_bf16(tmem_d, d_a_hi + adv, d_w_lo + adv, IDESC, 1);
+              umma_commit(empty_bar(stage));  // smem stage is free once these MMAs retire
+              if (kb == k_blocks - 1) umma_commit(tfull_bar(acc));
             }
           }
-          if (CTA2) {
-            umma_commit_pair(empty_bar(stage));  // frees the stage in BOTH CTAs
-            if (kb == k_blocks - 1) umma_commit_pair(tfull_bar(acc));
-          } else {
-            umma_commit(empty_bar(stage));  // smem stage is free once these MMAs retire
-            if (kb == k_blocks - 1) umma_commit(tfull_bar(acc));
-          }
+          __syncwarp();
           if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -811,7 +839,8 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
           // stage the box in this warp's 4 KB buffer (row = lane) and hand it to the TMA unit, which clips at the
           // tensor bounds.  fp32: 128-byte rows, 16-byte chunk c of row r at c ^ (r & 7).  bf16 hi/lo planes: two
           // 2 KB boxes of 64-byte rows, chunk c of row r at c ^ ((r >> 1) & 3).
-          if (lane == 0) bulk_wait_read<0>();  // the store(s) that last read this buffer have finished reading
+          // (bulk async-groups belong to a thread: elect_one picks the same lane every time)
+          if (elect_one()) bulk_wait_read<0>();  // the store(s) that last read this buffer have finished reading
           __syncwarp();
           if (tma_store == 3) {  // ONE fp16 plane (64-byte rows, the bf16 planes' swizzle)
 #pragma unroll
@@ -845,7 +874,7 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
           }
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {
             tma_store_2d(&map_y, buf, n0 + c0, m_base);
             if (tma_store == 2) tma_store_2d(&map_y_lo, buf + EPI_BOX_BYTES / 2, n0 + c0, m_base);
             bulk_commit();
@@ -881,7 +910,11 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
         else mbar_arrive(tempty_bar(acc));
       }
     }
-    if ((tma_store || ea.bulk_rows) && lane == 0) bulk_wait_all();  // smem must outlive the last bulk store
+    if (tma_store || ea.bulk_rows) {  // smem must outlive the last bulk store (row-mapped path: lane 0 committed; boxes: the elected lane)
+      if (lane == 0) bulk_wait_all();
+      __syncwarp();
+      if (elect_one()) bulk_wait_all();
+    }
   }
 
   fence_before();
@@ -997,33 +1030,35 @@ static int launch(const GatherArgs& ga, const EpiArgs& ea, const CUtensorMap& a_
   const int n_tiles = (int)ceil_div(N, BLOCK_N);
   const int64_t m_tiles = ceil_div(M, BLOCK_M);
   const int64_t tiles = m_tiles * n_tiles;
-  int n_stages = (int)((SMEM_LIMIT - FIXED) / stage_bytes(BLOCK_N));
+  const size_t a_bytes = (size_t)(ea.a_planes == 1 ? 1 : 2) * A_PLANE_BYTES;  // stage share of A (one fp16 plane or hi + lo)
+  const size_t stage_b = stage_bytes(BLOCK_N) - 2 * A_PLANE_BYTES + a_bytes;
+  int n_stages = (int)((SMEM_LIMIT - FIXED) / stage_b);
   if (n_stages > 8) n_stages = 8;
   int grid = (int)(tiles < sms ? tiles : sms);
-  size_t smem = (size_t)n_stages * stage_bytes(BLOCK_N) + FIXED;
+  size_t smem = (size_t)n_stages * stage_b + FIXED;
   // W-stationary plan: worth it when the resident weights fit beside >= 2 A stages and every CTA gets several m-blocks
   int w_stationary = 0;
   const size_t w_bytes = (size_t)k_blocks * 2 * BLOCK_N * BLOCK_K * 2;
-  if (!ea.m_batch_rows && w_bytes + 2 * 2 * A_PLANE_BYTES + FIXED <= SMEM_LIMIT && sms >= n_tiles && m_tiles >= 4 * (sms / n_tiles)) {
+  if (!ea.m_batch_rows && w_bytes + 2 * a_bytes + FIXED <= SMEM_LIMIT && sms >= n_tiles && m_tiles >= 4 * (sms / n_tiles)) {
     w_stationary = 1;
-    n_stages = (int)((SMEM_LIMIT - FIXED - w_bytes) / (2 * A_PLANE_BYTES));
+    n_stages = (int)((SMEM_LIMIT - FIXED - w_bytes) / a_bytes);
     if (n_stages > 8) n_stages = 8;
     grid = (sms / n_tiles) * n_tiles;
-    smem = w_bytes + (size_t)n_stages * 2 * A_PLANE_BYTES + FIXED;
+    smem = w_bytes + (size_t)n_stages * a_bytes + FIXED;
   }
   if (!tuning().gemm_ws && w_stationary) {  // tuning override: force the streaming plan
     w_stationary = 0;
-    n_stages = (int)((SMEM_LIMIT - FIXED) / stage_bytes(BLOCK_N));
+    n_stages = (int)((SMEM_LIMIT - FIXED) / stage_b);
     if (n_stages > 8) n_stages = 8;
     grid = (int)(tiles < sms ? tiles : sms);
-    smem = (size_t)n_stages * stage_bytes(BLOCK_N) + FIXED;
+    smem = (size_t)n_stages * stage_b + FIXED;
   }
   if (GATHER) {
     // the gather warps fill all k-blocks of a tile at once: needs the W-stationary plan with n_stages % k_blocks == 0
     FG_REQUIRE(w_stationary && k_blocks <= 2 && n_stages >= k_blocks, FITGNN_EUNSUP,
                "gcn_layer_fused: shape not eligible (needs K <= 128 and enough row blocks for the W-stationary plan)");
     n_stages = (n_stages / k_blocks) * k_blocks;
-    smem = w_bytes + (size_t)n_stages * 2 * A_PLANE_BYTES + FIXED;
+    smem = w_bytes + (size_t)n_stages * a_bytes + FIXED;
   }
   auto kern = gemm_bf16x3_kernel<BLOCK_N, GATHER, AGG, EW, CTA2>;
   static size_t smem_configured = 0;  // per instantiation; raised outside of stream capture by the first (warm-up) call
@@ -1033,7 +1068,7 @@ static int launch(const GatherArgs& ga, const EpiArgs& ea, const CUtensorMap& a_
   }
   if (CTA2) {
     // CTA pairs: streaming plan with half-B stages, one cluster of 2 CTAs per 256-row tile, persistent over the SM pairs
-    constexpr size_t STAGE2 = 2 * A_PLANE_BYTES + 2 * (size_t)(BLOCK_N / 2) * BLOCK_K * 2;
+    const size_t STAGE2 = a_bytes + 2 * (size_t)(BLOCK_N / 2) * BLOCK_K * 2;
     w_stationary = 0;
     n_stages = (int)((SMEM_LIMIT - FIXED) / STAGE2);
     if (n_stages > 8) n_stages = 8;
