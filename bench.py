@@ -71,6 +71,10 @@ def parse():
                         "auto = p2p up to 4 GPUs, ce above (measured); the variant not chosen (sharded / gathered) is timed "
                         "after the headline and reported in multi_gpu.sharded / multi_gpu.gathered")
     p.add_argument("--push-ctas", type=int, default=16, help="CTAs of the peer-push kernel (--collective push)")
+    p.add_argument("--sm-reserve", type=int, default=-1,
+                   help="SMs the persistent GEMM grids leave free (tuning 'sm_reserve'); -1 = the push kernel's CTA count with "
+                        "--collective push, else 0")
+    p.add_argument("--agg-wide", type=int, default=None, help="tuning 'agg_wide' (A/B of the fused-aggregation tile)")
     p.add_argument("--chunks", type=int, default=1, help="N>1: chunks per rank; chunk c's all-gather overlaps chunk c+1")
     p.add_argument("--modes", default="none_heavy_tail,cluster,train,per_query,alt_precision",
                    help="N=1: extra blocks measured after the headline (comma separated, '' = none): none_heavy_tail = same "
@@ -593,6 +597,12 @@ def main_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    from fitgnn_b200._lib import set_tuning
+    sm_reserve = args.sm_reserve if args.sm_reserve >= 0 else (args.push_ctas if (world > 1 and args.collective == "push") else 0)
+    if sm_reserve:
+        set_tuning("sm_reserve", sm_reserve)
+    if args.agg_wide is not None:
+        set_tuning("agg_wide", args.agg_wide)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
@@ -1008,7 +1018,8 @@ def main_ours(args):
             "kernels": kernels, "gpu_launches": gpu_launches, "clocks": sampler.summary(mark0, mark1),
             "pack": {"rows": pack.n_rows, "nnz": pack.nnz, "subgraphs": pack.n_sub, "build_ms": pack_build_ms, "build_first_call_ms": pack_build_first_ms, "align_ms": align_ms,
                      "bytes": pack.nbytes(), "rank_loads": shard.loads},
-            "multi_gpu": {"chunks_per_rank": n_chunks, "collective": collective,
+            "multi_gpu": {"chunks_per_rank": n_chunks, "collective": collective, "sm_reserve": sm_reserve,
+                          "push_ctas": args.push_ctas if "push" in (collective, coll_gather) else None,
                           "outputs": ("sharded by rank (independent subgraphs: no exchange on the path); multi_gpu.gathered times "
                                       "the all-gathered variant") if (world > 1 and collective == "none") else
                                      ("all-gathered on every rank every step; multi_gpu.sharded times the same steps with the "

@@ -34,7 +34,7 @@ static int env_int(const char* name, int dflt) {
 }
 static Tuning& tuning_mut() {
   static Tuning t{env_int("FITGNN_GEMM_WS", 1),   getenv("FITGNN_HEAD_BULK") ? 0 : 1, env_int("FITGNN_AGG_WIDE", 0),
-                  env_int("FITGNN_GEMM_WIDE", 0), env_int("FITGNN_GEMM_PAIR", 1)};
+                  env_int("FITGNN_GEMM_WIDE", 0), env_int("FITGNN_GEMM_PAIR", 1), env_int("FITGNN_SM_RESERVE", 0)};
   return t;
 }
 const Tuning& tuning() { return tuning_mut(); }
@@ -46,6 +46,7 @@ static int* tuning_field(const char* name) {
   if (!strcmp(name, "agg_wide")) return &t.agg_wide;
   if (!strcmp(name, "gemm_wide")) return &t.gemm_wide;
   if (!strcmp(name, "gemm_pair")) return &t.gemm_pair;
+  if (!strcmp(name, "sm_reserve")) return &t.sm_reserve;
   return nullptr;
 }
 

@@ -27,6 +27,7 @@ constexpr int BLOCK_K = 64;                      // bf16 elements = 128 bytes = 
 constexpr int UMMA_K = 16;
 constexpr int EPI_WARPS = 8;                      // default: two per TMEM lane quadrant, each taking half of the columns
 constexpr int EPI_WARPS_WIDE = 16;                // epilogue-bound instantiations: four per quadrant (one 32-column box each)
+constexpr int EPI_WARPS_12 = 12;                  // fused aggregation with an fp16-plane output: three per quadrant (3 + 3 + 2 boxes)
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr int GATHER_WARPS = 4;                   // fused layer: produce the A tile (Â·X) in-kernel, 32 rows per warp
 constexpr int GATHER_WARP0 = 2 + EPI_WARPS;
@@ -296,8 +297,12 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
   const bool leader = cta_rank == 0;
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N for M=128");
   static_assert(STAGES >= 2, "need at least two smem stages");
-  static_assert(EW == EPI_WARPS || (EW == EPI_WARPS_WIDE && !GATHER), "4 or 2 epilogue warps per TMEM lane quadrant");
-  constexpr uint32_t STAGING_BYTES = EW * EPI_BOX_BYTES;  // one 32 x 32 box per epilogue warp
+  static_assert(EW == EPI_WARPS || (EW == EPI_WARPS_WIDE && !GATHER) || (EW == EPI_WARPS_12 && AGG),
+                "2, 3 (fused aggregation, fp16 output) or 4 epilogue warps per TMEM lane quadrant");
+  // one 32 x 32 box per epilogue warp: 4 KB (fp32, or bf16 hi + lo); the 12-warp variant only writes ONE fp16 plane (2 KB)
+  constexpr bool HALF_STAGE = AGG && BLOCK_N == 256 && EW != EPI_WARPS;  // instantiations that require out_f16
+  constexpr uint32_t WARP_STAGE = HALF_STAGE ? EPI_BOX_BYTES / 2 : EPI_BOX_BYTES;
+  constexpr uint32_t STAGING_BYTES = EW * WARP_STAGE;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B atoms
@@ -741,8 +746,15 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
           }
         }
       }
-      float log_sum = logf(row_sum), inv_sum = 1.f / row_sum;
-      const uint32_t buf = smem_u32(staging) + (uint32_t)(warp - EPI_WARP0) * EPI_BOX_BYTES;
+      // only a two-pass (log-)softmax needs these here; computing them unconditionally put logf(0) and the 1/0 slow path
+      // (a CALL that waits for every outstanding load, i.e. for the next tile's prefetched descriptors) into EVERY tile of
+      // EVERY transform: 6.5 % of the fused-aggregation epilogue's samples (ncu r2s)
+      float log_sum = 0.f, inv_sum = 0.f;
+      if (head != FITGNN_HEAD_IDENTITY && !FAST_HEAD) {
+        log_sum = logf(row_sum);
+        inv_sum = 1.f / row_sum;
+      }
+      const uint32_t buf = smem_u32(staging) + (uint32_t)(warp - EPI_WARP0) * WARP_STAGE;
       const int m_base = (int)tile_row0(t) + quad * 32;
       for (int box = box_beg; box < box_end; ++box) {
         const int c0 = box * 32;
@@ -790,7 +802,7 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
           // next layer's aggregation over the warp's aligned group (see EpiArgs); padding rows (dr = 0) give 0 * h = 0
           // (the A operand's padding rows must hold finite values: the engine's SpMM writes zeros there)
           // AGG_W columns at a time (16 when the register budget is 112 per thread, i.e. 16 epilogue warps)
-          constexpr int AGG_W = EW == EPI_WARPS ? 32 : 16;
+          constexpr int AGG_W = EW == EPI_WARPS_WIDE ? 16 : 32;
 #pragma unroll
           for (int h0 = 0; h0 < 32; h0 += AGG_W) {
             float u[AGG_W];
@@ -994,6 +1006,9 @@ static int make_store_map_bf16(CUtensorMap* map, void* base, int64_t rows, int64
   return FITGNN_OK;
 }
 
+#ifndef FG_AGG12_DEFAULT
+#define FG_AGG12_DEFAULT 1
+#endif
 template <int BLOCK_N, bool GATHER, bool AGG, int EW = EPI_WARPS, bool CTA2 = false>
 static int launch(const GatherArgs& ga, const EpiArgs& ea, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const void* W_hi, const void* W_lo, int64_t ldw,
                   const float* bias, int64_t M, int K, int N, int act, int head, float* Y, void* Y_lo, int64_t ldy,
@@ -1024,7 +1039,10 @@ static int launch(const GatherArgs& ga, const EpiArgs& ea, const CUtensorMap& a_
   }
   constexpr size_t SMEM_LIMIT = 227 * 1024;
   // staging + alignment slack + barriers/TMEM slot (256 B) + softmax exchange buffers (2 x 8 warps x 32 x float2)
-  constexpr size_t FIXED = (size_t)EW * EPI_BOX_BYTES + 1024 + 256 + (BLOCK_N <= 64 ? 2 * EW * 32 * 8 : 0);
+  constexpr bool HALF_STAGE = AGG && BLOCK_N == 256 && EW != EPI_WARPS;
+  constexpr size_t FIXED = (size_t)EW * (HALF_STAGE ? EPI_BOX_BYTES / 2 : EPI_BOX_BYTES) + 1024 + 256 +
+                           (BLOCK_N <= 64 ? 2 * EW * 32 * 8 : 0);
+  FG_REQUIRE(!HALF_STAGE || ea.out_f16, FITGNN_EINVAL, "gemm: the 12/16-epilogue-warp 256-column tile stages one fp16 plane only");
   constexpr int NTHREADS = 64 + 32 * EW + (GATHER ? 32 * GATHER_WARPS : 0);
   const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
   const int n_tiles = (int)ceil_div(N, BLOCK_N);
@@ -1074,7 +1092,8 @@ static int launch(const GatherArgs& ga, const EpiArgs& ea, const CUtensorMap& a_
     if (n_stages > 8) n_stages = 8;
     smem = (size_t)n_stages * STAGE2 + FIXED;
     const int64_t pair_tiles = ceil_div(M, 2 * BLOCK_M) * n_tiles;
-    const int64_t pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
+    const int pair_sms = sms - tuning().sm_reserve > 2 ? sms - tuning().sm_reserve : 2;
+    const int64_t pairs = pair_tiles < pair_sms / 2 ? pair_tiles : pair_sms / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * pairs));
     cfg.blockDim = dim3(NTHREADS);
@@ -1120,7 +1139,10 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
   FG_REQUIRE(head == FITGNN_HEAD_IDENTITY || N <= 256, FITGNN_EUNSUP,
              "gemm_bf16x3: a fused (log-)softmax head needs N <= 256 (got %d)", N);
   FG_REQUIRE(M < (1ll << 31) - 128, FITGNN_ERANGE, "gemm_bf16x3: M exceeds the TMA coordinate range");
-  const int sms = sm_count();
+  // persistent grids: one CTA per SM, minus the SMs left to a concurrent exchange kernel.  A CTA pair needs both SMs of a
+  // TPC, and the other kernel's CTAs land on arbitrary TPCs, so the pair kernel leaves twice as many
+  int sms = sm_count() - tuning().sm_reserve;
+  if (sms < 2) sms = 2;
   CUtensorMap a_hi, a_lo;
   FG_TRY(tc::make_map(&a_hi, A_hi, M, K, lda, tc::BLOCK_M));
   FG_TRY(tc::make_map(&a_lo, A_lo ? A_lo : A_hi, M, K, lda, tc::BLOCK_M));  // unused with a single-plane A
@@ -1141,6 +1163,15 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
     if (tuning().agg_wide == 1)
       return tc::launch<128, false, true, tc::EPI_WARPS_WIDE>(ga, ea, a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y,
                                                               Y_lo, ldy, sms, st);
+    // fp16-plane output: 12 epilogue warps (three per scheduler; the 2 KB boxes leave the smem for it) hide more of the
+    // SHFL / MUFU latency of the exchange + ELU than 8: 1.38 -> 1.24 ms on the products workload; 16 warps at 96 registers
+    // (agg_wide = 3): 1.34 ms.  agg_wide = 2 forces the 12-warp tile, -1 the 8-warp one.
+    if (out_f16 && tuning().agg_wide == 3)
+      return tc::launch<256, false, true, tc::EPI_WARPS_WIDE>(ga, ea, a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y,
+                                                              Y_lo, ldy, sms, st);
+    if (out_f16 && (tuning().agg_wide == 2 || (tuning().agg_wide == 0 && FG_AGG12_DEFAULT)))
+      return tc::launch<256, false, true, tc::EPI_WARPS_12>(ga, ea, a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y,
+                                                            Y_lo, ldy, sms, st);
     return tc::launch<256, false, true>(ga, ea, a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y, Y_lo, ldy, sms, st);
   }
 #define FG_TC(BN) \

@@ -60,8 +60,9 @@ extern "C" int fitgnn_peer_free(void* dev_ptr) {
 namespace {
 
 constexpr int PUSH_CHUNK = 32 * 1024;  // bytes per bulk copy
-constexpr int PUSH_STAGES = 4;   // shared-memory stages
-constexpr int PUSH_DIST = 2;     // loads issued ahead of the stores
+constexpr int PUSH_STAGES = 7;   // shared-memory stages (224 KB: the CTA owns its SM)
+constexpr int PUSH_DIST = 4;     // loads issued ahead of the stores (128 KB in flight per CTA)
+constexpr int PUSH_PENDING = PUSH_STAGES - PUSH_DIST - 1;  // store groups that may still be reading shared memory
 constexpr int PUSH_MAX_PEERS = 8;
 
 struct PushArgs {
@@ -100,9 +101,9 @@ peer_push_kernel(const char* __restrict__ src, PushArgs pa, size_t bytes) {
   for (size_t i = 0; i < mine; ++i) {
     const int s = (int)(i % PUSH_STAGES);
     if (i + PUSH_DIST < mine) {
-      // the stage of chunk i + DIST was last read by the stores of chunk i + DIST - STAGES = i - 2: at most the newest
-      // store group (chunk i - 1) may still be reading shared memory
-      asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      // the stage of chunk i + DIST was last read by the stores of chunk i + DIST - STAGES: only the PENDING newest
+      // store groups (chunks i - PENDING .. i - 1) may still be reading shared memory
+      asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PUSH_PENDING) : "memory");
       load(i + PUSH_DIST, (int)((i + PUSH_DIST) % PUSH_STAGES));
     }
     const uint32_t bar = push_smem_u32(&full[s]);

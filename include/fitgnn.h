@@ -93,7 +93,8 @@ int fitgnn_last_error(char* buf, size_t n);
 int fitgnn_device_info(int* sm_count, int* cc);
 /* Kernel-tuning switches (A/B measurements only; results never depend on them).  Initial values come from the
  * environment, read ONCE per process: FITGNN_GEMM_WS, FITGNN_HEAD_BULK, FITGNN_AGG_WIDE, FITGNN_GEMM_WIDE,
- * FITGNN_GEMM_PAIR.  name = the lower-case suffix ("gemm_pair", ...). */
+ * FITGNN_GEMM_PAIR, FITGNN_SM_RESERVE (SMs the persistent GEMM grids leave free for a concurrent exchange kernel).
+ * name = the lower-case suffix ("gemm_pair", ...). */
 int fitgnn_tuning_set(const char* name, int value);
 int fitgnn_tuning_get(const char* name, int* value);
 
