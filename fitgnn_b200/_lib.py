@@ -72,6 +72,8 @@ SIGNATURES = {
                                             C.c_uint64, c_void, c_i64, c_void]),
     "fitgnn_adam_step": (c_i32, [c_void, c_void, c_void, c_void, c_i64, C.c_float, C.c_float, C.c_float, C.c_float,
                                  C.c_float, c_i64, c_void]),
+    "fitgnn_spmm_symnorm_f16": (c_i32, [c_void, c_void, c_void, c_void, c_i64, c_i32, c_void, c_void, c_i32, c_void, c_i64,
+                                        c_void, c_i64, c_void, c_void, c_i32, c_i32, c_void]),
     "fitgnn_split_f16": (c_i32, [c_void, c_i64, c_i64, c_i32, c_void, c_void, c_i64, c_void]),
     "fitgnn_gemm_f16": (c_i32, [c_void, c_i64, c_void, c_void, c_i64, c_void, c_void, c_i64, c_i32, c_i32, c_i32, c_i32, c_void,
                                 c_i64, c_i32, c_void, c_void]),

@@ -219,15 +219,15 @@ extern "C" int fitgnn_gcn_transform_aggregate_f16(int in_f16, const void* A_hi, 
                                                   const void* W_lo, int64_t ldw, const float* bias, int64_t M, int K, int N,
                                                   int act, const uint64_t* agg_desc, const float* dinv, int defer_row_scale,
                                                   void* Y, int64_t ldy, void* stream) {
-  FG_REQUIRE(A_hi && W_hi && W_lo && Y && agg_desc && dinv && M >= 0 && K > 0 && N > 0, FITGNN_EINVAL,
+  FG_REQUIRE(A_hi && W_hi && W_lo && Y && (!agg_desc || dinv) && M >= 0 && K > 0 && N > 0, FITGNN_EINVAL,
              "gcn_transform_aggregate_f16: bad arguments (M=%lld K=%d N=%d)", (long long)M, K, N);
   FG_REQUIRE(in_f16 ? !A_lo : A_lo != nullptr, FITGNN_EINVAL, "gcn_transform_aggregate_f16: A_lo must match in_f16");
   FG_REQUIRE(lda >= K && ldw >= K && ldy >= N, FITGNN_EINVAL, "gcn_transform_aggregate_f16: leading dimension too small");
   FG_REQUIRE(act == FITGNN_ACT_NONE || act == FITGNN_ACT_ELU, FITGNN_EINVAL, "gcn_transform_aggregate_f16: unknown act %d", act);
   if (M == 0) return FITGNN_OK;
   return gemm_bf16x3(A_hi, A_lo, lda, W_hi, W_lo, ldw, bias, M, K, N, act, FITGNN_HEAD_IDENTITY, static_cast<float*>(Y), nullptr,
-                     ldy, agg_desc, dinv, nullptr, nullptr, 0, nullptr, defer_row_scale, as_stream(stream), 0, 0, 0,
-                     in_f16 ? 1 : 0, 1);
+                     ldy, agg_desc, agg_desc ? dinv : nullptr, nullptr, nullptr, 0, nullptr, agg_desc ? defer_row_scale : 0,
+                     as_stream(stream), 0, 0, 0, in_f16 ? 1 : 0, 1);
 }
 
 extern "C" int fitgnn_gemm_f16_head_rows_peers(const void* A, int64_t lda, const void* W_hi, const void* W_lo, int64_t ldw,

@@ -74,7 +74,7 @@ struct Tuning {
   int agg_wide;   // fused aggregation tile: 0 = default, 1 = 128 columns / 16 epilogue warps, 2 = 256 / 12 (fp16 output only), -1 = 256 / 8
   int gemm_wide;  // 1 = same tile for small-K wide-output transforms (default 0)
   int gemm_pair;  // 0 = no CTA pairs (default 1)
-  int sm_reserve; // SMs the persistent GEMMs leave free (for a concurrent exchange kernel); pair kernels leave twice as many (default 0)
+  int sm_reserve; // SMs the persistent GEMMs leave free for a concurrent exchange kernel (default 0)
 };
 const Tuning& tuning();
 

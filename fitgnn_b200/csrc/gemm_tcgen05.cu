@@ -297,10 +297,10 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
   const bool leader = cta_rank == 0;
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N for M=128");
   static_assert(STAGES >= 2, "need at least two smem stages");
-  static_assert(EW == EPI_WARPS || (EW == EPI_WARPS_WIDE && !GATHER) || (EW == EPI_WARPS_12 && AGG),
-                "2, 3 (fused aggregation, fp16 output) or 4 epilogue warps per TMEM lane quadrant");
+  static_assert(EW == EPI_WARPS || (EW == EPI_WARPS_WIDE && !GATHER) || (EW == EPI_WARPS_12 && !GATHER && !CTA2 && BLOCK_N == 256),
+                "2, 3 (256-column tile with an fp16-plane output) or 4 epilogue warps per TMEM lane quadrant");
   // one 32 x 32 box per epilogue warp: 4 KB (fp32, or bf16 hi + lo); the 12-warp variant only writes ONE fp16 plane (2 KB)
-  constexpr bool HALF_STAGE = AGG && BLOCK_N == 256 && EW != EPI_WARPS;  // instantiations that require out_f16
+  constexpr bool HALF_STAGE = BLOCK_N == 256 && (EW == EPI_WARPS_12 || (AGG && EW == EPI_WARPS_WIDE));  // these require out_f16
   constexpr uint32_t WARP_STAGE = HALF_STAGE ? EPI_BOX_BYTES / 2 : EPI_BOX_BYTES;
   constexpr uint32_t STAGING_BYTES = EW * WARP_STAGE;
 
@@ -1039,7 +1039,7 @@ static int launch(const GatherArgs& ga, const EpiArgs& ea, const CUtensorMap& a_
   }
   constexpr size_t SMEM_LIMIT = 227 * 1024;
   // staging + alignment slack + barriers/TMEM slot (256 B) + softmax exchange buffers (2 x 8 warps x 32 x float2)
-  constexpr bool HALF_STAGE = AGG && BLOCK_N == 256 && EW != EPI_WARPS;
+  constexpr bool HALF_STAGE = BLOCK_N == 256 && (EW == EPI_WARPS_12 || (AGG && EW == EPI_WARPS_WIDE));
   constexpr size_t FIXED = (size_t)EW * (HALF_STAGE ? EPI_BOX_BYTES / 2 : EPI_BOX_BYTES) + 1024 + 256 +
                            (BLOCK_N <= 64 ? 2 * EW * 32 * 8 : 0);
   FG_REQUIRE(!HALF_STAGE || ea.out_f16, FITGNN_EINVAL, "gemm: the 12/16-epilogue-warp 256-column tile stages one fp16 plane only");
@@ -1092,8 +1092,7 @@ static int launch(const GatherArgs& ga, const EpiArgs& ea, const CUtensorMap& a_
     if (n_stages > 8) n_stages = 8;
     smem = (size_t)n_stages * STAGE2 + FIXED;
     const int64_t pair_tiles = ceil_div(M, 2 * BLOCK_M) * n_tiles;
-    const int pair_sms = sms - tuning().sm_reserve > 2 ? sms - tuning().sm_reserve : 2;
-    const int64_t pairs = pair_tiles < pair_sms / 2 ? pair_tiles : pair_sms / 2;
+    const int64_t pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * pairs));
     cfg.blockDim = dim3(NTHREADS);
@@ -1139,8 +1138,8 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
   FG_REQUIRE(head == FITGNN_HEAD_IDENTITY || N <= 256, FITGNN_EUNSUP,
              "gemm_bf16x3: a fused (log-)softmax head needs N <= 256 (got %d)", N);
   FG_REQUIRE(M < (1ll << 31) - 128, FITGNN_ERANGE, "gemm_bf16x3: M exceeds the TMA coordinate range");
-  // persistent grids: one CTA per SM, minus the SMs left to a concurrent exchange kernel.  A CTA pair needs both SMs of a
-  // TPC, and the other kernel's CTAs land on arbitrary TPCs, so the pair kernel leaves twice as many
+  // persistent grids: one CTA per SM, minus the SMs left to a concurrent exchange kernel (fitgnn_peer_push launches clusters
+  // of two, i.e. takes whole TPCs, so a CTA-pair GEMM loses the same number of SMs)
   int sms = sm_count() - tuning().sm_reserve;
   if (sms < 2) sms = 2;
   CUtensorMap a_hi, a_lo;
@@ -1181,7 +1180,11 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
   if (N <= 48) FG_TC(48);
   if (N <= 64) FG_TC(64);
   if (N <= 128) FG_TC(128);
-  // small-K wide-output transforms are epilogue-bound as well (tuning switch; see the AGG dispatch above)
+  // small-K wide-output transforms are epilogue-bound as well: with an fp16-plane output the 12-epilogue-warp tile
+  // (see the AGG dispatch above; gemm_wide = -1 forbids it)
+  if (K <= 128 && out_f16 && head == FITGNN_HEAD_IDENTITY && !row_map && tuning().gemm_wide >= 0 && FG_AGG12_DEFAULT)
+    return tc::launch<256, false, false, tc::EPI_WARPS_12>(ga, ea, a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y,
+                                                           Y_lo, ldy, sms, st);
   if (K <= 128 && head == FITGNN_HEAD_IDENTITY && tuning().gemm_wide)
     return tc::launch<128, false, false, tc::EPI_WARPS_WIDE>(ga, ea, a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y,
                                                              Y_lo, ldy, sms, st);

@@ -152,6 +152,24 @@ extern "C" int fitgnn_peer_push(const void* src, void* const* host_dst, int n_ds
     FG_CUDA(cudaFuncSetAttribute(peer_push_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
+  if (n_ctas % 2 == 0) {
+    // clusters of two: a cluster's CTAs share a TPC, so the kernel occupies WHOLE TPCs and the CTA-pair GEMM running beside it
+    // (tuning sm_reserve) loses exactly n_ctas SMs, not up to 2 x n_ctas half-blocked TPCs
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)n_ctas);
+    cfg.blockDim = dim3(32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = as_stream(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FG_CUDA(cudaLaunchKernelEx(&cfg, peer_push_kernel, static_cast<const char*>(src), pa, bytes));
+    return FITGNN_OK;
+  }
   peer_push_kernel<<<n_ctas, 32, smem, as_stream(stream)>>>(static_cast<const char*>(src), pa, bytes);
   FG_LAUNCH_CHECK();
   return FITGNN_OK;

@@ -14,6 +14,7 @@
 // once.  High-degree rows (deg >= hub_deg) are split across the 8 warps of a CTA and reduced through shared
 // memory by the hub kernel so one warp never serialises thousands of gathers.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace fitgnn {
@@ -34,6 +35,18 @@ constexpr int SPMM_THREADS = SPMM_WARPS * 32;
 __device__ __forceinline__ float elu1(float x) { return elu_fast(x); }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// I/O modes of the gather kernels: 0 = fp32 rows in, fp32 out; 1 = fp32 in, bf16 hi/lo planes out; 2 = ONE fp16 plane in and
+// out (the hidden state of FITGNN_GEMM_FP16X2: half the gathered bytes; accumulation stays fp32).  ldx / ldy count elements.
+constexpr int IO_F32 = 0, IO_SPLIT = 1, IO_F16 = 2;
+// four consecutive elements at element offset `off` of a row-major fp32 (or, XH, fp16) matrix
+template <bool XH>
+__device__ __forceinline__ float4 ldx4(const float* X, int64_t off) {
+  if (!XH) return ldg4(X + off);
+  const uint2 r = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(X) + off));
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
 
 __device__ __forceinline__ void fma4(float4& a, float w, const float4& x) {
   a.x = fmaf(w, x.x, a.x);
@@ -48,10 +61,15 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
-template <bool SPLIT>
+template <int SPLIT>
 __device__ __forceinline__ void store_row4(void* Y, void* Ylo, int64_t off, float4 v) {
-  if (!SPLIT) {
+  if (SPLIT == IO_F32) {
     *reinterpret_cast<float4*>(static_cast<float*>(Y) + off) = v;
+  } else if (SPLIT == IO_F16) {
+    uint2 h;
+    h.x = pack_f16x2_rn(v.x, v.y);
+    h.y = pack_f16x2_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(static_cast<__half*>(Y) + off) = h;
   } else {
     uint2 h, l;
     split_bf16x2(v.x, v.y, h.x, l.x);
@@ -62,7 +80,7 @@ __device__ __forceinline__ void store_row4(void* Y, void* Ylo, int64_t off, floa
 }
 
 // One warp accumulates edges [beg, end) of row r for the column block starting at float4 index q0.
-template <int NV>
+template <int NV, bool XH = false>
 __device__ __forceinline__ void gather_edges(float4 (&acc)[NV], int beg, int end, const int32_t* __restrict__ col,
                                              const float* __restrict__ dinv, const int32_t* __restrict__ src_index,
                                              const float* __restrict__ X, int64_t ldx, int q0, int nq, int lane) {
@@ -80,11 +98,11 @@ __device__ __forceinline__ void gather_edges(float4 (&acc)[NV], int beg, int end
     int j = 0;
     for (; j + 4 <= cnt; j += 4) {
       float wj[4];
-      const float* pj[4];
+      int64_t pj[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         wj[u] = __shfl_sync(0xffffffffu, w, j + u);
-        pj[u] = X + __shfl_sync(0xffffffffu, soff, j + u);
+        pj[u] = __shfl_sync(0xffffffffu, soff, j + u);
       }
       float4 x[4][NV];
 #pragma unroll
@@ -92,7 +110,7 @@ __device__ __forceinline__ void gather_edges(float4 (&acc)[NV], int beg, int end
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
           const int q = q0 + lane + 32 * v;
-          x[u][v] = (q < nq) ? ldg4(pj[u] + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          x[u][v] = (q < nq) ? ldx4<XH>(X, pj[u] + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
       for (int u = 0; u < 4; ++u)
@@ -101,17 +119,17 @@ __device__ __forceinline__ void gather_edges(float4 (&acc)[NV], int beg, int end
     }
     for (; j < cnt; ++j) {
       const float wj = __shfl_sync(0xffffffffu, w, j);
-      const float* pj = X + __shfl_sync(0xffffffffu, soff, j);
+      const int64_t pj = __shfl_sync(0xffffffffu, soff, j);
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         const int q = q0 + lane + 32 * v;
-        if (q < nq) fma4(acc[v], wj, ldg4(pj + 4 * q));
+        if (q < nq) fma4(acc[v], wj, ldx4<XH>(X, pj + 4 * q));
       }
     }
   }
 }
 
-template <int NV, bool SPLIT>
+template <int NV, int SPLIT>
 __device__ __forceinline__ void epilogue(const float4 (&acc)[NV], float dr, const float* __restrict__ bias, int act,
                                          void* Y, void* Ylo, int64_t yoff, int q0, int nq, int lane) {
 #pragma unroll
@@ -165,7 +183,38 @@ struct RowInfo {
   bool live;     // this warp writes the row (false: out of range, or a hub row the hub kernel owns)
 };
 
-template <int NV, int LPR, bool SPLIT>
+// A lane's unit of work is one GROUP of a row: 4 fp32 (one 16-byte load, one float4 accumulator) or, on the fp16 plane, 8
+// halfs (one 16-byte load, two float4 accumulators) — the same number of load instructions moves half the bytes, and a
+// 512-wide row takes 2 loads per lane instead of 4.  nq counts groups; NV = groups per lane and column block.
+template <bool F16>
+struct Grp {
+  float4 v[F16 ? 2 : 1];
+};
+template <bool F16>
+__device__ __forceinline__ Grp<F16> grp_zero() {
+  Grp<F16> g;
+#pragma unroll
+  for (int i = 0; i < (F16 ? 2 : 1); ++i) g.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  return g;
+}
+template <bool F16>
+__device__ __forceinline__ Grp<F16> grp_load(const float* X, int64_t off) {  // off: element offset of the group
+  Grp<F16> g;
+  if (!F16) {
+    g.v[0] = ldg4(X + off);
+  } else {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(X) + off));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&r.z));
+    const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&r.w));
+    g.v[0] = make_float4(a.x, a.y, b.x, b.y);
+    g.v[F16 ? 1 : 0] = make_float4(c.x, c.y, d.x, d.y);
+  }
+  return g;
+}
+
+template <int NV, int LPR, int SPLIT>
 __global__ void __launch_bounds__(SPMM_THREADS, FG_SPMM_MINB)
 spmm_pipe_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ dinv,
                  const float* __restrict__ X, int64_t ldx, int nq, const int32_t* __restrict__ src_index,
@@ -173,6 +222,9 @@ spmm_pipe_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
                  void* Ylo, int64_t ldy, int hub_deg, int rows_per_warp) {
   constexpr int G = 32 / LPR;
   constexpr unsigned FULL = 0xffffffffu;
+  constexpr bool F16 = SPLIT == IO_F16;
+  constexpr int EPG = F16 ? 8 : 4;  // elements per group
+  constexpr int W4 = F16 ? 2 : 1;   // float4 accumulators per group
   const int lane = threadIdx.x & 31;
   const int sub = lane & (LPR - 1);
   const int grp = lane / LPR;
@@ -201,32 +253,34 @@ spmm_pipe_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
   auto load_s = [&](int c) { return c >= 0 ? (src_index ? __ldg(src_index + c) : c) : 0; };
 
   // gather up to LPR edges (one per sub-lane: weight w, source row s) into acc for the column block at q0
-  auto gather_chunk = [&](float4 (&acc)[NV], int cnt, float w, int s, int q0) {
+  auto gather_chunk = [&](Grp<F16> (&acc)[NV], int cnt, float w, int s, int q0) {
     const int maxcnt = __reduce_max_sync(FULL, cnt);
     constexpr int U = FG_SPMM_UNROLL;
     for (int j = 0; j < maxcnt; j += U) {
       float wj[U];
-      const float* pj[U];
+      int64_t pj[U];
       bool on[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         wj[u] = __shfl_sync(FULL, w, j + u, LPR);
         const int sj = __shfl_sync(FULL, s, j + u, LPR);
-        pj[u] = X + (int64_t)sj * ldx;
+        pj[u] = (int64_t)sj * ldx;
         on[u] = j + u < cnt;
       }
-      float4 x[U][NV];
+      Grp<F16> x[U][NV];
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
           const int q = q0 + sub + LPR * v;
-          x[u][v] = (on[u] && q < nq) ? ldg4(pj[u] + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          x[u][v] = (on[u] && q < nq) ? grp_load<F16>(X, pj[u] + EPG * q) : grp_zero<F16>();
         }
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int v = 0; v < NV; ++v) fma4(acc[v], wj[u], x[u][v]);
+        for (int v = 0; v < NV; ++v)
+#pragma unroll
+          for (int h = 0; h < W4; ++h) fma4(acc[v].v[h], wj[u], x[u][v].v[h]);
     }
   };
 
@@ -245,9 +299,9 @@ spmm_pipe_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
     const int deg = ia.end - ia.beg;
     const bool long_row = deg > LPR;
     for (int q0 = 0; q0 < nq; q0 += LPR * NV) {
-      float4 acc[NV];
+      Grp<F16> acc[NV];
 #pragma unroll
-      for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int v = 0; v < NV; ++v) acc[v] = grp_zero<F16>();
       gather_chunk(acc, min(deg, LPR), wa, sa, q0);
       for (int e0 = ia.beg + LPR; __any_sync(FULL, long_row && e0 < ia.end); e0 += LPR) {
         const int c = (long_row) ? load_col(ia, e0) : -1;
@@ -258,15 +312,29 @@ spmm_pipe_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
         for (int v = 0; v < NV; ++v) {
           const int q = q0 + sub + LPR * v;
           if (q < nq) {
-            float4 o = make_float4(acc[v].x * ia.dr, acc[v].y * ia.dr, acc[v].z * ia.dr, acc[v].w * ia.dr);
-            if (bias) {
-              const float4 b = ldg4(bias + 4 * q);
-              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            float4 o[W4];
+#pragma unroll
+            for (int h = 0; h < W4; ++h) {
+              const float4 a = acc[v].v[h];
+              o[h] = make_float4(a.x * ia.dr, a.y * ia.dr, a.z * ia.dr, a.w * ia.dr);
+              if (bias) {
+                const float4 b = ldg4(bias + EPG * q + 4 * h);
+                o[h].x += b.x; o[h].y += b.y; o[h].z += b.z; o[h].w += b.w;
+              }
+              if (act == FITGNN_ACT_ELU) {
+                o[h].x = elu1(o[h].x); o[h].y = elu1(o[h].y); o[h].z = elu1(o[h].z); o[h].w = elu1(o[h].w);
+              }
             }
-            if (act == FITGNN_ACT_ELU) {
-              o.x = elu1(o.x); o.y = elu1(o.y); o.z = elu1(o.z); o.w = elu1(o.w);
+            if (F16) {
+              uint4 pk;
+              pk.x = pack_f16x2_rn(o[0].x, o[0].y);
+              pk.y = pack_f16x2_rn(o[0].z, o[0].w);
+              pk.z = pack_f16x2_rn(o[W4 - 1].x, o[W4 - 1].y);
+              pk.w = pack_f16x2_rn(o[W4 - 1].z, o[W4 - 1].w);
+              *reinterpret_cast<uint4*>(static_cast<__half*>(Y) + i * ldy + EPG * q) = pk;
+            } else {
+              store_row4<SPLIT>(Y, Ylo, i * ldy + 4 * q, o[0]);
             }
-            store_row4<SPLIT>(Y, Ylo, i * ldy + 4 * q, o);
           }
         }
       }
@@ -279,7 +347,7 @@ spmm_pipe_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
 
 // hub rows: one CTA per row, the 8 warps take interleaved 32-edge chunks, partial sums are
 // reduced through shared memory (NV*128 floats per warp) by warp 0.
-template <int NV, bool SPLIT>
+template <int NV, int SPLIT>
 __global__ void __launch_bounds__(SPMM_THREADS)
 spmm_hub_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ dinv,
                 const float* __restrict__ X, int64_t ldx, int nq, const int32_t* __restrict__ src_index,
@@ -301,7 +369,7 @@ spmm_hub_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
 #pragma unroll
     for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int e0 = beg + 32 * w; e0 < end; e0 += 32 * SPMM_WARPS)
-      gather_edges<NV>(acc, e0, min(e0 + 32, end), col, dinv, src_index, X, ldx, q0, nq, lane);
+      gather_edges<NV, SPLIT == IO_F16>(acc, e0, min(e0 + 32, end), col, dinv, src_index, X, ldx, q0, nq, lane);
 #pragma unroll
     for (int v = 0; v < NV; ++v) part[w][v][lane] = acc[v];
     __syncthreads();
@@ -694,7 +762,7 @@ __global__ void spmm_find_hubs_kernel(const int32_t* __restrict__ rowptr, const 
   }
 }
 
-template <int NV, int LPR, bool SPLIT>
+template <int NV, int LPR, int SPLIT>
 static int launch_spmm(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X, int64_t ldx,
                        int nq, const int32_t* src_index, const float* bias, int act, const int32_t* out_rows,
                        int64_t n_out, void* Y, void* Ylo, int64_t ldy, const int32_t* hub_list, int n_hub,
@@ -704,8 +772,9 @@ static int launch_spmm(const int32_t* rowptr, const int32_t* col, const float* d
   int rpw = FG_SPMM_RPW;
   while (rpw > 1 && ceil_div(n_out, (int64_t)G * rpw * SPMM_WARPS) < (int64_t)sm_count() * 4) rpw >>= 1;
   const int64_t blocks = ceil_div(n_out, (int64_t)G * rpw * SPMM_WARPS);
+  // nq counts float4 quads; the fp16 variant of the pipelined kernel works on groups of 8 halfs (the hub kernel on quads)
   spmm_pipe_kernel<NV, LPR, SPLIT><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(
-      rowptr, col, dinv, X, ldx, nq, src_index, bias, act, out_rows, n_out, Y, Ylo, ldy, hub_deg, rpw);
+      rowptr, col, dinv, X, ldx, SPLIT == IO_F16 ? nq / 2 : nq, src_index, bias, act, out_rows, n_out, Y, Ylo, ldy, hub_deg, rpw);
   FG_LAUNCH_CHECK();
   if (n_hub > 0) {
     const unsigned hub_blocks = hub_count_dev ? (unsigned)min((int64_t)n_hub, (int64_t)sm_count() * 4) : (unsigned)n_hub;
@@ -735,7 +804,7 @@ extern "C" int fitgnn_spmm_hubs(const int32_t* rowptr, const int32_t* out_rows, 
 static int spmm_dispatch(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X, int64_t ldx, int width,
                          const int32_t* src_index, const float* bias, int act, const int32_t* out_rows, int64_t n_out, void* Y,
                          void* Y_lo, int64_t ldy, const int32_t* hub_list, int n_hub, int hub_deg,
-                         const int32_t* hub_count_dev, void* stream);
+                         const int32_t* hub_count_dev, void* stream, int f16 = 0);
 
 extern "C" int fitgnn_spmm_symnorm_hub(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X,
                                        int64_t ldx, int width, const int32_t* src_index, const float* bias, int act,
@@ -759,8 +828,9 @@ extern "C" int fitgnn_spmm_symnorm_devhub(const int32_t* rowptr, const int32_t* 
 static int spmm_dispatch(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X, int64_t ldx, int width,
                          const int32_t* src_index, const float* bias, int act, const int32_t* out_rows, int64_t n_out, void* Y,
                          void* Y_lo, int64_t ldy, const int32_t* hub_list, int n_hub, int hub_deg,
-                         const int32_t* hub_count_dev, void* stream) {
+                         const int32_t* hub_count_dev, void* stream, int f16) {
   FG_REQUIRE(rowptr && col && dinv && X && Y, FITGNN_EINVAL, "spmm: null pointer");
+  FG_REQUIRE(!f16 || !Y_lo, FITGNN_EINVAL, "spmm: the fp16 variant writes ONE plane (Y_lo must be NULL)");
   FG_REQUIRE(n_out >= 0 && width > 0, FITGNN_EINVAL, "spmm: n_out=%lld width=%d", (long long)n_out, width);
   FG_REQUIRE(width % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, FITGNN_EUNSUP,
              "spmm: width (%d), ldx (%lld), ldy (%lld) must be multiples of 4", width, (long long)ldx, (long long)ldy);
@@ -774,17 +844,38 @@ static int spmm_dispatch(const int32_t* rowptr, const int32_t* col, const float*
   const int nq = width / 4;
   const bool split = Y_lo != nullptr;
   if (n_hub == 0) hub_deg = 0x7fffffff;
-#define FG_SPMM(NV, LPR)                                                                                          \
-  return split ? launch_spmm<NV, LPR, true>(rowptr, col, dinv, X, ldx, nq, src_index, bias, act, out_rows, n_out, \
-                                            Y, Y_lo, ldy, hub_list, n_hub, hub_deg, st, hub_count_dev)           \
-               : launch_spmm<NV, LPR, false>(rowptr, col, dinv, X, ldx, nq, src_index, bias, act, out_rows,      \
-                                             n_out, Y, Y_lo, ldy, hub_list, n_hub, hub_deg, st, hub_count_dev)
+#define FG_SPMM_IO(NV, LPR, IO)                                                                                            \
+  launch_spmm<NV, LPR, IO>(rowptr, col, dinv, X, ldx, nq, src_index, bias, act, out_rows, n_out, Y, Y_lo, ldy, hub_list, \
+                           n_hub, hub_deg, st, hub_count_dev)
+  if (f16) {  // 16-byte loads of 8 halfs: width, pitches multiples of 8 and 16-byte aligned planes
+    FG_REQUIRE(width % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && ((uintptr_t)Y % 16) == 0, FITGNN_EUNSUP,
+               "spmm_f16: width (%d), ldx (%lld), ldy (%lld) must be multiples of 8, planes 16-byte aligned", width,
+               (long long)ldx, (long long)ldy);
+    // (groups per lane NV, lanes per row): 64 halfs -> 8 lanes x 1, 128 -> 8 x 2, 256 -> 16 x 2, 512+ -> 32 x 2 per column block
+    if (nq <= 16) return FG_SPMM_IO(1, 8, IO_F16);
+    if (nq <= 32) return FG_SPMM_IO(2, 8, IO_F16);
+    if (nq <= 64) return FG_SPMM_IO(2, 16, IO_F16);
+    return FG_SPMM_IO(2, 32, IO_F16);
+  }
+#define FG_SPMM(NV, LPR) return split ? FG_SPMM_IO(NV, LPR, IO_SPLIT) : FG_SPMM_IO(NV, LPR, IO_F32)
   if (nq <= 8) { FG_SPMM(1, 8); }
   if (nq <= 16) { FG_SPMM(2, 8); }
   if (nq <= 32) { FG_SPMM(4, 8); }
   if (nq <= 64) { FG_SPMM(4, 16); }
   FG_SPMM(4, 32);  // nq > 128 loops over 512-column blocks
 #undef FG_SPMM
+#undef FG_SPMM_IO
+}
+
+// The same aggregation on the fp16 hidden state of FITGNN_GEMM_FP16X2: X and Y are ONE fp16 plane each (ldx / ldy in
+// elements), sums in fp32.  hub_count (device) may be NULL: hub_cap is then the host-known number of hub rows.
+extern "C" int fitgnn_spmm_symnorm_f16(const int32_t* rowptr, const int32_t* col, const float* dinv, const void* X,
+                                       int64_t ldx, int width, const int32_t* src_index, const float* bias, int act,
+                                       const int32_t* out_rows, int64_t n_out, void* Y, int64_t ldy,
+                                       const int32_t* hub_list, const int32_t* hub_count, int hub_cap, int hub_deg,
+                                       void* stream) {
+  return spmm_dispatch(rowptr, col, dinv, static_cast<const float*>(X), ldx, width, src_index, bias, act, out_rows, n_out, Y,
+                       nullptr, ldy, hub_list, hub_list ? hub_cap : 0, hub_deg, hub_count, stream, 1);
 }
 
 extern "C" int fitgnn_spmm_symnorm(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X,

@@ -128,7 +128,11 @@ class PackedForward:
                     self.W0_fold = self._prep_weight(torch.cat([w0, self.b[0][:, None]], 1))
         if fuse_aggregate is True and self.apack is None:
             raise ValueError("fuse_aggregate=True but the pack / model is not eligible for the fused aggregation")
-        if self.f16_hidden and self.apack is None:
+        # classic schedule with the fp16 hidden state: first layer aggregate-first on bf16 planes, its transform writes the
+        # fp16 plane, later layers aggregate fp16 -> fp16 (ops.spmm_symnorm_f16) and transform fp16 -> fp16, head on fp16
+        self.f16_classic = (self.f16_hidden and self.apack is None and self.precision == ops.GEMM_BF16X3 and self.L >= 2
+                            and not self.transform_first and with_head and self.H % 8 == 0 and self.H >= 32)
+        if self.f16_hidden and self.apack is None and not self.f16_classic:
             self.f16_hidden = False
         if self.f16_hidden:  # layers >= 1 and the head take fp16 hi/lo weights (the first layer's A operand stays bf16 hi/lo)
             for i in range(1, self.L):
@@ -171,7 +175,7 @@ class PackedForward:
             out[name] = dict(ms=sum(ms) / len(ms), launches=len(ms), bytes=rec["bytes"], flops=rec["flops"])
         return out
 
-    def _spmm_bytes(self, width, src_index, last, n_src_rows, out_elem=4):
+    def _spmm_bytes(self, width, src_index, last, n_src_rows, out_elem=4, in_elem=4):
         """Algorithmic bytes of one SpMM launch: CSR rowptr + col, dinv of the sources, the
         optional gid read, every distinct source row once, every output row once, bias."""
         p = self.pack
@@ -186,7 +190,7 @@ class PackedForward:
             self._nnz_cache[key] = nnz
         nnz = self._nnz_cache[key]
         r_out = self.n_out if last else p.n_rows
-        b = 4 * (r_out + 1) + 4 * nnz + 4 * n_src_rows * width + out_elem * r_out * width + 4 * width + 4 * n_src_rows
+        b = 4 * (r_out + 1) + 4 * nnz + in_elem * n_src_rows * width + out_elem * r_out * width + 4 * width + 4 * n_src_rows
         if src_index is not None:
             b += 4 * p.n_rows
         if last and self.out_rows is not None:
@@ -394,6 +398,8 @@ class PackedForward:
         X = self.pad_features(X)
         gid0 = None if packed else p.gid
         h = None
+        if self.f16_classic:
+            return self._forward_classic_f16(X, gid0, out)
         for i in range(self.L):
             last = i == self.L - 1
             if i == 0 and self.transform_first:
@@ -438,6 +444,46 @@ class PackedForward:
             view = out[:, : self.C]
         res = self._gemm(h, self.Wl, self.bl, ops.ACT_NONE, self.head, N=self.C, K=self.H, name="head", out=out)
         return res if view is None else view
+
+    def _forward_classic_f16(self, X, gid0, out):
+        """Classic schedule (SpMM + transform per layer) with the hidden state as ONE fp16 plane (precision='fp16x2')."""
+        p = self.pack
+        H, Fp = self.H, self.Fp
+        A = self._spmm(X, Fp, gid0, None, ops.ACT_NONE, False, split=True, name="spmm0")
+        self.launches += 1
+        M = p.n_rows
+        h = self._timed("gemm0", lambda: ops.gcn_transform_aggregate_f16(A, self.W[0], self.b[0], ops.ACT_ELU, None, None,
+                                                                         K=Fp, N=H),
+                        nbytes=4 * M * Fp + 4 * Fp * H + 2 * M * H, flops=2 * M * Fp * H)
+        for i in range(1, self.L):
+            last = i == self.L - 1
+            rows = self.out_rows if last else None
+            hubs = self.hubs_out if last else self.hubs_all
+            n_rows = self.n_out if last else p.n_rows
+            src = h
+            self.launches += 1 + (1 if hubs[1] > 0 else 0)
+            A = self._timed(f"spmm{i}", lambda: ops.spmm_symnorm_f16(p.rowptr, p.col, p.dinv, src, H, None, None, ops.ACT_NONE,
+                                                                      rows, hubs=hubs),
+                            nbytes=self._spmm_bytes(H, None, last, p.n_rows, out_elem=2, in_elem=2))
+            self.launches += 1
+            h = self._timed(f"gemm{i}", lambda: ops.gemm_f16(A, self.W[i], self.b[i], ops.ACT_ELU, out_f16=True, K=H, N=H),
+                            nbytes=2 * n_rows * H + 4 * H * H + 2 * n_rows * H, flops=2 * n_rows * H * H)
+        n = self.n_out
+        self.launches += 1
+        nb = 2 * n * H + 4 * H * self.C + 4 * n * self.C
+        fl = 2 * n * H * self.C
+        if self.out_map is not None:
+            self._timed("head", lambda: ops.gemm_f16(h, self.Wl, self.bl, ops.ACT_NONE, self.head, row_map=self.out_map, out=out,
+                                                     K=H, N=self.C), nbytes=nb + 4 * n, flops=fl)
+            return out
+        view = None
+        if out is None:
+            out = torch.empty(n, ops.pad4(self.C), dtype=torch.float32, device=X.device)
+        if out.shape[1] != self.C:
+            view = out[:, : self.C]
+        self._timed("head", lambda: ops.gemm_f16(h, self.Wl, self.bl, ops.ACT_NONE, self.head, out=out, K=H, N=self.C),
+                    nbytes=nb, flops=fl)
+        return out if view is None else view
 
     def capture(self, X_example):
         """CUDA-graph the whole forward (the small configs are launch-bound): returns run(X) that copies X

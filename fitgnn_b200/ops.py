@@ -86,6 +86,21 @@ def spmm_symnorm(rowptr, col, dinv, X, width=None, src_index=None, bias=None, ac
     return out
 
 
+def spmm_symnorm_f16(rowptr, col, dinv, X, width=None, src_index=None, bias=None, act=ACT_NONE, out_rows=None, out=None,
+                     hubs=None):
+    """spmm_symnorm on ONE fp16 plane in and out (FITGNN_GEMM_FP16X2's hidden state): fp32 sums, half the gathered bytes."""
+    assert X.dtype == torch.float16 and X.dim() == 2
+    width = X.shape[1] if width is None else width
+    n_out = out_rows.numel() if out_rows is not None else rowptr.numel() - 1
+    if out is None:
+        out = torch.empty(n_out, width, dtype=torch.float16, device=X.device)
+    hub_list, n_hub, hub_deg = hubs if (hubs is not None and hubs[1] > 0) else (None, 0, 0)
+    check(lib().fitgnn_spmm_symnorm_f16(ptr(rowptr), ptr(col), ptr(dinv), ptr(X), X.stride(0), width, ptr(src_index), ptr(bias),
+                                        act, ptr(out_rows), n_out, ptr(out), out.stride(0), ptr(hub_list), None, n_hub, hub_deg,
+                                        stream_ptr()))
+    return out
+
+
 def spmm_symnorm_grouped(rowptr, col, dinv, X, width=None, src_index=None, out=None, split=False, group=32,
                          pad_value=None):
     """Y = Â·X[src_index] on a group-aligned pack (Pack.aligned): fitgnn_spmm_symnorm_grouped, bit-identical to
@@ -536,7 +551,7 @@ def gemm_f16_head_rows_peers(A, W, bias, act, head, row_map, peer_ptrs, ldy, K=N
 
 def gcn_transform_aggregate_f16(A, W, bias, act, agg_desc, dinv, K=None, N=None, defer_row_scale=False):
     """gcn_transform_aggregate whose result is ONE fp16 plane.  A = bf16 (hi, lo) planes with W = bf16 planes, or A = one
-    fp16 plane with W = fp16 (hi, lo) planes."""
+    fp16 plane with W = fp16 (hi, lo) planes.  agg_desc = None: the plain transform into an fp16 plane."""
     w_hi, w_lo = W
     in_f16 = not isinstance(A, tuple)
     a_hi, a_lo = (A, None) if in_f16 else A

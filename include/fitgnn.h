@@ -283,11 +283,19 @@ int fitgnn_gemm_rowscale_bias_act_split(int precision, const void* A, const void
  *     FP16X2 product's A; no head / row map then), else fp32 [M, ldy] (row_map as in fitgnn_gemm_head_rows, may be NULL).
  *   fitgnn_gcn_transform_aggregate_f16: fitgnn_gcn_transform_aggregate with an fp16-plane OUTPUT; the input is a bf16
  *     hi/lo pair (in_f16 = 0, W = bf16 planes: the first layer) or an fp16 plane (in_f16 = 1, A_lo = NULL, W = fp16 planes).
+ *     agg_desc may be NULL: the plain transform act(A·W^T + bias) into an fp16 plane (classic schedule, first layer).
+ *   fitgnn_spmm_symnorm_f16: fitgnn_spmm_symnorm_hub / _devhub on ONE fp16 plane in and out (ldx / ldy in elements, fp32
+ *     sums): the later layers' aggregation of the classic schedule, half the gathered bytes.  hub_count (device) may be
+ *     NULL: hub_cap is then the host-known number of hub rows (0 = none).
  *   fitgnn_split_f16: fp32 -> fp16 hi/lo planes (lo may be NULL: the hi plane only); values beyond +-65504 saturate. */
 int fitgnn_split_f16(const float* X, int64_t ldx, int64_t rows, int cols, void* hi, void* lo, int64_t ldo, void* stream);
 int fitgnn_gemm_f16(const void* A, int64_t lda, const void* W_hi, const void* W_lo, int64_t ldw,
                     const float* row_scale, const float* bias, int64_t M, int K, int N, int act, int head,
                     void* Y, int64_t ldy, int out_f16, const int32_t* row_map, void* stream);
+int fitgnn_spmm_symnorm_f16(const int32_t* rowptr, const int32_t* col, const float* dinv, const void* X, int64_t ldx,
+                            int width, const int32_t* src_index, const float* bias, int act, const int32_t* out_rows,
+                            int64_t n_out, void* Y, int64_t ldy, const int32_t* hub_list, const int32_t* hub_count,
+                            int hub_cap, int hub_deg, void* stream);
 /* fitgnn_gemm_head_rows_peers with an fp16-plane A operand (FITGNN_GEMM_FP16X2) */
 int fitgnn_gemm_f16_head_rows_peers(const void* A, int64_t lda, const void* W_hi, const void* W_lo, int64_t ldw,
                                     const float* bias, int64_t M, int K, int N, int act, int head,

@@ -475,6 +475,72 @@ def test_fp16_hidden_state_schedule_matches_oracle(fg):
     g3 = fg.PackedForward(pack, sd3, precision="fp16x2")(X).cpu().numpy()
     r3 = fg.PackedForward(pack, sd3, precision="bf16x3")(X).cpu().numpy()
     assert np.abs(g3 - r3).max() <= 3e-4 * np.abs(r3).max()
-    # a pack the fused schedule cannot take (cluster mode) silently runs bf16x3
-    cl = fg.build_pack(ei[:, :100000], part, k, "cluster")
-    assert not fg.PackedForward(cl, sd, precision="fp16x2").f16_hidden
+    # a pack the fused schedule cannot take (cluster mode) runs the classic schedule on the fp16 plane
+    cl = fg.PackedForward(fg.build_pack(ei[:, :100000], part, k, "cluster"), sd, precision="fp16x2")
+    assert cl.f16_hidden and cl.f16_classic and cl.apack is None
+    # a model the fp16 plane does not cover (one layer) silently runs bf16x3
+    sd1 = fg.synth.init_state_dict(F, 512, C, num_layers=1, seed=4)
+    assert not fg.PackedForward(pack, sd1, precision="fp16x2", fuse_aggregate=False).f16_hidden
+
+
+@pytest.mark.parametrize("width", [64, 128, 256, 512, 1024])
+def test_spmm_f16_matches_the_fp32_spmm_of_the_same_plane(fg, width):
+    """fitgnn_spmm_symnorm_f16 (fp16 plane in, fp32 sums, fp16 plane out) against fitgnn_spmm_symnorm on the same values in
+    fp32: equal up to the final fp16 rounding (2^-11 relative); all rows / a row selection, bias + ELU, hub rows."""
+    n = 20000
+    ei, part, cw, k = planted(fg, n, 200000, seed=7, sizes="powerlaw")
+    pack = fg.build_pack(ei, part, k, "none")
+    g = torch.Generator(device="cuda").manual_seed(width)
+    Xh = torch.randn(pack.n_rows, width, generator=g, device=dev()).half()
+    bias = torch.randn(width, generator=g, device=dev())
+    rows = torch.randperm(pack.n_rows, generator=g, device=dev())[: pack.n_rows // 3].sort().values.to(torch.int32)
+    for out_rows in (None, rows):
+        for b, act in ((None, fg.ops.ACT_NONE), (bias, fg.ops.ACT_ELU)):
+            want = fg.ops.spmm_symnorm(pack.rowptr, pack.col, pack.dinv, Xh.float(), width, None, b, act, out_rows)
+            got = fg.ops.spmm_symnorm_f16(pack.rowptr, pack.col, pack.dinv, Xh, width, None, b, act, out_rows)
+            assert got.dtype == torch.float16 and got.shape == want.shape
+            assert bool(((got.float() - want).abs() <= 4.9e-4 * want.abs() + 1e-7).all())
+    # a star with 3000 leaves: the hub kernel (CTA-split row) on the fp16 plane
+    m = 3001
+    src = torch.cat([torch.zeros(m - 1, dtype=torch.long), torch.arange(1, m)])
+    dst = torch.cat([torch.arange(1, m), torch.zeros(m - 1, dtype=torch.long)])
+    rowptr, col, dinv = fg.ops.csr_from_coo(torch.stack([src, dst]).to(dev()), m)
+    hubs = fg.ops.find_hubs(rowptr, None, m)
+    assert hubs[1] == 1
+    Xs = torch.randn(m, width, generator=g, device=dev()).half()
+    want = fg.ops.spmm_symnorm(rowptr, col, dinv, Xs.float(), hubs=hubs)
+    got = fg.ops.spmm_symnorm_f16(rowptr, col, dinv, Xs, hubs=hubs)
+    assert bool(((got.float() - want).abs() <= 4.9e-4 * want.abs() + 1e-6).all())
+
+
+@pytest.mark.parametrize("mode", ["none", "extra", "cluster"])
+def test_classic_schedule_on_the_fp16_plane_matches_bf16x3_and_the_oracle(fg, mode):
+    """precision='fp16x2' without the fused schedule (fuse_aggregate=False, or a pack that is not eligible): SpMM + transform
+    per layer with the hidden state as ONE fp16 plane; power-law graph, so cluster mode has hub rows; row-mapped head."""
+    n, F, H, C = 5000, 100, 512, 47
+    ei = fg.synth.powerlaw_graph(n, 20000, seed=11)
+    partition, comps, C_list = fg.synth.neighborhood_partition(ei, n, 0.3, seed=11)
+    eid = torch.tensor(ei, device=dev())
+    X = fg.synth.features(n, F, seed=11, device=dev())
+    pack = fg.build_pack(eid, torch.tensor(partition.part), partition.k, mode)
+    Xg = torch.cat([X, fg.coarsen.project(eid, X, partition)["Xc"]], 0) if mode == "cluster" else X
+    for layers in (2, 3):
+        sd = fg.synth.init_state_dict(F, H, C, num_layers=layers, seed=layers)
+        f = fg.PackedForward(pack, sd, precision="fp16x2", fuse_aggregate=False)
+        assert f.f16_classic
+        got = f(Xg)
+        ref = fg.PackedForward(pack, sd, precision="bf16x3", fuse_aggregate=False)(Xg)
+        assert_close(got.cpu().numpy(), ref.cpu().numpy())
+        assert float((got - ref).abs().max()) <= 3e-4 * float(ref.abs().max())
+        if mode == "none" and layers == 2:
+            ids = np.arange(min(partition.k, 300))
+            subs = fo.subgraphs_from_partition(ei, X.cpu().numpy(), partition.part, ids)
+            sel = [np.ones(s_["x"].shape[0], dtype=bool) for s_ in subs]
+            want = fo.node_infer_batched({k_: v.cpu() for k_, v in sd.items()}, subs, sel, "node_cls", 128).numpy()
+            assert_close(got[: want.shape[0]].cpu().numpy(), want)
+            # the same rows through a row map into a caller's buffer
+            perm = torch.randperm(f.n_out, device=dev()).to(torch.int32)
+            out = torch.zeros(f.n_out, fg.ops.pad4(C), device=dev())
+            fm = fg.PackedForward(pack, sd, precision="fp16x2", fuse_aggregate=False, out_map=perm)
+            fm(Xg, out=out)
+            assert torch.equal(out[perm.long(), :C], got[:, :C])
