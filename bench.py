@@ -68,9 +68,11 @@ def parse():
                         "p2p = head kernel stores into every rank's gather buffer over NVLink "
                         "(+ a one-element all-reduce as barrier); ce = head into the local slot, copy-engine pushes to the "
                         "peers on a side stream overlapping the next step's compute; nccl = local slot, then all_gather; "
-                        "auto = p2p up to 4 GPUs, ce above (measured); the variant not chosen (sharded / gathered) is timed "
+                        "auto = p2p at 2 GPUs, push (with as many SMs left free by the GEMM grids) above (measured, "
+                        "profiles/r2_multi_gpu.md); the variant not chosen (sharded / gathered) is timed "
                         "after the headline and reported in multi_gpu.sharded / multi_gpu.gathered")
-    p.add_argument("--push-ctas", type=int, default=16, help="CTAs of the peer-push kernel (--collective push)")
+    p.add_argument("--push-ctas", type=int, default=-1,
+                   help="CTAs of the peer-push kernel (--collective push); -1 = 16 up to 4 GPUs, 24 at 8 (measured)")
     p.add_argument("--sm-reserve", type=int, default=-1,
                    help="SMs the persistent GEMM grids leave free (tuning 'sm_reserve'); -1 = the push kernel's CTA count with "
                         "--collective push, else 0")
@@ -598,9 +600,14 @@ def main_ours(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     from fitgnn_b200._lib import set_tuning
-    sm_reserve = args.sm_reserve if args.sm_reserve >= 0 else (args.push_ctas if (world > 1 and args.collective == "push") else 0)
-    if sm_reserve:
-        set_tuning("sm_reserve", sm_reserve)
+    if args.push_ctas <= 0:
+        args.push_ctas = 16 if world <= 4 else 24
+    uses_push = world > 1 and (args.collective == "push" or (args.collective in ("auto", "none") and world > 2))
+    sm_reserve = args.sm_reserve if args.sm_reserve >= 0 else (args.push_ctas if uses_push else 0)
+
+    def apply_reserve(coll):
+        """the persistent GEMM grids leave SMs free only while the push kernel runs beside them"""
+        set_tuning("sm_reserve", sm_reserve if (coll == "push" or args.sm_reserve >= 0) else 0)
     if args.agg_wide is not None:
         set_tuning("agg_wide", args.agg_wide)
     if world > 1:
@@ -677,15 +684,16 @@ def main_ours(args):
     # fused output exchange (see dist.PeerGather): needs the group-aligned schedule (row-mapped head stores)
     pg, coll_gather = None, "nccl" if world > 1 else "none"
     want_coll = args.collective
-    gather_pref = args.collective if args.collective not in ("auto", "none") else ("p2p" if world <= 4 else "ce")
+    gather_pref = args.collective if args.collective not in ("auto", "none") else ("p2p" if world <= 2 else "push")
     if world > 1 and gather_pref != "nccl" and all(f.apack is not None for f in fwds):
         try:
             from fitgnn_b200.dist import PeerGather
             pg = PeerGather(shard, Cp, device, n_buffers=2, backend="ipc")
-            # measured (profiles/r1_multi_gpu.md, profiles/r2_multi_gpu.md): the fused peer stores win up to 4 GPUs; at 8 the head
-            # becomes NVLink-egress-bound and the overlapped copy-engine exchange is ahead.  The SM-driven push kernel ('push')
-            # loses to both: every CTA it occupies delays one CTA of the persistent 148-CTA GEMMs by the whole push; the
-            # multicast store does not help an all-gather (every rank still has to RECEIVE all the other slots)
+            # measured (profiles/r1_multi_gpu.md, profiles/r2_multi_gpu.md): the fused peer stores win at 2 GPUs; from 4 on the head
+            # becomes NVLink-egress-bound and an exchange overlapped with the next step is ahead: copy engines reach ~310 GB/s
+            # in the all-to-all pattern, the SM-driven push kernel ~45 GB/s per CTA up to ~490 GB/s — provided the persistent GEMM
+            # grids leave its SMs free (tuning sm_reserve), otherwise every CTA it occupies delays one GEMM CTA by the whole push;
+            # the multicast store does not help an all-gather (every rank still has to RECEIVE all the other slots)
             coll_gather = gather_pref
         except Exception as e:  # IPC not permitted in this container, ...
             if args.collective == "p2p":
@@ -699,6 +707,7 @@ def main_ours(args):
     # the headline ends every step with ALL logits on every rank (north_star: "the final logit all-gather");
     # --collective none leaves them sharded.  The other variant is timed after the headline and reported beside it.
     collective = "none" if (world == 1 or want_coll == "none") else coll_gather
+    apply_reserve(collective)
 
     def run_local(Xin, buf):
         """outputs stay sharded: every chunk's head writes this rank's slot of `buf` (same layout as the gathered variants)"""
@@ -843,6 +852,7 @@ def main_ours(args):
         del res
         # the other variant (headline gathered -> sharded outputs, headline sharded -> all-gathered), same steps / warm-up / clock
         other = coll_gather if collective == "none" else "none"
+        apply_reserve(other)
         for _ in range(max(args.warmup, 3)):
             out = step(other)
         drain(other)
@@ -865,6 +875,7 @@ def main_ours(args):
                       "unit": UNIT, "all_gather_bytes": int(n * Cp * 4) if other != "none" else 0,
                       "vs_single_gpu_max_abs_err_all_ranks": g_err}
         del full
+        apply_reserve(collective)
         barrier()
 
     # ---- N = 1: the pack-ordered input gives the same logits, bit for bit, as the node-ordered table gathered through gid

@@ -213,12 +213,14 @@ class PeerGather:
         every peer on a side stream, then the barrier, all behind whatever the current stream does next (the following step's
         compute).  `wait(i)` makes the current stream wait for buffer i to be complete on every rank; `acquire(i)` must
         precede the next write of it.
-        engine 'ce' (default): per-peer cudaMemcpyAsync on one stream per peer (copy engines, no SM time).
-        engine 'push': ONE small kernel (fitgnn_peer_push, `push_ctas` CTAs) streams the slot through shared memory and
-        bulk-stores it to all peers.  Measured on 2 x B200 (profiles/r2_multi_gpu.md): ~50 GB/s per CTA (396 GB/s with 8,
-        695 GB/s with 32 CTAs; one copy-engine copy: 733 GB/s), and every SM it occupies holds back one CTA of the
-        persistent 148-CTA GEMM kernels for the whole push, so the step gets SLOWER (3.45-4.70 ms against 3.14 ms);
-        kept for schedules whose kernels do not need every SM."""
+        engine 'ce' (default): per-peer cudaMemcpyAsync on one stream per peer (copy engines, no SM time; ~310 GB/s in the
+        8-GPU all-to-all pattern).
+        engine 'push': ONE small kernel (fitgnn_peer_push, `push_ctas` CTAs launched as clusters of two = whole TPCs) streams the
+        slot through shared memory and bulk-stores it to all peers: ~45 GB/s of egress per CTA, ~490 GB/s at 24.  Every SM
+        it occupies would hold back one CTA of the persistent 148-CTA GEMM kernels for the whole push (2 GPUs: 3.45-4.70 ms
+        against 3.14 ms), so the caller sets the tuning switch `sm_reserve` (= push_ctas) while the push overlaps compute:
+        the GEMM grids then leave those SMs free.  Measured (profiles/r2_multi_gpu.md): 8 GPUs 1.28 (ce) -> 0.82 ms per step,
+        4 GPUs 1.61 (p2p) -> 1.27 ms."""
         s = self.shard
         cur = torch.cuda.current_stream()
         self._ready[i].record(cur)
