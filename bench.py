@@ -39,10 +39,11 @@ def parse():
     p.add_argument("--workload", default="products", choices=["products", "products-small"])
     p.add_argument("--mode", default="none", choices=["none", "extra", "cluster"])
     p.add_argument("--ratio", type=float, default=0.5)
-    p.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16x3", "fp16x2"],
+    p.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16x3", "fp16x2", "fp16"],
                    help="arithmetic of the dense transforms: bf16x3 = bf16 hi/lo planes for both operands, 3 MMAs (fp32-grade: parity "
                         "~5e-7); fp16x2 = bf16x3 first layer, then the hidden state as ONE fp16 plane, 2 MMAs (parity ~1.5e-5 of the "
-                        "1e-3 bound; the verdict's '2 instead of 3 MMAs for the K = 512 layer'); fp32 = CUDA-core GEMM; auto = fp16x2")
+                        "1e-3 bound; the verdict's '2 instead of 3 MMAs for the K = 512 layer'); fp16 = fp16x2 with ONE fp16 weight plane in "
+                        "the 512 x 512 transform (1 MMA, W-stationary CTA pairs; parity ~1.8e-5); fp32 = CUDA-core GEMM; auto = fp16")
     p.add_argument("--hidden", type=int, default=512)
     p.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -83,7 +84,7 @@ def parse():
                         "graph shape with power-law subgraph sizes (hybrid fused + classic schedule); cluster = the headline "
                         "graph with cluster_node augmentation (sharded pack, streamed forward); train = one GD training step "
                         "(forward + backward + Adam) on the headline pack; per_query = the reference's per-sample latency loop; "
-                        "alt_precision = the headline configuration in the other arithmetic (bf16x3 <-> fp16x2)")
+                        "alt_precision = the headline configuration in the other arithmetics (bf16x3 and fp16x2 beside an fp16 headline)")
     p.add_argument("--only-modes", action="store_true", help="skip the headline measurement (profiling the --modes blocks)")
     p.add_argument("--mode-steps", type=int, default=0, help="timed steps of the --modes blocks (0 = min(--steps, 5))")
     p.add_argument("--max-rows", type=int, default=1 << 22, help="rows per shard of the streamed forward (--modes blocks)")
@@ -491,6 +492,28 @@ def mode_train(args, fg, device, n, F, C, ei, part, k, X, precision, steps, samp
             "clocks": sampler.summary(m0, m1) if sampler else None}
 
 
+def dtype_of(fwd):
+    if not getattr(fwd, "f16_hidden", False):
+        return "bf16x3(f32 accumulate)"
+    if getattr(fwd, "w_single", False):
+        return ("bf16x3 first layer; fp16 hidden state x ONE fp16 weight plane (1 MMA) in the 512 x 512 transforms, x fp16 hi/lo "
+                "weights (2 MMAs) in the head; f32 accumulate")
+    return "bf16x3 first layer; fp16 A x fp16 hi/lo W, 2 MMAs, f32 accumulate for the 512-wide layers"
+
+
+def mode_precisions(args, fg, device, n, F, C, ei, part, k, X, sd, steps, sampler, precision):
+    """alt_precision block: every other tensor-core arithmetic than the headline's, same configuration, same box."""
+    others = [p_ for p_ in ("bf16x3", "fp16x2", "fp16") if p_ != precision]
+    if precision == "fp32":
+        others = ["bf16x3"]
+    res = {}
+    for which in others:
+        res[which] = mode_precision(args, fg, device, n, F, C, ei, part, k, X, sd, steps, sampler, which)
+        torch.cuda.empty_cache()
+    first = res[others[0]]
+    return {**first, "others": {w_: r_ for w_, r_ in res.items() if w_ != others[0]}}
+
+
 def mode_precision(args, fg, device, n, F, C, ei, part, k, X, sd, steps, sampler, which):
     """The headline configuration in the OTHER arithmetic than the headline's: 'bf16x3' = bf16 hi/lo planes for both operands of
     every transform (3 MMAs per product, fp32-grade agreement with the reference path) or 'fp16x2' = bf16x3 first layer, then the
@@ -522,8 +545,7 @@ def mode_precision(args, fg, device, n, F, C, ei, part, k, X, sd, steps, sampler
     want = fo.node_infer_batched({k_: v.cpu() for k_, v in sd.items()}, subs, sel, "node_cls", 128)
     return {"workload": f"headline configuration with precision='{which}'",
             "ms_per_step": ms, "value": n / (ms * 1e-3), "unit": UNIT, "steps": steps, "gpu_launches": fwd.launches - l0,
-            "dtype": "bf16x3 first layer; fp16 A x fp16 hi/lo W, 2 MMAs, f32 accumulate for the 512-wide layers" if fwd.f16_hidden
-                     else "bf16x3(f32 accumulate)",
+            "dtype": dtype_of(fwd),
             "kernels": kernels, "clocks": sampler.summary(m0, m1) if sampler else None,
             "parity": parity_block(out[: want.shape[0], :C], want, f"oracle CPU path, first {n_sub} subgraphs")}
 
@@ -617,7 +639,7 @@ def main_ours(args):
     n, F, C, ei, part, cw, k, X, sd = generate(args, device)
     if args.only_modes:  # profiling entry: just the --modes blocks, printed as the JSON line
         assert world == 1, "--only-modes is a single-GPU run"
-        precision = args.precision if args.precision != "auto" else os.environ.get("FITGNN_PRECISION", "fp16x2")
+        precision = args.precision if args.precision != "auto" else os.environ.get("FITGNN_PRECISION", "fp16")
         k_steps = args.mode_steps or min(args.steps, 5)
         res = {}
         for m in [m_ for m_ in args.modes.split(",") if m_]:
@@ -628,8 +650,7 @@ def main_ours(args):
             elif m == "per_query":
                 res[m] = mode_per_query(args, fg, device, n, F, C, ei, part, k, X, sd, precision, None)
             elif m == "alt_precision":
-                res[m] = mode_precision(args, fg, device, n, F, C, ei, part, k, X, sd, k_steps, None,
-                                        "bf16x3" if precision == "fp16x2" else "fp16x2")
+                res[m] = mode_precisions(args, fg, device, n, F, C, ei, part, k, X, sd, k_steps, None, precision)
             else:
                 res[m] = mode_cluster(args, fg, device, n, F, C, ei, part, cw, k, X, sd, precision, k_steps, None)
             torch.cuda.empty_cache()
@@ -653,7 +674,7 @@ def main_ours(args):
     shard = ShardedPack(pack, world, rank, args.hidden, F, n_chunks=n_chunks, local_table=world > 1)
     precision = args.precision
     if precision == "auto":
-        precision = os.environ.get("FITGNN_PRECISION", "fp16x2")
+        precision = os.environ.get("FITGNN_PRECISION", "fp16")
     fwds = [fg.PackedForward(lp, sd, head="log_softmax", rows="core", precision=precision,
                              fuse_aggregate=False if args.no_fuse_aggregate else "auto", align_policy=args.align_policy)
             for lp in shard.locals]
@@ -1000,6 +1021,8 @@ def main_ours(args):
         # MMAs per logical product: bf16x3 = 3 (hi*hi + lo*hi + hi*lo); fp16 hidden state = 2 (A*W_hi + A*W_lo) for every
         # transform whose A operand is the fp16 plane (all but the first)
         mmas = 2 if (f16_hidden and name not in ("gemm0_agg", "gemm0")) else 3
+        if f16_hidden and getattr(fwd, "w_single", False) and name.startswith("gemm") and name not in ("gemm0_agg", "gemm0"):
+            mmas = 1  # precision 'fp16': ONE fp16 weight plane in the hidden -> hidden transforms
         tensor_bound = (name.startswith("gemm") or name == "head") and precision != "fp32" and \
             mmas * r["TFLOPs"] / tc_peak > r["GBps"] / hbm_peak
         if tensor_bound:
@@ -1021,8 +1044,7 @@ def main_ours(args):
     line = {"metric": METRIC, "value": n / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None,
-            "dtype": "f32" if precision == "fp32" else ("bf16x3 first layer, fp16 hidden state x fp16 hi/lo weights (2 MMAs), f32 accumulate"
-                                                        if f16_hidden else "bf16x3(f32 accumulate)"), "data": "synthetic",
+            "dtype": "f32" if precision == "fp32" else dtype_of(fwd), "data": "synthetic",
             "config": config_of(args, n, F, C, k), "roofline": roofline_of(dom), "roofline_spmm": spmm_roof,
             "schedule": ("spmm0 -> [transform + next layer's aggregation in the epilogue] -> transform -> head (group-aligned "
                          f"pack, {fwd.apack.n_rows} rows incl. padding)") if fused else "spmm + transform per layer -> head",
@@ -1079,8 +1101,7 @@ def main_ours(args):
             elif m == "per_query":
                 line["modes"][m] = mode_per_query(args, fg, device, n, F, C, ei_keep, part, k, X, sd, precision, sampler2)
             elif m == "alt_precision":
-                line["modes"][m] = mode_precision(args, fg, device, n, F, C, ei_keep, part, k, X, sd, k_steps, sampler2,
-                                                  "bf16x3" if precision == "fp16x2" else "fp16x2")
+                line["modes"][m] = mode_precisions(args, fg, device, n, F, C, ei_keep, part, k, X, sd, k_steps, sampler2, precision)
             else:
                 raise SystemExit(f"bench: unknown --modes entry {m!r}")
             torch.cuda.empty_cache()

@@ -34,7 +34,8 @@ static int env_int(const char* name, int dflt) {
 }
 static Tuning& tuning_mut() {
   static Tuning t{env_int("FITGNN_GEMM_WS", 1),   getenv("FITGNN_HEAD_BULK") ? 0 : 1, env_int("FITGNN_AGG_WIDE", 0),
-                  env_int("FITGNN_GEMM_WIDE", 0), env_int("FITGNN_GEMM_PAIR", 1), env_int("FITGNN_SM_RESERVE", 0)};
+                  env_int("FITGNN_GEMM_WIDE", 0), env_int("FITGNN_GEMM_PAIR", 1), env_int("FITGNN_SM_RESERVE", 0),
+                  env_int("FITGNN_GEMM_PAIR_WS", 1)};
   return t;
 }
 const Tuning& tuning() { return tuning_mut(); }
@@ -47,6 +48,7 @@ static int* tuning_field(const char* name) {
   if (!strcmp(name, "gemm_wide")) return &t.gemm_wide;
   if (!strcmp(name, "gemm_pair")) return &t.gemm_pair;
   if (!strcmp(name, "sm_reserve")) return &t.sm_reserve;
+  if (!strcmp(name, "gemm_pair_ws")) return &t.gemm_pair_ws;
   return nullptr;
 }
 
@@ -205,7 +207,7 @@ extern "C" int fitgnn_gcn_layer_fused(const int32_t* rowptr, const int32_t* col,
 extern "C" int fitgnn_gemm_f16(const void* A, int64_t lda, const void* W_hi, const void* W_lo, int64_t ldw,
                                const float* row_scale, const float* bias, int64_t M, int K, int N, int act, int head, void* Y,
                                int64_t ldy, int out_f16, const int32_t* row_map, void* stream) {
-  FG_REQUIRE(A && W_hi && W_lo && Y && M >= 0 && K > 0 && N > 0, FITGNN_EINVAL, "gemm_f16: bad arguments (M=%lld K=%d N=%d)",
+  FG_REQUIRE(A && W_hi && Y && M >= 0 && K > 0 && N > 0, FITGNN_EINVAL, "gemm_f16: bad arguments (M=%lld K=%d N=%d)",
              (long long)M, K, N);
   FG_REQUIRE(lda >= K && ldw >= K && ldy >= N, FITGNN_EINVAL, "gemm_f16: leading dimension smaller than the extent");
   FG_REQUIRE(act == FITGNN_ACT_NONE || act == FITGNN_ACT_ELU, FITGNN_EINVAL, "gemm_f16: unknown act %d", act);
@@ -219,7 +221,7 @@ extern "C" int fitgnn_gcn_transform_aggregate_f16(int in_f16, const void* A_hi, 
                                                   const void* W_lo, int64_t ldw, const float* bias, int64_t M, int K, int N,
                                                   int act, const uint64_t* agg_desc, const float* dinv, int defer_row_scale,
                                                   void* Y, int64_t ldy, void* stream) {
-  FG_REQUIRE(A_hi && W_hi && W_lo && Y && (!agg_desc || dinv) && M >= 0 && K > 0 && N > 0, FITGNN_EINVAL,
+  FG_REQUIRE(A_hi && W_hi && (W_lo || in_f16) && Y && (!agg_desc || dinv) && M >= 0 && K > 0 && N > 0, FITGNN_EINVAL,
              "gcn_transform_aggregate_f16: bad arguments (M=%lld K=%d N=%d)", (long long)M, K, N);
   FG_REQUIRE(in_f16 ? !A_lo : A_lo != nullptr, FITGNN_EINVAL, "gcn_transform_aggregate_f16: A_lo must match in_f16");
   FG_REQUIRE(lda >= K && ldw >= K && ldy >= N, FITGNN_EINVAL, "gcn_transform_aggregate_f16: leading dimension too small");

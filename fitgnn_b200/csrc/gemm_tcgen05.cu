@@ -84,6 +84,10 @@ struct EpiArgs {
   int a_planes;
   int f16;
   int out_f16;
+  // w_planes = 1 (FITGNN_GEMM_FP16X2 with W_lo = NULL, i.e. "fp16x1"): W is ONE fp16 plane as well — one MMA per k-step, no
+  // W_lo load.  Halves the B bytes an SM has to ingest per k-block, and a pair's half of a 256 x 512 weight block (128 KB)
+  // then fits in shared memory: the W-stationary CTA-pair plan below.
+  int w_planes;
 };
 constexpr int EPI_WARP0 = 2;
 constexpr int ACC_STAGES = 2;
@@ -286,23 +290,24 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
   // cta_group::2 MMAs that read both halves.  Streaming plan only.
   constexpr int B_ROWS = CTA2 ? BLOCK_N / 2 : BLOCK_N;
   constexpr uint32_t B_PLANE_BYTES = (uint32_t)B_ROWS * BLOCK_K * 2;
-  constexpr uint32_t STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;
   constexpr int TMEM_COLS = tmem_cols(ACC_STAGES * BLOCK_N);
   constexpr uint32_t IDESC_BF16 = umma_idesc_bf16(CTA2 ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
   constexpr uint32_t IDESC_F16 = umma_idesc_f16(CTA2 ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
   const uint32_t IDESC = ea.f16 ? IDESC_F16 : IDESC_BF16;
   const bool a_single = ea.a_planes == 1;
+  const bool w_single = ea.w_planes == 1;
   static_assert(!CTA2 || (!GATHER && BLOCK_N % 32 == 0), "CTA pairs: streaming plan, UMMA N multiple of 32 for M=256");
   const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N for M=128");
   static_assert(STAGES >= 2, "need at least two smem stages");
-  static_assert(EW == EPI_WARPS || (EW == EPI_WARPS_WIDE && !GATHER) || (EW == EPI_WARPS_12 && !GATHER && !CTA2 && BLOCK_N == 256),
+  static_assert(EW == EPI_WARPS || (EW == EPI_WARPS_WIDE && !GATHER) || (EW == EPI_WARPS_12 && !GATHER && BLOCK_N == 256),
                 "2, 3 (256-column tile with an fp16-plane output) or 4 epilogue warps per TMEM lane quadrant");
   // one 32 x 32 box per epilogue warp: 4 KB (fp32, or bf16 hi + lo); the 12-warp variant only writes ONE fp16 plane (2 KB)
   constexpr bool HALF_STAGE = BLOCK_N == 256 && (EW == EPI_WARPS_12 || (AGG && EW == EPI_WARPS_WIDE));  // these require out_f16
-  constexpr uint32_t WARP_STAGE = HALF_STAGE ? EPI_BOX_BYTES / 2 : EPI_BOX_BYTES;
-  constexpr uint32_t STAGING_BYTES = EW * WARP_STAGE;
+  // (the CTA-pair instantiation decides at run time: an fp16-plane output leaves 16 KB for one more A stage)
+  const uint32_t WARP_STAGE = (HALF_STAGE || (CTA2 && ea.out_f16)) ? EPI_BOX_BYTES / 2 : EPI_BOX_BYTES;
+  const uint32_t STAGING_BYTES = EW * WARP_STAGE;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B atoms
@@ -310,11 +315,14 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
   // Two smem plans.  Streaming: n_stages x {A_hi, A_lo, W_hi, W_lo}.  W-stationary (small K): the CTA keeps its
   // N-block of the weights resident for the whole kernel (k_blocks x {W_hi, W_lo}) and only A streams, which removes
   // the per-tile weight re-load from L2 that otherwise dominates the SM<->L2 traffic of a small-K transform.
-  const uint32_t w_region_bytes = w_stationary ? (uint32_t)k_blocks * 2u * B_PLANE_BYTES : 0u;
+  // CTA pairs can be W-stationary too (each CTA keeps ITS half of the pair's N-block): the pair's n-block is fixed and it
+  // strides over the m-blocks, so per k-block an SM ingests only its 16 KB of A.
+  const uint32_t b_bytes = (w_single ? 1u : 2u) * B_PLANE_BYTES;  // W share of a k-block: hi (+ lo)
+  const uint32_t w_region_bytes = w_stationary ? (uint32_t)k_blocks * b_bytes : 0u;
   // a single-plane A (fp16) has no lo slot: the stage shrinks by one plane, which buys pipeline depth (the N = 48 head:
   // 5 stages of 16 KB instead of 2 of 32 KB beside its resident weights)
   const uint32_t a_bytes = (a_single ? 1u : 2u) * A_PLANE_BYTES;
-  const uint32_t stage_bytes_rt = w_stationary ? a_bytes : STAGE_BYTES - 2u * A_PLANE_BYTES + a_bytes;
+  const uint32_t stage_bytes_rt = w_stationary ? a_bytes : a_bytes + b_bytes;
   uint8_t* staging = smem + w_region_bytes + (size_t)n_stages * stage_bytes_rt;  // multiples of 1024 throughout
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 2 * ACC_STAGES + 1);
@@ -332,28 +340,48 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
   constexpr int TILE_M = CTA2 ? 2 * BLOCK_M : BLOCK_M;  // rows per tile of the walk (a pair's tile has 256)
   const int64_t m_tiles = (M + TILE_M - 1) / TILE_M;
   const int64_t tiles = m_tiles * n_tiles;
-  // first row THIS CTA owns in tile t
-  auto tile_row0 = [&](int64_t t) { return (t / n_tiles) * TILE_M + (int64_t)cta_rank * BLOCK_M; };
-  // batched product: first W row of the batch tile t belongs to
-  auto w_batch_off = [&](int64_t t) -> int {
-    return ea.m_batch_rows ? (int)(((t / n_tiles) * TILE_M) / ea.m_batch_rows) * ea.w_batch_rows : 0;
-  };
-  // tile walk: streaming = round robin over (m, n) with n fastest; W-stationary = this CTA's n-block is fixed
-  // (blockIdx % n_tiles) and it strides over the m-blocks
+  // Tile walk.  Every role (producer, MMA issuer, epilogue warps) steps through the same sequence of (m-block, n-block)
+  // pairs with a few 32-bit adds per tile.  (The first version derived every tile from a running index with 64-bit
+  // divisions — tile_at(i), t / n_tiles, t % n_tiles, twice per tile for the prefetch of the next tile's row data: ~370
+  // dependent instructions per tile and epilogue warp, a third of the epilogue warps' samples in ncu r2af.)
+  //   streaming, single CTA : tile t = blockIdx, + gridDim, ... with the n-block fastest (t = mb * n_tiles + nt)
+  //   W-stationary          : the CTA's (pair's) n-block is fixed, it strides over the m-blocks
+  //   streaming CTA pairs   : pair p takes m-blocks p, p + n_pairs, ... and ALL n-blocks of a block back to back: the block's
+  //                           A rows are re-read from L2 by the same two SMs a few microseconds later.  (Round-robin over
+  //                           (m, n) gave the two N-tiles of a block to two different pairs at about the same time; ncu r1x
+  //                           counted 7.1 GB of DRAM reads for 5.0 GB of operands.)
+  //   W-stationary pairs    : pair p keeps n-block p % n_tiles and walks the m-blocks p / n_tiles, + n_pairs / n_tiles, ...
+  //                           (the launcher makes n_pairs a multiple of n_tiles); the n_tiles pairs that share an m-block run
+  //                           side by side, so the block's second read is (mostly) an L2 hit.
+  struct Walk { int mb, nt; };
   const int ctas_per_n = (int)gridDim.x / n_tiles;
-  const int64_t t_first = CTA2 ? (int64_t)(blockIdx.x >> 1)
-                               : w_stationary ? (int64_t)(blockIdx.x / n_tiles) * n_tiles + (blockIdx.x % n_tiles) : blockIdx.x;
-  const int64_t t_step = CTA2 ? (int64_t)(gridDim.x >> 1) : w_stationary ? (int64_t)ctas_per_n * n_tiles : gridDim.x;
-  // i-th tile of this CTA's walk (-1 past the end).  CTA pairs walk m-blocks (pair, pair + n_pairs, ...) and take ALL
-  // N-tiles of a block back to back: the block's A rows are re-read from L2 by the same two SMs a few microseconds later.
-  // (Round-robin over (m, n) gave the two N-tiles of a block to two different pairs at about the same time; ncu r1x counted
-  // 7.1 GB of DRAM reads for 5.0 GB of operands.)
-  // (the other instantiations keep the plain arithmetic walk t = t_first, t_first + t_step, ...: CTA2 is a template
-  // parameter, so the selects below fold away)
-  auto tile_at = [&](int64_t i) -> int64_t {
-    const int64_t mb = t_first + (i / n_tiles) * t_step;
-    return mb < m_tiles ? mb * n_tiles + (i % n_tiles) : tiles;
+  Walk w0;
+  int walk_dm, walk_dn, walk_carry;
+  if (CTA2) {
+    const int p = (int)(blockIdx.x >> 1), np = (int)(gridDim.x >> 1);
+    if (w_stationary) { w0 = Walk{p / n_tiles, p % n_tiles}; walk_dm = np / n_tiles; walk_dn = 0; walk_carry = 0; }
+    else { w0 = Walk{p, 0}; walk_dm = 0; walk_dn = 1; walk_carry = np; }
+  } else if (w_stationary) {
+    w0 = Walk{(int)blockIdx.x / n_tiles, (int)blockIdx.x % n_tiles}; walk_dm = ctas_per_n; walk_dn = 0; walk_carry = 0;
+  } else {
+    w0 = Walk{(int)blockIdx.x / n_tiles, (int)blockIdx.x % n_tiles};
+    walk_dm = (int)gridDim.x / n_tiles; walk_dn = (int)gridDim.x % n_tiles; walk_carry = 1;
+  }
+  auto advance = [&](Walk& w) {
+    w.nt += walk_dn;
+    w.mb += walk_dm;
+    if (w.nt >= n_tiles) { w.nt -= n_tiles; w.mb += walk_carry; }
   };
+  auto valid = [&](const Walk& w) { return (int64_t)w.mb < m_tiles; };
+  // first row THIS CTA owns in the tile
+  auto tile_row0 = [&](const Walk& w) { return (int64_t)w.mb * TILE_M + (int64_t)cta_rank * BLOCK_M; };
+  // batched product: first W row of the batch the tile belongs to
+  auto w_batch_off = [&](const Walk& w) -> int {
+    return ea.m_batch_rows ? (int)(((int64_t)w.mb * TILE_M) / ea.m_batch_rows) * ea.w_batch_rows : 0;
+  };
+  // the gather warps (GATHER: single CTA, W-stationary) keep their own arithmetic walk over the running tile index
+  const int64_t t_first = blockIdx.x;
+  const int64_t t_step = (int64_t)ctas_per_n * n_tiles;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < n_stages; ++s) {
@@ -391,22 +419,30 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
     // warp-uniform loop, one elected lane issues (same reason as the MMA issuer below)
     {
       uint32_t stage = 0, phase = 0;
-      if (w_stationary && t_first < tiles) {
-        const int n0 = (int)(t_first % n_tiles) * BLOCK_N;
+      if (w_stationary && valid(w0)) {
+        const int n0 = w0.nt * BLOCK_N;
         if (elect_one()) {
-          mbar_arrive_expect_tx(wfull_bar, w_region_bytes);
-          for (int kb = 0; kb < k_blocks; ++kb) {
-            tma_load_2d(w_base + kb * 2 * B_PLANE_BYTES, &map_w_hi, wfull_bar, kb * BLOCK_K, n0);
-            tma_load_2d(w_base + kb * 2 * B_PLANE_BYTES + B_PLANE_BYTES, &map_w_lo, wfull_bar, kb * BLOCK_K, n0);
+          if (CTA2) {  // both CTAs' halves are counted on the LEADER's barrier (its MMA thread reads both)
+            const uint32_t lbar = mapa_rank(wfull_bar, 0);
+            if (leader) mbar_arrive_expect_tx(wfull_bar, 2 * w_region_bytes);
+            for (int kb = 0; kb < k_blocks; ++kb) {
+              tma_load_2d_pair(w_base + kb * b_bytes, &map_w_hi, lbar, kb * BLOCK_K, n0 + (int)cta_rank * B_ROWS);
+              if (!w_single)
+                tma_load_2d_pair(w_base + kb * b_bytes + B_PLANE_BYTES, &map_w_lo, lbar, kb * BLOCK_K, n0 + (int)cta_rank * B_ROWS);
+            }
+          } else {
+            mbar_arrive_expect_tx(wfull_bar, w_region_bytes);
+            for (int kb = 0; kb < k_blocks; ++kb) {
+              tma_load_2d(w_base + kb * b_bytes, &map_w_hi, wfull_bar, kb * BLOCK_K, n0);
+              if (!w_single) tma_load_2d(w_base + kb * b_bytes + B_PLANE_BYTES, &map_w_lo, wfull_bar, kb * BLOCK_K, n0);
+            }
           }
         }
         __syncwarp();
       }
-      int64_t wi = 0;
-      for (int64_t t = CTA2 ? tile_at(0) : t_first; t < tiles && !GATHER;
-           t = CTA2 ? tile_at(++wi) : t + t_step) {  // gather mode: A is produced by the gather warps
-        const int m0 = (int)tile_row0(t);
-        const int n0 = (int)(t % n_tiles) * BLOCK_N + w_batch_off(t);  // W row of this tile (epilogue columns: t % n_tiles)
+      for (Walk w = w0; valid(w) && !GATHER; advance(w)) {  // gather mode: A is produced by the gather warps
+        const int m0 = (int)tile_row0(w);
+        const int n0 = w.nt * BLOCK_N + w_batch_off(w);  // W row of this tile (epilogue columns: nt * BLOCK_N)
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t dst = smem_base + stage * stage_bytes_rt;
@@ -419,15 +455,18 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
               if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * tx_bytes);
               tma_load_2d_pair(dst, &map_a_hi, lbar, kb * BLOCK_K, m0);
               if (!a_single) tma_load_2d_pair(dst + A_PLANE_BYTES, &map_a_lo, lbar, kb * BLOCK_K, m0);
-              tma_load_2d_pair(dst + a_bytes, &map_w_hi, lbar, kb * BLOCK_K, n0 + (int)cta_rank * B_ROWS);
-              tma_load_2d_pair(dst + a_bytes + B_PLANE_BYTES, &map_w_lo, lbar, kb * BLOCK_K, n0 + (int)cta_rank * B_ROWS);
+              if (!w_stationary) {
+                tma_load_2d_pair(dst + a_bytes, &map_w_hi, lbar, kb * BLOCK_K, n0 + (int)cta_rank * B_ROWS);
+                if (!w_single)
+                  tma_load_2d_pair(dst + a_bytes + B_PLANE_BYTES, &map_w_lo, lbar, kb * BLOCK_K, n0 + (int)cta_rank * B_ROWS);
+              }
             } else {
               mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
               tma_load_2d(dst, &map_a_hi, full_bar(stage), kb * BLOCK_K, m0);
               if (!a_single) tma_load_2d(dst + A_PLANE_BYTES, &map_a_lo, full_bar(stage), kb * BLOCK_K, m0);
               if (!w_stationary) {
                 tma_load_2d(dst + a_bytes, &map_w_hi, full_bar(stage), kb * BLOCK_K, n0);
-                tma_load_2d(dst + a_bytes + B_PLANE_BYTES, &map_w_lo, full_bar(stage), kb * BLOCK_K, n0);
+                if (!w_single) tma_load_2d(dst + a_bytes + B_PLANE_BYTES, &map_w_lo, full_bar(stage), kb * BLOCK_K, n0);
               }
             }
           }
@@ -445,11 +484,11 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
     // level with the 8 MMAs of a pair's fp16 k-block.
     if (leader) {
       uint32_t stage = 0, phase = 0;
-      int64_t it = 0;
-      if (w_stationary && t_first < tiles) mbar_wait(wfull_bar, 0);  // resident weights have landed
-      for (int64_t t = CTA2 ? tile_at(0) : t_first; t < tiles; ++it, t = CTA2 ? tile_at(it) : t + t_step) {
-        const uint32_t acc = (uint32_t)(it % ACC_STAGES);
-        const uint32_t acc_phase = (uint32_t)((it / ACC_STAGES) & 1);
+      uint32_t it = 0;
+      if (w_stationary && valid(w0)) mbar_wait(wfull_bar, 0);  // resident weights have landed
+      for (Walk w = w0; valid(w); ++it, advance(w)) {
+        const uint32_t acc = it % ACC_STAGES;
+        const uint32_t acc_phase = (it / ACC_STAGES) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
         fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
@@ -457,7 +496,7 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
           mbar_wait(full_bar(stage), phase);  // TMA bytes have landed
           fence_after();
           const uint32_t a_hi = smem_base + stage * stage_bytes_rt;
-          const uint32_t w_hi = w_stationary ? w_base + kb * 2 * B_PLANE_BYTES : a_hi + a_bytes;
+          const uint32_t w_hi = w_stationary ? w_base + kb * b_bytes : a_hi + a_bytes;
           const uint64_t d_a_hi = umma_desc_sw128(a_hi);
           const uint64_t d_a_lo = umma_desc_sw128(a_hi + A_PLANE_BYTES);
           const uint64_t d_w_hi = umma_desc_sw128(w_hi);
@@ -470,11 +509,11 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
               if (CTA2) {
                 umma_bf16_pair(tmem_d, d_a_hi + adv, d_w_hi + adv, IDESC, (kb | k) != 0);
                 if (!a_single) umma_bf16_pair(tmem_d, d_a_lo + adv, d_w_hi + adv, IDESC, 1);
-                umma_bf16_pair(tmem_d, d_a_hi + adv, d_w_lo + adv, IDESC, 1);
+                if (!w_single) umma_bf16_pair(tmem_d, d_a_hi + adv, d_w_lo + adv, IDESC, 1);
               } else {
                 umma_bf16(tmem_d, d_a_hi + adv, d_w_hi + adv, IDESC, (kb | k) != 0);
                 if (!a_single) umma_bf16(tmem_d, d_a_lo + adv, d_w_hi + adv, IDESC, 1);
-                umma_bf16(tmem_d, d_a_hi + adv, d_w_lo + adv, IDESC, 1);
+                if (!w_single) umma_bf16(tmem_d, d_a_hi + adv, d_w_lo + adv, IDESC, 1);
               }
             }
             if (CTA2) {
@@ -630,16 +669,16 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
     const bool one_group = head != FITGNN_HEAD_IDENTITY && !FAST_HEAD;
     const int box_beg = one_group ? (col_group == 0 ? 0 : N_BOXES) : min(N_BOXES, col_group * BOXES_PER_GROUP);
     const int box_end = one_group ? N_BOXES : min(N_BOXES, box_beg + BOXES_PER_GROUP);
-    int64_t it = 0;
+    uint32_t it = 0;
     // aggregation descriptor + dinv of this thread's row, fetched one tile ahead of its use
     unsigned long long desc_next = 0ull;
     float dr_next = 0.f, rs_next = 1.f;
-    auto load_agg = [&](int64_t t) {
+    auto load_agg = [&](const Walk& wt) {
       desc_next = 0ull;
       dr_next = 0.f;
       rs_next = 1.f;
-      if ((AGG || ea.row_scale) && t < tiles) {
-        const int64_t mm = tile_row0(t) + row_in_tile;
+      if ((AGG || ea.row_scale) && valid(wt)) {
+        const int64_t mm = tile_row0(wt) + row_in_tile;
         if (mm < M) {
           if (AGG) {
             desc_next = __ldg(ea.agg_desc + mm);
@@ -649,16 +688,19 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
         }
       }
     };
-    load_agg(CTA2 ? tile_at(0) : t_first);
-    for (int64_t t = CTA2 ? tile_at(0) : t_first; t < tiles; ++it, t = CTA2 ? tile_at(it) : t + t_step) {
-      const uint32_t acc = (uint32_t)(it % ACC_STAGES);
-      const uint32_t acc_phase = (uint32_t)((it / ACC_STAGES) & 1);
-      const int64_t m = tile_row0(t) + row_in_tile;
-      const int n0 = (int)(t % n_tiles) * BLOCK_N;
+    load_agg(w0);
+    Walk w_next = w0;
+    for (Walk w = w0; valid(w); ++it, w = w_next) {
+      const uint32_t acc = it % ACC_STAGES;
+      const uint32_t acc_phase = (it / ACC_STAGES) & 1u;
+      const int64_t tile_m0 = tile_row0(w);
+      const int64_t m = tile_m0 + row_in_tile;
+      const int n0 = w.nt * BLOCK_N;
       const unsigned long long desc = desc_next;
       const float dr = dr_next;
       const float rs = rs_next;
-      load_agg(CTA2 ? tile_at(it + 1) : t + t_step);
+      advance(w_next);
+      load_agg(w_next);
       const int agg_cnt = (int)(desc & 15ull);
       const int agg_max = AGG ? __reduce_max_sync(0xffffffffu, agg_cnt) : 0;
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -755,7 +797,7 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
         inv_sum = 1.f / row_sum;
       }
       const uint32_t buf = smem_u32(staging) + (uint32_t)(warp - EPI_WARP0) * WARP_STAGE;
-      const int m_base = (int)tile_row0(t) + quad * 32;
+      const int m_base = (int)tile_m0 + quad * 32;
       for (int box = box_beg; box < box_end; ++box) {
         const int c0 = box * 32;
         if (n0 + c0 >= N) break;
@@ -1016,7 +1058,8 @@ static int launch(const GatherArgs& ga, const EpiArgs& ea, const CUtensorMap& a_
   CUtensorMap w_hi, w_lo;
   const int64_t w_rows = ea.m_batch_rows ? ea.w_rows_total : (int64_t)N;
   FG_TRY(make_map(&w_hi, W_hi, w_rows, K, ldw, CTA2 ? BLOCK_N / 2 : BLOCK_N));  // a CTA of a pair stages half of the B tile
-  FG_TRY(make_map(&w_lo, W_lo, w_rows, K, ldw, CTA2 ? BLOCK_N / 2 : BLOCK_N));
+  FG_TRY(make_map(&w_lo, W_lo ? W_lo : W_hi, w_rows, K, ldw, CTA2 ? BLOCK_N / 2 : BLOCK_N));  // unused with a single-plane W
+  const size_t w_planes = ea.w_planes == 1 ? 1 : 2;
   CUtensorMap y_map, y_lo_map;
   int tma_store = ((ldy * 4) % 16 == 0 && ((uintptr_t)Y & 15) == 0) ? 1 : 0;
   y_map = w_hi;  // placeholders when unused
@@ -1040,8 +1083,9 @@ static int launch(const GatherArgs& ga, const EpiArgs& ea, const CUtensorMap& a_
   constexpr size_t SMEM_LIMIT = 227 * 1024;
   // staging + alignment slack + barriers/TMEM slot (256 B) + softmax exchange buffers (2 x 8 warps x 32 x float2)
   constexpr bool HALF_STAGE = BLOCK_N == 256 && (EW == EPI_WARPS_12 || (AGG && EW == EPI_WARPS_WIDE));
-  constexpr size_t FIXED = (size_t)EW * (HALF_STAGE ? EPI_BOX_BYTES / 2 : EPI_BOX_BYTES) + 1024 + 256 +
-                           (BLOCK_N <= 64 ? 2 * EW * 32 * 8 : 0);
+  const bool half_stage = HALF_STAGE || (CTA2 && ea.out_f16);  // must match the kernel's WARP_STAGE
+  const size_t FIXED = (size_t)EW * (half_stage ? EPI_BOX_BYTES / 2 : EPI_BOX_BYTES) + 1024 + 256 +
+                       (BLOCK_N <= 64 ? 2 * EW * 32 * 8 : 0);
   FG_REQUIRE(!HALF_STAGE || ea.out_f16, FITGNN_EINVAL, "gemm: the 12/16-epilogue-warp 256-column tile stages one fp16 plane only");
   constexpr int NTHREADS = 64 + 32 * EW + (GATHER ? 32 * GATHER_WARPS : 0);
   const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
@@ -1049,14 +1093,14 @@ static int launch(const GatherArgs& ga, const EpiArgs& ea, const CUtensorMap& a_
   const int64_t m_tiles = ceil_div(M, BLOCK_M);
   const int64_t tiles = m_tiles * n_tiles;
   const size_t a_bytes = (size_t)(ea.a_planes == 1 ? 1 : 2) * A_PLANE_BYTES;  // stage share of A (one fp16 plane or hi + lo)
-  const size_t stage_b = stage_bytes(BLOCK_N) - 2 * A_PLANE_BYTES + a_bytes;
+  const size_t stage_b = a_bytes + w_planes * BLOCK_N * BLOCK_K * 2;
   int n_stages = (int)((SMEM_LIMIT - FIXED) / stage_b);
   if (n_stages > 8) n_stages = 8;
   int grid = (int)(tiles < sms ? tiles : sms);
   size_t smem = (size_t)n_stages * stage_b + FIXED;
   // W-stationary plan: worth it when the resident weights fit beside >= 2 A stages and every CTA gets several m-blocks
   int w_stationary = 0;
-  const size_t w_bytes = (size_t)k_blocks * 2 * BLOCK_N * BLOCK_K * 2;
+  const size_t w_bytes = (size_t)k_blocks * w_planes * BLOCK_N * BLOCK_K * 2;
   if (!ea.m_batch_rows && w_bytes + 2 * a_bytes + FIXED <= SMEM_LIMIT && sms >= n_tiles && m_tiles >= 4 * (sms / n_tiles)) {
     w_stationary = 1;
     n_stages = (int)((SMEM_LIMIT - FIXED - w_bytes) / a_bytes);
@@ -1086,13 +1130,29 @@ static int launch(const GatherArgs& ga, const EpiArgs& ea, const CUtensorMap& a_
   }
   if (CTA2) {
     // CTA pairs: streaming plan with half-B stages, one cluster of 2 CTAs per 256-row tile, persistent over the SM pairs
-    const size_t STAGE2 = a_bytes + 2 * (size_t)(BLOCK_N / 2) * BLOCK_K * 2;
+    const size_t b_half = w_planes * (size_t)(BLOCK_N / 2) * BLOCK_K * 2;  // this CTA's share of a k-block of W
+    const size_t STAGE2 = a_bytes + b_half;
     w_stationary = 0;
     n_stages = (int)((SMEM_LIMIT - FIXED) / STAGE2);
     if (n_stages > 8) n_stages = 8;
     smem = (size_t)n_stages * STAGE2 + FIXED;
-    const int64_t pair_tiles = ceil_div(M, 2 * BLOCK_M) * n_tiles;
-    const int64_t pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
+    const int64_t m_pair_tiles = ceil_div(M, 2 * BLOCK_M);
+    const int64_t pair_tiles = m_pair_tiles * n_tiles;
+    int64_t pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
+    // W-stationary pairs: every CTA keeps its half of the pair's n-block for all k-blocks (fp16 single-plane W, K = 512:
+    // 128 KB) and only A streams — the streaming pair kernel is bound by the L2 -> SM operand traffic (48 KB per k-block and
+    // SM at the ~8 TB/s the chip's L2 delivers), this plan moves 16 KB.  Needs >= 3 A stages beside the weights and several
+    // m-blocks per pair.  Tuning gemm_pair_ws = 0 forces the streaming plan.
+    const size_t w_res = (size_t)k_blocks * b_half;
+    const int64_t ws_pairs = (pairs / n_tiles) * n_tiles;
+    if (tuning().gemm_pair_ws && !ea.m_batch_rows && w_res + 3 * a_bytes + FIXED <= SMEM_LIMIT && ws_pairs >= n_tiles &&
+        m_pair_tiles >= 4 * (ws_pairs / n_tiles)) {
+      w_stationary = 1;
+      pairs = ws_pairs;
+      n_stages = (int)((SMEM_LIMIT - FIXED - w_res) / a_bytes);
+      if (n_stages > 8) n_stages = 8;
+      smem = w_res + (size_t)n_stages * a_bytes + FIXED;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * pairs));
     cfg.blockDim = dim3(NTHREADS);
@@ -1122,6 +1182,7 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
                 const uint64_t* agg_desc, const float* agg_dinv, const int32_t* row_map, float* const* peers, int n_peers,
                 const float* row_scale, int agg_defer_scale, cudaStream_t st, int64_t m_batch_rows, int w_batch_rows,
                 int64_t w_rows_total, int in_f16, int out_f16) {
+  FG_REQUIRE(W_lo || in_f16, FITGNN_EINVAL, "gemm: a single-plane W (W_lo = NULL) needs the fp16 operand format");
   FG_REQUIRE(!in_f16 || !A_lo, FITGNN_EINVAL, "gemm: FP16X2 takes ONE fp16 A plane (A_lo must be NULL)");
   FG_REQUIRE(in_f16 || A_lo, FITGNN_EINVAL, "gemm: BF16X3 needs the A_lo plane");
   FG_REQUIRE(!out_f16 || (head == FITGNN_HEAD_IDENTITY && !Y_lo && !row_map), FITGNN_EUNSUP,
@@ -1147,7 +1208,8 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
   FG_TRY(tc::make_map(&a_lo, A_lo ? A_lo : A_hi, M, K, lda, tc::BLOCK_M));  // unused with a single-plane A
   const tc::GatherArgs ga{};
   tc::EpiArgs ea{reinterpret_cast<const unsigned long long*>(agg_desc), agg_dinv, row_map, {}, n_peers, 0, row_scale,
-                 agg_defer_scale, m_batch_rows, w_batch_rows, w_rows_total, in_f16 ? 1 : 2, in_f16 ? 1 : 0, out_f16 ? 1 : 0};
+                 agg_defer_scale, m_batch_rows, w_batch_rows, w_rows_total, in_f16 ? 1 : 2, in_f16 ? 1 : 0, out_f16 ? 1 : 0,
+                 W_lo ? 2 : 1};
   for (int p = 0; p < n_peers; ++p) ea.peers[p] = peers[p];
   if (n_peers > 0) Y = peers[0];  // alignment checks / unused fallbacks refer to a real buffer
   if (row_map && N <= 64 && ldy == (N + 3) / 4 * 4 && tuning().head_bulk) {
@@ -1189,6 +1251,11 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
     return tc::launch<128, false, false, tc::EPI_WARPS_WIDE>(ga, ea, a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y,
                                                              Y_lo, ldy, sms, st);
   // large-K wide transforms: CTA pairs (cta_group::2) halve the B bytes every SM has to ingest
+  // (fp16-plane output: 12 epilogue warps — with ONE MMA per product the 8-warp epilogue, two latency-bound warps per
+  // scheduler at IPC 0.37, was the bound of the pair kernel: ncu r2af, tensor pipe 36 % active; gemm_wide = -1 forbids it)
+  if (K > 128 && head == FITGNN_HEAD_IDENTITY && !row_map && M >= 4096 && tuning().gemm_pair && out_f16 && tuning().gemm_wide >= 0)
+    return tc::launch<256, false, false, tc::EPI_WARPS_12, true>(ga, ea, a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y,
+                                                                 Y_lo, ldy, sms, st);
   if (K > 128 && head == FITGNN_HEAD_IDENTITY && !row_map && M >= 4096 && tuning().gemm_pair)
     return tc::launch<256, false, false, tc::EPI_WARPS, true>(ga, ea, a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y,
                                                               Y_lo, ldy, sms, st);
@@ -1211,7 +1278,7 @@ int gcn_layer_fused(const int32_t* rowptr, const int32_t* col, const float* dinv
   tc::GatherArgs ga{rowptr, col, dinv, X, src_index, out_rows, ldx, width / 4};
   CUtensorMap dummy;
   FG_TRY(tc::make_map(&dummy, W_hi, N, K, ldw, 16));  // placeholder for the unused A maps
-  const tc::EpiArgs ea{nullptr, nullptr, nullptr, {}, 0, 0, nullptr, 0, 0, 0, 0, 2, 0, 0};
+  const tc::EpiArgs ea{nullptr, nullptr, nullptr, {}, 0, 0, nullptr, 0, 0, 0, 0, 2, 0, 0, 2};
   return tc::launch<256, true, false>(ga, ea, dummy, dummy, W_hi, W_lo, ldw, bias, M, K, N, act, FITGNN_HEAD_IDENTITY, Y,
                                       Y_lo, ldy, sms, st);
 }

@@ -40,14 +40,18 @@ class PackedForward:
         ~2^-17 relative operand error) or 'fp32' (exact-fp32 CUDA-core GEMM: the numerics anchor, explicit opt-in).
         out_map (int32 [n_out]): output row i is written to row out_map[i] of the `out` tensor passed to __call__
         (which then is required) — how StreamedForward lets several forwards fill one result in subgraph_list order."""
-        if precision not in ("bf16x3", "fp32", "fp16x2"):
+        if precision not in ("bf16x3", "fp32", "fp16x2", "fp16"):
             raise ValueError(f"precision={precision!r}")
         self.pack = pack
         dev = pack.device
         # 'fp16x2' (opt-in): bf16x3 for the first layer, then the HIDDEN STATE travels as one fp16 plane (half the bytes, two MMAs
         # per product instead of three; 2^-11 per element — include/fitgnn.h FITGNN_GEMM_FP16X2).  Fused schedule only: a pack
         # that is not eligible for it runs plain bf16x3.
-        self.f16_hidden = precision == "fp16x2"
+        # 'fp16' (opt-in): fp16x2 whose hidden -> hidden transforms (layers >= 1) take their weights as ONE fp16 plane as well:
+        # one MMA per product, and a CTA pair's half of the 256 x 512 weight block stays resident in shared memory (the
+        # W-stationary pair plan of gemm_tcgen05.cu).  The head keeps its hi/lo weights (it is HBM-bound; they are free).
+        self.f16_hidden = precision in ("fp16x2", "fp16")
+        self.w_single = precision == "fp16"
         self.precision = ops.GEMM_FP32 if precision == "fp32" else ops.GEMM_BF16X3
         self.kalign = 8 if self.precision == ops.GEMM_BF16X3 else 4
         self.L = conv_layers(state_dict)
@@ -136,7 +140,8 @@ class PackedForward:
             self.f16_hidden = False
         if self.f16_hidden:  # layers >= 1 and the head take fp16 hi/lo weights (the first layer's A operand stays bf16 hi/lo)
             for i in range(1, self.L):
-                self.W[i] = ops.split_f16(state_dict[f"conv.{i}.lin.weight"].detach().to(**f32).contiguous(), ldo=self._kpad(self.H))
+                self.W[i] = ops.split_f16(state_dict[f"conv.{i}.lin.weight"].detach().to(**f32).contiguous(), ldo=self._kpad(self.H),
+                                          lo=not self.w_single)
             self.Wl = ops.split_f16(state_dict["lt1.weight"].detach().to(**f32).contiguous(), ldo=self._kpad(self.H))
         self.out_map = None
         if out_map is not None:

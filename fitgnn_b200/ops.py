@@ -521,7 +521,8 @@ def split_f16(X, cols=None, ldo=None, lo=True):
 
 def gemm_f16(A, W, bias=None, act=ACT_NONE, head=HEAD_IDENTITY, row_scale=None, out_f16=False, row_map=None, out=None,
              K=None, N=None):
-    """head(act(row_scale * (A·W^T) + bias)) with A ONE fp16 plane [M, K] and W = fp16 (hi, lo) planes (FITGNN_GEMM_FP16X2).
+    """head(act(row_scale * (A·W^T) + bias)) with A ONE fp16 plane [M, K] and W = fp16 (hi, lo) planes (FITGNN_GEMM_FP16X2);
+    W = (hi, None): ONE fp16 weight plane, one MMA per product.
     out_f16: the result as one fp16 plane (the next product's A); row_map: rows scattered into `out` (fp32, required then)."""
     w_hi, w_lo = W
     assert A.dtype == torch.float16 and w_hi.dtype == torch.float16

@@ -40,7 +40,7 @@ class StreamedForward:
             base = self.n_out
             self.n_out += pack.n_core
             split = None
-            if hybrid and precision in ("bf16x3", "fp16x2") and pack.n_core == pack.n_rows and pack.n_sub > 1:
+            if hybrid and precision in ("bf16x3", "fp16x2", "fp16") and pack.n_core == pack.n_rows and pack.n_sub > 1:
                 # fused-schedule candidates: subgraphs of <= 32 rows whose rows have <= 12 neighbours (the epilogue's
                 # aggregation descriptor, align.cu); one oversized subgraph or one high-degree row no longer drops the rest
                 sizes = (pack.sub_ptr[1:] - pack.sub_ptr[:-1]).long()

@@ -287,7 +287,12 @@ int fitgnn_gemm_rowscale_bias_act_split(int precision, const void* A, const void
  *   fitgnn_spmm_symnorm_f16: fitgnn_spmm_symnorm_hub / _devhub on ONE fp16 plane in and out (ldx / ldy in elements, fp32
  *     sums): the later layers' aggregation of the classic schedule, half the gathered bytes.  hub_count (device) may be
  *     NULL: hub_cap is then the host-known number of hub rows (0 = none).
- *   fitgnn_split_f16: fp32 -> fp16 hi/lo planes (lo may be NULL: the hi plane only); values beyond +-65504 saturate. */
+ *   fitgnn_split_f16: fp32 -> fp16 hi/lo planes (lo may be NULL: the hi plane only); values beyond +-65504 saturate.
+ * W_lo = NULL in fitgnn_gemm_f16 / fitgnn_gcn_transform_aggregate_f16 (in_f16 = 1) selects ONE fp16 weight plane as well
+ * (PackedForward(precision="fp16") for the hidden -> hidden transforms): one MMA per k-step, 2^-11 per element on both
+ * operands (measured end to end: 1.8e-5 of the largest logit against 1.6e-5 with hi/lo weights, profiles/r2_precision_study.md),
+ * and for K <= 512 the CTA-pair kernel keeps each CTA's half of the 256-row weight block resident in shared memory
+ * (W-stationary pairs: only A streams; tuning switch gemm_pair_ws = 0 restores the streaming plan). */
 int fitgnn_split_f16(const float* X, int64_t ldx, int64_t rows, int cols, void* hi, void* lo, int64_t ldo, void* stream);
 int fitgnn_gemm_f16(const void* A, int64_t lda, const void* W_hi, const void* W_lo, int64_t ldw,
                     const float* row_scale, const float* bias, int64_t M, int K, int N, int act, int head,

@@ -1,0 +1,12 @@
+# 12 epilogue warps in the CTA-pair kernel (fp16-plane output): parity, micro-benchmark, full step with ws on / off
+timeout 900 python -m pytest tests/test_gpu_stream.py tests/test_gpu_gemm_tc.py -m gpu -x -q -k "fp16 or f16 or gemm" 2>&1 | tail -3
+timeout 300 python scripts/bench_gemm1_f16.py 2>&1 | tail -9
+for ws in 1 0; do
+FITGNN_GEMM_PAIR_WS=$ws timeout 900 python bench.py --steps 10 --warmup 3 --modes= --no-cpu-baseline --no-projection > gpurun_out/bench_r2ag_ws$ws.log 2> gpurun_out/bench_r2ag.err; tail -3 gpurun_out/bench_r2ag.err
+python - <<PY
+import json
+l = json.loads(open("gpurun_out/bench_r2ag_ws$ws.log").read().strip().splitlines()[-1])
+print("ws=$ws", l["ms_per_step"], l["value"], l["clocks"])
+for k, v in l["kernels"].items(): print(k, round(v["ms"], 3), round(v["GBps"]), round(v["TFLOPs"], 1))
+PY
+done

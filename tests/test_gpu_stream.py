@@ -483,6 +483,67 @@ def test_fp16_hidden_state_schedule_matches_oracle(fg):
     assert not fg.PackedForward(pack, sd1, precision="fp16x2", fuse_aggregate=False).f16_hidden
 
 
+@pytest.mark.parametrize("M,K,N", [(1000, 512, 512), (5000, 512, 512), (4224, 192, 384), (100003, 512, 512), (70001, 320, 512),
+                                   (50000, 512, 47)])
+def test_gemm_fp16_single_weight_plane_matches_fp64_of_the_rounded_operands(fg, M, K, N):
+    """W_lo = NULL (precision='fp16'): A and W are ONE fp16 plane each, one MMA per k-step.  The product of the ROUNDED operands
+    must come out to fp32 accuracy on every plan the shapes select: single-CTA streaming (M < 4096), streaming CTA pairs (too
+    few row blocks for resident weights), W-stationary CTA pairs (M >= 148 * 256; K = 512 and K = 320), the narrow head; and the
+    W-stationary pair plan must be bit-identical to the streaming one."""
+    g = torch.Generator().manual_seed(M + N + 1)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g) * 0.1
+    rs = torch.rand(M, generator=g) + 0.5
+    a16, _ = fg.ops.split_f16(A.to(dev()), lo=False)
+    w16, none = fg.ops.split_f16(W.to(dev()), lo=False)
+    assert none is None
+    rows = torch.cat([torch.arange(700), torch.arange(M - 700, M)]) if M > 1400 else torch.arange(M)
+    want = torch.nn.functional.elu(rs.double()[rows, None] * (a16[rows].cpu().double() @ w16.cpu().double().T) + b.double())
+    got = fg.ops.gemm_f16(a16, (w16, None), b.to(dev()), fg.ops.ACT_ELU, row_scale=rs.to(dev()))
+    assert got.dtype == torch.float32
+    assert float((got[rows, :N].cpu().double() - want).abs().max()) <= 2e-5 * float(want.abs().max())
+    # against the two-plane product: the only difference is W's own rounding (2^-11 per element, averaging over K)
+    two = fg.ops.gemm_f16(a16, fg.ops.split_f16(W.to(dev())), b.to(dev()), fg.ops.ACT_ELU, row_scale=rs.to(dev()))
+    assert float((got - two).abs().max()) <= 2e-3 * float(two.abs().max())
+    if N % 8 == 0:
+        got16 = fg.ops.gemm_f16(a16, (w16, None), b.to(dev()), fg.ops.ACT_ELU, row_scale=rs.to(dev()), out_f16=True)
+        assert got16.dtype == torch.float16 and torch.equal(got16, got[:, :N].half())
+        old = fg._lib.set_tuning("gemm_pair_ws", 0)
+        try:
+            stream16 = fg.ops.gemm_f16(a16, (w16, None), b.to(dev()), fg.ops.ACT_ELU, row_scale=rs.to(dev()), out_f16=True)
+            stream32 = fg.ops.gemm_f16(a16, (w16, None), b.to(dev()), fg.ops.ACT_ELU, row_scale=rs.to(dev()))
+        finally:
+            fg._lib.set_tuning("gemm_pair_ws", old)
+        assert torch.equal(stream16, got16) and torch.equal(stream32, got)
+
+
+def test_fp16_single_weight_plane_schedule_matches_oracle(fg):
+    """PackedForward(precision='fp16') on the headline schedule at a size where the layer-2 transform runs as W-stationary CTA
+    pairs (>= 148 * 256 rows): logits against the oracle inside the 1e-3 bound (measured ~2e-5 of max |log-prob|)."""
+    n, F, C = 80000, 100, 47
+    ei, part, cw, k = planted(fg, n, 2000000, seed=5)
+    X = fg.synth.features(n, F, seed=5, device=dev())
+    sd = fg.synth.init_state_dict(F, 512, C, seed=5)
+    pack = fg.build_pack(ei, part, k, "none")
+    f16 = fg.PackedForward(pack, sd, precision="fp16")
+    assert f16.f16_hidden and f16.w_single and f16.apack is not None and f16.W[1][1] is None
+    want = oracle_none(ei, X, part, k, sd, sub_ids=np.arange(min(k, 6000)))
+    got = f16(X).cpu().numpy()
+    assert_close(got[: want.shape[0]], want)
+    assert np.abs(got[: want.shape[0]] - want).max() <= 2e-4 * max(1.0, np.abs(want).max())
+    ref = fg.PackedForward(pack, sd, precision="fp16x2")(X).cpu().numpy()
+    assert np.abs(got - ref).max() <= 2e-4 * np.abs(ref).max()
+    # classic schedule and three layers (the middle fused transform takes a single weight plane too)
+    cl = fg.PackedForward(pack, sd, precision="fp16", fuse_aggregate=False)
+    assert cl.f16_classic
+    assert np.abs(cl(X).cpu().numpy() - ref).max() <= 2e-4 * np.abs(ref).max()
+    sd3 = fg.synth.init_state_dict(F, 256, C, num_layers=3, seed=6)
+    g3 = fg.PackedForward(pack, sd3, precision="fp16")(X).cpu().numpy()
+    r3 = fg.PackedForward(pack, sd3, precision="bf16x3")(X).cpu().numpy()
+    assert np.abs(g3 - r3).max() <= 3e-4 * np.abs(r3).max()
+
+
 @pytest.mark.parametrize("width", [64, 128, 256, 512, 1024])
 def test_spmm_f16_matches_the_fp32_spmm_of_the_same_plane(fg, width):
     """fitgnn_spmm_symnorm_f16 (fp16 plane in, fp32 sums, fp16 plane out) against fitgnn_spmm_symnorm on the same values in
