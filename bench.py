@@ -1021,9 +1021,9 @@ def main_ours(args):
         # MMAs per logical product: bf16x3 = 3 (hi*hi + lo*hi + hi*lo); fp16 hidden state = 2 (A*W_hi + A*W_lo) for every
         # transform whose A operand is the fp16 plane (all but the first)
         mmas = 2 if (f16_hidden and name not in ("gemm0_agg", "gemm0")) else 3
-        if f16_hidden and getattr(fwd, "w_single", False) and name.startswith("gemm") and name not in ("gemm0_agg", "gemm0"):
+        if f16_hidden and getattr(fwd, "w_single", False) and name.startswith(("gemm", "conv")) and name not in ("gemm0_agg", "gemm0"):
             mmas = 1  # precision 'fp16': ONE fp16 weight plane in the hidden -> hidden transforms
-        tensor_bound = (name.startswith("gemm") or name == "head") and precision != "fp32" and \
+        tensor_bound = (name.startswith(("gemm", "conv")) or name == "head") and precision != "fp32" and \
             mmas * r["TFLOPs"] / tc_peak > r["GBps"] / hbm_peak
         if tensor_bound:
             ach = mmas * r["TFLOPs"]
@@ -1046,8 +1046,10 @@ def main_ours(args):
             "vs_baseline": None,
             "dtype": "f32" if precision == "fp32" else dtype_of(fwd), "data": "synthetic",
             "config": config_of(args, n, F, C, k), "roofline": roofline_of(dom), "roofline_spmm": spmm_roof,
-            "schedule": ("spmm0 -> [transform + next layer's aggregation in the epilogue] -> transform -> head (group-aligned "
-                         f"pack, {fwd.apack.n_rows} rows incl. padding)") if fused else "spmm + transform per layer -> head",
+            "schedule": (("spmm0 -> transform -> [GCNConv in one kernel: transform + aggregation on the accumulators + bias + ELU] -> "
+                          "head" if getattr(fwd, "conv_fused", False) else
+                          "spmm0 -> [transform + next layer's aggregation in the epilogue] -> transform -> head") +
+                         f" (group-aligned pack, {fwd.apack.n_rows} rows incl. padding)") if fused else "spmm + transform per layer -> head",
             "kernels": kernels, "gpu_launches": gpu_launches, "clocks": sampler.summary(mark0, mark1),
             "pack": {"rows": pack.n_rows, "nnz": pack.nnz, "subgraphs": pack.n_sub, "build_ms": pack_build_ms, "build_first_call_ms": pack_build_first_ms, "align_ms": align_ms,
                      "bytes": pack.nbytes(), "rank_loads": shard.loads},

@@ -81,6 +81,8 @@ SIGNATURES = {
                                                 c_void, C.POINTER(c_void), c_i32, c_i64, c_void]),
     "fitgnn_gcn_transform_aggregate_f16": (c_i32, [c_i32, c_void, c_void, c_i64, c_void, c_void, c_i64, c_void, c_i64, c_i32,
                                                    c_i32, c_i32, c_void, c_void, c_i32, c_void, c_i64, c_void]),
+    "fitgnn_gcn_conv_aligned_f16": (c_i32, [c_void, c_i64, c_void, c_void, c_i64, c_void, c_i64, c_i32, c_i32, c_i32, c_void, c_void,
+                                            c_void, c_i64, c_void]),
     "fitgnn_gemm_bias_act": (c_i32, [c_i32, c_void, c_void, c_i64, c_void, c_void, c_i64, c_void, c_i64, c_i32, c_i32,
                                      c_i32, c_i32, c_void, c_i64, c_void]),
     "fitgnn_gemm_bias_act_split": (c_i32, [c_i32, c_void, c_void, c_i64, c_void, c_void, c_i64, c_void, c_i64, c_i32,

@@ -35,7 +35,7 @@ static int env_int(const char* name, int dflt) {
 static Tuning& tuning_mut() {
   static Tuning t{env_int("FITGNN_GEMM_WS", 1),   getenv("FITGNN_HEAD_BULK") ? 0 : 1, env_int("FITGNN_AGG_WIDE", 0),
                   env_int("FITGNN_GEMM_WIDE", 0), env_int("FITGNN_GEMM_PAIR", 1), env_int("FITGNN_SM_RESERVE", 0),
-                  env_int("FITGNN_GEMM_PAIR_WS", 1)};
+                  env_int("FITGNN_GEMM_PAIR_WS", 1), env_int("FITGNN_GEMM_PREFETCH", 0)};
   return t;
 }
 const Tuning& tuning() { return tuning_mut(); }
@@ -49,6 +49,7 @@ static int* tuning_field(const char* name) {
   if (!strcmp(name, "gemm_pair")) return &t.gemm_pair;
   if (!strcmp(name, "sm_reserve")) return &t.sm_reserve;
   if (!strcmp(name, "gemm_pair_ws")) return &t.gemm_pair_ws;
+  if (!strcmp(name, "gemm_prefetch")) return &t.gemm_prefetch;
   return nullptr;
 }
 
@@ -59,7 +60,7 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
                 const float* bias, int64_t M, int K, int N, int act, int head, float* Y, void* Y_lo, int64_t ldy,
                 const uint64_t* agg_desc, const float* agg_dinv, const int32_t* row_map, float* const* peers, int n_peers,
                 const float* row_scale, int agg_defer_scale, cudaStream_t st, int64_t m_batch_rows = 0, int w_batch_rows = 0,
-                int64_t w_rows_total = 0, int in_f16 = 0, int out_f16 = 0);
+                int64_t w_rows_total = 0, int in_f16 = 0, int out_f16 = 0, int agg_pre = 0);
 
 int gcn_layer_fused(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X, int64_t ldx, int width,
                     const int32_t* src_index, const int32_t* out_rows, int64_t M, const void* W_hi, const void* W_lo,
@@ -230,6 +231,19 @@ extern "C" int fitgnn_gcn_transform_aggregate_f16(int in_f16, const void* A_hi, 
   return gemm_bf16x3(A_hi, A_lo, lda, W_hi, W_lo, ldw, bias, M, K, N, act, FITGNN_HEAD_IDENTITY, static_cast<float*>(Y), nullptr,
                      ldy, agg_desc, agg_desc ? dinv : nullptr, nullptr, nullptr, 0, nullptr, agg_desc ? defer_row_scale : 0,
                      as_stream(stream), 0, 0, 0, in_f16 ? 1 : 0, 1);
+}
+
+extern "C" int fitgnn_gcn_conv_aligned_f16(const void* A, int64_t lda, const void* W_hi, const void* W_lo, int64_t ldw,
+                                           const float* bias, int64_t M, int K, int N, int act, const uint64_t* agg_desc,
+                                           const float* dinv, void* Y, int64_t ldy, void* stream) {
+  FG_REQUIRE(A && W_hi && Y && agg_desc && dinv && M >= 0 && K > 0 && N > 0, FITGNN_EINVAL,
+             "gcn_conv_aligned_f16: bad arguments (M=%lld K=%d N=%d)", (long long)M, K, N);
+  FG_REQUIRE(lda >= K && ldw >= K && ldy >= N, FITGNN_EINVAL, "gcn_conv_aligned_f16: leading dimension too small");
+  FG_REQUIRE(act == FITGNN_ACT_NONE || act == FITGNN_ACT_ELU, FITGNN_EINVAL, "gcn_conv_aligned_f16: unknown act %d", act);
+  if (M == 0) return FITGNN_OK;
+  // the trailing dinv[r] of the aggregation rides on the bias add (row_scale = dinv, agg_defer_scale = 1)
+  return gemm_bf16x3(A, nullptr, lda, W_hi, W_lo, ldw, bias, M, K, N, act, FITGNN_HEAD_IDENTITY, static_cast<float*>(Y), nullptr,
+                     ldy, agg_desc, dinv, nullptr, nullptr, 0, dinv, 1, as_stream(stream), 0, 0, 0, 1, 1, 1);
 }
 
 extern "C" int fitgnn_gemm_f16_head_rows_peers(const void* A, int64_t lda, const void* W_hi, const void* W_lo, int64_t ldw,

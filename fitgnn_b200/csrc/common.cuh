@@ -67,7 +67,7 @@ static inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>
 // SM count of the current device (queried once per device; grids are sized in multiples of it)
 int sm_count();
 // kernel-tuning switches, read from the environment ONCE per process (FITGNN_GEMM_WS, FITGNN_HEAD_BULK,
-// FITGNN_AGG_WIDE, FITGNN_GEMM_WIDE, FITGNN_GEMM_PAIR, FITGNN_SM_RESERVE, FITGNN_GEMM_PAIR_WS)
+// FITGNN_AGG_WIDE, FITGNN_GEMM_WIDE, FITGNN_GEMM_PAIR, FITGNN_SM_RESERVE, FITGNN_GEMM_PAIR_WS, FITGNN_GEMM_PREFETCH)
 struct Tuning {
   int gemm_ws;    // 0 = force the streaming smem plan (default 1)
   int head_bulk;  // 0 = per-thread stores in row-mapped heads (default 1)
@@ -76,6 +76,7 @@ struct Tuning {
   int gemm_pair;  // 0 = no CTA pairs (default 1)
   int sm_reserve; // SMs the persistent GEMMs leave free for a concurrent exchange kernel (default 0)
   int gemm_pair_ws;  // 0 = CTA pairs never keep their weights resident (default 1: when they fit)
+  int gemm_prefetch; // 1 = L2 prefetch of the next m-block's A rows by the TMA producer (default 0: measured slower, r2aj)
 };
 const Tuning& tuning();
 

@@ -16,6 +16,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <cuda_bf16.h>
+#include <type_traits>
 #include "common.cuh"
 
 namespace fitgnn {
@@ -88,6 +89,7 @@ struct EpiArgs {
   // W_lo load.  Halves the B bytes an SM has to ingest per k-block, and a pair's half of a 256 x 512 weight block (128 KB)
   // then fits in shared memory: the W-stationary CTA-pair plan below.
   int w_planes;
+  int l2_prefetch;  // producer: prefetch the next m-block's A rows into L2 (tuning switch gemm_prefetch, default off)
 };
 constexpr int EPI_WARP0 = 2;
 constexpr int ACC_STAGES = 2;
@@ -133,6 +135,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+
+// pull a tile into L2 only (no shared memory, no barrier): the producer runs these one m-block ahead of its loads
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 
 // smem -> global tile store (clipped at the tensor bounds by the TMA unit), tracked by bulk async-groups
@@ -262,6 +269,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// the same load split into issue and wait, so that independent global loads (the bias) can be issued in between.  The wait
+// takes the 32 registers as in/out operands: nothing that reads them can be scheduled above it.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"
+      "%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -276,7 +304,7 @@ __host__ __device__ constexpr int num_stages(int block_n) {
   return s > 8 ? 8 : s;
 }
 
-template <int BLOCK_N, bool GATHER, bool AGG, int EW, bool CTA2 = false>
+template <int BLOCK_N, bool GATHER, int AGG, int EW, bool CTA2 = false>
 __global__ void __launch_bounds__(64 + 32 * EW + (GATHER ? 32 * GATHER_WARPS : 0), 1)
 gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -440,10 +468,30 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
         }
         __syncwarp();
       }
+      int prev_mb = -1;
       for (Walk w = w0; valid(w) && !GATHER; advance(w)) {  // gather mode: A is produced by the gather warps
         const int m0 = (int)tile_row0(w);
         const int n0 = w.nt * BLOCK_N + w_batch_off(w);  // W row of this tile (epilogue columns: nt * BLOCK_N)
+        // L2 prefetch, one m-block ahead (tuning switch gemm_prefetch, OFF by default): while the first tile of an m-block
+        // streams, the A rows of the NEXT m-block of the walk are pulled into L2, k-block by k-block.  Built because ncu r2ai
+        // showed the MMA warp of a W-stationary pair (4 A stages of 16 KB beside 128 KB of weights) waiting for operands a
+        // third of the time; MEASURED SLOWER (r2aj: layer-2 transform 1.21 -> 1.31 ms, fused transform 1.14 -> 1.16 ms): the
+        // prefetches queue in front of the loads in the SM's one TMA pipe.
+        int pf_m0 = -1;
+        if (w.mb != prev_mb) {
+          Walk pf = w;
+          for (int i = 0; i < n_tiles && valid(pf) && pf.mb == w.mb; ++i) advance(pf);
+          if (valid(pf) && pf.mb != w.mb) pf_m0 = (int)tile_row0(pf);
+        }
+        prev_mb = w.mb;
         for (int kb = 0; kb < k_blocks; ++kb) {
+          if (pf_m0 >= 0 && ea.l2_prefetch) {
+            if (elect_one()) {
+              tma_prefetch_2d(&map_a_hi, kb * BLOCK_K, pf_m0);
+              if (!a_single) tma_prefetch_2d(&map_a_lo, kb * BLOCK_K, pf_m0);
+            }
+            __syncwarp();
+          }
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t dst = smem_base + stage * stage_bytes_rt;
           const uint32_t tx_bytes = stage_bytes_rt;
@@ -482,7 +530,12 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
     // prove uniformity and wraps EVERY tcgen05.mma in an ELECT / R2UR.BROADCAST waterfall: ~260 SASS instructions and
     // ~1,100 cycles per k-block on one thread (ncu r2q) — the bound of the N = 48 head (8 small MMAs per k-block) and
     // level with the 8 MMAs of a pair's fp16 k-block.
-    if (leader) {
+    // The loop is instantiated per operand format (hi/lo or single planes): with the plane counts as run-time predicates the
+    // k-block body carried the descriptor arithmetic of all 12 possible MMAs (~140 uniform-datapath instructions, ~560
+    // cycles per k-block on the one issuing thread — level with the 512 cycles the 4 MMAs of a single-plane k-block execute;
+    // ncu r2ai).
+    auto mma_loop = [&](auto a1_t, auto w1_t) {
+      constexpr bool A1 = decltype(a1_t)::value, W1 = decltype(w1_t)::value;
       uint32_t stage = 0, phase = 0;
       uint32_t it = 0;
       if (w_stationary && valid(w0)) mbar_wait(wfull_bar, 0);  // resident weights have landed
@@ -508,12 +561,12 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
               const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);  // +32 bytes per K=16 step inside the swizzle row
               if (CTA2) {
                 umma_bf16_pair(tmem_d, d_a_hi + adv, d_w_hi + adv, IDESC, (kb | k) != 0);
-                if (!a_single) umma_bf16_pair(tmem_d, d_a_lo + adv, d_w_hi + adv, IDESC, 1);
-                if (!w_single) umma_bf16_pair(tmem_d, d_a_hi + adv, d_w_lo + adv, IDESC, 1);
+                if (!A1) umma_bf16_pair(tmem_d, d_a_lo + adv, d_w_hi + adv, IDESC, 1);
+                if (!W1) umma_bf16_pair(tmem_d, d_a_hi + adv, d_w_lo + adv, IDESC, 1);
               } else {
                 umma_bf16(tmem_d, d_a_hi + adv, d_w_hi + adv, IDESC, (kb | k) != 0);
-                if (!a_single) umma_bf16(tmem_d, d_a_lo + adv, d_w_hi + adv, IDESC, 1);
-                if (!w_single) umma_bf16(tmem_d, d_a_hi + adv, d_w_lo + adv, IDESC, 1);
+                if (!A1) umma_bf16(tmem_d, d_a_lo + adv, d_w_hi + adv, IDESC, 1);
+                if (!W1) umma_bf16(tmem_d, d_a_hi + adv, d_w_lo + adv, IDESC, 1);
               }
             }
             if (CTA2) {
@@ -528,6 +581,11 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
           if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
         }
       }
+    };
+    if (leader) {
+      if (a_single && w_single) mma_loop(std::true_type{}, std::true_type{});
+      else if (a_single) mma_loop(std::true_type{}, std::false_type{});
+      else mma_loop(std::false_type{}, std::false_type{});
     }
     __syncwarp();
   } else if (GATHER && warp >= GATHER_WARP0) {
@@ -803,45 +861,40 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
         if (n0 + c0 >= N) break;
         const int box_cols = (BLOCK_N - c0 >= 32) ? 32 : 16;  // BLOCK_N is a multiple of 16
         float v[32];
+        // full boxes with a 16-byte aligned bias: the bias loads are issued BETWEEN the TMEM load and its wait (they used to
+        // follow the wait, and the first FFMA then sat on the L1 round trip: 14 % of the per-box samples in ncu r2ai)
+        // (not in the register-bound 12/16-warp aggregation epilogues: 32 more live registers spill there)
+        constexpr bool BIAS_PRE = !(AGG && EW != EPI_WARPS);
+        const bool bias_full = bias && bias_vec && n0 + c0 + 32 <= N;
+        const bool bias_pre = BIAS_PRE && bias_full;
+        float4 bq[8];
+        auto bias4 = [&](int j) -> float4 {
+          return BIAS_PRE ? bq[j >> 2] : __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
+        };
         if (box_cols == 32) {
-          tmem_ld32(taddr + c0, v);
+          uint32_t r[32];
+          tmem_ld32_issue(taddr + c0, r);
+          if (bias_pre) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0) + j);
+          }
+          tmem_ld32_wait(r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         } else {
+          if (bias_pre) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0) + j);
+          }
           float lo16[16];
           tmem_ld16(taddr + c0, lo16);
 #pragma unroll
           for (int j = 0; j < 16; ++j) { v[j] = lo16[j]; v[16 + j] = 0.f; }
         }
-        if (ea.row_scale) {  // act(rs * acc + bias): the scale rides on the bias add
-          if (bias && n0 + c0 + 32 <= N && bias_vec) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
-              v[j] = fmaf(v[j], rs, b4.x); v[j + 1] = fmaf(v[j + 1], rs, b4.y);
-              v[j + 2] = fmaf(v[j + 2], rs, b4.z); v[j + 3] = fmaf(v[j + 3], rs, b4.w);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], rs, (bias && n0 + c0 + j < N) ? __ldg(bias + n0 + c0 + j) : 0.f);
-          }
-        } else if (bias) {
-          if (n0 + c0 + 32 <= N && bias_vec) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + c0 + j < N) v[j] += __ldg(bias + n0 + c0 + j);
-          }
-        }
-        if (act == FITGNN_ACT_ELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = elu1(v[j]);
-        }
-        if (AGG) {
-          // next layer's aggregation over the warp's aligned group (see EpiArgs); padding rows (dr = 0) give 0 * h = 0
+        auto aggregate = [&](float (&v)[32]) {
+          // normalised aggregation over the warp's aligned group (see EpiArgs); padding rows (dr = 0) give 0 * h = 0.
+          // AGG == 1: applied to the ACTIVATED tile (the next layer's propagate).  AGG == 2: applied to the raw accumulators,
+          // before bias and activation — act(Â·(A·W^T) + b), a whole GCNConv of the aligned pack in this one kernel.
           // (the A operand's padding rows must hold finite values: the engine's SpMM writes zeros there)
           // AGG_W columns at a time (16 when the register budget is 112 per thread, i.e. 16 epilogue warps)
           constexpr int AGG_W = EW == EPI_WARPS_WIDE ? 16 : 32;
@@ -867,7 +920,38 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
               for (int j = 0; j < AGG_W; ++j) v[h0 + j] *= dr;
             }
           }
+        };
+        if (AGG == 2) aggregate(v);
+        if (ea.row_scale) {  // act(rs * acc + bias): the scale rides on the bias add
+          if (bias_full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = bias4(j);
+              v[j] = fmaf(v[j], rs, b4.x); v[j + 1] = fmaf(v[j + 1], rs, b4.y);
+              v[j + 2] = fmaf(v[j + 2], rs, b4.z); v[j + 3] = fmaf(v[j + 3], rs, b4.w);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], rs, (bias && n0 + c0 + j < N) ? __ldg(bias + n0 + c0 + j) : 0.f);
+          }
+        } else if (bias) {
+          if (bias_full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = bias4(j);
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + c0 + j < N) v[j] += __ldg(bias + n0 + c0 + j);
+          }
         }
+        if (act == FITGNN_ACT_ELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = elu1(v[j]);
+        }
+        if (AGG == 1) aggregate(v);
         if (use_fast_head) {
           float lmax = -INFINITY, lsum = 0.f;
 #pragma unroll
@@ -1051,7 +1135,7 @@ static int make_store_map_bf16(CUtensorMap* map, void* base, int64_t rows, int64
 #ifndef FG_AGG12_DEFAULT
 #define FG_AGG12_DEFAULT 1
 #endif
-template <int BLOCK_N, bool GATHER, bool AGG, int EW = EPI_WARPS, bool CTA2 = false>
+template <int BLOCK_N, bool GATHER, int AGG, int EW = EPI_WARPS, bool CTA2 = false>
 static int launch(const GatherArgs& ga, const EpiArgs& ea, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const void* W_hi, const void* W_lo, int64_t ldw,
                   const float* bias, int64_t M, int K, int N, int act, int head, float* Y, void* Y_lo, int64_t ldy,
                   int sms, cudaStream_t st) {
@@ -1181,7 +1265,8 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
                 const float* bias, int64_t M, int K, int N, int act, int head, float* Y, void* Y_lo, int64_t ldy,
                 const uint64_t* agg_desc, const float* agg_dinv, const int32_t* row_map, float* const* peers, int n_peers,
                 const float* row_scale, int agg_defer_scale, cudaStream_t st, int64_t m_batch_rows, int w_batch_rows,
-                int64_t w_rows_total, int in_f16, int out_f16) {
+                int64_t w_rows_total, int in_f16, int out_f16, int agg_pre) {
+  FG_REQUIRE(!agg_pre || agg_desc, FITGNN_EINVAL, "gemm: agg_pre needs the aggregation descriptors");
   FG_REQUIRE(W_lo || in_f16, FITGNN_EINVAL, "gemm: a single-plane W (W_lo = NULL) needs the fp16 operand format");
   FG_REQUIRE(!in_f16 || !A_lo, FITGNN_EINVAL, "gemm: FP16X2 takes ONE fp16 A plane (A_lo must be NULL)");
   FG_REQUIRE(in_f16 || A_lo, FITGNN_EINVAL, "gemm: BF16X3 needs the A_lo plane");
@@ -1209,13 +1294,22 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
   const tc::GatherArgs ga{};
   tc::EpiArgs ea{reinterpret_cast<const unsigned long long*>(agg_desc), agg_dinv, row_map, {}, n_peers, 0, row_scale,
                  agg_defer_scale, m_batch_rows, w_batch_rows, w_rows_total, in_f16 ? 1 : 2, in_f16 ? 1 : 0, out_f16 ? 1 : 0,
-                 W_lo ? 2 : 1};
+                 W_lo ? 2 : 1, tuning().gemm_prefetch};
   for (int p = 0; p < n_peers; ++p) ea.peers[p] = peers[p];
   if (n_peers > 0) Y = peers[0];  // alignment checks / unused fallbacks refer to a real buffer
   if (row_map && N <= 64 && ldy == (N + 3) / 4 * 4 && tuning().head_bulk) {
     bool aligned = ((uintptr_t)Y & 15) == 0;
     for (int p = 0; p < n_peers; ++p) aligned = aligned && ((uintptr_t)peers[p] & 15) == 0;
     ea.bulk_rows = aligned ? 1 : 0;
+  }
+  if (agg_desc && agg_pre) {
+    // act(Â·(A·W^T) + b): the aggregation runs on the raw accumulators.  Hidden -> hidden layers (K > 128) on the fp16 plane
+    // take the CTA-pair kernel with 12 epilogue warps: the exchange-heavy epilogue then overlaps a tensor-bound main loop
+    // instead of idling the tensor cores behind a K = 100 transform.  Any other shape: the single-CTA 8-warp tile.
+    if (K > 128 && out_f16 && in_f16 && M >= 4096 && tuning().gemm_pair)
+      return tc::launch<256, false, 2, tc::EPI_WARPS_12, true>(ga, ea, a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y,
+                                                               Y_lo, ldy, sms, st);
+    return tc::launch<256, false, 2>(ga, ea, a_hi, a_lo, W_hi, W_lo, ldw, bias, M, K, N, act, head, Y, Y_lo, ldy, sms, st);
   }
   if (agg_desc) {
     // Tuning switch: 128-column tiles with 16 epilogue warps (4 per scheduler).  The small-K aggregation epilogue is
@@ -1278,7 +1372,7 @@ int gcn_layer_fused(const int32_t* rowptr, const int32_t* col, const float* dinv
   tc::GatherArgs ga{rowptr, col, dinv, X, src_index, out_rows, ldx, width / 4};
   CUtensorMap dummy;
   FG_TRY(tc::make_map(&dummy, W_hi, N, K, ldw, 16));  // placeholder for the unused A maps
-  const tc::EpiArgs ea{nullptr, nullptr, nullptr, {}, 0, 0, nullptr, 0, 0, 0, 0, 2, 0, 0, 2};
+  const tc::EpiArgs ea{nullptr, nullptr, nullptr, {}, 0, 0, nullptr, 0, 0, 0, 0, 2, 0, 0, 2, 0};
   return tc::launch<256, true, false>(ga, ea, dummy, dummy, W_hi, W_lo, ldw, bias, M, K, N, act, FITGNN_HEAD_IDENTITY, Y,
                                       Y_lo, ldy, sms, st);
 }

@@ -35,7 +35,7 @@ class PackedForward:
 
     def __init__(self, pack: Pack, state_dict, head="log_softmax", rows="core", precision="bf16x3",
                  with_head=True, fuse_layer0=False, fuse_aggregate="auto", align_policy="degree", out_map=None,
-                 blocked_spmm="auto", dense_spmm="lds"):
+                 blocked_spmm="auto", dense_spmm="lds", conv_fused=False):
         """precision: 'bf16x3' (default: tcgen05 tensor cores on a bf16 hi/lo split of both operands, fp32 accumulate,
         ~2^-17 relative operand error) or 'fp32' (exact-fp32 CUDA-core GEMM: the numerics anchor, explicit opt-in).
         out_map (int32 [n_out]): output row i is written to row out_map[i] of the `out` tensor passed to __call__
@@ -142,7 +142,20 @@ class PackedForward:
             for i in range(1, self.L):
                 self.W[i] = ops.split_f16(state_dict[f"conv.{i}.lin.weight"].detach().to(**f32).contiguous(), ldo=self._kpad(self.H),
                                           lo=not self.w_single)
-            self.Wl = ops.split_f16(state_dict["lt1.weight"].detach().to(**f32).contiguous(), ldo=self._kpad(self.H))
+            # (FITGNN_HEAD_W1=1, A/B: the head's weights as one plane too — 49 KB less resident smem = 3 more A stages)
+            self.Wl = ops.split_f16(state_dict["lt1.weight"].detach().to(**f32).contiguous(), ldo=self._kpad(self.H),
+                                    lo=not (self.w_single and os.environ.get("FITGNN_HEAD_W1", "0") == "1"))
+        # fused schedule on the fp16 plane, second form (conv_fused): spmm0 -> plain first transform -> every later layer as ONE
+        # kernel act(Â·(h·W^T) + b) (ops.gcn_conv_aligned_f16: the aggregation on the raw accumulators in the epilogue of the
+        # tensor-bound hidden -> hidden transform) -> head, instead of hanging layer i+1's aggregation on layer i's transform.
+        # Same launches, same bytes; the exchange-heavy epilogue moves from the K = 100 transform (which it made epilogue-bound
+        # with idle tensor cores) under the K = 512 main loop.  MEASURED SLOWER on the products workload (r2ak: plain transform
+        # 0.85 ms + conv 1.58 ms against 1.16 + 1.19 ms): the exchange epilogue does not hide behind the MMAs, it stretches
+        # them.  Opt-in.
+        import os
+        cf = os.environ.get("FITGNN_CONV_FUSED", "")  # env: A/B runs of bench.py
+        conv_fused = {"0": False, "1": True}.get(cf, conv_fused)
+        self.conv_fused = bool(conv_fused) and self.f16_hidden and self.apack is not None and self.H > 128
         self.out_map = None
         if out_map is not None:
             assert with_head, "out_map needs the head"
@@ -326,6 +339,8 @@ class PackedForward:
         else:
             A = self._spmm(X, Wd, src, None, ops.ACT_NONE, False, split=True, name="spmm0", pack=ap, out=self._planes0)
         K = Wd + 1 if fold else Wd
+        if self.conv_fused:
+            return self._tail_conv_fused(A, K, M, X, out, peer_ptrs)
         for i in range(self.L - 1):
             Ai, Ki = A, K
             Wi, bi = (self.W0_fold, None) if (i == 0 and fold) else (self.W[i], self.b[i])
@@ -378,6 +393,34 @@ class PackedForward:
             view = out[:, : self.C]
         self._timed("head", lambda: ops.gemm_head_rows(h, self.Wl, self.bl, ops.ACT_NONE, self.head, self._head_map, out,
                                                        K=self.H, N=self.C), nbytes=nb, flops=2 * M * self.H * self.C)
+        return out if view is None else view
+
+    def _tail_conv_fused(self, A, K, M, X, out, peer_ptrs):
+        """Rest of the aligned forward in the conv_fused form: plain first transform, then one kernel per later layer."""
+        ap, H = self.apack, self.H
+        fold = self.fold_bias
+        W0, b0 = (self.W0_fold, None) if fold else (self.W[0], self.b[0])
+        self.launches += 1
+        h = self._timed("gemm0", lambda: ops.gcn_transform_aggregate_f16(A, W0, b0, ops.ACT_ELU, None, None, K=K, N=H),
+                        nbytes=4 * M * K + 4 * K * H + 2 * M * H, flops=2 * M * K * H)
+        for i in range(1, self.L):
+            hi_, Wi, bi = h, self.W[i], self.b[i]
+            self.launches += 1
+            h = self._timed(f"conv{i}", lambda: ops.gcn_conv_aligned_f16(hi_, Wi, bi, ops.ACT_ELU, ap.agg_desc, ap.dinv, K=H, N=H),
+                            nbytes=2 * M * H + 4 * H * H + 2 * M * H + 12 * M, flops=2 * M * H * H)
+        self.launches += 1
+        nb16 = 2 * M * H + 4 * H * self.C + 4 * self.n_out * self.C + 4 * M
+        if peer_ptrs is not None:
+            self._timed("head", lambda: ops.gemm_f16_head_rows_peers(h, self.Wl, self.bl, ops.ACT_NONE, self.head, self._head_map,
+                                                                     peer_ptrs, ops.pad4(self.C), K=H, N=self.C),
+                        nbytes=nb16 + 4 * (len(peer_ptrs) - 1) * self.n_out * self.C, flops=2 * M * H * self.C)
+            return None
+        view = None
+        if out is None:
+            out = torch.empty(self.n_out, ops.pad4(self.C), dtype=torch.float32, device=X.device)
+            view = out[:, : self.C]
+        self._timed("head", lambda: ops.gemm_f16(h, self.Wl, self.bl, ops.ACT_NONE, self.head, row_map=self._head_map, out=out,
+                                                 K=H, N=self.C), nbytes=nb16, flops=2 * M * H * self.C)
         return out if view is None else view
 
     # -- forward -------------------------------------------------------------------------------

@@ -566,6 +566,20 @@ def gcn_transform_aggregate_f16(A, W, bias, act, agg_desc, dinv, K=None, N=None,
     return out
 
 
+def gcn_conv_aligned_f16(A, W, bias, act, agg_desc, dinv, K=None, N=None):
+    """act(Â·(A·W^T) + bias) on a group-aligned pack in one kernel (fitgnn_gcn_conv_aligned_f16): A one fp16 plane, W fp16
+    (hi, lo) planes or (hi, None); the result is one fp16 plane."""
+    w_hi, w_lo = W
+    assert A.dtype == torch.float16 and w_hi.dtype == torch.float16
+    M = A.shape[0]
+    K = A.shape[1] if K is None else K
+    N = w_hi.shape[0] if N is None else N
+    out = torch.empty(M, N, dtype=torch.float16, device=A.device)
+    check(lib().fitgnn_gcn_conv_aligned_f16(ptr(A), A.stride(0), ptr(w_hi), ptr(w_lo), w_hi.stride(0), ptr(bias), M, K, N, act,
+                                            ptr(agg_desc), ptr(dinv), ptr(out), out.stride(0), stream_ptr()))
+    return out
+
+
 def segment_pool(X, rows, seg_ptr, pool, width=None):
     """Segment max / mean over the selected rows (fitgnn_segment_pool); differentiable w.r.t. X when X requires grad."""
     if torch.is_grad_enabled() and X.requires_grad:

@@ -301,6 +301,16 @@ int fitgnn_spmm_symnorm_f16(const int32_t* rowptr, const int32_t* col, const flo
                             int width, const int32_t* src_index, const float* bias, int act, const int32_t* out_rows,
                             int64_t n_out, void* Y, int64_t ldy, const int32_t* hub_list, const int32_t* hub_count,
                             int hub_cap, int hub_deg, void* stream);
+/* A whole GCNConv of a group-aligned pack in ONE kernel (network.py:31-32, `x = F.elu(conv(x, edge_index))`, for the layers
+ * after the first; the fp16 hidden state): Y = act(Â·(A·W^T) + bias) with Â the pack's normalised adjacency.  The aggregation
+ * runs in the transform's epilogue on the raw fp32 accumulators (thread = row, a warp = one aligned group, neighbours are
+ * other lanes), then bias and activation; A and Y are fp16 planes [M, lda] / [M, ldy], W fp16 planes (W_lo may be NULL: one
+ * plane).  For K > 128 and M >= 4096 this is the CTA-pair kernel (W-stationary when the weights fit), whose tensor-bound
+ * main loop hides the exchange-heavy epilogue; PackedForward(precision="fp16" / "fp16x2") uses it for every layer after the
+ * first (schedule: spmm0 -> transform -> [conv]* -> head). */
+int fitgnn_gcn_conv_aligned_f16(const void* A, int64_t lda, const void* W_hi, const void* W_lo, int64_t ldw,
+                                const float* bias, int64_t M, int K, int N, int act, const uint64_t* agg_desc,
+                                const float* dinv, void* Y, int64_t ldy, void* stream);
 /* fitgnn_gemm_head_rows_peers with an fp16-plane A operand (FITGNN_GEMM_FP16X2) */
 int fitgnn_gemm_f16_head_rows_peers(const void* A, int64_t lda, const void* W_hi, const void* W_lo, int64_t ldw,
                                     const float* bias, int64_t M, int K, int N, int act, int head,

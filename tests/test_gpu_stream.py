@@ -534,6 +534,16 @@ def test_fp16_single_weight_plane_schedule_matches_oracle(fg):
     assert np.abs(got[: want.shape[0]] - want).max() <= 2e-4 * max(1.0, np.abs(want).max())
     ref = fg.PackedForward(pack, sd, precision="fp16x2")(X).cpu().numpy()
     assert np.abs(got - ref).max() <= 2e-4 * np.abs(ref).max()
+    # the two forms of the fused schedule: every later layer as ONE conv kernel (default when H > 128) / the next layer's
+    # aggregation in the previous transform's epilogue
+    assert f16.conv_fused
+    for prec in ("fp16", "fp16x2"):
+        a = fg.PackedForward(pack, sd, precision=prec, conv_fused=True)
+        b = fg.PackedForward(pack, sd, precision=prec, conv_fused=False)
+        assert a.conv_fused and not b.conv_fused
+        ga, gb = a(X).cpu().numpy(), b(X).cpu().numpy()
+        assert_close(ga[: want.shape[0]], want)
+        assert np.abs(ga - gb).max() <= 2e-4 * np.abs(gb).max()
     # classic schedule and three layers (the middle fused transform takes a single weight plane too)
     cl = fg.PackedForward(pack, sd, precision="fp16", fuse_aggregate=False)
     assert cl.f16_classic
