@@ -1012,7 +1012,8 @@ def main_ours(args):
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath) and world == 1 and args.workload == "products" and args.mode == "none":
         traffic = json.load(open(tpath))
-        traffic = traffic.get("_fp16x2", {}) if getattr(fwd, "f16_hidden", False) else traffic  # per-launch DRAM bytes from the committed ncu capture of this same command
+        if getattr(fwd, "f16_hidden", False):  # per-launch DRAM bytes from the committed ncu capture of this same command
+            traffic = traffic.get("_fp16" if getattr(fwd, "w_single", False) else "_fp16x2", {})
 
     f16_hidden = bool(getattr(fwd, "f16_hidden", False))
 

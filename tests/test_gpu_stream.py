@@ -534,9 +534,9 @@ def test_fp16_single_weight_plane_schedule_matches_oracle(fg):
     assert np.abs(got[: want.shape[0]] - want).max() <= 2e-4 * max(1.0, np.abs(want).max())
     ref = fg.PackedForward(pack, sd, precision="fp16x2")(X).cpu().numpy()
     assert np.abs(got - ref).max() <= 2e-4 * np.abs(ref).max()
-    # the two forms of the fused schedule: every later layer as ONE conv kernel (default when H > 128) / the next layer's
-    # aggregation in the previous transform's epilogue
-    assert f16.conv_fused
+    # the two forms of the fused schedule: the next layer's aggregation in the previous transform's epilogue (default) / every
+    # later layer as ONE conv kernel, aggregation on the raw accumulators (fitgnn_gcn_conv_aligned_f16, opt-in)
+    assert not f16.conv_fused
     for prec in ("fp16", "fp16x2"):
         a = fg.PackedForward(pack, sd, precision=prec, conv_fused=True)
         b = fg.PackedForward(pack, sd, precision=prec, conv_fused=False)
