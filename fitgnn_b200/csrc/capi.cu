@@ -35,7 +35,7 @@ static int env_int(const char* name, int dflt) {
 static Tuning& tuning_mut() {
   static Tuning t{env_int("FITGNN_GEMM_WS", 1),   getenv("FITGNN_HEAD_BULK") ? 0 : 1, env_int("FITGNN_AGG_WIDE", 0),
                   env_int("FITGNN_GEMM_WIDE", 0), env_int("FITGNN_GEMM_PAIR", 1), env_int("FITGNN_SM_RESERVE", 0),
-                  env_int("FITGNN_GEMM_PAIR_WS", 1), env_int("FITGNN_GEMM_PREFETCH", 0)};
+                  env_int("FITGNN_GEMM_PAIR_WS", 1), 0, env_int("FITGNN_GEMM_PREFETCH", 0)};
   return t;
 }
 const Tuning& tuning() { return tuning_mut(); }
@@ -50,6 +50,7 @@ static int* tuning_field(const char* name) {
   if (!strcmp(name, "sm_reserve")) return &t.sm_reserve;
   if (!strcmp(name, "gemm_pair_ws")) return &t.gemm_pair_ws;
   if (!strcmp(name, "gemm_prefetch")) return &t.gemm_prefetch;
+  if (!strcmp(name, "gemm_debug")) return &t.gemm_debug;
   return nullptr;
 }
 

@@ -76,6 +76,7 @@ struct Tuning {
   int gemm_pair;  // 0 = no CTA pairs (default 1)
   int sm_reserve; // SMs the persistent GEMMs leave free for a concurrent exchange kernel (default 0)
   int gemm_pair_ws;  // 0 = CTA pairs never keep their weights resident (default 1: when they fit)
+  int gemm_debug;    // measurement switches, never set in production: bit 0 = GEMM epilogues skip their TMA stores
   int gemm_prefetch; // 1 = L2 prefetch of the next m-block's A rows by the TMA producer (default 0: measured slower, r2aj)
 };
 const Tuning& tuning();

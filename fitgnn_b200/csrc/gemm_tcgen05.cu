@@ -90,6 +90,7 @@ struct EpiArgs {
   // then fits in shared memory: the W-stationary CTA-pair plan below.
   int w_planes;
   int l2_prefetch;  // producer: prefetch the next m-block's A rows into L2 (tuning switch gemm_prefetch, default off)
+  int debug;        // measurement switches (tuning gemm_debug, default 0): bit 0 = the epilogue skips its TMA stores
 };
 constexpr int EPI_WARP0 = 2;
 constexpr int ACC_STAGES = 2;
@@ -1012,7 +1013,7 @@ gemm_bf16x3_kernel(const GatherArgs ga, const EpiArgs ea, const __grid_constant_
           }
           fence_proxy_async();
           __syncwarp();
-          if (elect_one()) {
+          if (elect_one() && !(ea.debug & 1)) {  // debug bit 0 (tuning gemm_debug, measurements only): drop the stores
             tma_store_2d(&map_y, buf, n0 + c0, m_base);
             if (tma_store == 2) tma_store_2d(&map_y_lo, buf + EPI_BOX_BYTES / 2, n0 + c0, m_base);
             bulk_commit();
@@ -1294,7 +1295,7 @@ int gemm_bf16x3(const void* A_hi, const void* A_lo, int64_t lda, const void* W_h
   const tc::GatherArgs ga{};
   tc::EpiArgs ea{reinterpret_cast<const unsigned long long*>(agg_desc), agg_dinv, row_map, {}, n_peers, 0, row_scale,
                  agg_defer_scale, m_batch_rows, w_batch_rows, w_rows_total, in_f16 ? 1 : 2, in_f16 ? 1 : 0, out_f16 ? 1 : 0,
-                 W_lo ? 2 : 1, tuning().gemm_prefetch};
+                 W_lo ? 2 : 1, tuning().gemm_prefetch, tuning().gemm_debug};
   for (int p = 0; p < n_peers; ++p) ea.peers[p] = peers[p];
   if (n_peers > 0) Y = peers[0];  // alignment checks / unused fallbacks refer to a real buffer
   if (row_map && N <= 64 && ldy == (N + 3) / 4 * 4 && tuning().head_bulk) {
@@ -1372,7 +1373,7 @@ int gcn_layer_fused(const int32_t* rowptr, const int32_t* col, const float* dinv
   tc::GatherArgs ga{rowptr, col, dinv, X, src_index, out_rows, ldx, width / 4};
   CUtensorMap dummy;
   FG_TRY(tc::make_map(&dummy, W_hi, N, K, ldw, 16));  // placeholder for the unused A maps
-  const tc::EpiArgs ea{nullptr, nullptr, nullptr, {}, 0, 0, nullptr, 0, 0, 0, 0, 2, 0, 0, 2, 0};
+  const tc::EpiArgs ea{nullptr, nullptr, nullptr, {}, 0, 0, nullptr, 0, 0, 0, 0, 2, 0, 0, 2, 0, 0};
   return tc::launch<256, true, false>(ga, ea, dummy, dummy, W_hi, W_lo, ldw, bias, M, K, N, act, FITGNN_HEAD_IDENTITY, Y,
                                       Y_lo, ldy, sms, st);
 }
