@@ -72,6 +72,9 @@ def parse():
                         "auto = p2p at 2 GPUs, push (with as many SMs left free by the GEMM grids) above (measured, "
                         "profiles/r2_multi_gpu.md); the variant not chosen (sharded / gathered) is timed "
                         "after the headline and reported in multi_gpu.sharded / multi_gpu.gathered")
+    p.add_argument("--ce-peers", type=int, default=-1,
+                   help="--collective push: peers (by rank distance) served by the copy engines instead of the push kernel; "
+                        "-1 = measured default (0 up to 4 GPUs)")
     p.add_argument("--push-ctas", type=int, default=-1,
                    help="CTAs of the peer-push kernel (--collective push); -1 = 16 up to 4 GPUs, 24 at 8 (measured)")
     p.add_argument("--sm-reserve", type=int, default=-1,
@@ -624,6 +627,9 @@ def main_ours(args):
     from fitgnn_b200._lib import set_tuning
     if args.push_ctas <= 0:
         args.push_ctas = 16 if world <= 4 else 24
+    if args.ce_peers < 0:
+        args.ce_peers = 0
+    args.ce_peers = min(args.ce_peers, max(0, world - 2))
     uses_push = world > 1 and (args.collective == "push" or (args.collective in ("auto", "none") and world > 2))
     sm_reserve = args.sm_reserve if args.sm_reserve >= 0 else (args.push_ctas if uses_push else 0)
 
@@ -742,7 +748,7 @@ def main_ours(args):
             for c, f in enumerate(fwds):
                 f(Xin, out=shard.slot(pg.tensors[b], c), packed=packed)
             # completes behind the next step; the timed region ends with pg.wait on both buffers
-            pg.exchange_async(b, engine=coll, push_ctas=args.push_ctas)
+            pg.exchange_async(b, engine=coll, push_ctas=args.push_ctas, ce_peers=args.ce_peers if coll == "push" else 0)
             return pg.tensors[b]
         for c, f in enumerate(fwds):
             f(Xin, peer_ptrs=pg.slot_ptrs(b, c), packed=packed)
@@ -1056,6 +1062,7 @@ def main_ours(args):
                      "bytes": pack.nbytes(), "rank_loads": shard.loads},
             "multi_gpu": {"chunks_per_rank": n_chunks, "collective": collective, "sm_reserve": sm_reserve,
                           "push_ctas": args.push_ctas if "push" in (collective, coll_gather) else None,
+                          "ce_peers": args.ce_peers if "push" in (collective, coll_gather) else None,
                           "outputs": ("sharded by rank (independent subgraphs: no exchange on the path); multi_gpu.gathered times "
                                       "the all-gathered variant") if (world > 1 and collective == "none") else
                                      ("all-gathered on every rank every step; multi_gpu.sharded times the same steps with the "

@@ -208,7 +208,7 @@ class PeerGather:
             self._peer_slots[key] = ops.raw_tensor(self.bases[i][r] + off, (cnt, self.C), self._flag.device, owner=self)
         return self._peer_slots[key]
 
-    def exchange_async(self, i: int, engine: str = "ce", push_ctas: int = 16):
+    def exchange_async(self, i: int, engine: str = "ce", push_ctas: int = 16, ce_peers: int = 0):
         """After this rank's head kernels wrote slot (c, rank) of its OWN buffer i on the current stream: push the slots to
         every peer on a side stream, then the barrier, all behind whatever the current stream does next (the following step's
         compute).  `wait(i)` makes the current stream wait for buffer i to be complete on every rank; `acquire(i)` must
@@ -220,7 +220,10 @@ class PeerGather:
         it occupies would hold back one CTA of the persistent 148-CTA GEMM kernels for the whole push (2 GPUs: 3.45-4.70 ms
         against 3.14 ms), so the caller sets the tuning switch `sm_reserve` (= push_ctas) while the push overlaps compute:
         the GEMM grids then leave those SMs free.  Measured (profiles/r2_multi_gpu.md): 8 GPUs 1.28 (ce) -> 0.82 ms per step,
-        4 GPUs 1.61 (p2p) -> 1.27 ms."""
+        4 GPUs 1.61 (p2p) -> 1.27 ms.
+        `ce_peers` > 0 with engine 'push' (hybrid): the peers at rank distance 1..ce_peers are served by the copy engines (one
+        stream each) and only the rest by the push kernel — the two paths have separate limits (copy engines ~300 GB/s, SM egress
+        ~20 GB/s per CTA), so together they come closer to the link rate than either alone."""
         s = self.shard
         cur = torch.cuda.current_stream()
         self._ready[i].record(cur)
@@ -236,10 +239,21 @@ class PeerGather:
                     nbytes = src.numel() * 4
                     if nbytes == 0:
                         continue
-                    dsts = [self._peer_slot(i, r, c).data_ptr() for r in range(s.world) if r != s.rank]
-                    arr = (C.c_void_p * len(dsts))(*[C.c_void_p(d) for d in dsts])
-                    check(lib().fitgnn_peer_push(ops.ptr(src), arr, len(dsts), nbytes, push_ctas,
-                                                 C.c_void_p(ps.cuda_stream)))
+                    # peers in order of rank distance: every rank hands the same distances to the copy engines, so every
+                    # destination receives ce_peers copy-engine streams and world - 1 - ce_peers push streams
+                    order = [(s.rank + d) % s.world for d in range(1, s.world)]
+                    dsts = [self._peer_slot(i, r, c).data_ptr() for r in order[ce_peers:]]
+                    if dsts:
+                        arr = (C.c_void_p * len(dsts))(*[C.c_void_p(d) for d in dsts])
+                        check(lib().fitgnn_peer_push(ops.ptr(src), arr, len(dsts), nbytes, push_ctas,
+                                                     C.c_void_p(ps.cuda_stream)))
+            order = [(s.rank + d) % s.world for d in range(1, s.world)]
+            for k, r in enumerate(order[:ce_peers]):
+                cs = self.pstreams[1 + k]
+                with torch.cuda.stream(cs):
+                    cs.wait_event(self._ready[i])
+                    for c in range(s.n_chunks):
+                        self._peer_slot(i, r, c).copy_(s.slot(self.tensors[i], c), non_blocking=True)
         else:
             # one side stream per peer: a single copy stream reaches ~200 GB/s, several copy engines together ~310 GB/s
             k = 0
