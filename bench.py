@@ -498,6 +498,9 @@ def mode_train(args, fg, device, n, F, C, ei, part, k, X, precision, steps, samp
 def dtype_of(fwd):
     if not getattr(fwd, "f16_hidden", False):
         return "bf16x3(f32 accumulate)"
+    if getattr(fwd, "f16_layer0", False):
+        return ("fp16 planes for every operand of the two wide transforms (aggregated features, hidden state, weights: 1 MMA per "
+                "product), fp16 hidden state x fp16 hi/lo weights (2 MMAs) in the head; f32 accumulate")
     if getattr(fwd, "w_single", False):
         return ("bf16x3 first layer; fp16 hidden state x ONE fp16 weight plane (1 MMA) in the 512 x 512 transforms, x fp16 hi/lo "
                 "weights (2 MMAs) in the head; f32 accumulate")
@@ -1030,6 +1033,8 @@ def main_ours(args):
         mmas = 2 if (f16_hidden and name not in ("gemm0_agg", "gemm0")) else 3
         if f16_hidden and getattr(fwd, "w_single", False) and name.startswith(("gemm", "conv")) and name not in ("gemm0_agg", "gemm0"):
             mmas = 1  # precision 'fp16': ONE fp16 weight plane in the hidden -> hidden transforms
+        if getattr(fwd, "f16_layer0", False) and name in ("gemm0_agg", "gemm0"):
+            mmas = 1  # the first transform on fp16 planes as well
         tensor_bound = (name.startswith(("gemm", "conv")) or name == "head") and precision != "fp32" and \
             mmas * r["TFLOPs"] / tc_peak > r["GBps"] / hbm_peak
         if tensor_bound:

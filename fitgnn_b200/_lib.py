@@ -53,6 +53,8 @@ SIGNATURES = {
                                     c_void, c_void, c_i64, c_void]),
     "fitgnn_spmm_symnorm_grouped": (c_i32, [c_void, c_void, c_void, c_void, c_i64, c_i32, c_void, c_i64, c_i32, c_void,
                                             c_void, c_i64, c_i32, C.c_float, c_void]),
+    "fitgnn_spmm_symnorm_grouped_f16": (c_i32, [c_void, c_void, c_void, c_void, c_i64, c_i32, c_void, c_i64, c_i32, c_void,
+                                                c_i64, c_i32, C.c_float, c_void]),
     "fitgnn_spmm_symnorm_blocked": (c_i32, [c_void, c_void, c_void, c_void, c_i64, c_i32, c_void, c_void, c_i64, c_void,
                                             c_void, c_i32, c_void, c_void, c_i64, c_void]),
     "fitgnn_spmm_symnorm_mma": (c_i32, [c_void, c_void, c_void, c_void, c_i64, c_i32, c_void, c_void, c_i64, c_void,

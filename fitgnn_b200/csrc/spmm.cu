@@ -419,7 +419,8 @@ __device__ __forceinline__ float4 lds128(uint32_t a) {
   return v;
 }
 
-template <bool SPLIT>
+// SPLIT: 0 = fp32 rows out, 1 = bf16 hi/lo planes, 2 = ONE fp16 plane (the layer-1 operand of precision 'fp16')
+template <int SPLIT>
 __global__ void __launch_bounds__(32)
 spmm_group_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ dinv,
                   const float* __restrict__ X, int64_t ldx, int nq, const int32_t* __restrict__ src_index,
@@ -484,7 +485,10 @@ spmm_group_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
       }
       const float4 o = make_float4(acc.x * dr, acc.y * dr, acc.z * dr, acc.w * dr);
       __syncwarp();  // every lane has read column q
-      if (SPLIT) {
+      if (SPLIT == 2) {
+        const uint32_t h0 = pack_f16x2_rn(o.x, o.y), h1 = pack_f16x2_rn(o.z, o.w);  // the row's fp16 quad
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(mine + qo), "r"(h0), "r"(h1) : "memory");
+      } else if (SPLIT == 1) {
         uint4 pk;  // (hi quad, lo quad)
         split_bf16x2(o.x, o.y, pk.x, pk.z);
         split_bf16x2(o.z, o.w, pk.y, pk.w);
@@ -501,7 +505,9 @@ spmm_group_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
       for (int i = 0; i < rows_here; ++i) {
         const float4 v = xs[i * nq + lane];
         const int64_t yo = (R0 + i) * ldy + 4 * lane;
-        if (SPLIT) {
+        if (SPLIT == 2) {
+          *reinterpret_cast<uint2*>(static_cast<__half*>(Y) + yo) = make_uint2(__float_as_uint(v.x), __float_as_uint(v.y));
+        } else if (SPLIT == 1) {
           *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(Y) + yo) =
               make_uint2(__float_as_uint(v.x), __float_as_uint(v.y));
           *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(Ylo) + yo) =
@@ -510,7 +516,10 @@ spmm_group_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
           *reinterpret_cast<float4*>(static_cast<float*>(Y) + yo) = v;
         }
       }
-    } else if (SPLIT && fill_pad && lane == nq) {
+    } else if (SPLIT == 2 && fill_pad && lane == nq) {
+      for (int i = 0; i < rows_here; ++i)
+        *reinterpret_cast<uint2*>(static_cast<__half*>(Y) + (R0 + i) * ldy + 4 * lane) = make_uint2(pad_hi_bits, 0u);
+    } else if (SPLIT == 1 && fill_pad && lane == nq) {
       // the planes' 4 pad columns [width, ldy): written too, so that every 32-byte sector of the planes is fully written
       // (leaving them out costs a DRAM read-modify-write per row and plane: ncu r1u, +157 MB of reads)
       for (int i = 0; i < rows_here; ++i) {
@@ -941,14 +950,43 @@ extern "C" int fitgnn_spmm_symnorm_grouped(const int32_t* rowptr, const int32_t*
   const int do_pad = (fill_pad && Y_lo && ldy == width + 4 && width < 128) ? 1 : 0;
   const uint32_t pad_bits = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(pad_value));
   if (Y_lo) {
-    FG_CUDA(cudaFuncSetAttribute(spmm_group_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    spmm_group_kernel<true><<<blocks, 32, smem, st>>>(rowptr, col, dinv, X, ldx, nq, src_index, n_rows, Y, Y_lo, ldy,
-                                                      n_groups, do_pad, pad_bits);
+    FG_CUDA(cudaFuncSetAttribute(spmm_group_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    spmm_group_kernel<1><<<blocks, 32, smem, st>>>(rowptr, col, dinv, X, ldx, nq, src_index, n_rows, Y, Y_lo, ldy,
+                                                   n_groups, do_pad, pad_bits);
   } else {
-    FG_CUDA(cudaFuncSetAttribute(spmm_group_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    spmm_group_kernel<false><<<blocks, 32, smem, st>>>(rowptr, col, dinv, X, ldx, nq, src_index, n_rows, Y, Y_lo, ldy,
-                                                       n_groups, 0, 0u);
+    FG_CUDA(cudaFuncSetAttribute(spmm_group_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    spmm_group_kernel<0><<<blocks, 32, smem, st>>>(rowptr, col, dinv, X, ldx, nq, src_index, n_rows, Y, Y_lo, ldy,
+                                                   n_groups, 0, 0u);
   }
+  FG_LAUNCH_CHECK();
+  return FITGNN_OK;
+}
+
+// the same aggregation written as ONE fp16 plane [n_rows, ldy] (ldy in elements): the A operand of the first transform when
+// the whole forward runs on fp16 planes (PackedForward(precision="fp16")); fp32 sums, one rounding (saturating) at the end
+extern "C" int fitgnn_spmm_symnorm_grouped_f16(const int32_t* rowptr, const int32_t* col, const float* dinv, const float* X,
+                                               int64_t ldx, int width, const int32_t* src_index, int64_t n_rows, int group,
+                                               void* Y, int64_t ldy, int fill_pad, float pad_value, void* stream) {
+  FG_REQUIRE(rowptr && col && dinv && X && Y, FITGNN_EINVAL, "spmm_grouped_f16: null pointer");
+  FG_REQUIRE(n_rows >= 0 && width > 0, FITGNN_EINVAL, "spmm_grouped_f16: n_rows=%lld width=%d", (long long)n_rows, width);
+  FG_REQUIRE(group == 32, FITGNN_EUNSUP, "spmm_grouped_f16: group must be 32 (got %d)", group);
+  FG_REQUIRE(width % 4 == 0 && width <= 128 && ldx % 4 == 0 && ldy % 4 == 0 && ldy >= width, FITGNN_EUNSUP,
+             "spmm_grouped_f16: width (%d) must be a multiple of 4 and <= 128, ldx (%lld) / ldy (%lld) multiples of 4", width,
+             (long long)ldx, (long long)ldy);
+  FG_REQUIRE(((uintptr_t)X % 16) == 0 && ((uintptr_t)Y % 8) == 0, FITGNN_EUNSUP, "spmm_grouped_f16: X must be 16-byte, Y 8-byte aligned");
+  if (n_rows == 0) return FITGNN_OK;
+  cudaStream_t st = as_stream(stream);
+  const int nq = width / 4;
+  const int64_t n_groups = ceil_div(n_rows, 32);
+  const size_t smem = spmm_group_smem(nq);
+  const int64_t max_blocks = (int64_t)sm_count() * 64;
+  const unsigned blocks = (unsigned)(n_groups < max_blocks ? n_groups : max_blocks);
+  // pad fill (pitch = width + 4 only): Y[:, width] = pad_value, the other three pad elements 0 — whole 8-byte quads
+  const int do_pad = (fill_pad && ldy == width + 4 && width < 128) ? 1 : 0;
+  const uint32_t pad_bits = (uint32_t)__half_as_ushort(__float2half_rn(pad_value));
+  FG_CUDA(cudaFuncSetAttribute(spmm_group_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  spmm_group_kernel<2><<<blocks, 32, smem, st>>>(rowptr, col, dinv, X, ldx, nq, src_index, n_rows, Y, nullptr, ldy, n_groups,
+                                                 do_pad, pad_bits);
   FG_LAUNCH_CHECK();
   return FITGNN_OK;
 }

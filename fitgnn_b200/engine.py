@@ -138,6 +138,20 @@ class PackedForward:
                             and not self.transform_first and with_head and self.H % 8 == 0 and self.H >= 32)
         if self.f16_hidden and self.apack is None and not self.f16_classic:
             self.f16_hidden = False
+        # precision 'fp16' on the fused schedule with the group-local layer-1 aggregation: the FIRST transform runs on fp16 planes
+        # too (aggregated features as one fp16 plane straight out of the aggregation kernel, W0 as one fp16 plane).  Emulated
+        # logit error 1.9e-5 against 1.8e-5 (profiles/r2_precision_study.md: the hidden state's rounding dominates); what it
+        # buys is shared memory — the resident W0 block shrinks from 128 to 64 KB and an A stage from 32 to 16 KB, so the
+        # epilogue-bound fused transform gets 8 operand stages instead of 2 (its main loop alone was load-latency-bound at
+        # 2.6 us per tile with ONE tile in flight) — and half the bytes between the two kernels.
+        self.f16_layer0 = bool(self.f16_hidden and self.w_single and self.apack is not None
+                               and getattr(self, "grouped_spmm", False) and ops.pad4(self.F) <= 128
+                               and os.environ.get("FITGNN_F16_LAYER0", "1") != "0")
+        if self.f16_layer0:
+            w0 = state_dict["conv.0.lin.weight"].detach().to(**f32)
+            if self.fold_bias:
+                w0 = torch.cat([torch.nn.functional.pad(w0, (0, ops.pad4(self.F) - self.F)), self.b[0][:, None]], 1)
+            self.W0_f16 = ops.split_f16(w0.contiguous(), ldo=self._kpad(w0.shape[1]), lo=False)
         if self.f16_hidden:  # layers >= 1 and the head take fp16 hi/lo weights (the first layer's A operand stays bf16 hi/lo)
             for i in range(1, self.L):
                 self.W[i] = ops.split_f16(state_dict[f"conv.{i}.lin.weight"].detach().to(**f32).contiguous(), ldo=self._kpad(self.H),
@@ -320,14 +334,26 @@ class PackedForward:
         # touches columns >= F), so a PackedForward must be driven from one stream at a time.
         Wd = ops.pad4(self.F)  # columns the SpMM reads / writes (X has at least that many: see __call__)
         fold = self.fold_bias
-        if self._planes0 is None or self._planes0[0].device != X.device:
+        src = None if packed else ap.gid
+        if self.f16_layer0:
+            if self._planes0 is None or self._planes0.device != X.device:
+                self._planes0 = torch.zeros(M, self.Fp, dtype=torch.float16, device=X.device)
+                if fold:
+                    self._planes0[:, Wd] = 1.0
+            self.launches += 1
+            b4 = self._spmm_bytes_aligned(Wd, src, X.shape[0])
+            A = self._timed("spmm0", lambda: ops.spmm_symnorm_grouped_f16(ap.rowptr, ap.col, ap.dinv, X, Wd, src, out=self._planes0,
+                                                                          pad_value=(1.0 if fold else 0.0)),
+                            nbytes=b4 - 2 * ap.n_rows * Wd)  # the output is 2 bytes per element
+        elif self._planes0 is None or self._planes0[0].device != X.device:
             hi = torch.zeros(M, self.Fp, dtype=torch.bfloat16, device=X.device)
             lo = torch.zeros(M, self.Fp, dtype=torch.bfloat16, device=X.device)
             if fold:
                 hi[:, Wd] = 1.0
             self._planes0 = (hi, lo)
-        src = None if packed else ap.gid
-        if self.grouped_spmm and Wd <= 128:
+        if self.f16_layer0:
+            pass
+        elif self.grouped_spmm and Wd <= 128:
             # group-local aggregation: the group's 32 source rows are staged in shared memory once (spmm.cu)
             self.launches += 1
             # the pad columns of the planes (constant 1 of the bias fold / zeros) are re-written with the same values:
@@ -344,6 +370,8 @@ class PackedForward:
         for i in range(self.L - 1):
             Ai, Ki = A, K
             Wi, bi = (self.W0_fold, None) if (i == 0 and fold) else (self.W[i], self.b[i])
+            if i == 0 and self.f16_layer0:
+                Wi = self.W0_f16
             # the leading dinv[r] of the aggregation moves into the next transform's epilogue (one FFMA with its bias) when
             # that consumer is the plain last transform
             defer = self.defer_scale and i == self.L - 2
@@ -400,6 +428,8 @@ class PackedForward:
         ap, H = self.apack, self.H
         fold = self.fold_bias
         W0, b0 = (self.W0_fold, None) if fold else (self.W[0], self.b[0])
+        if self.f16_layer0:
+            W0 = self.W0_f16
         self.launches += 1
         h = self._timed("gemm0", lambda: ops.gcn_transform_aggregate_f16(A, W0, b0, ops.ACT_ELU, None, None, K=K, N=H),
                         nbytes=4 * M * K + 4 * K * H + 2 * M * H, flops=2 * M * K * H)

@@ -124,6 +124,21 @@ def spmm_symnorm_grouped(rowptr, col, dinv, X, width=None, src_index=None, out=N
     return out
 
 
+def spmm_symnorm_grouped_f16(rowptr, col, dinv, X, width=None, src_index=None, out=None, pad_value=None):
+    """spmm_symnorm_grouped written as ONE fp16 plane (fitgnn_spmm_symnorm_grouped_f16): fp32 sums, one rounding.  `out`:
+    fp16 [n_rows, ldy]; pad_value (pitch width + 4 only): out[:, width] = pad_value, the other pad elements 0."""
+    assert X.dtype == torch.float32 and X.dim() == 2
+    width = X.shape[1] if width is None else width
+    n = rowptr.numel() - 1
+    if out is None:
+        out = torch.empty(n, width, dtype=torch.float16, device=X.device)
+    assert out.dtype == torch.float16 and out.shape[0] == n
+    check(lib().fitgnn_spmm_symnorm_grouped_f16(ptr(rowptr), ptr(col), ptr(dinv), ptr(X), X.stride(0), width, ptr(src_index), n,
+                                                32, ptr(out), out.stride(0), int(pad_value is not None), float(pad_value or 0.0),
+                                                stream_ptr()))
+    return out
+
+
 def row_blocks(sub_ptr, n_rows, window=64, compact=False):
     """blk_ptr for spmm_symnorm_blocked: block b = the subgraphs whose first row lies in [b*window, (b+1)*window) — unions
     of whole subgraphs, so closed under adjacency; a block has fewer than window + (largest subgraph) rows, empty blocks

@@ -153,6 +153,13 @@ int fitgnn_spmm_symnorm_grouped(const int32_t* rowptr, const int32_t* col, const
                                 int fill_pad, float pad_value, void* stream);
 /* fill_pad != 0 (bf16 planes with ldy == width + 4 only, ignored otherwise): the four pad columns of every row are written
  * as well — hi[:, width] = pad_value, all other pad elements 0 — so that the planes are written in whole 32-byte sectors. */
+/* The same aggregation written as ONE fp16 plane [n_rows, ldy] (ldy in elements; fp32 sums, one saturating rounding): the A
+ * operand of the first transform when the whole forward runs on fp16 planes (PackedForward(precision="fp16")).  fill_pad as
+ * above: Y[:, width] = pad_value, the other three pad elements 0, when ldy == width + 4. */
+int fitgnn_spmm_symnorm_grouped_f16(const int32_t* rowptr, const int32_t* col, const float* dinv,
+                                    const float* X, int64_t ldx, int width, const int32_t* src_index,
+                                    int64_t n_rows, int group, void* Y, int64_t ldy, int fill_pad,
+                                    float pad_value, void* stream);
 /* The same aggregation (every row an output row) with SHARED-MEMORY STAGING of the sources: blk_ptr[n_blk + 1] (device)
  * cuts the pack rows into consecutive blocks that are closed under adjacency (unions of whole subgraphs, e.g. from
  * sub_ptr); a CTA stages a block's source rows (through src_index when given) in shared memory once and all rows of the

@@ -27,7 +27,7 @@ for label, act, desc, dbg in [("ELU + exchange (the forward's call)", ops.ACT_EL
                               ("ELU only (plain transform)", ops.ACT_ELU, None, 0), ("nothing (convert + store)", ops.ACT_NONE, None, 0),
                               ("ELU + exchange, NO TMA stores", ops.ACT_ELU, ap.agg_desc, 1), ("nothing, NO TMA stores", ops.ACT_NONE, None, 1)]:
     set_tuning("gemm_debug", dbg)
-    ms = t(lambda: ops.gcn_transform_aggregate_f16(A, fwd.W0_fold, None, act, desc, ap.dinv if desc is not None else None, K=K, N=H,
+    ms = t(lambda: ops.gcn_transform_aggregate_f16(A, fwd.W0_f16 if fwd.f16_layer0 else fwd.W0_fold, None, act, desc, ap.dinv if desc is not None else None, K=K, N=H,
                                                    defer_row_scale=desc is not None))
     print(f"{label:40s} {ms:.3f} ms", flush=True)
 set_tuning("gemm_debug", 0)

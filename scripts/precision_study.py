@@ -40,13 +40,14 @@ fmt = {
     "bf16x3 (hi+lo bf16, shipped)": lambda x: rnd_bits(x, 7) + rnd_bits(x - rnd_bits(x, 7), 7),
     "fp16 single plane (fp16x2)": lambda x: x.astype(np.float16).astype(np.float64),
     "fp16 single plane, layer-2 W one fp16 plane too (fp16)": lambda x: x.astype(np.float16).astype(np.float64),
+    "fp16 everywhere incl. layer 1 (aggregated X and W0 as fp16 planes)": lambda x: x.astype(np.float16).astype(np.float64),
     "tf32 RN, both operands": lambda x: rnd_bits(x, 10),
     "bf16 single plane": lambda x: rnd_bits(x, 7),
 }
 elu = lambda z: np.where(z > 0, z, np.expm1(np.minimum(z, 0)))
-def forward(r, r_w=lambda w: w, r_w2=None):
-    a1 = Ahat @ X
-    h1 = elu(a1 @ sd["conv.0.lin.weight"].T + sd["conv.0.bias"])
+def forward(r, r_w=lambda w: w, r_w2=None, r_in=lambda x: x):
+    a1 = r_in(Ahat @ X)                                 # operand of the layer-1 transform (emitted by spmm0)
+    h1 = elu(a1 @ r_in(sd["conv.0.lin.weight"]).T + sd["conv.0.bias"])
     a2 = r(Ahat @ h1)                                   # operand of the layer-2 transform (emitted by gemm0_agg)
     h2 = elu(a2 @ (r_w2 or r_w)(sd["conv.1.lin.weight"]).T + sd["conv.1.bias"])
     z = r(h2) @ r_w(sd["lt1.weight"]).T + sd["lt1.bias"]  # operand of the head
@@ -59,7 +60,10 @@ print(f"{'operand format of the hidden state':42s} {'max err / max|ref|':>20s} {
 for name, r in fmt.items():
     rw = (lambda w: rnd_bits(w, 10)) if name.startswith("tf32") else (lambda w: w)
     rw2 = (lambda w: w.astype(np.float16).astype(np.float64)) if "(fp16)" in name else None  # head weights stay hi/lo
-    out = forward(r, rw, rw2)
+    rin = (lambda x: x.astype(np.float16).astype(np.float64)) if "incl. layer 1" in name else (lambda x: x)
+    if "incl. layer 1" in name:
+        rw2 = lambda w: w.astype(np.float16).astype(np.float64)
+    out = forward(r, rw, rw2, rin)
     err = np.abs(out - ref)
     ratio = (err / (1e-3 * np.abs(ref) + 1e-5 * scale)).max()
     print(f"{name:42s} {err.max() / scale:20.3e} {ratio:26.3f}")

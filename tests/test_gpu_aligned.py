@@ -275,3 +275,31 @@ def test_grouped_spmm_fills_the_pad_columns(fg):
             assert bool((hi[:, width] == 1.0).all()) and bool((hi[:, width + 1:] == 0).all()) and bool((lo[:, width:] == 0).all())
         else:
             assert bool((hi[:, width:] == 7.0).all()) and bool((lo[:, width:] == 7.0).all())
+
+
+@pytest.mark.parametrize("packed", [True, False])
+@pytest.mark.parametrize("n,k,seed,max_size,width", [(40, 20, 0, None, 4), (5000, 2300, 1, None, 100), (3000, 400, 2, 13, 128),
+                                                     (33, 33, 4, None, 100), (20000, 9000, 5, 12, 100)])
+def test_grouped_spmm_fp16_plane_is_the_rounded_fp32_result(fg, n, k, seed, max_size, width, packed):
+    """fitgnn_spmm_symnorm_grouped_f16: the same fp32 sums as the fp32 kernel, rounded ONCE to fp16 (the layer-1 operand of
+    precision='fp16'); pad columns written when the pitch is width + 4, left alone otherwise."""
+    ei, part, k = small_subgraph_graph(n, k, seed, max_size=max_size)
+    pack = fg.build_pack(torch.tensor(ei, device=dev()), torch.tensor(part), k, "none")
+    ap = pack.aligned(32, "degree")
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    X = torch.randn(n, width, generator=g, device=dev())
+    src = None if packed else ap.gid
+    Xin = X[ap.gid.long()].contiguous() if packed else X
+    want = fg.ops.spmm_symnorm_grouped(ap.rowptr, ap.col, ap.dinv, Xin, width, src).half()
+    got = fg.ops.spmm_symnorm_grouped_f16(ap.rowptr, ap.col, ap.dinv, Xin, width, src)
+    assert got.dtype == torch.float16 and torch.equal(got, want)
+    for pitch in (width + 4, width + 12):
+        if width >= 128:
+            continue
+        out = torch.full((ap.n_rows, pitch), 7.0, dtype=torch.float16, device=dev())
+        fg.ops.spmm_symnorm_grouped_f16(ap.rowptr, ap.col, ap.dinv, Xin, width, src, out=out, pad_value=1.0)
+        assert torch.equal(out[:, :width], want)
+        if pitch == width + 4:
+            assert bool((out[:, width] == 1.0).all()) and bool((out[:, width + 1:] == 0).all())
+        else:
+            assert bool((out[:, width:] == 7.0).all())

@@ -528,6 +528,7 @@ def test_fp16_single_weight_plane_schedule_matches_oracle(fg):
     pack = fg.build_pack(ei, part, k, "none")
     f16 = fg.PackedForward(pack, sd, precision="fp16")
     assert f16.f16_hidden and f16.w_single and f16.apack is not None and f16.W[1][1] is None
+    assert f16.f16_layer0 and f16.W0_f16[1] is None  # the first transform runs on fp16 planes too
     want = oracle_none(ei, X, part, k, sd, sub_ids=np.arange(min(k, 6000)))
     got = f16(X).cpu().numpy()
     assert_close(got[: want.shape[0]], want)
@@ -544,6 +545,15 @@ def test_fp16_single_weight_plane_schedule_matches_oracle(fg):
         ga, gb = a(X).cpu().numpy(), b(X).cpu().numpy()
         assert_close(ga[: want.shape[0]], want)
         assert np.abs(ga - gb).max() <= 2e-4 * np.abs(gb).max()
+    # layer 1 on bf16 hi/lo planes instead (what fp16x2 does): the difference is the rounding of the aggregated features
+    import os
+    os.environ["FITGNN_F16_LAYER0"] = "0"
+    try:
+        b0 = fg.PackedForward(pack, sd, precision="fp16")
+    finally:
+        del os.environ["FITGNN_F16_LAYER0"]
+    assert not b0.f16_layer0
+    assert np.abs(b0(X).cpu().numpy() - got).max() <= 2e-4 * np.abs(got).max()
     # classic schedule and three layers (the middle fused transform takes a single weight plane too)
     cl = fg.PackedForward(pack, sd, precision="fp16", fuse_aggregate=False)
     assert cl.f16_classic
