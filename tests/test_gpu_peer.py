@@ -99,21 +99,23 @@ def _rank_main(rank, world, port, ret):
         ret[(rank, 10 + step)] = float((got - full).abs().max())
         pgather.release(b)
         dist.barrier()
-    # the fp16-hidden-state schedule stores through the same peer-mapped head (fitgnn_gemm_f16_head_rows_peers)
-    f16 = fg.PackedForward(shard.local, sd, precision="fp16x2", fuse_aggregate=True)
-    assert f16.f16_hidden
-    want16 = fg.PackedForward(pack, sd, precision="fp16x2", fuse_aggregate=True)(X)
-    full16 = torch.empty(n, Cc, device=d)
-    full16[pack.core_gid.long()] = want16
-    pgather.tensors[0].zero_()
-    torch.cuda.synchronize()
-    dist.barrier()
-    f16(X, peer_ptrs=pgather.slot_ptrs(0, 0))
-    torch.cuda.synchronize()
-    dist.barrier()
-    got = pgather.tensors[0].view(-1, Cp)[shard.node_index(d)][:, :Cc]
-    ret[(rank, 20)] = float((got - full16).abs().max())
-    dist.barrier()
+    # the fp16-hidden-state schedules store through the same peer-mapped head (fitgnn_gemm_f16_head_rows_peers): fp16x2, and
+    # 'fp16' (every operand of the wide transforms an fp16 plane: the multi-GPU bench's default arithmetic)
+    for slot, prec in ((20, "fp16x2"), (21, "fp16")):
+        f16 = fg.PackedForward(shard.local, sd, precision=prec, fuse_aggregate=True)
+        assert f16.f16_hidden and f16.f16_layer0 == (prec == "fp16")
+        want16 = fg.PackedForward(pack, sd, precision=prec, fuse_aggregate=True)(X)
+        full16 = torch.empty(n, Cc, device=d)
+        full16[pack.core_gid.long()] = want16
+        pgather.tensors[0].zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
+        f16(X, peer_ptrs=pgather.slot_ptrs(0, 0))
+        torch.cuda.synchronize()
+        dist.barrier()
+        got = pgather.tensors[0].view(-1, Cp)[shard.node_index(d)][:, :Cc]
+        ret[(rank, slot)] = float((got - full16).abs().max())
+        dist.barrier()
     del got
     pgather.tensors = None
     dist.barrier()
@@ -132,4 +134,4 @@ def test_two_ranks_exchange_through_peer_buffers(fg):
     for p in procs:
         p.join(300)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    assert len(ret) == 20 and max(ret.values()) < 1e-5, dict(ret)
+    assert len(ret) == 22 and max(ret.values()) < 1e-5, dict(ret)
