@@ -991,8 +991,32 @@ def main_ours(args):
         h2d = torch.tensor([X_host.numel() * 4], device=device, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(h2d)
+        # the host -> device link alone, every rank copying at once (no compute, no D2H): what the e2e step is bound by.  At N = 1
+        # this is the PCIe link (~55 GB/s); at N > 1 the ranks share the host's memory system and PCIe switches, and the
+        # per-rank figure shows how far below its own link each of them falls
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(s_in):
+            c0.record(s_in)
+            for _ in range(4):
+                X_in[0].copy_(X_host, non_blocking=True)
+            c1.record(s_in)
+        barrier()
+        t_copy = torch.tensor([c0.elapsed_time(c1) / 4], device=device, dtype=torch.float64)
+        my_bytes = float(X_host.numel() * 4)
+        copy_gbps = torch.tensor([my_bytes / (float(t_copy.item()) * 1e-3) / 1e9], device=device, dtype=torch.float64)
+        copy_min = copy_gbps.clone()
+        if world > 1:
+            dist.all_reduce(t_copy, op=dist.ReduceOp.MAX)
+            dist.all_reduce(copy_gbps)  # sum = aggregate
+            dist.all_reduce(copy_min, op=dist.ReduceOp.MIN)
         e2e = {"value": n / (float(t2.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(t2.item()),
                "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": int(n * Cp * 4),
+               "h2d_GBps_per_rank_in_step": float(h2d.item()) / world / (float(t2.item()) * 1e-3) / 1e9,
+               "h2d_alone": {"ms": float(t_copy.item()), "GBps_aggregate": float(copy_gbps.item()),
+                             "GBps_slowest_rank": float(copy_min.item()),
+                             "note": "the H2D copy of the step's features alone, all ranks at once (pinned memory, one DMA per rank): "
+                                     "the floor of the e2e step"},
                "pipelining": "3 streams, double-buffered; every rank copies in the feature rows its own subgraphs reference "
                              "(the whole table at N = 1) over its own PCIe link and copies its own slice of the logits out"}
     if rank == 0:
