@@ -91,10 +91,13 @@ int fitgnn_abi_version(void);
 int fitgnn_last_error(char* buf, size_t n);
 /* SM count and compute capability (major*10+minor) of the current device */
 int fitgnn_device_info(int* sm_count, int* cc);
-/* Kernel-tuning switches (A/B measurements only; results never depend on them).  Initial values come from the
- * environment, read ONCE per process: FITGNN_GEMM_WS, FITGNN_HEAD_BULK, FITGNN_AGG_WIDE, FITGNN_GEMM_WIDE,
- * FITGNN_GEMM_PAIR, FITGNN_SM_RESERVE (SMs the persistent GEMM grids leave free for a concurrent exchange kernel).
- * name = the lower-case suffix ("gemm_pair", ...). */
+/* Kernel-tuning switches (A/B measurements only; results never depend on them — except gemm_debug, which exists to BREAK
+ * them for a measurement).  Initial values come from the environment, read ONCE per process: FITGNN_GEMM_WS,
+ * FITGNN_HEAD_BULK, FITGNN_AGG_WIDE, FITGNN_GEMM_WIDE, FITGNN_GEMM_PAIR, FITGNN_GEMM_PAIR_WS (0 = CTA pairs never keep their
+ * weights resident), FITGNN_GEMM_PREFETCH (1 = the TMA producer prefetches the next m-block's A rows into L2; measured
+ * slower), FITGNN_SM_RESERVE (SMs the persistent GEMM grids leave free for a concurrent exchange kernel).
+ * name = the lower-case suffix ("gemm_pair", ...).  gemm_debug (no environment variable, default 0): bit 0 = GEMM epilogues
+ * skip their TMA stores (scripts/bench_*epilogue_cost.py only). */
 int fitgnn_tuning_set(const char* name, int value);
 int fitgnn_tuning_get(const char* name, int* value);
 

@@ -204,3 +204,26 @@ def test_reference_cache_layout_roundtrip(tmp_path, mode, flags):
     gg = fc.load_reference_cache(str(tmp_path), "zinc", "variation_neighborhoods", 0.3)
     assert gg.graph_level and gg.saved_graph_list == [0, 3] and gg.candidate is None and len(gg.Gc_list) == 2
     assert not os.path.exists(gpaths["candidate"])
+
+
+def test_tuning_switches_are_known_to_the_library():
+    """fitgnn_tuning_get / _set are host-only: every switch include/fitgnn.h documents exists, unknown names are refused,
+    a set value reads back (no GPU involved)."""
+    import ctypes as C
+    from fitgnn_b200._lib import FitgnnError, lib, set_tuning
+    names = ["gemm_ws", "head_bulk", "agg_wide", "gemm_wide", "gemm_pair", "gemm_pair_ws", "gemm_prefetch", "sm_reserve",
+             "gemm_debug"]
+    header = open(os.path.join(ROOT, "include", "fitgnn.h")).read().lower()
+    for name in names:
+        v = C.c_int32(-12345)
+        assert lib().fitgnn_tuning_get(name.encode(), C.byref(v)) == 0 and v.value != -12345, name
+        assert name in header, f"{name} is not documented in include/fitgnn.h"
+        old = set_tuning(name, v.value + 1)
+        assert old == v.value
+        w = C.c_int32(0)
+        lib().fitgnn_tuning_get(name.encode(), C.byref(w))
+        assert w.value == v.value + 1
+        set_tuning(name, old)
+    assert lib().fitgnn_tuning_get(b"gemm_debug", C.byref(v)) == 0 and v.value == 0  # never on by default
+    with pytest.raises(FitgnnError):
+        set_tuning("no_such_switch", 1)
