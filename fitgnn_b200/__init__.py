@@ -7,7 +7,7 @@ from . import _lib
 
 _lib.lib()  # fail loudly at import if the CUDA library has not been built
 
-from . import autograd, cache, coarsen, dist, engine, infer, nn, ops, pack, stream, synth, train  # noqa: E402
+from . import autograd, cache, coarsen, coarsen_algo, dist, engine, infer, nn, ops, pack, stream, synth, train  # noqa: E402
 from .engine import PackedForward  # noqa: E402
 from .nn import (Classify_graph_gc, Classify_graph_gs, Classify_node, GCNConv, Net1, Net2, Regress_graph_gc,  # noqa: E402
                  Regress_graph_gs, Regress_node)

@@ -1,0 +1,319 @@
+"""The coarsening ALGORITHM itself: multilevel local-variation coarsening with the neighbourhood
+candidate family — /root/reference/graph_coarsening/coarsening_utils.py `coarsen` :18-182 (method
+'variation_neighborhoods', the reference's default, utils.py:159) with `contract_variation_linear` :530-650,
+`get_coarsening_matrix` :212-254 and `coarsen_matrix` :201-205.
+
+What runs where.  The reference spends its time in a Python loop that builds, for each of the N closed neighbourhoods, a dense
+induced Laplacian and a dense projector and multiplies them (:554-560).  Here every level's parallel work is tensor code on
+the device, in fp64:
+  * the spectral basis (when the caller does not pass one): smallest-K eigenpairs of the level-1 Laplacian, dense `eigh` up
+    to 4096 nodes, Lanczos with full re-orthogonalisation on `offset*I - L` (the reference's own shift, :84-89) beyond;
+  * the costs of ALL candidate sets at once: membership pairs (set, node), the induced edges of every set by a sorted-key
+    lookup (wedges (i, u, v) with v in N[i]), `y = L_S b` by segment sums and `M_i = sum_u b_u y_u^T` — never a dense
+    nc x nc matrix;
+  * the level's coarsened graph `Wc = P W P^T` (zero diagonal; integer edge counts) from the ORIGINAL edge list through the
+    composed partition, and the basis update `B <- iC B`, `A = B diag(d^-1/2) V` (:97-103).
+The contraction itself (:606-648) pops candidates in cost order, marks nodes and re-inserts shrunk sets with a new cost —
+sequential by construction, as is its result; it runs on the host over the device-computed costs (a heap keyed
+(cost, insertion number) pops in the order of the reference's SortedList) and re-costs the few shrunk sets there.
+
+Parity: given the same (Uk, lk) the partition, the C weights and Wc equal the reference's bit for bit on
+tests/golden/coarsen_algo.npz (6 cases, up to 3 levels); the reference's own eigsh starts from a random vector, so two calls
+of the reference itself disagree on up to 85 % of the entries (recorded in the fixture) — which is why the basis is an argument.
+"""
+from __future__ import annotations
+
+import heapq
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+F64 = torch.float64
+
+
+@dataclass
+class Coarsening:
+    part: torch.Tensor      # int64 [N]: supernode of every node (= C.indices of the reference's CSC coarsening matrix)
+    cweight: torch.Tensor   # float64 [N]: C[part[v], v] = product over the levels of 1/sqrt(set size)
+    k: int                  # supernodes
+    levels: int
+    gc_row: torch.Tensor    # int64 [nnz]: coarsened graph, row-major sorted COO (both directions), zero diagonal
+    gc_col: torch.Tensor
+    gc_cnt: torch.Tensor    # float64 [nnz]: number of original edges between the two supernodes (Gc.W)
+
+
+# ------------------------------------------------------------------------------------------------ level graph
+def _coalesce(row, col, w, n):
+    """row-major sorted COO with duplicates summed (scipy's tocsr semantics) and its row pointer."""
+    key = row * n + col
+    key, order = torch.sort(key)
+    w = w[order]
+    uniq, inv = torch.unique_consecutive(key, return_inverse=True)
+    ws = torch.zeros(uniq.numel(), dtype=F64, device=row.device).index_add_(0, inv, w)
+    r, c = uniq // n, uniq % n
+    rowptr = torch.zeros(n + 1, dtype=torch.int64, device=row.device)
+    rowptr[1:] = torch.cumsum(torch.bincount(r, minlength=n), 0)
+    return r, c, ws, rowptr
+
+
+def _project_graph(row0, col0, part, k):
+    """Wc = P_bin W P_bin^T with the diagonal removed (coarsen_matrix :201-205 + zero_diag): edge counts between supernodes."""
+    pr, pc = part[row0], part[col0]
+    keep = pr != pc
+    return _coalesce(pr[keep], pc[keep], torch.ones(int(keep.sum()), dtype=F64, device=row0.device), k)
+
+
+# ------------------------------------------------------------------------------------------------ candidate costs
+def _neighbourhood_costs(row, col, w, rowptr, n, A, chunk=1 << 22):
+    """cost_i = ||B^T L_S B||_F / (nc - 1) for every closed neighbourhood S = N[i] (:554-560, :583-588), all at once.
+    B = rows of A centred over S; L_S = diag(2 deg - W_S 1) - W_S on the induced subgraph."""
+    dev = row.device
+    deg = torch.zeros(n, dtype=F64, device=dev).index_add_(0, row, w)
+    ar = torch.arange(n, device=dev)
+    mkey, _ = torch.sort(torch.cat([row * n + col, ar * n + ar]))  # membership pairs (set i, node u), sorted
+    mset, mnode = mkey // n, mkey % n
+    P = mkey.numel()
+    nc = torch.bincount(mset, minlength=n).to(F64)
+    K = A.shape[1]
+    mean = torch.zeros(n, K, dtype=F64, device=dev).index_add_(0, mset, A[mnode]) / nc[:, None]
+    b = A[mnode] - mean[mset]                                            # [P, K]
+    # induced edges: for a pair p = (i, u) every neighbour v of u with (i, v) a membership pair as well
+    du = rowptr[mnode + 1] - rowptr[mnode]
+    acc = torch.zeros(P, K, dtype=F64, device=dev)                        # sum_v w_uv b_v
+    wdeg = torch.zeros(P, dtype=F64, device=dev)                         # W_S 1
+    csum = torch.cumsum(du, 0)
+    p0 = 0
+    while p0 < P:
+        base = int(csum[p0 - 1]) if p0 > 0 else 0
+        p1 = int(torch.searchsorted(csum, torch.tensor(base + chunk, device=dev), right=True))
+        p1 = max(p1, p0 + 1)
+        cnt = du[p0:p1]
+        pp = torch.repeat_interleave(torch.arange(p0, p1, device=dev), cnt)
+        first = torch.repeat_interleave(csum[p0:p1] - cnt, cnt)
+        e = rowptr[mnode[pp]] + (torch.arange(base, base + pp.numel(), device=dev) - first)
+        q = torch.searchsorted(mkey, mset[pp] * n + col[e])
+        ok = (q < P) & (mkey[q.clamp(max=P - 1)] == mset[pp] * n + col[e])
+        pp, q, we = pp[ok], q[ok], w[e[ok]]
+        acc.index_add_(0, pp, we[:, None] * b[q])
+        wdeg.index_add_(0, pp, we)
+        p0 = p1
+    y = (2 * deg[mnode] - wdeg)[:, None] * b - acc                       # rows of L_S B
+    M = torch.zeros(n, K * K, dtype=F64, device=dev).index_add_(0, mset, (b[:, :, None] * y[:, None, :]).reshape(P, K * K))
+    cost = torch.sqrt((M * M).sum(1)) / (nc - 1)
+    return torch.where(nc > 1, cost, torch.full_like(cost, float("inf"))), deg  # an isolated node is no candidate
+
+
+def _cost_host(Wd, deg, A, nodes):
+    """the same cost for ONE (shrunk) set on the host: the contraction loop's re-costs (:640-643)."""
+    Ws = Wd[np.ix_(nodes, nodes)] if isinstance(Wd, np.ndarray) else Wd[nodes][:, nodes].toarray()
+    L = np.diag(2 * deg[nodes] - Ws.sum(1)) - Ws
+    B = A[nodes] - A[nodes].mean(0, keepdims=True)
+    return float(np.linalg.norm(B.T @ L @ B) / (len(nodes) - 1))
+
+
+def _contract(costs, rowptr, col, W_host, deg, A, r):
+    """:590-648 — the sequential contraction: smallest cost first; a set without marked nodes is contracted (unless it would
+    over-reduce), a set with marked nodes is shrunk, re-costed and re-inserted.  Equal costs pop oldest first."""
+    n = len(costs)
+    sets = [np.sort(np.append(col[rowptr[i]: rowptr[i + 1]], i)) for i in range(n)]
+    heap = [(float(costs[i]), i, i) for i in range(n)]
+    heapq.heapify(heap)
+    seq = n
+    marked = np.zeros(n, dtype=bool)
+    out = []
+    n_reduce = np.floor(r * n)
+    while heap:
+        _, _, i = heapq.heappop(heap)
+        s = sets[i]
+        m = marked[s]
+        if not m.any():
+            gain = len(s) - 1
+            if gain > n_reduce:
+                continue
+            marked[s] = True
+            out.append(s)
+            n_reduce -= gain
+            if n_reduce <= 0:
+                break
+        else:
+            s = s[~m]
+            if len(s) > 1:
+                sets[i] = s
+                heapq.heappush(heap, (_cost_host(W_host, deg, A, s), seq, i))
+                seq += 1
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ spectral basis
+def laplacian_subspace(row, col, w, n, K, tol=1e-5, dense_limit=4096):
+    """Smallest-K eigenpairs (lk ascending, Uk) of L = D - W on the device."""
+    dev = row.device
+    deg = torch.zeros(n, dtype=F64, device=dev).index_add_(0, row, w)
+    if n <= dense_limit:
+        L = torch.diag(deg)
+        L.index_put_((row, col), -w, accumulate=True)
+        lam, U = torch.linalg.eigh(L)
+        return lam[:K].clone(), U[:, :K].clone()
+    offset = 2 * float(deg.max())
+    def matvec(x):  # (offset I - L) x
+        return (offset - deg) * x + torch.zeros_like(x).index_add_(0, row, w * x[col])
+    g = torch.Generator(device="cpu").manual_seed(0)
+    m_max = min(n - 1, 600)
+    Q = torch.zeros(n, m_max + 1, dtype=F64, device=dev)
+    alpha, beta = [], []
+    q = torch.randn(n, generator=g, dtype=F64).to(dev)
+    Q[:, 0] = q / q.norm()
+    for j in range(m_max):
+        v = matvec(Q[:, j])
+        a = torch.dot(v, Q[:, j])
+        v = v - Q[:, : j + 1] @ (Q[:, : j + 1].T @ v)  # full re-orthogonalisation (twice is enough)
+        v = v - Q[:, : j + 1] @ (Q[:, : j + 1].T @ v)
+        bnorm = v.norm()
+        alpha.append(float(a)); beta.append(float(bnorm))
+        Q[:, j + 1] = v / bnorm
+        if (j + 1) % 20 == 0 and j + 1 >= 2 * K:
+            T = torch.diag(torch.tensor(alpha, dtype=F64)) + torch.diag(torch.tensor(beta[:-1], dtype=F64), 1) + \
+                torch.diag(torch.tensor(beta[:-1], dtype=F64), -1)
+            th, S = torch.linalg.eigh(T)
+            res = abs(beta[-1]) * S[-1, -K:].abs()  # residual norms of the K largest Ritz pairs
+            if float(res.max()) <= tol * float(th[-1].abs()):
+                break
+    m = len(alpha)
+    T = torch.diag(torch.tensor(alpha, dtype=F64)) + torch.diag(torch.tensor(beta[:-1], dtype=F64), 1) + \
+        torch.diag(torch.tensor(beta[:-1], dtype=F64), -1)
+    th, S = torch.linalg.eigh(T)
+    U = Q[:, :m] @ S[:, -K:].to(dev)
+    lam = offset - th[-K:].to(dev)
+    order = torch.argsort(lam)
+    return lam[order], U[:, order]
+
+
+# ------------------------------------------------------------------------------------------------ driver
+def _coarsen(edge_index, n, r=0.5, K=10, Uk=None, lk=None, max_levels=10, max_level_r=0.99) -> Coarsening:
+    """coarsen :18-182 on whatever device edge_index lives on (the public entry below insists on CUDA)."""
+    dev = edge_index.device
+    row0, col0 = edge_index[0].long(), edge_index[1].long()
+    if bool((row0 == col0).any()):
+        raise ValueError("coarsen: self loops are not supported (the reference's pipeline produces none)")
+    row, col, w, rowptr = _coalesce(row0, col0, torch.ones(row0.numel(), dtype=F64, device=dev), n)
+    r = float(np.clip(r, 0, 0.999))
+    n_cur, n_target = n, np.ceil((1 - r) * n)
+    if Uk is None or lk is None or len(lk) < K:
+        lk, Uk = laplacian_subspace(row, col, w, n, K)
+    lk = torch.as_tensor(lk, dtype=F64, device=dev).clone()
+    Uk = torch.as_tensor(Uk, dtype=F64, device=dev)
+    mask = lk < 1e-10                                   # :78-83
+    lk[mask] = 1
+    lsinv = lk ** -0.5
+    lsinv[mask] = 0
+    B = Uk[:, :K] * lsinv[:K][None, :]
+    part = torch.arange(n, device=dev)
+    cweight = torch.ones(n, dtype=F64, device=dev)
+    levels = 0
+    for level in range(1, max_levels + 1):
+        r_cur = float(np.clip(1 - n_target / n_cur, 0.0, max_level_r))
+        if level == 1:
+            A = B
+        else:                                           # :97-103
+            deg = torch.zeros(n_cur, dtype=F64, device=dev).index_add_(0, row, w)
+            LB = deg[:, None] * B - torch.zeros_like(B).index_add_(0, row, w[:, None] * B[col])
+            # Reference quirk (:98-103): `A = B @ diag(d^-1/2) @ V` scales COLUMN j of B by the j-th eigenvalue in the order
+            # numpy's general (non-symmetric) eig happens to return them — not B V D^-1/2 — so the result depends on that
+            # order.  The K x K matrix goes through the very same routine on the host (K = 10: nothing to parallelise).
+            d, V = np.linalg.eig((B.T @ LB).cpu().numpy())
+            d, V = np.real(d), np.real(V)
+            zero = d == 0
+            d[zero] = 1
+            dis = d ** (-1 / 2)
+            dis[zero] = 0
+            A = (B * torch.as_tensor(dis, dtype=F64, device=dev)[None, :]) @ torch.as_tensor(V, dtype=F64, device=dev)
+        costs, deg = _neighbourhood_costs(row, col, w, rowptr, n_cur, A)
+        # the sequential contraction, on the host over the device-computed costs
+        rp, cl = rowptr.cpu().numpy(), col.cpu().numpy()
+        import scipy.sparse as sp
+        W_host = sp.csr_matrix((w.cpu().numpy(), cl, rp), shape=(n_cur, n_cur))
+        sets = _contract(costs.cpu().numpy(), rp, cl, W_host, deg.cpu().numpy(), A.cpu().numpy(), r_cur)
+        levels += 1
+        n_next = n_cur - sum(len(s) - 1 for s in sets)
+        if n_cur - n_next <= 2:                         # :131-135
+            break
+        # get_coarsening_matrix :212-254: a set's row is its smallest member's; surviving rows keep their order
+        rep = np.arange(n_cur)
+        scale = np.ones(n_cur)
+        for s in sets:
+            rep[s] = s[0]
+            scale[s] = 1 / np.sqrt(len(s))
+        kept = np.unique(rep)
+        lvl_part = torch.as_tensor(np.searchsorted(kept, rep), device=dev)
+        lvl_scale = torch.as_tensor(scale, dtype=F64, device=dev)
+        cweight = lvl_scale[part] * cweight             # C = iC.dot(C) :136
+        part = lvl_part[part]
+        B = torch.zeros(n_next, B.shape[1], dtype=F64, device=dev).index_add_(0, lvl_part, lvl_scale[:, None] * B)
+        row, col, w, rowptr = _project_graph(row0, col0, part, n_next)  # :138-139 (composed partition, original edges)
+        n_cur = n_next
+        if n_cur <= n_target:
+            break
+    if levels == 1 and n_cur == n:  # the only level was abandoned: the graph itself
+        row, col, w, rowptr = _coalesce(row0, col0, torch.ones(row0.numel(), dtype=F64, device=dev), n)
+    return Coarsening(part, cweight, int(n_cur), levels, row, col, w)
+
+
+def variation_neighborhoods(edge_index: torch.Tensor, n: int, r: float = 0.5, K: int = 10, Uk=None, lk=None,
+                            max_levels: int = 10) -> Coarsening:
+    """`coarsen(G, K, r, method='variation_neighborhoods', Uk=, lk=)` (coarsening_utils.py:18) for ONE connected component
+    given as a CUDA edge_index [2, E] (both directions, no self loops).  Returns the partition in the form the pack builders
+    take (`part`, `cweight` = C.indices / C.data) plus the coarsened graph."""
+    if not edge_index.is_cuda:
+        raise ValueError("fitgnn_b200 runs on CUDA tensors only (there is no CPU path)")
+    return _coarsen(edge_index, n, r, K, Uk, lk, max_levels)
+
+
+def connected_components(edge_index: torch.Tensor, n: int) -> torch.Tensor:
+    """label[v] = smallest node id of v's component (min-label propagation with pointer jumping, on the device)."""
+    dev = edge_index.device
+    row, col = edge_index[0].long(), edge_index[1].long()
+    label = torch.arange(n, device=dev)
+    while True:
+        new = label.clone()
+        new.scatter_reduce_(0, row, label[col], reduce="amin")
+        new = new[new]  # pointer jumping
+        if bool((new == label).all()):
+            return label
+        label = new
+
+
+def coarsen_partition(edge_index: torch.Tensor, n: int, r: float = 0.5, K: int = 10, bases=None):
+    """The partition step of utils.coarsening_classification (:143-186) with the device algorithm: connected components in the
+    reference's candidate order (size-descending, stable over smallest-member order, :146), every component with more than
+    one node coarsened by `variation_neighborhoods`, single nodes passed through (:352-368); supernodes numbered component by
+    component.  Returns coarsen.Partition (what build_pack / project take).  `bases`: optional {component index: (Uk, lk)}."""
+    from .coarsen import Partition
+    core = variation_neighborhoods if edge_index.is_cuda else _coarsen
+    label = connected_components(edge_index, n)
+    roots, inv, sizes = torch.unique(label, return_inverse=True, return_counts=True)  # roots ascend = smallest-member order
+    order = torch.sort(sizes, descending=True, stable=True).indices
+    part = torch.full((n,), -1, dtype=torch.int64, device=edge_index.device)
+    cw = torch.ones(n, dtype=F64, device=edge_index.device)
+    comp_of_sub, offs, base = [], [0], 0
+    row, col = edge_index[0].long(), edge_index[1].long()
+    for ci, c in enumerate(order.tolist()):
+        nodes = torch.nonzero(inv == c).view(-1)  # ascending = H.info['orig_idx']
+        if nodes.numel() == 1:
+            part[nodes] = base
+            kc = 1
+        else:
+            local = torch.full((n,), -1, dtype=torch.int64, device=edge_index.device)
+            local[nodes] = torch.arange(nodes.numel(), device=edge_index.device)
+            sel = inv[row] == c
+            ei_c = torch.stack([local[row[sel]], local[col[sel]]])
+            Uk, lk = (bases or {}).get(ci, (None, None))
+            res = core(ei_c, int(nodes.numel()), r, K, Uk, lk)
+            part[nodes] = base + res.part
+            cw[nodes] = res.cweight
+            kc = res.k
+        comp_of_sub.extend([ci] * kc)
+        base += kc
+        offs.append(base)
+    return Partition(part.to(torch.int32).cpu().numpy(), cw.cpu().numpy(), base, np.asarray(comp_of_sub, dtype=np.int32),
+                     np.asarray(offs, dtype=np.int64))

@@ -1,0 +1,134 @@
+"""The coarsening algorithm: oracle and product against tests/golden/coarsen_algo.npz, which
+tests/golden/make_golden_coarsen.py produced by running the UNMODIFIED reference coarsen() (coarsening_utils.py:18-182,
+variation_neighborhoods) with the spectral basis passed through its own (Uk, lk) arguments."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from oracle import coarsen_oracle as co
+
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "coarsen_algo.npz"))
+CASES = [str(c) for c in GOLD["cases"]]
+K = int(GOLD["K"])
+
+
+def case(name):
+    n, r = int(GOLD[f"{name}_n"]), float(GOLD[f"{name}_r"])
+    return n, r, GOLD[f"{name}_row"], GOLD[f"{name}_col"], GOLD[f"{name}_Uk"], GOLD[f"{name}_lk"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_reproduces_the_reference_coarsening_bit_exactly(name):
+    n, r, row, col, Uk, lk = case(name)
+    W = sp.coo_matrix((np.ones(len(row)), (row, col)), shape=(n, n)).tocsr()
+    C, Wc, levels = co.coarsen(W, Uk, lk, K=K, r=r)
+    assert C.shape[0] == int(GOLD[f"{name}_C_rows"]) and levels == int(GOLD[f"{name}_levels"])
+    assert np.array_equal(C.indices, GOLD[f"{name}_C_indices"]) and np.array_equal(C.data, GOLD[f"{name}_C_data"])
+    want = sp.coo_matrix((GOLD[f"{name}_Wc_val"], (GOLD[f"{name}_Wc_row"], GOLD[f"{name}_Wc_col"])), shape=Wc.shape).tocsr()
+    assert abs(Wc - want).nnz == 0
+
+
+def check_product(res, name):
+    assert res.k == int(GOLD[f"{name}_C_rows"]) and res.levels == int(GOLD[f"{name}_levels"])
+    assert np.array_equal(res.part.cpu().numpy(), GOLD[f"{name}_C_indices"])        # partition indices: bit-exact
+    assert np.array_equal(res.cweight.cpu().numpy(), GOLD[f"{name}_C_data"])         # C's values: bit-exact
+    assert np.array_equal(res.gc_row.cpu().numpy(), GOLD[f"{name}_Wc_row"])          # coarsened adjacency: bit-exact
+    assert np.array_equal(res.gc_col.cpu().numpy(), GOLD[f"{name}_Wc_col"])
+    assert np.array_equal(res.gc_cnt.cpu().numpy(), GOLD[f"{name}_Wc_val"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_product_core_on_cpu_tensors_matches_the_reference(name):
+    """the device-agnostic core (fitgnn_b200.coarsen_algo._coarsen) on CPU tensors: same tensor code the GPU runs"""
+    from fitgnn_b200 import coarsen_algo as ca
+    n, r, row, col, Uk, lk = case(name)
+    check_product(ca._coarsen(torch.tensor(np.stack([row, col])), n, r, K, Uk, lk), name)
+
+
+def test_public_entry_refuses_cpu_tensors_and_self_loops():
+    from fitgnn_b200 import coarsen_algo as ca
+    ei = torch.tensor([[0, 1], [1, 0]])
+    with pytest.raises(ValueError, match="CUDA"):
+        ca.variation_neighborhoods(ei, 2, 0.5)
+    with pytest.raises(ValueError, match="self loops"):
+        ca._coarsen(torch.tensor([[0, 1, 1], [1, 0, 1]]), 2, 0.5)
+
+
+def test_batched_costs_equal_the_reference_cost_function():
+    """every closed neighbourhood's cost in one batched computation == the reference's per-set dense formula (:554-560)"""
+    from fitgnn_b200 import coarsen_algo as ca
+    n, r, row, col, Uk, lk = case("n300_r50")
+    W = sp.coo_matrix((np.ones(len(row)), (row, col)), shape=(n, n)).tocsr()
+    A = co.spectral_matrix(Uk, lk, K)
+    deg = np.ravel(W.sum(axis=0))
+    Wb = ((W > 0) + sp.eye(n, dtype=bool, format="csr")).tocsr()
+    Wb.sort_indices()
+    want = np.array([co.subgraph_cost(W.tolil(), deg, A, Wb.indices[Wb.indptr[i]: Wb.indptr[i + 1]]) for i in range(n)])
+    r_, c_, w_, rp = ca._coalesce(torch.tensor(row), torch.tensor(col), torch.ones(len(row), dtype=torch.float64), n)
+    for chunk in (1 << 22, 97):  # one chunk / many chunks of the wedge enumeration
+        got, _ = ca._neighbourhood_costs(r_, c_, w_, rp, n, torch.tensor(A), chunk=chunk)
+        assert np.abs(got.numpy() - want).max() <= 1e-12 * np.abs(want).max()
+
+
+def test_spectral_basis_dense_and_lanczos():
+    """smallest-K Laplacian eigenpairs: dense eigh (small graphs) and Lanczos on offset*I - L (the reference's shift) agree with
+    scipy; the first eigenvalue is 0 (connected graph) and is dropped by the lk < 1e-10 rule exactly as in the reference"""
+    import scipy.sparse.linalg as spla
+    from fitgnn_b200 import coarsen_algo as ca
+    from tests.golden.make_golden_coarsen_graph import synth_graph
+    n, ei = synth_graph(7, 1500)
+    t = torch.tensor(ei)
+    row, col, w, _ = ca._coalesce(t[0], t[1], torch.ones(ei.shape[1], dtype=torch.float64), n)
+    W = sp.coo_matrix((np.ones(ei.shape[1]), (ei[0], ei[1])), shape=(n, n)).tocsr()
+    L = (sp.diags(np.ravel(W.sum(0))) - W).asfptype()
+    ref = np.sort(spla.eigsh(L, k=K, sigma=-0.01, which="LM")[0])
+    for limit in (4096, 100):  # dense / Lanczos
+        lam, U = ca.laplacian_subspace(row, col, w, n, K, dense_limit=limit)
+        assert np.abs(lam.numpy() - ref).max() <= 1e-4 and abs(float(lam[0])) < 1e-8
+        res = np.linalg.norm(L @ U.numpy() - U.numpy() * lam.numpy()[None, :], axis=0)
+        assert res.max() <= 1e-5 * 2 * float(W.sum(0).max()) * 50  # the reference's tolerance is relative to |offset - lambda|
+    # and the whole algorithm runs from its own basis (no reference to compare with: eigsh's start vector is random there)
+    res = ca._coarsen(t, n, 0.5, K)
+    assert res.levels >= 1 and abs(res.k - n // 2) <= 2 and int(res.part.max()) == res.k - 1
+    sizes = np.bincount(res.part.numpy(), minlength=res.k)
+    assert np.allclose(res.cweight.numpy() ** -2, sizes[res.part.numpy()])  # single level: C values are 1/sqrt(set size)
+
+
+def test_coarsen_partition_orders_components_like_the_reference():
+    from fitgnn_b200 import coarsen_algo as ca
+    from tests.golden.make_golden_coarsen_graph import synth_graph
+    n1, e1 = synth_graph(1, 120)
+    n2, e2 = synth_graph(2, 40)
+    # components: [0, n1) large, [n1, n1 + n2) medium, a pair, two singletons — node ids shuffled
+    pair = np.array([[n1 + n2, n1 + n2 + 1], [n1 + n2 + 1, n1 + n2]])
+    n = n1 + n2 + 4
+    ei = np.concatenate([e1, e2 + n1, pair], 1)
+    perm = np.random.default_rng(0).permutation(n)
+    ei = perm[ei]
+    p = ca.coarsen_partition(torch.tensor(ei), n, 0.5, K)
+    assert p.k == len(np.unique(p.part)) and p.part.min() == 0 and p.part.max() == p.k - 1
+    comp_sizes = np.diff(p.sub_offset)
+    big, mid = set(perm[:n1]), set(perm[n1:n1 + n2])
+    # candidate order: size-descending
+    assert set(np.nonzero(p.part < p.sub_offset[1])[0]) == big
+    assert set(np.nonzero((p.part >= p.sub_offset[1]) & (p.part < p.sub_offset[2]))[0]) == mid
+    # the pair stays two supernodes: a level that removes <= 2 nodes is abandoned (coarsening_utils.py:131-135); singletons pass through
+    assert list(comp_sizes[2:]) == [2, 1, 1]
+    assert abs(int(comp_sizes[0]) - n1 // 2) <= 2
+    # no supernode spans two components
+    lab = ca.connected_components(torch.tensor(ei), n).numpy()
+    for s in range(p.k):
+        assert len(set(lab[p.part == s])) == 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_product_on_cuda_matches_the_reference(name):
+    from fitgnn_b200 import coarsen_algo as ca
+    n, r, row, col, Uk, lk = case(name)
+    res = ca.variation_neighborhoods(torch.tensor(np.stack([row, col]), device="cuda"), n, r, K, Uk, lk)
+    assert res.part.is_cuda
+    check_product(res, name)
