@@ -1,8 +1,8 @@
 """Host glue between the reference's coarsening outputs and the device builders.
 
-The coarsening ALGORITHM (graph_coarsening.coarsen: eigsh + greedy contraction, sequential CPU code) is out
-of scope; it produces, once, the coarsening matrices C.  Everything derived from them on
-the hot path runs on the device:
+The coarsening ALGORITHM (graph_coarsening.coarsen: eigsh + greedy contraction) produces, once, the coarsening
+matrices C; `coarsen_algo.py` implements it (candidate costs, spectral basis and level projections
+on the device, the sequential contraction on the host).  Everything derived from C on the hot path runs on the device:
   * partition vector + C weights  <- C.indices / C.data  (subgraph_mapping utils.py:113-121)
   * Xc = C·X                      <- utils.py:161, :738, :827
   * Ac pattern                    <- coarsening_utils.py:138 / utils.py:745-746
