@@ -82,12 +82,14 @@ def parse():
                         "--collective push, else 0")
     p.add_argument("--agg-wide", type=int, default=None, help="tuning 'agg_wide' (A/B of the fused-aggregation tile)")
     p.add_argument("--chunks", type=int, default=1, help="N>1: chunks per rank; chunk c's all-gather overlaps chunk c+1")
-    p.add_argument("--modes", default="none_heavy_tail,cluster,train,per_query,alt_precision",
+    p.add_argument("--modes", default="none_heavy_tail,cluster,train,per_query,alt_precision,coarsen",
                    help="N=1: extra blocks measured after the headline (comma separated, '' = none): none_heavy_tail = same "
                         "graph shape with power-law subgraph sizes (hybrid fused + classic schedule); cluster = the headline "
                         "graph with cluster_node augmentation (sharded pack, streamed forward); train = one GD training step "
                         "(forward + backward + Adam) on the headline pack; per_query = the reference's per-sample latency loop; "
-                        "alt_precision = the headline configuration in the other arithmetics (bf16x3 and fp16x2 beside an fp16 headline)")
+                        "alt_precision = the headline configuration in the other arithmetics (bf16x3 and fp16x2 beside an fp16 headline); "
+                        "coarsen = the coarsening algorithm itself on Cora- / PubMed-shaped graphs (device costs + host contraction) "
+                        "with the oracle's CPU path and a partition-equality check beside it")
     p.add_argument("--only-modes", action="store_true", help="skip the headline measurement (profiling the --modes blocks)")
     p.add_argument("--mode-steps", type=int, default=0, help="timed steps of the --modes blocks (0 = min(--steps, 5))")
     p.add_argument("--max-rows", type=int, default=1 << 22, help="rows per shard of the streamed forward (--modes blocks)")
@@ -556,6 +558,59 @@ def mode_precision(args, fg, device, n, F, C, ei, part, k, X, sd, steps, sampler
             "parity": parity_block(out[: want.shape[0], :C], want, f"oracle CPU path, first {n_sub} subgraphs")}
 
 
+def mode_coarsen(args, fg, device):
+    """The coarsening algorithm itself (coarsening_utils.py:18-182, variation_neighborhoods) on Cora- and
+    PubMed-shaped power-law graphs (BASELINE.json configs[0], [1]): spectral basis + batched candidate costs + level projections
+    on the device, the sequential contraction on the host.  CPU arm and parity on the Cora-shaped graph: the oracle's
+    restatement of the reference algorithm, fed the SAME spectral basis, must return the same partition.  Never raises: a
+    failure is reported in the block instead of costing the bench line."""
+    try:
+        from fitgnn_b200 import coarsen_algo as ca
+        out = {}
+        for name, n, e_und, r in (("cora_shaped", 2708, 5278, 0.7), ("pubmed_shaped", 19717, 44324, 0.5)):
+            ei = torch.tensor(fg.synth.powerlaw_graph(n, e_und, seed=0), device=device)
+            lab = ca.connected_components(ei, n)
+            roots, inv, sizes = torch.unique(lab, return_inverse=True, return_counts=True)
+            big = int(torch.argmax(sizes))  # the giant component (the reference coarsens component by component)
+            nodes = torch.nonzero(inv == big).view(-1)
+            local = torch.full((n,), -1, dtype=torch.int64, device=device)
+            local[nodes] = torch.arange(nodes.numel(), device=device)
+            sel = inv[ei[0]] == big
+            eic = torch.stack([local[ei[0][sel]], local[ei[1][sel]]])
+            nc = int(nodes.numel())
+            core = ca.variation_neighborhoods if device.type == "cuda" else ca._coarsen
+            sync = torch.cuda.synchronize if device.type == "cuda" else (lambda: None)
+            row, col, w, _ = ca._coalesce(eic[0], eic[1], torch.ones(eic.shape[1], dtype=torch.float64, device=device), nc)
+            sync(); t0 = time.perf_counter()
+            lk, Uk = ca.laplacian_subspace(row, col, w, nc, 10)
+            sync(); t_basis = time.perf_counter() - t0
+            core(eic, nc, r, 10, Uk, lk)  # warm-up
+            sync(); t0 = time.perf_counter()
+            res = core(eic, nc, r, 10, Uk, lk)
+            sync(); t_algo = time.perf_counter() - t0
+            blk = {"nodes": nc, "directed_edges": int(eic.shape[1]), "r": r, "supernodes": res.k, "levels": res.levels,
+                   "basis_ms": t_basis * 1e3, "contraction_levels_ms": t_algo * 1e3,
+                   "what": "basis = smallest-10 Laplacian eigenpairs on the device; contraction_levels = batched candidate costs + "
+                           "level projections on the device and the sequential contraction on the host, all levels"}
+            if name == "cora_shaped":
+                from oracle import coarsen_oracle as co
+                import scipy.sparse as sp
+                W = sp.coo_matrix((np.ones(eic.shape[1]), (eic[0].cpu().numpy(), eic[1].cpu().numpy())), shape=(nc, nc)).tocsr()
+                W.data[:] = 1.0
+                t0 = time.perf_counter()
+                Cm, _, lv = co.coarsen(W, Uk.cpu().numpy(), lk.cpu().numpy(), K=10, r=r)
+                t_cpu = time.perf_counter() - t0
+                blk["cpu_baseline"] = {"ms": t_cpu * 1e3, "kind": "port", "cores": 1,
+                                       "what": "oracle restatement of coarsening_utils.coarsen (numpy, per-set dense costs), same basis"}
+                blk["parity"] = {"partition_equal": bool(np.array_equal(Cm.indices, res.part.cpu().numpy())),
+                                 "cweight_equal": bool(np.array_equal(Cm.data, res.cweight.cpu().numpy())), "levels_equal": lv == res.levels,
+                                 "against": "oracle CPU path (pinned bit-exactly to the reference on tests/golden/coarsen_algo.npz), same (Uk, lk)"}
+            out[name] = blk
+        return out
+    except Exception as e:  # noqa: BLE001 — this block must not cost the bench line
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def mode_per_query(args, fg, device, n, F, C, ei, part, k, X, sd, precision, sampler):
     """The reference's own inference-time measurement (inference.py:672-688): ONE subgraph forward per queried node, timer
     around `model(x, edge_index)` only (the subgraph and its features are on the device before the timer starts), first sample
@@ -660,6 +715,8 @@ def main_ours(args):
                 res[m] = mode_per_query(args, fg, device, n, F, C, ei, part, k, X, sd, precision, None)
             elif m == "alt_precision":
                 res[m] = mode_precisions(args, fg, device, n, F, C, ei, part, k, X, sd, k_steps, None, precision)
+            elif m == "coarsen":
+                res[m] = mode_coarsen(args, fg, device)
             else:
                 res[m] = mode_cluster(args, fg, device, n, F, C, ei, part, cw, k, X, sd, precision, k_steps, None)
             torch.cuda.empty_cache()
@@ -1141,6 +1198,8 @@ def main_ours(args):
                 line["modes"][m] = mode_per_query(args, fg, device, n, F, C, ei_keep, part, k, X, sd, precision, sampler2)
             elif m == "alt_precision":
                 line["modes"][m] = mode_precisions(args, fg, device, n, F, C, ei_keep, part, k, X, sd, k_steps, sampler2, precision)
+            elif m == "coarsen":
+                line["modes"][m] = mode_coarsen(args, fg, device)
             else:
                 raise SystemExit(f"bench: unknown --modes entry {m!r}")
             torch.cuda.empty_cache()
