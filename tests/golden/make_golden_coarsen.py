@@ -30,14 +30,15 @@ from tests.golden.make_golden import synth_graph  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 K = 10
-CASES = [("n60_r50", 11, 60, 0.5), ("n300_r30", 3, 300, 0.3), ("n300_r50", 3, 300, 0.5), ("n300_r70", 3, 300, 0.7),
-         ("n800_r60", 5, 800, 0.6), ("n800_r90", 5, 800, 0.9)]
+CASES = [("n60_r50", 11, 60, 0.5, 4.0), ("n300_r30", 3, 300, 0.3, 4.0), ("n300_r50", 3, 300, 0.5, 4.0), ("n300_r70", 3, 300, 0.7, 4.0),
+         ("n800_r60", 5, 800, 0.6, 4.0), ("n800_r90", 5, 800, 0.9, 4.0),
+         ("n400_d10_r60", 9, 400, 0.6, 10.0)]  # denser: hundreds of triangles, i.e. induced edges inside the candidate sets
 
 
 def main():
     out = {"cases": np.array([c[0] for c in CASES]), "K": np.int64(K)}
-    for name, seed, n_main, r in CASES:
-        n, ei = synth_graph(seed, n_main, [])
+    for name, seed, n_main, r, avg_deg in CASES:
+        n, ei = synth_graph(seed, n_main, [], avg_deg=avg_deg)
         W = sp.coo_matrix((np.ones(ei.shape[1]), (ei[0], ei[1])), shape=(n, n)).tocsr()
         W.data[:] = 1.0  # simple graph
         G = pygsp.graphs.Graph(W=W)

@@ -1,6 +1,8 @@
 """The coarsening algorithm: oracle and product against tests/golden/coarsen_algo.npz, which
 tests/golden/make_golden_coarsen.py produced by running the UNMODIFIED reference coarsen() (coarsening_utils.py:18-182,
-variation_neighborhoods) with the spectral basis passed through its own (Uk, lk) arguments."""
+variation_neighborhoods) with the spectral basis passed through its own (Uk, lk) arguments.
+(The file name sorts last on purpose: the driver runs the GPU suite with -x, and this row — the last of SURVEY §8f — must not
+stand in front of the hot path's tests.)"""
 import os
 
 import numpy as np
