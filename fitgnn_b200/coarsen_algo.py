@@ -145,6 +145,55 @@ def _contract(costs, rowptr, col, W_host, deg, A, r):
     return out
 
 
+# ------------------------------------------------------------------------------------------------ edge family
+def _edge_costs(row, col, w, n, A):
+    """contract_variation_edges :483-513 for every edge at once.  The reference builds, per edge, the 2 x 2 Laplacian
+    L = [[2 deg_i - w, -w], [-w, 2 deg_j - w]] and B = (I - 11^T/2) A[[i, j]] = [d/2; -d/2] with d = a_i - a_j, so
+    ||B^T L B||_F = (2 deg_i + 2 deg_j) / 4 * ||d||^2.  Edges = the lower triangle in row-major order (pygsp get_edge_list)."""
+    deg = torch.zeros(n, dtype=F64, device=row.device).index_add_(0, row, w)
+    low = row > col
+    vi, vo, we = row[low], col[low], w[low]
+    d = A[vi] - A[vo]
+    cost = ((2 * deg[vi] - we) + (2 * deg[vo] - we) + 2 * we) / 4 * (d * d).sum(1)
+    return vi, vo, cost
+
+
+def _greedy_matching(vi, vo, rank, n, s_stop):
+    """matching_greedy :931-989 without its sequential scan: an edge is taken by the scan iff it precedes every other live edge
+    at both of its endpoints, so rounds of "take the locally first edges, drop their neighbours" select exactly the scan's
+    edges; the scan's early stop after s_stop selections keeps the s_stop selected edges of smallest rank."""
+    dev = vi.device
+    M = vi.numel()
+    alive = torch.ones(M, dtype=torch.bool, device=dev)
+    matched = torch.zeros(n, dtype=torch.bool, device=dev)
+    sel = torch.zeros(M, dtype=torch.bool, device=dev)
+    while bool(alive.any()):
+        best = torch.full((n,), M, dtype=torch.int64, device=dev)
+        ra = torch.where(alive, rank, torch.full_like(rank, M))
+        best.scatter_reduce_(0, vi, ra, reduce="amin")
+        best.scatter_reduce_(0, vo, ra, reduce="amin")
+        pick = alive & (best[vi] == rank) & (best[vo] == rank)
+        sel |= pick
+        matched[vi[pick]] = True
+        matched[vo[pick]] = True
+        alive &= ~(matched[vi] | matched[vo])
+    idx = torch.nonzero(sel).view(-1)
+    idx = idx[torch.argsort(rank[idx])][:s_stop]
+    return idx
+
+
+def _contract_edges(row, col, w, n, A, r):
+    vi, vo, cost = _edge_costs(row, col, w, n, A)
+    # the reference orders the edges with np.argsort(-weights), weights = -cost (numpy's default sort): the same call, on the host
+    order = np.argsort(-(-cost.cpu().numpy()))
+    rank = torch.empty(order.size, dtype=torch.int64)
+    rank[torch.as_tensor(order)] = torch.arange(order.size)
+    s_stop = n - int(np.floor((1 - r) * n))  # the scan stops once n - s <= (1 - r) n
+    idx = _greedy_matching(vi, vo, rank.to(vi.device), n, max(s_stop, 1))
+    pi, pj = vi[idx].cpu().numpy(), vo[idx].cpu().numpy()
+    return [np.array([a, b]) for a, b in zip(pi, pj)]  # [kept row (the larger id), contracted node] (:212-254)
+
+
 # ------------------------------------------------------------------------------------------------ spectral basis
 def laplacian_subspace(row, col, w, n, K, tol=1e-5, dense_limit=4096):
     """Smallest-K eigenpairs (lk ascending, Uk) of L = D - W on the device."""
@@ -190,8 +239,11 @@ def laplacian_subspace(row, col, w, n, K, tol=1e-5, dense_limit=4096):
 
 
 # ------------------------------------------------------------------------------------------------ driver
-def _coarsen(edge_index, n, r=0.5, K=10, Uk=None, lk=None, max_levels=10, max_level_r=0.99) -> Coarsening:
-    """coarsen :18-182 on whatever device edge_index lives on (the public entry below insists on CUDA)."""
+def _coarsen(edge_index, n, r=0.5, K=10, Uk=None, lk=None, max_levels=10, max_level_r=0.99,
+             method="variation_neighborhoods") -> Coarsening:
+    """coarsen :18-182 on whatever device edge_index lives on (the public entries below insist on CUDA)."""
+    if method not in ("variation_neighborhoods", "variation_edges"):
+        raise ValueError(f"coarsen: method {method!r} is not built (variation_neighborhoods, variation_edges)")
     dev = edge_index.device
     row0, col0 = edge_index[0].long(), edge_index[1].long()
     if bool((row0 == col0).any()):
@@ -201,39 +253,44 @@ def _coarsen(edge_index, n, r=0.5, K=10, Uk=None, lk=None, max_levels=10, max_le
     n_cur, n_target = n, np.ceil((1 - r) * n)
     if Uk is None or lk is None or len(lk) < K:
         lk, Uk = laplacian_subspace(row, col, w, n, K)
-    lk = torch.as_tensor(lk, dtype=F64, device=dev).clone()
-    Uk = torch.as_tensor(Uk, dtype=F64, device=dev)
+    # The n x K basis B and everything derived from it stay on the HOST in numpy, with the reference's own expressions: the
+    # level >= 2 rule below (:98-103) feeds a K x K matrix to numpy's general `eig` and uses the eigenvalues IN THE ORDER THEY
+    # COME BACK, which flips under perturbations of the last bit — so B^T L B has to be formed by the very same scipy / BLAS
+    # calls, not by a device reduction whose summation order differs (measured: one of eleven fixtures flipped).  This is
+    # O(nnz K) work per level; the O(sum deg^2 K^2) candidate costs stay on the device.
+    import scipy.sparse as sp
+    lk = np.array(lk.cpu().numpy() if torch.is_tensor(lk) else lk, dtype=np.float64)
+    Uk = np.asarray(Uk.cpu().numpy() if torch.is_tensor(Uk) else Uk, dtype=np.float64)
     mask = lk < 1e-10                                   # :78-83
     lk[mask] = 1
-    lsinv = lk ** -0.5
+    lsinv = lk ** (-0.5)
     lsinv[mask] = 0
-    B = Uk[:, :K] * lsinv[:K][None, :]
+    B = Uk[:, :K] @ np.diag(lsinv[:K])
     part = torch.arange(n, device=dev)
     cweight = torch.ones(n, dtype=F64, device=dev)
     levels = 0
     for level in range(1, max_levels + 1):
         r_cur = float(np.clip(1 - n_target / n_cur, 0.0, max_level_r))
+        W_host = sp.csr_matrix((w.cpu().numpy(), col.cpu().numpy(), rowptr.cpu().numpy()), shape=(n_cur, n_cur))
         if level == 1:
-            A = B
+            A_host = B
         else:                                           # :97-103
-            deg = torch.zeros(n_cur, dtype=F64, device=dev).index_add_(0, row, w)
-            LB = deg[:, None] * B - torch.zeros_like(B).index_add_(0, row, w[:, None] * B[col])
-            # Reference quirk (:98-103): `A = B @ diag(d^-1/2) @ V` scales COLUMN j of B by the j-th eigenvalue in the order
-            # numpy's general (non-symmetric) eig happens to return them — not B V D^-1/2 — so the result depends on that
-            # order.  The K x K matrix goes through the very same routine on the host (K = 10: nothing to parallelise).
-            d, V = np.linalg.eig((B.T @ LB).cpu().numpy())
-            d, V = np.real(d), np.real(V)
+            # Reference quirk: `A = B @ diag(d^-1/2) @ V` scales COLUMN j of B by the j-th eigenvalue in the order numpy's
+            # general (non-symmetric) eig happens to return them — not B V D^-1/2 — so the result depends on that order.
+            L = (sp.diags(np.ravel(W_host.sum(axis=0)), 0) - W_host).tocsc()
+            d, V = np.linalg.eig(B.T @ L.dot(B))
             zero = d == 0
             d[zero] = 1
             dis = d ** (-1 / 2)
             dis[zero] = 0
-            A = (B * torch.as_tensor(dis, dtype=F64, device=dev)[None, :]) @ torch.as_tensor(V, dtype=F64, device=dev)
-        costs, deg = _neighbourhood_costs(row, col, w, rowptr, n_cur, A)
-        # the sequential contraction, on the host over the device-computed costs
-        rp, cl = rowptr.cpu().numpy(), col.cpu().numpy()
-        import scipy.sparse as sp
-        W_host = sp.csr_matrix((w.cpu().numpy(), cl, rp), shape=(n_cur, n_cur))
-        sets = _contract(costs.cpu().numpy(), rp, cl, W_host, deg.cpu().numpy(), A.cpu().numpy(), r_cur)
+            A_host = B @ np.diag(dis) @ V
+        A = torch.as_tensor(np.ascontiguousarray(np.real(A_host)), dtype=F64, device=dev)
+        if method == "variation_edges":
+            sets = _contract_edges(row, col, w, n_cur, A, r_cur)
+        else:
+            costs, deg = _neighbourhood_costs(row, col, w, rowptr, n_cur, A)
+            # the sequential contraction, on the host over the device-computed costs
+            sets = _contract(costs.cpu().numpy(), W_host.indptr, W_host.indices, W_host, deg.cpu().numpy(), A.cpu().numpy(), r_cur)
         levels += 1
         n_next = n_cur - sum(len(s) - 1 for s in sets)
         if n_cur - n_next <= 2:                         # :131-135
@@ -249,7 +306,9 @@ def _coarsen(edge_index, n, r=0.5, K=10, Uk=None, lk=None, max_levels=10, max_le
         lvl_scale = torch.as_tensor(scale, dtype=F64, device=dev)
         cweight = lvl_scale[part] * cweight             # C = iC.dot(C) :136
         part = lvl_part[part]
-        B = torch.zeros(n_next, B.shape[1], dtype=F64, device=dev).index_add_(0, lvl_part, lvl_scale[:, None] * B)
+        Bn = np.zeros((n_next, B.shape[1]))
+        np.add.at(Bn, np.searchsorted(kept, rep), scale[:, None] * B)  # B <- iC.dot(B), accumulated in node order like scipy's csc product
+        B = Bn
         row, col, w, rowptr = _project_graph(row0, col0, part, n_next)  # :138-139 (composed partition, original edges)
         n_cur = n_next
         if n_cur <= n_target:
@@ -264,9 +323,16 @@ def variation_neighborhoods(edge_index: torch.Tensor, n: int, r: float = 0.5, K:
     """`coarsen(G, K, r, method='variation_neighborhoods', Uk=, lk=)` (coarsening_utils.py:18) for ONE connected component
     given as a CUDA edge_index [2, E] (both directions, no self loops).  Returns the partition in the form the pack builders
     take (`part`, `cweight` = C.indices / C.data) plus the coarsened graph."""
+    return coarsen(edge_index, n, r, K, Uk, lk, max_levels, "variation_neighborhoods")
+
+
+def coarsen(edge_index: torch.Tensor, n: int, r: float = 0.5, K: int = 10, Uk=None, lk=None, max_levels: int = 10,
+            method: str = "variation_neighborhoods") -> Coarsening:
+    """`coarsen(G, K, r, method=..., Uk=, lk=)` (coarsening_utils.py:18) for the methods 'variation_neighborhoods' and
+    'variation_edges' (edge costs in closed form for all edges at once, the greedy matching as parallel rounds on the device)."""
     if not edge_index.is_cuda:
         raise ValueError("fitgnn_b200 runs on CUDA tensors only (there is no CPU path)")
-    return _coarsen(edge_index, n, r, K, Uk, lk, max_levels)
+    return _coarsen(edge_index, n, r, K, Uk, lk, max_levels, method=method)
 
 
 def connected_components(edge_index: torch.Tensor, n: int) -> torch.Tensor:

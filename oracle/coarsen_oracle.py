@@ -1,9 +1,15 @@
 """CPU restatement of the reference's multilevel local-variation coarsening — TEST INFRASTRUCTURE, not product code (only
 tests/ may import it).  Follows /root/reference/graph_coarsening/coarsening_utils.py:
 
-    coarsen                      :18-182   (method 'variation_neighborhoods', the reference's default, utils.py:159)
+    coarsen                      :18-182   (methods 'variation_neighborhoods' — the reference's default, utils.py:159 —
+                                            and 'variation_edges')
     contract_variation_linear    :530-650  (candidate family = closed neighbourhoods :583-588, cost :554-560, the sequential
                                             contraction over a SortedList :606-648)
+    contract_variation_edges     :483-527  (edge costs)
+    matching_greedy              :931-989  (one pass over the edges in np.argsort(-weights) order, numpy's default sort)
+('heavy_edge', :689-696, is NOT restated: with the scipy / numpy of this image `np.max(G.W, 0)` on pygsp's lil matrix returns the
+matrix itself, so `wmax` becomes row 0 of W + 1e-5 instead of the column maxima — an accident of the installed versions, nothing
+to pin parity on.)
     get_coarsening_matrix        :212-254, coarsen_matrix :201-205, graph_utils.zero_diag :79-87
 
 plain numpy / scipy, same operations in the same order, so that the costs — and with them the contraction order — come out
@@ -74,6 +80,49 @@ def contract_variation_neighborhoods(W, A, r):
     return out
 
 
+def edge_list(W):
+    """pygsp Graph.get_edge_list: the lower triangle's entries in row-major order (v_in > v_out) and their weights."""
+    T = sp.tril(sp.csr_matrix(W)).tocoo()
+    return T.row, T.col, T.data
+
+
+def variation_edge_costs(W, A):
+    """:483-513 — cost of contracting one edge: ||B^T L B||_F with the 2 x 2 Laplacian of the pair and B = centred rows of A."""
+    deg = np.ravel(W.sum(axis=0))
+    vi, vo, ww = edge_list(W)
+    ones = np.ones(2)
+    Pibot = np.eye(2) - np.outer(ones, ones) / 2
+    out = np.empty(len(vi))
+    for e in range(len(vi)):
+        edge, w = np.array([vi[e], vo[e]]).astype(np.int32), ww[e]
+        deg_new = 2 * deg[edge] - w
+        L = np.array([[deg_new[0], -w], [-w, deg_new[1]]])
+        B = Pibot @ A[edge, :]
+        out[e] = np.linalg.norm(B.T @ L @ B)
+    return out
+
+
+def matching_greedy(W, weights, r):
+    """:931-989 — heaviest edge first (np.argsort(-weights), default sort), skip edges with a matched endpoint, stop once
+    n <= (1 - r) N."""
+    N = W.shape[0]
+    vi, vo, _ = edge_list(W)
+    idx = np.argsort(-weights)
+    marked = np.zeros(N, dtype=bool)
+    n, n_target = N, (1 - r) * N
+    out = []
+    for e in idx:
+        i, j = vi[e], vo[e]
+        if marked[i] or marked[j]:
+            continue
+        marked[[i, j]] = True
+        n -= 1
+        out.append(np.array([i, j]))
+        if n <= n_target:
+            break
+    return out
+
+
 def coarsening_matrix(N, sets):
     """:212-254 — row of a contracted set = its first (smallest) member, entries 1/sqrt(|set|); other rows identity."""
     C = sp.eye(N, format="lil")
@@ -96,7 +145,7 @@ def coarsen_weights(W, iC):
     return sp.csr_matrix((Wc + Wc.T) / 2)
 
 
-def coarsen(W, Uk, lk, K=10, r=0.5, max_levels=10, max_level_r=0.99):
+def coarsen(W, Uk, lk, K=10, r=0.5, max_levels=10, max_level_r=0.99, method="variation_neighborhoods"):
     """:18-182.  Returns (C csc [n_c, N], Wc csr, number of levels)."""
     r = np.clip(r, 0, 0.999)
     N = W.shape[0]
@@ -108,19 +157,24 @@ def coarsen(W, Uk, lk, K=10, r=0.5, max_levels=10, max_level_r=0.99):
     for level in range(1, max_levels + 1):
         Wl = Wc
         r_cur = np.clip(1 - n_target / n, 0.0, max_level_r)
-        if level == 1:
-            B = spectral_matrix(Uk, lk, K)
-            A = B
-        else:
-            B = iC.dot(B)
-            L = (sp.diags(np.ravel(Wl.sum(axis=0)), 0) - Wl).tocsc()
-            d, V = np.linalg.eig(B.T @ L.dot(B))
-            mask = d == 0
-            d[mask] = 1
-            dinvsqrt = d ** (-1 / 2)
-            dinvsqrt[mask] = 0
-            A = B @ np.diag(dinvsqrt) @ V
-        sets = contract_variation_neighborhoods(Wl, A, r_cur)
+        assert method in ("variation_neighborhoods", "variation_edges")
+        if True:
+            if level == 1:
+                B = spectral_matrix(Uk, lk, K)
+                A = B
+            else:
+                B = iC.dot(B)
+                L = (sp.diags(np.ravel(Wl.sum(axis=0)), 0) - Wl).tocsc()
+                d, V = np.linalg.eig(B.T @ L.dot(B))
+                mask = d == 0
+                d[mask] = 1
+                dinvsqrt = d ** (-1 / 2)
+                dinvsqrt[mask] = 0
+                A = B @ np.diag(dinvsqrt) @ V
+            if method == "variation_edges":  # :105-108, :523-525 (algorithm 'greedy': matching_greedy on -(-cost))
+                sets = matching_greedy(Wl, -variation_edge_costs(Wl, A), r_cur)
+            else:
+                sets = contract_variation_neighborhoods(Wl, A, r_cur)
         iC = coarsening_matrix(Wl.shape[0], sets)
         levels += 1
         if iC.shape[1] - iC.shape[0] <= 2:

@@ -76,7 +76,8 @@ class Graph:
 
     def get_edge_list(self):
         v_in, v_out = sp.tril(self.W).nonzero()
-        weights = np.asarray(self.W[v_in, v_out]).squeeze()
+        weights = self.W[v_in, v_out]
+        weights = (weights.toarray() if sp.issparse(weights) else np.asarray(weights)).squeeze()  # pygsp: .toarray().squeeze()
         return v_in, v_out, weights
 
     def subgraph(self, ind):

@@ -1,6 +1,6 @@
 """The coarsening algorithm: oracle and product against tests/golden/coarsen_algo.npz, which
 tests/golden/make_golden_coarsen.py produced by running the UNMODIFIED reference coarsen() (coarsening_utils.py:18-182,
-variation_neighborhoods) with the spectral basis passed through its own (Uk, lk) arguments.
+variation_neighborhoods and variation_edges) with the spectral basis passed through its own (Uk, lk) arguments.
 (The file name sorts last on purpose: the driver runs the GPU suite with -x, and this row — the last of SURVEY §8f — must not
 stand in front of the hot path's tests.)"""
 import os
@@ -13,7 +13,8 @@ import torch
 from oracle import coarsen_oracle as co
 
 GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "coarsen_algo.npz"))
-CASES = [str(c) for c in GOLD["cases"]]
+CASES = [(str(c), "variation_neighborhoods") for c in GOLD["cases"]] + \
+        [(str(c), str(m)) for c, m in zip(GOLD["edge_cases"], GOLD["edge_methods"])]
 K = int(GOLD["K"])
 
 
@@ -22,11 +23,11 @@ def case(name):
     return n, r, GOLD[f"{name}_row"], GOLD[f"{name}_col"], GOLD[f"{name}_Uk"], GOLD[f"{name}_lk"]
 
 
-@pytest.mark.parametrize("name", CASES)
-def test_oracle_reproduces_the_reference_coarsening_bit_exactly(name):
+@pytest.mark.parametrize("name,method", CASES)
+def test_oracle_reproduces_the_reference_coarsening_bit_exactly(name, method):
     n, r, row, col, Uk, lk = case(name)
     W = sp.coo_matrix((np.ones(len(row)), (row, col)), shape=(n, n)).tocsr()
-    C, Wc, levels = co.coarsen(W, Uk, lk, K=K, r=r)
+    C, Wc, levels = co.coarsen(W, Uk, lk, K=K, r=r, method=method)
     assert C.shape[0] == int(GOLD[f"{name}_C_rows"]) and levels == int(GOLD[f"{name}_levels"])
     assert np.array_equal(C.indices, GOLD[f"{name}_C_indices"]) and np.array_equal(C.data, GOLD[f"{name}_C_data"])
     want = sp.coo_matrix((GOLD[f"{name}_Wc_val"], (GOLD[f"{name}_Wc_row"], GOLD[f"{name}_Wc_col"])), shape=Wc.shape).tocsr()
@@ -42,12 +43,37 @@ def check_product(res, name):
     assert np.array_equal(res.gc_cnt.cpu().numpy(), GOLD[f"{name}_Wc_val"])
 
 
-@pytest.mark.parametrize("name", CASES)
-def test_product_core_on_cpu_tensors_matches_the_reference(name):
+@pytest.mark.parametrize("name,method", CASES)
+def test_product_core_on_cpu_tensors_matches_the_reference(name, method):
     """the device-agnostic core (fitgnn_b200.coarsen_algo._coarsen) on CPU tensors: same tensor code the GPU runs"""
     from fitgnn_b200 import coarsen_algo as ca
     n, r, row, col, Uk, lk = case(name)
-    check_product(ca._coarsen(torch.tensor(np.stack([row, col])), n, r, K, Uk, lk), name)
+    check_product(ca._coarsen(torch.tensor(np.stack([row, col])), n, r, K, Uk, lk, method=method), name)
+
+
+def test_edge_costs_and_parallel_matching_equal_the_reference_scan():
+    """variation_edges: the closed-form costs of all edges == the reference's per-edge 2 x 2 formula (:483-513), and the
+    parallel rounds of the greedy matching select exactly what its sequential scan (:931-989) selects, for every stop count."""
+    from fitgnn_b200 import coarsen_algo as ca
+    n, r, row, col, Uk, lk = case("ve_n400_d10_r50")
+    W = sp.coo_matrix((np.ones(len(row)), (row, col)), shape=(n, n)).tocsr()
+    A = co.spectral_matrix(Uk, lk, K)
+    want = co.variation_edge_costs(W, A)
+    r_, c_, w_, _ = ca._coalesce(torch.tensor(row), torch.tensor(col), torch.ones(len(row), dtype=torch.float64), n)
+    vi, vo, got = ca._edge_costs(r_, c_, w_, n, torch.tensor(A))
+    evi, evo, _ = co.edge_list(W)
+    assert np.array_equal(vi.numpy(), evi) and np.array_equal(vo.numpy(), evo)
+    assert np.abs(got.numpy() - want).max() <= 1e-13 * np.abs(want).max()
+    for rr in (0.05, 0.3, 0.45, 0.99):
+        seq = co.matching_greedy(W, -want, rr)
+        par = ca._contract_edges(r_, c_, w_, n, torch.tensor(A), rr)
+        assert len(seq) == len(par) and np.array_equal(np.array(seq), np.array(par))
+
+
+def test_unbuilt_methods_are_refused():
+    from fitgnn_b200 import coarsen_algo as ca
+    with pytest.raises(ValueError, match="not built"):
+        ca._coarsen(torch.tensor([[0, 1], [1, 0]]), 2, 0.5, method="heavy_edge")
 
 
 def test_public_entry_refuses_cpu_tensors_and_self_loops():
@@ -127,10 +153,10 @@ def test_coarsen_partition_orders_components_like_the_reference():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", CASES)
-def test_product_on_cuda_matches_the_reference(name):
+@pytest.mark.parametrize("name,method", CASES)
+def test_product_on_cuda_matches_the_reference(name, method):
     from fitgnn_b200 import coarsen_algo as ca
     n, r, row, col, Uk, lk = case(name)
-    res = ca.variation_neighborhoods(torch.tensor(np.stack([row, col]), device="cuda"), n, r, K, Uk, lk)
+    res = ca.coarsen(torch.tensor(np.stack([row, col]), device="cuda"), n, r, K, Uk, lk, method=method)
     assert res.part.is_cuda
     check_product(res, name)
