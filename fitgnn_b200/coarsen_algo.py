@@ -1,25 +1,30 @@
-"""The coarsening ALGORITHM itself: multilevel local-variation coarsening with the neighbourhood
-candidate family — /root/reference/graph_coarsening/coarsening_utils.py `coarsen` :18-182 (method
-'variation_neighborhoods', the reference's default, utils.py:159) with `contract_variation_linear` :530-650,
-`get_coarsening_matrix` :212-254 and `coarsen_matrix` :201-205.
+"""The coarsening ALGORITHM itself: multilevel local-variation coarsening —
+/root/reference/graph_coarsening/coarsening_utils.py `coarsen` :18-182 for the methods 'variation_neighborhoods' (the
+reference's default, utils.py:159; `contract_variation_linear` :530-650) and 'variation_edges' (`contract_variation_edges`
+:483-527 + `matching_greedy` :931-989), with `get_coarsening_matrix` :212-254 and `coarsen_matrix` :201-205.
 
-What runs where.  The reference spends its time in a Python loop that builds, for each of the N closed neighbourhoods, a dense
-induced Laplacian and a dense projector and multiplies them (:554-560).  Here every level's parallel work is tensor code on
-the device, in fp64:
+What runs where.  The reference spends its time in Python loops that build, for each of the N closed neighbourhoods (or each
+edge), a dense induced Laplacian and a dense projector and multiply them (:554-560, :492-498).  Here every level's parallel
+work is fp64 tensor code on the device:
   * the spectral basis (when the caller does not pass one): smallest-K eigenpairs of the level-1 Laplacian, dense `eigh` up
     to 4096 nodes, Lanczos with full re-orthogonalisation on `offset*I - L` (the reference's own shift, :84-89) beyond;
-  * the costs of ALL candidate sets at once: membership pairs (set, node), the induced edges of every set by a sorted-key
-    lookup (wedges (i, u, v) with v in N[i]), `y = L_S b` by segment sums and `M_i = sum_u b_u y_u^T` — never a dense
-    nc x nc matrix;
-  * the level's coarsened graph `Wc = P W P^T` (zero diagonal; integer edge counts) from the ORIGINAL edge list through the
-    composed partition, and the basis update `B <- iC B`, `A = B diag(d^-1/2) V` (:97-103).
-The contraction itself (:606-648) pops candidates in cost order, marks nodes and re-inserts shrunk sets with a new cost —
-sequential by construction, as is its result; it runs on the host over the device-computed costs (a heap keyed
-(cost, insertion number) pops in the order of the reference's SortedList) and re-costs the few shrunk sets there.
+  * the costs of ALL candidate sets at once — neighbourhoods: membership pairs (set, node), the induced edges of every set by a
+    sorted-key lookup (wedges (i, u, v) with v in N[i]), `y = L_S b` by segment sums and `M_i = sum_u b_u y_u^T`, never a
+    dense nc x nc matrix; edges: a closed form of the 2 x 2 problem;
+  * the greedy edge matching as exact parallel rounds (an edge is taken iff it precedes every live edge at both endpoints);
+  * each level's coarsened graph `Wc = P W P^T` (zero diagonal; integer edge counts) from the ORIGINAL edge list through the
+    composed partition.
+On the host: the neighbourhood contraction itself (:606-648) — it pops candidates in cost order, marks nodes and re-inserts
+shrunk sets with a new cost: sequential by construction, as is its result (a heap keyed (cost, insertion number) pops in the
+order of the reference's SortedList; the few shrunk sets are re-costed there) — and the n x K basis chain `B <- iC B`,
+`A = B diag(d^-1/2) V` of levels >= 2 (:97-103), formed with the reference's own numpy / scipy expressions: that rule uses the
+eigenvalues of a K x K matrix in the order numpy's general `eig` returns them, which flips with the last bit of its input.
 
 Parity: given the same (Uk, lk) the partition, the C weights and Wc equal the reference's bit for bit on
-tests/golden/coarsen_algo.npz (6 cases, up to 3 levels); the reference's own eigsh starts from a random vector, so two calls
-of the reference itself disagree on up to 85 % of the entries (recorded in the fixture) — which is why the basis is an argument.
+tests/golden/coarsen_algo.npz (11 cases, both methods, up to 3 levels), on CPU tensors and on CUDA; the reference's own eigsh
+starts from a random vector, so two calls of the reference itself disagree on up to 85 % of the entries (recorded in the
+fixture) — which is why the basis is an argument.  Not built: variation_cliques, heavy_edge (in this image's scipy / numpy the
+reference's `np.max(G.W, 0)` on a lil matrix returns the matrix itself — nothing to pin), algebraic_JC, affinity_GS, kron.
 """
 from __future__ import annotations
 
