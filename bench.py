@@ -605,6 +605,13 @@ def mode_coarsen(args, fg, device):
                 blk["parity"] = {"partition_equal": bool(np.array_equal(Cm.indices, res.part.cpu().numpy())),
                                  "cweight_equal": bool(np.array_equal(Cm.data, res.cweight.cpu().numpy())), "levels_equal": lv == res.levels,
                                  "against": "oracle CPU path (pinned bit-exactly to the reference on tests/golden/coarsen_algo.npz), same (Uk, lk)"}
+            if name == "pubmed_shaped":  # the edge family: closed-form costs of all edges + the greedy matching in parallel rounds
+                core_e = ca.coarsen if device.type == "cuda" else ca._coarsen
+                core_e(eic, nc, r, 10, Uk, lk, method="variation_edges")
+                sync(); t0 = time.perf_counter()
+                res_e = core_e(eic, nc, r, 10, Uk, lk, method="variation_edges")
+                sync()
+                blk["variation_edges"] = {"ms": (time.perf_counter() - t0) * 1e3, "supernodes": res_e.k, "levels": res_e.levels}
             out[name] = blk
         return out
     except Exception as e:  # noqa: BLE001 — this block must not cost the bench line
