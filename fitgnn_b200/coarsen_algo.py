@@ -361,30 +361,46 @@ def coarsen_partition(edge_index: torch.Tensor, n: int, r: float = 0.5, K: int =
     component.  Returns coarsen.Partition (what build_pack / project take).  `bases`: optional {component index: (Uk, lk)}."""
     from .coarsen import Partition
     core = variation_neighborhoods if edge_index.is_cuda else _coarsen
+    dev = edge_index.device
     label = connected_components(edge_index, n)
     roots, inv, sizes = torch.unique(label, return_inverse=True, return_counts=True)  # roots ascend = smallest-member order
-    order = torch.sort(sizes, descending=True, stable=True).indices
-    part = torch.full((n,), -1, dtype=torch.int64, device=edge_index.device)
-    cw = torch.ones(n, dtype=F64, device=edge_index.device)
-    comp_of_sub, offs, base = [], [0], 0
+    order = torch.sort(sizes, descending=True, stable=True).indices                   # candidate order (:146)
+    pos_of_comp = torch.empty_like(order)
+    pos_of_comp[order] = torch.arange(order.numel(), device=dev)
+    # nodes grouped by candidate position, ascending inside a component (= H.info['orig_idx']); edges grouped the same way
+    node_order = torch.argsort(pos_of_comp[inv] * n + torch.arange(n, device=dev))
+    sizes_sorted = sizes[order]
+    node_off = torch.zeros(order.numel() + 1, dtype=torch.int64, device=dev)
+    node_off[1:] = torch.cumsum(sizes_sorted, 0)
     row, col = edge_index[0].long(), edge_index[1].long()
-    for ci, c in enumerate(order.tolist()):
-        nodes = torch.nonzero(inv == c).view(-1)  # ascending = H.info['orig_idx']
-        if nodes.numel() == 1:
-            part[nodes] = base
-            kc = 1
-        else:
-            local = torch.full((n,), -1, dtype=torch.int64, device=edge_index.device)
-            local[nodes] = torch.arange(nodes.numel(), device=edge_index.device)
-            sel = inv[row] == c
-            ei_c = torch.stack([local[row[sel]], local[col[sel]]])
-            Uk, lk = (bases or {}).get(ci, (None, None))
-            res = core(ei_c, int(nodes.numel()), r, K, Uk, lk)
-            part[nodes] = base + res.part
-            cw[nodes] = res.cweight
-            kc = res.k
-        comp_of_sub.extend([ci] * kc)
-        base += kc
+    local = torch.empty(n, dtype=torch.int64, device=dev)
+    local[node_order] = torch.arange(n, device=dev) - node_off[pos_of_comp[inv[node_order]]]
+    epos = pos_of_comp[inv[row]]
+    eorder = torch.argsort(epos, stable=True)
+    edge_off = torch.zeros(order.numel() + 1, dtype=torch.int64, device=dev)
+    edge_off[1:] = torch.cumsum(torch.bincount(epos, minlength=order.numel()), 0)
+    part = torch.full((n,), -1, dtype=torch.int64, device=dev)
+    cw = torch.ones(n, dtype=F64, device=dev)
+    n_multi = int((sizes_sorted > 1).sum())  # size-descending: the single-node components come last
+    comp_of_sub, offs, base = [], [0], 0
+    node_off_h, edge_off_h = node_off.cpu().numpy(), edge_off.cpu().numpy()
+    for ci in range(n_multi):
+        nodes = node_order[node_off_h[ci]: node_off_h[ci + 1]]
+        es = eorder[edge_off_h[ci]: edge_off_h[ci + 1]]
+        ei_c = torch.stack([local[row[es]], local[col[es]]])
+        Uk, lk = (bases or {}).get(ci, (None, None))
+        res = core(ei_c, int(nodes.numel()), r, K, Uk, lk)
+        part[nodes] = base + res.part
+        cw[nodes] = res.cweight
+        comp_of_sub.extend([ci] * res.k)
+        base += res.k
         offs.append(base)
+    n_single = order.numel() - n_multi  # single nodes pass through (:352-368), one supernode each, in candidate order
+    if n_single:
+        singles = node_order[node_off_h[n_multi]:]
+        part[singles] = base + torch.arange(n_single, device=dev)
+        comp_of_sub.extend(range(n_multi, n_multi + n_single))
+        offs.extend(range(base + 1, base + n_single + 1))
+        base += n_single
     return Partition(part.to(torch.int32).cpu().numpy(), cw.cpu().numpy(), base, np.asarray(comp_of_sub, dtype=np.int32),
                      np.asarray(offs, dtype=np.int64))

@@ -152,6 +152,48 @@ def test_coarsen_partition_orders_components_like_the_reference():
         assert len(set(lab[p.part == s])) == 1
 
 
+def test_coarsen_partition_equals_a_plain_component_loop():
+    """the vectorised grouping of coarsen_partition against the obvious loop: scipy components, candidate order as the
+    reference builds it (extract_components order = smallest member, then a stable size-descending sort, utils.py:144-146),
+    one core call per component, single nodes passed through; 300 isolated nodes make the single-node tail non-trivial"""
+    import scipy.sparse.csgraph as csg
+    from fitgnn_b200 import coarsen_algo as ca
+    from tests.golden.make_golden_coarsen_graph import synth_graph
+    blocks, off = [], 0
+    for seed, size in ((1, 90), (2, 35), (3, 35), (4, 12), (5, 2)):
+        _, e = synth_graph(seed, size)
+        blocks.append(e + off)
+        off += size
+    n = off + 300
+    perm = np.random.default_rng(1).permutation(n)
+    ei = perm[np.concatenate(blocks, 1)]
+    got = ca.coarsen_partition(torch.tensor(ei), n, 0.4, K)
+    A = sp.coo_matrix((np.ones(ei.shape[1]), (ei[0], ei[1])), shape=(n, n)).tocsr()
+    _, lab = csg.connected_components(A, directed=False)
+    comps = {}
+    for v in range(n):
+        comps.setdefault(lab[v], []).append(v)
+    cand = sorted(sorted(comps.values(), key=lambda c: c[0]), key=len, reverse=True)
+    part = np.full(n, -1)
+    cw = np.ones(n)
+    base = 0
+    for comp in cand:
+        comp = np.array(comp)
+        if len(comp) == 1:
+            part[comp] = base
+            base += 1
+            continue
+        loc = np.full(n, -1)
+        loc[comp] = np.arange(len(comp))
+        sel = np.isin(ei[0], comp)
+        res = ca._coarsen(torch.tensor(loc[ei[:, sel]]), len(comp), 0.4, K)
+        part[comp] = base + res.part.numpy()
+        cw[comp] = res.cweight.numpy()
+        base += res.k
+    assert got.k == base and np.array_equal(got.part, part) and np.array_equal(got.cweight, cw)
+    assert got.sub_offset[-1] == base and len(got.comp_of_sub) == base and len(got.sub_offset) == len(cand) + 1
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,method", CASES)
 def test_product_on_cuda_matches_the_reference(name, method):
