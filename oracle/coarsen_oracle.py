@@ -2,7 +2,7 @@
 tests/ may import it).  Follows /root/reference/graph_coarsening/coarsening_utils.py:
 
     coarsen                      :18-182   (methods 'variation_neighborhoods' — the reference's default, utils.py:159 —
-                                            and 'variation_edges')
+                                            'variation_cliques' and 'variation_edges')
     contract_variation_linear    :530-650  (candidate family = closed neighbourhoods :583-588, cost :554-560, the sequential
                                             contraction over a SortedList :606-648)
     contract_variation_edges     :483-527  (edge costs)
@@ -42,8 +42,10 @@ def subgraph_cost(W, deg, A, nodes):
     return np.linalg.norm(B.T @ L @ B) / (nc - 1)
 
 
-def contract_variation_neighborhoods(W, A, r):
-    """:530-650 with mode 'neighborhood'.  W: CSR weights of the current level; returns the list of contraction sets.
+def contract_variation_neighborhoods(W, A, r, mode="neighborhood"):
+    """:530-650 with mode 'neighborhood' (family = closed neighbourhoods, :583-588) or 'cliques' (family = the maximal cliques
+    networkx enumerates, node order inside a clique as it yields them, :590-595).  W: CSR weights of the current level;
+    returns the list of contraction sets.
     The reference keeps its candidates in a SortedList ordered by cost only: equal costs keep insertion order and pop(0) takes
     the oldest — a heap keyed (cost, insertion number) pops in exactly that order."""
     N = W.shape[0]
@@ -52,8 +54,12 @@ def contract_variation_neighborhoods(W, A, r):
     Wb.sort_indices()
     Wl = W.tolil()  # the reference slices a lil matrix (:539); values and summation order equal the CSR's
     heap, seq = [], 0
-    for i in range(N):
-        s = Wb.indices[Wb.indptr[i]: Wb.indptr[i + 1]].copy()
+    if mode == "cliques":
+        import networkx as nx
+        family = [np.array(c) for c in nx.find_cliques(nx.from_scipy_sparse_array(Wl))]
+    else:
+        family = [Wb.indices[Wb.indptr[i]: Wb.indptr[i + 1]].copy() for i in range(N)]
+    for s in family:
         heap.append((subgraph_cost(Wl, deg, A, s), seq, s))
         seq += 1
     heapq.heapify(heap)
@@ -157,7 +163,7 @@ def coarsen(W, Uk, lk, K=10, r=0.5, max_levels=10, max_level_r=0.99, method="var
     for level in range(1, max_levels + 1):
         Wl = Wc
         r_cur = np.clip(1 - n_target / n, 0.0, max_level_r)
-        assert method in ("variation_neighborhoods", "variation_edges")
+        assert method in ("variation_neighborhoods", "variation_cliques", "variation_edges")
         if True:
             if level == 1:
                 B = spectral_matrix(Uk, lk, K)
@@ -174,7 +180,7 @@ def coarsen(W, Uk, lk, K=10, r=0.5, max_levels=10, max_level_r=0.99, method="var
             if method == "variation_edges":  # :105-108, :523-525 (algorithm 'greedy': matching_greedy on -(-cost))
                 sets = matching_greedy(Wl, -variation_edge_costs(Wl, A), r_cur)
             else:
-                sets = contract_variation_neighborhoods(Wl, A, r_cur)
+                sets = contract_variation_neighborhoods(Wl, A, r_cur, "cliques" if method == "variation_cliques" else "neighborhood")
         iC = coarsening_matrix(Wl.shape[0], sets)
         levels += 1
         if iC.shape[1] - iC.shape[0] <= 2:

@@ -1,7 +1,7 @@
 """Generates tests/golden/coarsen_algo.npz: the UNMODIFIED reference coarsening algorithm
 (/root/reference/graph_coarsening/coarsening_utils.py: coarsen :18-182 with contract_variation_linear :530-650,
 get_coarsening_matrix :212-254, coarsen_matrix :201-205, graph_utils.zero_diag) run behind oracle/ref_shims.py on seeded
-connected graphs, methods 'variation_neighborhoods' (the reference's default, utils.py:159) and 'variation_edges'
+connected graphs, methods 'variation_neighborhoods' (the reference's default, utils.py:159), 'variation_cliques' and 'variation_edges'
 (contract_variation_edges :483-527, matching_greedy :931-989).
 
 The reference obtains its spectral basis from scipy's eigsh with a RANDOM start vector and tol = 1e-5 (:84-89); the contraction
@@ -35,7 +35,9 @@ CASES = [("n60_r50", 11, 60, 0.5, 4.0), ("n300_r30", 3, 300, 0.3, 4.0), ("n300_r
          ("n800_r60", 5, 800, 0.6, 4.0), ("n800_r90", 5, 800, 0.9, 4.0),
          ("n400_d10_r60", 9, 400, 0.6, 10.0)]  # denser: hundreds of triangles, i.e. induced edges inside the candidate sets
 EDGE_CASES = [("ve_n300_r30", "variation_edges", 3, 300, 0.3, 4.0), ("ve_n300_r60", "variation_edges", 3, 300, 0.6, 4.0),
-              ("ve_n800_r70", "variation_edges", 5, 800, 0.7, 4.0), ("ve_n400_d10_r50", "variation_edges", 9, 400, 0.5, 10.0)]
+              ("ve_n800_r70", "variation_edges", 5, 800, 0.7, 4.0), ("ve_n400_d10_r50", "variation_edges", 9, 400, 0.5, 10.0),
+              ("vc_n300_r40", "variation_cliques", 3, 300, 0.4, 4.0), ("vc_n400_d10_r60", "variation_cliques", 9, 400, 0.6, 10.0),
+              ("vc_n800_r80", "variation_cliques", 5, 800, 0.8, 4.0)]
 
 
 def main():

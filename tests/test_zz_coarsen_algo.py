@@ -1,6 +1,6 @@
 """The coarsening algorithm: oracle and product against tests/golden/coarsen_algo.npz, which
 tests/golden/make_golden_coarsen.py produced by running the UNMODIFIED reference coarsen() (coarsening_utils.py:18-182,
-variation_neighborhoods and variation_edges) with the spectral basis passed through its own (Uk, lk) arguments.
+variation_neighborhoods, variation_cliques and variation_edges) with the spectral basis passed through its own (Uk, lk) arguments.
 (The file name sorts last on purpose: the driver runs the GPU suite with -x, and this row — the last of SURVEY §8f — must not
 stand in front of the hot path's tests.)"""
 import os
@@ -72,8 +72,9 @@ def test_edge_costs_and_parallel_matching_equal_the_reference_scan():
 
 def test_unbuilt_methods_are_refused():
     from fitgnn_b200 import coarsen_algo as ca
-    with pytest.raises(ValueError, match="not built"):
-        ca._coarsen(torch.tensor([[0, 1], [1, 0]]), 2, 0.5, method="heavy_edge")
+    for m in ("heavy_edge", "algebraic_JC", "affinity_GS", "kron"):
+        with pytest.raises(ValueError, match="not built"):
+            ca._coarsen(torch.tensor([[0, 1], [1, 0]]), 2, 0.5, method=m)
 
 
 def test_public_entry_refuses_cpu_tensors_and_self_loops():
@@ -194,8 +195,10 @@ def test_coarsen_partition_equals_a_plain_component_loop():
     assert got.sub_offset[-1] == base and len(got.comp_of_sub) == base and len(got.sub_offset) == len(cand) + 1
 
 
+# (variation_cliques was added after the round's GPU budget was spent: its family comes from networkx on the host and its
+# costs from the same _family_costs tensor code the neighbourhood family runs — verified above on CPU tensors only)
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,method", CASES)
+@pytest.mark.parametrize("name,method", [c for c in CASES if c[1] != "variation_cliques"])
 def test_product_on_cuda_matches_the_reference(name, method):
     from fitgnn_b200 import coarsen_algo as ca
     n, r, row, col, Uk, lk = case(name)
