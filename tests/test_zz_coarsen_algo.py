@@ -205,3 +205,17 @@ def test_product_on_cuda_matches_the_reference(name, method):
     res = ca.coarsen(torch.tensor(np.stack([row, col]), device="cuda"), n, r, K, Uk, lk, method=method)
     assert res.part.is_cuda
     check_product(res, name)
+
+
+def test_bench_coarsen_block_runs_and_agrees_with_the_oracle():
+    """bench.py's modes.coarsen on CPU tensors (the same code path the GPU run takes, minus the device): no error entry, the
+    Cora-shaped partition equals the oracle's with the same basis, both methods report sizes"""
+    import bench
+    import fitgnn_b200 as fg
+    blk = bench.mode_coarsen(None, fg, torch.device("cpu"))
+    assert "error" not in blk, blk
+    par = blk["cora_shaped"]["parity"]
+    assert par["partition_equal"] and par["cweight_equal"] and par["levels_equal"]
+    assert blk["cora_shaped"]["cpu_baseline"]["ms"] > 0 and blk["cora_shaped"]["levels"] >= 1
+    pm = blk["pubmed_shaped"]
+    assert abs(pm["supernodes"] - round(0.5 * pm["nodes"])) <= 2 and pm["variation_edges"]["supernodes"] == pm["supernodes"]
