@@ -8,10 +8,12 @@ Layout written by `save()` /root/reference/main.py:131-172 and read at main.py:2
     node_type  d | e | c  = default / extra_node / cluster_node (cluster_node wins, main.py:117-121, :134-138)
     graph_type full | community                                   (main.py:139-142)
 
-`subgraph_list.pt` and `candidate.pkl` pickle torch_geometric `Data` / pygsp `Graph` objects, so un-pickling needs those
-packages (or stand-ins registered under their module names) — the reader says so instead of failing obscurely.  Everything
-after the un-pickling is duck-typed: a subgraph is anything with `.x / .edge_index / .mask / .orig_idx`, a candidate
-anything with `.info['orig_idx']`, a C matrix anything scipy can convert.
+`subgraph_list.pt` and `candidate.pkl` pickle torch_geometric `Data` / pygsp `Graph` objects.  With those packages installed
+they un-pickle as themselves; without them (`stand_ins=True`, the default when the import fails) the reader substitutes
+state-holding stand-ins for every class of the two packages: a pickled PyG `Data` is `{'_store': GlobalStorage}` whose state
+holds the attribute dict `_mapping` (torch_geometric/data/data.py, storage.py `__getstate__`), a pygsp `Graph` is its
+`__dict__` — enough for everything downstream, which is duck-typed: a subgraph is anything with
+`.x / .edge_index / .mask / .orig_idx`, a candidate anything with `.info['orig_idx']`, a C matrix anything scipy can convert.
 """
 from __future__ import annotations
 
@@ -63,27 +65,102 @@ class ReferenceCache:
         return bool(self.subgraph_list) and isinstance(self.subgraph_list[0], (list, tuple))
 
 
+class _StandIn:
+    """An object of a class whose package is not installed: keeps the pickled state, and answers attribute reads the way a PyG
+    `Data` does — through `_store._mapping` (the GlobalStorage's attribute dict) — or a storage does (`_mapping`)."""
+
+    def __setstate__(self, state):
+        if isinstance(state, tuple) and len(state) == 2 and isinstance(state[1], dict):  # (dict state, slots state)
+            self.__dict__.update(state[0] or {})
+            self.__dict__.update(state[1])
+        elif isinstance(state, dict):
+            self.__dict__.update(state)
+        else:
+            self.__dict__["_state"] = state
+
+    def __getattr__(self, name):
+        d = self.__dict__
+        store = d.get("_store")
+        for mapping in (d.get("_mapping"), store.__dict__.get("_mapping") if store is not None else None):
+            if isinstance(mapping, dict) and name in mapping:
+                return mapping[name]
+        raise AttributeError(name)
+
+    def keys(self):
+        store = self.__dict__.get("_store")
+        m = self.__dict__.get("_mapping") or (store.__dict__.get("_mapping") if store is not None else None) or {}
+        return list(m.keys())
+
+
+_STAND_IN_PACKAGES = ("torch_geometric", "pygsp")
+_stand_in_classes = {}
+
+
+class _StandInUnpickler(pickle.Unpickler):
+    """pickle.Unpickler that resolves classes of the uninstalled reference dependencies to `_StandIn` subclasses."""
+
+    def find_class(self, module, name):
+        try:
+            return super().find_class(module, name)
+        except (ModuleNotFoundError, AttributeError):
+            if module.split(".")[0] not in _STAND_IN_PACKAGES:
+                raise
+            key = (module, name)
+            if key not in _stand_in_classes:
+                _stand_in_classes[key] = type(name, (_StandIn,), {"__module__": module})
+            return _stand_in_classes[key]
+
+
+class _StandInPickle:
+    """the `pickle_module` torch.load takes: Unpickler + load"""
+    __name__ = "fitgnn_b200.cache._StandInPickle"
+    Unpickler = _StandInUnpickler
+
+    @staticmethod
+    def load(f, **kw):
+        return _StandInUnpickler(f, **kw).load()
+
+
+def _have_reference_packages() -> bool:
+    """torch_geometric and pygsp importable (or registered in sys.modules, e.g. by a test's stand-in modules)?"""
+    import importlib.util
+    import sys
+    for p in _STAND_IN_PACKAGES:
+        if p in sys.modules:
+            continue
+        try:
+            if importlib.util.find_spec(p) is None:
+                return False
+        except (ImportError, ValueError):
+            return False
+    return True
+
+
 def _unpickle(path, loader):
     try:
         return loader(path)
     except ModuleNotFoundError as e:
         raise ModuleNotFoundError(
             f"{path} pickles {e.name} objects (torch_geometric Data / pygsp Graph): un-pickling the reference's cache needs "
-            f"that package (or a stand-in registered under its module name) in this environment") from e
+            f"that package, or load_reference_cache(..., stand_ins=True)") from e
 
 
 def load_reference_cache(root, dataset, coarsening_method, coarsening_ratio, extra_node=False, cluster_node=False,
-                         use_community_detection=False) -> ReferenceCache:
-    """Read whatever of the five files exists (subgraph_list.pt is mandatory, as in main.py:270 / :361)."""
+                         use_community_detection=False, stand_ins=None) -> ReferenceCache:
+    """Read whatever of the five files exists (subgraph_list.pt is mandatory, as in main.py:270 / :361).
+    stand_ins: None = only when torch_geometric / pygsp are not importable; True / False force it."""
     paths = cache_paths(root, dataset, coarsening_method, coarsening_ratio, extra_node, cluster_node, use_community_detection)
     if not os.path.exists(paths["subgraph_list"]):
         raise FileNotFoundError(f"no reference cache at {paths['subgraph_list']}")
-    out = ReferenceCache(_unpickle(paths["subgraph_list"], lambda p: torch.load(p, weights_only=False, map_location="cpu")),
-                         paths=paths)
+    if stand_ins is None:
+        stand_ins = not _have_reference_packages()
+    kw = {"pickle_module": _StandInPickle} if stand_ins else {}
+    out = ReferenceCache(_unpickle(paths["subgraph_list"],
+                                   lambda p: torch.load(p, weights_only=False, map_location="cpu", **kw)), paths=paths)
     for key in ("candidate", "C_list", "Gc_list", "saved_graph_list"):
         if os.path.exists(paths[key]):
             with open(paths[key], "rb") as f:
-                setattr(out, key, _unpickle(paths[key], lambda p, f=f: pickle.load(f)))
+                setattr(out, key, _unpickle(paths[key], lambda p, f=f: (_StandInPickle if stand_ins else pickle).load(f)))
     return out
 
 
