@@ -102,6 +102,27 @@ def test_batched_costs_equal_the_reference_cost_function():
         assert np.abs(got.numpy() - want).max() <= 1e-12 * np.abs(want).max()
 
 
+def test_family_costs_on_arbitrary_sets_and_weighted_graphs():
+    """the general family kernel on random node subsets (connected or not, sizes 2-9) of a WEIGHTED graph (a level-2 graph:
+    integer edge counts) against the reference's dense per-set formula"""
+    from fitgnn_b200 import coarsen_algo as ca
+    n, r, row, col, Uk, lk = case("n400_d10_r60")
+    rng = np.random.default_rng(0)
+    wts = rng.integers(1, 4, len(row)).astype(np.float64)
+    W = sp.coo_matrix((wts, (row, col)), shape=(n, n)).tocsr()
+    W = ((W + W.T) / 2).tocsr()  # symmetric weights (halves appear: still exact in fp64)
+    A = co.spectral_matrix(Uk, lk, K)
+    deg = np.ravel(W.sum(axis=0))
+    fam = [np.sort(rng.choice(n, size=int(rng.integers(2, 10)), replace=False)) for _ in range(500)]
+    want = np.array([co.subgraph_cost(W.tolil(), deg, A, s) for s in fam])
+    coo = W.tocoo()
+    r_, c_, w_, rp = ca._coalesce(torch.tensor(coo.row).long(), torch.tensor(coo.col).long(), torch.tensor(coo.data), n)
+    sid = np.repeat(np.arange(len(fam)), [len(s) for s in fam])
+    mkey, _ = torch.sort(torch.as_tensor(sid * n + np.concatenate(fam)))
+    got, _ = ca._family_costs(mkey, len(fam), r_, c_, w_, rp, n, torch.tensor(A), chunk=1000)
+    assert np.abs(got.numpy() - want).max() <= 1e-12 * np.abs(want).max()
+
+
 def test_spectral_basis_dense_and_lanczos():
     """smallest-K Laplacian eigenpairs: dense eigh (small graphs) and Lanczos on offset*I - L (the reference's shift) agree with
     scipy; the first eigenvalue is 0 (connected graph) and is dropped by the lk < 1e-10 rule exactly as in the reference"""
