@@ -119,8 +119,20 @@ def _family_costs(mkey, n_sets, row, col, w, rowptr, n, A, chunk=1 << 22):
 
 
 def _cost_host(Wd, deg, A, nodes):
-    """the same cost for ONE (shrunk) set on the host: the contraction loop's re-costs (:640-643)."""
-    Ws = Wd[np.ix_(nodes, nodes)] if isinstance(Wd, np.ndarray) else Wd[nodes][:, nodes].toarray()
+    """the same cost for ONE (shrunk) set on the host: the contraction loop's re-costs (:640-643).  The induced weights are
+    gathered straight from the CSR arrays (scipy's fancy indexing cost 0.4 ms per set: 3/4 of a PubMed-sized run)."""
+    nc = len(nodes)
+    order = np.argsort(nodes, kind="stable")
+    sn = nodes[order]
+    Ws = np.zeros((nc, nc))
+    indptr, indices, data = Wd.indptr, Wd.indices, Wd.data
+    for i in range(nc):
+        a, b = indptr[nodes[i]], indptr[nodes[i] + 1]
+        nb = indices[a:b]
+        k = np.searchsorted(sn, nb)
+        k[k == nc] = 0
+        hit = sn[k] == nb
+        Ws[i, order[k[hit]]] = data[a:b][hit]
     L = np.diag(2 * deg[nodes] - Ws.sum(1)) - Ws
     B = A[nodes] - A[nodes].mean(0, keepdims=True)
     return float(np.linalg.norm(B.T @ L @ B) / (len(nodes) - 1))
